@@ -1,0 +1,85 @@
+"""Batched, GPU-resident Cassie-v0 (host-side mirror of cassie/cassie.py's CassieEnv behind the Vectorize seam).
+
+Interface kept from the reference (file:line in /root/reference):
+  * env duck-type: reset(), step(action, f_term=0), observation_space / action_space (zero ndarrays whose
+    shape is read), mirrored_obs, mirrored_acts, clock_inds, clock_based, simrate (cassie/cassie.py:27-140,
+    389, 523);
+  * vectorised seam: step(actions[N, A]) -> obs[N, D], rews[N], dones[N], infos and num_envs
+    (rl/envs/vectorize.py:6-47).
+All tensors stay on the GPU; the physics, PD loop, reward and observation run in apex_cassie_env_step.
+"""
+import numpy as np
+import torch
+
+from . import lib as _lib
+
+_DT = {torch.float32: 0, torch.float64: 1}
+
+
+class BatchedCassieEnv:
+    def __init__(self, num_envs, device="cuda:0", dtype=torch.float32, seed=0, dynamics_randomization=True, simrate=50,
+                 command_profile="clock", input_profile="full", reward="clock", max_traj_len=400, env_id0=0, history=0, **kwargs):
+        if simrate != 50 or command_profile != "clock" or input_profile != "full" or history != 0:
+            raise NotImplementedError("kernel is specialised for simrate=50, clock command, full input, history=0")
+        if reward not in ("clock",):
+            raise NotImplementedError("only the 'clock' reward (cassie/rewards/clock_rewards.py:6) is implemented")
+        self.L = _lib.lib()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.ApexLibraryError("BatchedCassieEnv needs a CUDA device (no CPU fallback)")
+        self.dtype, self.dt = dtype, _DT[dtype]
+        self.num_envs = int(num_envs)
+        self.simrate, self.max_traj_len = simrate, int(max_traj_len)
+        self.command_profile, self.input_profile, self.reward_func = command_profile, input_profile, reward
+        self.dynamics_randomization = bool(dynamics_randomization)
+        self.clock_based = True
+        # cassie/cassie.py:236-265 (full input profile, clock command)
+        base = [0.1, 1, -2, 3, -4, -10, -11, 12, 13, 14, -5, -6, 7, 8, 9, 15, -16, 17, -18, 19, -20, -26, -27, 28, 29, 30, -21,
+                -22, 23, 24, 25, 31, -32, 33, 37, 38, 39, 34, 35, 36, 43, 44, 45, 40, 41, 42]
+        self.mirrored_obs = base + [46, 47, 48, 49]
+        self.clock_inds = [46, 47]
+        self.mirrored_acts = [-5, -6, 7, 8, 9, -0.1, -1, 2, 3, 4]
+        self.observation_space = np.zeros(50)
+        self.action_space = np.zeros(10)
+        n = self.num_envs
+        self.st = torch.zeros((n, self.L.apex_cassie_state_words()), dtype=dtype, device=self.device)
+        self.sti = torch.zeros((n, self.L.apex_cassie_istate_words()), dtype=torch.int32, device=self.device)
+        self.obs = torch.zeros((n, 50), dtype=dtype, device=self.device)
+        self.term_obs = torch.zeros((n, 50), dtype=dtype, device=self.device)
+        self.rew = torch.zeros((n,), dtype=dtype, device=self.device)
+        self.done = torch.zeros((n,), dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.L.apex_cassie_env_init(self.dt, self.st.data_ptr(), self.sti.data_ptr(), n, int(seed) & 0xFFFFFFFF,
+                                                   int(env_id0), int(self.dynamics_randomization), self._stream()), "env_init")
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def field(self, name, width=1):
+        """View of a named field of the persistent state (tests, command overrides)."""
+        off = _lib.layout(name)
+        ints = name in ("drive_hist", "time", "counter", "has_prev", "has_u", "drive_init", "joint_init", "flags", "stepcount",
+                        "rng_ctr", "env_id", "seed", "dyn_rand", "solver_iter", "ncon", "nefc")
+        return (self.sti if ints else self.st)[:, off:off + width]
+
+    def reset(self):
+        with torch.cuda.device(self.device):
+            _lib.check(self.L.apex_cassie_env_reset(self.dt, self.st.data_ptr(), self.sti.data_ptr(), self.num_envs,
+                                                    self.obs.data_ptr(), self._stream()), "env_reset")
+        return self.obs
+
+    def step(self, action, f_term=0):
+        """action [N, 10] on the device -> (obs [N, 50], reward [N], done [N] int32 (bit0 terminal, bit1 time-out), {})."""
+        a = action.to(device=self.device, dtype=self.dtype).contiguous()
+        assert a.shape == (self.num_envs, 10)
+        with torch.cuda.device(self.device):
+            _lib.check(self.L.apex_cassie_env_step(self.dt, self.st.data_ptr(), self.sti.data_ptr(), self.num_envs, a.data_ptr(),
+                                                   self.obs.data_ptr(), self.rew.data_ptr(), self.done.data_ptr(),
+                                                   self.term_obs.data_ptr(), self.max_traj_len, self._stream()), "env_step")
+        return self.obs, self.rew, self.done, {}
+
+    def set_command(self, speed=None, side_speed=None, phase=None):
+        """Synthetic-input hook: overwrite commanded speed / side speed / phase for all envs."""
+        for name, val in (("speed", speed), ("side_speed", side_speed), ("phase", phase)):
+            if val is not None:
+                self.field(name)[:, 0] = torch.as_tensor(val, dtype=self.dtype, device=self.device)

@@ -1,0 +1,46 @@
+"""ctypes binding of libapex_b200.so (include/apex_cassie.h).  No fallback: a missing library is an error."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libapex_b200.so")
+_lib = None
+
+
+class ApexLibraryError(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise ApexLibraryError(
+                f"{_LIB_PATH} is missing: build it with `python -m apex_b200.build` (nvcc, sm_100a). "
+                "apex_b200 has no CPU or PyTorch fallback for the environment step.")
+        L = C.CDLL(_LIB_PATH)
+        vp, ip, i, u = C.c_void_p, C.c_void_p, C.c_int, C.c_uint
+        L.apex_cassie_state_words.restype = i
+        L.apex_cassie_istate_words.restype = i
+        L.apex_cassie_layout.argtypes = [C.c_char_p]
+        L.apex_cassie_layout.restype = i
+        L.apex_cassie_env_init.argtypes = [i, vp, ip, i, u, i, i, vp]
+        L.apex_cassie_env_reset.argtypes = [i, vp, ip, i, vp, vp]
+        L.apex_cassie_env_step.argtypes = [i, vp, ip, i, vp, vp, vp, ip, vp, i, vp]
+        L.apex_cassie_mj_step.argtypes = [i, vp, ip, i, i, vp]
+        for f in (L.apex_cassie_env_init, L.apex_cassie_env_reset, L.apex_cassie_env_step, L.apex_cassie_mj_step):
+            f.restype = i
+        _lib = L
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        raise ApexLibraryError(f"{what} failed with code {rc}")
+
+
+def layout(name):
+    off = lib().apex_cassie_layout(name.encode())
+    if off < 0:
+        raise KeyError(name)
+    return off

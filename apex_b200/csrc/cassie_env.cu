@@ -1,0 +1,154 @@
+/* CUDA entry points (sm_100a) for the batched Cassie-v0 environment; see include/apex_cassie.h.
+ * One warp per environment, one warp per block; the per-env workspace (CassieWs<T>) is dynamic shared memory. */
+#include <cuda_runtime.h>
+#include <string.h>
+#include "cassie_envstep.h"
+#include "../../include/apex_cassie.h"
+
+template <typename T> __device__ __forceinline__ void ws_load(CassieWs<T> &w, const T *st, const int *sti, int lane) {
+  for (int k = lane; k < S_WORDS; k += 32) w.st[k] = st[k];
+  for (int k = lane; k < I_WORDS; k += 32) w.sti[k] = sti[k];
+  __syncwarp();
+}
+template <typename T> __device__ __forceinline__ void ws_store(const CassieWs<T> &w, T *st, int *sti, int lane) {
+  __syncwarp();
+  for (int k = lane; k < S_WORDS; k += 32) st[k] = w.st[k];
+  for (int k = lane; k < I_WORDS; k += 32) sti[k] = w.sti[k];
+}
+
+template <typename T> __global__ void __launch_bounds__(32) k_env_init(T *st, int *sti, int n, unsigned seed, int env_id0, int dyn) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  CassieWs<T> &w = *reinterpret_cast<CassieWs<T> *>(smem);
+  const int e = blockIdx.x, lane = threadIdx.x;
+  if (e >= n) return;
+  cw_env_init<T>(w, seed, (unsigned)(env_id0 + e), dyn, lane);
+  ws_store(w, st + (size_t)e * S_WORDS, sti + (size_t)e * I_WORDS, lane);
+}
+
+template <typename T> __global__ void __launch_bounds__(32) k_env_reset(T *st, int *sti, int n, T *obs) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  CassieWs<T> &w = *reinterpret_cast<CassieWs<T> *>(smem);
+  const int e = blockIdx.x, lane = threadIdx.x;
+  if (e >= n) return;
+  ws_load(w, st + (size_t)e * S_WORDS, sti + (size_t)e * I_WORDS, lane);
+  cw_env_reset<T>(w, obs + (size_t)e * CW_OBS, lane);
+  ws_store(w, st + (size_t)e * S_WORDS, sti + (size_t)e * I_WORDS, lane);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(32) k_env_step(T *st, int *sti, int n, const T *action, T *obs, T *reward, int *done, T *term_obs,
+                                                 int max_traj_len) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  CassieWs<T> &w = *reinterpret_cast<CassieWs<T> *>(smem);
+  const int e = blockIdx.x, lane = threadIdx.x;
+  if (e >= n) return;
+  ws_load(w, st + (size_t)e * S_WORDS, sti + (size_t)e * I_WORDS, lane);
+  if (lane < CW_ACT) w.action[lane] = action[(size_t)e * CW_ACT + lane];
+  __syncwarp();
+  T rew; int dn;
+  T *o = obs + (size_t)e * CW_OBS;
+  cw_env_step<T>(w, o, &rew, &dn, lane);
+  int flag = dn ? 1 : 0;
+  if (!dn && max_traj_len > 0 && w.sti[I_TIME] >= max_traj_len) flag |= 2;
+  if (lane == 0) { reward[e] = rew; done[e] = flag; }
+  if (flag && max_traj_len > 0) {
+    __syncwarp();
+    if (term_obs) for (int k = lane; k < CW_OBS; k += 32) term_obs[(size_t)e * CW_OBS + k] = o[k];
+    __syncwarp();
+    cw_env_reset<T>(w, o, lane);
+  }
+  ws_store(w, st + (size_t)e * S_WORDS, sti + (size_t)e * I_WORDS, lane);
+}
+
+template <typename T> __global__ void __launch_bounds__(32) k_mj_step(T *st, int *sti, int n, int flags) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  CassieWs<T> &w = *reinterpret_cast<CassieWs<T> *>(smem);
+  const int e = blockIdx.x, lane = threadIdx.x;
+  if (e >= n) return;
+  ws_load(w, st + (size_t)e * S_WORDS, sti + (size_t)e * I_WORDS, lane);
+  cw_mj_step<T>(w, true, flags, lane);
+  if (lane == 0) { w.sti[I_SOLVER_ITER] = w.solver_iter; w.sti[I_NCON] = w.ncon; w.sti[I_NEFC] = w.nefc; }
+  ws_store(w, st + (size_t)e * S_WORDS, sti + (size_t)e * I_WORDS, lane);
+}
+
+template <typename K> static int prep(K kernel, size_t smem) {
+  cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  return err == cudaSuccess ? 0 : -(int)err;
+}
+static int finish() {
+  cudaError_t err = cudaGetLastError();
+  return err == cudaSuccess ? 0 : -(int)err;
+}
+
+extern "C" {
+
+int apex_cassie_state_words(void) { return S_WORDS; }
+int apex_cassie_istate_words(void) { return I_WORDS; }
+
+int apex_cassie_layout(const char *name) {
+  static const struct { const char *n; int off; } tab[] = {
+      {"qpos", S_QPOS}, {"qvel", S_QVEL}, {"qacc_warmstart", S_QACC_WS}, {"ctrl", S_CTRL}, {"sens_actpos", S_SENS_ACTPOS},
+      {"sens_actvel", S_SENS_ACTVEL}, {"sens_jpos", S_SENS_JPOS}, {"sens_quat", S_SENS_QUAT}, {"sens_gyro", S_SENS_GYRO},
+      {"sens_acc", S_SENS_ACC}, {"sens_ppos", S_SENS_PPOS}, {"sens_pvel", S_SENS_PVEL}, {"footpos", S_FOOTPOS}, {"delay", S_DELAY},
+      {"jx", S_JX}, {"jy", S_JY}, {"ompos", S_OMPOS}, {"omvel", S_OMVEL}, {"uptarget", S_UPTARGET}, {"phase", S_PHASE},
+      {"phaselen", S_PHASELEN}, {"speed", S_SPEED}, {"side_speed", S_SIDE}, {"orient_add", S_ORIENT}, {"swing", S_SWING},
+      {"stance", S_STANCE}, {"prev_action", S_PREV_ACTION}, {"prev_torque", S_PREV_TORQUE}, {"menc_noise", S_MENC},
+      {"jenc_noise", S_JENC}, {"last_pelvis_pos", S_LASTPELVIS}, {"dof_damping", S_DAMPING}, {"body_mass", S_MASS},
+      {"friction", S_FRICTION}, {"floor_quat", S_FLOORQ}, {"dof_invweight0", S_DOFINVW}, {"body_invweight0", S_BODYINVW},
+      {"meaninertia", S_MEANINERTIA}, {"footvel", S_FOOTVEL},
+      {"drive_hist", I_DRIVEHIST}, {"time", I_TIME}, {"counter", I_COUNTER}, {"has_prev", I_HASPREV}, {"has_u", I_HASU},
+      {"drive_init", I_DRIVEINIT}, {"joint_init", I_JOINTINIT}, {"flags", I_FLAGS}, {"stepcount", I_STEPCOUNT}, {"rng_ctr", I_RNGCTR},
+      {"env_id", I_ENVID}, {"seed", I_SEED}, {"dyn_rand", I_DYNRAND}, {"solver_iter", I_SOLVER_ITER}, {"ncon", I_NCON}, {"nefc", I_NEFC}};
+  for (size_t i = 0; i < sizeof(tab) / sizeof(tab[0]); i++)
+    if (strcmp(tab[i].n, name) == 0) return tab[i].off;
+  return -1;
+}
+
+#define DISPATCH(CALL_F32, CALL_F64)             \
+  if (n <= 0) return 0;                          \
+  if (!st || !sti) return -1000;                 \
+  cudaStream_t s = (cudaStream_t)stream;         \
+  int rc;                                        \
+  if (dtype == 0) { CALL_F32; }                  \
+  else if (dtype == 1) { CALL_F64; }             \
+  else return -1000;                             \
+  return finish();
+
+int apex_cassie_env_init(int dtype, void *st, int *sti, int n, unsigned seed, int env_id0, int dyn_rand, void *stream) {
+  DISPATCH(
+      if ((rc = prep(k_env_init<float>, sizeof(CassieWs<float>)))) return rc;
+      (k_env_init<float><<<n, 32, sizeof(CassieWs<float>), s>>>((float *)st, sti, n, seed, env_id0, dyn_rand)),
+      if ((rc = prep(k_env_init<double>, sizeof(CassieWs<double>)))) return rc;
+      (k_env_init<double><<<n, 32, sizeof(CassieWs<double>), s>>>((double *)st, sti, n, seed, env_id0, dyn_rand)))
+}
+
+int apex_cassie_env_reset(int dtype, void *st, int *sti, int n, void *obs, void *stream) {
+  if (!obs) return -1000;
+  DISPATCH(
+      if ((rc = prep(k_env_reset<float>, sizeof(CassieWs<float>)))) return rc;
+      (k_env_reset<float><<<n, 32, sizeof(CassieWs<float>), s>>>((float *)st, sti, n, (float *)obs)),
+      if ((rc = prep(k_env_reset<double>, sizeof(CassieWs<double>)))) return rc;
+      (k_env_reset<double><<<n, 32, sizeof(CassieWs<double>), s>>>((double *)st, sti, n, (double *)obs)))
+}
+
+int apex_cassie_env_step(int dtype, void *st, int *sti, int n, const void *action, void *obs, void *reward, int *done,
+                         void *term_obs, int max_traj_len, void *stream) {
+  if (!action || !obs || !reward || !done) return -1000;
+  DISPATCH(
+      if ((rc = prep(k_env_step<float>, sizeof(CassieWs<float>)))) return rc;
+      (k_env_step<float><<<n, 32, sizeof(CassieWs<float>), s>>>((float *)st, sti, n, (const float *)action, (float *)obs,
+                                                                (float *)reward, done, (float *)term_obs, max_traj_len)),
+      if ((rc = prep(k_env_step<double>, sizeof(CassieWs<double>)))) return rc;
+      (k_env_step<double><<<n, 32, sizeof(CassieWs<double>), s>>>((double *)st, sti, n, (const double *)action, (double *)obs,
+                                                                  (double *)reward, done, (double *)term_obs, max_traj_len)))
+}
+
+int apex_cassie_mj_step(int dtype, void *st, int *sti, int n, int flags, void *stream) {
+  DISPATCH(
+      if ((rc = prep(k_mj_step<float>, sizeof(CassieWs<float>)))) return rc;
+      (k_mj_step<float><<<n, 32, sizeof(CassieWs<float>), s>>>((float *)st, sti, n, flags)),
+      if ((rc = prep(k_mj_step<double>, sizeof(CassieWs<double>)))) return rc;
+      (k_mj_step<double><<<n, 32, sizeof(CassieWs<double>), s>>>((double *)st, sti, n, flags)))
+}
+
+} /* extern "C" */

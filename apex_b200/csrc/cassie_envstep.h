@@ -1,0 +1,450 @@
+/* Wrapper layer (cassie_sim_step_pd) and Cassie-v0 env logic on top of cassie_warp.h; same warp-per-env scheme.
+ * Reference: libcassiemujoco.so cassie_sim_step_pd @0x8450 / cassie_sim_step_ethercat @0x7ae0,
+ * cassie/cassie.py:293-351 (step_simulation), :389-496 (step), :523-680 (reset), :787-859 (get_full_state),
+ * cassie/rewards/clock_rewards.py:6-110, cassie/phase_function.py:5-136.
+ */
+#ifndef CASSIE_ENVSTEP_H
+#define CASSIE_ENVSTEP_H
+#include "cassie_warp.h"
+
+#define CW_PI 3.141592653589793
+#define CW_TWO_PI 6.283185307179586
+
+CM_ARRAY int CW_FIR_W[9] = {2727, 534, -2658, -795, 72, 110, 19, -6, -3}; /* libcassiemujoco.so @0x80a3-0x80ef */
+CM_ARRAY double CW_OFFSET[10] = {0.0045, 0.0, 0.4973, -1.1997, -1.5968, 0.0045, 0.0, 0.4973, -1.1997, -1.5968}; /* cassie.py:107 */
+CM_ARRAY double CW_PGAIN[5] = {100, 100, 88, 96, 50};
+CM_ARRAY double CW_DGAIN[5] = {10.0, 10.0, 8.0, 9.6, 5.0}; /* cassie.py:57-58 */
+CM_ARRAY double CW_NEUTRAL_FOOT[4] = {-0.24790886454547323, -0.24679713195445646, -0.6609396704367185, 0.663921021343526};
+CM_ARRAY double CW_CLOCK_Y[4][8] = {{-1, -1, 0, 0, 1, 1, 0, 0}, {1, 1, 0, 0, -1, -1, 0, 0}, {1, 1, 0, 0, -1, -1, 0, 0}, {-1, -1, 0, 0, 1, 1, 0, 0}};
+
+/* ---------- cassie_sim_step_pd ---------- */
+template <typename T> CW_FN void cw_sim_step_pd(CassieWs<T> &w CW_LANE_PARAM) {
+  const int hasu = w.sti[I_HASU], dinit = w.sti[I_DRIVEINIT], jinit = w.sti[I_JOINTINIT];
+  CW_FOR_LANES {
+    if (lane < CM_NU) {
+      const int i = lane;
+      const T gear = (T)CM_act_gear[i];
+      /* pd_input_step on the previous call's cassie_out */
+      const T pg = hasu ? (T)CW_PGAIN[i % 5] : (T)0, dg = hasu ? (T)CW_DGAIN[i % 5] : (T)0;
+      const T ucmd = (T)0 + pg * (w.st[S_UPTARGET + i] - w.st[S_OMPOS + i]) + dg * ((T)0 - w.st[S_OMVEL + i]);
+      /* motor model, @0x7d30-0x7eaa */
+      const T wv = w.st[S_SENS_ACTVEL + i], wmax = (T)CM_act_rpm[i] * (T)CW_TWO_PI / (T)60.0, tmax = (T)CM_act_ctrlmax[i];
+      const T tlim = cw_max(cw_min(2 * tmax * (1 - cw_abs(wv) / wmax), tmax), (T)0);
+      T tau = cw_min(cw_abs(ucmd / gear), tlim);
+      if (ucmd < 0 || (ucmd == 0 && 1 / ucmd < 0)) tau = -tau; /* copysign */
+      T *dl = w.st + S_DELAY + 6 * i;
+      for (int k = 5; k > 0; k--) dl[k] = dl[k - 1];
+      dl[0] = tau;
+      w.st[S_CTRL + i] = dl[5];
+      w.y[Y_MTORQUE + i] = gear * dl[5];
+      /* drive encoder, @0x7fe0-0x8137 */
+      const T N = (T)(1 << CM_drive_bits[i]);
+      const int32_t c = (int32_t)(w.st[S_SENS_ACTPOS + i] / (T)CW_TWO_PI * N);
+      int *hist = w.sti + I_DRIVEHIST + 9 * i;
+      if (!dinit) for (int k = 0; k < 9; k++) hist[k] = c;
+      for (int k = 8; k > 0; k--) hist[k] = hist[k - 1];
+      hist[0] = c;
+      uint32_t acc = 0;
+      for (int k = 0; k < 9; k++) acc += (uint32_t)CW_FIR_W[k] * (uint32_t)hist[k];
+      const T mpos = (T)c * ((T)CW_TWO_PI / N) / gear;
+      const T mvel = (T)(int32_t)acc * ((T)CW_TWO_PI / N / gear) / (T)CW_PI;
+      w.st[S_OMPOS + i] = mpos; w.st[S_OMVEL + i] = mvel;
+      w.y[Y_MPOS + i] = mpos; w.y[Y_MVEL + i] = mvel;
+    } else if (lane < CM_NU + 6) {
+      /* joint encoder + IIR differentiator, @0x81a0-0x82b7, constants .rodata @0x2f2d8-0x2f2f0 */
+      const int s = lane - CM_NU;
+      const T N = (T)(1 << CM_jsens_bits[s]);
+      const int32_t c = (int32_t)(w.st[S_SENS_JPOS + s] / (T)CW_TWO_PI * N);
+      const T x = (T)c * ((T)CW_TWO_PI / N);
+      T *jx = w.st + S_JX + 4 * s, *jy = w.st + S_JY + 2 * s;
+      if (!jinit) { for (int k = 0; k < 4; k++) jx[k] = x; jy[0] = jy[1] = 0; }
+      for (int k = 3; k > 0; k--) jx[k] = jx[k - 1];
+      jx[0] = x;
+      const T yv = (T)12.348 * (jx[0] + jx[1] - jx[2] - jx[3]) + (T)1.7658 * jy[0] - (T)0.79045 * jy[1];
+      jy[1] = jy[0]; jy[0] = yv;
+      w.y[Y_JPOS + s] = x; w.y[Y_JVEL + s] = yv;
+    } else if (lane < CM_NU + 10) {
+      const int k = lane - CM_NU - 6;
+      w.y[Y_QUAT + k] = w.st[S_SENS_QUAT + k];
+    } else if (lane < CM_NU + 13) {
+      const int k = lane - CM_NU - 10;
+      w.y[Y_ROTVEL + k] = w.st[S_SENS_GYRO + k];
+      w.y[Y_PPOS + k] = w.st[S_SENS_PPOS + k];
+      w.y[Y_TVEL + k] = w.st[S_SENS_PVEL + k];
+    } else if (lane == CM_NU + 13) {
+      /* ideal estimator: world-frame linear acceleration with gravity removed */
+      const T qw = w.st[S_SENS_QUAT], x = w.st[S_SENS_QUAT + 1], yq = w.st[S_SENS_QUAT + 2], z = w.st[S_SENS_QUAT + 3];
+      const T a0 = w.st[S_SENS_ACC], a1 = w.st[S_SENS_ACC + 1], a2 = w.st[S_SENS_ACC + 2];
+      w.y[Y_TACC + 0] = (1 - 2 * (yq * yq + z * z)) * a0 + 2 * (x * yq - qw * z) * a1 + 2 * (x * z + qw * yq) * a2;
+      w.y[Y_TACC + 1] = 2 * (x * yq + qw * z) * a0 + (1 - 2 * (x * x + z * z)) * a1 + 2 * (yq * z - qw * x) * a2;
+      w.y[Y_TACC + 2] = 2 * (x * z - qw * yq) * a0 + 2 * (yq * z + qw * x) * a1 + (1 - 2 * (x * x + yq * yq)) * a2 + (T)CM_GRAVITY_Z;
+      w.sti[I_DRIVEINIT] = 1; w.sti[I_JOINTINIT] = 1;
+    }
+  }
+  CW_SYNC();
+  cw_mj_step<T>(w, true, 0 CW_LANE_ARG);
+}
+
+/* ---------- clock functions ---------- */
+template <typename T> CW_FN void cw_clock_knots(T swing, T stance, T *x, T *phaselen) {
+  const T F = 40, rel = (T)0.1;
+  T seg[5] = {0, swing, swing + stance, 2 * swing + stance, 2 * swing + 2 * stance};
+  for (int k = 0; k < 4; k++) {
+    const T a = seg[k] * F, b = seg[k + 1] * F, off = (b - a) * rel;
+    x[2 * k] = a + off; x[2 * k + 1] = b - off;
+  }
+  *phaselen = seg[4] * F;
+}
+template <typename T> CW_FN T cw_clock_eval(const T *x, T P, int which, T phase) {
+  T xa, xb, ya, yb;
+  if (phase < x[0]) { xa = x[7] - P; ya = (T)CW_CLOCK_Y[which][7]; xb = x[0]; yb = (T)CW_CLOCK_Y[which][0]; }
+  else if (phase >= x[7]) { xa = x[7]; ya = (T)CW_CLOCK_Y[which][7]; xb = x[0] + P; yb = (T)CW_CLOCK_Y[which][0]; }
+  else {
+    int k = 0;
+    while (k < 6 && phase >= x[k + 1]) k++;
+    xa = x[k]; xb = x[k + 1]; ya = (T)CW_CLOCK_Y[which][k]; yb = (T)CW_CLOCK_Y[which][k + 1];
+  }
+  const T t = (phase - xa) / (xb - xa);
+  return ya + (yb - ya) * t * t * (3 - 2 * t);
+}
+
+/* ---------- observation (get_full_state), warp-uniform math, lanes store ---------- */
+template <typename T> CW_FN void cw_env_obs(CassieWs<T> &w, T *obs_out CW_LANE_PARAM) {
+  const T oa = w.st[S_ORIENT];
+  T sz, cz;
+  cw_sincos<T>(oa / 2, &sz, &cz);
+  T q[4] = {cz, 0, 0, sz};
+  if (q[0] < 0) { q[0] = -q[0]; q[3] = -q[3]; }
+  const T iq[4] = {q[0], 0, 0, -q[3]};
+  T no[4], tv[3], ta[3];
+  {
+    const T *b = w.y + Y_QUAT;
+    no[0] = iq[0] * b[0] - iq[1] * b[1] - iq[2] * b[2] - iq[3] * b[3];
+    no[1] = iq[0] * b[1] + b[0] * iq[1] + iq[2] * b[3] - iq[3] * b[2];
+    no[2] = iq[0] * b[2] - iq[1] * b[3] + iq[2] * b[0] + iq[3] * b[1];
+    no[3] = iq[0] * b[3] + iq[1] * b[2] - iq[2] * b[1] + iq[3] * b[0];
+    if (no[0] < 0) for (int k = 0; k < 4; k++) no[k] = -no[k];
+  }
+  for (int pass = 0; pass < 2; pass++) { /* rotate_by_quaternion(v, iq) = iq * (0,v) * conj(iq) */
+    const T *v = pass == 0 ? w.y + Y_TVEL : w.y + Y_TACC;
+    T *o = pass == 0 ? tv : ta;
+    const T q2[4] = {0, v[0], v[1], v[2]}, q3[4] = {iq[0], -iq[1], -iq[2], -iq[3]};
+    T t[4], r[4];
+    t[0] = q2[0] * q3[0] - q2[1] * q3[1] - q2[2] * q3[2] - q2[3] * q3[3];
+    t[1] = q2[0] * q3[1] + q3[0] * q2[1] + q2[2] * q3[3] - q2[3] * q3[2];
+    t[2] = q2[0] * q3[2] - q2[1] * q3[3] + q2[2] * q3[0] + q2[3] * q3[1];
+    t[3] = q2[0] * q3[3] + q2[1] * q3[2] - q2[2] * q3[1] + q2[3] * q3[0];
+    r[1] = iq[0] * t[1] + t[0] * iq[1] + iq[2] * t[3] - iq[3] * t[2];
+    r[2] = iq[0] * t[2] - iq[1] * t[3] + iq[2] * t[0] + iq[3] * t[1];
+    r[3] = iq[0] * t[3] + iq[1] * t[2] - iq[2] * t[1] + iq[3] * t[0];
+    o[0] = r[1]; o[1] = r[2]; o[2] = r[3];
+  }
+  T sp, cp;
+  cw_sincos<T>((T)CW_TWO_PI * w.st[S_PHASE] / w.st[S_PHASELEN], &sp, &cp);
+  CW_FOR_LANES {
+    for (int o = lane; o < CW_OBS; o += 32) {
+      T v;
+      if (o == 0) v = w.y[Y_PPOS + 2] - (T)0;
+      else if (o < 5) v = no[o - 1];
+      else if (o < 15) v = w.y[Y_MPOS + o - 5] + w.st[S_MENC + o - 5];
+      else if (o < 18) v = tv[o - 15];
+      else if (o < 21) v = w.y[Y_ROTVEL + o - 18];
+      else if (o < 31) v = w.y[Y_MVEL + o - 21];
+      else if (o < 34) v = ta[o - 31];
+      else if (o < 40) v = w.y[Y_JPOS + o - 34] + w.st[S_JENC + o - 34];
+      else if (o < 46) v = w.y[Y_JVEL + o - 40];
+      else if (o == 46) v = sp;
+      else if (o == 47) v = cp;
+      else if (o == 48) v = w.st[S_SPEED];
+      else v = w.st[S_SIDE];
+      obs_out[o] = v;
+    }
+  }
+  CW_SYNC();
+}
+
+/* ---------- mj_setConst at qpos0: dof_invweight0, body_invweight0 (translational), meaninertia ---------- */
+template <typename T> CW_NOINL void cw_set_const(CassieWs<T> &w CW_LANE_PARAM) {
+  /* borrow vec[V_TMP..] is too small for a 35-long qpos: stage qpos0 in the J scratch row 47 */
+  T *q0 = w.J[CW_NEFC - 1];
+  CW_FOR_LANES { for (int k = lane; k < CM_NQ; k += 32) q0[k] = (T)CM_qpos0[k]; }
+  CW_SYNC();
+  cw_kinematics<T>(w, q0 CW_LANE_ARG);
+  cw_crb<T>(w CW_LANE_ARG);
+  cw_factor<T>(w, (T)0, false CW_LANE_ARG);
+  T tr = 0;
+  for (int i = 0; i < CW_NV; i++) tr += w.Mdiag[i];
+  CW_SYNC();
+  CW_FOR_LANES { if (lane == 0) w.st[S_MEANINERTIA] = tr / (T)CW_NV; }
+  /* (M^-1)_ii = sum_k y_k^2 / D_k with y = L^-T e_i */
+  CW_FOR_LANES { for (int r = 0; r < CW_NV; r++) w.J[r][lane] = (r == lane) ? (T)1 : (T)0; }
+  CW_SYNC();
+  cw_half_solve_rows<T>(w, CW_NV CW_LANE_ARG);
+  CW_FOR_LANES {
+    T s = 0;
+    for (int k = 0; k < CW_NV; k++) s += w.J[lane][k] * w.J[lane][k] * w.Dinv[k];
+    w.red[lane] = s;
+  }
+  CW_SYNC();
+  CW_FOR_LANES {
+    const int j = CM_dof_jnt[lane];
+    T v = w.red[lane];
+    if (CM_jnt_type[j] == 2) { const int da = CM_jnt_dofadr[j]; v = (w.red[da] + w.red[da + 1] + w.red[da + 2]) / (T)3; }
+    w.st[S_DOFINVW + lane] = v;
+    if (lane == 0) w.st[S_BODYINVW] = 0;
+  }
+  CW_SYNC();
+  const T org[3] = {w.xpos[1][0], w.xpos[1][1], w.xpos[1][2]};
+  for (int b0 = 1; b0 < CW_NB; b0 += 16) {
+    const int nb = (CW_NB - b0) < 16 ? (CW_NB - b0) : 16;
+    for (int bb = 0; bb < nb; bb++) {
+      const int b = b0 + bb;
+      T ip[3] = {(T)CM_body_ipos[b][0], (T)CM_body_ipos[b][1], (T)CM_body_ipos[b][2]}, off[3];
+      cw_mulv(off, w.xmat[b], ip);
+      for (int k = 0; k < 3; k++) off[k] += w.xpos[b][k] - org[k];
+      CW_FOR_LANES {
+        T col[3];
+        cw_jac_col(w, b, off, lane, col);
+        for (int k = 0; k < 3; k++) w.J[3 * bb + k][lane] = col[k];
+      }
+    }
+    CW_SYNC();
+    cw_half_solve_rows<T>(w, 3 * nb CW_LANE_ARG);
+    CW_FOR_LANES {
+      if (lane < nb) {
+        T s = 0;
+        for (int r = 0; r < 3; r++)
+          for (int k = 0; k < CW_NV; k++) s += w.J[3 * lane + r][k] * w.J[3 * lane + r][k] * w.Dinv[k];
+        w.st[S_BODYINVW + b0 + lane] = cw_max((T)1e-15, s / (T)3);
+      }
+    }
+    CW_SYNC();
+  }
+}
+
+/* ---------- state defaults (cassie_sim_init + CassieEnv.__init__) ---------- */
+template <typename T> CW_NOINL void cw_env_init(CassieWs<T> &w, uint32_t seed, uint32_t env_id, int dyn_rand CW_LANE_PARAM) {
+  CW_FOR_LANES {
+    for (int k = lane; k < S_WORDS; k += 32) w.st[k] = 0;
+    for (int k = lane; k < I_WORDS; k += 32) w.sti[k] = 0;
+  }
+  CW_SYNC();
+  CW_FOR_LANES {
+    w.st[S_DAMPING + lane] = (T)CM_dof_damping[lane];
+    if (lane < CW_NB) w.st[S_MASS + lane] = (T)CM_body_mass[lane];
+    for (int k = lane; k < CM_NQ; k += 32) w.st[S_QPOS + k] = (T)CM_qpos_init[k];
+    if (lane == 0) {
+      w.st[S_FRICTION] = 1; w.st[S_FLOORQ] = 1;
+      w.st[S_PHASELEN] = 32;
+      w.sti[I_SEED] = (int)seed; w.sti[I_ENVID] = (int)env_id; w.sti[I_DYNRAND] = dyn_rand;
+    }
+  }
+  CW_SYNC();
+  cw_set_const<T>(w CW_LANE_ARG);
+  cw_mj_step<T>(w, false, 0 CW_LANE_ARG);
+  T fp[6];
+  cw_foot_positions<T>(w, fp);
+  CW_SYNC();
+  CW_FOR_LANES { if (lane < 6) w.st[S_FOOTPOS + lane] = fp[lane]; }
+  CW_SYNC();
+}
+
+/* draw k of the current reset's Philox stream */
+CW_FN uint32_t cw_draw(uint32_t seed, uint32_t env, uint32_t ctr0, int k) {
+  uint32_t o[4];
+  cw_philox(seed, env, ctr0 + (uint32_t)(k >> 2), o);
+  return o[k & 3];
+}
+template <typename T> CW_FN T cw_uniform(uint32_t u, double lo, double hi) { return (T)lo + ((T)hi - (T)lo) * cw_u01<T>(u); }
+
+template <typename T> CW_FN void cw_set_clock(CassieWs<T> &w, T speed CW_LANE_PARAM) { /* cassie.py:556-559 */
+  const T as = cw_abs(speed);
+  const T total = ((T)0.9 - (T)0.25 / (T)3.0 * as) / 2;
+  const T swing = ((T)0.30 + (((T)0.70 - (T)0.30) / 3) * as) * total;
+  const T stance = ((T)0.70 - (((T)0.70 - (T)0.30) / 3) * as) * total;
+  T x[8], P;
+  cw_clock_knots<T>(swing, stance, x, &P);
+  CW_FOR_LANES { if (lane == 0) { w.st[S_SWING] = swing; w.st[S_STANCE] = stance; w.st[S_PHASELEN] = P; } }
+  CW_SYNC();
+}
+
+/* ---------- CassieEnv.reset ---------- */
+template <typename T> CW_NOINL void cw_env_reset(CassieWs<T> &w, T *obs_out CW_LANE_PARAM) {
+  const uint32_t seed = (uint32_t)w.sti[I_SEED], env = (uint32_t)w.sti[I_ENVID], ctr0 = (uint32_t)w.sti[I_RNGCTR];
+  const int dyn = w.sti[I_DYNRAND];
+  const T speed0 = cw_uniform<T>(cw_draw(seed, env, ctr0, 0), -0.3, 4.0);
+  cw_set_clock<T>(w, speed0 CW_LANE_ARG);
+  const T plen = w.st[S_PHASELEN];
+  const uint32_t nph = (uint32_t)floor((double)plen) + 1u;
+  const T phase = (T)(uint32_t)(((uint64_t)cw_draw(seed, env, ctr0, 2) * nph) >> 32);
+  int nd = 3;
+  if (dyn) {
+    CW_FOR_LANES {
+      { /* damping: pelvis, heel spring, plantar rod keep defaults (cassie.py:548-574) */
+        const int i = lane;
+        const int fixed = i < 6 || i == 15 || i == 17 || i == 28 || i == 30;
+        const double lo = fixed ? 1.0 : 0.3, hi = fixed ? 1.0 : 5.0;
+        const T d0 = (T)CM_dof_damping[i];
+        T v = d0 * (T)lo + (d0 * (T)hi - d0 * (T)lo) * cw_u01<T>(cw_draw(seed, env, ctr0, 3 + i));
+        w.st[S_DAMPING + i] = v < 0 ? (T)0 : v;
+      }
+      if (lane >= 1 && lane < CW_NB) {
+        const T m0 = (T)CM_body_mass[lane];
+        T v = (T)0.5 * m0 + ((T)1.5 * m0 - (T)0.5 * m0) * cw_u01<T>(cw_draw(seed, env, ctr0, 35 + lane - 1));
+        w.st[S_MASS + lane] = v < 0 ? (T)0 : v;
+      }
+      if (lane == 26) w.st[S_FRICTION] = cw_uniform<T>(cw_draw(seed, env, ctr0, 60), 0.4, 1.1);
+      if (lane == 27) {
+        const T roll = cw_uniform<T>(cw_draw(seed, env, ctr0, 63), -0.03, 0.03), pitch = cw_uniform<T>(cw_draw(seed, env, ctr0, 64), -0.03, 0.03);
+        T sy, cy, sx, cx;
+        cw_sincos<T>(pitch / 2, &sy, &cy);
+        cw_sincos<T>(roll / 2, &sx, &cx);
+        T q[4] = {cx * cy, cy * sx, cx * sy, sx * sy};
+        if (q[0] < 0) for (int k = 0; k < 4; k++) q[k] = -q[k];
+        for (int k = 0; k < 4; k++) w.st[S_FLOORQ + k] = q[k];
+      }
+      if (lane < 10) w.st[S_MENC + lane] = cw_uniform<T>(cw_draw(seed, env, ctr0, 65 + lane), -0.01, 0.01);
+      else if (lane < 16) w.st[S_JENC + lane - 10] = cw_uniform<T>(cw_draw(seed, env, ctr0, 75 + lane - 10), -0.01, 0.01);
+    }
+    CW_SYNC();
+    nd = 81;
+    cw_set_const<T>(w CW_LANE_ARG);
+  }
+  /* cassie_sim_set_const @0x7330: fixed pose, zero velocity, mj_forward */
+  CW_FOR_LANES {
+    for (int k = lane; k < CM_NQ; k += 32) w.st[S_QPOS + k] = (T)CM_qpos_init[k];
+    w.st[S_QVEL + lane] = 0;
+    if (lane == 0) { w.st[S_PHASE] = phase; w.sti[I_TIME] = 0; w.sti[I_COUNTER] = 0; }
+  }
+  CW_SYNC();
+  cw_mj_step<T>(w, false, 0 CW_LANE_ARG);
+  CW_FOR_LANES { if (lane < 3) w.st[S_LASTPELVIS + lane] = w.st[S_QPOS + lane]; }
+  /* one sub-step with the previous episode's pd_in_t (cassie.py:664-665) */
+  cw_sim_step_pd<T>(w CW_LANE_ARG);
+  T fp[6];
+  cw_foot_positions<T>(w, fp);
+  const T speed1 = cw_uniform<T>(cw_draw(seed, env, ctr0, nd), -0.3, 4.0);
+  const T side1 = cw_uniform<T>(cw_draw(seed, env, ctr0, nd + 1), -0.3, 0.3);
+  CW_SYNC();
+  CW_FOR_LANES {
+    if (lane < 6) w.st[S_FOOTPOS + lane] = fp[lane];
+    if (lane == 0) {
+      w.st[S_ORIENT] = 0; w.st[S_SPEED] = speed1; w.st[S_SIDE] = side1;
+      w.sti[I_RNGCTR] = (int)(ctr0 + (uint32_t)((nd + 2 + 3) >> 2));
+    }
+  }
+  CW_SYNC();
+  cw_env_obs<T>(w, obs_out CW_LANE_ARG);
+}
+
+/* ---------- CassieEnv.step ---------- */
+template <typename T> CW_NOINL void cw_env_step(CassieWs<T> &w, T *obs_out, T *reward_out, int *done_out CW_LANE_PARAM) {
+  CW_FOR_LANES {
+    if (lane < CW_ACT) w.st[S_UPTARGET + lane] = w.action[lane] + (T)CW_OFFSET[lane] - w.st[S_MENC + lane];
+    if (lane == 0) w.sti[I_HASU] = 1;
+  }
+  CW_SYNC();
+  T lfrc = 0, rfrc = 0, lori = 0, rori = 0, lfv[3] = {0, 0, 0}, rfv[3] = {0, 0, 0};
+  for (int s = 0; s < CW_SIMRATE; s++) {
+    T fp0[6], fp1[6], lz, rz;
+    for (int k = 0; k < 6; k++) fp0[k] = w.st[S_FOOTPOS + k];
+    cw_sim_step_pd<T>(w CW_LANE_ARG);
+    cw_foot_positions<T>(w, fp1);
+    for (int k = 0; k < 3; k++) { lfv[k] = (fp1[k] - fp0[k]) / (T)0.0005; rfv[k] = (fp1[3 + k] - fp0[3 + k]) / (T)0.0005; }
+    cw_foot_forces<T>(w, &lz, &rz);
+    int fl = w.sti[I_FLAGS], sc = w.sti[I_STEPCOUNT];
+    { /* the reference tests the LEFT force for both feet (cassie.py:338,348) */
+      int lh = fl & 1, rh = (fl >> 1) & 1, ls = (fl >> 2) & 1, rs = (fl >> 3) & 1;
+      if (lh && lz > 0) { lh = 0; sc++; } else if (!lh && fp1[2] >= (T)0.2) lh = 1;
+      if (rh && lz > 0) { sc++; rh = 0; } else if (!rh && fp1[5] >= (T)0.2) rh = 1;
+      if (ls && lz > 0) ls = 0; else if (!ls && fp1[2] >= 0) ls = 1;
+      if (rs && lz > 0) rs = 0; else if (!rs && fp1[5] >= 0) rs = 1;
+      fl = lh | (rh << 1) | (ls << 2) | (rs << 3);
+    }
+    lfrc += lz; rfrc += rz;
+    T dl = 0, dr = 0;
+    for (int k = 0; k < 4; k++) { dl += (T)CW_NEUTRAL_FOOT[k] * w.xquat[CW_LFOOT][k]; dr += (T)CW_NEUTRAL_FOOT[k] * w.xquat[CW_RFOOT][k]; }
+    lori += 1 - dl * dl; rori += 1 - dr * dr;
+    CW_SYNC();
+    CW_FOR_LANES {
+      if (lane < 6) w.st[S_FOOTPOS + lane] = fp1[lane];
+      if (lane == 0) { w.sti[I_FLAGS] = fl; w.sti[I_STEPCOUNT] = sc; }
+    }
+    CW_SYNC();
+  }
+  lfrc /= (T)CW_SIMRATE; rfrc /= (T)CW_SIMRATE; lori /= (T)CW_SIMRATE; rori /= (T)CW_SIMRATE;
+  const T *qpos = w.st + S_QPOS, *qvel = w.st + S_QVEL;
+  const T height = qpos[2];
+  const int time = w.sti[I_TIME] + 1;
+  int counter = w.sti[I_COUNTER];
+  T phase = w.st[S_PHASE] + (T)1;
+  const T plen = w.st[S_PHASELEN];
+  int wrapped = 0;
+  if (phase > plen) { phase = 0; counter++; wrapped = 1; }
+  int done = (height < (T)0.4 || height > (T)3.0) ? 1 : 0;
+  const int hasprev = w.sti[I_HASPREV];
+  /* clock_reward */
+  T reward;
+  {
+    const T speed = w.st[S_SPEED];
+    const T nlf = cw_min(lfrc, (T)250) / (T)250, nrf = cw_min(rfrc, (T)250) / (T)250;
+    const T nlv = cw_min(cw_sqrt<T>(cw_dot3(lfv, lfv)), (T)2.0) / (T)2.0, nrv = cw_min(cw_sqrt<T>(cw_dot3(rfv, rfv)), (T)2.0) / (T)2.0;
+    const T com_orient_error = 10 * (1 - qpos[3] * qpos[3]);
+    const T foot_orient_error = 10 * (lori + rori);
+    const T com_vel_error = cw_abs(qvel[0] - speed);
+    T straight_diff = cw_abs(qpos[1]);
+    if (straight_diff < (T)0.05) straight_diff = 0;
+    T height_diff = cw_abs(qpos[2] - (T)0.9);
+    const T deadzone = (T)0.05 + (T)0.05 * speed;
+    if (height_diff < deadzone) height_diff = 0;
+    T pelvis_acc = 0;
+    for (int k = 0; k < 3; k++) pelvis_acc += cw_abs(w.y[Y_ROTVEL + k]) + cw_abs(w.y[Y_TACC + k]);
+    pelvis_acc *= (T)0.25;
+    const T pelvis_motion = straight_diff + height_diff + pelvis_acc;
+    T x[8], P;
+    cw_clock_knots<T>(w.st[S_SWING], w.st[S_STANCE], x, &P);
+    const T lfc = cw_clock_eval<T>(x, P, 0, phase), lvc = cw_clock_eval<T>(x, P, 1, phase);
+    const T rfc = cw_clock_eval<T>(x, P, 2, phase), rvc = cw_clock_eval<T>(x, P, 3, phase);
+    const T q4 = (T)(CW_PI / 4);
+    const T foot_frc_score = cw_tan<T>(q4 * lfc * nlf) + cw_tan<T>(q4 * rfc * nrf);
+    const T foot_vel_score = cw_tan<T>(q4 * lvc * nlv) + cw_tan<T>(q4 * rvc * nrv);
+    const T hip_roll_penalty = cw_abs(qvel[6]) + cw_abs(qvel[13]);
+    T torque_penalty = 0, action_penalty = 0;
+    for (int k = 0; k < 10; k++) {
+      const T pt = hasprev ? w.st[S_PREV_TORQUE + k] : w.y[Y_MTORQUE + k];
+      const T pa = hasprev ? w.st[S_PREV_ACTION + k] : w.action[k];
+      torque_penalty += cw_abs(pt - w.y[Y_MTORQUE + k]);
+      action_penalty += cw_abs(pa - w.action[k]);
+    }
+    torque_penalty = (T)0.25 * (torque_penalty / 10);
+    action_penalty = 5 * action_penalty / 10;
+    reward = (T)0.200 * foot_frc_score + (T)0.200 * foot_vel_score + (T)0.200 * cw_exp<T>(-(com_orient_error + foot_orient_error)) +
+             (T)0.150 * cw_exp<T>(-pelvis_motion) + (T)0.150 * cw_exp<T>(-com_vel_error) + (T)0.050 * cw_exp<T>(-hip_roll_penalty) +
+             (T)0.025 * cw_exp<T>(-torque_penalty) + (T)0.025 * cw_exp<T>(-action_penalty);
+  }
+  if (reward < (T)-99.0) done = 1;
+  /* random command changes (cassie.py:483-491) */
+  uint32_t tr[4], va[4];
+  const uint32_t seed = (uint32_t)w.sti[I_SEED], env = (uint32_t)w.sti[I_ENVID], ctr = (uint32_t)w.sti[I_RNGCTR];
+  cw_philox(seed, env, ctr, tr);
+  cw_philox(seed, env, ctr + 1, va);
+  T orient = w.st[S_ORIENT], speed = w.st[S_SPEED], side = w.st[S_SIDE];
+  if ((uint32_t)(((uint64_t)tr[0] * 300) >> 32) == 0) orient += (T)-0.2 + (T)0.4 * cw_u01<T>(va[0]);
+  if ((uint32_t)(((uint64_t)tr[1] * 100) >> 32) == 0) speed = cw_min(cw_max((T)-0.3 + (T)4.3 * cw_u01<T>(va[1]), (T)-0.3), (T)4.0);
+  if ((uint32_t)(((uint64_t)tr[2] * 300) >> 32) == 0) side = (T)-0.3 + (T)0.6 * cw_u01<T>(va[2]);
+  CW_SYNC();
+  CW_FOR_LANES {
+    if (lane < 10) { w.st[S_PREV_ACTION + lane] = w.action[lane]; w.st[S_PREV_TORQUE + lane] = w.y[Y_MTORQUE + lane]; }
+    if (lane < 3) { w.st[S_FOOTVEL + lane] = lfv[lane]; w.st[S_FOOTVEL + 3 + lane] = rfv[lane]; if (wrapped) w.st[S_LASTPELVIS + lane] = qpos[lane]; }
+    if (lane == 0) {
+      w.sti[I_TIME] = time; w.sti[I_COUNTER] = counter; w.sti[I_HASPREV] = 1; w.sti[I_RNGCTR] = (int)(ctr + 2);
+      w.st[S_PHASE] = phase; w.st[S_ORIENT] = orient; w.st[S_SPEED] = speed; w.st[S_SIDE] = side;
+      w.sti[I_SOLVER_ITER] = w.solver_iter; w.sti[I_NCON] = w.ncon; w.sti[I_NEFC] = w.nefc;
+    }
+  }
+  CW_SYNC();
+  *reward_out = reward;
+  *done_out = done;
+  cw_env_obs<T>(w, obs_out CW_LANE_ARG);
+}
+#endif

@@ -1,0 +1,945 @@
+/* Warp-per-environment Cassie simulation: one 32-lane warp advances one environment.
+ *
+ * nv = 32 = warp size, so lane <-> dof (mass matrix rows, Jacobian columns, PGS residual slots) and
+ * lane <-> body (26 bodies; kinematics / RNE run level by level down the tree), lane <-> constraint row
+ * (two passes for up to 48 rows).  All per-env data lives in a shared-memory workspace (CassieWs<T>);
+ * phases are separated by CW_SYNC().  Code outside a CW_FOR_LANES block is "warp-uniform": every lane
+ * computes the same scalars from shared memory.
+ *
+ * The same source builds two ways:
+ *   - nvcc (sm_100a): CW_FOR_LANES is empty (`lane` = threadIdx.x & 31), CW_SYNC() = __syncwarp();
+ *   - host C++ (tests/ only): CW_FOR_LANES is a 32-iteration loop, used to check the kernel logic against
+ *     the oracle on machines without a GPU.  This is a test build of the product source, not a fallback:
+ *     the shipped library exposes only the CUDA entry points (apex_b200/csrc/cassie_env.cu).
+ *
+ * What is computed (reference file:line for each stage):
+ *   cassie_sim_step_pd (libcassiemujoco.so @0x8450): PD law, motor model + delay (@0x7d30-0x7eaa),
+ *   encoders (@0x7fe0-0x82b7), IMU copy, mj_step1 / mj_step2 on cassie/cassiemujoco/cassie.xml
+ *   (kinematics, CRBA, sparse L^T D L, plane/capsule collision, connect + limit + pyramidal contact rows,
+ *   warm-started dual PGS (cassie.xml:5), Euler implicit in joint damping), ideal state estimator;
+ *   CassieEnv.step / step_simulation / reset / get_full_state (cassie/cassie.py:389-496, :293-351, :523-680,
+ *   :787-859), clock_reward (cassie/rewards/clock_rewards.py:6-110), create_phase_reward
+ *   (cassie/phase_function.py:5-136).
+ */
+#ifndef CASSIE_WARP_H
+#define CASSIE_WARP_H
+#include <stdint.h>
+#include <math.h>
+
+#ifdef __CUDACC__
+#define CW_FN __device__ __forceinline__
+#define CW_NOINL __device__ __noinline__
+#define CW_FOR_LANES
+#define CW_SYNC() __syncwarp()
+#define CM_ARRAY static __device__ const
+#else
+#define CW_FN static inline
+#define CW_NOINL static
+#define CW_FOR_LANES for (int lane = 0; lane < 32; ++lane)
+#define CW_SYNC() ((void)0)
+#define CM_ARRAY static const
+#endif
+#include "cassie_model.h"
+
+#ifdef __CUDACC__
+#define CW_LANE_PARAM , const int lane
+#define CW_LANE_ARG , lane
+#else
+#define CW_LANE_PARAM
+#define CW_LANE_ARG
+#endif
+
+#define CW_NB CM_NBODY
+#define CW_NV CM_NV
+#define CW_NEFC 48
+#define CW_NCON 8
+#define CW_OBS 50
+#define CW_ACT 10
+#define CW_SIMRATE 50
+#define CW_LFOOT 13
+#define CW_RFOOT 25
+#define CW_FOOT_Z_OFFSET 0.0550841 /* libcassiemujoco.so .rodata @0x2f2b8 */
+
+/* persistent per-env record: real words */
+enum {
+  S_QPOS = 0, S_QVEL = 35, S_QACC_WS = 67, S_CTRL = 99,
+  S_SENS_ACTPOS = 109, S_SENS_ACTVEL = 119, S_SENS_JPOS = 129, S_SENS_QUAT = 135, S_SENS_GYRO = 139, S_SENS_ACC = 142,
+  S_SENS_PPOS = 145, S_SENS_PVEL = 148, S_FOOTPOS = 151,
+  S_DELAY = 157, S_JX = 217, S_JY = 241, S_OMPOS = 253, S_OMVEL = 263, S_UPTARGET = 273,
+  S_PHASE = 283, S_PHASELEN = 284, S_SPEED = 285, S_SIDE = 286, S_ORIENT = 287, S_SWING = 288, S_STANCE = 289,
+  S_PREV_ACTION = 290, S_PREV_TORQUE = 300, S_MENC = 310, S_JENC = 320, S_LASTPELVIS = 326,
+  S_DAMPING = 329, S_MASS = 361, S_FRICTION = 387, S_FLOORQ = 388, S_DOFINVW = 392, S_BODYINVW = 424, S_MEANINERTIA = 450,
+  S_FOOTVEL = 451, /* l_foot_vel(3), r_foot_vel(3) of the last sub-step */
+  S_WORDS = 480
+};
+/* persistent per-env record: int words */
+enum {
+  I_DRIVEHIST = 0, I_TIME = 90, I_COUNTER = 91, I_HASPREV = 92, I_HASU = 93, I_DRIVEINIT = 94, I_JOINTINIT = 95,
+  I_FLAGS = 96, I_STEPCOUNT = 97, I_RNGCTR = 98, I_ENVID = 99, I_SEED = 100, I_DYNRAND = 101, I_SOLVER_ITER = 102,
+  I_NCON = 103, I_NEFC = 104, I_WORDS = 128
+};
+/* state_out slice (workspace only) */
+enum { Y_PPOS = 0, Y_QUAT = 3, Y_ROTVEL = 7, Y_TVEL = 10, Y_TACC = 13, Y_MPOS = 16, Y_MVEL = 26, Y_MTORQUE = 36, Y_JPOS = 46, Y_JVEL = 52, Y_WORDS = 58 };
+/* dof-vector slots in ws.vec */
+enum { V_SMOOTH = 0, V_QACCS = 1, V_Z = 2, V_G = 3, V_QACC = 4, V_TMP = 5, V_BIAS = 6, V_NVEC = 7 };
+
+template <typename T>
+struct CassieWs {
+  T st[S_WORDS];
+  int sti[I_WORDS];
+  T xpos[CW_NB][3], xquat[CW_NB][4], xmat[CW_NB][9];
+  T cdof[CW_NV][6], cinert[CW_NB][10], crb[CW_NB][10];
+  T M[CW_NV][CW_NV + 1]; /* [j][i] j<i: mass matrix; [i][j] i>j: unit-lower factor L of M = L^T D L */
+  T Mdiag[CW_NV], D[CW_NV], Dinv[CW_NV];
+  T J[CW_NEFC][CW_NV + 1]; /* constraint Jacobian, later B = J L^-1 */
+  T A[CW_NEFC][CW_NEFC + 1];
+  T cvel[CW_NB][6], cdd[CW_NV][6], cacc[CW_NB][6];
+  T efc_pos[CW_NEFC], efc_diag[CW_NEFC], efc_R[CW_NEFC], efc_jv[CW_NEFC], efc_K[CW_NEFC], efc_B[CW_NEFC], efc_imp[CW_NEFC];
+  T efc_aref[CW_NEFC], efc_b[CW_NEFC], efc_f[CW_NEFC], efc_res[CW_NEFC], efc_dinv[CW_NEFC];
+  int efc_type[CW_NEFC];
+  T vec[V_NVEC][CW_NV];
+  T red[32];
+  int ncon, nefc, solver_iter;
+  T cand_dist[32], cand_pos[32][3], cand_n[32][3], cand_hint[32][3];
+  T con_pos[CW_NCON][3], con_frame[CW_NCON][9], con_dist[CW_NCON], con_mu[CW_NCON];
+  int con_geom[CW_NCON], con_geom1[CW_NCON], con_dim[CW_NCON], con_adr[CW_NCON];
+  T y[Y_WORDS];
+  T ucmd[CM_NU];
+  T action[CW_ACT];
+  T footf[12];
+};
+
+/* ---------- scalar helpers ---------- */
+CW_FN float cw_sqrt_o(float x) { return sqrtf(x); }
+CW_FN double cw_sqrt_o(double x) { return sqrt(x); }
+CW_FN void cw_sincos_o(float x, float *s, float *c) { *s = sinf(x); *c = cosf(x); }
+CW_FN void cw_sincos_o(double x, double *s, double *c) { *s = sin(x); *c = cos(x); }
+CW_FN float cw_exp_o(float x) { return expf(x); }
+CW_FN double cw_exp_o(double x) { return exp(x); }
+CW_FN float cw_tan_o(float x) { return tanf(x); }
+CW_FN double cw_tan_o(double x) { return tan(x); }
+template <typename T> CW_FN T cw_sqrt(T x) { return cw_sqrt_o(x); }
+template <typename T> CW_FN void cw_sincos(T x, T *s, T *c) { cw_sincos_o(x, s, c); }
+template <typename T> CW_FN T cw_exp(T x) { return cw_exp_o(x); }
+template <typename T> CW_FN T cw_tan(T x) { return cw_tan_o(x); }
+template <typename T> CW_FN T cw_abs(T x) { return x < 0 ? -x : x; }
+template <typename T> CW_FN T cw_min(T a, T b) { return a < b ? a : b; }
+template <typename T> CW_FN T cw_max(T a, T b) { return a > b ? a : b; }
+
+template <typename T> CW_FN void cw_cross(T *r, const T *a, const T *b) {
+  T x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
+  r[0] = x; r[1] = y; r[2] = z;
+}
+template <typename T> CW_FN T cw_dot3(const T *a, const T *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+template <typename T> CW_FN void cw_qmul(T *r, const T *a, const T *b) {
+  T w = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3];
+  T x = a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2];
+  T y = a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1];
+  T z = a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0];
+  r[0] = w; r[1] = x; r[2] = y; r[3] = z;
+}
+template <typename T> CW_FN void cw_qnorm(T *q) {
+  T n = cw_sqrt<T>(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  if (n < (T)1e-15) { q[0] = 1; q[1] = q[2] = q[3] = 0; return; }
+  T inv = (T)1 / n;
+  q[0] *= inv; q[1] *= inv; q[2] *= inv; q[3] *= inv;
+}
+template <typename T> CW_FN void cw_qmat(T *R, const T *q) {
+  T w = q[0], x = q[1], y = q[2], z = q[3];
+  R[0] = 1 - 2 * (y * y + z * z); R[1] = 2 * (x * y - w * z); R[2] = 2 * (x * z + w * y);
+  R[3] = 2 * (x * y + w * z); R[4] = 1 - 2 * (x * x + z * z); R[5] = 2 * (y * z - w * x);
+  R[6] = 2 * (x * z - w * y); R[7] = 2 * (y * z + w * x); R[8] = 1 - 2 * (x * x + y * y);
+}
+template <typename T> CW_FN void cw_mulv(T *r, const T *R, const T *v) {
+  T x = R[0] * v[0] + R[1] * v[1] + R[2] * v[2], y = R[3] * v[0] + R[4] * v[1] + R[5] * v[2], z = R[6] * v[0] + R[7] * v[1] + R[8] * v[2];
+  r[0] = x; r[1] = y; r[2] = z;
+}
+template <typename T> CW_FN void cw_tmulv(T *r, const T *R, const T *v) {
+  T x = R[0] * v[0] + R[3] * v[1] + R[6] * v[2], y = R[1] * v[0] + R[4] * v[1] + R[7] * v[2], z = R[2] * v[0] + R[5] * v[1] + R[8] * v[2];
+  r[0] = x; r[1] = y; r[2] = z;
+}
+/* spatial inertia (m, m c, I about org) times motion vector (w, v) -> (angular momentum, linear momentum) */
+template <typename T> CW_FN void cw_inert_mul(T *f, const T *I, const T *v) {
+  const T *mc = I + 1, *w = v, *l = v + 3;
+  T t[3];
+  f[0] = I[4] * w[0] + I[7] * w[1] + I[8] * w[2];
+  f[1] = I[7] * w[0] + I[5] * w[1] + I[9] * w[2];
+  f[2] = I[8] * w[0] + I[9] * w[1] + I[6] * w[2];
+  cw_cross(t, mc, l);
+  f[0] += t[0]; f[1] += t[1]; f[2] += t[2];
+  cw_cross(t, w, mc);
+  f[3] = I[0] * l[0] + t[0]; f[4] = I[0] * l[1] + t[1]; f[5] = I[0] * l[2] + t[2];
+}
+template <typename T> CW_FN T cw_dot6(const T *a, const T *b) { return cw_dot3(a, b) + cw_dot3(a + 3, b + 3); }
+
+CW_FN void cw_philox(uint32_t seed, uint32_t env_id, uint32_t ctr, uint32_t *out) {
+  uint32_t c0 = ctr, c1 = 0, c2 = env_id, c3 = 0x9e3779b9u, k0 = seed, k1 = 0xbb67ae85u;
+  for (int r = 0; r < 10; r++) {
+    uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+    uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+template <typename T> CW_FN T cw_u01(uint32_t x) { return (T)(x >> 8) * (T)(1.0 / 16777216.0); }
+
+/* =====================================================================================================
+ * position stage: kinematics, cdof, cinert (mj_kinematics + mj_comPos), lane = body, one tree level per phase
+ * ===================================================================================================== */
+template <typename T> CW_FN void cw_kinematics(CassieWs<T> &w, const T *qpos CW_LANE_PARAM) {
+  CW_FOR_LANES {
+    if (lane == 0) {
+      for (int k = 0; k < 3; k++) w.xpos[0][k] = 0;
+      w.xquat[0][0] = 1; w.xquat[0][1] = w.xquat[0][2] = w.xquat[0][3] = 0;
+      for (int k = 0; k < 9; k++) w.xmat[0][k] = (k % 4 == 0) ? (T)1 : (T)0;
+      for (int k = 0; k < 10; k++) w.cinert[0][k] = 0;
+    } else if (lane == 1) { /* pelvis: three world slides (z has ref 1.01 = body z) + ball */
+      T q[4] = {qpos[3], qpos[4], qpos[5], qpos[6]};
+      cw_qnorm(q);
+      for (int k = 0; k < 3; k++) w.xpos[1][k] = qpos[k];
+      for (int k = 0; k < 4; k++) w.xquat[1][k] = q[k];
+      cw_qmat(w.xmat[1], q);
+    }
+  }
+  CW_SYNC();
+  for (int lvl = 2; lvl <= CM_MAXLEVEL; lvl++) {
+    CW_FOR_LANES {
+      if (lane < CW_NB && CM_body_level[lane] == lvl) {
+        const int b = lane, p = CM_body_parent[b], j = CM_body_jnt[b];
+        T bp[3] = {(T)CM_body_pos[b][0], (T)CM_body_pos[b][1], (T)CM_body_pos[b][2]};
+        T bq[4] = {(T)CM_body_quat[b][0], (T)CM_body_quat[b][1], (T)CM_body_quat[b][2], (T)CM_body_quat[b][3]};
+        T pos[3], quat[4], t[3];
+        cw_mulv(t, w.xmat[p], bp);
+        for (int k = 0; k < 3; k++) pos[k] = w.xpos[p][k] + t[k];
+        cw_qmul(quat, w.xquat[p], bq);
+        if (j >= 0) {
+          const int qa = CM_jnt_qposadr[j];
+          T qj[4], qn[4];
+          if (CM_jnt_type[j] == 1) {
+            T s, c;
+            cw_sincos<T>((T)0.5 * (qpos[qa] - (T)CM_qpos0[qa]), &s, &c);
+            qj[0] = c; qj[1] = (T)CM_jnt_axis[j][0] * s; qj[2] = (T)CM_jnt_axis[j][1] * s; qj[3] = (T)CM_jnt_axis[j][2] * s;
+          } else {
+            qj[0] = qpos[qa]; qj[1] = qpos[qa + 1]; qj[2] = qpos[qa + 2]; qj[3] = qpos[qa + 3];
+            cw_qnorm(qj);
+          }
+          cw_qmul(qn, quat, qj);
+          for (int k = 0; k < 4; k++) quat[k] = qn[k];
+        }
+        cw_qnorm(quat);
+        for (int k = 0; k < 3; k++) w.xpos[b][k] = pos[k];
+        for (int k = 0; k < 4; k++) w.xquat[b][k] = quat[k];
+        cw_qmat(w.xmat[b], quat);
+      }
+    }
+    CW_SYNC();
+  }
+  /* cdof and cinert about org = pelvis origin */
+  CW_FOR_LANES {
+    if (lane >= 1 && lane < CW_NB) {
+      const int b = lane;
+      const T *R = w.xmat[b];
+      T org[3] = {w.xpos[1][0], w.xpos[1][1], w.xpos[1][2]};
+      T off[3] = {org[0] - w.xpos[b][0], org[1] - w.xpos[b][1], org[2] - w.xpos[b][2]};
+      if (b == 1) {
+        for (int a = 0; a < 3; a++)
+          for (int k = 0; k < 3; k++) {
+            w.cdof[a][k] = 0; w.cdof[a][3 + k] = (a == k) ? (T)1 : (T)0;
+            w.cdof[3 + a][k] = R[3 * k + a]; w.cdof[3 + a][3 + k] = 0;
+          }
+      } else {
+        const int j = CM_body_jnt[b];
+        if (j >= 0) {
+          const int da = CM_jnt_dofadr[j];
+          if (CM_jnt_type[j] == 1) {
+            T al[3] = {(T)CM_jnt_axis[j][0], (T)CM_jnt_axis[j][1], (T)CM_jnt_axis[j][2]}, ax[3];
+            cw_mulv(ax, R, al);
+            for (int k = 0; k < 3; k++) w.cdof[da][k] = ax[k];
+            cw_cross(w.cdof[da] + 3, ax, off);
+          } else {
+            for (int a = 0; a < 3; a++) {
+              T ax[3] = {R[a], R[3 + a], R[6 + a]};
+              for (int k = 0; k < 3; k++) w.cdof[da + a][k] = ax[k];
+              cw_cross(w.cdof[da + a] + 3, ax, off);
+            }
+          }
+        }
+      }
+      /* spatial inertia about org */
+      T in0 = (T)CM_body_inertia[b][0], in1 = (T)CM_body_inertia[b][1], in2 = (T)CM_body_inertia[b][2];
+      T in3 = (T)CM_body_inertia[b][3], in4 = (T)CM_body_inertia[b][4], in5 = (T)CM_body_inertia[b][5];
+      T Ib[9] = {in0, in3, in4, in3, in1, in5, in4, in5, in2}, Tm[9], Iw[9];
+      for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++) Tm[3 * r + c] = R[3 * r] * Ib[c] + R[3 * r + 1] * Ib[3 + c] + R[3 * r + 2] * Ib[6 + c];
+      for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++) Iw[3 * r + c] = Tm[3 * r] * R[3 * c] + Tm[3 * r + 1] * R[3 * c + 1] + Tm[3 * r + 2] * R[3 * c + 2];
+      T ip[3] = {(T)CM_body_ipos[b][0], (T)CM_body_ipos[b][1], (T)CM_body_ipos[b][2]}, c[3];
+      cw_mulv(c, R, ip);
+      for (int k = 0; k < 3; k++) c[k] -= off[k]; /* xipos - org */
+      const T mass = w.st[S_MASS + b], cc = cw_dot3(c, c);
+      T *I = w.cinert[b];
+      I[0] = mass; I[1] = mass * c[0]; I[2] = mass * c[1]; I[3] = mass * c[2];
+      I[4] = Iw[0] + mass * (cc - c[0] * c[0]);
+      I[5] = Iw[4] + mass * (cc - c[1] * c[1]);
+      I[6] = Iw[8] + mass * (cc - c[2] * c[2]);
+      I[7] = Iw[1] - mass * c[0] * c[1];
+      I[8] = Iw[2] - mass * c[0] * c[2];
+      I[9] = Iw[5] - mass * c[1] * c[2];
+      for (int k = 0; k < 10; k++) w.crb[b][k] = I[k];
+    }
+  }
+  CW_SYNC();
+}
+
+/* composite inertia (mj_crb): parents gather children, deepest level first; then M (lane = dof) */
+template <typename T> CW_FN void cw_crb(CassieWs<T> &w CW_LANE_PARAM) {
+  for (int lvl = CM_MAXLEVEL - 1; lvl >= 1; lvl--) {
+    CW_FOR_LANES {
+      if (lane < CW_NB && CM_body_level[lane] == lvl) {
+        const int nc = CM_body_nchild[lane];
+        for (int c = 0; c < nc; c++) {
+          const int ch = CM_body_child[lane][c];
+          for (int k = 0; k < 10; k++) w.crb[lane][k] += w.crb[ch][k];
+        }
+      }
+    }
+    CW_SYNC();
+  }
+  CW_FOR_LANES {
+    const int i = lane;
+    T f[6];
+    cw_inert_mul(f, w.crb[CM_dof_body[i]], w.cdof[i]);
+    w.Mdiag[i] = cw_dot6(w.cdof[i], f) + (T)CM_dof_armature[i];
+    const int na = CM_dof_nanc[i];
+    for (int t = 0; t < na; t++) {
+      const int j = CM_dof_anc[i][t];
+      const T v = cw_dot6(w.cdof[j], f);
+      w.M[j][i] = v;
+      w.M[i][j] = v;
+    }
+  }
+  CW_SYNC();
+}
+
+/* sparse L^T D L (mj_factorM): M = L^T D L, L unit lower with the sparsity of the dof tree.
+ * hdamp = 0: factor M; hdamp = h: factor M + h diag(damping) (mj_Euler's implicit damping). */
+template <typename T> CW_FN void cw_factor(CassieWs<T> &w, T hdamp, bool recopy CW_LANE_PARAM) {
+  CW_FOR_LANES {
+    const int i = lane;
+    w.D[i] = w.Mdiag[i] + hdamp * w.st[S_DAMPING + i];
+    if (recopy) {
+      const int na = CM_dof_nanc[i];
+      for (int t = 0; t < na; t++) { const int j = CM_dof_anc[i][t]; w.M[i][j] = w.M[j][i]; }
+    }
+  }
+  CW_SYNC();
+  for (int k = CW_NV - 1; k >= 0; k--) {
+    const int na = CM_dof_nanc[k];
+    const T dinv = (T)1 / w.D[k];
+    const unsigned mask = CM_dof_ancmask[k];
+    if (na > 0) {
+      CW_FOR_LANES {
+        if ((mask >> lane) & 1u) {
+          const T a = w.M[k][lane] * dinv;
+          for (int t = 0; t < na; t++) {
+            const int j = CM_dof_anc[k][t];
+            if (j > lane) break;
+            if (j < lane) w.M[lane][j] -= a * w.M[k][j];
+            else w.D[lane] -= a * w.M[k][lane];
+          }
+        }
+      }
+      CW_SYNC();
+      CW_FOR_LANES {
+        if ((mask >> lane) & 1u) w.M[k][lane] *= dinv;
+        if (lane == 0) w.Dinv[k] = dinv;
+      }
+      CW_SYNC();
+    } else {
+      CW_FOR_LANES { if (lane == 0) w.Dinv[k] = dinv; }
+      CW_SYNC();
+    }
+  }
+}
+
+/* v <- L^-T v (in place, shared vector) */
+template <typename T> CW_FN void cw_solve_LT(CassieWs<T> &w, T *v CW_LANE_PARAM) {
+  for (int k = CW_NV - 1; k >= 1; k--) {
+    const unsigned mask = CM_dof_ancmask[k];
+    const T vk = v[k];
+    CW_FOR_LANES { if ((mask >> lane) & 1u) v[lane] -= w.M[k][lane] * vk; }
+    CW_SYNC();
+  }
+}
+/* v <- L^-1 v: every dof has exactly one ancestor per depth, so 13 level sweeps suffice */
+template <typename T> CW_FN void cw_solve_L(CassieWs<T> &w, T *v CW_LANE_PARAM) {
+  for (int lvl = 0; lvl < CM_MAXANC; lvl++) {
+    CW_FOR_LANES {
+      if (CM_dof_nanc[lane] > lvl) { const int j = CM_dof_anc[lane][lvl]; v[lane] -= w.M[lane][j] * v[j]; }
+    }
+    CW_SYNC();
+  }
+}
+template <typename T> CW_FN void cw_scale_Dinv(CassieWs<T> &w, T *v CW_LANE_PARAM) {
+  CW_FOR_LANES { v[lane] *= w.Dinv[lane]; }
+  CW_SYNC();
+}
+
+/* translational Jacobian column of a point (offset from org) on body b for dof = lane */
+template <typename T> CW_FN void cw_jac_col(const CassieWs<T> &w, int b, const T *off, int dof, T *col) {
+  if ((CM_body_dofmask[b] >> dof) & 1u) {
+    T t[3];
+    cw_cross(t, w.cdof[dof], off);
+    col[0] = t[0] + w.cdof[dof][3]; col[1] = t[1] + w.cdof[dof][4]; col[2] = t[2] + w.cdof[dof][5];
+  } else {
+    col[0] = col[1] = col[2] = 0;
+  }
+}
+
+template <typename T> CW_FN void cw_make_frame(T *fr) { /* mju_makeFrame */
+  T *n = fr, *t1 = fr + 3, *t2 = fr + 6;
+  T d = cw_dot3(n, t1);
+  for (int k = 0; k < 3; k++) t1[k] -= d * n[k];
+  T l = cw_sqrt<T>(cw_dot3(t1, t1));
+  if (l < (T)0.5) {
+    if (n[1] < (T)0.5 && n[1] > (T)-0.5) { t1[0] = 0; t1[1] = 1; t1[2] = 0; } else { t1[0] = 0; t1[1] = 0; t1[2] = 1; }
+    d = cw_dot3(n, t1);
+    for (int k = 0; k < 3; k++) t1[k] -= d * n[k];
+    l = cw_sqrt<T>(cw_dot3(t1, t1));
+  }
+  const T inv = (T)1 / l;
+  for (int k = 0; k < 3; k++) t1[k] *= inv;
+  cw_cross(t2, n, t1);
+}
+
+template <typename T> CW_FN void cw_geom_world(const CassieWs<T> &w, int g, T *c, T *ax) {
+  const int b = CM_geom_body[g];
+  T gp[3] = {(T)CM_geom_pos[g][0], (T)CM_geom_pos[g][1], (T)CM_geom_pos[g][2]};
+  T ga[3] = {(T)CM_geom_axis[g][0], (T)CM_geom_axis[g][1], (T)CM_geom_axis[g][2]}, t[3];
+  cw_mulv(t, w.xmat[b], gp);
+  for (int k = 0; k < 3; k++) c[k] = w.xpos[b][k] + t[k];
+  cw_mulv(ax, w.xmat[b], ga);
+}
+
+/* candidate slots: 0..16 floor tests in priority order (feet first), 17..25 left x right capsule pairs */
+CM_ARRAY int CW_CAND_GEOM[17] = {4, 4, 8, 8, 3, 3, 7, 7, 2, 2, 6, 6, 1, 1, 5, 5, 0};
+CM_ARRAY int CW_CAND_END[17] = {1, -1, 1, -1, 1, -1, 1, -1, 1, -1, 1, -1, 1, -1, 1, -1, 0};
+CM_ARRAY int CW_PAIR_G1[9] = {2, 2, 2, 3, 3, 3, 4, 4, 4};
+CM_ARRAY int CW_PAIR_G2[9] = {6, 7, 8, 6, 7, 8, 6, 7, 8};
+
+template <typename T> CW_FN void cw_collision(CassieWs<T> &w CW_LANE_PARAM) {
+  CW_FOR_LANES {
+    w.cand_dist[lane] = 1;
+    if (lane < 17) {
+      const int g = CW_CAND_GEOM[lane];
+      T fq[4] = {w.st[S_FLOORQ], w.st[S_FLOORQ + 1], w.st[S_FLOORQ + 2], w.st[S_FLOORQ + 3]}, Rf[9];
+      cw_qmat(Rf, fq);
+      T n[3] = {Rf[2], Rf[5], Rf[8]}, c[3], ax[3];
+      cw_geom_world(w, g, c, ax);
+      const T r = (T)CM_geom_radius[g], hl = (T)CM_geom_halflen[g] * (T)CW_CAND_END[lane];
+      T pc[3] = {c[0] + hl * ax[0], c[1] + hl * ax[1], c[2] + hl * ax[2]};
+      T rel[3] = {pc[0], pc[1], pc[2] - (T)CM_FLOOR_Z};
+      const T dist = cw_dot3(rel, n) - r;
+      w.cand_dist[lane] = dist;
+      for (int k = 0; k < 3; k++) {
+        w.cand_pos[lane][k] = pc[k] - n[k] * (r + (T)0.5 * dist);
+        w.cand_n[lane][k] = n[k];
+        w.cand_hint[lane][k] = CW_CAND_END[lane] != 0 ? ax[k] : (T)0;
+      }
+    } else if (lane < 26) {
+      const int g1 = CW_PAIR_G1[lane - 17], g2 = CW_PAIR_G2[lane - 17];
+      T c1[3], a1[3], c2[3], a2[3];
+      cw_geom_world(w, g1, c1, a1);
+      cw_geom_world(w, g2, c2, a2);
+      const T h1 = (T)CM_geom_halflen[g1], h2 = (T)CM_geom_halflen[g2], r1 = (T)CM_geom_radius[g1], r2 = (T)CM_geom_radius[g2];
+      T r[3] = {c1[0] - c2[0], c1[1] - c2[1], c1[2] - c2[2]};
+      const T b = cw_dot3(a1, a2), c = cw_dot3(a1, r), f = cw_dot3(a2, r), den = 1 - b * b;
+      T ss = den > (T)1e-12 ? (b * f - c) / den : (T)0;
+      ss = cw_min(cw_max(ss, -h1), h1);
+      T tt = b * ss + f;
+      tt = cw_min(cw_max(tt, -h2), h2);
+      ss = b * tt - c;
+      ss = cw_min(cw_max(ss, -h1), h1);
+      T p1[3], nn[3];
+      for (int k = 0; k < 3; k++) { p1[k] = c1[k] + ss * a1[k]; nn[k] = c2[k] + tt * a2[k] - p1[k]; }
+      const T len = cw_sqrt<T>(cw_dot3(nn, nn)), dist = len - r1 - r2;
+      if (dist < 0 && len > (T)1e-15) {
+        w.cand_dist[lane] = dist;
+        const T inv = (T)1 / len;
+        for (int k = 0; k < 3; k++) {
+          nn[k] *= inv;
+          w.cand_pos[lane][k] = p1[k] + nn[k] * (r1 + (T)0.5 * dist);
+          w.cand_n[lane][k] = nn[k];
+          w.cand_hint[lane][k] = 0;
+        }
+      }
+    }
+  }
+  CW_SYNC();
+  /* uniform compaction in priority order */
+  int nc = 0;
+  for (int s = 0; s < 26 && nc < CW_NCON; s++) {
+    if (w.cand_dist[s] < 0) {
+      CW_FOR_LANES {
+        if (lane == 0) {
+          T fr[9];
+          for (int k = 0; k < 3; k++) { w.con_pos[nc][k] = w.cand_pos[s][k]; fr[k] = w.cand_n[s][k]; fr[3 + k] = w.cand_hint[s][k]; fr[6 + k] = 0; }
+          cw_make_frame(fr);
+          for (int k = 0; k < 9; k++) w.con_frame[nc][k] = fr[k];
+          w.con_dist[nc] = w.cand_dist[s];
+          if (s < 17) { w.con_geom[nc] = CW_CAND_GEOM[s]; w.con_geom1[nc] = -1; w.con_dim[nc] = 3; w.con_mu[nc] = w.st[S_FRICTION]; }
+          else { w.con_geom[nc] = CW_PAIR_G2[s - 17]; w.con_geom1[nc] = CW_PAIR_G1[s - 17]; w.con_dim[nc] = 1; w.con_mu[nc] = 0; }
+          w.con_adr[nc] = -1;
+        }
+      }
+      nc++;
+    }
+  }
+  CW_FOR_LANES { if (lane == 0) w.ncon = nc; }
+  CW_SYNC();
+}
+
+/* mj_makeConstraint: rows of J (lane = dof column), efc_pos / efc_diag / efc_type per row */
+CM_ARRAY int CW_LIM_JNT[16] = {4, 5, 6, 8, 9, 10, 12, 14, 15, 16, 17, 19, 20, 21, 23, 25};
+template <typename T> CW_FN void cw_make_constraint(CassieWs<T> &w, const T *qpos, int flags CW_LANE_PARAM) {
+  int r = 0;
+  const T org[3] = {w.xpos[1][0], w.xpos[1][1], w.xpos[1][2]};
+  if (!(flags & 1)) {
+    for (int e = 0; e < CM_NEQ; e++) {
+      const int b1 = CM_eq_body1[e], b2 = CM_eq_body2[e];
+      T a1[3] = {(T)CM_eq_anchor1[e][0], (T)CM_eq_anchor1[e][1], (T)CM_eq_anchor1[e][2]};
+      T a2[3] = {(T)CM_eq_anchor2[e][0], (T)CM_eq_anchor2[e][1], (T)CM_eq_anchor2[e][2]};
+      T o1[3], o2[3];
+      cw_mulv(o1, w.xmat[b1], a1);
+      cw_mulv(o2, w.xmat[b2], a2);
+      for (int k = 0; k < 3; k++) { o1[k] += w.xpos[b1][k] - org[k]; o2[k] += w.xpos[b2][k] - org[k]; }
+      const T diag = w.st[S_BODYINVW + b1] + w.st[S_BODYINVW + b2];
+      CW_FOR_LANES {
+        T c1[3], c2[3];
+        cw_jac_col(w, b1, o1, lane, c1);
+        cw_jac_col(w, b2, o2, lane, c2);
+        for (int k = 0; k < 3; k++) w.J[r + k][lane] = c1[k] - c2[k];
+        if (lane < 3) { w.efc_pos[r + lane] = o1[lane] - o2[lane]; w.efc_diag[r + lane] = diag; w.efc_type[r + lane] = 0; }
+      }
+      r += 3;
+    }
+    /* joint limits */
+    for (int l = 0; l < 16; l++) {
+      const int j = CW_LIM_JNT[l];
+      const T q = qpos[CM_jnt_qposadr[j]];
+      for (int side = -1; side <= 1; side += 2) {
+        const T dist = (T)side * ((T)CM_jnt_range[j][(side + 1) / 2] - q);
+        if (dist < 0 && r < CW_NEFC) {
+          const int da = CM_jnt_dofadr[j];
+          CW_FOR_LANES {
+            w.J[r][lane] = (lane == da) ? (T)(-side) : (T)0;
+            if (lane == 0) { w.efc_pos[r] = dist; w.efc_diag[r] = w.st[S_DOFINVW + da]; w.efc_type[r] = 1; }
+          }
+          r++;
+        }
+      }
+    }
+    /* contacts */
+    int nc = (flags & 2) ? 0 : w.ncon;
+    for (int c = 0; c < nc; c++) {
+      const int nrow = w.con_dim[c] == 3 ? 4 : 1;
+      if (r + nrow > CW_NEFC) { nc = c; break; }
+      const int b2 = CM_geom_body[w.con_geom[c]], g1 = w.con_geom1[c], b1 = g1 >= 0 ? CM_geom_body[g1] : 0;
+      T off[3] = {w.con_pos[c][0] - org[0], w.con_pos[c][1] - org[1], w.con_pos[c][2] - org[2]};
+      const T tran = w.st[S_BODYINVW + b1] + w.st[S_BODYINVW + b2], mu = w.con_mu[c], dist = w.con_dist[c];
+      const T *fr = w.con_frame[c];
+      CW_FOR_LANES {
+        T c2[3], c1[3] = {0, 0, 0}, jf[3];
+        cw_jac_col(w, b2, off, lane, c2);
+        if (b1 > 0) cw_jac_col(w, b1, off, lane, c1);
+        for (int a = 0; a < 3; a++) jf[a] = fr[3 * a] * (c2[0] - c1[0]) + fr[3 * a + 1] * (c2[1] - c1[1]) + fr[3 * a + 2] * (c2[2] - c1[2]);
+        if (nrow == 1) {
+          w.J[r][lane] = jf[0];
+          if (lane == 0) { w.efc_pos[r] = dist; w.efc_diag[r] = tran; w.efc_type[r] = 2; w.con_adr[c] = r; }
+        } else {
+          w.J[r][lane] = jf[0] + mu * jf[1];
+          w.J[r + 1][lane] = jf[0] - mu * jf[1];
+          w.J[r + 2][lane] = jf[0] + mu * jf[2];
+          w.J[r + 3][lane] = jf[0] - mu * jf[2];
+          if (lane < 4) { w.efc_pos[r + lane] = dist; w.efc_diag[r + lane] = tran + mu * mu * tran; w.efc_type[r + lane] = 2; }
+          if (lane == 0) w.con_adr[c] = r;
+        }
+      }
+      r += nrow;
+    }
+    CW_FOR_LANES { if (lane == 0) w.ncon = nc; }
+  } else {
+    CW_FOR_LANES { if (lane == 0) w.ncon = 0; }
+  }
+  CW_FOR_LANES { if (lane == 0) w.nefc = r; }
+  CW_SYNC();
+  /* impedance, regulariser, reference stiffness/damping (mj_makeImpedance), J qvel — lane = row */
+  for (int pass = 0; pass < 2; pass++) {
+    CW_FOR_LANES {
+      const int row = pass * 32 + lane;
+      if (row < r) {
+        const T pos = w.efc_pos[row];
+        T x = cw_abs(pos) / (T)CM_SOLIMP_WIDTH, yy, imp;
+        if (x >= 1) imp = (T)CM_SOLIMP_DMAX;
+        else {
+          if (x <= (T)CM_SOLIMP_MID) yy = x * x / (T)CM_SOLIMP_MID; /* power 2 */
+          else yy = 1 - (1 - x) * (1 - x) / (T)(1 - CM_SOLIMP_MID);
+          imp = (T)CM_SOLIMP_DMIN + yy * (T)(CM_SOLIMP_DMAX - CM_SOLIMP_DMIN);
+        }
+        const int ty = w.efc_type[row];
+        T tc = ty == 1 ? (T)CM_LIMIT_SOLREF_TC : (T)CM_EQ_SOLREF_TC; /* equality and geoms share solref 0.005 1 */
+        const T dr = 1;
+        if (tc < (T)(2 * CM_TIMESTEP)) tc = (T)(2 * CM_TIMESTEP);
+        const T dmax = (T)CM_SOLIMP_DMAX;
+        w.efc_K[row] = (T)1 / (dmax * dmax * tc * tc * dr * dr);
+        w.efc_B[row] = (T)2 / (dmax * tc);
+        w.efc_imp[row] = imp;
+        w.efc_R[row] = cw_max((T)1e-15, (1 - imp) / imp * w.efc_diag[row]);
+        T jv = 0;
+        for (int i = 0; i < CW_NV; i++) jv += w.J[row][i] * w.st[S_QVEL + i];
+        w.efc_jv[row] = jv;
+      }
+    }
+  }
+  CW_SYNC();
+}
+
+/* B = J L^-1 (each row: y <- L^-T y, lane = row) then A = B D^-1 B^T + diag(R) (mj_projectConstraint) */
+template <typename T> CW_FN void cw_half_solve_rows(CassieWs<T> &w, int n CW_LANE_PARAM) {
+  for (int pass = 0; pass * 32 < n; pass++) {
+    CW_FOR_LANES {
+      const int row = pass * 32 + lane;
+      if (row < n) {
+        T *y = w.J[row];
+        for (int k = CW_NV - 1; k >= 1; k--) {
+          const T yk = y[k];
+          const int na = CM_dof_nanc[k];
+          for (int t = 0; t < na; t++) { const int j = CM_dof_anc[k][t]; y[j] -= w.M[k][j] * yk; }
+        }
+      }
+    }
+  }
+  CW_SYNC();
+}
+template <typename T> CW_FN void cw_project(CassieWs<T> &w CW_LANE_PARAM) {
+  const int n = w.nefc;
+  cw_half_solve_rows<T>(w, n CW_LANE_ARG);
+  for (int pass = 0; pass * 32 < n; pass++) {
+    CW_FOR_LANES {
+      const int c = pass * 32 + lane;
+      if (c < n) {
+        T bs[CW_NV];
+        for (int i = 0; i < CW_NV; i++) bs[i] = w.J[c][i] * w.Dinv[i];
+        for (int rr = 0; rr <= c; rr++) {
+          T s = 0;
+          for (int i = 0; i < CW_NV; i++) s += w.J[rr][i] * bs[i];
+          if (rr == c) s += w.efc_R[c];
+          w.A[rr][c] = s;
+          w.A[c][rr] = s;
+        }
+        w.efc_dinv[c] = 0; /* set below once the diagonal is final */
+      }
+    }
+  }
+  CW_SYNC();
+  for (int pass = 0; pass * 32 < n; pass++) {
+    CW_FOR_LANES {
+      const int c = pass * 32 + lane;
+      if (c < n) w.efc_dinv[c] = (T)1 / w.A[c][c];
+    }
+  }
+  CW_SYNC();
+}
+
+/* velocity stage: mj_comVel + mj_rne (bias), lane = body, level by level */
+template <typename T> CW_FN void cw_rne(CassieWs<T> &w, const T *qvel CW_LANE_PARAM) {
+  CW_FOR_LANES {
+    if (lane == 0) {
+      for (int k = 0; k < 6; k++) { w.cvel[0][k] = 0; w.cacc[0][k] = 0; }
+      w.cacc[0][5] = (T)(-CM_GRAVITY_Z);
+    }
+  }
+  CW_SYNC();
+  for (int lvl = 1; lvl <= CM_MAXLEVEL; lvl++) {
+    CW_FOR_LANES {
+      if (lane < CW_NB && CM_body_level[lane] == lvl) {
+        const int b = lane, p = CM_body_parent[b];
+        T v[6], a[6];
+        for (int k = 0; k < 6; k++) { v[k] = w.cvel[p][k]; a[k] = w.cacc[p][k]; }
+        const int da = CM_body_dofadr[b], nd = CM_body_dofnum[b];
+        /* pelvis: slides one at a time, then the ball (all three cdof_dot from the pre-ball velocity) */
+        int d0 = 0;
+        while (d0 < nd) {
+          const int grp = (nd - d0 >= 3 && !(b == 1 && d0 < 3)) ? 3 : 1;
+          for (int s = 0; s < grp; s++) {
+            const T *cd = w.cdof[da + d0 + s];
+            T *o = w.cdd[da + d0 + s];
+            T t1[3], t2[3], t3[3];
+            cw_cross(t1, v, cd); cw_cross(t2, v, cd + 3); cw_cross(t3, v + 3, cd);
+            for (int k = 0; k < 3; k++) { o[k] = t1[k]; o[3 + k] = t2[k] + t3[k]; }
+          }
+          for (int s = 0; s < grp; s++) {
+            const T qd = qvel[da + d0 + s];
+            for (int k = 0; k < 6; k++) { v[k] += w.cdof[da + d0 + s][k] * qd; a[k] += w.cdd[da + d0 + s][k] * qd; }
+          }
+          d0 += grp;
+        }
+        for (int k = 0; k < 6; k++) { w.cvel[b][k] = v[k]; }
+        /* cfrc_body = I a + v x* (I v), stored over cacc after the children have read it: use crb as scratch */
+        T f[6], iv[6], t1[3], t2[3], t3[3];
+        cw_inert_mul(f, w.cinert[b], a);
+        cw_inert_mul(iv, w.cinert[b], v);
+        cw_cross(t1, v, iv); cw_cross(t2, v + 3, iv + 3); cw_cross(t3, v, iv + 3);
+        for (int k = 0; k < 3; k++) { f[k] += t1[k] + t2[k]; f[3 + k] += t3[k]; }
+        for (int k = 0; k < 6; k++) { w.cacc[b][k] = a[k]; w.crb[b][k] = f[k]; }
+      }
+    }
+    CW_SYNC();
+  }
+  for (int lvl = CM_MAXLEVEL - 1; lvl >= 1; lvl--) {
+    CW_FOR_LANES {
+      if (lane < CW_NB && CM_body_level[lane] == lvl) {
+        const int nc = CM_body_nchild[lane];
+        for (int c = 0; c < nc; c++) {
+          const int ch = CM_body_child[lane][c];
+          for (int k = 0; k < 6; k++) w.crb[lane][k] += w.crb[ch][k];
+        }
+      }
+    }
+    CW_SYNC();
+  }
+  CW_FOR_LANES { w.vec[V_BIAS][lane] = cw_dot6(w.cdof[lane], w.crb[CM_dof_body[lane]]); }
+  CW_SYNC();
+}
+
+/* foot positions (cassie_sim_foot_positions @0x6e10) and forces (cassie_sim_foot_forces @0x69f0), warp-uniform */
+template <typename T> CW_FN void cw_foot_positions(const CassieWs<T> &w, T *fp) {
+  for (int k = 0; k < 3; k++) { fp[k] = w.xpos[CW_LFOOT][k]; fp[3 + k] = w.xpos[CW_RFOOT][k]; }
+  fp[2] -= (T)CW_FOOT_Z_OFFSET; fp[5] -= (T)CW_FOOT_Z_OFFSET;
+}
+template <typename T> CW_FN void cw_foot_forces(const CassieWs<T> &w, T *lz, T *rz) {
+  T l = 0, r = 0;
+  for (int c = 0; c < w.ncon; c++) {
+    const int adr = w.con_adr[c];
+    if (adr < 0) continue;
+    const int b2 = CM_geom_body[w.con_geom[c]], g1 = w.con_geom1[c], b1 = g1 >= 0 ? CM_geom_body[g1] : 0;
+    T fl[3] = {0, 0, 0};
+    const T *f = w.efc_f + adr;
+    if (w.con_dim[c] == 1) fl[0] = f[0];
+    else { fl[0] = f[0] + f[1] + f[2] + f[3]; fl[1] = w.con_mu[c] * (f[0] - f[1]); fl[2] = w.con_mu[c] * (f[2] - f[3]); }
+    const T *fr = w.con_frame[c];
+    const T fz = fr[2] * fl[0] + fr[5] * fl[1] + fr[8] * fl[2];
+    if (b2 == CW_LFOOT || b1 == CW_LFOOT) l += fz;
+    if (b2 == CW_RFOOT || b1 == CW_RFOOT) r += fz;
+  }
+  *lz = l; *rz = r;
+}
+
+/* =====================================================================================================
+ * one physics sub-step: mj_step1 + mj_step2 (integrate = true) or mj_forward (integrate = false)
+ * ===================================================================================================== */
+template <typename T> CW_NOINL void cw_mj_step(CassieWs<T> &w, bool integrate, int flags CW_LANE_PARAM) {
+  T *qpos = w.st + S_QPOS, *qvel = w.st + S_QVEL;
+  const T h = (T)CM_TIMESTEP;
+  /* ---- step1 ---- */
+  cw_kinematics<T>(w, qpos CW_LANE_ARG);
+  cw_crb<T>(w CW_LANE_ARG);
+  cw_factor<T>(w, (T)0, false CW_LANE_ARG);
+  cw_collision<T>(w CW_LANE_ARG);
+  cw_make_constraint<T>(w, qpos, flags CW_LANE_ARG);
+  cw_rne<T>(w, qvel CW_LANE_ARG);
+  const int n = w.nefc;
+  /* sensors (positions / velocities) for the next wrapper call */
+  CW_FOR_LANES {
+    if (lane < CM_NU) {
+      w.st[S_SENS_ACTPOS + lane] = (T)CM_act_gear[lane] * qpos[CM_act_qposadr[lane]];
+      w.st[S_SENS_ACTVEL + lane] = (T)CM_act_gear[lane] * qvel[CM_act_dof[lane]];
+    } else if (lane < CM_NU + 6) {
+      w.st[S_SENS_JPOS + lane - CM_NU] = qpos[CM_jsens_qposadr[lane - CM_NU]];
+    } else if (lane < CM_NU + 10) {
+      w.st[S_SENS_QUAT + lane - CM_NU - 6] = w.xquat[CM_IMU_BODY][lane - CM_NU - 6];
+    } else if (lane < CM_NU + 13) {
+      const int k = lane - CM_NU - 10;
+      w.st[S_SENS_GYRO + k] = qvel[3 + k];
+      w.st[S_SENS_PPOS + k] = qpos[k];
+      w.st[S_SENS_PVEL + k] = qvel[k];
+    }
+  }
+  /* ---- step2: smooth forces ---- */
+  CW_FOR_LANES {
+    const int i = lane;
+    T f = -w.st[S_DAMPING + i] * qvel[i] - w.vec[V_BIAS][i];
+    const int j = CM_dof_jnt[i];
+    const T k = (T)CM_jnt_stiffness[j];
+    if (k != 0) f -= k * qpos[CM_jnt_qposadr[j]];
+    w.vec[V_SMOOTH][i] = f;
+  }
+  CW_SYNC();
+  CW_FOR_LANES {
+    if (lane < CM_NU) {
+      T c = w.st[S_CTRL + lane];
+      const T cm = (T)CM_act_ctrlmax[lane];
+      c = cw_min(cw_max(c, -cm), cm);
+      w.vec[V_SMOOTH][CM_act_dof[lane]] += (T)CM_act_gear[lane] * c;
+    }
+  }
+  CW_SYNC();
+  /* z = D^-1 L^-T qfrc_smooth ; qacc_smooth = L^-1 z */
+  CW_FOR_LANES { w.vec[V_Z][lane] = w.vec[V_SMOOTH][lane]; }
+  CW_SYNC();
+  cw_solve_LT<T>(w, w.vec[V_Z] CW_LANE_ARG);
+  cw_scale_Dinv<T>(w, w.vec[V_Z] CW_LANE_ARG);
+  CW_FOR_LANES { w.vec[V_QACCS][lane] = w.vec[V_Z][lane]; }
+  CW_SYNC();
+  cw_solve_L<T>(w, w.vec[V_QACCS] CW_LANE_ARG);
+  /* ---- constraints ---- */
+  CW_FOR_LANES { w.vec[V_G][lane] = 0; }
+  int iters = 0;
+  if (n > 0) {
+    cw_project<T>(w CW_LANE_ARG);
+    /* L qacc_warmstart (so that J a = B (L a)) */
+    CW_FOR_LANES {
+      const int i = lane, na = CM_dof_nanc[i];
+      T s = w.st[S_QACC_WS + i];
+      for (int t = 0; t < na; t++) { const int j = CM_dof_anc[i][t]; s += w.M[i][j] * w.st[S_QACC_WS + j]; }
+      w.vec[V_TMP][i] = s;
+    }
+    CW_SYNC();
+    for (int pass = 0; pass * 32 < n; pass++) {
+      CW_FOR_LANES {
+        const int row = pass * 32 + lane;
+        if (row < n) {
+          T ja = 0, jw = 0;
+          for (int i = 0; i < CW_NV; i++) { ja += w.J[row][i] * w.vec[V_Z][i]; jw += w.J[row][i] * w.vec[V_TMP][i]; }
+          const T aref = -w.efc_B[row] * w.efc_jv[row] - w.efc_K[row] * w.efc_imp[row] * w.efc_pos[row];
+          w.efc_aref[row] = aref;
+          w.efc_b[row] = ja - aref;
+          T f = -(jw - aref) / w.efc_R[row];
+          if (w.efc_type[row] != 0 && f < 0) f = 0;
+          w.efc_f[row] = f;
+        }
+      }
+    }
+    CW_SYNC();
+    /* residual res = A f + b and warm-start cost */
+    T cost = 0;
+    for (int pass = 0; pass * 32 < n; pass++) {
+      CW_FOR_LANES {
+        const int row = pass * 32 + lane;
+        T part = 0;
+        if (row < n) {
+          T s = 0;
+          for (int c = 0; c < n; c++) s += w.A[row][c] * w.efc_f[c];
+          w.efc_res[row] = s + w.efc_b[row];
+          part = w.efc_f[row] * ((T)0.5 * s + w.efc_b[row]);
+        }
+        w.red[lane] = part;
+      }
+      CW_SYNC();
+      for (int k = 0; k < 32; k++) cost += w.red[k];
+      CW_SYNC();
+    }
+    if (cost > 0) {
+      for (int pass = 0; pass * 32 < n; pass++) {
+        CW_FOR_LANES {
+          const int row = pass * 32 + lane;
+          if (row < n) { w.efc_f[row] = 0; w.efc_res[row] = w.efc_b[row]; }
+        }
+      }
+      CW_SYNC();
+    }
+    /* PGS sweeps (mj_solPGS): residual-update form, rows in order */
+    const T scale = (T)1 / (w.st[S_MEANINERTIA] * (T)CW_NV);
+    for (int it = 0; it < CM_ITERATIONS; it++) {
+      T improvement = 0;
+      for (int i = 0; i < n; i++) {
+        const T res = w.efc_res[i], old = w.efc_f[i];
+        T nf = old - res * w.efc_dinv[i];
+        if (w.efc_type[i] != 0 && nf < 0) nf = 0;
+        const T dl = nf - old;
+        if (dl != 0) {
+          improvement -= (T)0.5 * dl * dl * w.A[i][i] + dl * res;
+          CW_SYNC();
+          CW_FOR_LANES {
+            if (lane == 0) w.efc_f[i] = nf;
+            if (lane < n) w.efc_res[lane] += dl * w.A[i][lane];
+            if (lane + 32 < n) w.efc_res[lane + 32] += dl * w.A[i][lane + 32];
+          }
+          CW_SYNC();
+        }
+      }
+      iters = it + 1;
+      if (improvement * scale < (T)1e-8) break;
+    }
+    /* g = B^T f */
+    CW_FOR_LANES {
+      T s = 0;
+      for (int r = 0; r < n; r++) s += w.J[r][lane] * w.efc_f[r];
+      w.vec[V_G][lane] = s;
+    }
+  }
+  CW_SYNC();
+  /* qacc = qacc_smooth + L^-1 D^-1 g */
+  CW_FOR_LANES { w.vec[V_QACC][lane] = w.vec[V_G][lane] * w.Dinv[lane]; }
+  CW_SYNC();
+  cw_solve_L<T>(w, w.vec[V_QACC] CW_LANE_ARG);
+  CW_FOR_LANES {
+    w.vec[V_QACC][lane] += w.vec[V_QACCS][lane];
+    if (lane == 0) { w.solver_iter = iters; }
+  }
+  CW_SYNC();
+  /* accelerometer at the imu site (world-frame a_site - g, rotated into the site frame) */
+  {
+    const T *R = w.xmat[CM_IMU_BODY], *qa = w.vec[V_QACC];
+    T ip[3] = {(T)CM_imu_pos[0], (T)CM_imu_pos[1], (T)CM_imu_pos[2]}, r[3], wl[3] = {qvel[3], qvel[4], qvel[5]};
+    T al[3] = {qa[3], qa[4], qa[5]}, ww[3], aw[3], t1[3], t2[3], t3[3], a[3], out[3];
+    cw_mulv(r, R, ip); cw_mulv(ww, R, wl); cw_mulv(aw, R, al);
+    cw_cross(t1, aw, r); cw_cross(t2, ww, r); cw_cross(t3, ww, t2);
+    for (int k = 0; k < 3; k++) a[k] = qa[k] + t1[k] + t3[k];
+    a[2] -= (T)CM_GRAVITY_Z;
+    cw_tmulv(out, R, a);
+    CW_SYNC();
+    CW_FOR_LANES { if (lane < 3) w.st[S_SENS_ACC + lane] = out[lane]; }
+  }
+  if (!integrate) { CW_SYNC(); return; }
+  /* ---- Euler, implicit in damping: (M + h B) a' = qfrc_smooth + J^T f, J^T f = L^T g ---- */
+  CW_FOR_LANES {
+    const int j = lane;
+    T s = w.vec[V_G][j];
+    for (int i = j + 1; i < CW_NV; i++)
+      if ((CM_dof_ancmask[i] >> j) & 1u) s += w.M[i][j] * w.vec[V_G][i];
+    w.vec[V_TMP][j] = s + w.vec[V_SMOOTH][j];
+  }
+  CW_SYNC();
+  cw_factor<T>(w, h, true CW_LANE_ARG);
+  cw_solve_LT<T>(w, w.vec[V_TMP] CW_LANE_ARG);
+  cw_scale_Dinv<T>(w, w.vec[V_TMP] CW_LANE_ARG);
+  cw_solve_L<T>(w, w.vec[V_TMP] CW_LANE_ARG);
+  CW_FOR_LANES {
+    qvel[lane] += h * w.vec[V_TMP][lane];
+    w.st[S_QACC_WS + lane] = w.vec[V_QACC][lane];
+  }
+  CW_SYNC();
+  CW_FOR_LANES {
+    const int i = lane, j = CM_dof_jnt[i];
+    if (CM_jnt_type[j] != 2) {
+      qpos[CM_dof_qposadr[i]] += h * qvel[i];
+    } else if (i == CM_jnt_dofadr[j]) {
+      const int qa = CM_jnt_qposadr[j];
+      T wv[3] = {qvel[i], qvel[i + 1], qvel[i + 2]};
+      const T nrm = cw_sqrt<T>(cw_dot3(wv, wv)), ang = nrm * h;
+      if (ang > (T)1e-15) {
+        T s, c, dq[4], qn[4], q0[4] = {qpos[qa], qpos[qa + 1], qpos[qa + 2], qpos[qa + 3]};
+        cw_sincos<T>((T)0.5 * ang, &s, &c);
+        const T inv = s / nrm;
+        dq[0] = c; dq[1] = wv[0] * inv; dq[2] = wv[1] * inv; dq[3] = wv[2] * inv;
+        cw_qmul(qn, q0, dq);
+        cw_qnorm(qn);
+        for (int k = 0; k < 4; k++) qpos[qa + k] = qn[k];
+      }
+    }
+  }
+  CW_SYNC();
+}
+#endif

@@ -1,0 +1,48 @@
+/* C-ABI of libapex_b200.so — batched, GPU-resident Cassie-v0 environment (one warp per env, sm_100a).
+ *
+ * Drop-in seam: this replaces, for N environments at once, the per-env calls the reference makes through
+ * cassie/cassiemujoco/cassiemujoco_ctypes.py:310-546 into libcassiemujoco.so
+ *   cassie_sim_init            (cassiemujoco_ctypes.py:319-321)  -> apex_cassie_env_init
+ *   cassie_sim_set_const       (cassie/cassie.py:660)            -> inside apex_cassie_env_reset / _step
+ *   cassie_sim_step_pd         (cassiemujoco_ctypes.py:343-345; cassie/cassie.py:328,665) -> 50x inside _step
+ *   cassie_sim_foot_positions / _foot_forces / _xquat / _qpos / _qvel (cassie/cassie.py:300-334,415-429)
+ *                                                                 -> consumed on-chip inside _step
+ * together with the Python env logic around them (CassieEnv.step / reset / get_full_state / clock_reward).
+ *
+ * Conventions: every pointer is a DEVICE pointer owned by the caller (PyTorch tensors on the product path);
+ * no hidden allocations; `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ * dtype 0 = float32, 1 = float64 (applies to st, action, obs, reward, term_obs).
+ * Return value: 0 on success, a negative cudaError_t otherwise (-1000 = bad argument).
+ */
+#ifndef APEX_CASSIE_H
+#define APEX_CASSIE_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define APEX_CASSIE_OBS 50
+#define APEX_CASSIE_ACT 10
+
+/* size of the per-env persistent record: st is [n][state_words] reals, sti is [n][istate_words] int32 */
+int apex_cassie_state_words(void);
+int apex_cassie_istate_words(void);
+/* word offset of a named field inside st ("qpos", "qvel", "speed", …) or sti ("time", "rng_ctr", …); -1 if unknown */
+int apex_cassie_layout(const char *name);
+
+/* CassieEnv.__init__ + cassie_sim_init for envs [0,n): default model, mj_setConst, fixed start pose, mj_forward.
+ * env ids are env_id0 + i (they key the Philox streams, so shards of one job can share a seed). */
+int apex_cassie_env_init(int dtype, void *st, int *sti, int n, unsigned seed, int env_id0, int dyn_rand, void *stream);
+/* CassieEnv.reset for every env; obs [n][50] */
+int apex_cassie_env_reset(int dtype, void *st, int *sti, int n, void *obs, void *stream);
+/* CassieEnv.step for every env: action [n][10] -> obs [n][50], reward [n], done [n] (bit0 terminal, bit1 time-out).
+ * With max_traj_len > 0 an env whose episode ended is reset in the same launch: obs then holds the first
+ * observation of the new episode and term_obs [n][50] (may be NULL) the last one of the old episode. */
+int apex_cassie_env_step(int dtype, void *st, int *sti, int n, const void *action, void *obs, void *reward, int *done,
+                         void *term_obs, int max_traj_len, void *stream);
+/* one raw mj_step (no wrapper, no env logic) on the stored state with S_CTRL as control; test hook */
+int apex_cassie_mj_step(int dtype, void *st, int *sti, int n, int flags, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,79 @@
+/* ORACLE — test infrastructure only (tests/, __graft_entry__.smoke(), bench.py cpu_baseline / --impl reference).
+ * The product (apex_b200/) never includes, links or calls anything in this directory.
+ *
+ * CPU float64 restatement of (1) the wrapper layer of cassie/cassiemujoco/libcassiemujoco.so
+ * (cassie_sim_step_pd @0x8450: PD law, motor model + 6-deep torque delay, encoder quantisation and
+ * velocity filters, IMU copy — SURVEY.md Appendix C) and (2) the Cassie-v0 environment of
+ * cassie/cassie.py (step :389-496, step_simulation :293-351, reset :523-680, get_full_state :787-859),
+ * cassie/rewards/clock_rewards.py:6-110 and cassie/phase_function.py:5-136.
+ * Physics underneath: oracle/cassie_phys.c.  PARITY UNPINNED against the closed Agility blocks
+ * (pd_input_step / cassie_core_sim_step / state_output_step): software safeties are not restated and the
+ * state estimator is replaced by an ideal one (sensor pass-through) — see DESIGN.md.
+ */
+#ifndef CASSIE_ENV_H
+#define CASSIE_ENV_H
+#include <stdint.h>
+#include "cassie_phys.h"
+
+#define CE_OBS 50
+#define CE_ACT 10
+
+typedef struct { /* the slice of state_out_t (include/state_out_t.h:24-78) the env reads */
+  double pelvis_pos[3], pelvis_quat[4], pelvis_rotvel[3], pelvis_transvel[3], pelvis_transacc[3], terrain_height;
+  double motor_pos[10], motor_vel[10], motor_torque[10], joint_pos[6], joint_vel[6];
+} ce_state_out_t;
+
+typedef struct { /* the slice of pd_in_t (include/pd_in_t.h:24-49) the env writes */
+  double torque[10], ptarget[10], dtarget[10], pgain[10], dgain[10];
+} ce_pd_in_t;
+
+typedef struct {
+  cp_model_t m;
+  cp_data_t d;
+  /* wrapper (cassie_sim_t) state */
+  double delay[CM_NU][6];        /* [0] newest … [5] oldest = applied */
+  int32_t drive_hist[CM_NU][9];  /* encoder counts, [0] newest */
+  int drive_init;
+  double jx[6][4], jy[6][2];
+  int joint_init;
+  double o_mpos[10], o_mvel[10], o_mtorque[10], o_jpos[6], o_jvel[6], o_quat[4], o_gyro[3], o_acc[3], o_ppos[3], o_pvel[3];
+  ce_state_out_t y;
+  ce_pd_in_t u;
+  /* env (cassie/cassie.py) state */
+  int time, counter, has_prev;
+  double phase, phaselen, phase_add, speed, side_speed, orient_add, swing_duration, stance_duration;
+  double prev_action[10], prev_torque[10];
+  double l_foot_vel[3], r_foot_vel[3];
+  int l_high, r_high, l_swing, r_swing, stepcount;
+  double menc_noise[10], jenc_noise[6], last_pelvis_pos[3];
+  double l_foot_frc, r_foot_frc, l_foot_pos[3], r_foot_pos[3], l_foot_orient_cost, r_foot_orient_cost, hiproll_cost, hiproll_act;
+  uint32_t seed, env_id, rng_ctr;
+  int dyn_rand;
+} ce_env_t;
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+int ce_sizeof_env(void);
+void ce_philox(uint32_t seed, uint32_t env_id, uint32_t ctr, uint32_t out[4]);
+void ce_sim_init(ce_env_t *e);                                        /* cassie_sim_init */
+void ce_sim_step_pd(ce_env_t *e, const ce_pd_in_t *u, ce_state_out_t *y); /* cassie_sim_step_pd */
+void ce_clock_knots(double swing, double stance, double x[8], double *phaselen);
+double ce_clock_eval(double swing, double stance, int which, double phase); /* which: 0 r_frc 1 r_vel 2 l_frc 3 l_vel */
+void ce_env_init(ce_env_t *e, uint32_t seed, uint32_t env_id, int dyn_rand);
+void ce_env_reset(ce_env_t *e, double *obs);
+void ce_env_set_command(ce_env_t *e, double speed, double side_speed, double phase); /* synthetic-input hook */
+void ce_env_step(ce_env_t *e, const double *action, double *obs, double *reward, int *done);
+void ce_env_obs(ce_env_t *e, double *obs);
+double ce_env_reward(ce_env_t *e, const double *action);
+/* batched helpers for the CPU baseline: envs is an array of n ce_env_t, OpenMP over envs */
+void ce_batch_init(ce_env_t *envs, int n, uint32_t seed, int dyn_rand, int nthreads);
+void ce_batch_reset(ce_env_t *envs, int n, double *obs, int nthreads);
+/* done: bit0 terminal, bit1 time-out (time >= max_traj_len); when either is set and max_traj_len > 0 the env is reset,
+ * obs holds the first observation of the new episode and term_obs (optional) the last one of the old episode */
+void ce_batch_step(ce_env_t *envs, int n, const double *actions, double *obs, double *rew, int *done, int max_traj_len,
+                   double *term_obs, int nthreads);
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,83 @@
+/* Host build of the product kernel source (apex_b200/csrc/cassie_warp.h, cassie_envstep.h) with the 32 lanes
+ * of a warp emulated by a loop.  Test infrastructure: lets the CPU-only suite compare the kernel logic with the
+ * oracle; never part of the shipped library. */
+#include <cstring>
+#include <cstdlib>
+#include "../../apex_b200/csrc/cassie_envstep.h"
+
+template <typename T> static void load(CassieWs<T> &w, const T *st, const int *sti) {
+  memcpy(w.st, st, sizeof(T) * S_WORDS);
+  memcpy(w.sti, sti, sizeof(int) * I_WORDS);
+}
+template <typename T> static void store(const CassieWs<T> &w, T *st, int *sti) {
+  memcpy(st, w.st, sizeof(T) * S_WORDS);
+  memcpy(sti, w.sti, sizeof(int) * I_WORDS);
+}
+
+#define DEFINE(T, SUF)                                                                                              \
+  extern "C" void emu_init_##SUF(T *st, int *sti, int n, unsigned seed, int dyn) {                                  \
+    CassieWs<T> *w = new CassieWs<T>();                                                                             \
+    for (int e = 0; e < n; e++) {                                                                                   \
+      memset(w, 0, sizeof(*w));                                                                                     \
+      cw_env_init<T>(*w, seed, (unsigned)e, dyn);                                                                   \
+      store(*w, st + (size_t)e * S_WORDS, sti + (size_t)e * I_WORDS);                                               \
+    }                                                                                                               \
+    delete w;                                                                                                       \
+  }                                                                                                                 \
+  extern "C" void emu_reset_##SUF(T *st, int *sti, int n, T *obs) {                                                 \
+    CassieWs<T> *w = new CassieWs<T>();                                                                             \
+    for (int e = 0; e < n; e++) {                                                                                   \
+      memset(w, 0, sizeof(*w));                                                                                     \
+      load(*w, st + (size_t)e * S_WORDS, sti + (size_t)e * I_WORDS);                                                \
+      cw_env_reset<T>(*w, obs + (size_t)e * CW_OBS);                                                                \
+      store(*w, st + (size_t)e * S_WORDS, sti + (size_t)e * I_WORDS);                                               \
+    }                                                                                                               \
+    delete w;                                                                                                       \
+  }                                                                                                                 \
+  extern "C" void emu_step_##SUF(T *st, int *sti, int n, const T *act, T *obs, T *rew, int *done, T *term_obs,      \
+                                 int max_traj_len) {                                                                \
+    CassieWs<T> *w = new CassieWs<T>();                                                                             \
+    for (int e = 0; e < n; e++) {                                                                                   \
+      memset(w, 0, sizeof(*w));                                                                                     \
+      load(*w, st + (size_t)e * S_WORDS, sti + (size_t)e * I_WORDS);                                                \
+      for (int k = 0; k < CW_ACT; k++) w->action[k] = act[(size_t)e * CW_ACT + k];                                  \
+      int dn;                                                                                                       \
+      cw_env_step<T>(*w, obs + (size_t)e * CW_OBS, rew + e, &dn);                                                   \
+      int flag = dn ? 1 : 0;                                                                                        \
+      if (!dn && max_traj_len > 0 && w->sti[I_TIME] >= max_traj_len) flag |= 2;                                     \
+      done[e] = flag;                                                                                               \
+      if (flag && max_traj_len > 0) {                                                                               \
+        if (term_obs) memcpy(term_obs + (size_t)e * CW_OBS, obs + (size_t)e * CW_OBS, sizeof(T) * CW_OBS);          \
+        cw_env_reset<T>(*w, obs + (size_t)e * CW_OBS);                                                              \
+      }                                                                                                             \
+      store(*w, st + (size_t)e * S_WORDS, sti + (size_t)e * I_WORDS);                                               \
+    }                                                                                                               \
+    delete w;                                                                                                       \
+  }                                                                                                                 \
+  /* one raw physics sub-step with a dump of the intermediate arrays (bring-up / parity of M, A, forces) */        \
+  extern "C" void emu_mjstep_##SUF(T *st, int *sti, int flags, T *M, T *A, T *f, T *qacc, int *nefc, int *ncon,     \
+                                   int *iters) {                                                                    \
+    CassieWs<T> *w = new CassieWs<T>();                                                                             \
+    memset(w, 0, sizeof(*w));                                                                                       \
+    load(*w, st, sti);                                                                                              \
+    cw_kinematics<T>(*w, w->st + S_QPOS);                                                                           \
+    cw_crb<T>(*w);                                                                                                  \
+    for (int i = 0; i < 32; i++)                                                                                    \
+      for (int j = 0; j < 32; j++) M[i * 32 + j] = i == j ? w->Mdiag[i] : (i < j ? w->M[i][j] : w->M[j][i]);        \
+    cw_mj_step<T>(*w, true, flags);                                                                                 \
+    for (int i = 0; i < CW_NEFC; i++) {                                                                             \
+      f[i] = w->efc_f[i];                                                                                           \
+      for (int j = 0; j < CW_NEFC; j++) A[i * CW_NEFC + j] = w->A[i][j];                                            \
+    }                                                                                                               \
+    for (int i = 0; i < 32; i++) qacc[i] = w->vec[V_QACC][i];                                                       \
+    *nefc = w->nefc; *ncon = w->ncon; *iters = w->solver_iter;                                                      \
+    store(*w, st, sti);                                                                                             \
+    delete w;                                                                                                       \
+  }
+
+DEFINE(double, f64)
+DEFINE(float, f32)
+
+extern "C" int emu_state_words(void) { return S_WORDS; }
+extern "C" int emu_istate_words(void) { return I_WORDS; }
+extern "C" int emu_ws_bytes(int f64) { return f64 ? (int)sizeof(CassieWs<double>) : (int)sizeof(CassieWs<float>); }
