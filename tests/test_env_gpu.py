@@ -1,0 +1,84 @@
+"""GPU parity: CUDA env kernels (through the C-ABI, via apex_b200.envs) against the CPU oracle on seeded inputs."""
+import numpy as np
+import pytest
+import torch
+
+from tests.oracle_util import OracleBatch
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(dtype, dyn, n=16, steps=12, seed=11):
+    from apex_b200.envs import BatchedCassieEnv
+    env = BatchedCassieEnv(n, dtype=dtype, seed=seed, dynamics_randomization=dyn)
+    ora = OracleBatch(n, seed, dyn)
+    o_g = env.reset().cpu().numpy().astype(np.float64)
+    o_c = ora.reset().copy()
+    rng = np.random.default_rng(3)
+    out = dict(reset=np.abs(o_g - o_c).max(), obs=[], rew=[], done_mismatch=0, ints=0)
+    for k in range(steps):
+        act = rng.normal(size=(n, 10)) * 0.3
+        og, rg, dg, _ = env.step(torch.as_tensor(act, dtype=dtype, device=env.device))
+        oc, rc, dc = ora.step(act)
+        og, rg, dg = og.cpu().numpy().astype(np.float64), rg.cpu().numpy().astype(np.float64), dg.cpu().numpy()
+        out["done_mismatch"] += int((dg != dc).sum())
+        out["obs"].append(np.linalg.norm(og - oc, axis=1) / np.linalg.norm(oc, axis=1))
+        out["rew"].append(np.abs(rg - rc))
+    return out, env
+
+
+def test_env_f64_matches_oracle():
+    """float64 kernel: integers (done flags, time counters, rng counters) bit-exact, floats <= 1e-8 relative."""
+    out, env = _run(torch.float64, dyn=False)
+    assert out["reset"] < 1e-10
+    assert out["done_mismatch"] == 0
+    assert np.max(out["obs"]) < 1e-8, np.max(out["obs"])
+    assert np.max(out["rew"]) < 1e-8
+
+
+def test_env_f64_dynrand_matches_oracle():
+    out, env = _run(torch.float64, dyn=True)
+    assert out["reset"] < 1e-10
+    assert out["done_mismatch"] == 0
+    assert np.max(out["obs"]) < 1e-8, np.max(out["obs"])
+    assert np.max(out["rew"]) < 1e-8
+
+
+def test_env_f32_one_step_close_to_oracle():
+    """float32 kernel from identical state: one env step (50 sub-steps).  qpos <= 1e-5 relative; observations are
+    limited by encoder quantisation (a one-count flip of a 13-bit drive encoder moves a velocity channel by 0.0416),
+    so the check is norm-wise 5e-2 on obs and 5e-3 absolute on reward."""
+    from apex_b200.envs import BatchedCassieEnv
+    n = 32
+    e64 = BatchedCassieEnv(n, dtype=torch.float64, seed=5, dynamics_randomization=False)
+    e32 = BatchedCassieEnv(n, dtype=torch.float32, seed=5, dynamics_randomization=False)
+    e64.reset(); e32.reset()
+    g = torch.Generator().manual_seed(0)
+    for k in range(10):
+        act = torch.randn((n, 10), generator=g) * 0.3
+        e32.st.copy_(e64.st.to(torch.float32)); e32.sti.copy_(e64.sti)
+        o64, r64, d64, _ = e64.step(act.double().cuda())
+        o32, r32, d32, _ = e32.step(act.cuda())
+        q64, q32 = e64.field("qpos", 35), e32.field("qpos", 35).double()
+        assert float(((q64 - q32).norm(dim=1) / q64.norm(dim=1)).max()) < 1e-5
+        same = (d64 == d32)
+        rel = ((o64 - o32.double()).norm(dim=1) / o64.norm(dim=1))[same]
+        assert float(rel.max()) < 5e-2, float(rel.max())
+        assert float((r64 - r32.double()).abs()[same].max()) < 5e-3
+
+
+def test_env_roundtrip_properties_full_size():
+    """4096 envs, float32: finite outputs, unit quaternions, obs clock on the unit circle, bounded reward."""
+    from apex_b200.envs import BatchedCassieEnv
+    n = 4096
+    env = BatchedCassieEnv(n, dtype=torch.float32, seed=1, dynamics_randomization=True)
+    obs = env.reset()
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for k in range(8):
+        act = torch.randn((n, 10), generator=g, device="cuda") * 0.2
+        obs, rew, done, _ = env.step(act)
+        assert torch.isfinite(obs).all() and torch.isfinite(rew).all()
+        q = env.field("qpos", 35)
+        assert float((q[:, 3:7].norm(dim=1) - 1).abs().max()) < 1e-4
+        assert float(((obs[:, 46] ** 2 + obs[:, 47] ** 2) - 1).abs().max()) < 1e-4
+        assert float(rew.max()) <= 1.0001 and float(rew.min()) > -0.5
