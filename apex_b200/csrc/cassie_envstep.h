@@ -18,7 +18,7 @@ CM_ARRAY double CW_NEUTRAL_FOOT[4] = {-0.24790886454547323, -0.24679713195445646
 CM_ARRAY double CW_CLOCK_Y[4][8] = {{-1, -1, 0, 0, 1, 1, 0, 0}, {1, 1, 0, 0, -1, -1, 0, 0}, {1, 1, 0, 0, -1, -1, 0, 0}, {-1, -1, 0, 0, 1, 1, 0, 0}};
 
 /* ---------- cassie_sim_step_pd ---------- */
-template <typename T> CW_FN void cw_sim_step_pd(CassieWs<T> &w CW_LANE_PARAM) {
+template <typename T> CW_NOINL void cw_sim_step_pd(CassieWs<T> &w CW_LANE_PARAM) {
   const int hasu = w.sti[I_HASU], dinit = w.sti[I_DRIVEINIT], jinit = w.sti[I_JOINTINIT];
   CW_FOR_LANES {
     if (lane < CM_NU) {
@@ -109,7 +109,7 @@ template <typename T> CW_FN T cw_clock_eval(const T *x, T P, int which, T phase)
 }
 
 /* ---------- observation (get_full_state), warp-uniform math, lanes store ---------- */
-template <typename T> CW_FN void cw_env_obs(CassieWs<T> &w, T *obs_out CW_LANE_PARAM) {
+template <typename T> CW_NOINL void cw_env_obs(CassieWs<T> &w, T *obs_out CW_LANE_PARAM) {
   const T oa = w.st[S_ORIENT];
   T sz, cz;
   cw_sincos<T>(oa / 2, &sz, &cz);

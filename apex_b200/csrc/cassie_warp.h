@@ -84,29 +84,33 @@ enum { Y_PPOS = 0, Y_QUAT = 3, Y_ROTVEL = 7, Y_TVEL = 10, Y_TACC = 13, Y_MPOS = 
 enum { V_SMOOTH = 0, V_QACCS = 1, V_Z = 2, V_G = 3, V_QACC = 4, V_TMP = 5, V_BIAS = 6, V_NVEC = 7 };
 
 template <typename T>
+struct CassieWsPre { /* scratch that is dead before the constraint matrix A is built */
+  T cand_dist[32], cand_pos[32][3], cand_n[32][3], cand_hint[32][3];
+  T cvel[CW_NB][6], cdd[CW_NV][6], cacc[CW_NB][6], cfrc[CW_NB][6];
+};
+template <typename T>
 struct CassieWs {
   T st[S_WORDS];
   int sti[I_WORDS];
   T xpos[CW_NB][3], xquat[CW_NB][4], xmat[CW_NB][9];
-  T cdof[CW_NV][6], cinert[CW_NB][10], crb[CW_NB][10];
-  T M[CW_NV][CW_NV + 1]; /* [j][i] j<i: mass matrix; [i][j] i>j: unit-lower factor L of M = L^T D L */
+  T cdof[CW_NV][6], crb[CW_NB][10]; /* crb: spatial inertia per body, turned into the composite inertia by cw_crb */
+  T M[CW_NV][CW_NV + 1]; /* [j][i] j<i: mass matrix; [k][j] k>j: U = D_k L[k][j] of M = L^T D L (unscaled rows) */
   T Mdiag[CW_NV], D[CW_NV], Dinv[CW_NV];
   T J[CW_NEFC][CW_NV + 1]; /* constraint Jacobian, later B = J L^-1 */
-  T A[CW_NEFC][CW_NEFC + 1];
-  T cvel[CW_NB][6], cdd[CW_NV][6], cacc[CW_NB][6];
+  union U {
+    T A[CW_NEFC][CW_NEFC + 1];
+    CassieWsPre<T> p;
+  } u;
   T efc_pos[CW_NEFC], efc_diag[CW_NEFC], efc_R[CW_NEFC], efc_jv[CW_NEFC], efc_K[CW_NEFC], efc_B[CW_NEFC], efc_imp[CW_NEFC];
-  T efc_aref[CW_NEFC], efc_b[CW_NEFC], efc_f[CW_NEFC], efc_res[CW_NEFC], efc_dinv[CW_NEFC];
+  T efc_b[CW_NEFC], efc_f[CW_NEFC], efc_res[CW_NEFC], efc_dinv[CW_NEFC];
   int efc_type[CW_NEFC];
   T vec[V_NVEC][CW_NV];
   T red[32];
   int ncon, nefc, solver_iter;
-  T cand_dist[32], cand_pos[32][3], cand_n[32][3], cand_hint[32][3];
   T con_pos[CW_NCON][3], con_frame[CW_NCON][9], con_dist[CW_NCON], con_mu[CW_NCON];
   int con_geom[CW_NCON], con_geom1[CW_NCON], con_dim[CW_NCON], con_adr[CW_NCON];
   T y[Y_WORDS];
-  T ucmd[CM_NU];
   T action[CW_ACT];
-  T footf[12];
 };
 
 /* ---------- scalar helpers ---------- */
@@ -118,6 +122,11 @@ CW_FN float cw_exp_o(float x) { return expf(x); }
 CW_FN double cw_exp_o(double x) { return exp(x); }
 CW_FN float cw_tan_o(float x) { return tanf(x); }
 CW_FN double cw_tan_o(double x) { return tan(x); }
+#ifdef __CUDA_ARCH__
+CW_FN int cw_ctz(unsigned m) { return __ffs((int)m) - 1; }
+#else
+CW_FN int cw_ctz(unsigned m) { return __builtin_ctz(m); }
+#endif
 template <typename T> CW_FN T cw_sqrt(T x) { return cw_sqrt_o(x); }
 template <typename T> CW_FN void cw_sincos(T x, T *s, T *c) { cw_sincos_o(x, s, c); }
 template <typename T> CW_FN T cw_exp(T x) { return cw_exp_o(x); }
@@ -184,16 +193,18 @@ CW_FN void cw_philox(uint32_t seed, uint32_t env_id, uint32_t ctr, uint32_t *out
 }
 template <typename T> CW_FN T cw_u01(uint32_t x) { return (T)(x >> 8) * (T)(1.0 / 16777216.0); }
 
+#include "cassie_gen.h"
+
 /* =====================================================================================================
  * position stage: kinematics, cdof, cinert (mj_kinematics + mj_comPos), lane = body, one tree level per phase
  * ===================================================================================================== */
-template <typename T> CW_FN void cw_kinematics(CassieWs<T> &w, const T *qpos CW_LANE_PARAM) {
+template <typename T> CW_NOINL void cw_kinematics(CassieWs<T> &w, const T *qpos CW_LANE_PARAM) {
   CW_FOR_LANES {
     if (lane == 0) {
       for (int k = 0; k < 3; k++) w.xpos[0][k] = 0;
       w.xquat[0][0] = 1; w.xquat[0][1] = w.xquat[0][2] = w.xquat[0][3] = 0;
       for (int k = 0; k < 9; k++) w.xmat[0][k] = (k % 4 == 0) ? (T)1 : (T)0;
-      for (int k = 0; k < 10; k++) w.cinert[0][k] = 0;
+      for (int k = 0; k < 10; k++) w.crb[0][k] = 0;
     } else if (lane == 1) { /* pelvis: three world slides (z has ref 1.01 = body z) + ball */
       T q[4] = {qpos[3], qpos[4], qpos[5], qpos[6]};
       cw_qnorm(q);
@@ -278,7 +289,7 @@ template <typename T> CW_FN void cw_kinematics(CassieWs<T> &w, const T *qpos CW_
       cw_mulv(c, R, ip);
       for (int k = 0; k < 3; k++) c[k] -= off[k]; /* xipos - org */
       const T mass = w.st[S_MASS + b], cc = cw_dot3(c, c);
-      T *I = w.cinert[b];
+      T *I = w.crb[b];
       I[0] = mass; I[1] = mass * c[0]; I[2] = mass * c[1]; I[3] = mass * c[2];
       I[4] = Iw[0] + mass * (cc - c[0] * c[0]);
       I[5] = Iw[4] + mass * (cc - c[1] * c[1]);
@@ -286,14 +297,13 @@ template <typename T> CW_FN void cw_kinematics(CassieWs<T> &w, const T *qpos CW_
       I[7] = Iw[1] - mass * c[0] * c[1];
       I[8] = Iw[2] - mass * c[0] * c[2];
       I[9] = Iw[5] - mass * c[1] * c[2];
-      for (int k = 0; k < 10; k++) w.crb[b][k] = I[k];
     }
   }
   CW_SYNC();
 }
 
 /* composite inertia (mj_crb): parents gather children, deepest level first; then M (lane = dof) */
-template <typename T> CW_FN void cw_crb(CassieWs<T> &w CW_LANE_PARAM) {
+template <typename T> CW_NOINL void cw_crb(CassieWs<T> &w CW_LANE_PARAM) {
   for (int lvl = CM_MAXLEVEL - 1; lvl >= 1; lvl--) {
     CW_FOR_LANES {
       if (lane < CW_NB && CM_body_level[lane] == lvl) {
@@ -322,9 +332,10 @@ template <typename T> CW_FN void cw_crb(CassieWs<T> &w CW_LANE_PARAM) {
   CW_SYNC();
 }
 
-/* sparse L^T D L (mj_factorM): M = L^T D L, L unit lower with the sparsity of the dof tree.
- * hdamp = 0: factor M; hdamp = h: factor M + h diag(damping) (mj_Euler's implicit damping). */
-template <typename T> CW_FN void cw_factor(CassieWs<T> &w, T hdamp, bool recopy CW_LANE_PARAM) {
+/* sparse L^T D L (mj_factorM): M = L^T D L with the sparsity of the dof tree; rows are kept unscaled
+ * (w.M[k][j] = D_k L[k][j]), w.Dinv[k] = 1/D_k.  hdamp = 0: factor M; hdamp = h: factor M + h diag(damping)
+ * (mj_Euler's implicit damping).  The elimination itself is generated straight-line code (cassie_gen.h). */
+template <typename T> CW_NOINL void cw_factor(CassieWs<T> &w, T hdamp, bool recopy CW_LANE_PARAM) {
   CW_FOR_LANES {
     const int i = lane;
     w.D[i] = w.Mdiag[i] + hdamp * w.st[S_DAMPING + i];
@@ -334,56 +345,74 @@ template <typename T> CW_FN void cw_factor(CassieWs<T> &w, T hdamp, bool recopy 
     }
   }
   CW_SYNC();
-  for (int k = CW_NV - 1; k >= 0; k--) {
-    const int na = CM_dof_nanc[k];
-    const T dinv = (T)1 / w.D[k];
-    const unsigned mask = CM_dof_ancmask[k];
-    if (na > 0) {
-      CW_FOR_LANES {
-        if ((mask >> lane) & 1u) {
-          const T a = w.M[k][lane] * dinv;
-          for (int t = 0; t < na; t++) {
-            const int j = CM_dof_anc[k][t];
-            if (j > lane) break;
-            if (j < lane) w.M[lane][j] -= a * w.M[k][j];
-            else w.D[lane] -= a * w.M[k][lane];
+  /* the two legs are independent sub-trees hanging off the 6 base dofs: eliminate dof 6+s and 19+s together */
+  for (int s = 12; s >= 0; s--) {
+    const int kL = 6 + s, kR = 19 + s;
+    const unsigned legmask = CM_leg_ancmask[s];
+    const T dL = (T)1 / w.D[kL], dR = (T)1 / w.D[kR];
+    CW_FOR_LANES {
+      if (lane == 0) { w.Dinv[kL] = dL; w.Dinv[kR] = dR; }
+      if (lane >= 6) {
+        const bool rt = lane >= 19;
+        const int off = rt ? 13 : 0, ll = lane - off;
+        if ((legmask >> ll) & 1u) {
+          const T *rk = rt ? w.M[kR] : w.M[kL];
+          T *rl = w.M[lane];
+          const T a = rk[lane] * (rt ? dR : dL);
+          rl[0] -= a * rk[0]; rl[1] -= a * rk[1]; rl[2] -= a * rk[2];
+          rl[3] -= a * rk[3]; rl[4] -= a * rk[4]; rl[5] -= a * rk[5];
+          unsigned m = legmask & ((1u << ll) - 1u);
+          while (m) {
+            const int j = cw_ctz(m) + off;
+            m &= m - 1u;
+            rl[j] -= a * rk[j];
           }
+          w.D[lane] -= a * rk[lane];
         }
+      } else {
+        const T aL = w.M[kL][lane] * dL, aR = w.M[kR][lane] * dR;
+        for (int j = 0; j < lane; j++) w.M[lane][j] -= aL * w.M[kL][j] + aR * w.M[kR][j];
+        w.D[lane] -= aL * w.M[kL][lane] + aR * w.M[kR][lane];
       }
-      CW_SYNC();
-      CW_FOR_LANES {
-        if ((mask >> lane) & 1u) w.M[k][lane] *= dinv;
-        if (lane == 0) w.Dinv[k] = dinv;
-      }
-      CW_SYNC();
-    } else {
-      CW_FOR_LANES { if (lane == 0) w.Dinv[k] = dinv; }
-      CW_SYNC();
     }
+    CW_SYNC();
+  }
+  for (int k = 5; k >= 1; k--) {
+    const T d = (T)1 / w.D[k];
+    CW_FOR_LANES {
+      if (lane == 0) w.Dinv[k] = d;
+      if (lane < k) {
+        const T a = w.M[k][lane] * d;
+        for (int j = 0; j < lane; j++) w.M[lane][j] -= a * w.M[k][j];
+        w.D[lane] -= a * w.M[k][lane];
+      }
+    }
+    CW_SYNC();
+  }
+  {
+    const T d = (T)1 / w.D[0];
+    CW_FOR_LANES { if (lane == 0) w.Dinv[0] = d; }
+    CW_SYNC();
   }
 }
 
 /* v <- L^-T v (in place, shared vector) */
-template <typename T> CW_FN void cw_solve_LT(CassieWs<T> &w, T *v CW_LANE_PARAM) {
+template <typename T> CW_NOINL void cw_solve_LT(CassieWs<T> &w, T *v CW_LANE_PARAM) {
   for (int k = CW_NV - 1; k >= 1; k--) {
     const unsigned mask = CM_dof_ancmask[k];
-    const T vk = v[k];
+    const T vk = v[k] * w.Dinv[k];
     CW_FOR_LANES { if ((mask >> lane) & 1u) v[lane] -= w.M[k][lane] * vk; }
     CW_SYNC();
   }
 }
 /* v <- L^-1 v: every dof has exactly one ancestor per depth, so 13 level sweeps suffice */
-template <typename T> CW_FN void cw_solve_L(CassieWs<T> &w, T *v CW_LANE_PARAM) {
+template <typename T> CW_NOINL void cw_solve_L(CassieWs<T> &w, T *v CW_LANE_PARAM) {
   for (int lvl = 0; lvl < CM_MAXANC; lvl++) {
     CW_FOR_LANES {
-      if (CM_dof_nanc[lane] > lvl) { const int j = CM_dof_anc[lane][lvl]; v[lane] -= w.M[lane][j] * v[j]; }
+      if (CM_dof_nanc[lane] > lvl) { const int j = CM_dof_anc[lane][lvl]; v[lane] -= w.M[lane][j] * w.Dinv[lane] * v[j]; }
     }
     CW_SYNC();
   }
-}
-template <typename T> CW_FN void cw_scale_Dinv(CassieWs<T> &w, T *v CW_LANE_PARAM) {
-  CW_FOR_LANES { v[lane] *= w.Dinv[lane]; }
-  CW_SYNC();
 }
 
 /* translational Jacobian column of a point (offset from org) on body b for dof = lane */
@@ -428,9 +457,9 @@ CM_ARRAY int CW_CAND_END[17] = {1, -1, 1, -1, 1, -1, 1, -1, 1, -1, 1, -1, 1, -1,
 CM_ARRAY int CW_PAIR_G1[9] = {2, 2, 2, 3, 3, 3, 4, 4, 4};
 CM_ARRAY int CW_PAIR_G2[9] = {6, 7, 8, 6, 7, 8, 6, 7, 8};
 
-template <typename T> CW_FN void cw_collision(CassieWs<T> &w CW_LANE_PARAM) {
+template <typename T> CW_NOINL void cw_collision(CassieWs<T> &w CW_LANE_PARAM) {
   CW_FOR_LANES {
-    w.cand_dist[lane] = 1;
+    w.u.p.cand_dist[lane] = 1;
     if (lane < 17) {
       const int g = CW_CAND_GEOM[lane];
       T fq[4] = {w.st[S_FLOORQ], w.st[S_FLOORQ + 1], w.st[S_FLOORQ + 2], w.st[S_FLOORQ + 3]}, Rf[9];
@@ -441,11 +470,11 @@ template <typename T> CW_FN void cw_collision(CassieWs<T> &w CW_LANE_PARAM) {
       T pc[3] = {c[0] + hl * ax[0], c[1] + hl * ax[1], c[2] + hl * ax[2]};
       T rel[3] = {pc[0], pc[1], pc[2] - (T)CM_FLOOR_Z};
       const T dist = cw_dot3(rel, n) - r;
-      w.cand_dist[lane] = dist;
+      w.u.p.cand_dist[lane] = dist;
       for (int k = 0; k < 3; k++) {
-        w.cand_pos[lane][k] = pc[k] - n[k] * (r + (T)0.5 * dist);
-        w.cand_n[lane][k] = n[k];
-        w.cand_hint[lane][k] = CW_CAND_END[lane] != 0 ? ax[k] : (T)0;
+        w.u.p.cand_pos[lane][k] = pc[k] - n[k] * (r + (T)0.5 * dist);
+        w.u.p.cand_n[lane][k] = n[k];
+        w.u.p.cand_hint[lane][k] = CW_CAND_END[lane] != 0 ? ax[k] : (T)0;
       }
     } else if (lane < 26) {
       const int g1 = CW_PAIR_G1[lane - 17], g2 = CW_PAIR_G2[lane - 17];
@@ -465,13 +494,13 @@ template <typename T> CW_FN void cw_collision(CassieWs<T> &w CW_LANE_PARAM) {
       for (int k = 0; k < 3; k++) { p1[k] = c1[k] + ss * a1[k]; nn[k] = c2[k] + tt * a2[k] - p1[k]; }
       const T len = cw_sqrt<T>(cw_dot3(nn, nn)), dist = len - r1 - r2;
       if (dist < 0 && len > (T)1e-15) {
-        w.cand_dist[lane] = dist;
+        w.u.p.cand_dist[lane] = dist;
         const T inv = (T)1 / len;
         for (int k = 0; k < 3; k++) {
           nn[k] *= inv;
-          w.cand_pos[lane][k] = p1[k] + nn[k] * (r1 + (T)0.5 * dist);
-          w.cand_n[lane][k] = nn[k];
-          w.cand_hint[lane][k] = 0;
+          w.u.p.cand_pos[lane][k] = p1[k] + nn[k] * (r1 + (T)0.5 * dist);
+          w.u.p.cand_n[lane][k] = nn[k];
+          w.u.p.cand_hint[lane][k] = 0;
         }
       }
     }
@@ -480,14 +509,14 @@ template <typename T> CW_FN void cw_collision(CassieWs<T> &w CW_LANE_PARAM) {
   /* uniform compaction in priority order */
   int nc = 0;
   for (int s = 0; s < 26 && nc < CW_NCON; s++) {
-    if (w.cand_dist[s] < 0) {
+    if (w.u.p.cand_dist[s] < 0) {
       CW_FOR_LANES {
         if (lane == 0) {
           T fr[9];
-          for (int k = 0; k < 3; k++) { w.con_pos[nc][k] = w.cand_pos[s][k]; fr[k] = w.cand_n[s][k]; fr[3 + k] = w.cand_hint[s][k]; fr[6 + k] = 0; }
+          for (int k = 0; k < 3; k++) { w.con_pos[nc][k] = w.u.p.cand_pos[s][k]; fr[k] = w.u.p.cand_n[s][k]; fr[3 + k] = w.u.p.cand_hint[s][k]; fr[6 + k] = 0; }
           cw_make_frame(fr);
           for (int k = 0; k < 9; k++) w.con_frame[nc][k] = fr[k];
-          w.con_dist[nc] = w.cand_dist[s];
+          w.con_dist[nc] = w.u.p.cand_dist[s];
           if (s < 17) { w.con_geom[nc] = CW_CAND_GEOM[s]; w.con_geom1[nc] = -1; w.con_dim[nc] = 3; w.con_mu[nc] = w.st[S_FRICTION]; }
           else { w.con_geom[nc] = CW_PAIR_G2[s - 17]; w.con_geom1[nc] = CW_PAIR_G1[s - 17]; w.con_dim[nc] = 1; w.con_mu[nc] = 0; }
           w.con_adr[nc] = -1;
@@ -502,7 +531,7 @@ template <typename T> CW_FN void cw_collision(CassieWs<T> &w CW_LANE_PARAM) {
 
 /* mj_makeConstraint: rows of J (lane = dof column), efc_pos / efc_diag / efc_type per row */
 CM_ARRAY int CW_LIM_JNT[16] = {4, 5, 6, 8, 9, 10, 12, 14, 15, 16, 17, 19, 20, 21, 23, 25};
-template <typename T> CW_FN void cw_make_constraint(CassieWs<T> &w, const T *qpos, int flags CW_LANE_PARAM) {
+template <typename T> CW_NOINL void cw_make_constraint(CassieWs<T> &w, const T *qpos, int flags CW_LANE_PARAM) {
   int r = 0;
   const T org[3] = {w.xpos[1][0], w.xpos[1][1], w.xpos[1][2]};
   if (!(flags & 1)) {
@@ -605,27 +634,34 @@ template <typename T> CW_FN void cw_make_constraint(CassieWs<T> &w, const T *qpo
   CW_SYNC();
 }
 
-/* B = J L^-1 (each row: y <- L^-T y, lane = row) then A = B D^-1 B^T + diag(R) (mj_projectConstraint) */
-template <typename T> CW_FN void cw_half_solve_rows(CassieWs<T> &w, int n CW_LANE_PARAM) {
+/* B = J L^-1 (each row: y <- L^-T y in registers, lane = row) then A = B D^-1 B^T + diag(R) (mj_projectConstraint) */
+template <typename T> CW_NOINL void cw_half_solve_rows(CassieWs<T> &w, int n CW_LANE_PARAM) {
   for (int pass = 0; pass * 32 < n; pass++) {
     CW_FOR_LANES {
       const int row = pass * 32 + lane;
       if (row < n) {
-        T *y = w.J[row];
-        for (int k = CW_NV - 1; k >= 1; k--) {
-          const T yk = y[k];
-          const int na = CM_dof_nanc[k];
-          for (int t = 0; t < na; t++) { const int j = CM_dof_anc[k][t]; y[j] -= w.M[k][j] * yk; }
-        }
+        T y[CW_NV];
+        for (int i = 0; i < CW_NV; i++) y[i] = w.J[row][i];
+        cw_half_solve_regs<T>(w, y);
+        for (int i = 0; i < CW_NV; i++) w.J[row][i] = y[i];
       }
     }
   }
   CW_SYNC();
 }
-template <typename T> CW_FN void cw_project(CassieWs<T> &w CW_LANE_PARAM) {
+template <typename T> CW_NOINL void cw_project(CassieWs<T> &w CW_LANE_PARAM) {
   const int n = w.nefc;
-  cw_half_solve_rows<T>(w, n CW_LANE_ARG);
   for (int pass = 0; pass * 32 < n; pass++) {
+    CW_FOR_LANES {
+      const int c = pass * 32 + lane;
+      if (c < n) {
+        T y[CW_NV];
+        for (int i = 0; i < CW_NV; i++) y[i] = w.J[c][i];
+        cw_half_solve_regs<T>(w, y);
+        for (int i = 0; i < CW_NV; i++) w.J[c][i] = y[i];
+      }
+    }
+    CW_SYNC();
     CW_FOR_LANES {
       const int c = pass * 32 + lane;
       if (c < n) {
@@ -634,30 +670,21 @@ template <typename T> CW_FN void cw_project(CassieWs<T> &w CW_LANE_PARAM) {
         for (int rr = 0; rr <= c; rr++) {
           T s = 0;
           for (int i = 0; i < CW_NV; i++) s += w.J[rr][i] * bs[i];
-          if (rr == c) s += w.efc_R[c];
-          w.A[rr][c] = s;
-          w.A[c][rr] = s;
+          if (rr == c) { s += w.efc_R[c]; w.efc_dinv[c] = (T)1 / s; }
+          w.u.A[rr][c] = s;
+          w.u.A[c][rr] = s;
         }
-        w.efc_dinv[c] = 0; /* set below once the diagonal is final */
       }
     }
+    CW_SYNC();
   }
-  CW_SYNC();
-  for (int pass = 0; pass * 32 < n; pass++) {
-    CW_FOR_LANES {
-      const int c = pass * 32 + lane;
-      if (c < n) w.efc_dinv[c] = (T)1 / w.A[c][c];
-    }
-  }
-  CW_SYNC();
 }
-
 /* velocity stage: mj_comVel + mj_rne (bias), lane = body, level by level */
-template <typename T> CW_FN void cw_rne(CassieWs<T> &w, const T *qvel CW_LANE_PARAM) {
+template <typename T> CW_NOINL void cw_rne(CassieWs<T> &w, const T *qvel CW_LANE_PARAM) {
   CW_FOR_LANES {
     if (lane == 0) {
-      for (int k = 0; k < 6; k++) { w.cvel[0][k] = 0; w.cacc[0][k] = 0; }
-      w.cacc[0][5] = (T)(-CM_GRAVITY_Z);
+      for (int k = 0; k < 6; k++) { w.u.p.cvel[0][k] = 0; w.u.p.cacc[0][k] = 0; }
+      w.u.p.cacc[0][5] = (T)(-CM_GRAVITY_Z);
     }
   }
   CW_SYNC();
@@ -666,7 +693,7 @@ template <typename T> CW_FN void cw_rne(CassieWs<T> &w, const T *qvel CW_LANE_PA
       if (lane < CW_NB && CM_body_level[lane] == lvl) {
         const int b = lane, p = CM_body_parent[b];
         T v[6], a[6];
-        for (int k = 0; k < 6; k++) { v[k] = w.cvel[p][k]; a[k] = w.cacc[p][k]; }
+        for (int k = 0; k < 6; k++) { v[k] = w.u.p.cvel[p][k]; a[k] = w.u.p.cacc[p][k]; }
         const int da = CM_body_dofadr[b], nd = CM_body_dofnum[b];
         /* pelvis: slides one at a time, then the ball (all three cdof_dot from the pre-ball velocity) */
         int d0 = 0;
@@ -674,25 +701,25 @@ template <typename T> CW_FN void cw_rne(CassieWs<T> &w, const T *qvel CW_LANE_PA
           const int grp = (nd - d0 >= 3 && !(b == 1 && d0 < 3)) ? 3 : 1;
           for (int s = 0; s < grp; s++) {
             const T *cd = w.cdof[da + d0 + s];
-            T *o = w.cdd[da + d0 + s];
+            T *o = w.u.p.cdd[da + d0 + s];
             T t1[3], t2[3], t3[3];
             cw_cross(t1, v, cd); cw_cross(t2, v, cd + 3); cw_cross(t3, v + 3, cd);
             for (int k = 0; k < 3; k++) { o[k] = t1[k]; o[3 + k] = t2[k] + t3[k]; }
           }
           for (int s = 0; s < grp; s++) {
             const T qd = qvel[da + d0 + s];
-            for (int k = 0; k < 6; k++) { v[k] += w.cdof[da + d0 + s][k] * qd; a[k] += w.cdd[da + d0 + s][k] * qd; }
+            for (int k = 0; k < 6; k++) { v[k] += w.cdof[da + d0 + s][k] * qd; a[k] += w.u.p.cdd[da + d0 + s][k] * qd; }
           }
           d0 += grp;
         }
-        for (int k = 0; k < 6; k++) { w.cvel[b][k] = v[k]; }
-        /* cfrc_body = I a + v x* (I v), stored over cacc after the children have read it: use crb as scratch */
+        for (int k = 0; k < 6; k++) { w.u.p.cvel[b][k] = v[k]; }
+        /* cfrc_body = I a + v x* (I v); w.crb still holds the per-body (not yet composite) inertia here */
         T f[6], iv[6], t1[3], t2[3], t3[3];
-        cw_inert_mul(f, w.cinert[b], a);
-        cw_inert_mul(iv, w.cinert[b], v);
+        cw_inert_mul(f, w.crb[b], a);
+        cw_inert_mul(iv, w.crb[b], v);
         cw_cross(t1, v, iv); cw_cross(t2, v + 3, iv + 3); cw_cross(t3, v, iv + 3);
         for (int k = 0; k < 3; k++) { f[k] += t1[k] + t2[k]; f[3 + k] += t3[k]; }
-        for (int k = 0; k < 6; k++) { w.cacc[b][k] = a[k]; w.crb[b][k] = f[k]; }
+        for (int k = 0; k < 6; k++) { w.u.p.cacc[b][k] = a[k]; w.u.p.cfrc[b][k] = f[k]; }
       }
     }
     CW_SYNC();
@@ -703,13 +730,13 @@ template <typename T> CW_FN void cw_rne(CassieWs<T> &w, const T *qvel CW_LANE_PA
         const int nc = CM_body_nchild[lane];
         for (int c = 0; c < nc; c++) {
           const int ch = CM_body_child[lane][c];
-          for (int k = 0; k < 6; k++) w.crb[lane][k] += w.crb[ch][k];
+          for (int k = 0; k < 6; k++) w.u.p.cfrc[lane][k] += w.u.p.cfrc[ch][k];
         }
       }
     }
     CW_SYNC();
   }
-  CW_FOR_LANES { w.vec[V_BIAS][lane] = cw_dot6(w.cdof[lane], w.crb[CM_dof_body[lane]]); }
+  CW_FOR_LANES { w.vec[V_BIAS][lane] = cw_dot6(w.cdof[lane], w.u.p.cfrc[CM_dof_body[lane]]); }
   CW_SYNC();
 }
 
@@ -744,11 +771,11 @@ template <typename T> CW_NOINL void cw_mj_step(CassieWs<T> &w, bool integrate, i
   const T h = (T)CM_TIMESTEP;
   /* ---- step1 ---- */
   cw_kinematics<T>(w, qpos CW_LANE_ARG);
+  cw_rne<T>(w, qvel CW_LANE_ARG); /* before cw_crb: it reads the per-body inertias */
   cw_crb<T>(w CW_LANE_ARG);
   cw_factor<T>(w, (T)0, false CW_LANE_ARG);
   cw_collision<T>(w CW_LANE_ARG);
   cw_make_constraint<T>(w, qpos, flags CW_LANE_ARG);
-  cw_rne<T>(w, qvel CW_LANE_ARG);
   const int n = w.nefc;
   /* sensors (positions / velocities) for the next wrapper call */
   CW_FOR_LANES {
@@ -789,8 +816,7 @@ template <typename T> CW_NOINL void cw_mj_step(CassieWs<T> &w, bool integrate, i
   CW_FOR_LANES { w.vec[V_Z][lane] = w.vec[V_SMOOTH][lane]; }
   CW_SYNC();
   cw_solve_LT<T>(w, w.vec[V_Z] CW_LANE_ARG);
-  cw_scale_Dinv<T>(w, w.vec[V_Z] CW_LANE_ARG);
-  CW_FOR_LANES { w.vec[V_QACCS][lane] = w.vec[V_Z][lane]; }
+  CW_FOR_LANES { w.vec[V_Z][lane] *= w.Dinv[lane]; w.vec[V_QACCS][lane] = w.vec[V_Z][lane]; }
   CW_SYNC();
   cw_solve_L<T>(w, w.vec[V_QACCS] CW_LANE_ARG);
   /* ---- constraints ---- */
@@ -802,8 +828,9 @@ template <typename T> CW_NOINL void cw_mj_step(CassieWs<T> &w, bool integrate, i
     CW_FOR_LANES {
       const int i = lane, na = CM_dof_nanc[i];
       T s = w.st[S_QACC_WS + i];
-      for (int t = 0; t < na; t++) { const int j = CM_dof_anc[i][t]; s += w.M[i][j] * w.st[S_QACC_WS + j]; }
-      w.vec[V_TMP][i] = s;
+      T acc = 0;
+      for (int t = 0; t < na; t++) { const int j = CM_dof_anc[i][t]; acc += w.M[i][j] * w.st[S_QACC_WS + j]; }
+      w.vec[V_TMP][i] = s + acc * w.Dinv[i];
     }
     CW_SYNC();
     for (int pass = 0; pass * 32 < n; pass++) {
@@ -813,7 +840,6 @@ template <typename T> CW_NOINL void cw_mj_step(CassieWs<T> &w, bool integrate, i
           T ja = 0, jw = 0;
           for (int i = 0; i < CW_NV; i++) { ja += w.J[row][i] * w.vec[V_Z][i]; jw += w.J[row][i] * w.vec[V_TMP][i]; }
           const T aref = -w.efc_B[row] * w.efc_jv[row] - w.efc_K[row] * w.efc_imp[row] * w.efc_pos[row];
-          w.efc_aref[row] = aref;
           w.efc_b[row] = ja - aref;
           T f = -(jw - aref) / w.efc_R[row];
           if (w.efc_type[row] != 0 && f < 0) f = 0;
@@ -830,7 +856,7 @@ template <typename T> CW_NOINL void cw_mj_step(CassieWs<T> &w, bool integrate, i
         T part = 0;
         if (row < n) {
           T s = 0;
-          for (int c = 0; c < n; c++) s += w.A[row][c] * w.efc_f[c];
+          for (int c = 0; c < n; c++) s += w.u.A[row][c] * w.efc_f[c];
           w.efc_res[row] = s + w.efc_b[row];
           part = w.efc_f[row] * ((T)0.5 * s + w.efc_b[row]);
         }
@@ -851,6 +877,47 @@ template <typename T> CW_NOINL void cw_mj_step(CassieWs<T> &w, bool integrate, i
     }
     /* PGS sweeps (mj_solPGS): residual-update form, rows in order */
     const T scale = (T)1 / (w.st[S_MEANINERTIA] * (T)CW_NV);
+#ifdef __CUDA_ARCH__
+    { /* device path: rows lane and lane+32 live in registers; the row owner computes the update, one shuffle
+       * broadcasts it, every lane applies column i of A to its two residual slots */
+      const bool v0 = lane < n, v1 = lane + 32 < n;
+      T res0 = v0 ? w.efc_res[lane] : (T)0, res1 = v1 ? w.efc_res[lane + 32] : (T)0;
+      T f0 = v0 ? w.efc_f[lane] : (T)0, f1 = v1 ? w.efc_f[lane + 32] : (T)0;
+      const T di0 = v0 ? w.efc_dinv[lane] : (T)0, di1 = v1 ? w.efc_dinv[lane + 32] : (T)0;
+      const T ad0 = v0 ? w.u.A[lane][lane] : (T)0, ad1 = v1 ? w.u.A[lane + 32][lane + 32] : (T)0;
+      const bool in0 = v0 && w.efc_type[lane] != 0, in1 = v1 && w.efc_type[lane + 32] != 0;
+      for (int it = 0; it < CM_ITERATIONS; it++) {
+        T imp = 0;
+        const int n0 = n < 32 ? n : 32;
+        for (int i = 0; i < n0; i++) {
+          const T a0 = w.u.A[i][lane], a1 = v1 ? w.u.A[i][lane + 32] : (T)0;
+          T nf = f0 - res0 * di0;
+          if (in0 && nf < 0) nf = 0;
+          const T dlo = nf - f0;
+          const T dl = __shfl_sync(0xffffffffu, dlo, i);
+          if (lane == i) { imp -= (T)0.5 * dl * dl * ad0 + dl * res0; f0 = nf; }
+          res0 += dl * a0;
+          res1 += dl * a1;
+        }
+        for (int i = 32; i < n; i++) {
+          const T a0 = w.u.A[i][lane], a1 = v1 ? w.u.A[i][lane + 32] : (T)0;
+          T nf = f1 - res1 * di1;
+          if (in1 && nf < 0) nf = 0;
+          const T dlo = nf - f1;
+          const T dl = __shfl_sync(0xffffffffu, dlo, i - 32);
+          if (lane == i - 32) { imp -= (T)0.5 * dl * dl * ad1 + dl * res1; f1 = nf; }
+          res0 += dl * a0;
+          res1 += dl * a1;
+        }
+        for (int o = 16; o > 0; o >>= 1) imp += __shfl_xor_sync(0xffffffffu, imp, o);
+        iters = it + 1;
+        if (imp * scale < (T)1e-8) break;
+      }
+      if (v0) w.efc_f[lane] = f0;
+      if (v1) w.efc_f[lane + 32] = f1;
+      __syncwarp();
+    }
+#else
     for (int it = 0; it < CM_ITERATIONS; it++) {
       T improvement = 0;
       for (int i = 0; i < n; i++) {
@@ -859,19 +926,18 @@ template <typename T> CW_NOINL void cw_mj_step(CassieWs<T> &w, bool integrate, i
         if (w.efc_type[i] != 0 && nf < 0) nf = 0;
         const T dl = nf - old;
         if (dl != 0) {
-          improvement -= (T)0.5 * dl * dl * w.A[i][i] + dl * res;
-          CW_SYNC();
+          improvement -= (T)0.5 * dl * dl * w.u.A[i][i] + dl * res;
+          w.efc_f[i] = nf;
           CW_FOR_LANES {
-            if (lane == 0) w.efc_f[i] = nf;
-            if (lane < n) w.efc_res[lane] += dl * w.A[i][lane];
-            if (lane + 32 < n) w.efc_res[lane + 32] += dl * w.A[i][lane + 32];
+            if (lane < n) w.efc_res[lane] += dl * w.u.A[i][lane];
+            if (lane + 32 < n) w.efc_res[lane + 32] += dl * w.u.A[i][lane + 32];
           }
-          CW_SYNC();
         }
       }
       iters = it + 1;
       if (improvement * scale < (T)1e-8) break;
     }
+#endif
     /* g = B^T f */
     CW_FOR_LANES {
       T s = 0;
@@ -908,13 +974,14 @@ template <typename T> CW_NOINL void cw_mj_step(CassieWs<T> &w, bool integrate, i
     const int j = lane;
     T s = w.vec[V_G][j];
     for (int i = j + 1; i < CW_NV; i++)
-      if ((CM_dof_ancmask[i] >> j) & 1u) s += w.M[i][j] * w.vec[V_G][i];
+      if ((CM_dof_ancmask[i] >> j) & 1u) s += w.M[i][j] * w.Dinv[i] * w.vec[V_G][i];
     w.vec[V_TMP][j] = s + w.vec[V_SMOOTH][j];
   }
   CW_SYNC();
   cw_factor<T>(w, h, true CW_LANE_ARG);
   cw_solve_LT<T>(w, w.vec[V_TMP] CW_LANE_ARG);
-  cw_scale_Dinv<T>(w, w.vec[V_TMP] CW_LANE_ARG);
+  CW_FOR_LANES { w.vec[V_TMP][lane] *= w.Dinv[lane]; }
+  CW_SYNC();
   cw_solve_L<T>(w, w.vec[V_TMP] CW_LANE_ARG);
   CW_FOR_LANES {
     qvel[lane] += h * w.vec[V_TMP][lane];

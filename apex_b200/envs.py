@@ -11,7 +11,7 @@ All tensors stay on the GPU; the physics, PD loop, reward and observation run in
 import numpy as np
 import torch
 
-from . import lib as _lib
+from . import _capi as _lib
 
 _DT = {torch.float32: 0, torch.float64: 1}
 

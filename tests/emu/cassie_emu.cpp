@@ -67,7 +67,7 @@ template <typename T> static void store(const CassieWs<T> &w, T *st, int *sti) {
     cw_mj_step<T>(*w, true, flags);                                                                                 \
     for (int i = 0; i < CW_NEFC; i++) {                                                                             \
       f[i] = w->efc_f[i];                                                                                           \
-      for (int j = 0; j < CW_NEFC; j++) A[i * CW_NEFC + j] = w->A[i][j];                                            \
+      for (int j = 0; j < CW_NEFC; j++) A[i * CW_NEFC + j] = w->u.A[i][j];                                            \
     }                                                                                                               \
     for (int i = 0; i < 32; i++) qacc[i] = w->vec[V_QACC][i];                                                       \
     *nefc = w->nefc; *ncon = w->ncon; *iters = w->solver_iter;                                                      \

@@ -359,6 +359,40 @@ def emit(m):
     return ''.join(o)
 
 
+def emit_gen(m):
+    """Straight-line code for the sparse L^T D L factorisation and the row half-solve (indices are compile-time)."""
+    D = m.dofs
+    nv = m.nv
+    anc = []
+    for i in range(nv):
+        ch = []
+        p = D[i]['parent']
+        while p >= 0:
+            ch.append(p)
+            p = D[p]['parent']
+        anc.append(ch[::-1])
+    o = ['/* GENERATED by tools/gen_model.py — do not edit.  Unrolled tree-sparse kernels for the Cassie dof tree.\n'
+         ' * Storage convention: w.M[k][j] (k>j) holds U = D_k * L[k][j] (unscaled factor rows), w.Dinv[k] = 1/D_k. */\n'
+         '#ifndef CASSIE_GEN_H\n#define CASSIE_GEN_H\n']
+    # ---- leg-ancestor masks for the two-legs-at-once factorisation (bit = left-leg dof index) ----
+    masks = []
+    for s_ in range(13):
+        kL, kR = 6 + s_, 19 + s_
+        assert [a + 13 if a >= 6 else a for a in anc[kL]] == anc[kR]
+        masks.append(sum(1 << a for a in anc[kL] if a >= 6))
+    o.append('CM_ARRAY unsigned CM_leg_ancmask[13] = {' + ', '.join(f'{x}u' for x in masks) + '};\n\n')
+    # ---- half solve: y <- L^-T y with y in registers ----
+    o.append('/* y <- L^-T y for one row held in registers (all indices compile-time) */\n')
+    o.append('template <typename T> CW_FN void cw_half_solve_regs(const CassieWs<T> &w, T *y) {\n')
+    for k in range(nv - 1, 0, -1):
+        o.append(f'  {{ const T s = y[{k}] * w.Dinv[{k}];')
+        for j in anc[k]:
+            o.append(f' y[{j}] -= w.M[{k}][{j}] * s;')
+        o.append(' }\n')
+    o.append('}\n#endif\n')
+    return ''.join(o)
+
+
 INIT_QPOS = [0.0, 0.0, 1.01, 1.0, 0.0, 0.0, 0.0, 0.0045, 0.0, 0.4973, 0.9785, -0.0164, 0.01787, -0.2049, -1.1997, 0.0,
              1.4267, 0.0, -1.5244, 1.5244, -1.5968, -0.0045, 0.0, 0.4973, 0.9786, 0.00386, -0.01524, -0.2051, -1.1997,
              0.0, 1.4267, 0.0, -1.5244, 1.5244, -1.5968]
@@ -369,4 +403,7 @@ if __name__ == '__main__':
     for out in sys.argv[2:]:
         with open(out, 'w') as f:
             f.write(text)
+    import os
+    with open(os.path.join(os.path.dirname(sys.argv[2]), 'cassie_gen.h'), 'w') as f:
+        f.write(emit_gen(mdl))
     print(f'nbody={mdl.nbody} nq={mdl.nq} nv={mdl.nv} njnt={mdl.njnt} ngeom={len(mdl.geoms)}')
