@@ -183,20 +183,20 @@ template <typename T> CW_NOINL void cw_set_const(CassieWs<T> &w CW_LANE_PARAM) {
   CW_FOR_LANES {
     T s = 0;
     for (int k = 0; k < CW_NV; k++) s += w.J[lane][k] * w.J[lane][k] * w.Dinv[k];
-    w.red[lane] = s;
+    w.vec[V_TMP][lane] = s;
   }
   CW_SYNC();
   CW_FOR_LANES {
     const int j = CM_dof_jnt[lane];
-    T v = w.red[lane];
-    if (CM_jnt_type[j] == 2) { const int da = CM_jnt_dofadr[j]; v = (w.red[da] + w.red[da + 1] + w.red[da + 2]) / (T)3; }
+    T v = w.vec[V_TMP][lane];
+    if (CM_jnt_type[j] == 2) { const int da = CM_jnt_dofadr[j]; v = (w.vec[V_TMP][da] + w.vec[V_TMP][da + 1] + w.vec[V_TMP][da + 2]) / (T)3; }
     w.st[S_DOFINVW + lane] = v;
     if (lane == 0) w.st[S_BODYINVW] = 0;
   }
   CW_SYNC();
   const T org[3] = {w.xpos[1][0], w.xpos[1][1], w.xpos[1][2]};
-  for (int b0 = 1; b0 < CW_NB; b0 += 16) {
-    const int nb = (CW_NB - b0) < 16 ? (CW_NB - b0) : 16;
+  for (int b0 = 1; b0 < CW_NB; b0 += 10) {
+    const int nb = (CW_NB - b0) < 10 ? (CW_NB - b0) : 10;
     for (int bb = 0; bb < nb; bb++) {
       const int b = b0 + bb;
       T ip[3] = {(T)CM_body_ipos[b][0], (T)CM_body_ipos[b][1], (T)CM_body_ipos[b][2]}, off[3];

@@ -51,7 +51,7 @@
 
 #define CW_NB CM_NBODY
 #define CW_NV CM_NV
-#define CW_NEFC 48
+#define CW_NEFC 32 /* constraint-row capacity (njmax analogue): 12 equality + limits + contacts */
 #define CW_NCON 8
 #define CW_OBS 50
 #define CW_ACT 10
@@ -101,11 +101,10 @@ struct CassieWs {
     T A[CW_NEFC][CW_NEFC + 1];
     CassieWsPre<T> p;
   } u;
-  T efc_pos[CW_NEFC], efc_diag[CW_NEFC], efc_R[CW_NEFC], efc_jv[CW_NEFC], efc_K[CW_NEFC], efc_B[CW_NEFC], efc_imp[CW_NEFC];
+  T efc_pos[CW_NEFC], efc_R[CW_NEFC], efc_jv[CW_NEFC], efc_K[CW_NEFC], efc_B[CW_NEFC], efc_imp[CW_NEFC];
   T efc_b[CW_NEFC], efc_f[CW_NEFC], efc_res[CW_NEFC], efc_dinv[CW_NEFC];
   int efc_type[CW_NEFC];
   T vec[V_NVEC][CW_NV];
-  T red[32];
   int ncon, nefc, solver_iter;
   T con_pos[CW_NCON][3], con_frame[CW_NCON][9], con_dist[CW_NCON], con_mu[CW_NCON];
   int con_geom[CW_NCON], con_geom1[CW_NCON], con_dim[CW_NCON], con_adr[CW_NCON];
@@ -123,9 +122,13 @@ CW_FN double cw_exp_o(double x) { return exp(x); }
 CW_FN float cw_tan_o(float x) { return tanf(x); }
 CW_FN double cw_tan_o(double x) { return tan(x); }
 #ifdef __CUDA_ARCH__
+CW_FN float cw_rcp(float x) { return __frcp_rn(x); }
+CW_FN double cw_rcp(double x) { return 1.0 / x; }
 CW_FN int cw_ctz(unsigned m) { return __ffs((int)m) - 1; }
 #else
 CW_FN int cw_ctz(unsigned m) { return __builtin_ctz(m); }
+CW_FN float cw_rcp(float x) { return 1.0f / x; }
+CW_FN double cw_rcp(double x) { return 1.0 / x; }
 #endif
 template <typename T> CW_FN T cw_sqrt(T x) { return cw_sqrt_o(x); }
 template <typename T> CW_FN void cw_sincos(T x, T *s, T *c) { cw_sincos_o(x, s, c); }
@@ -198,7 +201,7 @@ template <typename T> CW_FN T cw_u01(uint32_t x) { return (T)(x >> 8) * (T)(1.0 
 /* =====================================================================================================
  * position stage: kinematics, cdof, cinert (mj_kinematics + mj_comPos), lane = body, one tree level per phase
  * ===================================================================================================== */
-template <typename T> CW_NOINL void cw_kinematics(CassieWs<T> &w, const T *qpos CW_LANE_PARAM) {
+template <typename T> CW_FN void cw_kinematics(CassieWs<T> &w, const T *qpos CW_LANE_PARAM) {
   CW_FOR_LANES {
     if (lane == 0) {
       for (int k = 0; k < 3; k++) w.xpos[0][k] = 0;
@@ -303,7 +306,7 @@ template <typename T> CW_NOINL void cw_kinematics(CassieWs<T> &w, const T *qpos 
 }
 
 /* composite inertia (mj_crb): parents gather children, deepest level first; then M (lane = dof) */
-template <typename T> CW_NOINL void cw_crb(CassieWs<T> &w CW_LANE_PARAM) {
+template <typename T> CW_FN void cw_crb(CassieWs<T> &w CW_LANE_PARAM) {
   for (int lvl = CM_MAXLEVEL - 1; lvl >= 1; lvl--) {
     CW_FOR_LANES {
       if (lane < CW_NB && CM_body_level[lane] == lvl) {
@@ -349,7 +352,7 @@ template <typename T> CW_NOINL void cw_factor(CassieWs<T> &w, T hdamp, bool reco
   for (int s = 12; s >= 0; s--) {
     const int kL = 6 + s, kR = 19 + s;
     const unsigned legmask = CM_leg_ancmask[s];
-    const T dL = (T)1 / w.D[kL], dR = (T)1 / w.D[kR];
+    const T dL = cw_rcp(w.D[kL]), dR = cw_rcp(w.D[kR]);
     CW_FOR_LANES {
       if (lane == 0) { w.Dinv[kL] = dL; w.Dinv[kR] = dR; }
       if (lane >= 6) {
@@ -369,16 +372,24 @@ template <typename T> CW_NOINL void cw_factor(CassieWs<T> &w, T hdamp, bool reco
           }
           w.D[lane] -= a * rk[lane];
         }
-      } else {
-        const T aL = w.M[kL][lane] * dL, aR = w.M[kR][lane] * dR;
-        for (int j = 0; j < lane; j++) w.M[lane][j] -= aL * w.M[kL][j] + aR * w.M[kR][j];
-        w.D[lane] -= aL * w.M[kL][lane] + aR * w.M[kR][lane];
       }
     }
     CW_SYNC();
   }
+  /* Schur complement of both legs on the 6 base dofs, one (i, j <= i) entry per lane */
+  CW_FOR_LANES {
+    if (lane < 21) {
+      int i = 0, rem = lane;
+      while (rem > i) { rem -= i + 1; i++; }
+      const int j = rem;
+      T acc = 0;
+      for (int k = 6; k < CW_NV; k++) acc += w.M[k][i] * w.M[k][j] * w.Dinv[k];
+      if (i == j) w.D[i] -= acc; else w.M[i][j] -= acc;
+    }
+  }
+  CW_SYNC();
   for (int k = 5; k >= 1; k--) {
-    const T d = (T)1 / w.D[k];
+    const T d = cw_rcp(w.D[k]);
     CW_FOR_LANES {
       if (lane == 0) w.Dinv[k] = d;
       if (lane < k) {
@@ -390,7 +401,7 @@ template <typename T> CW_NOINL void cw_factor(CassieWs<T> &w, T hdamp, bool reco
     CW_SYNC();
   }
   {
-    const T d = (T)1 / w.D[0];
+    const T d = cw_rcp(w.D[0]);
     CW_FOR_LANES { if (lane == 0) w.Dinv[0] = d; }
     CW_SYNC();
   }
@@ -457,7 +468,7 @@ CM_ARRAY int CW_CAND_END[17] = {1, -1, 1, -1, 1, -1, 1, -1, 1, -1, 1, -1, 1, -1,
 CM_ARRAY int CW_PAIR_G1[9] = {2, 2, 2, 3, 3, 3, 4, 4, 4};
 CM_ARRAY int CW_PAIR_G2[9] = {6, 7, 8, 6, 7, 8, 6, 7, 8};
 
-template <typename T> CW_NOINL void cw_collision(CassieWs<T> &w CW_LANE_PARAM) {
+template <typename T> CW_FN void cw_collision(CassieWs<T> &w CW_LANE_PARAM) {
   CW_FOR_LANES {
     w.u.p.cand_dist[lane] = 1;
     if (lane < 17) {
@@ -531,7 +542,7 @@ template <typename T> CW_NOINL void cw_collision(CassieWs<T> &w CW_LANE_PARAM) {
 
 /* mj_makeConstraint: rows of J (lane = dof column), efc_pos / efc_diag / efc_type per row */
 CM_ARRAY int CW_LIM_JNT[16] = {4, 5, 6, 8, 9, 10, 12, 14, 15, 16, 17, 19, 20, 21, 23, 25};
-template <typename T> CW_NOINL void cw_make_constraint(CassieWs<T> &w, const T *qpos, int flags CW_LANE_PARAM) {
+template <typename T> CW_FN void cw_make_constraint(CassieWs<T> &w, const T *qpos, int flags CW_LANE_PARAM) {
   int r = 0;
   const T org[3] = {w.xpos[1][0], w.xpos[1][1], w.xpos[1][2]};
   if (!(flags & 1)) {
@@ -549,31 +560,38 @@ template <typename T> CW_NOINL void cw_make_constraint(CassieWs<T> &w, const T *
         cw_jac_col(w, b1, o1, lane, c1);
         cw_jac_col(w, b2, o2, lane, c2);
         for (int k = 0; k < 3; k++) w.J[r + k][lane] = c1[k] - c2[k];
-        if (lane < 3) { w.efc_pos[r + lane] = o1[lane] - o2[lane]; w.efc_diag[r + lane] = diag; w.efc_type[r + lane] = 0; }
+        if (lane < 3) { w.efc_pos[r + lane] = o1[lane] - o2[lane]; w.efc_R[r + lane] = diag; w.efc_type[r + lane] = 0; }
       }
       r += 3;
     }
+    /* row budget: contacts (feet first) are seated before joint limits, whole contacts at a time */
+    int nckeep = 0, crows = 0;
+    if (!(flags & 2))
+      for (int c = 0; c < w.ncon; c++) {
+        const int nrow = w.con_dim[c] == 3 ? 4 : 1;
+        if (r + crows + nrow > CW_NEFC) break;
+        crows += nrow; nckeep++;
+      }
     /* joint limits */
     for (int l = 0; l < 16; l++) {
       const int j = CW_LIM_JNT[l];
       const T q = qpos[CM_jnt_qposadr[j]];
       for (int side = -1; side <= 1; side += 2) {
         const T dist = (T)side * ((T)CM_jnt_range[j][(side + 1) / 2] - q);
-        if (dist < 0 && r < CW_NEFC) {
+        if (dist < 0 && r + crows < CW_NEFC) {
           const int da = CM_jnt_dofadr[j];
           CW_FOR_LANES {
             w.J[r][lane] = (lane == da) ? (T)(-side) : (T)0;
-            if (lane == 0) { w.efc_pos[r] = dist; w.efc_diag[r] = w.st[S_DOFINVW + da]; w.efc_type[r] = 1; }
+            if (lane == 0) { w.efc_pos[r] = dist; w.efc_R[r] = w.st[S_DOFINVW + da]; w.efc_type[r] = 1; }
           }
           r++;
         }
       }
     }
     /* contacts */
-    int nc = (flags & 2) ? 0 : w.ncon;
+    const int nc = nckeep;
     for (int c = 0; c < nc; c++) {
       const int nrow = w.con_dim[c] == 3 ? 4 : 1;
-      if (r + nrow > CW_NEFC) { nc = c; break; }
       const int b2 = CM_geom_body[w.con_geom[c]], g1 = w.con_geom1[c], b1 = g1 >= 0 ? CM_geom_body[g1] : 0;
       T off[3] = {w.con_pos[c][0] - org[0], w.con_pos[c][1] - org[1], w.con_pos[c][2] - org[2]};
       const T tran = w.st[S_BODYINVW + b1] + w.st[S_BODYINVW + b2], mu = w.con_mu[c], dist = w.con_dist[c];
@@ -585,13 +603,13 @@ template <typename T> CW_NOINL void cw_make_constraint(CassieWs<T> &w, const T *
         for (int a = 0; a < 3; a++) jf[a] = fr[3 * a] * (c2[0] - c1[0]) + fr[3 * a + 1] * (c2[1] - c1[1]) + fr[3 * a + 2] * (c2[2] - c1[2]);
         if (nrow == 1) {
           w.J[r][lane] = jf[0];
-          if (lane == 0) { w.efc_pos[r] = dist; w.efc_diag[r] = tran; w.efc_type[r] = 2; w.con_adr[c] = r; }
+          if (lane == 0) { w.efc_pos[r] = dist; w.efc_R[r] = tran; w.efc_type[r] = 2; w.con_adr[c] = r; }
         } else {
           w.J[r][lane] = jf[0] + mu * jf[1];
           w.J[r + 1][lane] = jf[0] - mu * jf[1];
           w.J[r + 2][lane] = jf[0] + mu * jf[2];
           w.J[r + 3][lane] = jf[0] - mu * jf[2];
-          if (lane < 4) { w.efc_pos[r + lane] = dist; w.efc_diag[r + lane] = tran + mu * mu * tran; w.efc_type[r + lane] = 2; }
+          if (lane < 4) { w.efc_pos[r + lane] = dist; w.efc_R[r + lane] = tran + mu * mu * tran; w.efc_type[r + lane] = 2; }
           if (lane == 0) w.con_adr[c] = r;
         }
       }
@@ -604,83 +622,75 @@ template <typename T> CW_NOINL void cw_make_constraint(CassieWs<T> &w, const T *
   CW_FOR_LANES { if (lane == 0) w.nefc = r; }
   CW_SYNC();
   /* impedance, regulariser, reference stiffness/damping (mj_makeImpedance), J qvel — lane = row */
-  for (int pass = 0; pass < 2; pass++) {
-    CW_FOR_LANES {
-      const int row = pass * 32 + lane;
-      if (row < r) {
-        const T pos = w.efc_pos[row];
-        T x = cw_abs(pos) / (T)CM_SOLIMP_WIDTH, yy, imp;
-        if (x >= 1) imp = (T)CM_SOLIMP_DMAX;
-        else {
-          if (x <= (T)CM_SOLIMP_MID) yy = x * x / (T)CM_SOLIMP_MID; /* power 2 */
-          else yy = 1 - (1 - x) * (1 - x) / (T)(1 - CM_SOLIMP_MID);
-          imp = (T)CM_SOLIMP_DMIN + yy * (T)(CM_SOLIMP_DMAX - CM_SOLIMP_DMIN);
-        }
-        const int ty = w.efc_type[row];
-        T tc = ty == 1 ? (T)CM_LIMIT_SOLREF_TC : (T)CM_EQ_SOLREF_TC; /* equality and geoms share solref 0.005 1 */
-        const T dr = 1;
-        if (tc < (T)(2 * CM_TIMESTEP)) tc = (T)(2 * CM_TIMESTEP);
-        const T dmax = (T)CM_SOLIMP_DMAX;
-        w.efc_K[row] = (T)1 / (dmax * dmax * tc * tc * dr * dr);
-        w.efc_B[row] = (T)2 / (dmax * tc);
-        w.efc_imp[row] = imp;
-        w.efc_R[row] = cw_max((T)1e-15, (1 - imp) / imp * w.efc_diag[row]);
-        T jv = 0;
-        for (int i = 0; i < CW_NV; i++) jv += w.J[row][i] * w.st[S_QVEL + i];
-        w.efc_jv[row] = jv;
+  CW_FOR_LANES {
+    const int row = lane;
+    if (row < r) {
+      const T pos = w.efc_pos[row];
+      T x = cw_abs(pos) / (T)CM_SOLIMP_WIDTH, yy, imp;
+      if (x >= 1) imp = (T)CM_SOLIMP_DMAX;
+      else {
+        if (x <= (T)CM_SOLIMP_MID) yy = x * x / (T)CM_SOLIMP_MID; /* power 2 */
+        else yy = 1 - (1 - x) * (1 - x) / (T)(1 - CM_SOLIMP_MID);
+        imp = (T)CM_SOLIMP_DMIN + yy * (T)(CM_SOLIMP_DMAX - CM_SOLIMP_DMIN);
       }
+      const int ty = w.efc_type[row];
+      T tc = ty == 1 ? (T)CM_LIMIT_SOLREF_TC : (T)CM_EQ_SOLREF_TC; /* equality and geoms share solref 0.005 1 */
+      const T dr = 1;
+      if (tc < (T)(2 * CM_TIMESTEP)) tc = (T)(2 * CM_TIMESTEP);
+      const T dmax = (T)CM_SOLIMP_DMAX;
+      w.efc_K[row] = (T)1 / (dmax * dmax * tc * tc * dr * dr);
+      w.efc_B[row] = (T)2 / (dmax * tc);
+      w.efc_imp[row] = imp;
+      w.efc_R[row] = cw_max((T)1e-15, (1 - imp) / imp * w.efc_R[row]); /* efc_R held diagApprox until here */
+      T jv = 0;
+      for (int i = 0; i < CW_NV; i++) jv += w.J[row][i] * w.st[S_QVEL + i];
+      w.efc_jv[row] = jv;
     }
   }
   CW_SYNC();
 }
 
 /* B = J L^-1 (each row: y <- L^-T y in registers, lane = row) then A = B D^-1 B^T + diag(R) (mj_projectConstraint) */
-template <typename T> CW_NOINL void cw_half_solve_rows(CassieWs<T> &w, int n CW_LANE_PARAM) {
-  for (int pass = 0; pass * 32 < n; pass++) {
-    CW_FOR_LANES {
-      const int row = pass * 32 + lane;
-      if (row < n) {
-        T y[CW_NV];
-        for (int i = 0; i < CW_NV; i++) y[i] = w.J[row][i];
-        cw_half_solve_regs<T>(w, y);
-        for (int i = 0; i < CW_NV; i++) w.J[row][i] = y[i];
+template <typename T> CW_FN void cw_half_solve_rows(CassieWs<T> &w, int n CW_LANE_PARAM) {
+  CW_FOR_LANES {
+    if (lane < n) {
+      T y[CW_NV];
+      for (int i = 0; i < CW_NV; i++) y[i] = w.J[lane][i];
+      cw_half_solve_regs<T>(w, y);
+      for (int i = 0; i < CW_NV; i++) w.J[lane][i] = y[i];
+    }
+  }
+  CW_SYNC();
+}
+template <typename T> CW_FN void cw_project(CassieWs<T> &w CW_LANE_PARAM) {
+  const int n = w.nefc;
+  CW_FOR_LANES {
+    if (lane < n) {
+      T y[CW_NV];
+      for (int i = 0; i < CW_NV; i++) y[i] = w.J[lane][i];
+      cw_half_solve_regs<T>(w, y);
+      for (int i = 0; i < CW_NV; i++) { w.J[lane][i] = y[i]; }
+    }
+  }
+  CW_SYNC();
+  CW_FOR_LANES {
+    const int c = lane;
+    if (c < n) {
+      T bs[CW_NV];
+      for (int i = 0; i < CW_NV; i++) bs[i] = w.J[c][i] * w.Dinv[i];
+      for (int rr = 0; rr <= c; rr++) {
+        T s = 0;
+        for (int i = 0; i < CW_NV; i++) s += w.J[rr][i] * bs[i];
+        if (rr == c) { s += w.efc_R[c]; w.efc_dinv[c] = (T)1 / s; }
+        w.u.A[rr][c] = s;
+        w.u.A[c][rr] = s;
       }
     }
   }
   CW_SYNC();
 }
-template <typename T> CW_NOINL void cw_project(CassieWs<T> &w CW_LANE_PARAM) {
-  const int n = w.nefc;
-  for (int pass = 0; pass * 32 < n; pass++) {
-    CW_FOR_LANES {
-      const int c = pass * 32 + lane;
-      if (c < n) {
-        T y[CW_NV];
-        for (int i = 0; i < CW_NV; i++) y[i] = w.J[c][i];
-        cw_half_solve_regs<T>(w, y);
-        for (int i = 0; i < CW_NV; i++) w.J[c][i] = y[i];
-      }
-    }
-    CW_SYNC();
-    CW_FOR_LANES {
-      const int c = pass * 32 + lane;
-      if (c < n) {
-        T bs[CW_NV];
-        for (int i = 0; i < CW_NV; i++) bs[i] = w.J[c][i] * w.Dinv[i];
-        for (int rr = 0; rr <= c; rr++) {
-          T s = 0;
-          for (int i = 0; i < CW_NV; i++) s += w.J[rr][i] * bs[i];
-          if (rr == c) { s += w.efc_R[c]; w.efc_dinv[c] = (T)1 / s; }
-          w.u.A[rr][c] = s;
-          w.u.A[c][rr] = s;
-        }
-      }
-    }
-    CW_SYNC();
-  }
-}
 /* velocity stage: mj_comVel + mj_rne (bias), lane = body, level by level */
-template <typename T> CW_NOINL void cw_rne(CassieWs<T> &w, const T *qvel CW_LANE_PARAM) {
+template <typename T> CW_FN void cw_rne(CassieWs<T> &w, const T *qvel CW_LANE_PARAM) {
   CW_FOR_LANES {
     if (lane == 0) {
       for (int k = 0; k < 6; k++) { w.u.p.cvel[0][k] = 0; w.u.p.cacc[0][k] = 0; }
@@ -827,94 +837,73 @@ template <typename T> CW_NOINL void cw_mj_step(CassieWs<T> &w, bool integrate, i
     /* L qacc_warmstart (so that J a = B (L a)) */
     CW_FOR_LANES {
       const int i = lane, na = CM_dof_nanc[i];
-      T s = w.st[S_QACC_WS + i];
       T acc = 0;
       for (int t = 0; t < na; t++) { const int j = CM_dof_anc[i][t]; acc += w.M[i][j] * w.st[S_QACC_WS + j]; }
-      w.vec[V_TMP][i] = s + acc * w.Dinv[i];
+      w.vec[V_TMP][i] = w.st[S_QACC_WS + i] + acc * w.Dinv[i];
     }
     CW_SYNC();
-    for (int pass = 0; pass * 32 < n; pass++) {
-      CW_FOR_LANES {
-        const int row = pass * 32 + lane;
-        if (row < n) {
-          T ja = 0, jw = 0;
-          for (int i = 0; i < CW_NV; i++) { ja += w.J[row][i] * w.vec[V_Z][i]; jw += w.J[row][i] * w.vec[V_TMP][i]; }
-          const T aref = -w.efc_B[row] * w.efc_jv[row] - w.efc_K[row] * w.efc_imp[row] * w.efc_pos[row];
-          w.efc_b[row] = ja - aref;
-          T f = -(jw - aref) / w.efc_R[row];
-          if (w.efc_type[row] != 0 && f < 0) f = 0;
-          w.efc_f[row] = f;
-        }
+    CW_FOR_LANES {
+      const int row = lane;
+      T f = 0;
+      if (row < n) {
+        T ja = 0, jw = 0;
+        for (int i = 0; i < CW_NV; i++) { ja += w.J[row][i] * w.vec[V_Z][i]; jw += w.J[row][i] * w.vec[V_TMP][i]; }
+        const T aref = -w.efc_B[row] * w.efc_jv[row] - w.efc_K[row] * w.efc_imp[row] * w.efc_pos[row];
+        w.efc_b[row] = ja - aref;
+        f = -(jw - aref) / w.efc_R[row];
+        if (w.efc_type[row] != 0 && f < 0) f = 0;
       }
+      w.efc_f[row] = f;
     }
     CW_SYNC();
-    /* residual res = A f + b and warm-start cost */
+    /* residual res = A f + b and warm-start cost (mj_solPGS start: keep the warm start only if it beats f = 0) */
+    CW_FOR_LANES {
+      const int row = lane;
+      T part = 0;
+      if (row < n) {
+        T sacc = 0;
+        for (int c = 0; c < n; c++) sacc += w.u.A[row][c] * w.efc_f[c];
+        w.efc_res[row] = sacc + w.efc_b[row];
+        part = w.efc_f[row] * ((T)0.5 * sacc + w.efc_b[row]);
+      }
+      w.vec[V_G][lane] = part;
+    }
+    CW_SYNC();
     T cost = 0;
-    for (int pass = 0; pass * 32 < n; pass++) {
-      CW_FOR_LANES {
-        const int row = pass * 32 + lane;
-        T part = 0;
-        if (row < n) {
-          T s = 0;
-          for (int c = 0; c < n; c++) s += w.u.A[row][c] * w.efc_f[c];
-          w.efc_res[row] = s + w.efc_b[row];
-          part = w.efc_f[row] * ((T)0.5 * s + w.efc_b[row]);
-        }
-        w.red[lane] = part;
-      }
-      CW_SYNC();
-      for (int k = 0; k < 32; k++) cost += w.red[k];
-      CW_SYNC();
-    }
+    for (int k = 0; k < 32; k++) cost += w.vec[V_G][k];
+    CW_SYNC();
     if (cost > 0) {
-      for (int pass = 0; pass * 32 < n; pass++) {
-        CW_FOR_LANES {
-          const int row = pass * 32 + lane;
-          if (row < n) { w.efc_f[row] = 0; w.efc_res[row] = w.efc_b[row]; }
-        }
-      }
+      CW_FOR_LANES { if (lane < n) { w.efc_f[lane] = 0; w.efc_res[lane] = w.efc_b[lane]; } }
       CW_SYNC();
     }
     /* PGS sweeps (mj_solPGS): residual-update form, rows in order */
     const T scale = (T)1 / (w.st[S_MEANINERTIA] * (T)CW_NV);
 #ifdef __CUDA_ARCH__
-    { /* device path: rows lane and lane+32 live in registers; the row owner computes the update, one shuffle
-       * broadcasts it, every lane applies column i of A to its two residual slots */
-      const bool v0 = lane < n, v1 = lane + 32 < n;
-      T res0 = v0 ? w.efc_res[lane] : (T)0, res1 = v1 ? w.efc_res[lane + 32] : (T)0;
-      T f0 = v0 ? w.efc_f[lane] : (T)0, f1 = v1 ? w.efc_f[lane + 32] : (T)0;
-      const T di0 = v0 ? w.efc_dinv[lane] : (T)0, di1 = v1 ? w.efc_dinv[lane + 32] : (T)0;
-      const T ad0 = v0 ? w.u.A[lane][lane] : (T)0, ad1 = v1 ? w.u.A[lane + 32][lane + 32] : (T)0;
-      const bool in0 = v0 && w.efc_type[lane] != 0, in1 = v1 && w.efc_type[lane + 32] != 0;
+    { /* device path: row `lane` lives in registers; its owner computes the update, one shuffle broadcasts it,
+       * every lane applies column i of A to its own residual */
+      const bool v0 = lane < n;
+      T res0 = v0 ? w.efc_res[lane] : (T)0, f0 = v0 ? w.efc_f[lane] : (T)0;
+      const T di0 = v0 ? w.efc_dinv[lane] : (T)0, had0 = v0 ? (T)0.5 * w.u.A[lane][lane] : (T)0;
+      const T lb0 = (v0 && w.efc_type[lane] != 0) ? (T)0 : (T)-3.0e38; /* lower bound of the row's force */
+      const T *acol = &w.u.A[0][v0 ? lane : 0];
       for (int it = 0; it < CM_ITERATIONS; it++) {
         T imp = 0;
-        const int n0 = n < 32 ? n : 32;
-        for (int i = 0; i < n0; i++) {
-          const T a0 = w.u.A[i][lane], a1 = v1 ? w.u.A[i][lane + 32] : (T)0;
-          T nf = f0 - res0 * di0;
-          if (in0 && nf < 0) nf = 0;
+#pragma unroll 4
+        for (int i = 0; i < n; i++) {
+          const T a0 = acol[i * (CW_NEFC + 1)];
+          const T nf = cw_max(f0 - res0 * di0, lb0);
           const T dlo = nf - f0;
           const T dl = __shfl_sync(0xffffffffu, dlo, i);
-          if (lane == i) { imp -= (T)0.5 * dl * dl * ad0 + dl * res0; f0 = nf; }
+          const bool own = lane == i;
+          imp = own ? imp - dl * (dl * had0 + res0) : imp;
+          f0 = own ? nf : f0;
           res0 += dl * a0;
-          res1 += dl * a1;
-        }
-        for (int i = 32; i < n; i++) {
-          const T a0 = w.u.A[i][lane], a1 = v1 ? w.u.A[i][lane + 32] : (T)0;
-          T nf = f1 - res1 * di1;
-          if (in1 && nf < 0) nf = 0;
-          const T dlo = nf - f1;
-          const T dl = __shfl_sync(0xffffffffu, dlo, i - 32);
-          if (lane == i - 32) { imp -= (T)0.5 * dl * dl * ad1 + dl * res1; f1 = nf; }
-          res0 += dl * a0;
-          res1 += dl * a1;
         }
         for (int o = 16; o > 0; o >>= 1) imp += __shfl_xor_sync(0xffffffffu, imp, o);
         iters = it + 1;
         if (imp * scale < (T)1e-8) break;
       }
       if (v0) w.efc_f[lane] = f0;
-      if (v1) w.efc_f[lane + 32] = f1;
       __syncwarp();
     }
 #else
@@ -928,10 +917,7 @@ template <typename T> CW_NOINL void cw_mj_step(CassieWs<T> &w, bool integrate, i
         if (dl != 0) {
           improvement -= (T)0.5 * dl * dl * w.u.A[i][i] + dl * res;
           w.efc_f[i] = nf;
-          CW_FOR_LANES {
-            if (lane < n) w.efc_res[lane] += dl * w.u.A[i][lane];
-            if (lane + 32 < n) w.efc_res[lane + 32] += dl * w.u.A[i][lane + 32];
-          }
+          CW_FOR_LANES { if (lane < n) w.efc_res[lane] += dl * w.u.A[i][lane]; }
         }
       }
       iters = it + 1;

@@ -423,6 +423,14 @@ static void make_constraint(const cp_model_t *m, cp_data_t *d) {
     }
   }
   d->ne = r;
+  /* row budget: contacts (feet first) are seated before joint limits, whole contacts at a time */
+  int nckeep = 0, crows = 0;
+  for (int c = 0; c < d->ncon; c++) {
+    int nrow = d->con[c].dim == 3 ? 4 : 1;
+    if (r + crows + nrow > CP_NEFC_MAX) break;
+    crows += nrow; nckeep++;
+  }
+  d->ncon = nckeep;
   /* joint limits (hinges with limited=true; default solref 0.02 1) */
   for (int j = 0; j < CM_NJNT; j++) {
     if (!CM_jnt_limited[j] || CM_jnt_type[j] != 1) continue;
@@ -430,7 +438,7 @@ static void make_constraint(const cp_model_t *m, cp_data_t *d) {
     int da = CM_jnt_dofadr[j];
     for (int side = -1; side <= 1; side += 2) {
       double dist = side * (CM_jnt_range[j][(side + 1) / 2] - q);
-      if (dist < 0 && r < CP_NEFC_MAX) {
+      if (dist < 0 && r + crows < CP_NEFC_MAX) {
         d->efc_J[r][da] = -side;
         finish_row(d, r, 1, dist, m->dof_invweight0[da], CM_LIMIT_SOLREF_TC, CM_LIMIT_SOLREF_DR);
         r++;
@@ -442,7 +450,6 @@ static void make_constraint(const cp_model_t *m, cp_data_t *d) {
   for (int c = 0; c < d->ncon; c++) {
     cp_contact_t *con = &d->con[c];
     int nrow = con->dim == 3 ? 4 : 1;
-    if (r + nrow > CP_NEFC_MAX) { d->ncon = c; break; }
     con->efc_adr = r;
     int b2 = CM_geom_body[con->geom], b1 = con->geom1 >= 0 ? CM_geom_body[con->geom1] : 0;
     double j2[3][NV], j1[3][NV], jf[3][NV];

@@ -12,7 +12,7 @@
 #define CASSIE_PHYS_H
 #include "cassie_model.h"
 
-#define CP_NEFC_MAX 48   /* constraint-row capacity (MuJoCo njmax analogue): 12 equality + limits + contacts */
+#define CP_NEFC_MAX 32   /* constraint-row capacity (MuJoCo njmax analogue): 12 equality + limits + contacts; contacts are seated first */
 #define CP_NCON_MAX 8    /* contact capacity (nconmax analogue); later detections are dropped */
 
 typedef struct {
