@@ -35,13 +35,18 @@ template <typename T> __global__ void __launch_bounds__(32) k_env_reset(T *st, i
   ws_store(w, st + (size_t)e * S_WORDS, sti + (size_t)e * I_WORDS, lane);
 }
 
+/* W warps (= W envs) per CTA; the CTA barrier inside cw_env_step's sub-step loop must be reached by every warp, so
+ * warps past the end of the batch run the barriers only. */
 template <typename T>
-__global__ void __launch_bounds__(32) k_env_step(T *st, int *sti, int n, const T *action, T *obs, T *reward, int *done, T *term_obs,
-                                                 int max_traj_len) {
+__global__ void k_env_step(T *st, int *sti, int n, const T *action, T *obs, T *reward, int *done, T *term_obs, int max_traj_len) {
   extern __shared__ __align__(16) unsigned char smem[];
-  CassieWs<T> &w = *reinterpret_cast<CassieWs<T> *>(smem);
-  const int e = blockIdx.x, lane = threadIdx.x;
-  if (e >= n) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  CassieWs<T> &w = reinterpret_cast<CassieWs<T> *>(smem)[warp];
+  const int e = blockIdx.x * wpb + warp;
+  if (e >= n) {
+    for (int s = 0; s < CW_SIMRATE; s++) __syncthreads();
+    return;
+  }
   ws_load(w, st + (size_t)e * S_WORDS, sti + (size_t)e * I_WORDS, lane);
   if (lane < CW_ACT) w.action[lane] = action[(size_t)e * CW_ACT + lane];
   __syncwarp();
@@ -81,6 +86,10 @@ static int finish() {
 }
 
 extern "C" {
+
+/* tuning knob (envs per CTA of the step kernel); float64 is capped at 5 by shared memory */
+int apex_cassie_warps_per_cta = 10;
+void apex_cassie_set_warps_per_cta(int w) { apex_cassie_warps_per_cta = w; }
 
 int apex_cassie_state_words(void) { return S_WORDS; }
 int apex_cassie_istate_words(void) { return I_WORDS; }
@@ -134,12 +143,15 @@ int apex_cassie_env_reset(int dtype, void *st, int *sti, int n, void *obs, void 
 int apex_cassie_env_step(int dtype, void *st, int *sti, int n, const void *action, void *obs, void *reward, int *done,
                          void *term_obs, int max_traj_len, void *stream) {
   if (!action || !obs || !reward || !done) return -1000;
+  int wpb = apex_cassie_warps_per_cta;
+  if (dtype == 1 && wpb > 5) wpb = 5;
+  if (wpb < 1) wpb = 1;
   DISPATCH(
-      if ((rc = prep(k_env_step<float>, sizeof(CassieWs<float>)))) return rc;
-      (k_env_step<float><<<n, 32, sizeof(CassieWs<float>), s>>>((float *)st, sti, n, (const float *)action, (float *)obs,
+      if ((rc = prep(k_env_step<float>, wpb * sizeof(CassieWs<float>)))) return rc;
+      (k_env_step<float><<<(n + wpb - 1) / wpb, 32 * wpb, wpb * sizeof(CassieWs<float>), s>>>((float *)st, sti, n, (const float *)action, (float *)obs,
                                                                 (float *)reward, done, (float *)term_obs, max_traj_len)),
-      if ((rc = prep(k_env_step<double>, sizeof(CassieWs<double>)))) return rc;
-      (k_env_step<double><<<n, 32, sizeof(CassieWs<double>), s>>>((double *)st, sti, n, (const double *)action, (double *)obs,
+      if ((rc = prep(k_env_step<double>, wpb * sizeof(CassieWs<double>)))) return rc;
+      (k_env_step<double><<<(n + wpb - 1) / wpb, 32 * wpb, wpb * sizeof(CassieWs<double>), s>>>((double *)st, sti, n, (const double *)action, (double *)obs,
                                                                   (double *)reward, done, (double *)term_obs, max_traj_len)))
 }
 

@@ -346,6 +346,7 @@ template <typename T> CW_NOINL void cw_env_step(CassieWs<T> &w, T *obs_out, T *r
   CW_SYNC();
   T lfrc = 0, rfrc = 0, lori = 0, rori = 0, lfv[3] = {0, 0, 0}, rfv[3] = {0, 0, 0};
   for (int s = 0; s < CW_SIMRATE; s++) {
+    CW_BLOCK_SYNC();
     T fp0[6], fp1[6], lz, rz;
     for (int k = 0; k < 6; k++) fp0[k] = w.st[S_FOOTPOS + k];
     cw_sim_step_pd<T>(w CW_LANE_ARG);

@@ -31,12 +31,14 @@
 #define CW_NOINL __device__ __noinline__
 #define CW_FOR_LANES
 #define CW_SYNC() __syncwarp()
+#define CW_BLOCK_SYNC() __syncthreads() /* keeps the warps of a CTA within one sub-step of each other (I-cache reuse) */
 #define CM_ARRAY static __device__ const
 #else
 #define CW_FN static inline
 #define CW_NOINL static
 #define CW_FOR_LANES for (int lane = 0; lane < 32; ++lane)
 #define CW_SYNC() ((void)0)
+#define CW_BLOCK_SYNC() ((void)0)
 #define CM_ARRAY static const
 #endif
 #include "cassie_model.h"
@@ -122,7 +124,7 @@ CW_FN double cw_exp_o(double x) { return exp(x); }
 CW_FN float cw_tan_o(float x) { return tanf(x); }
 CW_FN double cw_tan_o(double x) { return tan(x); }
 #ifdef __CUDA_ARCH__
-CW_FN float cw_rcp(float x) { return __frcp_rn(x); }
+CW_FN float cw_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 CW_FN double cw_rcp(double x) { return 1.0 / x; }
 CW_FN int cw_ctz(unsigned m) { return __ffs((int)m) - 1; }
 #else

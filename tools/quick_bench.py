@@ -9,6 +9,10 @@ from apex_b200.envs import BatchedCassieEnv
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
 dt = torch.float64 if (len(sys.argv) > 3 and sys.argv[3] == "f64") else torch.float32
+import os
+from apex_b200 import lib
+if os.environ.get("WPB"):
+    lib().apex_cassie_set_warps_per_cta(int(os.environ["WPB"]))
 env = BatchedCassieEnv(n, dtype=dt, seed=0, dynamics_randomization=True)
 env.reset()
 g = torch.Generator(device="cuda").manual_seed(0)
