@@ -30,6 +30,22 @@ def lib():
         L.apex_cassie_mj_step.argtypes = [i, vp, ip, i, i, vp]
         for f in (L.apex_cassie_env_init, L.apex_cassie_env_reset, L.apex_cassie_env_step, L.apex_cassie_mj_step):
             f.restype = i
+        L.apex_cassie_set_warps_per_cta.argtypes = [i]
+        L.apex_cassie_set_warps_per_cta.restype = None
+        fl, lng = C.c_float, C.c_long
+        L.apex_mlp_forward.argtypes = [vp, i, i, i, i, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+        L.apex_mlp_backward.argtypes = [vp, i, i, i, i, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+        L.apex_prepare_obs.argtypes = [vp, vp, i, i, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+        L.apex_gaussian_sample.argtypes = [vp, vp, fl, i, i, u, u, u, vp, vp, vp]
+        L.apex_ppo_loss.argtypes = [i, i, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, fl, fl, vp, vp, vp, vp, vp, vp, vp]
+        L.apex_grad_sumsq.argtypes = [vp, i, vp, vp]
+        L.apex_adam_step.argtypes = [vp, vp, vp, vp, i, vp, fl, fl, fl, fl, fl, fl, i, vp]
+        L.apex_gae_scan.argtypes = [i, i, vp, vp, vp, vp, vp, fl, fl, vp, vp, vp]
+        L.apex_moments.argtypes = [vp, lng, vp, vp]
+        L.apex_normalize.argtypes = [vp, lng, vp, fl, vp]
+        for f in (L.apex_mlp_forward, L.apex_mlp_backward, L.apex_prepare_obs, L.apex_gaussian_sample, L.apex_ppo_loss,
+                  L.apex_grad_sumsq, L.apex_adam_step, L.apex_gae_scan, L.apex_moments, L.apex_normalize):
+            f.restype = i
         _lib = L
     return _lib
 

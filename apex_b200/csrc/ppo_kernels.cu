@@ -1,0 +1,452 @@
+/* Hand-written sm_100a kernels for the learner side of the PPO path (float32, SIMT):
+ *   - reverse return / GAE scan over the [T, N] rollout buffer (rl/algos/ppo.py:73-89 finish_path; lam = 1 is the
+ *     reference's discounted Monte-Carlo return with bootstrap), advantage statistics and normalisation (:395-396);
+ *   - tiled GEMM with fused bias / ReLU / ReLU-mask epilogues for the 50-256-256-{10,1} MLPs
+ *     (rl/policies/actor.py:142-215, critic.py:37-74) forward and backward;
+ *   - Gaussian head: sampling a ~ N(mu, sigma) with Philox + Box-Muller and log-probability (actor.py:199-215);
+ *   - PPO clipped-ratio / value / mirror-symmetry loss forward + backward (ppo.py:276-345);
+ *   - mirror gather (rl/envs/wrappers.py:46-67), gradient-norm clip + Adam (ppo.py:319-330, torch.optim.Adam semantics).
+ * C-ABI in include/apex_ppo.h.  All pointers are device pointers; stream is a cudaStream_t.
+ */
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+#include "../../include/apex_ppo.h"
+
+#define CK(call)                                   \
+  do {                                             \
+    cudaError_t e_ = (call);                       \
+    if (e_ != cudaSuccess) return -(int)e_;        \
+  } while (0)
+static inline int last_err() { cudaError_t e = cudaGetLastError(); return e == cudaSuccess ? 0 : -(int)e; }
+
+/* ===================================================================================================
+ * GEMM  C[M,N] (+)= A[M,K] * B[K,N] with arbitrary element strides; epilogue: + bias[n], relu, * (mask > 0)
+ * split over K through blockIdx.z (atomicAdd accumulation when gridDim.z > 1 or accumulate != 0)
+ * =================================================================================================== */
+#define BM 64
+#define BN 64
+#define BK 16
+__global__ void __launch_bounds__(256) k_gemm(int M, int N, int K, const float *__restrict__ A, long sam, long sak,
+                                              const float *__restrict__ B, long sbk, long sbn, float *__restrict__ C, long scm,
+                                              long scn, const float *__restrict__ bias, int relu, const float *__restrict__ mask,
+                                              long smm, long smn, int accumulate, int kchunk) {
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Bs[BK][BN + 4];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int kbeg = blockIdx.z * kchunk, kend = min(K, kbeg + kchunk);
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) acc[i][j] = 0.f;
+  const bool a_kfast = (sak == 1), b_nfast = (sbn == 1);
+  for (int k0 = kbeg; k0 < kend; k0 += BK) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int e = tid + i * 256;
+      int m, k;
+      if (a_kfast) { k = e & (BK - 1); m = e >> 4; } else { m = e & (BM - 1); k = e >> 6; }
+      const int gm = m0 + m, gk = k0 + k;
+      As[k][m] = (gm < M && gk < kend) ? A[gm * sam + gk * sak] : 0.f;
+      int n, kb;
+      if (b_nfast) { n = e & (BN - 1); kb = e >> 6; } else { kb = e & (BK - 1); n = e >> 4; }
+      const int gn = n0 + n, gkb = k0 + kb;
+      Bs[kb][n] = (gn < N && gkb < kend) ? B[gkb * sbk + gn * sbn] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < BK; k++) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) a[i] = As[k][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; j++) b[j] = Bs[k][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  const bool atomic = accumulate || gridDim.z > 1;
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int gm = m0 + ty * 4 + i;
+    if (gm >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int gn = n0 + tx * 4 + j;
+      if (gn >= N) continue;
+      float v = acc[i][j];
+      if (bias && blockIdx.z == 0) v += bias[gn];
+      if (relu) v = fmaxf(v, 0.f);
+      if (mask) v = mask[gm * smm + gn * smn] > 0.f ? v : 0.f;
+      if (atomic) atomicAdd(&C[gm * scm + gn * scn], v); else C[gm * scm + gn * scn] = v;
+    }
+  }
+}
+
+static int gemm(int M, int N, int K, const float *A, long sam, long sak, const float *B, long sbk, long sbn, float *C, long scm,
+                long scn, const float *bias, int relu, const float *mask, long smm, long smn, int accumulate, int splits,
+                cudaStream_t s) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  if (splits < 1) splits = 1;
+  int kchunk = ((K + splits - 1) / splits + BK - 1) / BK * BK;
+  splits = (K + kchunk - 1) / kchunk;
+  dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, splits);
+  k_gemm<<<grid, 256, 0, s>>>(M, N, K, A, sam, sak, B, sbk, sbn, C, scm, scn, bias, relu, mask, smm, smn, accumulate, kchunk);
+  return last_err();
+}
+
+/* column sums: out[n] += sum_m X[m, n] (bias gradients) */
+__global__ void k_colsum(int M, int N, const float *__restrict__ X, float *__restrict__ out, int rows_per_block) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const int mb = blockIdx.y * rows_per_block, me = min(M, mb + rows_per_block);
+  float s = 0.f;
+  for (int m = mb; m < me; m++) s += X[(long)m * N + n];
+  atomicAdd(&out[n], s);
+}
+
+/* ===================================================================================================
+ * MLP forward / backward (three Linear layers, ReLU on the two hidden ones)
+ * =================================================================================================== */
+extern "C" int apex_mlp_forward(const float *x, int rows, int in_dim, int hid, int out_dim, const float *w1, const float *b1,
+                                const float *w2, const float *b2, const float *w3, const float *b3, float *h1, float *h2, float *y,
+                                void *stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc;
+  /* torch Linear: y = x W^T + b, W [out, in] row-major  ->  B(k, n) = W[n * in + k] */
+  if ((rc = gemm(rows, hid, in_dim, x, in_dim, 1, w1, 1, in_dim, h1, hid, 1, b1, 1, nullptr, 0, 0, 0, 1, s))) return rc;
+  if ((rc = gemm(rows, hid, hid, h1, hid, 1, w2, 1, hid, h2, hid, 1, b2, 1, nullptr, 0, 0, 0, 1, s))) return rc;
+  if ((rc = gemm(rows, out_dim, hid, h2, hid, 1, w3, 1, hid, y, out_dim, 1, b3, 0, nullptr, 0, 0, 0, 1, s))) return rc;
+  return 0;
+}
+
+extern "C" int apex_mlp_backward(const float *x, int rows, int in_dim, int hid, int out_dim, const float *w2, const float *w3,
+                                 const float *h1, const float *h2, const float *dy, float *dh2, float *dh1, float *gw1, float *gb1,
+                                 float *gw2, float *gb2, float *gw3, float *gb3, void *stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc;
+  const int splits = 148; /* the weight gradients reduce over `rows`: split that dimension across the SMs */
+  const int rpb = 512;
+  /* layer 3: gW3[o, k] += sum_r dy[r, o] h2[r, k];  dh2 = (dy W3) * (h2 > 0) */
+  if ((rc = gemm(out_dim, hid, rows, dy, 1, out_dim, h2, hid, 1, gw3, hid, 1, nullptr, 0, nullptr, 0, 0, 1, splits, s))) return rc;
+  k_colsum<<<dim3((out_dim + 63) / 64, (rows + rpb - 1) / rpb), 64, 0, s>>>(rows, out_dim, dy, gb3, rpb);
+  if ((rc = gemm(rows, hid, out_dim, dy, out_dim, 1, w3, hid, 1, dh2, hid, 1, nullptr, 0, h2, hid, 1, 0, 1, s))) return rc;
+  /* layer 2 */
+  if ((rc = gemm(hid, hid, rows, dh2, 1, hid, h1, hid, 1, gw2, hid, 1, nullptr, 0, nullptr, 0, 0, 1, splits, s))) return rc;
+  k_colsum<<<dim3((hid + 63) / 64, (rows + rpb - 1) / rpb), 64, 0, s>>>(rows, hid, dh2, gb2, rpb);
+  if ((rc = gemm(rows, hid, hid, dh2, hid, 1, w2, hid, 1, dh1, hid, 1, nullptr, 0, h1, hid, 1, 0, 1, s))) return rc;
+  /* layer 1 */
+  if ((rc = gemm(hid, in_dim, rows, dh1, 1, hid, x, in_dim, 1, gw1, in_dim, 1, nullptr, 0, nullptr, 0, 0, 1, splits, s))) return rc;
+  k_colsum<<<dim3((hid + 63) / 64, (rows + rpb - 1) / rpb), 64, 0, s>>>(rows, hid, dh1, gb1, rpb);
+  return last_err();
+}
+
+/* ===================================================================================================
+ * observation helpers: normalise, gather minibatch rows, mirror (signed permutation + clock flip)
+ * =================================================================================================== */
+__global__ void k_prepare_obs(const float *__restrict__ obs, const int64_t *__restrict__ idx, int rows, int dim,
+                              const float *__restrict__ mean, const float *__restrict__ stdv, const int *__restrict__ mir_src,
+                              const float *__restrict__ mir_sign, const int *__restrict__ clock_mask, float *__restrict__ raw,
+                              float *__restrict__ xn, float *__restrict__ xn_mir) {
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long)rows * dim) return;
+  const int r = (int)(t / dim), j = (int)(t % dim);
+  const long src = idx ? idx[r] : r;
+  const float v = obs[src * dim + j];
+  if (raw) raw[t] = v;
+  const float m = mean ? mean[j] : 0.f, sd = stdv ? stdv[j] : 1.f;
+  if (xn) xn[t] = (v - m) / sd;
+  if (xn_mir) { /* (obs @ M)[j] = sign_j * obs[src_j]; clock entries: sin(asin(c) + pi)  (wrappers.py:59-67) */
+    float mv = mir_sign[j] * obs[src * dim + mir_src[j]];
+    if (clock_mask[j]) mv = sinf(asinf(mv) + 3.14159265358979323846f);
+    xn_mir[t] = (mv - m) / sd;
+  }
+}
+
+extern "C" int apex_prepare_obs(const float *obs, const int64_t *idx, int rows, int dim, const float *mean, const float *stdv,
+                                const int *mir_src, const float *mir_sign, const int *clock_mask, float *raw, float *xn,
+                                float *xn_mir, void *stream) {
+  if (rows <= 0) return 0;
+  const long tot = (long)rows * dim;
+  k_prepare_obs<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(obs, idx, rows, dim, mean, stdv, mir_src, mir_sign,
+                                                                               clock_mask, raw, xn, xn_mir);
+  return last_err();
+}
+
+/* ===================================================================================================
+ * Gaussian head: a = mu + sigma * anneal * eps, log-prob summed over the action dims
+ * =================================================================================================== */
+__device__ __forceinline__ void philox4(uint32_t seed, uint32_t a, uint32_t b, uint32_t c, uint32_t out[4]) {
+  uint32_t c0 = a, c1 = b, c2 = c, c3 = 0x5851f42du, k0 = seed, k1 = 0xbb67ae85u;
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__global__ void k_gaussian_sample(const float *__restrict__ mu, const float *__restrict__ sigma, float anneal, int rows, int adim,
+                                  uint32_t seed, uint32_t step, uint32_t row0, float *__restrict__ act, float *__restrict__ logp) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  float lp = 0.f;
+  for (int j = 0; j < adim; j += 2) {
+    uint32_t u[4];
+    philox4(seed, row0 + (uint32_t)r, step, (uint32_t)(j >> 1), u);
+    const float u1 = ((float)(u[0] >> 8) + 0.5f) * (1.0f / 16777216.0f), u2 = (float)(u[1] >> 8) * (1.0f / 16777216.0f);
+    const float rad = sqrtf(-2.0f * logf(u1));
+    float sn, cs;
+    sincosf(6.283185307179586f * u2, &sn, &cs);
+    const float e[2] = {rad * cs, rad * sn};
+    for (int k = 0; k < 2 && j + k < adim; k++) {
+      const float sd = sigma[j + k] * anneal, m = mu[(long)r * adim + j + k];
+      const float a = m + sd * e[k];
+      act[(long)r * adim + j + k] = a;
+      const float z = (a - m) / sd;
+      lp += -0.5f * z * z - logf(sd) - 0.9189385332046727f;
+    }
+  }
+  logp[r] = lp;
+}
+
+extern "C" int apex_gaussian_sample(const float *mu, const float *sigma, float anneal, int rows, int adim, unsigned seed,
+                                    unsigned step, unsigned row0, float *act, float *logp, void *stream) {
+  if (rows <= 0) return 0;
+  k_gaussian_sample<<<(rows + 127) / 128, 128, 0, (cudaStream_t)stream>>>(mu, sigma, anneal, rows, adim, seed, step, row0, act, logp);
+  return last_err();
+}
+
+/* ===================================================================================================
+ * PPO loss forward + backward (ppo.py:276-345): per-row gradients wrt the policy means (both the plain and
+ * the mirrored batch) and the value; scalar statistics accumulated with double atomics:
+ * stats[0..5] = sum of: surrogate (min(cpi, clip)), 0.5 (R - V)^2, ratio, KL(pi || pi_old), mirror squared error, count
+ * =================================================================================================== */
+__global__ void k_ppo_loss(int rows, int adim, const float *__restrict__ mu, const float *__restrict__ mu_mir,
+                           const float *__restrict__ act, const int64_t *__restrict__ idx, const float *__restrict__ act_all,
+                           const float *__restrict__ oldlogp_all, const float *__restrict__ adv_all, const float *__restrict__ ret_all,
+                           const float *__restrict__ oldmu_all, const float *__restrict__ value, const float *__restrict__ sigma,
+                           float clip, float mirror_coeff, const int *__restrict__ amir_src, const float *__restrict__ amir_sign,
+                           float inv_rows, float *__restrict__ dmu, float *__restrict__ dmu_mir, float *__restrict__ dvalue,
+                           double *__restrict__ stats) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  float s_sur = 0, s_v = 0, s_ratio = 0, s_kl = 0, s_mir = 0, s_cnt = 0;
+  if (r < rows) {
+    const long src = idx ? idx[r] : r;
+    float lp = 0.f, kl = 0.f;
+    for (int j = 0; j < adim; j++) {
+      const float sd = sigma[j], m = mu[(long)r * adim + j], a = act_all[src * adim + j];
+      const float z = (a - m) / sd;
+      lp += -0.5f * z * z - logf(sd) - 0.9189385332046727f;
+      const float dm = (m - oldmu_all[src * adim + j]) / sd; /* KL of equal-variance Gaussians */
+      kl += 0.5f * dm * dm;
+    }
+    const float ratio = expf(lp - oldlogp_all[src]), A = adv_all[src];
+    const float cpi = ratio * A, clp = fminf(fmaxf(ratio, 1.f - clip), 1.f + clip) * A;
+    /* d min(cpi, clip) / d ratio: A when the unclipped branch is active (ties: both branches carry A inside the clip range) */
+    const bool inside = ratio >= 1.f - clip && ratio <= 1.f + clip;
+    const float dsur_dratio = (cpi < clp || inside) ? A : 0.f;
+    const float g_lp = -inv_rows * dsur_dratio * ratio; /* d(-mean surrogate)/d logp */
+    const float mscale = mirror_coeff * 2.f * inv_rows / (float)adim;
+    for (int j = 0; j < adim; j++) {
+      const float sd = sigma[j], m = mu[(long)r * adim + j], a = act_all[src * adim + j];
+      float g = g_lp * (a - m) / (sd * sd);
+      if (mu_mir) {
+        /* mirror_action(mu_mir)[j] = sign_j * mu_mir[src_j]; loss 0.4 mean((mu - that)^2) */
+        const float mm = amir_sign[j] * mu_mir[(long)r * adim + amir_src[j]];
+        const float d = m - mm;
+        s_mir += d * d;
+        g += mscale * d;
+        dmu_mir[(long)r * adim + amir_src[j]] = -mscale * d * amir_sign[j];
+      }
+      dmu[(long)r * adim + j] = g;
+    }
+    const float v = value[r], R = ret_all[src];
+    dvalue[r] = -(R - v) * inv_rows;
+    s_sur = fminf(cpi, clp); s_v = 0.5f * (R - v) * (R - v); s_ratio = ratio; s_kl = kl; s_cnt = 1.f;
+  }
+  /* block reduction of the statistics */
+  __shared__ float red[6][8];
+  float vals[6] = {s_sur, s_v, s_ratio, s_kl, s_mir, s_cnt};
+#pragma unroll
+  for (int q = 0; q < 6; q++) {
+    float x = vals[q];
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if ((threadIdx.x & 31) == 0) red[q][threadIdx.x >> 5] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    float x = 0;
+    for (int w = 0; w < (blockDim.x >> 5); w++) x += red[threadIdx.x][w];
+    atomicAdd(&stats[threadIdx.x], (double)x);
+  }
+}
+
+extern "C" int apex_ppo_loss(int rows, int adim, const float *mu, const float *mu_mir, const int64_t *idx, const float *act_all,
+                             const float *oldlogp_all, const float *adv_all, const float *ret_all, const float *oldmu_all,
+                             const float *value, const float *sigma, float clip, float mirror_coeff, const int *amir_src,
+                             const float *amir_sign, float *dmu, float *dmu_mir, float *dvalue, double *stats, void *stream) {
+  if (rows <= 0) return 0;
+  k_ppo_loss<<<(rows + 255) / 256, 256, 0, (cudaStream_t)stream>>>(rows, adim, mu, mu_mir, nullptr, idx, act_all, oldlogp_all, adv_all,
+                                                                  ret_all, oldmu_all, value, sigma, clip, mirror_coeff, amir_src,
+                                                                  amir_sign, 1.0f / (float)rows, dmu, dmu_mir, dvalue, stats);
+  return last_err();
+}
+
+/* ===================================================================================================
+ * gradient norms per parameter group, clip_grad_norm_ + Adam (torch semantics: eps added to sqrt(v_hat))
+ * =================================================================================================== */
+__global__ void k_sumsq(const float *__restrict__ g, int n, double *__restrict__ out) {
+  float s = 0.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) s += g[i] * g[i];
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  __shared__ float red[8];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float x = 0;
+    for (int w = 0; w < (blockDim.x >> 5); w++) x += red[w];
+    atomicAdd(out, (double)x);
+  }
+}
+__global__ void k_adam(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m, float *__restrict__ v, int n,
+                       const double *__restrict__ sumsq, float gscale, float max_norm, float lr, float beta1, float beta2, float eps,
+                       float bc1, float bc2) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float norm = sqrtf((float)(*sumsq)) * gscale;
+  const float coef = fminf(max_norm / (norm + 1e-6f), 1.0f); /* torch.nn.utils.clip_grad_norm_ */
+  const float gi = g[i] * gscale * coef;
+  const float mi = beta1 * m[i] + (1.f - beta1) * gi, vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+  m[i] = mi; v[i] = vi;
+  const float denom = sqrtf(vi) / sqrtf(bc2) + eps;
+  p[i] -= (lr / bc1) * (mi / denom);
+}
+
+extern "C" int apex_grad_sumsq(const float *g, int n, double *out, void *stream) {
+  if (n <= 0) return 0;
+  k_sumsq<<<min(148, (n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(g, n, out);
+  return last_err();
+}
+extern "C" int apex_adam_step(float *p, const float *g, float *m, float *v, int n, const double *sumsq, float gscale, float max_norm,
+                              float lr, float beta1, float beta2, float eps, int step, void *stream) {
+  if (n <= 0) return 0;
+  const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
+  k_adam<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, sumsq, gscale, max_norm, lr, beta1, beta2, eps, bc1, bc2);
+  return last_err();
+}
+
+/* ===================================================================================================
+ * reverse return / GAE scan over time for a [T, N] buffer.  One CTA = 32 envs (coalesced rows of 32 floats are
+ * staged through shared memory), one warp = one env, each lane owns a contiguous run of time steps and the
+ * affine maps x_t = a_t x_{t+1} + b_t are composed across lanes with a warp shuffle scan.
+ *   delta_t = r_t + gamma * vnext_t - v_t,  vnext_t = v_{t+1} | last_val (t = T-1) | 0 (terminal) | term_val_t (time-out)
+ *   A_t = delta_t + gamma * lam * (1 - end_t) * A_{t+1},  ret_t = A_t + v_t      (lam = 1: ppo.py:73-89)
+ * =================================================================================================== */
+#define SCAN_TMAX 512
+__global__ void __launch_bounds__(1024) k_gae_scan(int T, int N, const float *__restrict__ rew, const float *__restrict__ val,
+                                                   const int *__restrict__ done, const float *__restrict__ term_val,
+                                                   const float *__restrict__ last_val, float gamma, float lam, float *__restrict__ ret,
+                                                   float *__restrict__ adv) {
+  extern __shared__ float sm[]; /* a[T][33], b[T][33] */
+  float *sa = sm, *sb = sm + (size_t)T * 33;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n0 = blockIdx.x * 32;
+  const int n = n0 + lane;
+  for (int t = warp; t < T; t += 32) {
+    float a = 0.f, b = 0.f;
+    if (n < N) {
+      const long o = (long)t * N + n;
+      const int d = done[o];
+      const float v = val[o];
+      float vnext;
+      if (d & 1) vnext = 0.f;
+      else if (d & 2) vnext = term_val[o];
+      else vnext = (t == T - 1) ? last_val[n] : val[o + N];
+      a = d ? 0.f : gamma * lam;
+      b = rew[o] + gamma * vnext - v;
+    }
+    sa[t * 33 + lane] = a; sb[t * 33 + lane] = b;
+  }
+  __syncthreads();
+  /* warp `warp` scans env n0 + warp; lane owns times [lane*per, (lane+1)*per) */
+  const int env = n0 + warp;
+  if (env >= N) return;
+  const int per = (T + 31) / 32, tb = lane * per, te = min(T, tb + per);
+  /* compose this lane's segment from its last step backwards: x_tb = Aseg * x_te + Bseg */
+  float Aseg = 1.f, Bseg = 0.f;
+  for (int t = te - 1; t >= tb; t--) {
+    const float a = sa[t * 33 + warp], b = sb[t * 33 + warp];
+    Bseg = a * Bseg + b; /* x_t = a (Aseg x_te + Bseg) + b */
+    Aseg = a * Aseg;
+  }
+  /* suffix scan over lanes: carry_in(lane) = x at time te = value produced by lanes > lane, x_T = 0 */
+  float ca = Aseg, cb = Bseg; /* composition of segments lane .. 31 applied to x_T */
+  for (int o = 1; o < 32; o <<= 1) {
+    const float ua = __shfl_down_sync(0xffffffffu, ca, o), ub = __shfl_down_sync(0xffffffffu, cb, o);
+    if (lane + o < 32) { cb = ca * ub + cb; ca = ca * ua; }
+  }
+  float x = __shfl_down_sync(0xffffffffu, cb, 1); /* x at the start of the next lane's segment (x_T = 0 folded in) */
+  if (lane == 31) x = 0.f;
+  for (int t = te - 1; t >= tb; t--) {
+    x = sa[t * 33 + warp] * x + sb[t * 33 + warp];
+    sb[t * 33 + warp] = x; /* reuse the b tile for the advantages */
+  }
+  __syncthreads();
+  for (int t = warp; t < T; t += 32)
+    if (n < N) {
+      const long o = (long)t * N + n;
+      const float A = sb[t * 33 + lane];
+      adv[o] = A;
+      ret[o] = A + val[o];
+    }
+}
+
+extern "C" int apex_gae_scan(int T, int N, const float *rew, const float *val, const int *done, const float *term_val,
+                             const float *last_val, float gamma, float lam, float *ret, float *adv, void *stream) {
+  if (T <= 0 || N <= 0) return 0;
+  if (T > SCAN_TMAX) return -1000;
+  const size_t smem = (size_t)T * 33 * 2 * sizeof(float);
+  CK(cudaFuncSetAttribute(k_gae_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_gae_scan<<<(N + 31) / 32, 1024, smem, (cudaStream_t)stream>>>(T, N, rew, val, done, term_val, last_val, gamma, lam, ret, adv);
+  return last_err();
+}
+
+/* advantage statistics (sum, sum of squares, count as doubles) and in-place normalisation (ppo.py:396: unbiased std + eps) */
+__global__ void k_moments(const float *__restrict__ x, long n, double *__restrict__ out) {
+  double s = 0, q = 0;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) { const double v = x[i]; s += v; q += v * v; }
+  for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+  __shared__ double rs[8], rq[8];
+  if ((threadIdx.x & 31) == 0) { rs[threadIdx.x >> 5] = s; rq[threadIdx.x >> 5] = q; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0, b = 0;
+    for (int w = 0; w < (blockDim.x >> 5); w++) { a += rs[w]; b += rq[w]; }
+    atomicAdd(&out[0], a); atomicAdd(&out[1], b);
+    if (blockIdx.x == 0) atomicAdd(&out[2], (double)n);
+  }
+}
+__global__ void k_normalize(float *__restrict__ x, long n, const double *__restrict__ mom, float eps) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double cnt = mom[2], mean = mom[0] / cnt;
+  const double var = (mom[1] - cnt * mean * mean) / (cnt - 1.0);
+  x[i] = (float)(((double)x[i] - mean) / (sqrt(var > 0 ? var : 0) + (double)eps));
+}
+extern "C" int apex_moments(const float *x, long n, double *out3, void *stream) {
+  if (n <= 0) return 0;
+  k_moments<<<296, 256, 0, (cudaStream_t)stream>>>(x, n, out3);
+  return last_err();
+}
+extern "C" int apex_normalize(float *x, long n, const double *mom3, float eps, void *stream) {
+  if (n <= 0) return 0;
+  k_normalize<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, n, mom3, eps);
+  return last_err();
+}

@@ -68,15 +68,18 @@ class BatchedCassieEnv:
                                                     self.obs.data_ptr(), self._stream()), "env_reset")
         return self.obs
 
-    def step(self, action, f_term=0):
-        """action [N, 10] on the device -> (obs [N, 50], reward [N], done [N] int32 (bit0 terminal, bit1 time-out), {})."""
+    def step(self, action, f_term=0, rew_out=None, done_out=None):
+        """action [N, 10] on the device -> (obs [N, 50], reward [N], done [N] int32 (bit0 terminal, bit1 time-out), {}).
+        rew_out / done_out: optional contiguous device tensors that receive reward and done (e.g. rollout-buffer rows)."""
         a = action.to(device=self.device, dtype=self.dtype).contiguous()
         assert a.shape == (self.num_envs, 10)
+        rew = self.rew if rew_out is None else rew_out
+        done = self.done if done_out is None else done_out
         with torch.cuda.device(self.device):
             _lib.check(self.L.apex_cassie_env_step(self.dt, self.st.data_ptr(), self.sti.data_ptr(), self.num_envs, a.data_ptr(),
-                                                   self.obs.data_ptr(), self.rew.data_ptr(), self.done.data_ptr(),
+                                                   self.obs.data_ptr(), rew.data_ptr(), done.data_ptr(),
                                                    self.term_obs.data_ptr(), self.max_traj_len, self._stream()), "env_step")
-        return self.obs, self.rew, self.done, {}
+        return self.obs, rew, done, {}
 
     def set_command(self, speed=None, side_speed=None, phase=None):
         """Synthetic-input hook: overwrite commanded speed / side speed / phase for all envs."""

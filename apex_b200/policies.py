@@ -1,0 +1,90 @@
+"""Actor / critic modules with the reference's parameter names and conventions, so checkpoints interoperate.
+
+Reference: rl/policies/actor.py:142-215 (Gaussian_FF_Actor), rl/policies/critic.py:37-74 (FF_V),
+rl/policies/base.py:7-13 (normc_fn).  state_dict keys: actor_layers.{0,1}.{weight,bias}, means.{weight,bias};
+critic_layers.{0,1}.{weight,bias}, network_out.{weight,bias}; obs_mean / obs_std are plain attributes.
+The modules own the parameters; the rollout and the PPO update read them through `flat_views` (one contiguous
+device buffer for actor + critic, so the hand-written kernels and the single gradient all-reduce see one array).
+"""
+import torch
+import torch.nn as nn
+
+
+def normc_fn(m):
+    if m.__class__.__name__.find("Linear") != -1:
+        m.weight.data.normal_(0, 1)
+        m.weight.data *= 1 / torch.sqrt(m.weight.data.pow(2).sum(1, keepdim=True))
+        if m.bias is not None:
+            m.bias.data.fill_(0)
+
+
+class Gaussian_FF_Actor(nn.Module):
+    def __init__(self, state_dim, action_dim, layers=(256, 256), env_name=None, fixed_std=None, normc_init=True):
+        super().__init__()
+        if fixed_std is None:
+            raise NotImplementedError("learned std is not on the PPO hot path (ppo.py:536 always passes fixed_std)")
+        self.actor_layers = nn.ModuleList([nn.Linear(state_dim, layers[0])] +
+                                          [nn.Linear(layers[i], layers[i + 1]) for i in range(len(layers) - 1)])
+        self.means = nn.Linear(layers[-1], action_dim)
+        self.fixed_std = fixed_std
+        self.learn_std = False
+        self.action_dim, self.env_name = action_dim, env_name
+        self.obs_std, self.obs_mean = 1.0, 0.0
+        self.is_recurrent = False
+        if normc_init:
+            self.apply(normc_fn)
+            self.means.weight.data.mul_(0.01)
+
+    def _get_dist_params(self, state):
+        x = (state - self.obs_mean) / self.obs_std
+        for l in self.actor_layers:
+            x = torch.relu(l(x))
+        return self.means(x), self.fixed_std
+
+    def forward(self, state, deterministic=True, anneal=1.0):
+        mu, sd = self._get_dist_params(state)
+        sd = sd * anneal
+        return mu if deterministic else torch.distributions.Normal(mu, sd).sample()
+
+    def distribution(self, inputs):
+        mu, sd = self._get_dist_params(inputs)
+        return torch.distributions.Normal(mu, sd)
+
+
+class FF_V(nn.Module):
+    def __init__(self, state_dim, layers=(256, 256), env_name="NOT SET", normc_init=True, obs_std=None, obs_mean=None):
+        super().__init__()
+        self.critic_layers = nn.ModuleList([nn.Linear(state_dim, layers[0])] +
+                                           [nn.Linear(layers[i], layers[i + 1]) for i in range(len(layers) - 1)])
+        self.network_out = nn.Linear(layers[-1], 1)
+        self.env_name, self.obs_std, self.obs_mean = env_name, obs_std, obs_mean
+        self.is_recurrent = False
+        if normc_init:
+            self.apply(normc_fn)
+        self.train()
+
+    def forward(self, inputs):
+        if not self.training:  # critic.py:66 — the critic normalises its input only in eval mode
+            inputs = (inputs - self.obs_mean) / self.obs_std
+        x = inputs
+        for l in self.critic_layers:
+            x = torch.relu(l(x))
+        return self.network_out(x)
+
+
+def flatten_modules(modules, device):
+    """Re-home every parameter of `modules` into one contiguous float32 device buffer (and one for gradients).
+    Returns (flat_params, flat_grads, [(name, offset, shape)])."""
+    params = [(f"{mi}.{n}", p) for mi, m in enumerate(modules) for n, p in m.named_parameters()]
+    total = sum(p.numel() for _, p in params)
+    flat = torch.zeros(total, dtype=torch.float32, device=device)
+    grad = torch.zeros(total, dtype=torch.float32, device=device)
+    index, off = [], 0
+    for name, p in params:
+        n = p.numel()
+        flat[off:off + n].copy_(p.data.reshape(-1))
+        p.data = flat[off:off + n].view(p.shape)
+        p.grad = grad[off:off + n].view(p.shape)
+        index.append((name, off, tuple(p.shape)))
+        off += n
+    return flat, grad, index

@@ -1,0 +1,333 @@
+"""GPU-resident PPO (host-side mirror of rl/algos/ppo.py's PPO class for the batched Cassie env).
+
+Kept from the reference (file:line in /root/reference/rl/algos/ppo.py):
+  PPO(args: dict, save_path)                                   :98-127
+  sample_parallel(env_fn, policy, critic, min_steps, max_traj_len, deterministic, anneal, term_thresh) -> buffer   :188-237
+      buffer.get() -> (states, actions, returns, values), .ep_returns, .ep_lens, len(buffer)          :91-97
+  update_policy(obs, act, ret, adv, mask, env_fn, mirror_observation, mirror_action)
+      -> (actor_loss, entropy, critic_loss, ratio, kl, mirror_loss)                                    :276-345
+  train-loop pieces: advantage normalisation :395-396, epochs x shuffled minibatches with drop_last :407-451,
+      KL early stop on the last minibatch's KL :449, save(actor.pt / critic.pt) :129-137.
+What changes: rollouts are a fixed [T, N] horizon over N device-resident envs (episodes continue across
+iterations and are bootstrapped with V at the horizon), pi_old's log-probabilities are stored at sampling time
+(identical to evaluating old_policy, which equals the sampling policy), and every tensor op on the path is one of
+the hand-written kernels in apex_b200/csrc (no autograd, no cuBLAS).  With world_size > 1 each rank owns N envs and
+the flattened actor+critic gradient is all-reduced once per optimizer step over NCCL.
+"""
+import math
+import os
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _capi
+from .policies import flatten_modules
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+class RolloutBuffer:
+    """[T, N] device buffers of one sampling phase (the PPOBuffer of the reference, ppo.py:26-97)."""
+
+    def __init__(self, T, N, obs_dim, act_dim, device):
+        f = dict(dtype=torch.float32, device=device)
+        self.T, self.N = T, N
+        self.obs = torch.zeros((T, N, obs_dim), **f)
+        self.act = torch.zeros((T, N, act_dim), **f)
+        self.mu = torch.zeros((T, N, act_dim), **f)
+        self.logp = torch.zeros((T, N), **f)
+        self.rew = torch.zeros((T, N), **f)
+        self.val = torch.zeros((T, N), **f)
+        self.term_val = torch.zeros((T, N), **f)
+        self.done = torch.zeros((T, N), dtype=torch.int32, device=device)
+        self.last_val = torch.zeros((N,), **f)
+        self.ret = torch.zeros((T, N), **f)
+        self.adv = torch.zeros((T, N), **f)
+
+    def __len__(self):
+        return self.T * self.N
+
+    def get(self):
+        return (self.obs.view(-1, self.obs.shape[-1]), self.act.view(-1, self.act.shape[-1]), self.ret.view(-1, 1),
+                self.val.view(-1, 1))
+
+    def _episodes(self):
+        """Returns / lengths of the episodes that both started and ended inside this buffer (logging only)."""
+        d = self.done != 0
+        idx = torch.nonzero(d.t(), as_tuple=False)  # (env, t), sorted by env then t
+        if idx.shape[0] < 2:
+            return [], []
+        csum = torch.cumsum(self.rew.double(), dim=0)
+        env, t = idx[:, 0], idx[:, 1]
+        first = torch.ones_like(env, dtype=torch.bool)
+        first[1:] = env[1:] != env[:-1]
+        prev_t = torch.roll(t, 1)
+        keep = ~first
+        rets = (csum[t, env] - csum[prev_t, env])[keep]
+        lens = (t - prev_t)[keep]
+        return rets.float().tolist(), lens.tolist()
+
+    @property
+    def ep_returns(self):
+        return self._episodes()[0]
+
+    @property
+    def ep_lens(self):
+        return self._episodes()[1]
+
+
+class PPO:
+    def __init__(self, args, save_path=None):
+        self.env_name = args.get("env_name", "Cassie-v0")
+        self.gamma = args.get("gamma", 0.99)
+        self.lam = args.get("lam", 1.0)  # the reference parses --lam but its returns are lam = 1 (ppo.py:73-89)
+        self.lr = args.get("lr", 1e-4)
+        self.eps = args.get("eps", 1e-5)
+        self.entropy_coeff = args.get("entropy_coeff", 0.0)
+        self.clip = args.get("clip", 0.2)
+        self.minibatch_size = args.get("minibatch_size", 64)
+        self.epochs = args.get("epochs", 3)
+        self.num_steps = args.get("num_steps", 5096)
+        self.max_traj_len = args.get("max_traj_len", 400)
+        self.grad_clip = args.get("max_grad_norm", 0.05)
+        self.mirror_coeff = 0.4 if args.get("mirror", True) else 0.0
+        self.seed = int(args.get("seed", 0))
+        self.save_path = save_path
+        self.total_steps = 0
+        self.highest_reward = -1
+        self.L = _capi.lib()
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.env = None
+        self.buf = None
+        self._opt_step = [0, 0]
+        self._sample_calls = 0
+        self.launches = 0  # kernels of ours launched (bench.py reports it)
+
+    # ------------------------------------------------------------------ setup
+    def attach(self, policy, critic, env):
+        """Bind the modules and the batched env: parameters are re-homed into one flat device buffer."""
+        dev = env.device
+        self.device = dev
+        self.policy, self.critic, self.env = policy, critic, env
+        policy.to(dev)
+        critic.to(dev)
+        self.flat, self.grad, index = flatten_modules([policy, critic], dev)
+        self.off = {name: off for name, off, _ in index}
+        self.n_actor = sum(p.numel() for p in policy.parameters())
+        self.n_total = self.flat.numel()
+        self.adam_m = torch.zeros_like(self.flat)
+        self.adam_v = torch.zeros_like(self.flat)
+        self.sumsq = torch.zeros(2, dtype=torch.float64, device=dev)
+        self.stats = torch.zeros(6, dtype=torch.float64, device=dev)
+        self.mom = torch.zeros(3, dtype=torch.float64, device=dev)
+        od, ad = env.observation_space.shape[0], env.action_space.shape[0]
+        self.obs_dim, self.act_dim, self.hid = od, ad, policy.actor_layers[0].out_features
+        f = dict(dtype=torch.float32, device=dev)
+        sd = policy.fixed_std
+        self.sigma = (sd.to(**f) if torch.is_tensor(sd) else torch.full((ad,), float(sd), **f)).contiguous()
+        self.set_obs_normalization(policy.obs_mean, policy.obs_std)
+
+        def table(m):  # mirror tables (rl/envs/wrappers.py:70-77): (x @ M)[j] = sign * x[src]
+            n = len(m)
+            src, sign = np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.float32)
+            for i, v in enumerate(m):
+                src[int(abs(v))] = i
+                sign[int(abs(v))] = 1.0 if v > 0 else -1.0  # 0.1 / -0.1 encode +0 / -0 (cassie.py:69,244)
+            return torch.as_tensor(src, device=dev), torch.as_tensor(sign, device=dev)
+
+        self.omir_src, self.omir_sign = table(env.mirrored_obs)
+        self.amir_src, self.amir_sign = table(env.mirrored_acts)
+        cm = np.zeros(od, dtype=np.int32)
+        cm[env.clock_inds] = 1
+        self.clock_mask = torch.as_tensor(cm, device=dev)
+        N = env.num_envs
+        self.xn = torch.zeros((N, od), **f)
+        self.h = [torch.zeros((N, self.hid), **f) for _ in range(4)]
+        self.cur_obs = None
+
+    def set_obs_normalization(self, mean, std):
+        f = dict(dtype=torch.float32, device=self.device)
+        od = self.env.observation_space.shape[0]
+        self.obs_mean = (torch.as_tensor(mean, **f) * torch.ones(od, **f)).contiguous()
+        self.obs_std = (torch.as_tensor(std, **f) * torch.ones(od, **f)).contiguous()
+        self.policy.obs_mean, self.policy.obs_std = self.obs_mean, self.obs_std
+        self.critic.obs_mean, self.critic.obs_std = self.obs_mean, self.obs_std
+
+    def _s(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _w(self, net, name):
+        off = self.off[("0." if net == 0 else "1.") + name]
+        return self.flat.data_ptr() + 4 * off, self.grad.data_ptr() + 4 * off
+
+    def _actor_ptrs(self):
+        return [self._w(0, n) for n in ("actor_layers.0.weight", "actor_layers.0.bias", "actor_layers.1.weight",
+                                        "actor_layers.1.bias", "means.weight", "means.bias")]
+
+    def _critic_ptrs(self):
+        return [self._w(1, n) for n in ("critic_layers.0.weight", "critic_layers.0.bias", "critic_layers.1.weight",
+                                        "critic_layers.1.bias", "network_out.weight", "network_out.bias")]
+
+    def _mlp_fwd(self, ptrs, x, rows, out_dim, h1, h2, y):
+        _capi.check(self.L.apex_mlp_forward(_p(x), rows, self.obs_dim, self.hid, out_dim, ptrs[0][0], ptrs[1][0], ptrs[2][0],
+                                            ptrs[3][0], ptrs[4][0], ptrs[5][0], _p(h1), _p(h2), _p(y), self._s()), "mlp_forward")
+        self.launches += 3
+
+    def _mlp_bwd(self, ptrs, x, rows, out_dim, h1, h2, dy, dh2, dh1):
+        _capi.check(self.L.apex_mlp_backward(_p(x), rows, self.obs_dim, self.hid, out_dim, ptrs[2][0], ptrs[4][0], _p(h1), _p(h2),
+                                             _p(dy), _p(dh2), _p(dh1), ptrs[0][1], ptrs[1][1], ptrs[2][1], ptrs[3][1], ptrs[4][1],
+                                             ptrs[5][1], self._s()), "mlp_backward")
+        self.launches += 8
+
+    # ------------------------------------------------------------------ sampling
+    @torch.no_grad()
+    def sample_parallel(self, env_fn, policy, critic, min_steps, max_traj_len, deterministic=False, anneal=1.0, term_thresh=0):
+        """Collect ceil(min_steps / N) steps from each of the N envs of this rank (ppo.py:188-237)."""
+        if self.env is None:
+            self.attach(policy, critic, env_fn())
+        env, N = self.env, self.env.num_envs
+        env.max_traj_len = int(max_traj_len)
+        T = max(1, math.ceil(min_steps / N))
+        if self.buf is None or self.buf.T != T:
+            self.buf = RolloutBuffer(T, N, self.obs_dim, self.act_dim, self.device)
+        buf = self.buf
+        if self.cur_obs is None:
+            self.cur_obs = env.reset()
+            self.launches += 1
+        ap, cp = self._actor_ptrs(), self._critic_ptrs()
+        L, s = self.L, self._s()
+        self._sample_calls += 1
+        seed = (self.seed * 0x9E3779B1 + 0x5BD1E995 * self._sample_calls) & 0xFFFFFFFF
+        for t in range(T):
+            obs_t = buf.obs[t]
+            obs_t.copy_(self.cur_obs)
+            _capi.check(L.apex_prepare_obs(_p(obs_t), None, N, self.obs_dim, _p(self.obs_mean), _p(self.obs_std), None, None, None,
+                                           None, _p(self.xn), None, s), "prepare_obs")
+            self._mlp_fwd(ap, self.xn, N, self.act_dim, self.h[0], self.h[1], buf.mu[t])
+            self._mlp_fwd(cp, obs_t, N, 1, self.h[2], self.h[3], buf.val[t])  # critic in train mode: raw obs (critic.py:66)
+            _capi.check(L.apex_gaussian_sample(_p(buf.mu[t]), _p(self.sigma), float(anneal), N, self.act_dim, seed, t,
+                                               self.rank * N, _p(buf.act[t]), _p(buf.logp[t]), s), "gaussian_sample")
+            obs, _, _, _ = env.step(buf.act[t], rew_out=buf.rew[t], done_out=buf.done[t])
+            self._mlp_fwd(cp, env.term_obs, N, 1, self.h[2], self.h[3], buf.term_val[t])  # V(s_T) of time-limit cuts
+            self.cur_obs = obs
+            self.launches += 3
+        self._mlp_fwd(cp, self.cur_obs, N, 1, self.h[2], self.h[3], buf.last_val)
+        _capi.check(L.apex_gae_scan(T, N, _p(buf.rew), _p(buf.val), _p(buf.done), _p(buf.term_val), _p(buf.last_val),
+                                    float(self.gamma), float(self.lam), _p(buf.ret), _p(buf.adv), s), "gae_scan")
+        self.launches += 1
+        return buf
+
+    @torch.no_grad()
+    def normalize_advantages(self, buf):
+        """advantages = returns - values, (A - mean) / (std_unbiased + eps) over the whole (global) batch (ppo.py:395-396)."""
+        self.mom.zero_()
+        _capi.check(self.L.apex_moments(_p(buf.adv), buf.adv.numel(), _p(self.mom), self._s()), "moments")
+        if self.world > 1:
+            dist.all_reduce(self.mom)
+        _capi.check(self.L.apex_normalize(_p(buf.adv), buf.adv.numel(), _p(self.mom), float(self.eps), self._s()), "normalize")
+        self.launches += 2
+
+    # ------------------------------------------------------------------ update
+    def _ensure_mb(self, B):
+        if getattr(self, "_mbB", 0) == B:
+            return
+        f = dict(dtype=torch.float32, device=self.device)
+        self._mbB = B
+        self.mb_x = torch.zeros((2 * B, self.obs_dim), **f)  # [normalised obs ; normalised mirrored obs]
+        self.mb_raw = torch.zeros((B, self.obs_dim), **f)
+        self.mb_h1 = torch.zeros((2 * B, self.hid), **f)
+        self.mb_h2 = torch.zeros((2 * B, self.hid), **f)
+        self.mb_dh1 = torch.zeros((2 * B, self.hid), **f)
+        self.mb_dh2 = torch.zeros((2 * B, self.hid), **f)
+        self.mb_mu = torch.zeros((2 * B, self.act_dim), **f)
+        self.mb_dmu = torch.zeros((2 * B, self.act_dim), **f)
+        self.mb_g1 = torch.zeros((B, self.hid), **f)
+        self.mb_g2 = torch.zeros((B, self.hid), **f)
+        self.mb_v = torch.zeros((B,), **f)
+        self.mb_dv = torch.zeros((B,), **f)
+
+    @torch.no_grad()
+    def update_minibatch(self, buf, idx):
+        """One optimizer step of actor and critic on the rows `idx` (int64, device) of the flattened buffer."""
+        B = idx.numel()
+        self._ensure_mb(B)
+        L, s = self.L, self._s()
+        mirror = self.mirror_coeff > 0
+        rows_a = 2 * B if mirror else B
+        obs_all = buf.obs.view(-1, self.obs_dim)
+        _capi.check(L.apex_prepare_obs(_p(obs_all), _p(idx), B, self.obs_dim, _p(self.obs_mean), _p(self.obs_std), _p(self.omir_src),
+                                       _p(self.omir_sign), _p(self.clock_mask), _p(self.mb_raw), _p(self.mb_x),
+                                       _p(self.mb_x[B:]) if mirror else None, s), "prepare_obs")
+        ap, cp = self._actor_ptrs(), self._critic_ptrs()
+        self._mlp_fwd(ap, self.mb_x, rows_a, self.act_dim, self.mb_h1, self.mb_h2, self.mb_mu)
+        self._mlp_fwd(cp, self.mb_raw, B, 1, self.mb_g1, self.mb_g2, self.mb_v)
+        self.stats.zero_()
+        self.grad.zero_()
+        self.sumsq.zero_()
+        _capi.check(L.apex_ppo_loss(B, self.act_dim, _p(self.mb_mu), _p(self.mb_mu[B:]) if mirror else None, _p(idx),
+                                    _p(buf.act.view(-1, self.act_dim)), _p(buf.logp.view(-1)), _p(buf.adv.view(-1)),
+                                    _p(buf.ret.view(-1)), _p(buf.mu.view(-1, self.act_dim)), _p(self.mb_v), _p(self.sigma),
+                                    float(self.clip), float(self.mirror_coeff), _p(self.amir_src), _p(self.amir_sign),
+                                    _p(self.mb_dmu), _p(self.mb_dmu[B:]) if mirror else None, _p(self.mb_dv), _p(self.stats), s),
+                    "ppo_loss")
+        self._mlp_bwd(ap, self.mb_x, rows_a, self.act_dim, self.mb_h1, self.mb_h2, self.mb_dmu, self.mb_dh2, self.mb_dh1)
+        self._mlp_bwd(cp, self.mb_raw, B, 1, self.mb_g1, self.mb_g2, self.mb_dv, self.mb_dh2, self.mb_dh1)
+        gscale = 1.0
+        if self.world > 1:  # one all-reduce of the flattened actor+critic gradient per optimizer step
+            dist.all_reduce(self.grad)
+            gscale = 1.0 / self.world
+        na, nt = self.n_actor, self.n_total
+        gp, pp, mp, vp = self.grad.data_ptr(), self.flat.data_ptr(), self.adam_m.data_ptr(), self.adam_v.data_ptr()
+        _capi.check(L.apex_grad_sumsq(gp, na, self.sumsq.data_ptr(), s), "sumsq")
+        _capi.check(L.apex_grad_sumsq(gp + 4 * na, nt - na, self.sumsq.data_ptr() + 8, s), "sumsq")
+        self._opt_step[0] += 1
+        self._opt_step[1] += 1
+        _capi.check(L.apex_adam_step(pp, gp, mp, vp, na, self.sumsq.data_ptr(), gscale, float(self.grad_clip), float(self.lr),
+                                     0.9, 0.999, float(self.eps), self._opt_step[0], s), "adam")
+        _capi.check(L.apex_adam_step(pp + 4 * na, gp + 4 * na, mp + 4 * na, vp + 4 * na, nt - na, self.sumsq.data_ptr() + 8, gscale,
+                                     float(self.grad_clip), float(self.lr), 0.9, 0.999, float(self.eps), self._opt_step[1], s), "adam")
+        self.launches += 6
+
+    def minibatch_scalars(self):
+        """(actor_loss, entropy, critic_loss, ratio, kl, mirror_loss) of the last minibatch — one device->host read."""
+        st = self.stats.tolist()
+        cnt = max(st[5], 1.0)
+        ent = float((0.5 + 0.5 * math.log(2 * math.pi) + torch.log(self.sigma)).mean())
+        return (-st[0] / cnt, ent, st[1] / cnt, st[2] / cnt, st[3] / (cnt * self.act_dim),
+                self.mirror_coeff * st[4] / (cnt * self.act_dim))
+
+    def update_policy(self, obs_batch, action_batch, return_batch, advantage_batch, mask, env_fn, mirror_observation=None,
+                      mirror_action=None):
+        """Reference-shaped entry (ppo.py:276).  On the GPU path a minibatch is a row selection of the current buffer:
+        `obs_batch` carries the int64 row indices and the kernels gather the rows themselves."""
+        self.update_minibatch(self.buf, obs_batch)
+        return self.minibatch_scalars()
+
+    def optimize(self, buf, generator=None):
+        """epochs x shuffled minibatches with drop_last, KL early stop on the last minibatch (ppo.py:407-451)."""
+        n = len(buf)
+        mb = min(self.minibatch_size or n, n)
+        scalars = None
+        for epoch in range(self.epochs):
+            perm = torch.randperm(n, device=self.device, generator=generator)
+            for i in range(0, n - mb + 1, mb):
+                self.update_minibatch(buf, perm[i:i + mb])
+            scalars = self.minibatch_scalars()
+            if scalars[4] > 0.02:
+                break
+        return scalars
+
+    def train_iteration(self, env_fn, policy, critic, anneal=1.0, generator=None):
+        buf = self.sample_parallel(env_fn, policy, critic, self.num_steps, self.max_traj_len, anneal=anneal)
+        self.normalize_advantages(buf)
+        self.total_steps += len(buf) * self.world
+        return buf, self.optimize(buf, generator)
+
+    def save(self, policy, critic):
+        os.makedirs(self.save_path, exist_ok=True)
+        torch.save(policy, os.path.join(self.save_path, "actor.pt"))
+        torch.save(critic, os.path.join(self.save_path, "critic.pt"))

@@ -1,0 +1,52 @@
+/* C-ABI of libapex_b200.so — learner-side kernels of the PPO path (float32, device pointers, cudaStream_t as void*).
+ *
+ * Each entry point replaces a piece of rl/algos/ppo.py that the reference runs as PyTorch-on-CPU code:
+ *   apex_gae_scan        PPOBuffer.finish_path (ppo.py:73-89) for every env at once; lam = 1 reproduces it exactly
+ *   apex_moments / apex_normalize   advantage normalisation (ppo.py:395-396)
+ *   apex_mlp_forward / apex_mlp_backward   Gaussian_FF_Actor / FF_V trunks (rl/policies/actor.py:183-197, critic.py:65-74)
+ *   apex_gaussian_sample torch.distributions.Normal(mu, sd).sample() + log_prob (actor.py:199-215)
+ *   apex_prepare_obs     minibatch gather, observation normalisation, SymmetricEnv.mirror_clock_observation
+ *                        (rl/envs/wrappers.py:59-67)
+ *   apex_ppo_loss        the loss block of PPO.update_policy (ppo.py:276-317) forward + backward
+ *   apex_grad_sumsq / apex_adam_step   clip_grad_norm_ + Adam.step (ppo.py:319-330)
+ * Return value: 0 on success, negative cudaError_t otherwise (-1000 = bad argument).
+ */
+#ifndef APEX_PPO_H
+#define APEX_PPO_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* y = W3 relu(W2 relu(W1 x + b1) + b2) + b3; W are torch Linear weights [out, in]; h1, h2 [rows, hid] are kept for backward */
+int apex_mlp_forward(const float *x, int rows, int in_dim, int hid, int out_dim, const float *w1, const float *b1, const float *w2,
+                     const float *b2, const float *w3, const float *b3, float *h1, float *h2, float *y, void *stream);
+/* accumulates (+=) into gw*, gb*; dh2, dh1 [rows, hid] are scratch */
+int apex_mlp_backward(const float *x, int rows, int in_dim, int hid, int out_dim, const float *w2, const float *w3, const float *h1,
+                      const float *h2, const float *dy, float *dh2, float *dh1, float *gw1, float *gb1, float *gw2, float *gb2,
+                      float *gw3, float *gb3, void *stream);
+/* rows of obs (optionally gathered through idx) -> raw copy, normalised copy, mirrored + normalised copy (any may be NULL) */
+int apex_prepare_obs(const float *obs, const int64_t *idx, int rows, int dim, const float *mean, const float *stdv,
+                     const int *mir_src, const float *mir_sign, const int *clock_mask, float *raw, float *xn, float *xn_mir,
+                     void *stream);
+/* act = mu + sigma * anneal * N(0,1) (Philox keyed by seed, row0 + row, step), logp [rows] */
+int apex_gaussian_sample(const float *mu, const float *sigma, float anneal, int rows, int adim, unsigned seed, unsigned step,
+                         unsigned row0, float *act, float *logp, void *stream);
+/* stats[6] (double, += ): sum surrogate, sum 0.5 (R-V)^2, sum ratio, sum KL (summed over action dims), sum mirror sq. err, count */
+int apex_ppo_loss(int rows, int adim, const float *mu, const float *mu_mir, const int64_t *idx, const float *act_all,
+                  const float *oldlogp_all, const float *adv_all, const float *ret_all, const float *oldmu_all, const float *value,
+                  const float *sigma, float clip, float mirror_coeff, const int *amir_src, const float *amir_sign, float *dmu,
+                  float *dmu_mir, float *dvalue, double *stats, void *stream);
+int apex_grad_sumsq(const float *g, int n, double *out, void *stream); /* out += sum g^2 */
+int apex_adam_step(float *p, const float *g, float *m, float *v, int n, const double *sumsq, float gscale, float max_norm, float lr,
+                   float beta1, float beta2, float eps, int step, void *stream);
+/* rew, val, term_val, ret, adv [T, N]; done [T, N] (bit0 terminal, bit1 time-out); last_val [N]; T <= 512 */
+int apex_gae_scan(int T, int N, const float *rew, const float *val, const int *done, const float *term_val, const float *last_val,
+                  float gamma, float lam, float *ret, float *adv, void *stream);
+int apex_moments(const float *x, long n, double *out3, void *stream);            /* out3 += (sum, sum sq, count) */
+int apex_normalize(float *x, long n, const double *mom3, float eps, void *stream); /* (x - mean) / (std_unbiased + eps) */
+
+#ifdef __cplusplus
+}
+#endif
+#endif
