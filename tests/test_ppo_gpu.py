@@ -88,7 +88,7 @@ def test_update_step_matches_reference_update_policy():
         step_ref = v - before
         step = p.detach().cpu().numpy() - before
         # Adam's first step is lr * sign-like; compare the parameter update itself
-        assert np.allclose(step, step_ref, rtol=2e-3, atol=2e-8), (k, np.abs(step - step_ref).max(), np.abs(step_ref).max())
+        assert np.allclose(step, step_ref, rtol=2e-3, atol=1e-7), (k, np.abs(step - step_ref).max(), np.abs(step_ref).max())
 
 
 def test_gae_scan_matches_finish_path():
