@@ -377,7 +377,7 @@ __global__ void __launch_bounds__(1024) k_gae_scan(int T, int N, const float *__
   __syncthreads();
   /* warp `warp` scans env n0 + warp; lane owns times [lane*per, (lane+1)*per) */
   const int env = n0 + warp;
-  if (env >= N) return;
+  if (env < N) { /* warps past the batch end skip the scan but still take part in the tile copy below */
   const int per = (T + 31) / 32, tb = lane * per, te = min(T, tb + per);
   /* compose this lane's segment from its last step backwards: x_tb = Aseg * x_te + Bseg */
   float Aseg = 1.f, Bseg = 0.f;
@@ -397,6 +397,7 @@ __global__ void __launch_bounds__(1024) k_gae_scan(int T, int N, const float *__
   for (int t = te - 1; t >= tb; t--) {
     x = sa[t * 33 + warp] * x + sb[t * 33 + warp];
     sb[t * 33 + warp] = x; /* reuse the b tile for the advantages */
+  }
   }
   __syncthreads();
   for (int t = warp; t < T; t += 32)

@@ -94,6 +94,7 @@ class PPO:
         self.max_traj_len = args.get("max_traj_len", 400)
         self.grad_clip = args.get("max_grad_norm", 0.05)
         self.mirror_coeff = 0.4 if args.get("mirror", True) else 0.0
+        self.max_kl = args.get("max_kl", 0.02)  # ppo.py:449; None disables the early stop (fixed-work benchmarking)
         self.seed = int(args.get("seed", 0))
         self.save_path = save_path
         self.total_steps = 0
@@ -265,6 +266,7 @@ class PPO:
         ap, cp = self._actor_ptrs(), self._critic_ptrs()
         self._mlp_fwd(ap, self.mb_x, rows_a, self.act_dim, self.mb_h1, self.mb_h2, self.mb_mu)
         self._mlp_fwd(cp, self.mb_raw, B, 1, self.mb_g1, self.mb_g2, self.mb_v)
+        self.launches += 2  # prepare_obs, ppo_loss
         self.stats.zero_()
         self.grad.zero_()
         self.sumsq.zero_()
@@ -317,7 +319,7 @@ class PPO:
             for i in range(0, n - mb + 1, mb):
                 self.update_minibatch(buf, perm[i:i + mb])
             scalars = self.minibatch_scalars()
-            if scalars[4] > 0.02:
+            if self.max_kl is not None and scalars[4] > self.max_kl:
                 break
         return scalars
 

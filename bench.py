@@ -204,7 +204,8 @@ def main():
     torch.manual_seed(0)
     actor = Gaussian_FF_Actor(50, 10, fixed_std=torch.ones(10) * float(np.exp(-1.5)), env_name="Cassie-v0")
     critic = FF_V(50)
-    algo = PPO(dict(num_steps=args.envs * args.horizon, minibatch_size=MINIBATCH, epochs=EPOCHS, max_traj_len=400, seed=0))
+    algo = PPO(dict(num_steps=args.envs * args.horizon, minibatch_size=MINIBATCH, epochs=EPOCHS, max_traj_len=400, seed=0,
+                    max_kl=None))  # fixed work per step: all epochs always run (the reference stops early when KL > 0.02)
     env_fn = lambda: BatchedCassieEnv(args.envs, device=dev, seed=0, dynamics_randomization=True, env_id0=rank * args.envs)
     gen = torch.Generator(device=dev).manual_seed(1234)
 
