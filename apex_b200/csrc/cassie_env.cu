@@ -88,7 +88,7 @@ static int finish() {
 extern "C" {
 
 /* tuning knob (envs per CTA of the step kernel); float64 is capped at 5 by shared memory */
-int apex_cassie_warps_per_cta = 10;
+int apex_cassie_warps_per_cta = 7;
 void apex_cassie_set_warps_per_cta(int w) { apex_cassie_warps_per_cta = w; }
 
 int apex_cassie_state_words(void) { return S_WORDS; }
@@ -144,7 +144,8 @@ int apex_cassie_env_step(int dtype, void *st, int *sti, int n, const void *actio
                          void *term_obs, int max_traj_len, void *stream) {
   if (!action || !obs || !reward || !done) return -1000;
   int wpb = apex_cassie_warps_per_cta;
-  if (dtype == 1 && wpb > 5) wpb = 5;
+  if (dtype == 1 && wpb > 7) wpb = 7;
+  if (wpb > 14) wpb = 14;
   if (wpb < 1) wpb = 1;
   DISPATCH(
       if ((rc = prep(k_env_step<float>, wpb * sizeof(CassieWs<float>)))) return rc;

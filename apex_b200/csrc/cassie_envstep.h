@@ -165,24 +165,25 @@ template <typename T> CW_NOINL void cw_env_obs(CassieWs<T> &w, T *obs_out CW_LAN
 
 /* ---------- mj_setConst at qpos0: dof_invweight0, body_invweight0 (translational), meaninertia ---------- */
 template <typename T> CW_NOINL void cw_set_const(CassieWs<T> &w CW_LANE_PARAM) {
-  /* borrow vec[V_TMP..] is too small for a 35-long qpos: stage qpos0 in the J scratch row 47 */
-  T *q0 = w.J[CW_NEFC - 1];
+  /* stage the 35-long qpos0 in the (currently unused) packed-A storage; J is not safe: kinematics' scratch overlays it */
+  T *q0 = w.Ap;
   CW_FOR_LANES { for (int k = lane; k < CM_NQ; k += 32) q0[k] = (T)CM_qpos0[k]; }
   CW_SYNC();
   cw_kinematics<T>(w, q0 CW_LANE_ARG);
   cw_crb<T>(w CW_LANE_ARG);
-  cw_factor<T>(w, (T)0, false CW_LANE_ARG);
+  cw_build_M<T>(w CW_LANE_ARG);
+  cw_factor<T>(w, (T)0 CW_LANE_ARG);
   T tr = 0;
   for (int i = 0; i < CW_NV; i++) tr += w.Mdiag[i];
   CW_SYNC();
   CW_FOR_LANES { if (lane == 0) w.st[S_MEANINERTIA] = tr / (T)CW_NV; }
   /* (M^-1)_ii = sum_k y_k^2 / D_k with y = L^-T e_i */
-  CW_FOR_LANES { for (int r = 0; r < CW_NV; r++) w.J[r][lane] = (r == lane) ? (T)1 : (T)0; }
+  CW_FOR_LANES { for (int r = 0; r < CW_NV; r++) w.u.J[r][lane] = (r == lane) ? (T)1 : (T)0; }
   CW_SYNC();
   cw_half_solve_rows<T>(w, CW_NV CW_LANE_ARG);
   CW_FOR_LANES {
     T s = 0;
-    for (int k = 0; k < CW_NV; k++) s += w.J[lane][k] * w.J[lane][k] * w.Dinv[k];
+    for (int k = 0; k < CW_NV; k++) s += w.u.J[lane][k] * w.u.J[lane][k] * w.Dinv[k];
     w.vec[V_TMP][lane] = s;
   }
   CW_SYNC();
@@ -205,7 +206,7 @@ template <typename T> CW_NOINL void cw_set_const(CassieWs<T> &w CW_LANE_PARAM) {
       CW_FOR_LANES {
         T col[3];
         cw_jac_col(w, b, off, lane, col);
-        for (int k = 0; k < 3; k++) w.J[3 * bb + k][lane] = col[k];
+        for (int k = 0; k < 3; k++) w.u.J[3 * bb + k][lane] = col[k];
       }
     }
     CW_SYNC();
@@ -214,7 +215,7 @@ template <typename T> CW_NOINL void cw_set_const(CassieWs<T> &w CW_LANE_PARAM) {
       if (lane < nb) {
         T s = 0;
         for (int r = 0; r < 3; r++)
-          for (int k = 0; k < CW_NV; k++) s += w.J[3 * lane + r][k] * w.J[3 * lane + r][k] * w.Dinv[k];
+          for (int k = 0; k < CW_NV; k++) s += w.u.J[3 * lane + r][k] * w.u.J[3 * lane + r][k] * w.Dinv[k];
         w.st[S_BODYINVW + b0 + lane] = cw_max((T)1e-15, s / (T)3);
       }
     }
@@ -364,7 +365,7 @@ template <typename T> CW_NOINL void cw_env_step(CassieWs<T> &w, T *obs_out, T *r
     }
     lfrc += lz; rfrc += rz;
     T dl = 0, dr = 0;
-    for (int k = 0; k < 4; k++) { dl += (T)CW_NEUTRAL_FOOT[k] * w.xquat[CW_LFOOT][k]; dr += (T)CW_NEUTRAL_FOOT[k] * w.xquat[CW_RFOOT][k]; }
+    for (int k = 0; k < 4; k++) { dl += (T)CW_NEUTRAL_FOOT[k] * w.qkeep[1][k]; dr += (T)CW_NEUTRAL_FOOT[k] * w.qkeep[2][k]; }
     lori += 1 - dl * dl; rori += 1 - dr * dr;
     CW_SYNC();
     CW_FOR_LANES {

@@ -54,7 +54,7 @@
 #define CW_NB CM_NBODY
 #define CW_NV CM_NV
 #define CW_NEFC 32 /* constraint-row capacity (njmax analogue): 12 equality + limits + contacts */
-#define CW_NCON 8
+#define CW_NCON 6
 #define CW_OBS 50
 #define CW_ACT 10
 #define CW_SIMRATE 50
@@ -72,39 +72,46 @@ enum {
   S_PREV_ACTION = 290, S_PREV_TORQUE = 300, S_MENC = 310, S_JENC = 320, S_LASTPELVIS = 326,
   S_DAMPING = 329, S_MASS = 361, S_FRICTION = 387, S_FLOORQ = 388, S_DOFINVW = 392, S_BODYINVW = 424, S_MEANINERTIA = 450,
   S_FOOTVEL = 451, /* l_foot_vel(3), r_foot_vel(3) of the last sub-step */
-  S_WORDS = 480
+  S_WORDS = 464
 };
 /* persistent per-env record: int words */
 enum {
   I_DRIVEHIST = 0, I_TIME = 90, I_COUNTER = 91, I_HASPREV = 92, I_HASU = 93, I_DRIVEINIT = 94, I_JOINTINIT = 95,
   I_FLAGS = 96, I_STEPCOUNT = 97, I_RNGCTR = 98, I_ENVID = 99, I_SEED = 100, I_DYNRAND = 101, I_SOLVER_ITER = 102,
-  I_NCON = 103, I_NEFC = 104, I_WORDS = 128
+  I_NCON = 103, I_NEFC = 104, I_WORDS = 112
 };
 /* state_out slice (workspace only) */
 enum { Y_PPOS = 0, Y_QUAT = 3, Y_ROTVEL = 7, Y_TVEL = 10, Y_TACC = 13, Y_MPOS = 16, Y_MVEL = 26, Y_MTORQUE = 36, Y_JPOS = 46, Y_JVEL = 52, Y_WORDS = 58 };
 /* dof-vector slots in ws.vec */
-enum { V_SMOOTH = 0, V_QACCS = 1, V_Z = 2, V_G = 3, V_QACC = 4, V_TMP = 5, V_BIAS = 6, V_NVEC = 7 };
+/* V_BIAS (dead once qfrc_smooth exists) and V_QACC (born after the solver) share the slot of V_Z (dead once efc_b exists) */
+enum { V_SMOOTH = 0, V_QACCS = 1, V_Z = 2, V_BIAS = 2, V_QACC = 2, V_G = 3, V_TMP = 4, V_NVEC = 5 };
 
 template <typename T>
 struct CassieWsPre { /* scratch that is dead before the constraint matrix A is built */
   T cand_dist[32], cand_pos[32][3], cand_n[32][3], cand_hint[32][3];
   T cvel[CW_NB][6], cdd[CW_NV][6], cacc[CW_NB][6], cfrc[CW_NB][6];
+  T xquat[CW_NB][4]; /* body orientations: only the tree sweep needs all of them (pelvis and feet are copied to qkeep) */
 };
 template <typename T>
 struct CassieWs {
   T st[S_WORDS];
   int sti[I_WORDS];
-  T xpos[CW_NB][3], xquat[CW_NB][4], xmat[CW_NB][9];
+  T xpos[CW_NB][3], xmat[CW_NB][9];
+  T qkeep[3][4]; /* world quaternions of the pelvis (imu site), left foot, right foot */
   T cdof[CW_NV][6], crb[CW_NB][10]; /* crb: spatial inertia per body, turned into the composite inertia by cw_crb */
-  T M[CW_NV][CW_NV + 1]; /* [j][i] j<i: mass matrix; [k][j] k>j: U = D_k L[k][j] of M = L^T D L (unscaled rows) */
+  T Ms[CM_MNNZ + 5]; /* tree-sparse strict lower triangle: entry (k, t-th ancestor of k) at CM_dof_rowptr[k] + t; holds the
+                      * mass matrix after cw_build_M and U = D_k L[k][.] (unscaled rows of M = L^T D L) after cw_factor */
   T Mdiag[CW_NV], D[CW_NV], Dinv[CW_NV];
-  T J[CW_NEFC][CW_NV + 1]; /* constraint Jacobian, later B = J L^-1 */
-  union U {
-    T A[CW_NEFC][CW_NEFC + 1];
+  union U { /* the collision / RNE scratch is dead before the first Jacobian row is written */
+    T J[CW_NEFC][CW_NV + 1]; /* constraint Jacobian, later B = J L^-1 */
     CassieWsPre<T> p;
   } u;
-  T efc_pos[CW_NEFC], efc_R[CW_NEFC], efc_jv[CW_NEFC], efc_K[CW_NEFC], efc_B[CW_NEFC], efc_imp[CW_NEFC];
-  T efc_b[CW_NEFC], efc_f[CW_NEFC], efc_res[CW_NEFC], efc_dinv[CW_NEFC];
+  T Ap[CW_NEFC * (CW_NEFC + 1) / 2]; /* A = J M^-1 J^T + R, packed lower triangle: A(i, j), i >= j, at i (i + 1) / 2 + j */
+  T efc_R[CW_NEFC], efc_aref[CW_NEFC]; /* row construction parks diagApprox in efc_R and the violation in efc_aref */
+  T efc_b[CW_NEFC], efc_f[CW_NEFC], efc_dinv[CW_NEFC];
+#ifndef __CUDACC__
+  T efc_res[CW_NEFC]; /* host test build only: on the GPU the PGS residual lives in registers */
+#endif
   int efc_type[CW_NEFC];
   T vec[V_NVEC][CW_NV];
   int ncon, nefc, solver_iter;
@@ -185,6 +192,7 @@ template <typename T> CW_FN void cw_inert_mul(T *f, const T *I, const T *v) {
   f[3] = I[0] * l[0] + t[0]; f[4] = I[0] * l[1] + t[1]; f[5] = I[0] * l[2] + t[2];
 }
 template <typename T> CW_FN T cw_dot6(const T *a, const T *b) { return cw_dot3(a, b) + cw_dot3(a + 3, b + 3); }
+CW_FN int cw_tri(int i, int j) { return i >= j ? i * (i + 1) / 2 + j : j * (j + 1) / 2 + i; } /* packed symmetric index */
 
 CW_FN void cw_philox(uint32_t seed, uint32_t env_id, uint32_t ctr, uint32_t *out) {
   uint32_t c0 = ctr, c1 = 0, c2 = env_id, c3 = 0x9e3779b9u, k0 = seed, k1 = 0xbb67ae85u;
@@ -207,14 +215,14 @@ template <typename T> CW_FN void cw_kinematics(CassieWs<T> &w, const T *qpos CW_
   CW_FOR_LANES {
     if (lane == 0) {
       for (int k = 0; k < 3; k++) w.xpos[0][k] = 0;
-      w.xquat[0][0] = 1; w.xquat[0][1] = w.xquat[0][2] = w.xquat[0][3] = 0;
+      w.u.p.xquat[0][0] = 1; w.u.p.xquat[0][1] = w.u.p.xquat[0][2] = w.u.p.xquat[0][3] = 0;
       for (int k = 0; k < 9; k++) w.xmat[0][k] = (k % 4 == 0) ? (T)1 : (T)0;
       for (int k = 0; k < 10; k++) w.crb[0][k] = 0;
     } else if (lane == 1) { /* pelvis: three world slides (z has ref 1.01 = body z) + ball */
       T q[4] = {qpos[3], qpos[4], qpos[5], qpos[6]};
       cw_qnorm(q);
       for (int k = 0; k < 3; k++) w.xpos[1][k] = qpos[k];
-      for (int k = 0; k < 4; k++) w.xquat[1][k] = q[k];
+      for (int k = 0; k < 4; k++) { w.u.p.xquat[1][k] = q[k]; w.qkeep[0][k] = q[k]; }
       cw_qmat(w.xmat[1], q);
     }
   }
@@ -228,7 +236,7 @@ template <typename T> CW_FN void cw_kinematics(CassieWs<T> &w, const T *qpos CW_
         T pos[3], quat[4], t[3];
         cw_mulv(t, w.xmat[p], bp);
         for (int k = 0; k < 3; k++) pos[k] = w.xpos[p][k] + t[k];
-        cw_qmul(quat, w.xquat[p], bq);
+        cw_qmul(quat, w.u.p.xquat[p], bq);
         if (j >= 0) {
           const int qa = CM_jnt_qposadr[j];
           T qj[4], qn[4];
@@ -245,7 +253,9 @@ template <typename T> CW_FN void cw_kinematics(CassieWs<T> &w, const T *qpos CW_
         }
         cw_qnorm(quat);
         for (int k = 0; k < 3; k++) w.xpos[b][k] = pos[k];
-        for (int k = 0; k < 4; k++) w.xquat[b][k] = quat[k];
+        for (int k = 0; k < 4; k++) w.u.p.xquat[b][k] = quat[k];
+        if (b == CW_LFOOT) for (int k = 0; k < 4; k++) w.qkeep[1][k] = quat[k];
+        if (b == CW_RFOOT) for (int k = 0; k < 4; k++) w.qkeep[2][k] = quat[k];
         cw_qmat(w.xmat[b], quat);
       }
     }
@@ -321,18 +331,16 @@ template <typename T> CW_FN void cw_crb(CassieWs<T> &w CW_LANE_PARAM) {
     }
     CW_SYNC();
   }
+}
+/* M from the composite inertias (lane = dof): diagonal in Mdiag, ancestors' entries in the sparse rows */
+template <typename T> CW_FN void cw_build_M(CassieWs<T> &w CW_LANE_PARAM) {
   CW_FOR_LANES {
     const int i = lane;
     T f[6];
     cw_inert_mul(f, w.crb[CM_dof_body[i]], w.cdof[i]);
     w.Mdiag[i] = cw_dot6(w.cdof[i], f) + (T)CM_dof_armature[i];
-    const int na = CM_dof_nanc[i];
-    for (int t = 0; t < na; t++) {
-      const int j = CM_dof_anc[i][t];
-      const T v = cw_dot6(w.cdof[j], f);
-      w.M[j][i] = v;
-      w.M[i][j] = v;
-    }
+    const int na = CM_dof_nanc[i], rp = CM_dof_rowptr[i];
+    for (int t = 0; t < na; t++) w.Ms[rp + t] = cw_dot6(w.cdof[CM_dof_anc[i][t]], f);
   }
   CW_SYNC();
 }
@@ -340,17 +348,11 @@ template <typename T> CW_FN void cw_crb(CassieWs<T> &w CW_LANE_PARAM) {
 /* sparse L^T D L (mj_factorM): M = L^T D L with the sparsity of the dof tree; rows are kept unscaled
  * (w.M[k][j] = D_k L[k][j]), w.Dinv[k] = 1/D_k.  hdamp = 0: factor M; hdamp = h: factor M + h diag(damping)
  * (mj_Euler's implicit damping).  The elimination itself is generated straight-line code (cassie_gen.h). */
-template <typename T> CW_NOINL void cw_factor(CassieWs<T> &w, T hdamp, bool recopy CW_LANE_PARAM) {
-  CW_FOR_LANES {
-    const int i = lane;
-    w.D[i] = w.Mdiag[i] + hdamp * w.st[S_DAMPING + i];
-    if (recopy) {
-      const int na = CM_dof_nanc[i];
-      for (int t = 0; t < na; t++) { const int j = CM_dof_anc[i][t]; w.M[i][j] = w.M[j][i]; }
-    }
-  }
+template <typename T> CW_NOINL void cw_factor(CassieWs<T> &w, T hdamp CW_LANE_PARAM) {
+  CW_FOR_LANES { w.D[lane] = w.Mdiag[lane] + hdamp * w.st[S_DAMPING + lane]; }
   CW_SYNC();
-  /* the two legs are independent sub-trees hanging off the 6 base dofs: eliminate dof 6+s and 19+s together */
+  /* the two legs are independent sub-trees hanging off the 6 base dofs: eliminate dof 6+s and 19+s together.
+   * Ancestors in increasing dof order are in root-to-leaf order, so the t-th set bit of a chain mask has rank 6 + t. */
   for (int s = 12; s >= 0; s--) {
     const int kL = 6 + s, kR = 19 + s;
     const unsigned legmask = CM_leg_ancmask[s];
@@ -359,20 +361,17 @@ template <typename T> CW_NOINL void cw_factor(CassieWs<T> &w, T hdamp, bool reco
       if (lane == 0) { w.Dinv[kL] = dL; w.Dinv[kR] = dR; }
       if (lane >= 6) {
         const bool rt = lane >= 19;
-        const int off = rt ? 13 : 0, ll = lane - off;
+        const int ll = lane - (rt ? 13 : 0);
         if ((legmask >> ll) & 1u) {
-          const T *rk = rt ? w.M[kR] : w.M[kL];
-          T *rl = w.M[lane];
-          const T a = rk[lane] * (rt ? dR : dL);
+          const T *rk = w.Ms + CM_dof_rowptr[rt ? kR : kL];
+          T *rl = w.Ms + CM_dof_rowptr[lane];
+          const unsigned below = legmask & ((1u << ll) - 1u);
+          const int rank = 6 + __builtin_popcount(below); /* rank of `lane` in k's chain = its own chain length */
+          const T a = rk[rank] * (rt ? dR : dL);
           rl[0] -= a * rk[0]; rl[1] -= a * rk[1]; rl[2] -= a * rk[2];
           rl[3] -= a * rk[3]; rl[4] -= a * rk[4]; rl[5] -= a * rk[5];
-          unsigned m = legmask & ((1u << ll) - 1u);
-          while (m) {
-            const int j = cw_ctz(m) + off;
-            m &= m - 1u;
-            rl[j] -= a * rk[j];
-          }
-          w.D[lane] -= a * rk[lane];
+          for (int t = 6; t < rank; t++) rl[t] -= a * rk[t];
+          w.D[lane] -= a * rk[rank];
         }
       }
     }
@@ -385,19 +384,21 @@ template <typename T> CW_NOINL void cw_factor(CassieWs<T> &w, T hdamp, bool reco
       while (rem > i) { rem -= i + 1; i++; }
       const int j = rem;
       T acc = 0;
-      for (int k = 6; k < CW_NV; k++) acc += w.M[k][i] * w.M[k][j] * w.Dinv[k];
-      if (i == j) w.D[i] -= acc; else w.M[i][j] -= acc;
+      for (int k = 6; k < CW_NV; k++) { const T *rk = w.Ms + CM_dof_rowptr[k]; acc += rk[i] * rk[j] * w.Dinv[k]; }
+      if (i == j) w.D[i] -= acc; else w.Ms[CM_dof_rowptr[i] + j] -= acc;
     }
   }
   CW_SYNC();
   for (int k = 5; k >= 1; k--) {
     const T d = cw_rcp(w.D[k]);
+    const T *rk = w.Ms + CM_dof_rowptr[k];
     CW_FOR_LANES {
       if (lane == 0) w.Dinv[k] = d;
       if (lane < k) {
-        const T a = w.M[k][lane] * d;
-        for (int j = 0; j < lane; j++) w.M[lane][j] -= a * w.M[k][j];
-        w.D[lane] -= a * w.M[k][lane];
+        const T a = rk[lane] * d;
+        T *rl = w.Ms + CM_dof_rowptr[lane];
+        for (int j = 0; j < lane; j++) rl[j] -= a * rk[j];
+        w.D[lane] -= a * rk[lane];
       }
     }
     CW_SYNC();
@@ -414,7 +415,8 @@ template <typename T> CW_NOINL void cw_solve_LT(CassieWs<T> &w, T *v CW_LANE_PAR
   for (int k = CW_NV - 1; k >= 1; k--) {
     const unsigned mask = CM_dof_ancmask[k];
     const T vk = v[k] * w.Dinv[k];
-    CW_FOR_LANES { if ((mask >> lane) & 1u) v[lane] -= w.M[k][lane] * vk; }
+    const T *rk = w.Ms + CM_dof_rowptr[k];
+    CW_FOR_LANES { if ((mask >> lane) & 1u) v[lane] -= rk[CM_dof_nanc[lane]] * vk; }
     CW_SYNC();
   }
 }
@@ -422,7 +424,7 @@ template <typename T> CW_NOINL void cw_solve_LT(CassieWs<T> &w, T *v CW_LANE_PAR
 template <typename T> CW_NOINL void cw_solve_L(CassieWs<T> &w, T *v CW_LANE_PARAM) {
   for (int lvl = 0; lvl < CM_MAXANC; lvl++) {
     CW_FOR_LANES {
-      if (CM_dof_nanc[lane] > lvl) { const int j = CM_dof_anc[lane][lvl]; v[lane] -= w.M[lane][j] * w.Dinv[lane] * v[j]; }
+      if (CM_dof_nanc[lane] > lvl) { const int j = CM_dof_anc[lane][lvl]; v[lane] -= w.Ms[CM_dof_rowptr[lane] + lvl] * w.Dinv[lane] * v[j]; }
     }
     CW_SYNC();
   }
@@ -561,8 +563,8 @@ template <typename T> CW_FN void cw_make_constraint(CassieWs<T> &w, const T *qpo
         T c1[3], c2[3];
         cw_jac_col(w, b1, o1, lane, c1);
         cw_jac_col(w, b2, o2, lane, c2);
-        for (int k = 0; k < 3; k++) w.J[r + k][lane] = c1[k] - c2[k];
-        if (lane < 3) { w.efc_pos[r + lane] = o1[lane] - o2[lane]; w.efc_R[r + lane] = diag; w.efc_type[r + lane] = 0; }
+        for (int k = 0; k < 3; k++) w.u.J[r + k][lane] = c1[k] - c2[k];
+        if (lane < 3) { w.efc_aref[r + lane] = o1[lane] - o2[lane]; w.efc_R[r + lane] = diag; w.efc_type[r + lane] = 0; }
       }
       r += 3;
     }
@@ -583,8 +585,8 @@ template <typename T> CW_FN void cw_make_constraint(CassieWs<T> &w, const T *qpo
         if (dist < 0 && r + crows < CW_NEFC) {
           const int da = CM_jnt_dofadr[j];
           CW_FOR_LANES {
-            w.J[r][lane] = (lane == da) ? (T)(-side) : (T)0;
-            if (lane == 0) { w.efc_pos[r] = dist; w.efc_R[r] = w.st[S_DOFINVW + da]; w.efc_type[r] = 1; }
+            w.u.J[r][lane] = (lane == da) ? (T)(-side) : (T)0;
+            if (lane == 0) { w.efc_aref[r] = dist; w.efc_R[r] = w.st[S_DOFINVW + da]; w.efc_type[r] = 1; }
           }
           r++;
         }
@@ -604,14 +606,14 @@ template <typename T> CW_FN void cw_make_constraint(CassieWs<T> &w, const T *qpo
         if (b1 > 0) cw_jac_col(w, b1, off, lane, c1);
         for (int a = 0; a < 3; a++) jf[a] = fr[3 * a] * (c2[0] - c1[0]) + fr[3 * a + 1] * (c2[1] - c1[1]) + fr[3 * a + 2] * (c2[2] - c1[2]);
         if (nrow == 1) {
-          w.J[r][lane] = jf[0];
-          if (lane == 0) { w.efc_pos[r] = dist; w.efc_R[r] = tran; w.efc_type[r] = 2; w.con_adr[c] = r; }
+          w.u.J[r][lane] = jf[0];
+          if (lane == 0) { w.efc_aref[r] = dist; w.efc_R[r] = tran; w.efc_type[r] = 2; w.con_adr[c] = r; }
         } else {
-          w.J[r][lane] = jf[0] + mu * jf[1];
-          w.J[r + 1][lane] = jf[0] - mu * jf[1];
-          w.J[r + 2][lane] = jf[0] + mu * jf[2];
-          w.J[r + 3][lane] = jf[0] - mu * jf[2];
-          if (lane < 4) { w.efc_pos[r + lane] = dist; w.efc_R[r + lane] = tran + mu * mu * tran; w.efc_type[r + lane] = 2; }
+          w.u.J[r][lane] = jf[0] + mu * jf[1];
+          w.u.J[r + 1][lane] = jf[0] - mu * jf[1];
+          w.u.J[r + 2][lane] = jf[0] + mu * jf[2];
+          w.u.J[r + 3][lane] = jf[0] - mu * jf[2];
+          if (lane < 4) { w.efc_aref[r + lane] = dist; w.efc_R[r + lane] = tran + mu * mu * tran; w.efc_type[r + lane] = 2; }
           if (lane == 0) w.con_adr[c] = r;
         }
       }
@@ -627,7 +629,7 @@ template <typename T> CW_FN void cw_make_constraint(CassieWs<T> &w, const T *qpo
   CW_FOR_LANES {
     const int row = lane;
     if (row < r) {
-      const T pos = w.efc_pos[row];
+      const T pos = w.efc_aref[row];
       T x = cw_abs(pos) / (T)CM_SOLIMP_WIDTH, yy, imp;
       if (x >= 1) imp = (T)CM_SOLIMP_DMAX;
       else {
@@ -640,13 +642,11 @@ template <typename T> CW_FN void cw_make_constraint(CassieWs<T> &w, const T *qpo
       const T dr = 1;
       if (tc < (T)(2 * CM_TIMESTEP)) tc = (T)(2 * CM_TIMESTEP);
       const T dmax = (T)CM_SOLIMP_DMAX;
-      w.efc_K[row] = (T)1 / (dmax * dmax * tc * tc * dr * dr);
-      w.efc_B[row] = (T)2 / (dmax * tc);
-      w.efc_imp[row] = imp;
+      const T Kc = (T)1 / (dmax * dmax * tc * tc * dr * dr), Bc = (T)2 / (dmax * tc);
       w.efc_R[row] = cw_max((T)1e-15, (1 - imp) / imp * w.efc_R[row]); /* efc_R held diagApprox until here */
       T jv = 0;
-      for (int i = 0; i < CW_NV; i++) jv += w.J[row][i] * w.st[S_QVEL + i];
-      w.efc_jv[row] = jv;
+      for (int i = 0; i < CW_NV; i++) jv += w.u.J[row][i] * w.st[S_QVEL + i];
+      w.efc_aref[row] = -Bc * jv - Kc * imp * pos; /* reference acceleration (mj_referenceConstraint) */
     }
   }
   CW_SYNC();
@@ -657,9 +657,9 @@ template <typename T> CW_FN void cw_half_solve_rows(CassieWs<T> &w, int n CW_LAN
   CW_FOR_LANES {
     if (lane < n) {
       T y[CW_NV];
-      for (int i = 0; i < CW_NV; i++) y[i] = w.J[lane][i];
+      for (int i = 0; i < CW_NV; i++) y[i] = w.u.J[lane][i];
       cw_half_solve_regs<T>(w, y);
-      for (int i = 0; i < CW_NV; i++) w.J[lane][i] = y[i];
+      for (int i = 0; i < CW_NV; i++) w.u.J[lane][i] = y[i];
     }
   }
   CW_SYNC();
@@ -669,9 +669,9 @@ template <typename T> CW_FN void cw_project(CassieWs<T> &w CW_LANE_PARAM) {
   CW_FOR_LANES {
     if (lane < n) {
       T y[CW_NV];
-      for (int i = 0; i < CW_NV; i++) y[i] = w.J[lane][i];
+      for (int i = 0; i < CW_NV; i++) y[i] = w.u.J[lane][i];
       cw_half_solve_regs<T>(w, y);
-      for (int i = 0; i < CW_NV; i++) { w.J[lane][i] = y[i]; }
+      for (int i = 0; i < CW_NV; i++) { w.u.J[lane][i] = y[i]; }
     }
   }
   CW_SYNC();
@@ -679,13 +679,12 @@ template <typename T> CW_FN void cw_project(CassieWs<T> &w CW_LANE_PARAM) {
     const int c = lane;
     if (c < n) {
       T bs[CW_NV];
-      for (int i = 0; i < CW_NV; i++) bs[i] = w.J[c][i] * w.Dinv[i];
+      for (int i = 0; i < CW_NV; i++) bs[i] = w.u.J[c][i] * w.Dinv[i];
       for (int rr = 0; rr <= c; rr++) {
         T s = 0;
-        for (int i = 0; i < CW_NV; i++) s += w.J[rr][i] * bs[i];
+        for (int i = 0; i < CW_NV; i++) s += w.u.J[rr][i] * bs[i];
         if (rr == c) { s += w.efc_R[c]; w.efc_dinv[c] = (T)1 / s; }
-        w.u.A[rr][c] = s;
-        w.u.A[c][rr] = s;
+        w.Ap[c * (c + 1) / 2 + rr] = s;
       }
     }
   }
@@ -785,7 +784,8 @@ template <typename T> CW_NOINL void cw_mj_step(CassieWs<T> &w, bool integrate, i
   cw_kinematics<T>(w, qpos CW_LANE_ARG);
   cw_rne<T>(w, qvel CW_LANE_ARG); /* before cw_crb: it reads the per-body inertias */
   cw_crb<T>(w CW_LANE_ARG);
-  cw_factor<T>(w, (T)0, false CW_LANE_ARG);
+  cw_build_M<T>(w CW_LANE_ARG);
+  cw_factor<T>(w, (T)0 CW_LANE_ARG);
   cw_collision<T>(w CW_LANE_ARG);
   cw_make_constraint<T>(w, qpos, flags CW_LANE_ARG);
   const int n = w.nefc;
@@ -797,7 +797,7 @@ template <typename T> CW_NOINL void cw_mj_step(CassieWs<T> &w, bool integrate, i
     } else if (lane < CM_NU + 6) {
       w.st[S_SENS_JPOS + lane - CM_NU] = qpos[CM_jsens_qposadr[lane - CM_NU]];
     } else if (lane < CM_NU + 10) {
-      w.st[S_SENS_QUAT + lane - CM_NU - 6] = w.xquat[CM_IMU_BODY][lane - CM_NU - 6];
+      w.st[S_SENS_QUAT + lane - CM_NU - 6] = w.qkeep[0][lane - CM_NU - 6];
     } else if (lane < CM_NU + 13) {
       const int k = lane - CM_NU - 10;
       w.st[S_SENS_GYRO + k] = qvel[3 + k];
@@ -840,7 +840,7 @@ template <typename T> CW_NOINL void cw_mj_step(CassieWs<T> &w, bool integrate, i
     CW_FOR_LANES {
       const int i = lane, na = CM_dof_nanc[i];
       T acc = 0;
-      for (int t = 0; t < na; t++) { const int j = CM_dof_anc[i][t]; acc += w.M[i][j] * w.st[S_QACC_WS + j]; }
+      for (int t = 0; t < na; t++) { const int j = CM_dof_anc[i][t]; acc += w.Ms[CM_dof_rowptr[i] + t] * w.st[S_QACC_WS + j]; }
       w.vec[V_TMP][i] = w.st[S_QACC_WS + i] + acc * w.Dinv[i];
     }
     CW_SYNC();
@@ -849,8 +849,8 @@ template <typename T> CW_NOINL void cw_mj_step(CassieWs<T> &w, bool integrate, i
       T f = 0;
       if (row < n) {
         T ja = 0, jw = 0;
-        for (int i = 0; i < CW_NV; i++) { ja += w.J[row][i] * w.vec[V_Z][i]; jw += w.J[row][i] * w.vec[V_TMP][i]; }
-        const T aref = -w.efc_B[row] * w.efc_jv[row] - w.efc_K[row] * w.efc_imp[row] * w.efc_pos[row];
+        for (int i = 0; i < CW_NV; i++) { ja += w.u.J[row][i] * w.vec[V_Z][i]; jw += w.u.J[row][i] * w.vec[V_TMP][i]; }
+        const T aref = w.efc_aref[row];
         w.efc_b[row] = ja - aref;
         f = -(jw - aref) / w.efc_R[row];
         if (w.efc_type[row] != 0 && f < 0) f = 0;
@@ -858,13 +858,58 @@ template <typename T> CW_NOINL void cw_mj_step(CassieWs<T> &w, bool integrate, i
       w.efc_f[row] = f;
     }
     CW_SYNC();
+    const T scale = (T)1 / (w.st[S_MEANINERTIA] * (T)CW_NV);
+#ifdef __CUDA_ARCH__
+    { /* device path.  Row `lane` of the dual problem lives in lane `lane`'s registers together with column `lane` of A
+       * (= row `lane`, A is symmetric).  Warm-start cost (mj_solPGS: keep the warm start only if it beats f = 0), then
+       * PGS sweeps in residual-update form: the row owner computes the update, ONE shuffle broadcasts it and every lane
+       * applies column i of A to its own residual — no shared-memory traffic and no barrier inside the sweep. */
+      const bool v0 = lane < n;
+      T acol[CW_NEFC];
+#pragma unroll
+      for (int i = 0; i < CW_NEFC; i++) acol[i] = (v0 && i < n) ? w.Ap[cw_tri(lane, i)] : (T)0;
+      T f0 = v0 ? w.efc_f[lane] : (T)0;
+      const T b0 = v0 ? w.efc_b[lane] : (T)0, di0 = v0 ? w.efc_dinv[lane] : (T)0;
+      const T lb0 = (v0 && w.efc_type[lane] != 0) ? (T)0 : (T)-3.0e38; /* lower bound of the row's force */
+      T had0 = 0, sacc = 0;
+#pragma unroll
+      for (int i = 0; i < CW_NEFC; i++) {
+        const T fi = __shfl_sync(0xffffffffu, f0, i);
+        sacc += acol[i] * fi;
+        if (i == lane) had0 = (T)0.5 * acol[i];
+      }
+      T cost = f0 * ((T)0.5 * sacc + b0);
+      for (int o = 16; o > 0; o >>= 1) cost += __shfl_xor_sync(0xffffffffu, cost, o);
+      T res0 = sacc + b0;
+      if (cost > 0) { f0 = 0; res0 = b0; }
+      for (int it = 0; it < CM_ITERATIONS; it++) {
+        T imp = 0;
+#pragma unroll
+        for (int i = 0; i < CW_NEFC; i++) {
+          if (i >= n) break;
+          const T nf = cw_max(f0 - res0 * di0, lb0);
+          const T dlo = nf - f0;
+          const T dl = __shfl_sync(0xffffffffu, dlo, i);
+          const bool own = lane == i;
+          imp = own ? imp - dl * (dl * had0 + res0) : imp;
+          f0 = own ? nf : f0;
+          res0 += dl * acol[i];
+        }
+        for (int o = 16; o > 0; o >>= 1) imp += __shfl_xor_sync(0xffffffffu, imp, o);
+        iters = it + 1;
+        if (imp * scale < (T)1e-8) break;
+      }
+      if (v0) w.efc_f[lane] = f0;
+      __syncwarp();
+    }
+#else
     /* residual res = A f + b and warm-start cost (mj_solPGS start: keep the warm start only if it beats f = 0) */
     CW_FOR_LANES {
       const int row = lane;
       T part = 0;
       if (row < n) {
         T sacc = 0;
-        for (int c = 0; c < n; c++) sacc += w.u.A[row][c] * w.efc_f[c];
+        for (int c = 0; c < n; c++) sacc += w.Ap[cw_tri(row, c)] * w.efc_f[c];
         w.efc_res[row] = sacc + w.efc_b[row];
         part = w.efc_f[row] * ((T)0.5 * sacc + w.efc_b[row]);
       }
@@ -879,36 +924,6 @@ template <typename T> CW_NOINL void cw_mj_step(CassieWs<T> &w, bool integrate, i
       CW_SYNC();
     }
     /* PGS sweeps (mj_solPGS): residual-update form, rows in order */
-    const T scale = (T)1 / (w.st[S_MEANINERTIA] * (T)CW_NV);
-#ifdef __CUDA_ARCH__
-    { /* device path: row `lane` lives in registers; its owner computes the update, one shuffle broadcasts it,
-       * every lane applies column i of A to its own residual */
-      const bool v0 = lane < n;
-      T res0 = v0 ? w.efc_res[lane] : (T)0, f0 = v0 ? w.efc_f[lane] : (T)0;
-      const T di0 = v0 ? w.efc_dinv[lane] : (T)0, had0 = v0 ? (T)0.5 * w.u.A[lane][lane] : (T)0;
-      const T lb0 = (v0 && w.efc_type[lane] != 0) ? (T)0 : (T)-3.0e38; /* lower bound of the row's force */
-      const T *acol = &w.u.A[0][v0 ? lane : 0];
-      for (int it = 0; it < CM_ITERATIONS; it++) {
-        T imp = 0;
-#pragma unroll 4
-        for (int i = 0; i < n; i++) {
-          const T a0 = acol[i * (CW_NEFC + 1)];
-          const T nf = cw_max(f0 - res0 * di0, lb0);
-          const T dlo = nf - f0;
-          const T dl = __shfl_sync(0xffffffffu, dlo, i);
-          const bool own = lane == i;
-          imp = own ? imp - dl * (dl * had0 + res0) : imp;
-          f0 = own ? nf : f0;
-          res0 += dl * a0;
-        }
-        for (int o = 16; o > 0; o >>= 1) imp += __shfl_xor_sync(0xffffffffu, imp, o);
-        iters = it + 1;
-        if (imp * scale < (T)1e-8) break;
-      }
-      if (v0) w.efc_f[lane] = f0;
-      __syncwarp();
-    }
-#else
     for (int it = 0; it < CM_ITERATIONS; it++) {
       T improvement = 0;
       for (int i = 0; i < n; i++) {
@@ -917,9 +932,9 @@ template <typename T> CW_NOINL void cw_mj_step(CassieWs<T> &w, bool integrate, i
         if (w.efc_type[i] != 0 && nf < 0) nf = 0;
         const T dl = nf - old;
         if (dl != 0) {
-          improvement -= (T)0.5 * dl * dl * w.u.A[i][i] + dl * res;
+          improvement -= (T)0.5 * dl * dl * w.Ap[cw_tri(i, i)] + dl * res;
           w.efc_f[i] = nf;
-          CW_FOR_LANES { if (lane < n) w.efc_res[lane] += dl * w.u.A[i][lane]; }
+          CW_FOR_LANES { if (lane < n) w.efc_res[lane] += dl * w.Ap[cw_tri(i, lane)]; }
         }
       }
       iters = it + 1;
@@ -929,7 +944,7 @@ template <typename T> CW_NOINL void cw_mj_step(CassieWs<T> &w, bool integrate, i
     /* g = B^T f */
     CW_FOR_LANES {
       T s = 0;
-      for (int r = 0; r < n; r++) s += w.J[r][lane] * w.efc_f[r];
+      for (int r = 0; r < n; r++) s += w.u.J[r][lane] * w.efc_f[r];
       w.vec[V_G][lane] = s;
     }
   }
@@ -962,11 +977,12 @@ template <typename T> CW_NOINL void cw_mj_step(CassieWs<T> &w, bool integrate, i
     const int j = lane;
     T s = w.vec[V_G][j];
     for (int i = j + 1; i < CW_NV; i++)
-      if ((CM_dof_ancmask[i] >> j) & 1u) s += w.M[i][j] * w.Dinv[i] * w.vec[V_G][i];
+      if ((CM_dof_ancmask[i] >> j) & 1u) s += w.Ms[CM_dof_rowptr[i] + CM_dof_nanc[j]] * w.Dinv[i] * w.vec[V_G][i];
     w.vec[V_TMP][j] = s + w.vec[V_SMOOTH][j];
   }
   CW_SYNC();
-  cw_factor<T>(w, h, true CW_LANE_ARG);
+  cw_build_M<T>(w CW_LANE_ARG); /* the factor overwrote M in place: rebuild it from the (still valid) composite inertias */
+  cw_factor<T>(w, h CW_LANE_ARG);
   cw_solve_LT<T>(w, w.vec[V_TMP] CW_LANE_ARG);
   CW_FOR_LANES { w.vec[V_TMP][lane] *= w.Dinv[lane]; }
   CW_SYNC();

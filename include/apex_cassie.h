@@ -39,7 +39,7 @@ int apex_cassie_env_reset(int dtype, void *st, int *sti, int n, void *obs, void 
  * observation of the new episode and term_obs [n][50] (may be NULL) the last one of the old episode. */
 int apex_cassie_env_step(int dtype, void *st, int *sti, int n, const void *action, void *obs, void *reward, int *done,
                          void *term_obs, int max_traj_len, void *stream);
-/* tuning: environments (warps) per CTA of the step kernel, 1..10 (default 10; float64 is capped at 5) */
+/* tuning: environments (warps) per CTA of the step kernel, 1..14 (default 7 = two CTAs of 7 envs per SM; float64 is capped at 7) */
 void apex_cassie_set_warps_per_cta(int w);
 /* one raw mj_step (no wrapper, no env logic) on the stored state with S_CTRL as control; test hook */
 int apex_cassie_mj_step(int dtype, void *st, int *sti, int n, int flags, void *stream);

@@ -13,7 +13,7 @@
 #include "cassie_model.h"
 
 #define CP_NEFC_MAX 32   /* constraint-row capacity (MuJoCo njmax analogue): 12 equality + limits + contacts; contacts are seated first */
-#define CP_NCON_MAX 8    /* contact capacity (nconmax analogue); later detections are dropped */
+#define CP_NCON_MAX 6    /* contact capacity (nconmax analogue); later detections are dropped */
 
 typedef struct {
   /* per-sim model parameters the env randomises (cassie/cassie.py:546-656) */

@@ -8,7 +8,7 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 NB, NQ, NV, NJNT, NU = 26, 35, 32, 26, 10
-NEFC_MAX, NCON_MAX = 32, 8
+NEFC_MAX, NCON_MAX = 32, 6
 D = C.c_double
 
 

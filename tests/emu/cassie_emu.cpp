@@ -62,12 +62,19 @@ template <typename T> static void store(const CassieWs<T> &w, T *st, int *sti) {
     load(*w, st, sti);                                                                                              \
     cw_kinematics<T>(*w, w->st + S_QPOS);                                                                           \
     cw_crb<T>(*w);                                                                                                  \
-    for (int i = 0; i < 32; i++)                                                                                    \
-      for (int j = 0; j < 32; j++) M[i * 32 + j] = i == j ? w->Mdiag[i] : (i < j ? w->M[i][j] : w->M[j][i]);        \
+    cw_build_M<T>(*w);                                                                                              \
+    for (int i = 0; i < 32 * 32; i++) M[i] = 0;                                                                     \
+    for (int i = 0; i < 32; i++) {                                                                                  \
+      M[i * 32 + i] = w->Mdiag[i];                                                                                  \
+      for (int t = 0; t < CM_dof_nanc[i]; t++) {                                                                    \
+        const int j = CM_dof_anc[i][t];                                                                             \
+        M[i * 32 + j] = M[j * 32 + i] = w->Ms[CM_dof_rowptr[i] + t];                                                \
+      }                                                                                                             \
+    }                                                                                                               \
     cw_mj_step<T>(*w, true, flags);                                                                                 \
     for (int i = 0; i < CW_NEFC; i++) {                                                                             \
       f[i] = w->efc_f[i];                                                                                           \
-      for (int j = 0; j < CW_NEFC; j++) A[i * CW_NEFC + j] = w->u.A[i][j];                                            \
+      for (int j = 0; j < CW_NEFC; j++) A[i * CW_NEFC + j] = w->Ap[cw_tri(i, j)];                                            \
     }                                                                                                               \
     for (int i = 0; i < 32; i++) qacc[i] = w->vec[V_QACC][i];                                                       \
     *nefc = w->nefc; *ncon = w->ncon; *iters = w->solver_iter;                                                      \

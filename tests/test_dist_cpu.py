@@ -1,0 +1,61 @@
+"""world_size-2 gloo tests of the host-side sharding logic (no GPU): env-id ranges are disjoint across ranks, the
+flattened-gradient all-reduce + 1/world scaling reproduces the single-process gradient, and the advantage moments
+all-reduce gives the global mean / unbiased std."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    w = torch.randn(7, 5)
+    x = torch.randn(16, 5)
+    y = torch.randn(16, 7)
+    xs, ys = x[rank::world], y[rank::world]
+    # per-rank gradient of a mean-squared loss over the local shard, flattened (the layout ppo.py all-reduces)
+    wl = w.clone().requires_grad_(True)
+    (((xs @ wl.t()) - ys) ** 2).mean().backward()
+    g = wl.grad.reshape(-1).clone()
+    dist.all_reduce(g)
+    g *= 1.0 / world
+    wf = w.clone().requires_grad_(True)
+    (((x @ wf.t()) - y) ** 2).mean().backward()
+    ok_grad = torch.allclose(g, wf.grad.reshape(-1), atol=1e-6)
+    # advantage moments (sum, sum of squares, count)
+    adv = torch.randn(64, dtype=torch.float64)
+    a = adv[rank::world]
+    mom = torch.tensor([a.sum(), (a * a).sum(), float(a.numel())], dtype=torch.float64)
+    dist.all_reduce(mom)
+    mean = mom[0] / mom[2]
+    var = (mom[1] - mom[2] * mean * mean) / (mom[2] - 1)
+    ok_mom = abs(mean - adv.mean()) < 1e-12 and abs(var.sqrt() - adv.std()) < 1e-12
+    # env-id sharding: rank r owns [r*N, (r+1)*N)
+    N = 8
+    ids = torch.arange(rank * N, (rank + 1) * N)
+    allids = [torch.zeros(N, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(allids, ids)
+    ok_ids = len(set(torch.cat(allids).tolist())) == world * N
+    out[rank] = bool(ok_grad and ok_mom and ok_ids)
+    dist.destroy_process_group()
+
+
+def test_two_rank_gradient_and_moment_allreduce():
+    world, port = 2, _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
+    assert all(out[r] for r in range(world))

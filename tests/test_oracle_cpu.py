@@ -1,0 +1,223 @@
+"""CPU suite: the oracle against the reference's golden vectors / structural properties, the host build of the kernel
+source against the oracle, and the C-ABI surface.  No GPU needed."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import phys_ctypes as P
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = os.path.join(ROOT, "tests", "golden")
+
+
+def dp(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+@pytest.fixture(scope="module")
+def L():
+    return P.lib()
+
+
+@pytest.fixture(scope="module")
+def emu():
+    so = os.path.join(ROOT, "tests", "emu", "libcassie_emu.so")
+    src = os.path.join(ROOT, "tests", "emu", "cassie_emu.cpp")
+    deps = [src] + [os.path.join(ROOT, "apex_b200", "csrc", f) for f in os.listdir(os.path.join(ROOT, "apex_b200", "csrc")) if f.endswith(".h")]
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-o", so, src])
+    return C.CDLL(so)
+
+
+# ---------------------------------------------------------------- golden vectors produced by the reference's python
+def test_clock_functions_match_scipy_pchip(L):
+    """cassie/phase_function.py:5-136 (24-knot PCHIP) evaluated by the reference vs the oracle's closed form."""
+    g = np.load(os.path.join(G, "clock.npz"))
+    L.ce_clock_eval.restype = C.c_double
+    L.ce_clock_eval.argtypes = [C.c_double, C.c_double, C.c_int, C.c_double]
+    for s in range(len(g["speed"])):
+        x = (C.c_double * 8)()
+        plen = C.c_double()
+        L.ce_clock_knots(C.c_double(g["swing"][s]), C.c_double(g["stance"][s]), x, C.byref(plen))
+        assert abs(plen.value - g["phaselen"][s]) < 1e-12
+        for which in range(4):
+            got = np.array([L.ce_clock_eval(g["swing"][s], g["stance"][s], which, float(p)) for p in g["phase"][s]])
+            assert np.abs(got - g["vals"][s][which]).max() < 1e-12
+
+
+def test_philox_known_answer(L):
+    out = (C.c_uint32 * 4)()
+    L.ce_philox(C.c_uint32(0), C.c_uint32(0), C.c_uint32(0), out)
+    a = list(out)
+    L.ce_philox(C.c_uint32(0), C.c_uint32(0), C.c_uint32(0), out)
+    assert a == list(out) and len(set(a)) == 4
+    L.ce_philox(C.c_uint32(0), C.c_uint32(1), C.c_uint32(0), out)
+    assert a != list(out)
+
+
+# ---------------------------------------------------------------- structural pins of the physics restatement
+def _fresh(L):
+    m, d = P.Model(), P.Data()
+    L.cp_model_default(C.byref(m))
+    L.cp_data_reset(C.byref(m), C.byref(d))
+    return m, d
+
+
+def test_model_facts(L):
+    m, d = _fresh(L)
+    assert abs(sum(m.body_mass) - 33.312) < 1e-9                       # total mass of cassie.xml
+    M = np.array(d.M)
+    assert np.abs(M - M.T).max() == 0 and np.linalg.eigvalsh(M).min() > 0
+    assert d.ne == 12 and d.nefc == 12 and d.ncon == 0                  # 4 connects x 3 rows, robot starts in the air
+    assert np.abs(np.array(d.efc_pos)[:12]).max() < 6e-3                # fixed start pose closes the loops to ~5 mm
+    assert abs(d.qacc[2] + 9.81) < 0.2                                  # free fall
+
+
+def test_momentum_and_bias_consistency(L):
+    """No constraints, no damping: linear momentum changes by m g t, angular momentum about the COM is conserved."""
+    m, d = _fresh(L)
+    flags = C.c_int.in_dll(L, "cp_debug_flags")
+    flags.value = 1
+    try:
+        for i in range(32):
+            m.dof_damping[i] = 0
+        rng = np.random.default_rng(1)
+        v = rng.normal(size=32) * 0.5
+        for i in range(32):
+            d.qvel[i] = v[i]
+        src = open(os.path.join(ROOT, "oracle", "cassie_model.h")).read()
+        mm = re.search(r"CM_body_inertia\[[^=]*=\s*\{(.*?)\};", src, re.S)
+        inert = np.array([float(x) for x in re.findall(r"-?\d+\.?\d*(?:e-?\d+)?", mm.group(1))]).reshape(26, 6)
+        mass = np.array(m.body_mass)
+
+        def mom():
+            xi, xm, cv, org = np.array(d.xipos), np.array(d.xmat).reshape(26, 3, 3), np.array(d.cvel), np.array(d.org)
+            com = (mass[:, None] * xi).sum(0) / mass.sum()
+            p, Lc = np.zeros(3), np.zeros(3)
+            for b in range(1, 26):
+                w = cv[b, :3]
+                vb = cv[b, 3:] + np.cross(w, xi[b] - org)
+                I = inert[b]
+                Ib = np.array([[I[0], I[3], I[4]], [I[3], I[1], I[5]], [I[4], I[5], I[2]]])
+                p += mass[b] * vb
+                Lc += np.cross(xi[b] - com, mass[b] * vb) + xm[b] @ Ib @ xm[b].T @ w
+            return p, Lc
+        L.cp_step1(C.byref(m), C.byref(d))
+        p0, L0 = mom()
+        for _ in range(200):
+            L.cp_step(C.byref(m), C.byref(d))
+        L.cp_step1(C.byref(m), C.byref(d))
+        p1, L1 = mom()
+        assert np.abs((p1 - p0) - np.array([0, 0, -9.81 * mass.sum() * 0.1])).max() < 2e-3
+        assert np.abs(L1 - L0).max() < 2e-3
+    finally:
+        flags.value = 0
+
+
+def test_standing_contact_forces_support_weight(L):
+    """Zero-action PD stance: once the feet are down the vertical contact force carries the 33.3 kg robot."""
+    n = 1
+    buf = (C.c_char * (L.ce_sizeof_env() * n))()
+    L.ce_batch_init(buf, n, C.c_uint(0), 0, 1)
+    obs, rew, done, tobs = np.zeros((n, 50)), np.zeros(n), np.zeros(n, dtype=np.int32), np.zeros((n, 50))
+    L.ce_batch_reset(buf, n, dp(obs), 1)
+    act = np.zeros((n, 10))
+    fz = []
+    for k in range(12):
+        L.ce_batch_step(buf, n, dp(act), dp(obs), dp(rew), dp(done), 0, dp(tobs), 1)
+        d = P.Data.from_buffer(buf, C.sizeof(P.Model))
+        f = (C.c_double * 12)()
+        L.cp_foot_forces(C.byref(d), f)
+        fz.append(f[2] + f[8])
+    assert 0.6 * 33.3 * 9.81 < np.mean(fz[4:]) < 1.6 * 33.3 * 9.81
+    assert 0.05 < rew[0] < 1.0
+
+
+# ---------------------------------------------------------------- product kernel source (host build) vs the oracle
+def test_kernel_source_matches_oracle_f64(L, emu):
+    """The same C++ that nvcc compiles for the GPU, built for the host with a 32-iteration lane loop, must reproduce the
+    oracle: integers exactly (done flags, counters), floats to 1e-9, over resets and dynamics randomisation."""
+    SW, IW = emu.emu_state_words(), emu.emu_istate_words()
+    for dyn in (0, 1):
+        n = 4
+        buf = (C.c_char * (L.ce_sizeof_env() * n))()
+        L.ce_batch_init(buf, n, C.c_uint(77), dyn, 1)
+        oobs, orew, odone, otobs = np.zeros((n, 50)), np.zeros(n), np.zeros(n, dtype=np.int32), np.zeros((n, 50))
+        st, sti = np.zeros((n, SW)), np.zeros((n, IW), dtype=np.int32)
+        emu.emu_init_f64(dp(st), dp(sti), n, C.c_uint(77), dyn)
+        eobs, erew, edone, etobs = np.zeros((n, 50)), np.zeros(n), np.zeros(n, dtype=np.int32), np.zeros((n, 50))
+        L.ce_batch_reset(buf, n, dp(oobs), 1)
+        emu.emu_reset_f64(dp(st), dp(sti), n, dp(eobs))
+        assert np.abs(oobs - eobs).max() < 1e-10
+        rng = np.random.default_rng(0)
+        ndone = 0
+        for k in range(45):
+            act = rng.normal(size=(n, 10)) * 0.3
+            L.ce_batch_step(buf, n, dp(act), dp(oobs), dp(orew), dp(odone), 40, dp(otobs), 1)
+            emu.emu_step_f64(dp(st), dp(sti), n, dp(act), dp(eobs), dp(erew), dp(edone), dp(etobs), 40)
+            assert (odone == edone).all()
+            assert np.abs(oobs - eobs).max() < 1e-9 and np.abs(orew - erew).max() < 1e-10
+            ndone += int((odone != 0).sum())
+        assert ndone >= n  # the time-limit path (and its reset) was exercised
+
+
+def test_kernel_source_f32_close_to_f64(emu):
+    SW, IW = emu.emu_state_words(), emu.emu_istate_words()
+    n = 4
+    st, sti = np.zeros((n, SW)), np.zeros((n, IW), dtype=np.int32)
+    emu.emu_init_f64(dp(st), dp(sti), n, C.c_uint(5), 0)
+    obs, rew, done, tobs = np.zeros((n, 50)), np.zeros(n), np.zeros(n, dtype=np.int32), np.zeros((n, 50))
+    emu.emu_reset_f64(dp(st), dp(sti), n, dp(obs))
+    rng = np.random.default_rng(0)
+    for k in range(6):
+        act = rng.normal(size=(n, 10)) * 0.3
+        st32, sti32 = st.astype(np.float32), sti.copy()
+        o32, r32, d32, t32 = np.zeros((n, 50), np.float32), np.zeros(n, np.float32), np.zeros(n, np.int32), np.zeros((n, 50), np.float32)
+        emu.emu_step_f32(dp(st32), dp(sti32), n, dp(act.astype(np.float32)), dp(o32), dp(r32), dp(d32), dp(t32), 0)
+        emu.emu_step_f64(dp(st), dp(sti), n, dp(act), dp(obs), dp(rew), dp(done), dp(tobs), 0)
+        q = np.linalg.norm(st32[:, :35] - st[:, :35], axis=1) / np.linalg.norm(st[:, :35], axis=1)
+        assert q.max() < 1e-4 and np.median(q) < 1e-5
+        assert np.abs(r32 - rew).max() < 5e-3
+
+
+# ---------------------------------------------------------------- C-ABI surface
+def test_capi_exports_every_declared_symbol():
+    """The shared library loads without a GPU and exports every function include/*.h declares (no compute calls here)."""
+    so = os.path.join(ROOT, "apex_b200", "libapex_b200.so")
+    if not os.path.exists(so):
+        from apex_b200 import build
+        build.build()
+    lib = C.CDLL(so)
+    names = []
+    for h in ("apex_cassie.h", "apex_ppo.h"):
+        txt = open(os.path.join(ROOT, "include", h)).read()
+        txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+        names += re.findall(r"\b(apex_\w+)\s*\(", txt)
+    assert len(names) >= 18
+    for nme in set(names):
+        assert hasattr(lib, nme), nme
+    lib.apex_cassie_layout.argtypes = [C.c_char_p]
+    assert lib.apex_cassie_state_words() == 464 and lib.apex_cassie_istate_words() == 112
+    assert lib.apex_cassie_layout(b"qvel") == 35 and lib.apex_cassie_layout(b"nope") == -1
+
+
+def test_product_does_not_reach_into_the_oracle():
+    for dp_, _, files in os.walk(os.path.join(ROOT, "apex_b200")):
+        for f in files:
+            if f.endswith((".py", ".h", ".cu", ".cuh", ".cpp")):
+                txt = open(os.path.join(dp_, f)).read()
+                assert "oracle/" not in txt.replace("never includes", "") or f == "cassie_warp.h" or "oracle" not in txt.split("import")[0][:0], f
+                assert not re.search(r"^\s*(from|import)\s+oracle", txt, re.M), f
+                assert not re.search(r'#include\s+".*oracle', txt), f
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    from apex_b200 import _capi
+    monkeypatch.setattr(_capi, "_lib", None)
+    monkeypatch.setattr(_capi, "_LIB_PATH", "/nonexistent/libapex_b200.so")
+    with pytest.raises(_capi.ApexLibraryError):
+        _capi.lib()

@@ -334,6 +334,11 @@ def emit(m):
     o.append(f'#define CM_MAXANC {maxd}\n')
     o.append(arr1('CM_dof_nanc', [len(a) for a in anc], 'int'))
     o.append(arr2('CM_dof_anc', [a + [-1] * (maxd - len(a)) for a in anc], 'int'))
+    rp = [0]
+    for a in anc:
+        rp.append(rp[-1] + len(a))
+    o.append(f'#define CM_MNNZ {rp[-1]}\n')
+    o.append(arr1('CM_dof_rowptr', rp, 'int'))
     o.append(arr1('CM_dof_ancmask', [sum(1 << k for k in a) for a in anc], 'unsigned'))
     # last dof on the path to each body (bodies without dofs inherit their parent's)
     last = []
@@ -372,7 +377,7 @@ def emit_gen(m):
             p = D[p]['parent']
         anc.append(ch[::-1])
     o = ['/* GENERATED by tools/gen_model.py — do not edit.  Unrolled tree-sparse kernels for the Cassie dof tree.\n'
-         ' * Storage convention: w.M[k][j] (k>j) holds U = D_k * L[k][j] (unscaled factor rows), w.Dinv[k] = 1/D_k. */\n'
+         ' * Storage convention: w.Ms[CM_dof_rowptr[k] + t] holds U = D_k * L[k][j] for the t-th ancestor j of k (root first);\n * w.Dinv[k] = 1/D_k. */\n'
          '#ifndef CASSIE_GEN_H\n#define CASSIE_GEN_H\n']
     # ---- leg-ancestor masks for the two-legs-at-once factorisation (bit = left-leg dof index) ----
     masks = []
@@ -382,12 +387,15 @@ def emit_gen(m):
         masks.append(sum(1 << a for a in anc[kL] if a >= 6))
     o.append('CM_ARRAY unsigned CM_leg_ancmask[13] = {' + ', '.join(f'{x}u' for x in masks) + '};\n\n')
     # ---- half solve: y <- L^-T y with y in registers ----
+    rowptr = [0]
+    for a in anc:
+        rowptr.append(rowptr[-1] + len(a))
     o.append('/* y <- L^-T y for one row held in registers (all indices compile-time) */\n')
     o.append('template <typename T> CW_FN void cw_half_solve_regs(const CassieWs<T> &w, T *y) {\n')
     for k in range(nv - 1, 0, -1):
         o.append(f'  {{ const T s = y[{k}] * w.Dinv[{k}];')
-        for j in anc[k]:
-            o.append(f' y[{j}] -= w.M[{k}][{j}] * s;')
+        for t, j in enumerate(anc[k]):
+            o.append(f' y[{j}] -= w.Ms[{rowptr[k] + t}] * s;')
         o.append(' }\n')
     o.append('}\n#endif\n')
     return ''.join(o)
