@@ -88,7 +88,7 @@ static int finish() {
 extern "C" {
 
 /* tuning knob (envs per CTA of the step kernel); float64 is capped at 5 by shared memory */
-int apex_cassie_warps_per_cta = 7;
+int apex_cassie_warps_per_cta = 14;
 void apex_cassie_set_warps_per_cta(int w) { apex_cassie_warps_per_cta = w; }
 
 int apex_cassie_state_words(void) { return S_WORDS; }
