@@ -43,6 +43,8 @@ def lib():
         L.apex_gae_scan.argtypes = [i, i, vp, vp, vp, vp, vp, fl, fl, vp, vp, vp]
         L.apex_moments.argtypes = [vp, lng, vp, vp]
         L.apex_normalize.argtypes = [vp, lng, vp, fl, vp]
+        L.apex_col_moments.argtypes = [vp, i, i, vp, vp]
+        L.apex_col_moments.restype = i
         for f in (L.apex_mlp_forward, L.apex_mlp_backward, L.apex_prepare_obs, L.apex_gaussian_sample, L.apex_ppo_loss,
                   L.apex_grad_sumsq, L.apex_adam_step, L.apex_gae_scan, L.apex_moments, L.apex_normalize):
             f.restype = i

@@ -451,3 +451,21 @@ extern "C" int apex_normalize(float *x, long n, const double *mom3, float eps, v
   k_normalize<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, n, mom3, eps);
   return last_err();
 }
+
+/* per-column sum and sum of squares (double, +=) of a [rows, dim] matrix: observation statistics for
+ * get_normalization_params (rl/envs/normalize.py:35-48) */
+__global__ void k_col_moments(const float *__restrict__ x, int rows, int dim, double *__restrict__ out, int rows_per_block) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= dim) return;
+  const int rb = blockIdx.y * rows_per_block, re = min(rows, rb + rows_per_block);
+  double s = 0, q = 0;
+  for (int r = rb; r < re; r++) { const double v = x[(long)r * dim + j]; s += v; q += v * v; }
+  atomicAdd(&out[j], s);
+  atomicAdd(&out[dim + j], q);
+}
+extern "C" int apex_col_moments(const float *x, int rows, int dim, double *out, void *stream) {
+  if (rows <= 0 || dim <= 0) return 0;
+  const int rpb = 256;
+  k_col_moments<<<dim3((dim + 63) / 64, (rows + rpb - 1) / rpb), 64, 0, (cudaStream_t)stream>>>(x, rows, dim, out, rpb);
+  return last_err();
+}

@@ -46,6 +46,9 @@ int apex_gae_scan(int T, int N, const float *rew, const float *val, const int *d
 int apex_moments(const float *x, long n, double *out3, void *stream);            /* out3 += (sum, sum sq, count) */
 int apex_normalize(float *x, long n, const double *mom3, float eps, void *stream); /* (x - mean) / (std_unbiased + eps) */
 
+/* out[0..dim) += column sums, out[dim..2dim) += column sums of squares of x [rows, dim]  (rl/envs/normalize.py:48) */
+int apex_col_moments(const float *x, int rows, int dim, double *out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -172,3 +172,25 @@ def test_rollout_and_optimize_run_end_to_end():
     assert all(np.isfinite(scal))
     assert float((algo.flat - w0).abs().max()) > 0
     assert torch.isfinite(algo.flat).all()
+
+
+def test_get_normalization_params_matches_numpy_statistics():
+    """rl/envs/normalize.py:35-48 on the batched env: mean and sqrt(var + 1e-8) of every visited state."""
+    from apex_b200.envs import BatchedCassieEnv
+    from apex_b200.policies import Gaussian_FF_Actor
+    from apex_b200.normalize import get_normalization_params
+    torch.manual_seed(0)
+    actor = Gaussian_FF_Actor(50, 10, fixed_std=torch.ones(10) * 0.2)
+    seen = []
+
+    class Spy(BatchedCassieEnv):
+        def reset(self):
+            o = super().reset(); seen.append(o.clone()); return o
+
+        def step(self, a, **k):
+            out = super().step(a, **k); seen.append(out[0].clone()); return out
+    mean, std = get_normalization_params(64 * 6, actor, lambda: Spy(64, seed=2, dynamics_randomization=True), 1.0)
+    states = torch.cat(seen[:-1]).double().cpu().numpy()   # the state after the last step is not recorded (normalize.py:18-31)
+    assert states.shape == (64 * 6, 50)
+    assert np.allclose(mean, states.mean(0), rtol=1e-5, atol=1e-5)
+    assert np.allclose(std, np.sqrt(states.var(0) + 1e-8), rtol=1e-4, atol=1e-5)
