@@ -43,6 +43,12 @@ def lib():
         L.apex_gae_scan.argtypes = [i, i, vp, vp, vp, vp, vp, fl, fl, vp, vp, vp]
         L.apex_moments.argtypes = [vp, lng, vp, vp]
         L.apex_normalize.argtypes = [vp, lng, vp, fl, vp]
+        L.apex_cassie_env_step_masked.argtypes = [i, vp, ip, i, vp, vp, vp, ip, vp, i, vp, vp]
+        L.apex_cassie_env_step_masked.restype = i
+        L.apex_ars_policy.argtypes = [vp, i, i, i, i, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+        L.apex_ars_policy.restype = i
+        L.apex_ars_update.argtypes = [vp, i, vp, vp, vp, i, fl, vp]
+        L.apex_ars_update.restype = i
         L.apex_col_moments.argtypes = [vp, i, i, vp, vp]
         L.apex_col_moments.restype = i
         for f in (L.apex_mlp_forward, L.apex_mlp_backward, L.apex_prepare_obs, L.apex_gaussian_sample, L.apex_ppo_loss,

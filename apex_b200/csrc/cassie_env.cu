@@ -38,12 +38,14 @@ template <typename T> __global__ void __launch_bounds__(32) k_env_reset(T *st, i
 /* W warps (= W envs) per CTA; the CTA barrier inside cw_env_step's sub-step loop must be reached by every warp, so
  * warps past the end of the batch run the barriers only. */
 template <typename T>
-__global__ void k_env_step(T *st, int *sti, int n, const T *action, T *obs, T *reward, int *done, T *term_obs, int max_traj_len) {
+__global__ void k_env_step(T *st, int *sti, int n, const T *action, T *obs, T *reward, int *done, T *term_obs, int max_traj_len,
+                           const int *active) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   CassieWs<T> &w = reinterpret_cast<CassieWs<T> *>(smem)[warp];
   const int e = blockIdx.x * wpb + warp;
-  if (e >= n) {
+  if (e >= n || (active && !active[e])) { /* idle slot: keep the CTA barriers company, touch nothing */
+    if (e < n && lane == 0) { reward[e] = 0; done[e] = 4; }
     for (int s = 0; s < CW_SIMRATE; s++) __syncthreads();
     return;
   }
@@ -140,8 +142,8 @@ int apex_cassie_env_reset(int dtype, void *st, int *sti, int n, void *obs, void 
       (k_env_reset<double><<<n, 32, sizeof(CassieWs<double>), s>>>((double *)st, sti, n, (double *)obs)))
 }
 
-int apex_cassie_env_step(int dtype, void *st, int *sti, int n, const void *action, void *obs, void *reward, int *done,
-                         void *term_obs, int max_traj_len, void *stream) {
+static int env_step_impl(int dtype, void *st, int *sti, int n, const void *action, void *obs, void *reward, int *done,
+                         void *term_obs, int max_traj_len, const int *active, void *stream) {
   if (!action || !obs || !reward || !done) return -1000;
   int wpb = apex_cassie_warps_per_cta;
   if (dtype == 1 && wpb > 7) wpb = 7;
@@ -150,10 +152,19 @@ int apex_cassie_env_step(int dtype, void *st, int *sti, int n, const void *actio
   DISPATCH(
       if ((rc = prep(k_env_step<float>, wpb * sizeof(CassieWs<float>)))) return rc;
       (k_env_step<float><<<(n + wpb - 1) / wpb, 32 * wpb, wpb * sizeof(CassieWs<float>), s>>>((float *)st, sti, n, (const float *)action, (float *)obs,
-                                                                (float *)reward, done, (float *)term_obs, max_traj_len)),
+                                                                (float *)reward, done, (float *)term_obs, max_traj_len, active)),
       if ((rc = prep(k_env_step<double>, wpb * sizeof(CassieWs<double>)))) return rc;
       (k_env_step<double><<<(n + wpb - 1) / wpb, 32 * wpb, wpb * sizeof(CassieWs<double>), s>>>((double *)st, sti, n, (const double *)action, (double *)obs,
-                                                                  (double *)reward, done, (double *)term_obs, max_traj_len)))
+                                                                  (double *)reward, done, (double *)term_obs, max_traj_len, active)))
+}
+
+int apex_cassie_env_step(int dtype, void *st, int *sti, int n, const void *action, void *obs, void *reward, int *done,
+                         void *term_obs, int max_traj_len, void *stream) {
+  return env_step_impl(dtype, st, sti, n, action, obs, reward, done, term_obs, max_traj_len, nullptr, stream);
+}
+int apex_cassie_env_step_masked(int dtype, void *st, int *sti, int n, const void *action, void *obs, void *reward, int *done,
+                                void *term_obs, int max_traj_len, const int *active, void *stream) {
+  return env_step_impl(dtype, st, sti, n, action, obs, reward, done, term_obs, max_traj_len, active, stream);
 }
 
 int apex_cassie_mj_step(int dtype, void *st, int *sti, int n, int flags, void *stream) {

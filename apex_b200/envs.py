@@ -68,7 +68,7 @@ class BatchedCassieEnv:
                                                     self.obs.data_ptr(), self._stream()), "env_reset")
         return self.obs
 
-    def step(self, action, f_term=0, rew_out=None, done_out=None):
+    def step(self, action, f_term=0, rew_out=None, done_out=None, active=None):
         """action [N, 10] on the device -> (obs [N, 50], reward [N], done [N] int32 (bit0 terminal, bit1 time-out), {}).
         rew_out / done_out: optional contiguous device tensors that receive reward and done (e.g. rollout-buffer rows)."""
         a = action.to(device=self.device, dtype=self.dtype).contiguous()
@@ -76,9 +76,15 @@ class BatchedCassieEnv:
         rew = self.rew if rew_out is None else rew_out
         done = self.done if done_out is None else done_out
         with torch.cuda.device(self.device):
-            _lib.check(self.L.apex_cassie_env_step(self.dt, self.st.data_ptr(), self.sti.data_ptr(), self.num_envs, a.data_ptr(),
-                                                   self.obs.data_ptr(), rew.data_ptr(), done.data_ptr(),
-                                                   self.term_obs.data_ptr(), self.max_traj_len, self._stream()), "env_step")
+            if active is None:
+                _lib.check(self.L.apex_cassie_env_step(self.dt, self.st.data_ptr(), self.sti.data_ptr(), self.num_envs, a.data_ptr(),
+                                                       self.obs.data_ptr(), rew.data_ptr(), done.data_ptr(),
+                                                       self.term_obs.data_ptr(), self.max_traj_len, self._stream()), "env_step")
+            else:  # int32 mask: envs with active == 0 are skipped (done = 4)
+                _lib.check(self.L.apex_cassie_env_step_masked(self.dt, self.st.data_ptr(), self.sti.data_ptr(), self.num_envs,
+                                                              a.data_ptr(), self.obs.data_ptr(), rew.data_ptr(), done.data_ptr(),
+                                                              self.term_obs.data_ptr(), self.max_traj_len, active.data_ptr(),
+                                                              self._stream()), "env_step_masked")
         return self.obs, rew, done, {}
 
     def set_command(self, speed=None, side_speed=None, phase=None):

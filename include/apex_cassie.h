@@ -39,6 +39,10 @@ int apex_cassie_env_reset(int dtype, void *st, int *sti, int n, void *obs, void 
  * observation of the new episode and term_obs [n][50] (may be NULL) the last one of the old episode. */
 int apex_cassie_env_step(int dtype, void *st, int *sti, int n, const void *action, void *obs, void *reward, int *done,
                          void *term_obs, int max_traj_len, void *stream);
+/* as apex_cassie_env_step, but envs with active[e] == 0 are skipped (state, obs untouched; reward 0, done = 4): used by
+ * ARS, where every env runs exactly one episode (rl/algos/ars.py:185-201 eval_fn) */
+int apex_cassie_env_step_masked(int dtype, void *st, int *sti, int n, const void *action, void *obs, void *reward, int *done,
+                                void *term_obs, int max_traj_len, const int *active, void *stream);
 /* tuning: environments (warps) per CTA of the step kernel, 1..14 (default 7 = two CTAs of 7 envs per SM; float64 is capped at 7) */
 void apex_cassie_set_warps_per_cta(int w);
 /* one raw mj_step (no wrapper, no env logic) on the stored state with S_CTRL as control; test hook */

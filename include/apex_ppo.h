@@ -49,6 +49,13 @@ int apex_normalize(float *x, long n, const double *mom3, float eps, void *stream
 /* out[0..dim) += column sums, out[dim..2dim) += column sums of squares of x [rows, dim]  (rl/envs/normalize.py:48) */
 int apex_col_moments(const float *x, int rows, int dim, double *out, void *stream);
 
+/* ARS (rl/algos/ars.py): act[e] = Linear_Actor(theta + sign[e] * noise[idx[dir[e]] : +P])(obs[e]); S <= 64, H, A <= 32 */
+int apex_ars_policy(const float *obs, int n, int S, int H, int A, const float *theta, const float *noise, const int64_t *idx,
+                    const int *dir, const float *sign, const float *obs_mean, const float *obs_std, float *act, void *stream);
+/* theta += coef * sum_d weight[d] * noise[idx[d] : +P]   (ars.py:152-156) */
+int apex_ars_update(float *theta, int P, const float *noise, const int64_t *idx, const float *weight, int ndir, float coef,
+                    void *stream);
+
 #ifdef __cplusplus
 }
 #endif
