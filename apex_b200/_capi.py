@@ -49,6 +49,15 @@ def lib():
         L.apex_ars_policy.restype = i
         L.apex_ars_update.argtypes = [vp, i, vp, vp, vp, i, fl, vp]
         L.apex_ars_update.restype = i
+        L.apex_mlp_backward_dx.argtypes = [vp, i, i, i, i] + [vp] * 10 + [i] + [vp] * 7
+        L.apex_replay_gather.argtypes = [vp, vp, i, i, i, vp, vp, vp, vp, vp, vp]
+        L.apex_td3_action.argtypes = [vp, vp, vp, i, i, i, fl, fl, fl, u, u, vp, vp, vp]
+        L.apex_td3_critic_loss.argtypes = [i, vp, vp, vp, vp, vp, vp, fl, vp, vp, vp, vp]
+        L.apex_td3_actor_grad.argtypes = [i, i, i, vp, vp, fl, vp, vp]
+        L.apex_polyak.argtypes = [vp, vp, i, fl, vp]
+        for f in (L.apex_mlp_backward_dx, L.apex_replay_gather, L.apex_td3_action, L.apex_td3_critic_loss, L.apex_td3_actor_grad,
+                  L.apex_polyak):
+            f.restype = i
         L.apex_col_moments.argtypes = [vp, i, i, vp, vp]
         L.apex_col_moments.restype = i
         for f in (L.apex_mlp_forward, L.apex_mlp_backward, L.apex_prepare_obs, L.apex_gaussian_sample, L.apex_ppo_loss,

@@ -469,3 +469,139 @@ extern "C" int apex_col_moments(const float *x, int rows, int dim, double *out, 
   k_col_moments<<<dim3((dim + 63) / 64, (rows + rpb - 1) / rpb), 64, 0, (cudaStream_t)stream>>>(x, rows, dim, out, rpb);
   return last_err();
 }
+
+/* ===================================================================================================
+ * TD3 (rl/algos/sync_td3.py:133-209): replay gather, target-policy smoothing, twin-Q target and loss gradient,
+ * tanh head, Polyak averaging.  The MLP trunks reuse apex_mlp_forward / apex_mlp_backward(_dx).
+ * =================================================================================================== */
+/* like apex_mlp_backward, plus dx = dL/dx [rows, in_dim] (needed for -Q1(s, pi(s))) and a switch for the weight gradients */
+extern "C" int apex_mlp_backward_dx(const float *x, int rows, int in_dim, int hid, int out_dim, const float *w1, const float *w2,
+                                    const float *w3, const float *h1, const float *h2, const float *dy, float *dh2, float *dh1,
+                                    float *dx, int want_wgrads, float *gw1, float *gb1, float *gw2, float *gb2, float *gw3,
+                                    float *gb3, void *stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc;
+  const int splits = 148, rpb = 512;
+  if (want_wgrads) {
+    if ((rc = gemm(out_dim, hid, rows, dy, 1, out_dim, h2, hid, 1, gw3, hid, 1, nullptr, 0, nullptr, 0, 0, 1, splits, s))) return rc;
+    k_colsum<<<dim3((out_dim + 63) / 64, (rows + rpb - 1) / rpb), 64, 0, s>>>(rows, out_dim, dy, gb3, rpb);
+  }
+  if ((rc = gemm(rows, hid, out_dim, dy, out_dim, 1, w3, hid, 1, dh2, hid, 1, nullptr, 0, h2, hid, 1, 0, 1, s))) return rc;
+  if (want_wgrads) {
+    if ((rc = gemm(hid, hid, rows, dh2, 1, hid, h1, hid, 1, gw2, hid, 1, nullptr, 0, nullptr, 0, 0, 1, splits, s))) return rc;
+    k_colsum<<<dim3((hid + 63) / 64, (rows + rpb - 1) / rpb), 64, 0, s>>>(rows, hid, dh2, gb2, rpb);
+  }
+  if ((rc = gemm(rows, hid, hid, dh2, hid, 1, w2, hid, 1, dh1, hid, 1, nullptr, 0, h1, hid, 1, 0, 1, s))) return rc;
+  if (want_wgrads) {
+    if ((rc = gemm(hid, in_dim, rows, dh1, 1, hid, x, in_dim, 1, gw1, in_dim, 1, nullptr, 0, nullptr, 0, 0, 1, splits, s))) return rc;
+    k_colsum<<<dim3((hid + 63) / 64, (rows + rpb - 1) / rpb), 64, 0, s>>>(rows, hid, dh1, gb1, rpb);
+  }
+  if (dx) if ((rc = gemm(rows, in_dim, hid, dh1, hid, 1, w1, in_dim, 1, dx, in_dim, 1, nullptr, 0, nullptr, 0, 0, 0, 1, s))) return rc;
+  return last_err();
+}
+
+/* storage row = [state(S) | next_state(S) | action(A) | reward | done]  (rl/utils/remote_replay.py:65-90) */
+__global__ void k_replay_gather(const float *__restrict__ storage, const int64_t *__restrict__ idx, int rows, int S, int A,
+                                float *__restrict__ state, float *__restrict__ next_state, float *__restrict__ sa,
+                                float *__restrict__ reward, float *__restrict__ notdone) {
+  const int W = 2 * S + A + 2;
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long)rows * W) return;
+  const int r = (int)(t / W), j = (int)(t % W);
+  const float v = storage[idx[r] * W + j];
+  if (j < S) { state[(long)r * S + j] = v; sa[(long)r * (S + A) + j] = v; }
+  else if (j < 2 * S) next_state[(long)r * S + j - S] = v;
+  else if (j < 2 * S + A) sa[(long)r * (S + A) + S + j - 2 * S] = v;
+  else if (j == 2 * S + A) reward[r] = v;
+  else notdone[r] = 1.f - v;
+}
+extern "C" int apex_replay_gather(const float *storage, const int64_t *idx, int rows, int S, int A, float *state, float *next_state,
+                                  float *sa, float *reward, float *notdone, void *stream) {
+  if (rows <= 0) return 0;
+  const long tot = (long)rows * (2 * S + A + 2);
+  k_replay_gather<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(storage, idx, rows, S, A, state, next_state, sa,
+                                                                                 reward, notdone);
+  return last_err();
+}
+
+/* out[r] = [state[r] | clamp(max_a * tanh(pre[r]) + clamp(noise, +-noise_clip), +-max_a)]; noise = explicit tensor or
+ * policy_noise * N(0,1) from Philox.  policy_noise = 0 and noise = NULL gives the plain policy action (actor loss pass);
+ * tanh_out (optional) receives tanh(pre) for the backward pass. */
+__global__ void k_td3_action(const float *__restrict__ pre, const float *__restrict__ state, const float *__restrict__ noise, int rows,
+                             int S, int A, float max_a, float policy_noise, float noise_clip, uint32_t seed, uint32_t step,
+                             float *__restrict__ sa, float *__restrict__ tanh_out) {
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long)rows * (S + A)) return;
+  const int r = (int)(t / (S + A)), j = (int)(t % (S + A));
+  if (j < S) { sa[t] = state[(long)r * S + j]; return; }
+  const int a = j - S;
+  const float th = tanhf(pre[(long)r * A + a]);
+  if (tanh_out) tanh_out[(long)r * A + a] = th;
+  float nz = 0.f;
+  if (noise) nz = noise[(long)r * A + a];
+  else if (policy_noise > 0.f) {
+    uint32_t u[4];
+    philox4(seed, (uint32_t)r, step, (uint32_t)a, u);
+    const float u1 = ((float)(u[0] >> 8) + 0.5f) * (1.0f / 16777216.0f), u2 = (float)(u[1] >> 8) * (1.0f / 16777216.0f);
+    nz = policy_noise * sqrtf(-2.0f * logf(u1)) * cosf(6.283185307179586f * u2);
+  }
+  nz = fminf(fmaxf(nz, -noise_clip), noise_clip);
+  sa[t] = fminf(fmaxf(max_a * th + nz, -max_a), max_a);
+}
+extern "C" int apex_td3_action(const float *pre, const float *state, const float *noise, int rows, int S, int A, float max_a,
+                               float policy_noise, float noise_clip, unsigned seed, unsigned step, float *sa, float *tanh_out,
+                               void *stream) {
+  if (rows <= 0) return 0;
+  const long tot = (long)rows * (S + A);
+  k_td3_action<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(pre, state, noise, rows, S, A, max_a, policy_noise,
+                                                                              noise_clip, seed, step, sa, tanh_out);
+  return last_err();
+}
+
+/* y = r + notdone * discount * min(Q1', Q2');  dq_i = 2 (Q_i - y) / rows  (F.mse_loss mean);  stats += {loss, sum Q1, sum Q2} */
+__global__ void k_td3_critic_loss(int rows, const float *__restrict__ q1, const float *__restrict__ q2, const float *__restrict__ q1t,
+                                  const float *__restrict__ q2t, const float *__restrict__ reward, const float *__restrict__ notdone,
+                                  float discount, float *__restrict__ dq1, float *__restrict__ dq2, double *__restrict__ stats) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  float l = 0, s1 = 0, s2 = 0;
+  if (r < rows) {
+    const float y = reward[r] + notdone[r] * discount * fminf(q1t[r], q2t[r]);
+    const float e1 = q1[r] - y, e2 = q2[r] - y;
+    dq1[r] = 2.f * e1 / rows; dq2[r] = 2.f * e2 / rows;
+    l = (e1 * e1 + e2 * e2) / rows; s1 = q1[r]; s2 = q2[r];
+  }
+  for (int o = 16; o > 0; o >>= 1) { l += __shfl_xor_sync(0xffffffffu, l, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+  if ((threadIdx.x & 31) == 0) { atomicAdd(&stats[0], (double)l); atomicAdd(&stats[1], (double)s1); atomicAdd(&stats[2], (double)s2); }
+}
+extern "C" int apex_td3_critic_loss(int rows, const float *q1, const float *q2, const float *q1t, const float *q2t, const float *reward,
+                                    const float *notdone, float discount, float *dq1, float *dq2, double *stats, void *stream) {
+  if (rows <= 0) return 0;
+  k_td3_critic_loss<<<(rows + 255) / 256, 256, 0, (cudaStream_t)stream>>>(rows, q1, q2, q1t, q2t, reward, notdone, discount, dq1, dq2, stats);
+  return last_err();
+}
+
+/* actor loss -mean Q1(s, pi(s)): dpre = dsa[:, S:] * max_a * (1 - tanh^2);  dq = -1/rows is filled by the caller's fill */
+__global__ void k_td3_actor_grad(int rows, int S, int A, const float *__restrict__ dsa, const float *__restrict__ th, float max_a,
+                                 float *__restrict__ dpre) {
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long)rows * A) return;
+  const int r = (int)(t / A), a = (int)(t % A);
+  const float x = th[t];
+  dpre[t] = dsa[(long)r * (S + A) + S + a] * max_a * (1.f - x * x);
+}
+extern "C" int apex_td3_actor_grad(int rows, int S, int A, const float *dsa, const float *tanh_v, float max_a, float *dpre, void *stream) {
+  if (rows <= 0) return 0;
+  const long tot = (long)rows * A;
+  k_td3_actor_grad<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rows, S, A, dsa, tanh_v, max_a, dpre);
+  return last_err();
+}
+
+__global__ void k_polyak(float *__restrict__ target, const float *__restrict__ src, int n, float tau) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) target[i] = tau * src[i] + (1.f - tau) * target[i];
+}
+extern "C" int apex_polyak(float *target, const float *src, int n, float tau, void *stream) {
+  if (n <= 0) return 0;
+  k_polyak<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(target, src, n, tau);
+  return last_err();
+}

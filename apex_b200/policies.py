@@ -72,6 +72,52 @@ class FF_V(nn.Module):
         return self.network_out(x)
 
 
+class FF_Actor(nn.Module):
+    """rl/policies/actor.py:43-71 — deterministic actor with tanh output (TD3 / DDPG)."""
+
+    def __init__(self, state_dim, action_dim, layers=(256, 256), env_name=None, max_action=1):
+        super().__init__()
+        self.actor_layers = nn.ModuleList([nn.Linear(state_dim, layers[0])] +
+                                          [nn.Linear(layers[i], layers[i + 1]) for i in range(len(layers) - 1)])
+        self.network_out = nn.Linear(layers[-1], action_dim)
+        self.action_dim, self.env_name, self.max_action = action_dim, env_name, max_action
+        self.apply(normc_fn)
+
+    def forward(self, state, deterministic=True):
+        x = state
+        for l in self.actor_layers:
+            x = torch.relu(l(x))
+        return torch.tanh(self.network_out(x)) * self.max_action
+
+
+class Dual_Q_Critic(nn.Module):
+    """rl/policies/critic.py:118-168 — two independent Q networks on [state | action]."""
+
+    def __init__(self, state_dim, action_dim, hidden_size=256, hidden_layers=2, env_name="NOT SET"):
+        super().__init__()
+        self.q1_layers = nn.ModuleList([nn.Linear(state_dim + action_dim, hidden_size)] +
+                                       [nn.Linear(hidden_size, hidden_size) for _ in range(hidden_layers - 1)])
+        self.q1_out = nn.Linear(hidden_size, 1)
+        self.q2_layers = nn.ModuleList([nn.Linear(state_dim + action_dim, hidden_size)] +
+                                       [nn.Linear(hidden_size, hidden_size) for _ in range(hidden_layers - 1)])
+        self.q2_out = nn.Linear(hidden_size, 1)
+        self.env_name = env_name
+
+    def forward(self, state, action):
+        x1 = x2 = torch.cat([state, action], -1)
+        for l in self.q1_layers:
+            x1 = torch.relu(l(x1))
+        for l in self.q2_layers:
+            x2 = torch.relu(l(x2))
+        return self.q1_out(x1), self.q2_out(x2)
+
+    def Q1(self, state, action):
+        x1 = torch.cat([state, action], -1)
+        for l in self.q1_layers:
+            x1 = torch.relu(l(x1))
+        return self.q1_out(x1)
+
+
 def flatten_modules(modules, device):
     """Re-home every parameter of `modules` into one contiguous float32 device buffer (and one for gradients).
     Returns (flat_params, flat_grads, [(name, offset, shape)])."""

@@ -49,6 +49,23 @@ int apex_normalize(float *x, long n, const double *mom3, float eps, void *stream
 /* out[0..dim) += column sums, out[dim..2dim) += column sums of squares of x [rows, dim]  (rl/envs/normalize.py:48) */
 int apex_col_moments(const float *x, int rows, int dim, double *out, void *stream);
 
+/* ---- TD3 (rl/algos/sync_td3.py:133-209, rl/utils/remote_replay.py:65-90) ---- */
+/* apex_mlp_backward + dx [rows, in_dim] (may be NULL) and a switch for the weight gradients */
+int apex_mlp_backward_dx(const float *x, int rows, int in_dim, int hid, int out_dim, const float *w1, const float *w2, const float *w3,
+                         const float *h1, const float *h2, const float *dy, float *dh2, float *dh1, float *dx, int want_wgrads,
+                         float *gw1, float *gb1, float *gw2, float *gb2, float *gw3, float *gb3, void *stream);
+/* replay rows [state | next_state | action | reward | done] gathered by idx -> state, next_state, [state|action], reward, 1-done */
+int apex_replay_gather(const float *storage, const int64_t *idx, int rows, int S, int A, float *state, float *next_state, float *sa,
+                       float *reward, float *notdone, void *stream);
+/* sa = [state | clamp(max_a tanh(pre) + clamp(noise, +-noise_clip), +-max_a)]; noise: explicit [rows, A] or Philox N(0, policy_noise) */
+int apex_td3_action(const float *pre, const float *state, const float *noise, int rows, int S, int A, float max_a, float policy_noise,
+                    float noise_clip, unsigned seed, unsigned step, float *sa, float *tanh_out, void *stream);
+/* twin-Q target and MSE gradients; stats[3] (double, +=): loss, sum Q1, sum Q2 */
+int apex_td3_critic_loss(int rows, const float *q1, const float *q2, const float *q1t, const float *q2t, const float *reward,
+                         const float *notdone, float discount, float *dq1, float *dq2, double *stats, void *stream);
+int apex_td3_actor_grad(int rows, int S, int A, const float *dsa, const float *tanh_v, float max_a, float *dpre, void *stream);
+int apex_polyak(float *target, const float *src, int n, float tau, void *stream); /* target = tau src + (1 - tau) target */
+
 /* ARS (rl/algos/ars.py): act[e] = Linear_Actor(theta + sign[e] * noise[idx[dir[e]] : +P])(obs[e]); S <= 64, H, A <= 32 */
 int apex_ars_policy(const float *obs, int n, int S, int H, int A, const float *theta, const float *noise, const int64_t *idx,
                     const int *dir, const float *sign, const float *obs_mean, const float *obs_std, float *act, void *stream);

@@ -24,8 +24,9 @@ ray = types.ModuleType("ray")
 ray.remote = lambda f=None, **kw: (f if f is not None else (lambda g: g))
 ray.init = lambda *a, **k: None
 sys.modules["ray"] = ray
-for name in ("matplotlib", "matplotlib.pyplot", "lxml", "lxml.etree"):
+for name in ("matplotlib", "matplotlib.pyplot", "lxml", "lxml.etree", "gym", "colorama"):
     sys.modules.setdefault(name, types.ModuleType(name))
+sys.modules["colorama"].Fore = sys.modules["colorama"].Style = types.SimpleNamespace()
 tb = types.ModuleType("torch.utils.tensorboard")
 tb.SummaryWriter = object
 sys.modules.setdefault("torch.utils.tensorboard", tb)
@@ -153,7 +154,53 @@ def clocks():
     print("clock phaselen", [round(r["phaselen"], 3) for r in rows])
 
 
+
+
+def td3():
+    """Two iterations of the reference's TD3.train (sync_td3.py:133-209) on fixed replay samples and fixed smoothing noise."""
+    import rl.algos.sync_td3 as reftd3
+    torch.manual_seed(3)
+    np.random.seed(3)
+    S, A, B, iters = 50, 10, 64, 2
+    algo = reftd3.TD3(S, A, 1.0, 1e-3, 1e-3)
+    out = {}
+    for k, v in sd_np(algo.actor).items():
+        out["actor0." + k] = v
+    for k, v in sd_np(algo.critic).items():
+        out["critic0." + k] = v
+    cap = 256
+    storage = [(np.random.randn(S).astype(np.float32), np.random.randn(S).astype(np.float32),
+                np.tanh(np.random.randn(A)).astype(np.float32), np.float32(np.random.rand()), np.float32(np.random.rand() < 0.1))
+               for _ in range(cap)]
+    inds = [np.random.randint(0, cap, size=B) for _ in range(iters)]
+
+    class Replay:
+        def __init__(self):
+            self.k = 0
+
+        def sample(self, batch):
+            ind = inds[self.k]; self.k += 1
+            x, y, u, r, d = zip(*[storage[i] for i in ind])
+            return np.array(x), np.array(y), np.array(u), np.array(r).reshape(-1, 1), np.array(d).reshape(-1, 1)
+    # the reference draws the smoothing noise with torch's global CPU generator: replay the same stream to record it
+    torch.manual_seed(11)
+    noises = [torch.FloatTensor(B, A).normal_(0, 0.2).numpy().copy() for _ in range(iters)]
+    torch.manual_seed(11)
+    res = algo.train(Replay(), iters, batch_size=B, discount=0.99, tau=0.005, policy_noise=0.2, noise_clip=0.5, policy_freq=2)
+    out["storage"] = np.array([np.concatenate([s, s2, a, [r], [d]]) for s, s2, a, r, d in storage], dtype=np.float32)
+    out["inds"] = np.array(inds)
+    out["noises"] = np.array(noises)
+    out["q_loss"] = np.array(float(res[2]))
+    for name, m in (("actor2.", algo.actor), ("critic2.", algo.critic), ("actor_target2.", algo.actor_target),
+                    ("critic_target2.", algo.critic_target)):
+        for k, v in sd_np(m).items():
+            out[name + k] = v
+    np.savez_compressed(os.path.join(HERE, "td3_update.npz"), **out)
+    print("td3 q_loss", float(res[2]))
+
+
 if __name__ == "__main__":
     policies_and_update()
     returns()
     clocks()
+    td3()

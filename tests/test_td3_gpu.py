@@ -1,0 +1,58 @@
+"""TD3 update kernels against two iterations of the reference's own TD3.train (tests/golden/td3_update.npz)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_td3_train_matches_reference():
+    from apex_b200.td3 import TD3, ReplayBuffer
+    g = np.load(os.path.join(G, "td3_update.npz"))
+    S, A, B = 50, 10, 64
+    algo = TD3(S, A, 1.0, 1e-3, 1e-3)
+    sd = lambda pre: {k[len(pre):]: torch.as_tensor(v) for k, v in g.items() if k.startswith(pre)}
+    algo.load_state(sd("actor0."), sd("critic0."))
+    rb = ReplayBuffer(S, A, max_size=256)
+    rb.storage.copy_(torch.as_tensor(g["storage"]))
+    rb.size = 256
+    inds = [torch.as_tensor(i, dtype=torch.int64, device="cuda:0") for i in g["inds"]]
+    noises = [torch.as_tensor(n, dtype=torch.float32, device="cuda:0").contiguous() for n in g["noises"]]
+    q1, q2, q_loss = algo.train(rb, 2, batch_size=B, discount=0.99, tau=0.005, policy_noise=0.2, noise_clip=0.5, policy_freq=2,
+                                indices=inds, noises=noises)
+    assert abs(q_loss - float(g["q_loss"])) < 1e-4 * max(1.0, abs(float(g["q_loss"])))
+    for pre, mod, start in (("actor2.", algo.actor, "actor0."), ("critic2.", algo.critic, "critic0."),
+                            ("actor_target2.", algo.actor_target, "actor0."), ("critic_target2.", algo.critic_target, "critic0.")):
+        params = dict(mod.named_parameters())
+        for k, v in g.items():
+            if not k.startswith(pre):
+                continue
+            name = k[len(pre):]
+            before = g[start + name]
+            step_ref, step = v - before, params[name].detach().cpu().numpy() - before
+            scale = max(np.abs(step_ref).max(), 1e-12)
+            assert np.abs(step - step_ref).max() < 2e-2 * scale + 1e-7, (k, np.abs(step - step_ref).max(), scale)
+
+
+def test_replay_buffer_ring_and_gather():
+    from apex_b200.td3 import ReplayBuffer
+    from apex_b200 import _capi
+    rb = ReplayBuffer(4, 2, max_size=10)
+    dev = rb.device
+    for k in range(3):  # 12 rows into a ring of 10
+        n = 4
+        base = torch.arange(k * n, (k + 1) * n, device=dev, dtype=torch.float32).view(n, 1)
+        rb.add(base.repeat(1, 4), base.repeat(1, 4) + 0.5, base.repeat(1, 2) * 0.1, base.view(-1), (base.view(-1) % 2 == 0))
+    assert len(rb) == 10 and rb.ptr == 2
+    assert float(rb.storage[0, 0]) == 10.0 and float(rb.storage[2, 0]) == 2.0
+    idx = torch.tensor([0, 9, 5], dtype=torch.int64, device=dev)
+    z = lambda *s: torch.zeros(s, device=dev)
+    st, nx, sa, r, nd = z(3, 4), z(3, 4), z(3, 6), z(3), z(3)
+    _capi.check(_capi.lib().apex_replay_gather(rb.storage.data_ptr(), idx.data_ptr(), 3, 4, 2, st.data_ptr(), nx.data_ptr(),
+                                               sa.data_ptr(), r.data_ptr(), nd.data_ptr(), None), "gather")
+    row = rb.storage[idx]
+    assert torch.equal(st, row[:, :4]) and torch.equal(nx, row[:, 4:8]) and torch.equal(sa, torch.cat([row[:, :4], row[:, 8:10]], 1))
+    assert torch.equal(r, row[:, 10]) and torch.equal(nd, 1 - row[:, 11])
