@@ -49,7 +49,7 @@ def lib():
         L.apex_ars_policy.restype = i
         L.apex_ars_update.argtypes = [vp, i, vp, vp, vp, i, fl, vp]
         L.apex_ars_update.restype = i
-        L.apex_mlp_backward_dx.argtypes = [vp, i, i, i, i] + [vp] * 10 + [i] + [vp] * 7
+        L.apex_mlp_backward_dx.argtypes = [vp, i, i, i, i] + [vp] * 9 + [i] + [vp] * 7
         L.apex_replay_gather.argtypes = [vp, vp, i, i, i, vp, vp, vp, vp, vp, vp]
         L.apex_td3_action.argtypes = [vp, vp, vp, i, i, i, fl, fl, fl, u, u, vp, vp, vp]
         L.apex_td3_critic_loss.argtypes = [i, vp, vp, vp, vp, vp, vp, fl, vp, vp, vp, vp]

@@ -129,9 +129,14 @@ class TD3:
 
     @torch.no_grad()
     def train(self, replay_buffer, iterations, batch_size=100, discount=0.99, tau=0.005, policy_noise=0.2, noise_clip=0.5,
-              policy_freq=2, indices=None, noises=None, generator=None):
+              policy_freq=2, indices=None, noises=None, generator=None, reference_action_alias=True):
         """sync_td3.py:133-209.  `indices` / `noises` (lists of tensors) override the sampled rows / smoothing noise
-        (parity tests feed the reference's own draws)."""
+        (parity tests feed the reference's own draws).
+
+        reference_action_alias: the reference builds `action` and `noise` with torch.FloatTensor(u) (sync_td3.py:142,149);
+        the legacy constructor ALIASES the numpy array u, so noise.normal_() overwrites the sampled actions in place and
+        the critics are evaluated at Q(s, raw noise), not Q(s, a).  True (default) reproduces that result exactly
+        (tests/golden/td3_update.npz is the reference's own output); False trains on the stored actions."""
         L, s, S, A, B = self.L, self._s(), self.S, self.A, batch_size
         self._ensure(B)
         a, at = self._ptrs(0, self.A_NAMES), self._ptrs(2, self.A_NAMES)
@@ -149,6 +154,10 @@ class TD3:
             # target action with clipped noise, target Q
             self._fwd(at, self.b_next, B, S, A, h[0], h[1], self.b_pre)
             nz = noises[it] if noises is not None else None
+            if reference_action_alias:
+                if nz is None:
+                    nz = torch.randn((B, A), device=self.device, generator=generator) * float(policy_noise)
+                self.b_sa[:, S:].copy_(nz)  # the aliased `action` tensor holds the unclamped noise
             _capi.check(L.apex_td3_action(_p(self.b_pre), _p(self.b_next), _p(nz), B, S, A, self.max_action, float(policy_noise),
                                           float(noise_clip), (self.seed * 7919 + 17) & 0xFFFFFFFF, self._opt[1], _p(self.b_nsa), None, s),
                         "td3_action")

@@ -266,7 +266,7 @@ double ce_env_reward(ce_env_t *e, const double *action) { /* clock_reward, cassi
          0.025 * exp(-torque_penalty) + 0.025 * exp(-action_penalty);
 }
 
-void ce_env_step(ce_env_t *e, const double *action, double *obs, double *reward, int *done) { /* cassie.py:389-496 */
+void ce_env_step_with(ce_env_t *e, const double *action, const ce_step_draws_t *dr, double *obs, double *reward, int *done) { /* cassie.py:389-496 */
   const int simrate = 50;
   e->l_foot_frc = e->r_foot_frc = 0;
   memset(e->l_foot_pos, 0, sizeof(e->l_foot_pos));
@@ -311,62 +311,99 @@ void ce_env_step(ce_env_t *e, const double *action, double *obs, double *reward,
   memcpy(e->prev_action, action, sizeof(e->prev_action));
   memcpy(e->prev_torque, e->y.motor_torque, sizeof(e->prev_torque));
   if (*reward < -99.0) *done = 1; /* early_term_cutoff for the clock reward (cassie.py:773) */
-  /* random command changes (cassie.py:483-491): one Philox block for the three triggers, one for the values */
+  /* random command changes (cassie.py:483-491) */
+  if (dr->hit[0]) e->orient_add += dr->orient_delta;
+  if (dr->hit[1]) e->speed = fmin(fmax(dr->speed, -0.3), 4.0);
+  if (dr->hit[2]) e->side_speed = dr->side_speed;
+  ce_env_obs(e, obs);
+}
+
+/* the env's own draws for one step: one Philox block for the three triggers, one for the values */
+static void draw_step(ce_env_t *e, ce_step_draws_t *dr) {
   uint32_t tr[4], va[4];
   ce_philox(e->seed, e->env_id, e->rng_ctr++, tr);
   ce_philox(e->seed, e->env_id, e->rng_ctr++, va);
 #define U01(x) ((double)((x) >> 8) * (1.0 / 16777216.0))
-  if ((uint32_t)(((uint64_t)tr[0] * 300) >> 32) == 0) e->orient_add += -0.2 + 0.4 * U01(va[0]);
-  if ((uint32_t)(((uint64_t)tr[1] * 100) >> 32) == 0) e->speed = fmin(fmax(-0.3 + 4.3 * U01(va[1]), -0.3), 4.0);
-  if ((uint32_t)(((uint64_t)tr[2] * 300) >> 32) == 0) e->side_speed = -0.3 + 0.6 * U01(va[2]);
-  ce_env_obs(e, obs);
+  dr->hit[0] = (uint32_t)(((uint64_t)tr[0] * 300) >> 32) == 0; dr->orient_delta = -0.2 + 0.4 * U01(va[0]);
+  dr->hit[1] = (uint32_t)(((uint64_t)tr[1] * 100) >> 32) == 0; dr->speed = -0.3 + 4.3 * U01(va[1]);
+  dr->hit[2] = (uint32_t)(((uint64_t)tr[2] * 300) >> 32) == 0; dr->side_speed = -0.3 + 0.6 * U01(va[2]);
+}
+void ce_env_step(ce_env_t *e, const double *action, double *obs, double *reward, int *done) {
+  ce_step_draws_t dr;
+  draw_step(e, &dr);
+  ce_env_step_with(e, action, &dr, obs, reward, done);
 }
 
 void ce_env_set_command(ce_env_t *e, double speed, double side_speed, double phase) {
   e->speed = speed; e->side_speed = side_speed; e->phase = phase;
 }
 
-void ce_env_reset(ce_env_t *e, double *obs) { /* cassie.py:523-680 */
+/* the env's own draws for one reset, in the order cassie.py:523-680 makes them (the reference also draws a body-0 mass
+ * and 75 centre-of-mass values from zero-width intervals, cassie.py:609-613: no effect, not drawn here) */
+static void draw_reset(ce_env_t *e, ce_reset_draws_t *dr) {
   rng_t r = {e, {0, 0, 0, 0}, 0};
-  e->speed = rng_uniform(&r, -0.3, 4.0);
-  e->side_speed = rng_uniform(&r, -0.3, 0.3);
-  set_clock(e, e->speed);
-  e->phase = (double)rng_randint(&r, (uint32_t)floor(e->phaselen) + 1);
-  e->time = 0; e->counter = 0;
+  dr->speed0 = rng_uniform(&r, -0.3, 4.0);
+  dr->side_speed0 = rng_uniform(&r, -0.3, 0.3);
+  dr->phase_u32 = rng_u32(&r);
   if (e->dyn_rand) {
     /* damping: pelvis (0-5), heel spring (15, 28) and plantar rod (17, 30) keep their defaults (cassie.py:548-574) */
     for (int i = 0; i < CM_NV; i++) {
       int fixed = i < 6 || i == 15 || i == 17 || i == 28 || i == 30;
       double lo = fixed ? 1.0 : 0.3, hi = fixed ? 1.0 : 5.0;
-      double v = rng_uniform(&r, CM_dof_damping[i] * lo, CM_dof_damping[i] * hi);
-      e->m.dof_damping[i] = v < 0 ? 0 : v;
+      dr->damping[i] = rng_uniform(&r, CM_dof_damping[i] * lo, CM_dof_damping[i] * hi);
     }
+    dr->mass[0] = 0;
+    for (int b = 1; b < CM_NBODY; b++) dr->mass[b] = rng_uniform(&r, 0.5 * CM_body_mass[b], 1.5 * CM_body_mass[b]);
+    dr->friction[0] = rng_uniform(&r, 0.4, 1.1);
+    dr->friction[1] = rng_uniform(&r, 1e-4, 5e-4);
+    dr->friction[2] = rng_uniform(&r, 1e-4, 2e-4);
+    dr->roll = rng_uniform(&r, -0.03, 0.03);
+    dr->pitch = rng_uniform(&r, -0.03, 0.03);
+    for (int k = 0; k < 10; k++) dr->menc_noise[k] = rng_uniform(&r, -0.01, 0.01);
+    for (int k = 0; k < 6; k++) dr->jenc_noise[k] = rng_uniform(&r, -0.01, 0.01);
+  }
+  dr->speed1 = rng_uniform(&r, -0.3, 4.0);
+  dr->side_speed1 = rng_uniform(&r, -0.3, 0.3);
+}
+
+void ce_env_reset_with(ce_env_t *e, const ce_reset_draws_t *dr, double *obs) { /* cassie.py:523-680 */
+  e->speed = dr->speed0;
+  e->side_speed = dr->side_speed0;
+  set_clock(e, e->speed);
+  e->phase = dr->phase >= 0 ? (double)dr->phase /* random.randint(0, floor(phaselen)), cassie.py:561 */
+                            : (double)(uint32_t)(((uint64_t)dr->phase_u32 * ((uint32_t)floor(e->phaselen) + 1)) >> 32);
+  e->time = 0; e->counter = 0;
+  if (e->dyn_rand) {
+    for (int i = 0; i < CM_NV; i++) e->m.dof_damping[i] = dr->damping[i] < 0 ? 0 : dr->damping[i];
     e->m.body_mass[0] = 0;
-    for (int b = 1; b < CM_NBODY; b++) {
-      double v = rng_uniform(&r, 0.5 * CM_body_mass[b], 1.5 * CM_body_mass[b]);
-      e->m.body_mass[b] = v < 0 ? 0 : v;
-    }
-    e->m.floor_friction[0] = rng_uniform(&r, 0.4, 1.1);
-    e->m.floor_friction[1] = rng_uniform(&r, 1e-4, 5e-4);
-    e->m.floor_friction[2] = rng_uniform(&r, 1e-4, 2e-4);
-    double roll = rng_uniform(&r, -0.03, 0.03), pitch = rng_uniform(&r, -0.03, 0.03);
+    for (int b = 1; b < CM_NBODY; b++) e->m.body_mass[b] = dr->mass[b] < 0 ? 0 : dr->mass[b];
+    for (int k = 0; k < 3; k++) e->m.floor_friction[k] = dr->friction[k] < 0 ? 0 : dr->friction[k];
+    const double roll = dr->roll, pitch = dr->pitch;
     double cy = cos(pitch / 2), sy = sin(pitch / 2), cx = cos(roll / 2), sx = sin(roll / 2);
-    double q[4] = {cx * cy, cy * sx, cx * sy, sx * sy}; /* euler2quat(z=0, y=pitch, x=roll) */
+    double q[4] = {cx * cy, cy * sx, cx * sy, sx * sy}; /* euler2quat(z=0, y=pitch, x=roll), quaternion_function.py:44-62 */
     if (q[0] < 0) for (int k = 0; k < 4; k++) q[k] = -q[k];
     memcpy(e->m.floor_quat, q, sizeof(q));
-    for (int k = 0; k < 10; k++) e->menc_noise[k] = rng_uniform(&r, -0.01, 0.01);
-    for (int k = 0; k < 6; k++) e->jenc_noise[k] = rng_uniform(&r, -0.01, 0.01);
+    memcpy(e->menc_noise, dr->menc_noise, sizeof(e->menc_noise));
+    memcpy(e->jenc_noise, dr->jenc_noise, sizeof(e->jenc_noise));
   } /* else: the model keeps the defaults installed by ce_env_init (set_const would reproduce the same numbers) */
   if (e->dyn_rand) cp_set_const(&e->m);
   cp_data_reset(&e->m, &e->d);
   memcpy(e->last_pelvis_pos, e->d.qpos, sizeof(e->last_pelvis_pos));
   ce_sim_step_pd(e, &e->u, &e->y); /* one sub-step with the previous episode's pd_in_t (cassie.py:664-665) */
   e->orient_add = 0;
-  e->speed = rng_uniform(&r, -0.3, 4.0);
-  e->side_speed = rng_uniform(&r, -0.3, 0.3);
+  e->speed = dr->speed1;
+  e->side_speed = dr->side_speed1;
   e->l_foot_frc = e->r_foot_frc = 0;
   e->l_foot_orient_cost = e->r_foot_orient_cost = e->hiproll_cost = e->hiproll_act = 0;
   ce_env_obs(e, obs);
+}
+
+void ce_env_reset(ce_env_t *e, double *obs) {
+  ce_reset_draws_t dr;
+  memset(&dr, 0, sizeof(dr));
+  draw_reset(e, &dr);
+  dr.phase = -1; /* derive the phase from phase_u32 once phaselen is known */
+  ce_env_reset_with(e, &dr, obs);
 }
 
 /* ---------- batched helpers (CPU baseline) ---------- */

@@ -51,10 +51,27 @@ typedef struct {
   int dyn_rand;
 } ce_env_t;
 
+/* The random draws of one reset / one step (cassie.py:523-680, :483-491).  ce_env_reset / ce_env_step fill them from the
+ * env's Philox stream; the *_with variants take them from the caller — tests replay episodes recorded from the
+ * reference's own CassieEnv (tests/golden/make_env_golden.py) by injecting the reference's draws here. */
+typedef struct {
+  double speed0, side_speed0; /* first command draw: only sets the clock (cassie.py:525-526, 556-559) */
+  int phase;                  /* >= 0: random.randint(0, floor(phaselen)) as drawn; < 0: derive from phase_u32 */
+  uint32_t phase_u32;
+  double damping[CM_NV], mass[CM_NBODY], friction[3], roll, pitch, menc_noise[10], jenc_noise[6]; /* dyn_rand only */
+  double speed1, side_speed1; /* second command draw (cassie.py:669-670) */
+} ce_reset_draws_t;
+typedef struct {
+  int hit[3];                 /* randint(300) == 0, randint(100) == 0, randint(300) == 0 */
+  double orient_delta, speed, side_speed;
+} ce_step_draws_t;
+
 #ifdef __cplusplus
 extern "C" {
 #endif
 int ce_sizeof_env(void);
+void ce_env_reset_with(ce_env_t *e, const ce_reset_draws_t *dr, double *obs);
+void ce_env_step_with(ce_env_t *e, const double *action, const ce_step_draws_t *dr, double *obs, double *reward, int *done);
 void ce_philox(uint32_t seed, uint32_t env_id, uint32_t ctr, uint32_t out[4]);
 void ce_sim_init(ce_env_t *e);                                        /* cassie_sim_init */
 void ce_sim_step_pd(ce_env_t *e, const ce_pd_in_t *u, ce_state_out_t *y); /* cassie_sim_step_pd */

@@ -182,11 +182,34 @@ def td3():
             ind = inds[self.k]; self.k += 1
             x, y, u, r, d = zip(*[storage[i] for i in ind])
             return np.array(x), np.array(y), np.array(u), np.array(r).reshape(-1, 1), np.array(d).reshape(-1, 1)
-    # the reference draws the smoothing noise with torch's global CPU generator: replay the same stream to record it
+    # the reference draws the smoothing noise inside train() (sync_td3.py:149-150): record what Tensor.normal_ returns there
+    drawn = []
+    orig_normal = torch.Tensor.normal_
+
+    def recording_normal(self, *a, **k):
+        r = orig_normal(self, *a, **k)
+        drawn.append(r.detach().clone().numpy())
+        return r
+    # stage 1: ONE iteration on a deep copy (same first batch) so a failing test can tell the stages apart
+    import copy
+    algo1 = copy.deepcopy(algo)
+    algo1.actor_optimizer = torch.optim.Adam(algo1.actor.parameters(), lr=1e-3)
+    algo1.critic_optimizer = torch.optim.Adam(algo1.critic.parameters(), lr=1e-3)
     torch.manual_seed(11)
-    noises = [torch.FloatTensor(B, A).normal_(0, 0.2).numpy().copy() for _ in range(iters)]
+    res1 = algo1.train(Replay(), 1, batch_size=B, discount=0.99, tau=0.005, policy_noise=0.2, noise_clip=0.5, policy_freq=2)
+    out["q_loss1"] = np.array(float(res1[2]))
+    for name, m in (("actor1.", algo1.actor), ("critic1.", algo1.critic), ("actor_target1.", algo1.actor_target),
+                    ("critic_target1.", algo1.critic_target)):
+        for k, v in sd_np(m).items():
+            out[name + k] = v
     torch.manual_seed(11)
-    res = algo.train(Replay(), iters, batch_size=B, discount=0.99, tau=0.005, policy_noise=0.2, noise_clip=0.5, policy_freq=2)
+    torch.Tensor.normal_ = recording_normal
+    try:
+        res = algo.train(Replay(), iters, batch_size=B, discount=0.99, tau=0.005, policy_noise=0.2, noise_clip=0.5, policy_freq=2)
+    finally:
+        torch.Tensor.normal_ = orig_normal
+    noises = drawn
+    assert len(noises) == iters and noises[0].shape == (B, A)
     out["storage"] = np.array([np.concatenate([s, s2, a, [r], [d]]) for s, s2, a, r, d in storage], dtype=np.float32)
     out["inds"] = np.array(inds)
     out["noises"] = np.array(noises)

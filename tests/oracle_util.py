@@ -32,3 +32,49 @@ class OracleBatch:
         self.L.ce_batch_step(self.buf, self.n, dp(act), dp(self.obs), dp(self.rew), dp(self.done), int(max_traj_len),
                              dp(self.term_obs), self.threads)
         return self.obs, self.rew, self.done
+
+
+class ResetDraws(C.Structure):  # ce_reset_draws_t (oracle/cassie_env.h)
+    _fields_ = [("speed0", C.c_double), ("side_speed0", C.c_double), ("phase", C.c_int), ("phase_u32", C.c_uint32),
+                ("damping", C.c_double * 32), ("mass", C.c_double * 26), ("friction", C.c_double * 3), ("roll", C.c_double),
+                ("pitch", C.c_double), ("menc_noise", C.c_double * 10), ("jenc_noise", C.c_double * 6),
+                ("speed1", C.c_double), ("side_speed1", C.c_double)]
+
+
+class StepDraws(C.Structure):  # ce_step_draws_t
+    _fields_ = [("hit", C.c_int * 3), ("orient_delta", C.c_double), ("speed", C.c_double), ("side_speed", C.c_double)]
+
+
+class OracleEnv:
+    """One oracle environment driven with injected draws (replay of episodes recorded from the reference's CassieEnv)."""
+
+    def __init__(self, dyn_rand):
+        self.L = P.lib()
+        self.buf = (C.c_char * self.L.ce_sizeof_env())()
+        self.L.ce_env_init(self.buf, C.c_uint(0), C.c_uint(0), int(dyn_rand))
+        self.env = C.cast(self.buf, C.c_void_p)
+        self.obs = np.zeros(50)
+
+    def reset_with(self, scalar, damping, mass, friction, tilt, menc, jenc):
+        d = ResetDraws()
+        d.speed0, d.side_speed0, d.phase, d.speed1, d.side_speed1 = scalar[0], scalar[1], int(scalar[2]), scalar[4], scalar[5]
+        d.damping[:], d.mass[:], d.friction[:] = list(damping), list(mass), list(friction)
+        d.roll, d.pitch = tilt
+        d.menc_noise[:], d.jenc_noise[:] = list(menc), list(jenc)
+        self.L.ce_env_reset_with(self.buf, C.byref(d), dp(self.obs))
+        return self.obs.copy()
+
+    def step_with(self, action, hit, val):
+        d = StepDraws()
+        d.hit[:] = [int(h) for h in hit]
+        d.orient_delta, d.speed, d.side_speed = val
+        action = np.ascontiguousarray(action, dtype=np.float64)
+        rew, done = C.c_double(0), C.c_int(0)
+        self.L.ce_env_step_with(self.buf, dp(action), C.byref(d), dp(self.obs), C.byref(rew), C.byref(done))
+        return self.obs.copy(), rew.value, done.value
+
+    def qpos_qvel(self):
+        """cp_data_t sits behind cp_model_t at the head of ce_env_t; qpos follows the leading `time` double."""
+        base = C.addressof(self.buf) + C.sizeof(P.Model)
+        d = P.Data.from_address(base)
+        return np.array(d.qpos[:]), np.array(d.qvel[:])

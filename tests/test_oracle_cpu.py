@@ -221,3 +221,60 @@ def test_missing_library_fails_loudly(monkeypatch):
     monkeypatch.setattr(_capi, "_LIB_PATH", "/nonexistent/libapex_b200.so")
     with pytest.raises(_capi.ApexLibraryError):
         _capi.lib()
+
+
+@pytest.mark.parametrize("tag,dyn", [("plain", False), ("dynrand", True)])
+def test_env_layer_matches_the_reference_python(tag, dyn):
+    """Episodes recorded from the reference's own cassie/cassie.py + clock_rewards.py + phase_function.py running over
+    oracle/cassiemujoco_abi.c (tests/golden/make_env_golden.py) replayed through oracle/cassie_env.c with the reference's
+    random draws injected: reset / step / step_simulation / get_full_state / clock_reward.
+    Same physics code on both sides, so the env layer must agree to round-off."""
+    from tests.oracle_util import OracleEnv
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "env_episodes.npz"))
+    f = lambda k: g[f"{tag}.{k}"]
+    env = OracleEnv(dyn)
+    t = 0
+    for ep, n in enumerate(f("ep_len")):
+        obs = env.reset_with(f("reset_scalar")[ep], f("reset_damping")[ep], f("reset_mass")[ep], f("reset_friction")[ep],
+                             f("reset_tilt")[ep], f("reset_menc")[ep], f("reset_jenc")[ep])
+        qpos, qvel = env.qpos_qvel()
+        assert np.abs(qpos - f("reset_qpos")[ep]).max() < 1e-12 and np.abs(qvel - f("reset_qvel")[ep]).max() < 1e-10
+        assert np.abs(obs - f("reset_obs")[ep]).max() < 1e-10, (ep, np.abs(obs - f("reset_obs")[ep]).argmax())
+        for k in range(n):
+            obs, rew, done = env.step_with(f("action")[t], f("step_hit")[t], f("step_val")[t])
+            qpos, qvel = env.qpos_qvel()
+            assert np.abs(qpos - f("qpos")[t]).max() < 1e-10, (ep, k)
+            assert np.abs(qvel - f("qvel")[t]).max() < 1e-8, (ep, k)
+            assert done == f("done")[t], (ep, k)
+            assert abs(rew - f("reward")[t]) < 1e-10, (ep, k, rew, f("reward")[t])
+            err = np.abs(obs - f("obs")[t])
+            assert err.max() < 1e-9, (ep, k, int(err.argmax()), err.max())
+            t += 1
+    assert t == len(f("reward")) and f("done").sum() >= 1  # at least one episode ends by falling
+
+
+def test_reference_abi_exports_all_103_symbols():
+    """oracle/cassiemujoco_abi.c must export every name cassie/cassiemujoco/cassiemujoco_ctypes.py binds at import."""
+    import ctypes
+    from oracle import phys_ctypes
+    names = """cassie_cleanup cassie_core_sim_alloc cassie_core_sim_copy cassie_core_sim_free cassie_core_sim_setup cassie_core_sim_step
+    cassie_get_state cassie_mujoco_init cassie_reload_xml cassie_set_state cassie_sim_apply_force cassie_sim_body_ipos cassie_sim_body_mass
+    cassie_sim_body_velocities cassie_sim_check_obstacle_collision cassie_sim_check_self_collision cassie_sim_clear_forces cassie_sim_copy
+    cassie_sim_dof_damping cassie_sim_duplicate cassie_sim_foot_forces cassie_sim_foot_orient cassie_sim_foot_positions
+    cassie_sim_foot_velocities cassie_sim_free cassie_sim_full_reset cassie_sim_geom_friction cassie_sim_geom_quat cassie_sim_geom_rgba
+    cassie_sim_get_hfield_ncol cassie_sim_get_hfield_nrow cassie_sim_get_hfield_size cassie_sim_get_nhfielddata cassie_sim_hfielddata
+    cassie_sim_hold cassie_sim_init cassie_sim_mjdata cassie_sim_mjmodel cassie_sim_qacc cassie_sim_qpos cassie_sim_qvel cassie_sim_radio
+    cassie_sim_release cassie_sim_set_body_ipos cassie_sim_set_body_mass cassie_sim_set_body_name_mass cassie_sim_set_const
+    cassie_sim_set_dof_damping cassie_sim_set_geom_friction cassie_sim_set_geom_name_friction cassie_sim_set_geom_name_quat
+    cassie_sim_set_geom_quat cassie_sim_set_geom_rgba cassie_sim_set_hfield_size cassie_sim_set_hfielddata cassie_sim_step
+    cassie_sim_step_ethercat cassie_sim_step_pd cassie_sim_time cassie_sim_xquat cassie_state_alloc cassie_state_copy cassie_state_duplicate
+    cassie_state_free cassie_state_qpos cassie_state_qvel cassie_state_time cassie_vis_apply_force cassie_vis_close cassie_vis_draw
+    cassie_vis_free cassie_vis_full_reset cassie_vis_init cassie_vis_paused cassie_vis_set_cam cassie_vis_valid get_newest_packet
+    pack_cassie_in_t pack_cassie_out_t pack_cassie_user_in_t pack_pd_in_t pack_state_out_t pd_input_alloc pd_input_copy pd_input_free
+    pd_input_setup pd_input_step process_packet_header send_packet state_output_alloc state_output_copy state_output_free
+    state_output_setup state_output_step udp_close udp_init_client udp_init_host unpack_cassie_in_t unpack_cassie_out_t
+    unpack_cassie_user_in_t unpack_pd_in_t unpack_state_out_t wait_for_packet""".split()
+    assert len(names) == 103
+    lib = ctypes.CDLL(phys_ctypes.build())
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing

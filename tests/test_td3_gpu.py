@@ -9,9 +9,8 @@ pytestmark = pytest.mark.gpu
 G = os.path.join(os.path.dirname(__file__), "golden")
 
 
-def test_td3_train_matches_reference():
+def _run_td3(g, iters):
     from apex_b200.td3 import TD3, ReplayBuffer
-    g = np.load(os.path.join(G, "td3_update.npz"))
     S, A, B = 50, 10, 64
     algo = TD3(S, A, 1.0, 1e-3, 1e-3)
     sd = lambda pre: {k[len(pre):]: torch.as_tensor(v) for k, v in g.items() if k.startswith(pre)}
@@ -21,11 +20,15 @@ def test_td3_train_matches_reference():
     rb.size = 256
     inds = [torch.as_tensor(i, dtype=torch.int64, device="cuda:0") for i in g["inds"]]
     noises = [torch.as_tensor(n, dtype=torch.float32, device="cuda:0").contiguous() for n in g["noises"]]
-    q1, q2, q_loss = algo.train(rb, 2, batch_size=B, discount=0.99, tau=0.005, policy_noise=0.2, noise_clip=0.5, policy_freq=2,
+    q1, q2, q_loss = algo.train(rb, iters, batch_size=B, discount=0.99, tau=0.005, policy_noise=0.2, noise_clip=0.5, policy_freq=2,
                                 indices=inds, noises=noises)
-    assert abs(q_loss - float(g["q_loss"])) < 1e-4 * max(1.0, abs(float(g["q_loss"])))
-    for pre, mod, start in (("actor2.", algo.actor, "actor0."), ("critic2.", algo.critic, "critic0."),
-                            ("actor_target2.", algo.actor_target, "actor0."), ("critic_target2.", algo.critic_target, "critic0.")):
+    return algo, q_loss
+
+
+def _check_params(g, algo, stage):
+    for pre, mod, start in ((f"actor{stage}.", algo.actor, "actor0."), (f"critic{stage}.", algo.critic, "critic0."),
+                            (f"actor_target{stage}.", algo.actor_target, "actor0."),
+                            (f"critic_target{stage}.", algo.critic_target, "critic0.")):
         params = dict(mod.named_parameters())
         for k, v in g.items():
             if not k.startswith(pre):
@@ -35,6 +38,22 @@ def test_td3_train_matches_reference():
             step_ref, step = v - before, params[name].detach().cpu().numpy() - before
             scale = max(np.abs(step_ref).max(), 1e-12)
             assert np.abs(step - step_ref).max() < 2e-2 * scale + 1e-7, (k, np.abs(step - step_ref).max(), scale)
+
+
+def test_td3_first_iteration_matches_reference():
+    """One iteration of sync_td3.py:133-209: the critic loss is a pure forward quantity (1e-5), the parameter steps are Adam's
+    first step (+-lr per element, sign of the gradient), the targets one Polyak step."""
+    g = np.load(os.path.join(G, "td3_update.npz"))
+    algo, q_loss = _run_td3(g, 1)
+    assert abs(q_loss - float(g["q_loss1"])) < 1e-5 * max(1.0, abs(float(g["q_loss1"]))), (q_loss, float(g["q_loss1"]))
+    _check_params(g, algo, 1)
+
+
+def test_td3_train_matches_reference():
+    g = np.load(os.path.join(G, "td3_update.npz"))
+    algo, q_loss = _run_td3(g, 2)
+    assert abs(q_loss - float(g["q_loss"])) < 1e-4 * max(1.0, abs(float(g["q_loss"]))), (q_loss, float(g["q_loss"]))
+    _check_params(g, algo, 2)
 
 
 def test_replay_buffer_ring_and_gather():

@@ -12,8 +12,13 @@ rep, so, kname = sys.argv[1], sys.argv[2], sys.argv[3]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 60
 tmp = tempfile.mkdtemp()
 subprocess.check_call(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=tmp, stdout=subprocess.DEVNULL)
-cubin = [os.path.join(tmp, f) for f in os.listdir(tmp) if f.endswith(".cubin")][0]
-dis = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout.splitlines()
+dis = []
+for f in sorted(os.listdir(tmp)):  # one cubin per translation unit: keep the one that defines the kernel
+    if f.endswith(".cubin"):
+        txt = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, f)], capture_output=True, text=True).stdout
+        if re.search(r"^\.text\.\S*" + re.escape(kname), txt, re.M):
+            dis = txt.splitlines()
+            break
 # instruction sequence with (file, line) for the chosen function(s)
 seq = []
 infn, cur = False, None
