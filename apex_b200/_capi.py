@@ -30,6 +30,11 @@ def lib():
         L.apex_cassie_mj_step.argtypes = [i, vp, ip, i, i, vp]
         for f in (L.apex_cassie_env_init, L.apex_cassie_env_reset, L.apex_cassie_env_step, L.apex_cassie_mj_step):
             f.restype = i
+        L.apex_cassietraj_env_init.argtypes = [i, vp, ip, i, u, i, i, vp]
+        L.apex_cassietraj_env_reset.argtypes = [i, vp, ip, i, vp, vp, i, i, vp]
+        L.apex_cassietraj_env_step.argtypes = [i, vp, ip, i, vp, vp, vp, ip, vp, i, vp, vp, i, i, vp]
+        for f in (L.apex_cassietraj_env_init, L.apex_cassietraj_env_reset, L.apex_cassietraj_env_step):
+            f.restype = i
         L.apex_cassie_set_warps_per_cta.argtypes = [i]
         L.apex_cassie_set_warps_per_cta.restype = None
         fl, lng = C.c_float, C.c_long

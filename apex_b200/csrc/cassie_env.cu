@@ -16,22 +16,23 @@ template <typename T> __device__ __forceinline__ void ws_store(const CassieWs<T>
   for (int k = lane; k < I_WORDS; k += 32) sti[k] = w.sti[k];
 }
 
-template <typename T> __global__ void __launch_bounds__(32) k_env_init(T *st, int *sti, int n, unsigned seed, int env_id0, int dyn) {
+template <typename T> __global__ void __launch_bounds__(32) k_env_init(T *st, int *sti, int n, unsigned seed, int env_id0, int dyn, int variant) {
   extern __shared__ __align__(16) unsigned char smem[];
   CassieWs<T> &w = *reinterpret_cast<CassieWs<T> *>(smem);
   const int e = blockIdx.x, lane = threadIdx.x;
   if (e >= n) return;
   cw_env_init<T>(w, seed, (unsigned)(env_id0 + e), dyn, lane);
+  if (lane == 0) w.sti[I_VARIANT] = variant;
   ws_store(w, st + (size_t)e * S_WORDS, sti + (size_t)e * I_WORDS, lane);
 }
 
-template <typename T> __global__ void __launch_bounds__(32) k_env_reset(T *st, int *sti, int n, T *obs) {
+template <typename T> __global__ void __launch_bounds__(32) k_env_reset(T *st, int *sti, int n, T *obs, CassieTraj<T> traj) {
   extern __shared__ __align__(16) unsigned char smem[];
   CassieWs<T> &w = *reinterpret_cast<CassieWs<T> *>(smem);
   const int e = blockIdx.x, lane = threadIdx.x;
   if (e >= n) return;
   ws_load(w, st + (size_t)e * S_WORDS, sti + (size_t)e * I_WORDS, lane);
-  cw_env_reset<T>(w, obs + (size_t)e * CW_OBS, lane);
+  cw_env_reset<T>(w, obs + (size_t)e * CW_OBS, traj, lane);
   ws_store(w, st + (size_t)e * S_WORDS, sti + (size_t)e * I_WORDS, lane);
 }
 
@@ -39,7 +40,7 @@ template <typename T> __global__ void __launch_bounds__(32) k_env_reset(T *st, i
  * warps past the end of the batch run the barriers only. */
 template <typename T>
 __global__ void k_env_step(T *st, int *sti, int n, const T *action, T *obs, T *reward, int *done, T *term_obs, int max_traj_len,
-                           const int *active) {
+                           const int *active, CassieTraj<T> traj) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   CassieWs<T> &w = reinterpret_cast<CassieWs<T> *>(smem)[warp];
@@ -62,7 +63,7 @@ __global__ void k_env_step(T *st, int *sti, int n, const T *action, T *obs, T *r
     __syncwarp();
     if (term_obs) for (int k = lane; k < CW_OBS; k += 32) term_obs[(size_t)e * CW_OBS + k] = o[k];
     __syncwarp();
-    cw_env_reset<T>(w, o, lane);
+    cw_env_reset<T>(w, o, traj, lane);
   }
   ws_store(w, st + (size_t)e * S_WORDS, sti + (size_t)e * I_WORDS, lane);
 }
@@ -109,7 +110,7 @@ int apex_cassie_layout(const char *name) {
       {"meaninertia", S_MEANINERTIA}, {"footvel", S_FOOTVEL},
       {"drive_hist", I_DRIVEHIST}, {"time", I_TIME}, {"counter", I_COUNTER}, {"has_prev", I_HASPREV}, {"has_u", I_HASU},
       {"drive_init", I_DRIVEINIT}, {"joint_init", I_JOINTINIT}, {"flags", I_FLAGS}, {"stepcount", I_STEPCOUNT}, {"rng_ctr", I_RNGCTR},
-      {"env_id", I_ENVID}, {"seed", I_SEED}, {"dyn_rand", I_DYNRAND}, {"solver_iter", I_SOLVER_ITER}, {"ncon", I_NCON}, {"nefc", I_NEFC}};
+      {"env_id", I_ENVID}, {"seed", I_SEED}, {"dyn_rand", I_DYNRAND}, {"solver_iter", I_SOLVER_ITER}, {"ncon", I_NCON}, {"nefc", I_NEFC}, {"variant", I_VARIANT}};
   for (size_t i = 0; i < sizeof(tab) / sizeof(tab[0]); i++)
     if (strcmp(tab[i].n, name) == 0) return tab[i].off;
   return -1;
@@ -125,46 +126,76 @@ int apex_cassie_layout(const char *name) {
   else return -1000;                             \
   return finish();
 
-int apex_cassie_env_init(int dtype, void *st, int *sti, int n, unsigned seed, int env_id0, int dyn_rand, void *stream) {
+static int env_init_impl(int dtype, void *st, int *sti, int n, unsigned seed, int env_id0, int dyn_rand, int variant, void *stream) {
   DISPATCH(
       if ((rc = prep(k_env_init<float>, sizeof(CassieWs<float>)))) return rc;
-      (k_env_init<float><<<n, 32, sizeof(CassieWs<float>), s>>>((float *)st, sti, n, seed, env_id0, dyn_rand)),
+      (k_env_init<float><<<n, 32, sizeof(CassieWs<float>), s>>>((float *)st, sti, n, seed, env_id0, dyn_rand, variant)),
       if ((rc = prep(k_env_init<double>, sizeof(CassieWs<double>)))) return rc;
-      (k_env_init<double><<<n, 32, sizeof(CassieWs<double>), s>>>((double *)st, sti, n, seed, env_id0, dyn_rand)))
+      (k_env_init<double><<<n, 32, sizeof(CassieWs<double>), s>>>((double *)st, sti, n, seed, env_id0, dyn_rand, variant)))
 }
 
-int apex_cassie_env_reset(int dtype, void *st, int *sti, int n, void *obs, void *stream) {
+static int env_reset_impl(int dtype, void *st, int *sti, int n, void *obs, const void *traj, int traj_rows, int traj_len, void *stream) {
   if (!obs) return -1000;
+  const CassieTraj<float> tf = {(const float *)traj, traj_rows, traj_len};
+  const CassieTraj<double> td = {(const double *)traj, traj_rows, traj_len};
   DISPATCH(
       if ((rc = prep(k_env_reset<float>, sizeof(CassieWs<float>)))) return rc;
-      (k_env_reset<float><<<n, 32, sizeof(CassieWs<float>), s>>>((float *)st, sti, n, (float *)obs)),
+      (k_env_reset<float><<<n, 32, sizeof(CassieWs<float>), s>>>((float *)st, sti, n, (float *)obs, tf)),
       if ((rc = prep(k_env_reset<double>, sizeof(CassieWs<double>)))) return rc;
-      (k_env_reset<double><<<n, 32, sizeof(CassieWs<double>), s>>>((double *)st, sti, n, (double *)obs)))
+      (k_env_reset<double><<<n, 32, sizeof(CassieWs<double>), s>>>((double *)st, sti, n, (double *)obs, td)))
 }
 
 static int env_step_impl(int dtype, void *st, int *sti, int n, const void *action, void *obs, void *reward, int *done,
-                         void *term_obs, int max_traj_len, const int *active, void *stream) {
+                         void *term_obs, int max_traj_len, const int *active, const void *traj, int traj_rows, int traj_len,
+                         void *stream) {
   if (!action || !obs || !reward || !done) return -1000;
   int wpb = apex_cassie_warps_per_cta;
   if (dtype == 1 && wpb > 7) wpb = 7;
   if (wpb > 14) wpb = 14;
   if (wpb < 1) wpb = 1;
+  const CassieTraj<float> tf = {(const float *)traj, traj_rows, traj_len};
+  const CassieTraj<double> td = {(const double *)traj, traj_rows, traj_len};
   DISPATCH(
       if ((rc = prep(k_env_step<float>, wpb * sizeof(CassieWs<float>)))) return rc;
       (k_env_step<float><<<(n + wpb - 1) / wpb, 32 * wpb, wpb * sizeof(CassieWs<float>), s>>>((float *)st, sti, n, (const float *)action, (float *)obs,
-                                                                (float *)reward, done, (float *)term_obs, max_traj_len, active)),
+                                                                (float *)reward, done, (float *)term_obs, max_traj_len, active, tf)),
       if ((rc = prep(k_env_step<double>, wpb * sizeof(CassieWs<double>)))) return rc;
       (k_env_step<double><<<(n + wpb - 1) / wpb, 32 * wpb, wpb * sizeof(CassieWs<double>), s>>>((double *)st, sti, n, (const double *)action, (double *)obs,
-                                                                  (double *)reward, done, (double *)term_obs, max_traj_len, active)))
+                                                                  (double *)reward, done, (double *)term_obs, max_traj_len, active, td)))
 }
 
+int apex_cassie_env_init(int dtype, void *st, int *sti, int n, unsigned seed, int env_id0, int dyn_rand, void *stream) {
+  return env_init_impl(dtype, st, sti, n, seed, env_id0, dyn_rand, 0, stream);
+}
+int apex_cassie_env_reset(int dtype, void *st, int *sti, int n, void *obs, void *stream) {
+  return env_reset_impl(dtype, st, sti, n, obs, nullptr, 0, 0, stream);
+}
 int apex_cassie_env_step(int dtype, void *st, int *sti, int n, const void *action, void *obs, void *reward, int *done,
                          void *term_obs, int max_traj_len, void *stream) {
-  return env_step_impl(dtype, st, sti, n, action, obs, reward, done, term_obs, max_traj_len, nullptr, stream);
+  return env_step_impl(dtype, st, sti, n, action, obs, reward, done, term_obs, max_traj_len, nullptr, nullptr, 0, 0, stream);
 }
 int apex_cassie_env_step_masked(int dtype, void *st, int *sti, int n, const void *action, void *obs, void *reward, int *done,
                                 void *term_obs, int max_traj_len, const int *active, void *stream) {
-  return env_step_impl(dtype, st, sti, n, action, obs, reward, done, term_obs, max_traj_len, active, stream);
+  return env_step_impl(dtype, st, sti, n, action, obs, reward, done, term_obs, max_traj_len, active, nullptr, 0, 0, stream);
+}
+
+/* CassieTraj-v0 (cassie/cassie_traj.py): same state record, variant flag 1, resets start from the reference trajectory */
+static int traj_ok(const void *traj, int traj_rows, int traj_len) {
+  return traj && traj_rows >= 1 && traj_len >= CW_SIMRATE && traj_rows >= traj_len / CW_SIMRATE + 1;
+}
+int apex_cassietraj_env_init(int dtype, void *st, int *sti, int n, unsigned seed, int env_id0, int dyn_rand, void *stream) {
+  return env_init_impl(dtype, st, sti, n, seed, env_id0, dyn_rand, 1, stream);
+}
+int apex_cassietraj_env_reset(int dtype, void *st, int *sti, int n, void *obs, const void *traj, int traj_rows, int traj_len,
+                              void *stream) {
+  if (!traj_ok(traj, traj_rows, traj_len)) return -1000;
+  return env_reset_impl(dtype, st, sti, n, obs, traj, traj_rows, traj_len, stream);
+}
+int apex_cassietraj_env_step(int dtype, void *st, int *sti, int n, const void *action, void *obs, void *reward, int *done,
+                             void *term_obs, int max_traj_len, const int *active, const void *traj, int traj_rows, int traj_len,
+                             void *stream) {
+  if (!traj_ok(traj, traj_rows, traj_len)) return -1000;
+  return env_step_impl(dtype, st, sti, n, action, obs, reward, done, term_obs, max_traj_len, active, traj, traj_rows, traj_len, stream);
 }
 
 int apex_cassie_mj_step(int dtype, void *st, int *sti, int n, int flags, void *stream) {

@@ -1,8 +1,14 @@
-/* Wrapper layer (cassie_sim_step_pd) and Cassie-v0 env logic on top of cassie_warp.h; same warp-per-env scheme.
+/* Wrapper layer (cassie_sim_step_pd) and Cassie-v0 / CassieTraj-v0 env logic on top of cassie_warp.h; same warp-per-env scheme.
  * Reference: libcassiemujoco.so cassie_sim_step_pd @0x8450 / cassie_sim_step_ethercat @0x7ae0,
  * cassie/cassie.py:293-351 (step_simulation), :389-496 (step), :523-680 (reset), :787-859 (get_full_state),
- * cassie/rewards/clock_rewards.py:6-110, cassie/phase_function.py:5-136.
+ * cassie/rewards/clock_rewards.py:6-110, cassie/phase_function.py:5-136;
+ * cassie/cassie_traj.py:599-697 (reset), :926-972 (get_ref_state) for variant 1 (clock command, full input, no_delta=True:
+ * step / step_simulation / get_full_state then compute exactly what Cassie-v0's do, cassie_traj.py:345-570, 974-1050).
  */
+/* reference trajectory for CassieTraj-v0: rows k = 0..rows-1 hold (qpos[35], qvel[32]) of trajectory row k * simrate
+ * (cassie/trajectory/trajectory.py:8-19); len = number of rows of the full 2 kHz trajectory */
+template <typename T> struct CassieTraj { const T *table; int rows; int len; };
+#define CW_TRAJ_W (CM_NQ + CM_NV)
 #ifndef CASSIE_ENVSTEP_H
 #define CASSIE_ENVSTEP_H
 #include "cassie_warp.h"
@@ -236,7 +242,7 @@ template <typename T> CW_NOINL void cw_env_init(CassieWs<T> &w, uint32_t seed, u
     for (int k = lane; k < CM_NQ; k += 32) w.st[S_QPOS + k] = (T)CM_qpos_init[k];
     if (lane == 0) {
       w.st[S_FRICTION] = 1; w.st[S_FLOORQ] = 1;
-      w.st[S_PHASELEN] = 32;
+      w.st[S_PHASELEN] = 32; w.sti[I_PHASEFLOOR] = 32;
       w.sti[I_SEED] = (int)seed; w.sti[I_ENVID] = (int)env_id; w.sti[I_DYNRAND] = dyn_rand;
     }
   }
@@ -258,25 +264,39 @@ CW_FN uint32_t cw_draw(uint32_t seed, uint32_t env, uint32_t ctr0, int k) {
 }
 template <typename T> CW_FN T cw_uniform(uint32_t u, double lo, double hi) { return (T)lo + ((T)hi - (T)lo) * cw_u01<T>(u); }
 
-template <typename T> CW_FN void cw_set_clock(CassieWs<T> &w, T speed CW_LANE_PARAM) { /* cassie.py:556-559 */
-  const T as = cw_abs(speed);
-  const T total = ((T)0.9 - (T)0.25 / (T)3.0 * as) / 2;
-  const T swing = ((T)0.30 + (((T)0.70 - (T)0.30) / 3) * as) * total;
-  const T stance = ((T)0.70 - (((T)0.70 - (T)0.30) / 3) * as) * total;
-  T x[8], P;
-  cw_clock_knots<T>(swing, stance, x, &P);
-  CW_FOR_LANES { if (lane == 0) { w.st[S_SWING] = swing; w.st[S_STANCE] = stance; w.st[S_PHASELEN] = P; } }
+/* swing / stance durations and the clock period from the commanded speed (cassie.py:556-559, phase_function.py:7-8), in float64
+ * with the reference's operation order whatever T is: for CassieTraj-v0's discrete speeds the period lands on (or one ulp
+ * below) an integer, and floor(phaselen) is used as an integer twice (phase draw :561, phase wrap :450) */
+CW_FN void cw_clock_from_speed(double speed, double *swing, double *stance, double *phaselen) {
+  const double as = speed < 0 ? -speed : speed;
+  const double total = cw_dadd(0.9, -cw_dmul(0.25 / 3.0, as)) / 2;
+  const double k = (0.70 - 0.30) / 3;
+  *swing = cw_dmul(cw_dadd(0.30, cw_dmul(k, as)), total);
+  *stance = cw_dmul(cw_dadd(0.70, -cw_dmul(k, as)), total);
+  *phaselen = cw_dmul(cw_dadd(cw_dmul(2, *swing), cw_dmul(2, *stance)), 40.0); /* FREQ = 2000 // simrate */
+}
+template <typename T> CW_FN void cw_set_clock(CassieWs<T> &w, T speed CW_LANE_PARAM) {
+  double swing, stance, P;
+  cw_clock_from_speed((double)speed, &swing, &stance, &P);
+  CW_FOR_LANES {
+    if (lane == 0) {
+      w.st[S_SWING] = (T)swing; w.st[S_STANCE] = (T)stance; w.st[S_PHASELEN] = (T)P;
+      w.sti[I_PHASEFLOOR] = (int)floor(P);
+    }
+  }
   CW_SYNC();
 }
 
-/* ---------- CassieEnv.reset ---------- */
-template <typename T> CW_NOINL void cw_env_reset(CassieWs<T> &w, T *obs_out CW_LANE_PARAM) {
+/* ---------- CassieEnv.reset / CassieTrajEnv.reset ---------- */
+template <typename T> CW_NOINL void cw_env_reset(CassieWs<T> &w, T *obs_out, const CassieTraj<T> &traj CW_LANE_PARAM) {
   const uint32_t seed = (uint32_t)w.sti[I_SEED], env = (uint32_t)w.sti[I_ENVID], ctr0 = (uint32_t)w.sti[I_RNGCTR];
-  const int dyn = w.sti[I_DYNRAND];
-  const T speed0 = cw_uniform<T>(cw_draw(seed, env, ctr0, 0), -0.3, 4.0);
+  const int dyn = w.sti[I_DYNRAND], variant = w.sti[I_VARIANT];
+  /* Cassie-v0: speed ~ U[-0.3, 4] (cassie.py:525); CassieTraj-v0: random.randint(0, 40) / 10 (cassie_traj.py:608) */
+  const T speed0 = variant == 0 ? cw_uniform<T>(cw_draw(seed, env, ctr0, 0), -0.3, 4.0)
+                                : (T)(uint32_t)(((uint64_t)cw_draw(seed, env, ctr0, 0) * 41u) >> 32) / (T)10;
   cw_set_clock<T>(w, speed0 CW_LANE_ARG);
   const T plen = w.st[S_PHASELEN];
-  const uint32_t nph = (uint32_t)floor((double)plen) + 1u;
+  const uint32_t nph = (uint32_t)w.sti[I_PHASEFLOOR] + 1u;
   const T phase = (T)(uint32_t)(((uint64_t)cw_draw(seed, env, ctr0, 2) * nph) >> 32);
   int nd = 3;
   if (dyn) {
@@ -319,6 +339,19 @@ template <typename T> CW_NOINL void cw_env_reset(CassieWs<T> &w, T *obs_out CW_L
   }
   CW_SYNC();
   cw_mj_step<T>(w, false, 0 CW_LANE_ARG);
+  if (variant == 1 && traj.table) {
+    /* set_qpos / set_qvel from get_ref_state(phase) (cassie_traj.py:681-689, 926-972): written straight into the state with
+     * no mj_forward, so the sub-step below still reads the encoders of the fixed start pose */
+    int ph = (int)phase;
+    if (ph > traj.len / CW_SIMRATE - 1) ph = (int)floor((double)((phase / plen) * (T)traj.len / (T)CW_SIMRATE));
+    if (ph > traj.rows - 1) ph = traj.rows - 1;
+    const T *row = traj.table + (size_t)ph * CW_TRAJ_W;
+    CW_FOR_LANES {
+      for (int k = lane; k < CM_NQ; k += 32) w.st[S_QPOS + k] = k == 0 ? row[0] * speed0 : (k == 1 ? (T)0 : row[k]);
+      w.st[S_QVEL + lane] = lane == 0 ? row[CM_NQ] * speed0 : row[CM_NQ + lane];
+    }
+    CW_SYNC();
+  }
   CW_FOR_LANES { if (lane < 3) w.st[S_LASTPELVIS + lane] = w.st[S_QPOS + lane]; }
   /* one sub-step with the previous episode's pd_in_t (cassie.py:664-665) */
   cw_sim_step_pd<T>(w CW_LANE_ARG);
@@ -382,7 +415,7 @@ template <typename T> CW_NOINL void cw_env_step(CassieWs<T> &w, T *obs_out, T *r
   T phase = w.st[S_PHASE] + (T)1;
   const T plen = w.st[S_PHASELEN];
   int wrapped = 0;
-  if (phase > plen) { phase = 0; counter++; wrapped = 1; }
+  if ((int)phase > w.sti[I_PHASEFLOOR]) { phase = 0; counter++; wrapped = 1; } /* phase > phaselen for an integer phase */
   int done = (height < (T)0.4 || height > (T)3.0) ? 1 : 0;
   const int hasprev = w.sti[I_HASPREV];
   /* clock_reward */

@@ -78,7 +78,7 @@ enum {
 enum {
   I_DRIVEHIST = 0, I_TIME = 90, I_COUNTER = 91, I_HASPREV = 92, I_HASU = 93, I_DRIVEINIT = 94, I_JOINTINIT = 95,
   I_FLAGS = 96, I_STEPCOUNT = 97, I_RNGCTR = 98, I_ENVID = 99, I_SEED = 100, I_DYNRAND = 101, I_SOLVER_ITER = 102,
-  I_NCON = 103, I_NEFC = 104, I_WORDS = 112
+  I_NCON = 103, I_NEFC = 104, I_VARIANT = 105 /* 0 Cassie-v0, 1 CassieTraj-v0 */, I_PHASEFLOOR = 106 /* floor(phaselen), from float64 */, I_WORDS = 112
 };
 /* state_out slice (workspace only) */
 enum { Y_PPOS = 0, Y_QUAT = 3, Y_ROTVEL = 7, Y_TVEL = 10, Y_TACC = 13, Y_MPOS = 16, Y_MVEL = 26, Y_MTORQUE = 36, Y_JPOS = 46, Y_JVEL = 52, Y_WORDS = 58 };
@@ -138,6 +138,15 @@ CW_FN int cw_ctz(unsigned m) { return __ffs((int)m) - 1; }
 CW_FN int cw_ctz(unsigned m) { return __builtin_ctz(m); }
 CW_FN float cw_rcp(float x) { return 1.0f / x; }
 CW_FN double cw_rcp(double x) { return 1.0 / x; }
+#endif
+/* float64 arithmetic that the compiler may not contract into FMAs: the clock period must round exactly like the reference's
+ * Python floats, because floor(phaselen) decides integers (the phase draw, the phase wrap) */
+#ifdef __CUDA_ARCH__
+CW_FN double cw_dmul(double a, double b) { return __dmul_rn(a, b); }
+CW_FN double cw_dadd(double a, double b) { return __dadd_rn(a, b); }
+#else
+CW_FN double cw_dmul(double a, double b) { volatile double r = a * b; return r; }
+CW_FN double cw_dadd(double a, double b) { volatile double r = a + b; return r; }
 #endif
 template <typename T> CW_FN T cw_sqrt(T x) { return cw_sqrt_o(x); }
 template <typename T> CW_FN void cw_sincos(T x, T *s, T *c) { cw_sincos_o(x, s, c); }

@@ -48,9 +48,12 @@ class BatchedCassieEnv:
         self.term_obs = torch.zeros((n, 50), dtype=dtype, device=self.device)
         self.rew = torch.zeros((n,), dtype=dtype, device=self.device)
         self.done = torch.zeros((n,), dtype=torch.int32, device=self.device)
+        self._init_state(int(seed) & 0xFFFFFFFF, int(env_id0))
+
+    def _init_state(self, seed, env_id0):
         with torch.cuda.device(self.device):
-            _lib.check(self.L.apex_cassie_env_init(self.dt, self.st.data_ptr(), self.sti.data_ptr(), n, int(seed) & 0xFFFFFFFF,
-                                                   int(env_id0), int(self.dynamics_randomization), self._stream()), "env_init")
+            _lib.check(self.L.apex_cassie_env_init(self.dt, self.st.data_ptr(), self.sti.data_ptr(), self.num_envs, seed, env_id0,
+                                                   int(self.dynamics_randomization), self._stream()), "env_init")
 
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream
@@ -59,7 +62,7 @@ class BatchedCassieEnv:
         """View of a named field of the persistent state (tests, command overrides)."""
         off = _lib.layout(name)
         ints = name in ("drive_hist", "time", "counter", "has_prev", "has_u", "drive_init", "joint_init", "flags", "stepcount",
-                        "rng_ctr", "env_id", "seed", "dyn_rand", "solver_iter", "ncon", "nefc")
+                        "rng_ctr", "env_id", "seed", "dyn_rand", "solver_iter", "ncon", "nefc", "variant")
         return (self.sti if ints else self.st)[:, off:off + width]
 
     def reset(self):
@@ -92,3 +95,59 @@ class BatchedCassieEnv:
         for name, val in (("speed", speed), ("side_speed", side_speed), ("phase", phase)):
             if val is not None:
                 self.field(name)[:, 0] = torch.as_tensor(val, dtype=self.dtype, device=self.device)
+
+
+def load_trajectory(path, simrate=50):
+    """cassie/trajectory/trajectory.py:8-19 (CassieTrajectory): a headerless float64 file of rows
+    [time 1 | qpos 35 | qvel 32 | torque 10 | mpos 10 | mvel 10] recorded at 2 kHz (cassie/trajectory/stepdata.bin).
+    Returns (rows [len // simrate + 1, 67] float64 = (qpos, qvel) of every simrate-th row, len): the rows a reset can reach
+    (get_ref_state indexes row phase * simrate, cassie_traj.py:926-945)."""
+    data = np.fromfile(path, dtype=np.double).reshape((-1, 1 + 35 + 32 + 10 + 10 + 10))
+    return np.ascontiguousarray(np.concatenate([data[::simrate, 1:36], data[::simrate, 36:68]], axis=1)), data.shape[0]
+
+
+class BatchedCassieTrajEnv(BatchedCassieEnv):
+    """Batched CassieTraj-v0 (cassie/cassie_traj.py:27 as util/env.py:26 builds it: traj="walking", clock command, full input,
+    no_delta=True, clock reward).  With these settings step / step_simulation / get_full_state compute what Cassie-v0's do
+    (cassie_traj.py:345-570, 974-1050: the reference pose is fetched but only used when no_delta=False or for the
+    trajectory-matching rewards); reset() differs (cassie_traj.py:599-697): speed = randint(0, 40) / 10 builds the clock and
+    the episode starts from row phase * simrate of the reference trajectory.
+
+    trajectory: path of a CassieTrajectory file (e.g. the reference's cassie/trajectory/stepdata.bin), or a
+    (rows [K, 67], full_length) pair as returned by load_trajectory."""
+
+    def __init__(self, num_envs, trajectory, traj="walking", no_delta=True, ik_baseline=False, **kwargs):
+        if traj != "walking" or not no_delta or ik_baseline:
+            raise NotImplementedError("kernel covers traj='walking', no_delta=True, ik_baseline=False")
+        rows, length = load_trajectory(trajectory, kwargs.get("simrate", 50)) if isinstance(trajectory, (str, bytes)) else trajectory
+        if rows.shape[1] != 67 or rows.shape[0] < length // 50 + 1:
+            raise ValueError("trajectory table must be [len // simrate + 1, 67]")
+        self._traj_len = int(length)
+        super().__init__(num_envs, **kwargs)
+        self.traj_rows = torch.as_tensor(np.asarray(rows), dtype=self.dtype, device=self.device).contiguous()
+        self.phase_based = False
+
+    def _init_state(self, seed, env_id0):
+        with torch.cuda.device(self.device):
+            _lib.check(self.L.apex_cassietraj_env_init(self.dt, self.st.data_ptr(), self.sti.data_ptr(), self.num_envs, seed, env_id0,
+                                                       int(self.dynamics_randomization), self._stream()), "traj_env_init")
+
+    def reset(self):
+        with torch.cuda.device(self.device):
+            _lib.check(self.L.apex_cassietraj_env_reset(self.dt, self.st.data_ptr(), self.sti.data_ptr(), self.num_envs,
+                                                        self.obs.data_ptr(), self.traj_rows.data_ptr(), self.traj_rows.shape[0],
+                                                        self._traj_len, self._stream()), "traj_env_reset")
+        return self.obs
+
+    def step(self, action, f_term=0, rew_out=None, done_out=None, active=None):
+        a = action.to(device=self.device, dtype=self.dtype).contiguous()
+        assert a.shape == (self.num_envs, 10)
+        rew = self.rew if rew_out is None else rew_out
+        done = self.done if done_out is None else done_out
+        with torch.cuda.device(self.device):
+            _lib.check(self.L.apex_cassietraj_env_step(self.dt, self.st.data_ptr(), self.sti.data_ptr(), self.num_envs, a.data_ptr(),
+                                                       self.obs.data_ptr(), rew.data_ptr(), done.data_ptr(), self.term_obs.data_ptr(),
+                                                       self.max_traj_len, None if active is None else active.data_ptr(),
+                                                       self.traj_rows.data_ptr(), self.traj_rows.shape[0], self._traj_len,
+                                                       self._stream()), "traj_env_step")
+        return self.obs, rew, done, {}

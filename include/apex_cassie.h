@@ -43,6 +43,19 @@ int apex_cassie_env_step(int dtype, void *st, int *sti, int n, const void *actio
  * ARS, where every env runs exactly one episode (rl/algos/ars.py:185-201 eval_fn) */
 int apex_cassie_env_step_masked(int dtype, void *st, int *sti, int n, const void *action, void *obs, void *reward, int *done,
                                 void *term_obs, int max_traj_len, const int *active, void *stream);
+/* ---- CassieTraj-v0 (cassie/cassie_traj.py:27, util/env.py:26; clock command, full input, no_delta=True, clock reward) ----
+ * Same record layout, dynamics randomisation and step arithmetic as Cassie-v0; reset differs (cassie_traj.py:599-697): speed =
+ * randint(0,40)/10 sets the clock and the episode starts from row phase * simrate of the reference trajectory (x and vx
+ * scaled by that speed, y = 0; get_ref_state, :926-972).
+ * traj: DEVICE table [traj_rows][67] (qpos 35, qvel 32) in `dtype`, row k = row k * 50 of the 2 kHz trajectory
+ * (cassie/trajectory/trajectory.py:8-19); traj_len = rows of the full trajectory (1682 for stepdata.bin);
+ * traj_rows must be >= traj_len / 50 + 1.  active may be NULL. */
+int apex_cassietraj_env_init(int dtype, void *st, int *sti, int n, unsigned seed, int env_id0, int dyn_rand, void *stream);
+int apex_cassietraj_env_reset(int dtype, void *st, int *sti, int n, void *obs, const void *traj, int traj_rows, int traj_len,
+                              void *stream);
+int apex_cassietraj_env_step(int dtype, void *st, int *sti, int n, const void *action, void *obs, void *reward, int *done,
+                             void *term_obs, int max_traj_len, const int *active, const void *traj, int traj_rows, int traj_len,
+                             void *stream);
 /* tuning: environments (warps) per CTA of the step kernel, 1..14 (default 7 = two CTAs of 7 envs per SM; float64 is capped at 7) */
 void apex_cassie_set_warps_per_cta(int w);
 /* one raw mj_step (no wrapper, no env logic) on the stored state with S_CTRL as control; test hook */

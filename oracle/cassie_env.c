@@ -118,7 +118,10 @@ void ce_sim_step_pd(ce_env_t *e, const ce_pd_in_t *u, ce_state_out_t *y) {
 /* ---------- clock functions (cassie/phase_function.py:5-136) ----------
  * Every knot of the 24-knot PCHIP borders a flat segment, so every PCHIP node derivative is zero and each
  * segment is the cubic Hermite y0 + (y1-y0) t^2 (3-2t); tests/ check this against scipy.PchipInterpolator. */
-void ce_clock_knots(double swing, double stance, double x[8], double *phaselen) {
+/* NOFMA: the period must round exactly like the reference's Python floats (floor(phaselen) decides the phase draw and the
+ * phase wrap, and CassieTraj-v0's discrete speeds put it on or one ulp below an integer), so gcc may not contract a*b+c here */
+#define NOFMA __attribute__((optimize("fp-contract=off")))
+NOFMA void ce_clock_knots(double swing, double stance, double x[8], double *phaselen) {
   const double F = 40.0, rel = 0.1; /* FREQ = 2000 // simrate, strict_relaxer (cassie.py:90,559) */
   double seg[5] = {0, swing, swing + stance, 2 * swing + stance, 2 * swing + 2 * stance};
   for (int k = 0; k < 4; k++) {
@@ -156,14 +159,17 @@ void ce_env_init(ce_env_t *e, uint32_t seed, uint32_t env_id, int dyn_rand) {
   e->phaselen = 32; e->phase_add = 1;
 }
 
+void ce_clock_from_speed(double speed, double *swing, double *stance, double *phaselen);
 static void set_clock(ce_env_t *e, double speed) { /* cassie.py:556-559 */
-  double total = (0.9 - 0.25 / 3.0 * fabs(speed)) / 2;
-  e->swing_duration = (0.30 + ((0.70 - 0.30) / 3) * fabs(speed)) * total;
-  e->stance_duration = (0.70 - ((0.70 - 0.30) / 3) * fabs(speed)) * total;
-  double x[8];
-  ce_clock_knots(e->swing_duration, e->stance_duration, x, &e->phaselen);
+  ce_clock_from_speed(speed, &e->swing_duration, &e->stance_duration, &e->phaselen);
 }
-
+NOFMA void ce_clock_from_speed(double speed, double *swing, double *stance, double *phaselen) {
+  double total = (0.9 - 0.25 / 3.0 * fabs(speed)) / 2;
+  *swing = (0.30 + ((0.70 - 0.30) / 3) * fabs(speed)) * total;
+  *stance = (0.70 - ((0.70 - 0.30) / 3) * fabs(speed)) * total;
+  double x[8];
+  ce_clock_knots(*swing, *stance, x, phaselen);
+}
 static void yaw_quat_inv(double orient_add, double iq[4]) { /* euler2quat(z=orient_add) then inverse (cassie.py:281-282) */
   double cz = cos(orient_add / 2), sz = sin(orient_add / 2);
   double q[4] = {cz, 0, 0, sz};
@@ -334,6 +340,12 @@ void ce_env_step(ce_env_t *e, const double *action, double *obs, double *reward,
   ce_env_step_with(e, action, &dr, obs, reward, done);
 }
 
+void ce_env_set_trajectory(ce_env_t *e, const double *table, int rows, int len) {
+  e->variant = 1; e->traj = table; e->traj_rows = rows; e->traj_len = len;
+}
+void ce_batch_set_trajectory(ce_env_t *envs, int n, const double *table, int rows, int len) {
+  for (int i = 0; i < n; i++) ce_env_set_trajectory(&envs[i], table, rows, len);
+}
 void ce_env_set_command(ce_env_t *e, double speed, double side_speed, double phase) {
   e->speed = speed; e->side_speed = side_speed; e->phase = phase;
 }
@@ -342,7 +354,8 @@ void ce_env_set_command(ce_env_t *e, double speed, double side_speed, double pha
  * and 75 centre-of-mass values from zero-width intervals, cassie.py:609-613: no effect, not drawn here) */
 static void draw_reset(ce_env_t *e, ce_reset_draws_t *dr) {
   rng_t r = {e, {0, 0, 0, 0}, 0};
-  dr->speed0 = rng_uniform(&r, -0.3, 4.0);
+  if (e->variant == 1) dr->speed0 = (double)rng_randint(&r, 41) / 10; /* random.randint(0, 40) / 10, cassie_traj.py:608 */
+  else dr->speed0 = rng_uniform(&r, -0.3, 4.0);
   dr->side_speed0 = rng_uniform(&r, -0.3, 0.3);
   dr->phase_u32 = rng_u32(&r);
   if (e->dyn_rand) {
@@ -388,6 +401,21 @@ void ce_env_reset_with(ce_env_t *e, const ce_reset_draws_t *dr, double *obs) { /
   } /* else: the model keeps the defaults installed by ce_env_init (set_const would reproduce the same numbers) */
   if (e->dyn_rand) cp_set_const(&e->m);
   cp_data_reset(&e->m, &e->d);
+  if (e->variant == 1 && e->traj) {
+    /* qpos, qvel = get_ref_state(phase); sim.set_qpos / set_qvel (cassie_traj.py:681-689, 926-972): plain stores into
+     * mjData, no mj_forward — the sub-step below still reads the sensor values of the fixed start pose */
+    const int simrate = 50;
+    double phase = e->phase; /* self.speed is still the randint / 10 draw, self.counter is 0 */
+    if (phase > e->traj_len / simrate - 1) phase = floor((phase / e->phaselen) * e->traj_len / simrate);
+    int k = (int)phase;
+    if (k > e->traj_rows - 1) k = e->traj_rows - 1;
+    const double *row = e->traj + (size_t)k * (CM_NQ + CM_NV);
+    memcpy(e->d.qpos, row, sizeof(e->d.qpos));
+    memcpy(e->d.qvel, row + CM_NQ, sizeof(e->d.qvel));
+    e->d.qpos[0] *= e->speed;
+    e->d.qpos[1] = 0;
+    e->d.qvel[0] *= e->speed;
+  }
   memcpy(e->last_pelvis_pos, e->d.qpos, sizeof(e->last_pelvis_pos));
   ce_sim_step_pd(e, &e->u, &e->y); /* one sub-step with the previous episode's pd_in_t (cassie.py:664-665) */
   e->orient_add = 0;

@@ -49,6 +49,11 @@ typedef struct {
   double l_foot_frc, r_foot_frc, l_foot_pos[3], r_foot_pos[3], l_foot_orient_cost, r_foot_orient_cost, hiproll_cost, hiproll_act;
   uint32_t seed, env_id, rng_ctr;
   int dyn_rand;
+  /* CassieTraj-v0 (cassie/cassie_traj.py): variant 1 starts episodes from the reference trajectory.  traj is a borrowed
+   * [traj_rows][67] table (qpos 35, qvel 32), row k = row k * simrate of the 2 kHz file; traj_len = rows of the full file */
+  int variant;
+  const double *traj;
+  int traj_rows, traj_len;
 } ce_env_t;
 
 /* The random draws of one reset / one step (cassie.py:523-680, :483-491).  ce_env_reset / ce_env_step fill them from the
@@ -76,9 +81,12 @@ void ce_philox(uint32_t seed, uint32_t env_id, uint32_t ctr, uint32_t out[4]);
 void ce_sim_init(ce_env_t *e);                                        /* cassie_sim_init */
 void ce_sim_step_pd(ce_env_t *e, const ce_pd_in_t *u, ce_state_out_t *y); /* cassie_sim_step_pd */
 void ce_clock_knots(double swing, double stance, double x[8], double *phaselen);
+void ce_clock_from_speed(double speed, double *swing, double *stance, double *phaselen); /* cassie.py:556-559 */
 double ce_clock_eval(double swing, double stance, int which, double phase); /* which: 0 r_frc 1 r_vel 2 l_frc 3 l_vel */
 void ce_env_init(ce_env_t *e, uint32_t seed, uint32_t env_id, int dyn_rand);
 void ce_env_reset(ce_env_t *e, double *obs);
+void ce_env_set_trajectory(ce_env_t *e, const double *table, int rows, int len); /* switches the env to CassieTraj-v0 */
+void ce_batch_set_trajectory(ce_env_t *envs, int n, const double *table, int rows, int len);
 void ce_env_set_command(ce_env_t *e, double speed, double side_speed, double phase); /* synthetic-input hook */
 void ce_env_step(ce_env_t *e, const double *action, double *obs, double *reward, int *done);
 void ce_env_obs(ce_env_t *e, double *obs);

@@ -15,27 +15,30 @@ template <typename T> static void store(const CassieWs<T> &w, T *st, int *sti) {
 }
 
 #define DEFINE(T, SUF)                                                                                              \
-  extern "C" void emu_init_##SUF(T *st, int *sti, int n, unsigned seed, int dyn) {                                  \
+  extern "C" void emu_init_##SUF(T *st, int *sti, int n, unsigned seed, int dyn, int variant) {                     \
     CassieWs<T> *w = new CassieWs<T>();                                                                             \
     for (int e = 0; e < n; e++) {                                                                                   \
       memset(w, 0, sizeof(*w));                                                                                     \
       cw_env_init<T>(*w, seed, (unsigned)e, dyn);                                                                   \
+      w->sti[I_VARIANT] = variant;                                                                                  \
       store(*w, st + (size_t)e * S_WORDS, sti + (size_t)e * I_WORDS);                                               \
     }                                                                                                               \
     delete w;                                                                                                       \
   }                                                                                                                 \
-  extern "C" void emu_reset_##SUF(T *st, int *sti, int n, T *obs) {                                                 \
+  extern "C" void emu_reset_##SUF(T *st, int *sti, int n, T *obs, const T *traj, int traj_rows, int traj_len) {     \
+    const CassieTraj<T> tr = {traj, traj_rows, traj_len};                                                           \
     CassieWs<T> *w = new CassieWs<T>();                                                                             \
     for (int e = 0; e < n; e++) {                                                                                   \
       memset(w, 0, sizeof(*w));                                                                                     \
       load(*w, st + (size_t)e * S_WORDS, sti + (size_t)e * I_WORDS);                                                \
-      cw_env_reset<T>(*w, obs + (size_t)e * CW_OBS);                                                                \
+      cw_env_reset<T>(*w, obs + (size_t)e * CW_OBS, tr);                                                            \
       store(*w, st + (size_t)e * S_WORDS, sti + (size_t)e * I_WORDS);                                               \
     }                                                                                                               \
     delete w;                                                                                                       \
   }                                                                                                                 \
   extern "C" void emu_step_##SUF(T *st, int *sti, int n, const T *act, T *obs, T *rew, int *done, T *term_obs,      \
-                                 int max_traj_len) {                                                                \
+                                 int max_traj_len, const T *traj, int traj_rows, int traj_len) {                    \
+    const CassieTraj<T> tr = {traj, traj_rows, traj_len};                                                           \
     CassieWs<T> *w = new CassieWs<T>();                                                                             \
     for (int e = 0; e < n; e++) {                                                                                   \
       memset(w, 0, sizeof(*w));                                                                                     \
@@ -48,7 +51,7 @@ template <typename T> static void store(const CassieWs<T> &w, T *st, int *sti) {
       done[e] = flag;                                                                                               \
       if (flag && max_traj_len > 0) {                                                                               \
         if (term_obs) memcpy(term_obs + (size_t)e * CW_OBS, obs + (size_t)e * CW_OBS, sizeof(T) * CW_OBS);          \
-        cw_env_reset<T>(*w, obs + (size_t)e * CW_OBS);                                                              \
+        cw_env_reset<T>(*w, obs + (size_t)e * CW_OBS, tr);                                                          \
       }                                                                                                             \
       store(*w, st + (size_t)e * S_WORDS, sti + (size_t)e * I_WORDS);                                               \
     }                                                                                                               \
@@ -85,6 +88,7 @@ template <typename T> static void store(const CassieWs<T> &w, T *st, int *sti) {
 DEFINE(double, f64)
 DEFINE(float, f32)
 
+extern "C" void emu_clock_from_speed(double speed, double *out) { cw_clock_from_speed(speed, out, out + 1, out + 2); }
 extern "C" int emu_state_words(void) { return S_WORDS; }
 extern "C" int emu_istate_words(void) { return I_WORDS; }
 extern "C" int emu_ws_bytes(int f64) { return f64 ? (int)sizeof(CassieWs<double>) : (int)sizeof(CassieWs<float>); }

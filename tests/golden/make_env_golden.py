@@ -83,15 +83,20 @@ class DrawLog:
         np.random.uniform, np.random.randint, random.randint = self._u, self._ri, self._pri
 
 
-def parse_reset(calls, dyn):
-    """cassie.py:523-680 draw order -> the fields of ce_reset_draws_t (oracle/cassie_env.h)."""
+def parse_reset(calls, dyn, traj=False):
+    """cassie.py:523-680 / cassie_traj.py:599-697 draw order -> the fields of ce_reset_draws_t (oracle/cassie_env.h)."""
     it = iter(calls)
 
     def u(lo=None, hi=None):
         k, a, b, v = next(it)
         assert k == "u" and (lo is None or (abs(a - lo) < 1e-12 and abs(b - hi) < 1e-12)), (k, a, b, lo, hi)
         return v
-    d = {"speed0": u(-0.3, 4.0), "side_speed0": u(-0.3, 0.3)}
+    if traj:  # cassie_traj.py:608: speed = random.randint(0, 40) / 10
+        k, a, b, v = next(it)
+        assert k == "pri" and (a, b) == (0, 40)
+        d = {"speed0": v / 10, "side_speed0": u(-0.3, 0.3)}
+    else:
+        d = {"speed0": u(-0.3, 4.0), "side_speed0": u(-0.3, 0.3)}
     k, a, b, v = next(it)
     assert k == "pri" and a == 0
     d["phase"], d["phase_hi"] = v, b
@@ -130,7 +135,7 @@ def parse_step(calls, dyn):
     return hit, val
 
 
-def record(env, dyn, n_episodes, steps_per_episode, rng, hit_boost):
+def record(env, dyn, n_episodes, steps_per_episode, rng, hit_boost, traj=False):
     """hit_boost: replace the 1/300, 1/100, 1/300 triggers' results by frequent hits so the command changes are exercised."""
     out = {k: [] for k in ("reset_scalar", "reset_damping", "reset_mass", "reset_friction", "reset_tilt", "reset_menc",
                            "reset_jenc", "reset_obs", "reset_qpos", "reset_qvel", "action", "obs", "reward", "done", "qpos",
@@ -138,7 +143,7 @@ def record(env, dyn, n_episodes, steps_per_episode, rng, hit_boost):
     for ep in range(n_episodes):
         with DrawLog() as log:
             obs = env.reset()
-        d = parse_reset(log.calls, dyn)
+        d = parse_reset(log.calls, dyn, traj)
         out["reset_scalar"].append([d["speed0"], d["side_speed0"], d["phase"], d["phase_hi"], d["speed1"], d["side_speed1"]])
         out["reset_damping"].append(d["damping"]); out["reset_mass"].append(d["mass"]); out["reset_friction"].append(d["friction"])
         out["reset_tilt"].append([d["roll"], d["pitch"]]); out["reset_menc"].append(d["menc_noise"]); out["reset_jenc"].append(d["jenc_noise"])
@@ -192,6 +197,24 @@ def main():
         res["mirrored_obs"] = np.array(env.mirrored_obs, dtype=np.float64)
         res["mirrored_acts"] = np.array(env.mirrored_acts, dtype=np.float64)
         res["clock_inds"] = np.array(env.clock_inds)
+        # CassieTraj-v0 as util/env.py:26 builds it (traj="walking", clock command, full input, no_delta=True)
+        from cassie.cassie_traj import CassieTrajEnv
+        for tag, dyn in (("traj_plain", False), ("traj_dynrand", True)):
+            np.random.seed(4321 + dyn)
+            random.seed(77 + dyn)
+            rng = np.random.default_rng(17 + dyn)
+            env = CassieTrajEnv(traj="walking", simrate=50, command_profile="clock", input_profile="full", dynamics_randomization=dyn,
+                                no_delta=True, reward="clock")
+            assert env.observation_space.shape[0] == 50 and env.action_space.shape[0] == 10
+            r = record(env, dyn, n_episodes=5, steps_per_episode=10, rng=rng, hit_boost=True, traj=True)
+            for k, v in r.items():
+                res[f"{tag}.{k}"] = v
+            print(tag, "episode lengths", r["ep_len"], "done flags", int(r["done"].sum()), "phases", r["reset_scalar"][:, 2], "speeds", r["reset_scalar"][:, 0])
+        # the rows of the reference trajectory a reset can reach: row k * simrate, k = 0 .. len // simrate (trajectory.py:8-19)
+        tr = env.trajectory
+        rows = np.concatenate([tr.qpos[::50], tr.qvel[::50]], axis=1)
+        np.savez_compressed(os.path.join(HERE, "traj_walking_rows.npz"), rows=rows, traj_len=np.array(len(tr)), simrate=np.array(50))
+        print("trajectory rows", rows.shape, "of", len(tr))
         np.savez_compressed(os.path.join(HERE, "env_episodes.npz"), **res)
     finally:
         os.chdir(cwd)

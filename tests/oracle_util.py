@@ -13,11 +13,14 @@ def dp(a):
 class OracleBatch:
     """N oracle environments (oracle/cassie_env.c) stepped on the host."""
 
-    def __init__(self, n, seed, dyn_rand, threads=8):
+    def __init__(self, n, seed, dyn_rand, threads=8, trajectory=None):
         self.L = P.lib()
         self.n, self.threads = n, threads
         self.buf = (C.c_char * (self.L.ce_sizeof_env() * n))()
         self.L.ce_batch_init(self.buf, n, C.c_uint(seed), int(dyn_rand), threads)
+        if trajectory is not None:  # CassieTraj-v0
+            self.table, tlen = trajectory
+            self.L.ce_batch_set_trajectory(self.buf, n, dp(self.table), self.table.shape[0], int(tlen))
         self.obs = np.zeros((n, 50))
         self.rew = np.zeros(n)
         self.done = np.zeros(n, dtype=np.int32)
@@ -48,10 +51,13 @@ class StepDraws(C.Structure):  # ce_step_draws_t
 class OracleEnv:
     """One oracle environment driven with injected draws (replay of episodes recorded from the reference's CassieEnv)."""
 
-    def __init__(self, dyn_rand):
+    def __init__(self, dyn_rand, trajectory=None):
         self.L = P.lib()
         self.buf = (C.c_char * self.L.ce_sizeof_env())()
         self.L.ce_env_init(self.buf, C.c_uint(0), C.c_uint(0), int(dyn_rand))
+        if trajectory is not None:  # CassieTraj-v0: (decimated table [rows, 67], rows of the full trajectory)
+            self.table, tlen = trajectory
+            self.L.ce_env_set_trajectory(self.buf, dp(self.table), self.table.shape[0], int(tlen))
         self.env = C.cast(self.buf, C.c_void_p)
         self.obs = np.zeros(50)
 

@@ -94,3 +94,37 @@ def test_env_roundtrip_properties_full_size():
         assert float((q[:, 3:7].norm(dim=1) - 1).abs().max()) < 1e-4
         assert float(((obs[:, 46] ** 2 + obs[:, 47] ** 2) - 1).abs().max()) < 1e-4
         assert float(rew.max()) <= 1.0001 and float(rew.min()) > -0.5
+
+
+def _traj_table():
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "traj_walking_rows.npz"))
+    return np.ascontiguousarray(g["rows"], dtype=np.float64), int(g["traj_len"])
+
+
+@pytest.mark.parametrize("dyn", [False, True])
+def test_trajenv_f64_matches_oracle(dyn):
+    """CassieTraj-v0 (cassie/cassie_traj.py): float64 kernel against the oracle, whose env layer is pinned to the reference's own
+    CassieTrajEnv (tests/test_oracle_cpu.py); episodes start from the reference trajectory (tests/golden/traj_walking_rows.npz),
+    time-limit resets every 8 steps exercise the in-kernel reset."""
+    from apex_b200.envs import BatchedCassieTrajEnv
+    n, seed = 24, 21
+    table = _traj_table()
+    env = BatchedCassieTrajEnv(n, table, dtype=torch.float64, seed=seed, dynamics_randomization=dyn, max_traj_len=8)
+    ora = OracleBatch(n, seed, dyn, trajectory=table)
+    og, oc = env.reset().cpu().numpy(), ora.reset().copy()
+    assert np.abs(og - oc).max() < 1e-10
+    # the episodes do not start from the fixed pose: the trajectory row was installed
+    assert np.abs(env.field("qpos", 35).cpu().numpy()[:, 7:] - np.array(table[0][0][7:35])).max() > 1e-3
+    rng = np.random.default_rng(5)
+    nreset = 0
+    for k in range(20):
+        act = rng.normal(size=(n, 10)) * 0.2
+        og, rg, dg, _ = env.step(torch.as_tensor(act, device=env.device))
+        oc, rc, dc = ora.step(act, max_traj_len=8)
+        assert (dg.cpu().numpy() == dc).all()
+        rel = np.linalg.norm(og.cpu().numpy() - oc, axis=1) / np.linalg.norm(oc, axis=1)
+        assert rel.max() < 1e-8, (k, rel.max())
+        assert np.abs(rg.cpu().numpy() - rc).max() < 1e-8
+        nreset += int((dc != 0).sum())
+    assert nreset >= 2 * n

@@ -29,7 +29,7 @@ def emu():
     src = os.path.join(ROOT, "tests", "emu", "cassie_emu.cpp")
     deps = [src] + [os.path.join(ROOT, "apex_b200", "csrc", f) for f in os.listdir(os.path.join(ROOT, "apex_b200", "csrc")) if f.endswith(".h")]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
-        subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-o", so, src])
+        subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-o", so, src])
     return C.CDLL(so)
 
 
@@ -138,27 +138,39 @@ def test_standing_contact_forces_support_weight(L):
 
 
 # ---------------------------------------------------------------- product kernel source (host build) vs the oracle
-def test_kernel_source_matches_oracle_f64(L, emu):
+def _traj_table():
+    """Decimated reference trajectory (tests/golden/make_env_golden.py): rows k * 50 of cassie/trajectory/stepdata.bin."""
+    g = np.load(os.path.join(G, "traj_walking_rows.npz"))
+    return np.ascontiguousarray(g["rows"], dtype=np.float64), int(g["traj_len"])
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_kernel_source_matches_oracle_f64(L, emu, variant):
     """The same C++ that nvcc compiles for the GPU, built for the host with a 32-iteration lane loop, must reproduce the
-    oracle: integers exactly (done flags, counters), floats to 1e-9, over resets and dynamics randomisation."""
+    oracle: integers exactly (done flags, counters), floats to 1e-9, over resets and dynamics randomisation.
+    variant 0 = Cassie-v0, 1 = CassieTraj-v0 (episodes start from the reference trajectory)."""
     SW, IW = emu.emu_state_words(), emu.emu_istate_words()
+    table, tlen = _traj_table() if variant else (None, 0)
+    tp, trows = (dp(table), table.shape[0]) if variant else (None, 0)
     for dyn in (0, 1):
         n = 4
         buf = (C.c_char * (L.ce_sizeof_env() * n))()
         L.ce_batch_init(buf, n, C.c_uint(77), dyn, 1)
+        if variant:
+            L.ce_batch_set_trajectory(buf, n, tp, trows, tlen)
         oobs, orew, odone, otobs = np.zeros((n, 50)), np.zeros(n), np.zeros(n, dtype=np.int32), np.zeros((n, 50))
         st, sti = np.zeros((n, SW)), np.zeros((n, IW), dtype=np.int32)
-        emu.emu_init_f64(dp(st), dp(sti), n, C.c_uint(77), dyn)
+        emu.emu_init_f64(dp(st), dp(sti), n, C.c_uint(77), dyn, variant)
         eobs, erew, edone, etobs = np.zeros((n, 50)), np.zeros(n), np.zeros(n, dtype=np.int32), np.zeros((n, 50))
         L.ce_batch_reset(buf, n, dp(oobs), 1)
-        emu.emu_reset_f64(dp(st), dp(sti), n, dp(eobs))
+        emu.emu_reset_f64(dp(st), dp(sti), n, dp(eobs), tp, trows, tlen)
         assert np.abs(oobs - eobs).max() < 1e-10
         rng = np.random.default_rng(0)
         ndone = 0
         for k in range(45):
             act = rng.normal(size=(n, 10)) * 0.3
             L.ce_batch_step(buf, n, dp(act), dp(oobs), dp(orew), dp(odone), 40, dp(otobs), 1)
-            emu.emu_step_f64(dp(st), dp(sti), n, dp(act), dp(eobs), dp(erew), dp(edone), dp(etobs), 40)
+            emu.emu_step_f64(dp(st), dp(sti), n, dp(act), dp(eobs), dp(erew), dp(edone), dp(etobs), 40, tp, trows, tlen)
             assert (odone == edone).all()
             assert np.abs(oobs - eobs).max() < 1e-9 and np.abs(orew - erew).max() < 1e-10
             ndone += int((odone != 0).sum())
@@ -169,16 +181,16 @@ def test_kernel_source_f32_close_to_f64(emu):
     SW, IW = emu.emu_state_words(), emu.emu_istate_words()
     n = 4
     st, sti = np.zeros((n, SW)), np.zeros((n, IW), dtype=np.int32)
-    emu.emu_init_f64(dp(st), dp(sti), n, C.c_uint(5), 0)
+    emu.emu_init_f64(dp(st), dp(sti), n, C.c_uint(5), 0, 0)
     obs, rew, done, tobs = np.zeros((n, 50)), np.zeros(n), np.zeros(n, dtype=np.int32), np.zeros((n, 50))
-    emu.emu_reset_f64(dp(st), dp(sti), n, dp(obs))
+    emu.emu_reset_f64(dp(st), dp(sti), n, dp(obs), None, 0, 0)
     rng = np.random.default_rng(0)
     for k in range(6):
         act = rng.normal(size=(n, 10)) * 0.3
         st32, sti32 = st.astype(np.float32), sti.copy()
         o32, r32, d32, t32 = np.zeros((n, 50), np.float32), np.zeros(n, np.float32), np.zeros(n, np.int32), np.zeros((n, 50), np.float32)
-        emu.emu_step_f32(dp(st32), dp(sti32), n, dp(act.astype(np.float32)), dp(o32), dp(r32), dp(d32), dp(t32), 0)
-        emu.emu_step_f64(dp(st), dp(sti), n, dp(act), dp(obs), dp(rew), dp(done), dp(tobs), 0)
+        emu.emu_step_f32(dp(st32), dp(sti32), n, dp(act.astype(np.float32)), dp(o32), dp(r32), dp(d32), dp(t32), 0, None, 0, 0)
+        emu.emu_step_f64(dp(st), dp(sti), n, dp(act), dp(obs), dp(rew), dp(done), dp(tobs), 0, None, 0, 0)
         q = np.linalg.norm(st32[:, :35] - st[:, :35], axis=1) / np.linalg.norm(st[:, :35], axis=1)
         assert q.max() < 1e-4 and np.median(q) < 1e-5
         assert np.abs(r32 - rew).max() < 5e-3
@@ -223,16 +235,18 @@ def test_missing_library_fails_loudly(monkeypatch):
         _capi.lib()
 
 
-@pytest.mark.parametrize("tag,dyn", [("plain", False), ("dynrand", True)])
-def test_env_layer_matches_the_reference_python(tag, dyn):
-    """Episodes recorded from the reference's own cassie/cassie.py + clock_rewards.py + phase_function.py running over
-    oracle/cassiemujoco_abi.c (tests/golden/make_env_golden.py) replayed through oracle/cassie_env.c with the reference's
-    random draws injected: reset / step / step_simulation / get_full_state / clock_reward.
-    Same physics code on both sides, so the env layer must agree to round-off."""
+@pytest.mark.parametrize("tag,dyn,traj", [("plain", False, False), ("dynrand", True, False), ("traj_plain", False, True),
+                                          ("traj_dynrand", True, True)])
+def test_env_layer_matches_the_reference_python(tag, dyn, traj):
+    """Episodes recorded from the reference's own cassie/cassie.py (CassieEnv) and cassie/cassie_traj.py (CassieTrajEnv) +
+    clock_rewards.py + phase_function.py running over oracle/cassiemujoco_abi.c (tests/golden/make_env_golden.py), replayed
+    through oracle/cassie_env.c with the reference's random draws injected: reset / step / step_simulation / get_full_state /
+    get_ref_state / clock_reward.  Same physics code on both sides, so the env layer must agree
+    to round-off."""
     from tests.oracle_util import OracleEnv
-    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "env_episodes.npz"))
+    g = np.load(os.path.join(G, "env_episodes.npz"))
     f = lambda k: g[f"{tag}.{k}"]
-    env = OracleEnv(dyn)
+    env = OracleEnv(dyn, trajectory=_traj_table() if traj else None)
     t = 0
     for ep, n in enumerate(f("ep_len")):
         obs = env.reset_with(f("reset_scalar")[ep], f("reset_damping")[ep], f("reset_mass")[ep], f("reset_friction")[ep],
@@ -278,3 +292,35 @@ def test_reference_abi_exports_all_103_symbols():
     lib = ctypes.CDLL(phys_ctypes.build())
     missing = [n for n in names if not hasattr(lib, n)]
     assert not missing, missing
+
+
+def test_clock_period_rounds_like_the_reference(L, emu):
+    """floor(phaselen) is used as an integer (phase draw cassie.py:561, phase wrap :450).  For CassieTraj-v0's discrete speeds
+    (randint(0, 40) / 10) the period lands on or one ulp below an integer, so the oracle and the kernel source must round
+    exactly like the reference's Python floats (cassie.py:556-559, phase_function.py:7-8 restated here)."""
+    L.ce_clock_from_speed.argtypes = [C.c_double] + [C.POINTER(C.c_double)] * 3
+    emu.emu_clock_from_speed.argtypes = [C.c_double, C.POINTER(C.c_double)]
+    speeds = [k / 10 for k in range(41)] + list(np.random.default_rng(0).uniform(-0.3, 4.0, 200))
+    n_int = 0
+    for v in speeds:
+        total_duration = (0.9 - 0.25 / 3.0 * abs(v)) / 2
+        swing = (0.30 + ((0.70 - 0.30) / 3) * abs(v)) * total_duration
+        stance = (0.70 - ((0.70 - 0.30) / 3) * abs(v)) * total_duration
+        phaselen = (2 * swing + 2 * stance) * 40
+        a, b, c = C.c_double(), C.c_double(), C.c_double()
+        L.ce_clock_from_speed(v, C.byref(a), C.byref(b), C.byref(c))
+        out = (C.c_double * 3)()
+        emu.emu_clock_from_speed(v, out)
+        assert (a.value, b.value, c.value) == (swing, stance, phaselen), v
+        assert tuple(out) == (swing, stance, phaselen), v
+        n_int += abs(phaselen - round(phaselen)) < 1e-9
+    assert n_int >= 3  # the edge case exists: several discrete speeds give (near-)integer periods
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/cassie/trajectory/stepdata.bin"), reason="reference tree not mounted")
+def test_trajectory_loader_reads_the_reference_file():
+    """apex_b200.envs.load_trajectory on the reference's own stepdata.bin gives the committed fixture (build container only)."""
+    from apex_b200.envs import load_trajectory
+    rows, n = load_trajectory("/root/reference/cassie/trajectory/stepdata.bin")
+    table, tlen = _traj_table()
+    assert n == tlen == 1682 and rows.shape == (34, 67) and np.array_equal(rows, table)
