@@ -35,6 +35,9 @@ def lib():
         L.apex_cassietraj_env_step.argtypes = [i, vp, ip, i, vp, vp, vp, ip, vp, i, vp, vp, i, i, vp]
         for f in (L.apex_cassietraj_env_init, L.apex_cassietraj_env_reset, L.apex_cassietraj_env_step):
             f.restype = i
+        L.apex_cassie_env_order.argtypes = [ip, i, ip, vp]
+        L.apex_cassie_env_step_ordered.argtypes = [i, vp, ip, i, vp, vp, vp, ip, vp, i, vp, vp, i, i, vp, vp]
+        L.apex_cassie_env_order.restype = L.apex_cassie_env_step_ordered.restype = i
         L.apex_cassie_set_warps_per_cta.argtypes = [i]
         L.apex_cassie_set_warps_per_cta.restype = None
         fl, lng = C.c_float, C.c_long

@@ -39,19 +39,23 @@ template <typename T> __global__ void __launch_bounds__(32) k_env_reset(T *st, i
 /* W warps (= W envs) per CTA; the CTA barrier inside cw_env_step's sub-step loop must be reached by every warp, so
  * warps past the end of the batch run the barriers only. */
 template <typename T>
-__global__ void k_env_step(T *st, int *sti, int n, const T *action, T *obs, T *reward, int *done, T *term_obs, int max_traj_len,
-                           const int *active, CassieTraj<T> traj) {
+__global__ void __launch_bounds__(sizeof(T) == 4 ? 480 : 224) k_env_step(T *st, int *sti, int n, const T *action, T *obs, T *reward, int *done, T *term_obs, int max_traj_len,
+                           const int *active, CassieTraj<T> traj, const int *order, int bar_mask) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   CassieWs<T> &w = reinterpret_cast<CassieWs<T> *>(smem)[warp];
-  const int e = blockIdx.x * wpb + warp;
+  const int slot = blockIdx.x * wpb + warp;
+  /* order (optional): slot -> env, envs of similar solver cost share a CTA (and its per-sub-step barrier), dearest first */
+  const int e = slot < n ? (order ? order[slot] : slot) : n;
   if (e >= n || (active && !active[e])) { /* idle slot: keep the CTA barriers company, touch nothing */
     if (e < n && lane == 0) { reward[e] = 0; done[e] = 4; }
-    for (int s = 0; s < CW_SIMRATE; s++) __syncthreads();
+    const int nbar = CW_SIMRATE * (1 + __popc(bar_mask & CW_BAR_ALL));
+    for (int s = 0; s < nbar; s++) __syncthreads();
     return;
   }
   ws_load(w, st + (size_t)e * S_WORDS, sti + (size_t)e * I_WORDS, lane);
   if (lane < CW_ACT) w.action[lane] = action[(size_t)e * CW_ACT + lane];
+  if (lane == 0) w.bar_mask = bar_mask;
   __syncwarp();
   T rew; int dn;
   T *o = obs + (size_t)e * CW_OBS;
@@ -79,6 +83,29 @@ template <typename T> __global__ void __launch_bounds__(32) k_mj_step(T *st, int
   ws_store(w, st + (size_t)e * S_WORDS, sti + (size_t)e * I_WORDS, lane);
 }
 
+/* Counting sort of the envs by the solver cost of their last step, dearest first (one CTA; the order inside a bucket is
+ * whatever the atomics give: placement never changes an env's results, only which envs wait for each other). */
+#define ORDER_BUCKETS 256
+__global__ void __launch_bounds__(1024) k_env_order(const int *sti, int n, int shift, int *order) {
+  __shared__ int hist[ORDER_BUCKETS], start[ORDER_BUCKETS];
+  for (int b = threadIdx.x; b < ORDER_BUCKETS; b += blockDim.x) hist[b] = 0;
+  __syncthreads();
+  for (int e = threadIdx.x; e < n; e += blockDim.x) {
+    const int b = min(sti[(size_t)e * I_WORDS + I_COST] >> shift, ORDER_BUCKETS - 1);
+    atomicAdd(&hist[b], 1);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int b = ORDER_BUCKETS - 1; b >= 0; b--) { start[b] = acc; acc += hist[b]; }
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < n; e += blockDim.x) {
+    const int b = min(sti[(size_t)e * I_WORDS + I_COST] >> shift, ORDER_BUCKETS - 1);
+    order[atomicAdd(&start[b], 1)] = e;
+  }
+}
+
 template <typename K> static int prep(K kernel, size_t smem) {
   cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   return err == cudaSuccess ? 0 : -(int)err;
@@ -93,6 +120,8 @@ extern "C" {
 /* tuning knob (envs per CTA of the step kernel); float64 is capped at 5 by shared memory */
 int apex_cassie_warps_per_cta = 14;
 void apex_cassie_set_warps_per_cta(int w) { apex_cassie_warps_per_cta = w; }
+int apex_cassie_bar_mask = 0;
+void apex_cassie_set_barrier_mask(int m) { apex_cassie_bar_mask = m & CW_BAR_ALL; }
 
 int apex_cassie_state_words(void) { return S_WORDS; }
 int apex_cassie_istate_words(void) { return I_WORDS; }
@@ -110,7 +139,7 @@ int apex_cassie_layout(const char *name) {
       {"meaninertia", S_MEANINERTIA}, {"footvel", S_FOOTVEL},
       {"drive_hist", I_DRIVEHIST}, {"time", I_TIME}, {"counter", I_COUNTER}, {"has_prev", I_HASPREV}, {"has_u", I_HASU},
       {"drive_init", I_DRIVEINIT}, {"joint_init", I_JOINTINIT}, {"flags", I_FLAGS}, {"stepcount", I_STEPCOUNT}, {"rng_ctr", I_RNGCTR},
-      {"env_id", I_ENVID}, {"seed", I_SEED}, {"dyn_rand", I_DYNRAND}, {"solver_iter", I_SOLVER_ITER}, {"ncon", I_NCON}, {"nefc", I_NEFC}, {"variant", I_VARIANT}};
+      {"env_id", I_ENVID}, {"seed", I_SEED}, {"dyn_rand", I_DYNRAND}, {"solver_iter", I_SOLVER_ITER}, {"ncon", I_NCON}, {"nefc", I_NEFC}, {"variant", I_VARIANT}, {"phase_floor", I_PHASEFLOOR}, {"cost", I_COST}};
   for (size_t i = 0; i < sizeof(tab) / sizeof(tab[0]); i++)
     if (strcmp(tab[i].n, name) == 0) return tab[i].off;
   return -1;
@@ -147,21 +176,21 @@ static int env_reset_impl(int dtype, void *st, int *sti, int n, void *obs, const
 
 static int env_step_impl(int dtype, void *st, int *sti, int n, const void *action, void *obs, void *reward, int *done,
                          void *term_obs, int max_traj_len, const int *active, const void *traj, int traj_rows, int traj_len,
-                         void *stream) {
+                         const int *order, void *stream) {
   if (!action || !obs || !reward || !done) return -1000;
   int wpb = apex_cassie_warps_per_cta;
   if (dtype == 1 && wpb > 7) wpb = 7;
-  if (wpb > 14) wpb = 14;
+  if (wpb > 15) wpb = 15;
   if (wpb < 1) wpb = 1;
   const CassieTraj<float> tf = {(const float *)traj, traj_rows, traj_len};
   const CassieTraj<double> td = {(const double *)traj, traj_rows, traj_len};
   DISPATCH(
       if ((rc = prep(k_env_step<float>, wpb * sizeof(CassieWs<float>)))) return rc;
       (k_env_step<float><<<(n + wpb - 1) / wpb, 32 * wpb, wpb * sizeof(CassieWs<float>), s>>>((float *)st, sti, n, (const float *)action, (float *)obs,
-                                                                (float *)reward, done, (float *)term_obs, max_traj_len, active, tf)),
+                                                                (float *)reward, done, (float *)term_obs, max_traj_len, active, tf, order, apex_cassie_bar_mask)),
       if ((rc = prep(k_env_step<double>, wpb * sizeof(CassieWs<double>)))) return rc;
       (k_env_step<double><<<(n + wpb - 1) / wpb, 32 * wpb, wpb * sizeof(CassieWs<double>), s>>>((double *)st, sti, n, (const double *)action, (double *)obs,
-                                                                  (double *)reward, done, (double *)term_obs, max_traj_len, active, td)))
+                                                                  (double *)reward, done, (double *)term_obs, max_traj_len, active, td, order, apex_cassie_bar_mask)))
 }
 
 int apex_cassie_env_init(int dtype, void *st, int *sti, int n, unsigned seed, int env_id0, int dyn_rand, void *stream) {
@@ -172,11 +201,11 @@ int apex_cassie_env_reset(int dtype, void *st, int *sti, int n, void *obs, void 
 }
 int apex_cassie_env_step(int dtype, void *st, int *sti, int n, const void *action, void *obs, void *reward, int *done,
                          void *term_obs, int max_traj_len, void *stream) {
-  return env_step_impl(dtype, st, sti, n, action, obs, reward, done, term_obs, max_traj_len, nullptr, nullptr, 0, 0, stream);
+  return env_step_impl(dtype, st, sti, n, action, obs, reward, done, term_obs, max_traj_len, nullptr, nullptr, 0, 0, nullptr, stream);
 }
 int apex_cassie_env_step_masked(int dtype, void *st, int *sti, int n, const void *action, void *obs, void *reward, int *done,
                                 void *term_obs, int max_traj_len, const int *active, void *stream) {
-  return env_step_impl(dtype, st, sti, n, action, obs, reward, done, term_obs, max_traj_len, active, nullptr, 0, 0, stream);
+  return env_step_impl(dtype, st, sti, n, action, obs, reward, done, term_obs, max_traj_len, active, nullptr, 0, 0, nullptr, stream);
 }
 
 /* CassieTraj-v0 (cassie/cassie_traj.py): same state record, variant flag 1, resets start from the reference trajectory */
@@ -195,7 +224,23 @@ int apex_cassietraj_env_step(int dtype, void *st, int *sti, int n, const void *a
                              void *term_obs, int max_traj_len, const int *active, const void *traj, int traj_rows, int traj_len,
                              void *stream) {
   if (!traj_ok(traj, traj_rows, traj_len)) return -1000;
-  return env_step_impl(dtype, st, sti, n, action, obs, reward, done, term_obs, max_traj_len, active, traj, traj_rows, traj_len, stream);
+  return env_step_impl(dtype, st, sti, n, action, obs, reward, done, term_obs, max_traj_len, active, traj, traj_rows, traj_len, nullptr, stream);
+}
+
+/* Load balancing.  apex_cassie_env_order fills order[n] (a permutation of 0..n-1) from the solver cost each env recorded in
+ * its last step; apex_cassie_env_step_ordered is apex_cassie_env_step / _masked / apex_cassietraj_env_step (traj may be NULL
+ * for Cassie-v0 records) with that slot -> env map.  Results per env are identical with or without it. */
+int apex_cassie_env_order(const int *sti, int n, int *order, void *stream) {
+  if (n <= 0) return 0;
+  if (!sti || !order) return -1000;
+  k_env_order<<<1, 1024, 0, (cudaStream_t)stream>>>(sti, n, 8, order); /* cost <= 50 * 50 * 32 = 80000 -> 256 buckets of 313 */
+  return finish();
+}
+int apex_cassie_env_step_ordered(int dtype, void *st, int *sti, int n, const void *action, void *obs, void *reward, int *done,
+                                 void *term_obs, int max_traj_len, const int *active, const void *traj, int traj_rows,
+                                 int traj_len, const int *order, void *stream) {
+  if (traj && !traj_ok(traj, traj_rows, traj_len)) return -1000;
+  return env_step_impl(dtype, st, sti, n, action, obs, reward, done, term_obs, max_traj_len, active, traj, traj_rows, traj_len, order, stream);
 }
 
 int apex_cassie_mj_step(int dtype, void *st, int *sti, int n, int flags, void *stream) {

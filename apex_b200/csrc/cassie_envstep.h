@@ -17,24 +17,27 @@ template <typename T> struct CassieTraj { const T *table; int rows; int len; };
 #define CW_TWO_PI 6.283185307179586
 
 CM_ARRAY int CW_FIR_W[9] = {2727, 534, -2658, -795, 72, 110, 19, -6, -3}; /* libcassiemujoco.so @0x80a3-0x80ef */
-CM_ARRAY double CW_OFFSET[10] = {0.0045, 0.0, 0.4973, -1.1997, -1.5968, 0.0045, 0.0, 0.4973, -1.1997, -1.5968}; /* cassie.py:107 */
-CM_ARRAY double CW_PGAIN[5] = {100, 100, 88, 96, 50};
-CM_ARRAY double CW_DGAIN[5] = {10.0, 10.0, 8.0, 9.6, 5.0}; /* cassie.py:57-58 */
-CM_ARRAY double CW_NEUTRAL_FOOT[4] = {-0.24790886454547323, -0.24679713195445646, -0.6609396704367185, 0.663921021343526};
-CM_ARRAY double CW_CLOCK_Y[4][8] = {{-1, -1, 0, 0, 1, 1, 0, 0}, {1, 1, 0, 0, -1, -1, 0, 0}, {1, 1, 0, 0, -1, -1, 0, 0}, {-1, -1, 0, 0, 1, 1, 0, 0}};
+/* double and float copies of the env constants (CWT(name) picks by T, like CMT for the model tables) */
+#define CW_DEF_TABLE(name, dims, ...) CM_ARRAY double name dims = __VA_ARGS__; CM_ARRAY float name##_f32 dims = __VA_ARGS__;
+#define CWT(name) (CmSel<T>::get(name, name##_f32))
+CW_DEF_TABLE(CW_OFFSET, [10], {0.0045, 0.0, 0.4973, -1.1997, -1.5968, 0.0045, 0.0, 0.4973, -1.1997, -1.5968}) /* cassie.py:107 */
+CW_DEF_TABLE(CW_PGAIN, [5], {100, 100, 88, 96, 50})
+CW_DEF_TABLE(CW_DGAIN, [5], {10.0, 10.0, 8.0, 9.6, 5.0}) /* cassie.py:57-58 */
+CW_DEF_TABLE(CW_CLOCK_Y, [4][8], {{-1, -1, 0, 0, 1, 1, 0, 0}, {1, 1, 0, 0, -1, -1, 0, 0}, {1, 1, 0, 0, -1, -1, 0, 0}, {-1, -1, 0, 0, 1, 1, 0, 0}})
+#define CW_NEUTRAL_FOOT(T, k) ((T)((k) == 0 ? -0.24790886454547323 : (k) == 1 ? -0.24679713195445646 : (k) == 2 ? -0.6609396704367185 : 0.663921021343526)) /* cassie.py:119 */
 
 /* ---------- cassie_sim_step_pd ---------- */
-template <typename T> CW_NOINL void cw_sim_step_pd(CassieWs<T> &w CW_LANE_PARAM) {
+template <typename T> CW_NOINL void cw_sim_step_pd(CassieWs<T> &w, int bar CW_LANE_PARAM) {
   const int hasu = w.sti[I_HASU], dinit = w.sti[I_DRIVEINIT], jinit = w.sti[I_JOINTINIT];
   CW_FOR_LANES {
     if (lane < CM_NU) {
       const int i = lane;
-      const T gear = (T)CM_act_gear[i];
+      const T gear = (T)CMT(act_gear)[i];
       /* pd_input_step on the previous call's cassie_out */
-      const T pg = hasu ? (T)CW_PGAIN[i % 5] : (T)0, dg = hasu ? (T)CW_DGAIN[i % 5] : (T)0;
+      const T pg = hasu ? (T)CWT(CW_PGAIN)[i % 5] : (T)0, dg = hasu ? (T)CWT(CW_DGAIN)[i % 5] : (T)0;
       const T ucmd = (T)0 + pg * (w.st[S_UPTARGET + i] - w.st[S_OMPOS + i]) + dg * ((T)0 - w.st[S_OMVEL + i]);
       /* motor model, @0x7d30-0x7eaa */
-      const T wv = w.st[S_SENS_ACTVEL + i], wmax = (T)CM_act_rpm[i] * (T)CW_TWO_PI / (T)60.0, tmax = (T)CM_act_ctrlmax[i];
+      const T wv = w.st[S_SENS_ACTVEL + i], wmax = (T)CMT(act_rpm)[i] * (T)CW_TWO_PI / (T)60.0, tmax = (T)CMT(act_ctrlmax)[i];
       const T tlim = cw_max(cw_min(2 * tmax * (1 - cw_abs(wv) / wmax), tmax), (T)0);
       T tau = cw_min(cw_abs(ucmd / gear), tlim);
       if (ucmd < 0 || (ucmd == 0 && 1 / ucmd < 0)) tau = -tau; /* copysign */
@@ -88,7 +91,7 @@ template <typename T> CW_NOINL void cw_sim_step_pd(CassieWs<T> &w CW_LANE_PARAM)
     }
   }
   CW_SYNC();
-  cw_mj_step<T>(w, true, 0 CW_LANE_ARG);
+  cw_mj_step<T>(w, true, bar CW_LANE_ARG);
 }
 
 /* ---------- clock functions ---------- */
@@ -103,12 +106,12 @@ template <typename T> CW_FN void cw_clock_knots(T swing, T stance, T *x, T *phas
 }
 template <typename T> CW_FN T cw_clock_eval(const T *x, T P, int which, T phase) {
   T xa, xb, ya, yb;
-  if (phase < x[0]) { xa = x[7] - P; ya = (T)CW_CLOCK_Y[which][7]; xb = x[0]; yb = (T)CW_CLOCK_Y[which][0]; }
-  else if (phase >= x[7]) { xa = x[7]; ya = (T)CW_CLOCK_Y[which][7]; xb = x[0] + P; yb = (T)CW_CLOCK_Y[which][0]; }
+  if (phase < x[0]) { xa = x[7] - P; ya = (T)CWT(CW_CLOCK_Y)[which][7]; xb = x[0]; yb = (T)CWT(CW_CLOCK_Y)[which][0]; }
+  else if (phase >= x[7]) { xa = x[7]; ya = (T)CWT(CW_CLOCK_Y)[which][7]; xb = x[0] + P; yb = (T)CWT(CW_CLOCK_Y)[which][0]; }
   else {
     int k = 0;
     while (k < 6 && phase >= x[k + 1]) k++;
-    xa = x[k]; xb = x[k + 1]; ya = (T)CW_CLOCK_Y[which][k]; yb = (T)CW_CLOCK_Y[which][k + 1];
+    xa = x[k]; xb = x[k + 1]; ya = (T)CWT(CW_CLOCK_Y)[which][k]; yb = (T)CWT(CW_CLOCK_Y)[which][k + 1];
   }
   const T t = (phase - xa) / (xb - xa);
   return ya + (yb - ya) * t * t * (3 - 2 * t);
@@ -173,7 +176,7 @@ template <typename T> CW_NOINL void cw_env_obs(CassieWs<T> &w, T *obs_out CW_LAN
 template <typename T> CW_NOINL void cw_set_const(CassieWs<T> &w CW_LANE_PARAM) {
   /* stage the 35-long qpos0 in the (currently unused) packed-A storage; J is not safe: kinematics' scratch overlays it */
   T *q0 = w.Ap;
-  CW_FOR_LANES { for (int k = lane; k < CM_NQ; k += 32) q0[k] = (T)CM_qpos0[k]; }
+  CW_FOR_LANES { for (int k = lane; k < CM_NQ; k += 32) q0[k] = (T)CMT(qpos0)[k]; }
   CW_SYNC();
   cw_kinematics<T>(w, q0 CW_LANE_ARG);
   cw_crb<T>(w CW_LANE_ARG);
@@ -206,7 +209,7 @@ template <typename T> CW_NOINL void cw_set_const(CassieWs<T> &w CW_LANE_PARAM) {
     const int nb = (CW_NB - b0) < 10 ? (CW_NB - b0) : 10;
     for (int bb = 0; bb < nb; bb++) {
       const int b = b0 + bb;
-      T ip[3] = {(T)CM_body_ipos[b][0], (T)CM_body_ipos[b][1], (T)CM_body_ipos[b][2]}, off[3];
+      T ip[3] = {(T)CMT(body_ipos)[b][0], (T)CMT(body_ipos)[b][1], (T)CMT(body_ipos)[b][2]}, off[3];
       cw_mulv(off, w.xmat[b], ip);
       for (int k = 0; k < 3; k++) off[k] += w.xpos[b][k] - org[k];
       CW_FOR_LANES {
@@ -237,9 +240,9 @@ template <typename T> CW_NOINL void cw_env_init(CassieWs<T> &w, uint32_t seed, u
   }
   CW_SYNC();
   CW_FOR_LANES {
-    w.st[S_DAMPING + lane] = (T)CM_dof_damping[lane];
-    if (lane < CW_NB) w.st[S_MASS + lane] = (T)CM_body_mass[lane];
-    for (int k = lane; k < CM_NQ; k += 32) w.st[S_QPOS + k] = (T)CM_qpos_init[k];
+    w.st[S_DAMPING + lane] = (T)CMT(dof_damping)[lane];
+    if (lane < CW_NB) w.st[S_MASS + lane] = (T)CMT(body_mass)[lane];
+    for (int k = lane; k < CM_NQ; k += 32) w.st[S_QPOS + k] = (T)CMT(qpos_init)[k];
     if (lane == 0) {
       w.st[S_FRICTION] = 1; w.st[S_FLOORQ] = 1;
       w.st[S_PHASELEN] = 32; w.sti[I_PHASEFLOOR] = 32;
@@ -305,12 +308,12 @@ template <typename T> CW_NOINL void cw_env_reset(CassieWs<T> &w, T *obs_out, con
         const int i = lane;
         const int fixed = i < 6 || i == 15 || i == 17 || i == 28 || i == 30;
         const double lo = fixed ? 1.0 : 0.3, hi = fixed ? 1.0 : 5.0;
-        const T d0 = (T)CM_dof_damping[i];
+        const T d0 = (T)CMT(dof_damping)[i];
         T v = d0 * (T)lo + (d0 * (T)hi - d0 * (T)lo) * cw_u01<T>(cw_draw(seed, env, ctr0, 3 + i));
         w.st[S_DAMPING + i] = v < 0 ? (T)0 : v;
       }
       if (lane >= 1 && lane < CW_NB) {
-        const T m0 = (T)CM_body_mass[lane];
+        const T m0 = (T)CMT(body_mass)[lane];
         T v = (T)0.5 * m0 + ((T)1.5 * m0 - (T)0.5 * m0) * cw_u01<T>(cw_draw(seed, env, ctr0, 35 + lane - 1));
         w.st[S_MASS + lane] = v < 0 ? (T)0 : v;
       }
@@ -333,7 +336,7 @@ template <typename T> CW_NOINL void cw_env_reset(CassieWs<T> &w, T *obs_out, con
   }
   /* cassie_sim_set_const @0x7330: fixed pose, zero velocity, mj_forward */
   CW_FOR_LANES {
-    for (int k = lane; k < CM_NQ; k += 32) w.st[S_QPOS + k] = (T)CM_qpos_init[k];
+    for (int k = lane; k < CM_NQ; k += 32) w.st[S_QPOS + k] = (T)CMT(qpos_init)[k];
     w.st[S_QVEL + lane] = 0;
     if (lane == 0) { w.st[S_PHASE] = phase; w.sti[I_TIME] = 0; w.sti[I_COUNTER] = 0; }
   }
@@ -354,7 +357,7 @@ template <typename T> CW_NOINL void cw_env_reset(CassieWs<T> &w, T *obs_out, con
   }
   CW_FOR_LANES { if (lane < 3) w.st[S_LASTPELVIS + lane] = w.st[S_QPOS + lane]; }
   /* one sub-step with the previous episode's pd_in_t (cassie.py:664-665) */
-  cw_sim_step_pd<T>(w CW_LANE_ARG);
+  cw_sim_step_pd<T>(w, 0 CW_LANE_ARG);
   T fp[6];
   cw_foot_positions<T>(w, fp);
   const T speed1 = cw_uniform<T>(cw_draw(seed, env, ctr0, nd), -0.3, 4.0);
@@ -374,19 +377,22 @@ template <typename T> CW_NOINL void cw_env_reset(CassieWs<T> &w, T *obs_out, con
 /* ---------- CassieEnv.step ---------- */
 template <typename T> CW_NOINL void cw_env_step(CassieWs<T> &w, T *obs_out, T *reward_out, int *done_out CW_LANE_PARAM) {
   CW_FOR_LANES {
-    if (lane < CW_ACT) w.st[S_UPTARGET + lane] = w.action[lane] + (T)CW_OFFSET[lane] - w.st[S_MENC + lane];
+    if (lane < CW_ACT) w.st[S_UPTARGET + lane] = w.action[lane] + (T)CWT(CW_OFFSET)[lane] - w.st[S_MENC + lane];
     if (lane == 0) w.sti[I_HASU] = 1;
   }
   CW_SYNC();
   T lfrc = 0, rfrc = 0, lori = 0, rori = 0, lfv[3] = {0, 0, 0}, rfv[3] = {0, 0, 0};
+  int cost = 0;
+  const int bar = w.bar_mask & CW_BAR_ALL;
   for (int s = 0; s < CW_SIMRATE; s++) {
     CW_BLOCK_SYNC();
     T fp0[6], fp1[6], lz, rz;
     for (int k = 0; k < 6; k++) fp0[k] = w.st[S_FOOTPOS + k];
-    cw_sim_step_pd<T>(w CW_LANE_ARG);
+    cw_sim_step_pd<T>(w, bar CW_LANE_ARG);
     cw_foot_positions<T>(w, fp1);
     for (int k = 0; k < 3; k++) { lfv[k] = (fp1[k] - fp0[k]) / (T)0.0005; rfv[k] = (fp1[3 + k] - fp0[3 + k]) / (T)0.0005; }
     cw_foot_forces<T>(w, &lz, &rz);
+    cost += w.solver_iter * w.nefc;
     int fl = w.sti[I_FLAGS], sc = w.sti[I_STEPCOUNT];
     { /* the reference tests the LEFT force for both feet (cassie.py:338,348) */
       int lh = fl & 1, rh = (fl >> 1) & 1, ls = (fl >> 2) & 1, rs = (fl >> 3) & 1;
@@ -398,7 +404,7 @@ template <typename T> CW_NOINL void cw_env_step(CassieWs<T> &w, T *obs_out, T *r
     }
     lfrc += lz; rfrc += rz;
     T dl = 0, dr = 0;
-    for (int k = 0; k < 4; k++) { dl += (T)CW_NEUTRAL_FOOT[k] * w.qkeep[1][k]; dr += (T)CW_NEUTRAL_FOOT[k] * w.qkeep[2][k]; }
+    for (int k = 0; k < 4; k++) { dl += CW_NEUTRAL_FOOT(T, k) * w.qkeep[1][k]; dr += CW_NEUTRAL_FOOT(T, k) * w.qkeep[2][k]; }
     lori += 1 - dl * dl; rori += 1 - dr * dr;
     CW_SYNC();
     CW_FOR_LANES {
@@ -474,7 +480,7 @@ template <typename T> CW_NOINL void cw_env_step(CassieWs<T> &w, T *obs_out, T *r
     if (lane == 0) {
       w.sti[I_TIME] = time; w.sti[I_COUNTER] = counter; w.sti[I_HASPREV] = 1; w.sti[I_RNGCTR] = (int)(ctr + 2);
       w.st[S_PHASE] = phase; w.st[S_ORIENT] = orient; w.st[S_SPEED] = speed; w.st[S_SIDE] = side;
-      w.sti[I_SOLVER_ITER] = w.solver_iter; w.sti[I_NCON] = w.ncon; w.sti[I_NEFC] = w.nefc;
+      w.sti[I_SOLVER_ITER] = w.solver_iter; w.sti[I_NCON] = w.ncon; w.sti[I_NEFC] = w.nefc; w.sti[I_COST] = cost;
     }
   }
   CW_SYNC();

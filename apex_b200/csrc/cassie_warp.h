@@ -42,6 +42,18 @@
 #define CM_ARRAY static const
 #endif
 #include "cassie_model.h"
+#include "cassie_model_f32.h"
+/* CMT(name): the model table CM_name in the precision of the enclosing template (T): the float32 kernel reads 4-byte
+ * constants instead of loading doubles and converting them at every use */
+template <typename T> struct CmSel;
+#ifdef __CUDACC__
+#define CW_MEMBER_FN static __device__ __forceinline__
+#else
+#define CW_MEMBER_FN static inline
+#endif
+template <> struct CmSel<double> { template <class D, class F> CW_MEMBER_FN const D &get(const D &d, const F &) { return d; } };
+template <> struct CmSel<float> { template <class D, class F> CW_MEMBER_FN const F &get(const D &, const F &f) { return f; } };
+#define CMT(name) (CmSel<T>::get(CM_##name, CM_##name##_f32))
 
 #ifdef __CUDACC__
 #define CW_LANE_PARAM , const int lane
@@ -51,6 +63,12 @@
 #define CW_LANE_ARG
 #endif
 
+/* cw_mj_step flags: bit0 no constraints, bit1 no contacts (test hooks); CW_BAR_*: CTA barrier at that point (step kernel only) */
+#define CW_BAR_FACTOR 0x100
+#define CW_BAR_SOLVE 0x200
+#define CW_BAR_POST 0x400
+#define CW_BAR_EULER 0x800
+#define CW_BAR_ALL 0xF00
 #define CW_NB CM_NBODY
 #define CW_NV CM_NV
 #define CW_NEFC 32 /* constraint-row capacity (njmax analogue): 12 equality + limits + contacts */
@@ -78,7 +96,8 @@ enum {
 enum {
   I_DRIVEHIST = 0, I_TIME = 90, I_COUNTER = 91, I_HASPREV = 92, I_HASU = 93, I_DRIVEINIT = 94, I_JOINTINIT = 95,
   I_FLAGS = 96, I_STEPCOUNT = 97, I_RNGCTR = 98, I_ENVID = 99, I_SEED = 100, I_DYNRAND = 101, I_SOLVER_ITER = 102,
-  I_NCON = 103, I_NEFC = 104, I_VARIANT = 105 /* 0 Cassie-v0, 1 CassieTraj-v0 */, I_PHASEFLOOR = 106 /* floor(phaselen), from float64 */, I_WORDS = 112
+  I_NCON = 103, I_NEFC = 104, I_VARIANT = 105 /* 0 Cassie-v0, 1 CassieTraj-v0 */, I_PHASEFLOOR = 106 /* floor(phaselen), from float64 */,
+  I_COST = 107 /* sum over the last env step's sub-steps of solver_iter * nefc: load-balancing key */, I_WORDS = 112
 };
 /* state_out slice (workspace only) */
 enum { Y_PPOS = 0, Y_QUAT = 3, Y_ROTVEL = 7, Y_TVEL = 10, Y_TACC = 13, Y_MPOS = 16, Y_MVEL = 26, Y_MTORQUE = 36, Y_JPOS = 46, Y_JVEL = 52, Y_WORDS = 58 };
@@ -115,6 +134,7 @@ struct CassieWs {
   int efc_type[CW_NEFC];
   T vec[V_NVEC][CW_NV];
   int ncon, nefc, solver_iter;
+  int bar_mask; /* extra CTA barriers inside a sub-step (CW_BAR_* bits), GPU build: keeps the CTA's warps on the same code */
   T con_pos[CW_NCON][3], con_frame[CW_NCON][9], con_dist[CW_NCON], con_mu[CW_NCON];
   int con_geom[CW_NCON], con_geom1[CW_NCON], con_dim[CW_NCON], con_adr[CW_NCON];
   T y[Y_WORDS];
@@ -240,8 +260,8 @@ template <typename T> CW_FN void cw_kinematics(CassieWs<T> &w, const T *qpos CW_
     CW_FOR_LANES {
       if (lane < CW_NB && CM_body_level[lane] == lvl) {
         const int b = lane, p = CM_body_parent[b], j = CM_body_jnt[b];
-        T bp[3] = {(T)CM_body_pos[b][0], (T)CM_body_pos[b][1], (T)CM_body_pos[b][2]};
-        T bq[4] = {(T)CM_body_quat[b][0], (T)CM_body_quat[b][1], (T)CM_body_quat[b][2], (T)CM_body_quat[b][3]};
+        T bp[3] = {(T)CMT(body_pos)[b][0], (T)CMT(body_pos)[b][1], (T)CMT(body_pos)[b][2]};
+        T bq[4] = {(T)CMT(body_quat)[b][0], (T)CMT(body_quat)[b][1], (T)CMT(body_quat)[b][2], (T)CMT(body_quat)[b][3]};
         T pos[3], quat[4], t[3];
         cw_mulv(t, w.xmat[p], bp);
         for (int k = 0; k < 3; k++) pos[k] = w.xpos[p][k] + t[k];
@@ -251,8 +271,8 @@ template <typename T> CW_FN void cw_kinematics(CassieWs<T> &w, const T *qpos CW_
           T qj[4], qn[4];
           if (CM_jnt_type[j] == 1) {
             T s, c;
-            cw_sincos<T>((T)0.5 * (qpos[qa] - (T)CM_qpos0[qa]), &s, &c);
-            qj[0] = c; qj[1] = (T)CM_jnt_axis[j][0] * s; qj[2] = (T)CM_jnt_axis[j][1] * s; qj[3] = (T)CM_jnt_axis[j][2] * s;
+            cw_sincos<T>((T)0.5 * (qpos[qa] - (T)CMT(qpos0)[qa]), &s, &c);
+            qj[0] = c; qj[1] = (T)CMT(jnt_axis)[j][0] * s; qj[2] = (T)CMT(jnt_axis)[j][1] * s; qj[3] = (T)CMT(jnt_axis)[j][2] * s;
           } else {
             qj[0] = qpos[qa]; qj[1] = qpos[qa + 1]; qj[2] = qpos[qa + 2]; qj[3] = qpos[qa + 3];
             cw_qnorm(qj);
@@ -288,7 +308,7 @@ template <typename T> CW_FN void cw_kinematics(CassieWs<T> &w, const T *qpos CW_
         if (j >= 0) {
           const int da = CM_jnt_dofadr[j];
           if (CM_jnt_type[j] == 1) {
-            T al[3] = {(T)CM_jnt_axis[j][0], (T)CM_jnt_axis[j][1], (T)CM_jnt_axis[j][2]}, ax[3];
+            T al[3] = {(T)CMT(jnt_axis)[j][0], (T)CMT(jnt_axis)[j][1], (T)CMT(jnt_axis)[j][2]}, ax[3];
             cw_mulv(ax, R, al);
             for (int k = 0; k < 3; k++) w.cdof[da][k] = ax[k];
             cw_cross(w.cdof[da] + 3, ax, off);
@@ -302,14 +322,14 @@ template <typename T> CW_FN void cw_kinematics(CassieWs<T> &w, const T *qpos CW_
         }
       }
       /* spatial inertia about org */
-      T in0 = (T)CM_body_inertia[b][0], in1 = (T)CM_body_inertia[b][1], in2 = (T)CM_body_inertia[b][2];
-      T in3 = (T)CM_body_inertia[b][3], in4 = (T)CM_body_inertia[b][4], in5 = (T)CM_body_inertia[b][5];
+      T in0 = (T)CMT(body_inertia)[b][0], in1 = (T)CMT(body_inertia)[b][1], in2 = (T)CMT(body_inertia)[b][2];
+      T in3 = (T)CMT(body_inertia)[b][3], in4 = (T)CMT(body_inertia)[b][4], in5 = (T)CMT(body_inertia)[b][5];
       T Ib[9] = {in0, in3, in4, in3, in1, in5, in4, in5, in2}, Tm[9], Iw[9];
       for (int r = 0; r < 3; r++)
         for (int c = 0; c < 3; c++) Tm[3 * r + c] = R[3 * r] * Ib[c] + R[3 * r + 1] * Ib[3 + c] + R[3 * r + 2] * Ib[6 + c];
       for (int r = 0; r < 3; r++)
         for (int c = 0; c < 3; c++) Iw[3 * r + c] = Tm[3 * r] * R[3 * c] + Tm[3 * r + 1] * R[3 * c + 1] + Tm[3 * r + 2] * R[3 * c + 2];
-      T ip[3] = {(T)CM_body_ipos[b][0], (T)CM_body_ipos[b][1], (T)CM_body_ipos[b][2]}, c[3];
+      T ip[3] = {(T)CMT(body_ipos)[b][0], (T)CMT(body_ipos)[b][1], (T)CMT(body_ipos)[b][2]}, c[3];
       cw_mulv(c, R, ip);
       for (int k = 0; k < 3; k++) c[k] -= off[k]; /* xipos - org */
       const T mass = w.st[S_MASS + b], cc = cw_dot3(c, c);
@@ -347,7 +367,7 @@ template <typename T> CW_FN void cw_build_M(CassieWs<T> &w CW_LANE_PARAM) {
     const int i = lane;
     T f[6];
     cw_inert_mul(f, w.crb[CM_dof_body[i]], w.cdof[i]);
-    w.Mdiag[i] = cw_dot6(w.cdof[i], f) + (T)CM_dof_armature[i];
+    w.Mdiag[i] = cw_dot6(w.cdof[i], f) + (T)CMT(dof_armature)[i];
     const int na = CM_dof_nanc[i], rp = CM_dof_rowptr[i];
     for (int t = 0; t < na; t++) w.Ms[rp + t] = cw_dot6(w.cdof[CM_dof_anc[i][t]], f);
   }
@@ -468,8 +488,8 @@ template <typename T> CW_FN void cw_make_frame(T *fr) { /* mju_makeFrame */
 
 template <typename T> CW_FN void cw_geom_world(const CassieWs<T> &w, int g, T *c, T *ax) {
   const int b = CM_geom_body[g];
-  T gp[3] = {(T)CM_geom_pos[g][0], (T)CM_geom_pos[g][1], (T)CM_geom_pos[g][2]};
-  T ga[3] = {(T)CM_geom_axis[g][0], (T)CM_geom_axis[g][1], (T)CM_geom_axis[g][2]}, t[3];
+  T gp[3] = {(T)CMT(geom_pos)[g][0], (T)CMT(geom_pos)[g][1], (T)CMT(geom_pos)[g][2]};
+  T ga[3] = {(T)CMT(geom_axis)[g][0], (T)CMT(geom_axis)[g][1], (T)CMT(geom_axis)[g][2]}, t[3];
   cw_mulv(t, w.xmat[b], gp);
   for (int k = 0; k < 3; k++) c[k] = w.xpos[b][k] + t[k];
   cw_mulv(ax, w.xmat[b], ga);
@@ -490,7 +510,7 @@ template <typename T> CW_FN void cw_collision(CassieWs<T> &w CW_LANE_PARAM) {
       cw_qmat(Rf, fq);
       T n[3] = {Rf[2], Rf[5], Rf[8]}, c[3], ax[3];
       cw_geom_world(w, g, c, ax);
-      const T r = (T)CM_geom_radius[g], hl = (T)CM_geom_halflen[g] * (T)CW_CAND_END[lane];
+      const T r = (T)CMT(geom_radius)[g], hl = (T)CMT(geom_halflen)[g] * (T)CW_CAND_END[lane];
       T pc[3] = {c[0] + hl * ax[0], c[1] + hl * ax[1], c[2] + hl * ax[2]};
       T rel[3] = {pc[0], pc[1], pc[2] - (T)CM_FLOOR_Z};
       const T dist = cw_dot3(rel, n) - r;
@@ -505,7 +525,7 @@ template <typename T> CW_FN void cw_collision(CassieWs<T> &w CW_LANE_PARAM) {
       T c1[3], a1[3], c2[3], a2[3];
       cw_geom_world(w, g1, c1, a1);
       cw_geom_world(w, g2, c2, a2);
-      const T h1 = (T)CM_geom_halflen[g1], h2 = (T)CM_geom_halflen[g2], r1 = (T)CM_geom_radius[g1], r2 = (T)CM_geom_radius[g2];
+      const T h1 = (T)CMT(geom_halflen)[g1], h2 = (T)CMT(geom_halflen)[g2], r1 = (T)CMT(geom_radius)[g1], r2 = (T)CMT(geom_radius)[g2];
       T r[3] = {c1[0] - c2[0], c1[1] - c2[1], c1[2] - c2[2]};
       const T b = cw_dot3(a1, a2), c = cw_dot3(a1, r), f = cw_dot3(a2, r), den = 1 - b * b;
       T ss = den > (T)1e-12 ? (b * f - c) / den : (T)0;
@@ -561,8 +581,8 @@ template <typename T> CW_FN void cw_make_constraint(CassieWs<T> &w, const T *qpo
   if (!(flags & 1)) {
     for (int e = 0; e < CM_NEQ; e++) {
       const int b1 = CM_eq_body1[e], b2 = CM_eq_body2[e];
-      T a1[3] = {(T)CM_eq_anchor1[e][0], (T)CM_eq_anchor1[e][1], (T)CM_eq_anchor1[e][2]};
-      T a2[3] = {(T)CM_eq_anchor2[e][0], (T)CM_eq_anchor2[e][1], (T)CM_eq_anchor2[e][2]};
+      T a1[3] = {(T)CMT(eq_anchor1)[e][0], (T)CMT(eq_anchor1)[e][1], (T)CMT(eq_anchor1)[e][2]};
+      T a2[3] = {(T)CMT(eq_anchor2)[e][0], (T)CMT(eq_anchor2)[e][1], (T)CMT(eq_anchor2)[e][2]};
       T o1[3], o2[3];
       cw_mulv(o1, w.xmat[b1], a1);
       cw_mulv(o2, w.xmat[b2], a2);
@@ -590,7 +610,7 @@ template <typename T> CW_FN void cw_make_constraint(CassieWs<T> &w, const T *qpo
       const int j = CW_LIM_JNT[l];
       const T q = qpos[CM_jnt_qposadr[j]];
       for (int side = -1; side <= 1; side += 2) {
-        const T dist = (T)side * ((T)CM_jnt_range[j][(side + 1) / 2] - q);
+        const T dist = (T)side * ((T)CMT(jnt_range)[j][(side + 1) / 2] - q);
         if (dist < 0 && r + crows < CW_NEFC) {
           const int da = CM_jnt_dofadr[j];
           CW_FOR_LANES {
@@ -795,14 +815,15 @@ template <typename T> CW_NOINL void cw_mj_step(CassieWs<T> &w, bool integrate, i
   cw_crb<T>(w CW_LANE_ARG);
   cw_build_M<T>(w CW_LANE_ARG);
   cw_factor<T>(w, (T)0 CW_LANE_ARG);
+  if (flags & CW_BAR_FACTOR) CW_BLOCK_SYNC();
   cw_collision<T>(w CW_LANE_ARG);
   cw_make_constraint<T>(w, qpos, flags CW_LANE_ARG);
   const int n = w.nefc;
   /* sensors (positions / velocities) for the next wrapper call */
   CW_FOR_LANES {
     if (lane < CM_NU) {
-      w.st[S_SENS_ACTPOS + lane] = (T)CM_act_gear[lane] * qpos[CM_act_qposadr[lane]];
-      w.st[S_SENS_ACTVEL + lane] = (T)CM_act_gear[lane] * qvel[CM_act_dof[lane]];
+      w.st[S_SENS_ACTPOS + lane] = (T)CMT(act_gear)[lane] * qpos[CM_act_qposadr[lane]];
+      w.st[S_SENS_ACTVEL + lane] = (T)CMT(act_gear)[lane] * qvel[CM_act_dof[lane]];
     } else if (lane < CM_NU + 6) {
       w.st[S_SENS_JPOS + lane - CM_NU] = qpos[CM_jsens_qposadr[lane - CM_NU]];
     } else if (lane < CM_NU + 10) {
@@ -819,7 +840,7 @@ template <typename T> CW_NOINL void cw_mj_step(CassieWs<T> &w, bool integrate, i
     const int i = lane;
     T f = -w.st[S_DAMPING + i] * qvel[i] - w.vec[V_BIAS][i];
     const int j = CM_dof_jnt[i];
-    const T k = (T)CM_jnt_stiffness[j];
+    const T k = (T)CMT(jnt_stiffness)[j];
     if (k != 0) f -= k * qpos[CM_jnt_qposadr[j]];
     w.vec[V_SMOOTH][i] = f;
   }
@@ -827,9 +848,9 @@ template <typename T> CW_NOINL void cw_mj_step(CassieWs<T> &w, bool integrate, i
   CW_FOR_LANES {
     if (lane < CM_NU) {
       T c = w.st[S_CTRL + lane];
-      const T cm = (T)CM_act_ctrlmax[lane];
+      const T cm = (T)CMT(act_ctrlmax)[lane];
       c = cw_min(cw_max(c, -cm), cm);
-      w.vec[V_SMOOTH][CM_act_dof[lane]] += (T)CM_act_gear[lane] * c;
+      w.vec[V_SMOOTH][CM_act_dof[lane]] += (T)CMT(act_gear)[lane] * c;
     }
   }
   CW_SYNC();
@@ -843,6 +864,7 @@ template <typename T> CW_NOINL void cw_mj_step(CassieWs<T> &w, bool integrate, i
   /* ---- constraints ---- */
   CW_FOR_LANES { w.vec[V_G][lane] = 0; }
   int iters = 0;
+  if (flags & CW_BAR_SOLVE) CW_BLOCK_SYNC();
   if (n > 0) {
     cw_project<T>(w CW_LANE_ARG);
     /* L qacc_warmstart (so that J a = B (L a)) */
@@ -894,15 +916,18 @@ template <typename T> CW_NOINL void cw_mj_step(CassieWs<T> &w, bool integrate, i
       for (int it = 0; it < CM_ITERATIONS; it++) {
         T imp = 0;
 #pragma unroll
-        for (int i = 0; i < CW_NEFC; i++) {
-          if (i >= n) break;
-          const T nf = cw_max(f0 - res0 * di0, lb0);
-          const T dlo = nf - f0;
-          const T dl = __shfl_sync(0xffffffffu, dlo, i);
-          const bool own = lane == i;
-          imp = own ? imp - dl * (dl * had0 + res0) : imp;
-          f0 = own ? nf : f0;
-          res0 += dl * acol[i];
+        for (int i0 = 0; i0 < CW_NEFC; i0 += 4) {
+          if (i0 >= n) break; /* tested once per 4 rows: a row >= n has di0 = 0 and a zero column, so its update is exactly 0 */
+#pragma unroll
+          for (int i = i0; i < i0 + 4; i++) {
+            const T nf = cw_max(f0 - res0 * di0, lb0);
+            const T dlo = nf - f0;
+            const T dl = __shfl_sync(0xffffffffu, dlo, i);
+            const bool own = lane == i;
+            imp = own ? imp - dl * (dl * had0 + res0) : imp;
+            f0 = own ? nf : f0;
+            res0 += dl * acol[i];
+          }
         }
         for (int o = 16; o > 0; o >>= 1) imp += __shfl_xor_sync(0xffffffffu, imp, o);
         iters = it + 1;
@@ -958,6 +983,7 @@ template <typename T> CW_NOINL void cw_mj_step(CassieWs<T> &w, bool integrate, i
     }
   }
   CW_SYNC();
+  if (flags & CW_BAR_POST) CW_BLOCK_SYNC(); /* the solver's length varies per env: realign before the common tail */
   /* qacc = qacc_smooth + L^-1 D^-1 g */
   CW_FOR_LANES { w.vec[V_QACC][lane] = w.vec[V_G][lane] * w.Dinv[lane]; }
   CW_SYNC();
@@ -970,7 +996,7 @@ template <typename T> CW_NOINL void cw_mj_step(CassieWs<T> &w, bool integrate, i
   /* accelerometer at the imu site (world-frame a_site - g, rotated into the site frame) */
   {
     const T *R = w.xmat[CM_IMU_BODY], *qa = w.vec[V_QACC];
-    T ip[3] = {(T)CM_imu_pos[0], (T)CM_imu_pos[1], (T)CM_imu_pos[2]}, r[3], wl[3] = {qvel[3], qvel[4], qvel[5]};
+    T ip[3] = {(T)CMT(imu_pos)[0], (T)CMT(imu_pos)[1], (T)CMT(imu_pos)[2]}, r[3], wl[3] = {qvel[3], qvel[4], qvel[5]};
     T al[3] = {qa[3], qa[4], qa[5]}, ww[3], aw[3], t1[3], t2[3], t3[3], a[3], out[3];
     cw_mulv(r, R, ip); cw_mulv(ww, R, wl); cw_mulv(aw, R, al);
     cw_cross(t1, aw, r); cw_cross(t2, ww, r); cw_cross(t3, ww, t2);
@@ -990,6 +1016,7 @@ template <typename T> CW_NOINL void cw_mj_step(CassieWs<T> &w, bool integrate, i
     w.vec[V_TMP][j] = s + w.vec[V_SMOOTH][j];
   }
   CW_SYNC();
+  if (flags & CW_BAR_EULER) CW_BLOCK_SYNC();
   cw_build_M<T>(w CW_LANE_ARG); /* the factor overwrote M in place: rebuild it from the (still valid) composite inertias */
   cw_factor<T>(w, h CW_LANE_ARG);
   cw_solve_LT<T>(w, w.vec[V_TMP] CW_LANE_ARG);

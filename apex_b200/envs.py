@@ -18,7 +18,8 @@ _DT = {torch.float32: 0, torch.float64: 1}
 
 class BatchedCassieEnv:
     def __init__(self, num_envs, device="cuda:0", dtype=torch.float32, seed=0, dynamics_randomization=True, simrate=50,
-                 command_profile="clock", input_profile="full", reward="clock", max_traj_len=400, env_id0=0, history=0, **kwargs):
+                 command_profile="clock", input_profile="full", reward="clock", max_traj_len=400, env_id0=0, history=0, balance=True,
+                 **kwargs):
         if simrate != 50 or command_profile != "clock" or input_profile != "full" or history != 0:
             raise NotImplementedError("kernel is specialised for simrate=50, clock command, full input, history=0")
         if reward not in ("clock",):
@@ -48,6 +49,8 @@ class BatchedCassieEnv:
         self.term_obs = torch.zeros((n, 50), dtype=dtype, device=self.device)
         self.rew = torch.zeros((n,), dtype=dtype, device=self.device)
         self.done = torch.zeros((n,), dtype=torch.int32, device=self.device)
+        self.balance = bool(balance)
+        self.order = torch.arange(n, dtype=torch.int32, device=self.device)
         self._init_state(int(seed) & 0xFFFFFFFF, int(env_id0))
 
     def _init_state(self, seed, env_id0):
@@ -62,7 +65,7 @@ class BatchedCassieEnv:
         """View of a named field of the persistent state (tests, command overrides)."""
         off = _lib.layout(name)
         ints = name in ("drive_hist", "time", "counter", "has_prev", "has_u", "drive_init", "joint_init", "flags", "stepcount",
-                        "rng_ctr", "env_id", "seed", "dyn_rand", "solver_iter", "ncon", "nefc", "variant")
+                        "rng_ctr", "env_id", "seed", "dyn_rand", "solver_iter", "ncon", "nefc", "variant", "phase_floor", "cost")
         return (self.sti if ints else self.st)[:, off:off + width]
 
     def reset(self):
@@ -71,23 +74,29 @@ class BatchedCassieEnv:
                                                     self.obs.data_ptr(), self._stream()), "env_reset")
         return self.obs
 
+    def _traj_args(self):
+        return None, 0, 0
+
     def step(self, action, f_term=0, rew_out=None, done_out=None, active=None):
         """action [N, 10] on the device -> (obs [N, 50], reward [N], done [N] int32 (bit0 terminal, bit1 time-out), {}).
-        rew_out / done_out: optional contiguous device tensors that receive reward and done (e.g. rollout-buffer rows)."""
+        rew_out / done_out: optional contiguous device tensors that receive reward and done (e.g. rollout-buffer rows).
+        active: optional int32 mask, envs with active == 0 are skipped (done = 4)."""
         a = action.to(device=self.device, dtype=self.dtype).contiguous()
         assert a.shape == (self.num_envs, 10)
         rew = self.rew if rew_out is None else rew_out
         done = self.done if done_out is None else done_out
+        tp, trows, tlen = self._traj_args()
         with torch.cuda.device(self.device):
-            if active is None:
-                _lib.check(self.L.apex_cassie_env_step(self.dt, self.st.data_ptr(), self.sti.data_ptr(), self.num_envs, a.data_ptr(),
-                                                       self.obs.data_ptr(), rew.data_ptr(), done.data_ptr(),
-                                                       self.term_obs.data_ptr(), self.max_traj_len, self._stream()), "env_step")
-            else:  # int32 mask: envs with active == 0 are skipped (done = 4)
-                _lib.check(self.L.apex_cassie_env_step_masked(self.dt, self.st.data_ptr(), self.sti.data_ptr(), self.num_envs,
-                                                              a.data_ptr(), self.obs.data_ptr(), rew.data_ptr(), done.data_ptr(),
-                                                              self.term_obs.data_ptr(), self.max_traj_len, active.data_ptr(),
-                                                              self._stream()), "env_step_masked")
+            order = None
+            if self.balance:  # group envs of similar solver cost into the same CTA (results do not depend on it)
+                _lib.check(self.L.apex_cassie_env_order(self.sti.data_ptr(), self.num_envs, self.order.data_ptr(), self._stream()),
+                           "env_order")
+                order = self.order.data_ptr()
+            _lib.check(self.L.apex_cassie_env_step_ordered(self.dt, self.st.data_ptr(), self.sti.data_ptr(), self.num_envs,
+                                                           a.data_ptr(), self.obs.data_ptr(), rew.data_ptr(), done.data_ptr(),
+                                                           self.term_obs.data_ptr(), self.max_traj_len,
+                                                           None if active is None else active.data_ptr(), tp, trows, tlen, order,
+                                                           self._stream()), "env_step")
         return self.obs, rew, done, {}
 
     def set_command(self, speed=None, side_speed=None, phase=None):
@@ -139,15 +148,5 @@ class BatchedCassieTrajEnv(BatchedCassieEnv):
                                                         self._traj_len, self._stream()), "traj_env_reset")
         return self.obs
 
-    def step(self, action, f_term=0, rew_out=None, done_out=None, active=None):
-        a = action.to(device=self.device, dtype=self.dtype).contiguous()
-        assert a.shape == (self.num_envs, 10)
-        rew = self.rew if rew_out is None else rew_out
-        done = self.done if done_out is None else done_out
-        with torch.cuda.device(self.device):
-            _lib.check(self.L.apex_cassietraj_env_step(self.dt, self.st.data_ptr(), self.sti.data_ptr(), self.num_envs, a.data_ptr(),
-                                                       self.obs.data_ptr(), rew.data_ptr(), done.data_ptr(), self.term_obs.data_ptr(),
-                                                       self.max_traj_len, None if active is None else active.data_ptr(),
-                                                       self.traj_rows.data_ptr(), self.traj_rows.shape[0], self._traj_len,
-                                                       self._stream()), "traj_env_step")
-        return self.obs, rew, done, {}
+    def _traj_args(self):
+        return self.traj_rows.data_ptr(), self.traj_rows.shape[0], self._traj_len

@@ -215,7 +215,7 @@ class PPO:
             obs, _, _, _ = env.step(buf.act[t], rew_out=buf.rew[t], done_out=buf.done[t])
             self._mlp_fwd(cp, env.term_obs, N, 1, self.h[2], self.h[3], buf.term_val[t])  # V(s_T) of time-limit cuts
             self.cur_obs = obs
-            self.launches += 3
+            self.launches += 3 + int(getattr(env, "balance", False))
         self._mlp_fwd(cp, self.cur_obs, N, 1, self.h[2], self.h[3], buf.last_val)
         _capi.check(L.apex_gae_scan(T, N, _p(buf.rew), _p(buf.val), _p(buf.done), _p(buf.term_val), _p(buf.last_val),
                                     float(self.gamma), float(self.lam), _p(buf.ret), _p(buf.adv), s), "gae_scan")

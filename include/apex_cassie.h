@@ -56,6 +56,15 @@ int apex_cassietraj_env_reset(int dtype, void *st, int *sti, int n, void *obs, c
 int apex_cassietraj_env_step(int dtype, void *st, int *sti, int n, const void *action, void *obs, void *reward, int *done,
                              void *term_obs, int max_traj_len, const int *active, const void *traj, int traj_rows, int traj_len,
                              void *stream);
+/* ---- load balancing (ours; no reference counterpart) ----
+ * The step kernel runs W envs per CTA with one CTA barrier per physics sub-step, so a CTA advances at the pace of its
+ * dearest env (PGS sweeps x rows).  Each env records that cost in sti["cost"]; apex_cassie_env_order counting-sorts the envs
+ * by it (dearest first) into order[n], and apex_cassie_env_step_ordered runs slot s on env order[s] (order NULL = identity;
+ * traj NULL for Cassie-v0 records; active NULL = all).  Per-env results do not depend on the order. */
+int apex_cassie_env_order(const int *sti, int n, int *order, void *stream);
+int apex_cassie_env_step_ordered(int dtype, void *st, int *sti, int n, const void *action, void *obs, void *reward, int *done,
+                                 void *term_obs, int max_traj_len, const int *active, const void *traj, int traj_rows,
+                                 int traj_len, const int *order, void *stream);
 /* tuning: environments (warps) per CTA of the step kernel, 1..14 (default 7 = two CTAs of 7 envs per SM; float64 is capped at 7) */
 void apex_cassie_set_warps_per_cta(int w);
 /* one raw mj_step (no wrapper, no env logic) on the stored state with S_CTRL as control; test hook */

@@ -15,6 +15,7 @@ the two trees never include each other's files.
 Array storage class is left to the includer through CM_ARRAY (C: `static const`,
 CUDA: `static __device__ const`).
 """
+import re
 import sys
 import math
 import xml.etree.ElementTree as ET
@@ -401,11 +402,27 @@ def emit_gen(m):
     return ''.join(o)
 
 
+def emit_f32(text):
+    """float copies (NAME_f32) of every double table of cassie_model.h, for the float32 kernel: the device code would otherwise
+    load 8-byte constants and convert them (F2F.F32.F64 runs on the slow fp64 pipe) at every use."""
+    o = ['/* GENERATED by tools/gen_model.py from cassie_model.h: float32 copies of its double tables.  Do not edit. */\n'
+         '#ifndef CASSIE_MODEL_F32_H\n#define CASSIE_MODEL_F32_H\n']
+    for m in re.finditer(r'CM_ARRAY double (\w+)((?:\[\d+\])+) = (\{.*?\});', text, re.S):
+        body = re.sub(r'(?<![\w.])(-?\d+\.\d*(?:e[-+]?\d+)?|-?\d+e[-+]?\d+)(?![\w.])', lambda k: k.group(1) + 'f', m.group(3))
+        o.append(f'CM_ARRAY float {m.group(1)}_f32{m.group(2)} = {body};\n')
+    o.append('#endif\n')
+    return ''.join(o)
+
+
 INIT_QPOS = [0.0, 0.0, 1.01, 1.0, 0.0, 0.0, 0.0, 0.0045, 0.0, 0.4973, 0.9785, -0.0164, 0.01787, -0.2049, -1.1997, 0.0,
              1.4267, 0.0, -1.5244, 1.5244, -1.5968, -0.0045, 0.0, 0.4973, 0.9786, 0.00386, -0.01524, -0.2051, -1.1997,
              0.0, 1.4267, 0.0, -1.5244, 1.5244, -1.5968]
 
 if __name__ == '__main__':
+    if sys.argv[1] == '--f32':  # python tools/gen_model.py --f32 apex_b200/csrc/cassie_model.h apex_b200/csrc/cassie_model_f32.h
+        with open(sys.argv[3], 'w') as f:
+            f.write(emit_f32(open(sys.argv[2]).read()))
+        sys.exit(0)
     mdl = compile_model(sys.argv[1])
     text = emit(mdl)
     for out in sys.argv[2:]:

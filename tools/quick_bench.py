@@ -13,7 +13,9 @@ import os
 from apex_b200 import lib
 if os.environ.get("WPB"):
     lib().apex_cassie_set_warps_per_cta(int(os.environ["WPB"]))
-env = BatchedCassieEnv(n, dtype=dt, seed=0, dynamics_randomization=True)
+if os.environ.get("BARM"):
+    lib().apex_cassie_set_barrier_mask(int(os.environ["BARM"], 0))
+env = BatchedCassieEnv(n, dtype=dt, seed=0, dynamics_randomization=True, balance=os.environ.get("BALANCE", "1") == "1")
 env.reset()
 g = torch.Generator(device="cuda").manual_seed(0)
 act = torch.randn((n, 10), generator=g, device="cuda", dtype=dt) * 0.2
