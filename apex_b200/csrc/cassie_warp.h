@@ -255,41 +255,60 @@ template <typename T> CW_FN void cw_kinematics(CassieWs<T> &w, const T *qpos CW_
       cw_qmat(w.xmat[1], q);
     }
   }
+  /* local rotation of every body at once: body_quat * joint rotation (hinge about its axis by q - qpos0, or the ball's own
+   * quaternion), parked in xmat[b][0..3] until the sweep below has consumed it */
+  CW_FOR_LANES {
+    if (lane >= 2 && lane < CW_NB) {
+      const int b = lane, j = CM_body_jnt[b];
+      T ql[4] = {(T)CMT(body_quat)[b][0], (T)CMT(body_quat)[b][1], (T)CMT(body_quat)[b][2], (T)CMT(body_quat)[b][3]};
+      if (j >= 0) {
+        const int qa = CM_jnt_qposadr[j];
+        T qj[4], qn[4];
+        if (CM_jnt_type[j] == 1) {
+          T s, c;
+          cw_sincos<T>((T)0.5 * (qpos[qa] - (T)CMT(qpos0)[qa]), &s, &c);
+          qj[0] = c; qj[1] = (T)CMT(jnt_axis)[j][0] * s; qj[2] = (T)CMT(jnt_axis)[j][1] * s; qj[3] = (T)CMT(jnt_axis)[j][2] * s;
+        } else {
+          qj[0] = qpos[qa]; qj[1] = qpos[qa + 1]; qj[2] = qpos[qa + 2]; qj[3] = qpos[qa + 3];
+          cw_qnorm(qj);
+        }
+        cw_qmul(qn, ql, qj);
+        for (int k = 0; k < 4; k++) ql[k] = qn[k];
+      }
+      for (int k = 0; k < 4; k++) w.xmat[b][k] = ql[k];
+    }
+  }
   CW_SYNC();
+  /* tree sweep, one level per phase, kept light: xquat = norm(xquat[parent] * local), xpos = xpos[parent] + R(xquat[parent]) body_pos
+   * (the vector is rotated by the parent's quaternion directly: v + 2 w (u x v) + 2 u x (u x v)) */
   for (int lvl = 2; lvl <= CM_MAXLEVEL; lvl++) {
     CW_FOR_LANES {
       if (lane < CW_NB && CM_body_level[lane] == lvl) {
-        const int b = lane, p = CM_body_parent[b], j = CM_body_jnt[b];
-        T bp[3] = {(T)CMT(body_pos)[b][0], (T)CMT(body_pos)[b][1], (T)CMT(body_pos)[b][2]};
-        T bq[4] = {(T)CMT(body_quat)[b][0], (T)CMT(body_quat)[b][1], (T)CMT(body_quat)[b][2], (T)CMT(body_quat)[b][3]};
-        T pos[3], quat[4], t[3];
-        cw_mulv(t, w.xmat[p], bp);
-        for (int k = 0; k < 3; k++) pos[k] = w.xpos[p][k] + t[k];
-        cw_qmul(quat, w.u.p.xquat[p], bq);
-        if (j >= 0) {
-          const int qa = CM_jnt_qposadr[j];
-          T qj[4], qn[4];
-          if (CM_jnt_type[j] == 1) {
-            T s, c;
-            cw_sincos<T>((T)0.5 * (qpos[qa] - (T)CMT(qpos0)[qa]), &s, &c);
-            qj[0] = c; qj[1] = (T)CMT(jnt_axis)[j][0] * s; qj[2] = (T)CMT(jnt_axis)[j][1] * s; qj[3] = (T)CMT(jnt_axis)[j][2] * s;
-          } else {
-            qj[0] = qpos[qa]; qj[1] = qpos[qa + 1]; qj[2] = qpos[qa + 2]; qj[3] = qpos[qa + 3];
-            cw_qnorm(qj);
-          }
-          cw_qmul(qn, quat, qj);
-          for (int k = 0; k < 4; k++) quat[k] = qn[k];
-        }
+        const int b = lane, p = CM_body_parent[b];
+        const T pq[4] = {w.u.p.xquat[p][0], w.u.p.xquat[p][1], w.u.p.xquat[p][2], w.u.p.xquat[p][3]};
+        const T ql[4] = {w.xmat[b][0], w.xmat[b][1], w.xmat[b][2], w.xmat[b][3]};
+        const T bp[3] = {(T)CMT(body_pos)[b][0], (T)CMT(body_pos)[b][1], (T)CMT(body_pos)[b][2]};
+        T quat[4], t1[3], t2[3];
+        cw_qmul(quat, pq, ql);
         cw_qnorm(quat);
-        for (int k = 0; k < 3; k++) w.xpos[b][k] = pos[k];
+        cw_cross(t1, pq + 1, bp);
+        cw_cross(t2, pq + 1, t1);
+        for (int k = 0; k < 3; k++) w.xpos[b][k] = w.xpos[p][k] + bp[k] + 2 * (pq[0] * t1[k] + t2[k]);
         for (int k = 0; k < 4; k++) w.u.p.xquat[b][k] = quat[k];
-        if (b == CW_LFOOT) for (int k = 0; k < 4; k++) w.qkeep[1][k] = quat[k];
-        if (b == CW_RFOOT) for (int k = 0; k < 4; k++) w.qkeep[2][k] = quat[k];
-        cw_qmat(w.xmat[b], quat);
       }
     }
     CW_SYNC();
   }
+  CW_FOR_LANES {
+    if (lane >= 2 && lane < CW_NB) {
+      const int b = lane;
+      const T quat[4] = {w.u.p.xquat[b][0], w.u.p.xquat[b][1], w.u.p.xquat[b][2], w.u.p.xquat[b][3]};
+      if (b == CW_LFOOT) for (int k = 0; k < 4; k++) w.qkeep[1][k] = quat[k];
+      if (b == CW_RFOOT) for (int k = 0; k < 4; k++) w.qkeep[2][k] = quat[k];
+      cw_qmat(w.xmat[b], quat);
+    }
+  }
+  CW_SYNC();
   /* cdof and cinert about org = pelvis origin */
   CW_FOR_LANES {
     if (lane >= 1 && lane < CW_NB) {
@@ -352,10 +371,13 @@ template <typename T> CW_FN void cw_crb(CassieWs<T> &w CW_LANE_PARAM) {
     CW_FOR_LANES {
       if (lane < CW_NB && CM_body_level[lane] == lvl) {
         const int nc = CM_body_nchild[lane];
+        T acc[10];
+        for (int k = 0; k < 10; k++) acc[k] = w.crb[lane][k];
         for (int c = 0; c < nc; c++) {
           const int ch = CM_body_child[lane][c];
-          for (int k = 0; k < 10; k++) w.crb[lane][k] += w.crb[ch][k];
+          for (int k = 0; k < 10; k++) acc[k] += w.crb[ch][k];
         }
+        for (int k = 0; k < 10; k++) w.crb[lane][k] = acc[k];
       }
     }
     CW_SYNC();
@@ -719,8 +741,11 @@ template <typename T> CW_FN void cw_project(CassieWs<T> &w CW_LANE_PARAM) {
   }
   CW_SYNC();
 }
-/* velocity stage: mj_comVel + mj_rne (bias), lane = body, level by level */
+/* velocity stage: mj_comVel + mj_rne (bias).  The tree recurrences (cvel, cacc down; cfrc up) are level loops that only add
+ * 6-vectors (two lanes are busy on most levels: one body per leg); everything heavy — cdof_dot for all 32 dofs, the body
+ * wrench I a + v x* (I v) for all 26 bodies — is hoisted out of them and runs once at full width. */
 template <typename T> CW_FN void cw_rne(CassieWs<T> &w, const T *qvel CW_LANE_PARAM) {
+  /* pass 1 (down): cvel[b] = cvel[parent] + sum over b's dofs of cdof * qvel */
   CW_FOR_LANES {
     if (lane == 0) {
       for (int k = 0; k < 6; k++) { w.u.p.cvel[0][k] = 0; w.u.p.cacc[0][k] = 0; }
@@ -731,47 +756,76 @@ template <typename T> CW_FN void cw_rne(CassieWs<T> &w, const T *qvel CW_LANE_PA
   for (int lvl = 1; lvl <= CM_MAXLEVEL; lvl++) {
     CW_FOR_LANES {
       if (lane < CW_NB && CM_body_level[lane] == lvl) {
-        const int b = lane, p = CM_body_parent[b];
-        T v[6], a[6];
-        for (int k = 0; k < 6; k++) { v[k] = w.u.p.cvel[p][k]; a[k] = w.u.p.cacc[p][k]; }
-        const int da = CM_body_dofadr[b], nd = CM_body_dofnum[b];
-        /* pelvis: slides one at a time, then the ball (all three cdof_dot from the pre-ball velocity) */
-        int d0 = 0;
-        while (d0 < nd) {
-          const int grp = (nd - d0 >= 3 && !(b == 1 && d0 < 3)) ? 3 : 1;
-          for (int s = 0; s < grp; s++) {
-            const T *cd = w.cdof[da + d0 + s];
-            T *o = w.u.p.cdd[da + d0 + s];
-            T t1[3], t2[3], t3[3];
-            cw_cross(t1, v, cd); cw_cross(t2, v, cd + 3); cw_cross(t3, v + 3, cd);
-            for (int k = 0; k < 3; k++) { o[k] = t1[k]; o[3 + k] = t2[k] + t3[k]; }
-          }
-          for (int s = 0; s < grp; s++) {
-            const T qd = qvel[da + d0 + s];
-            for (int k = 0; k < 6; k++) { v[k] += w.cdof[da + d0 + s][k] * qd; a[k] += w.u.p.cdd[da + d0 + s][k] * qd; }
-          }
-          d0 += grp;
+        const int b = lane, p = CM_body_parent[b], da = CM_body_dofadr[b], nd = CM_body_dofnum[b];
+        T v[6];
+        for (int k = 0; k < 6; k++) v[k] = w.u.p.cvel[p][k];
+        for (int s = 0; s < nd; s++) {
+          const T qd = qvel[da + s];
+          for (int k = 0; k < 6; k++) v[k] += w.cdof[da + s][k] * qd;
         }
-        for (int k = 0; k < 6; k++) { w.u.p.cvel[b][k] = v[k]; }
-        /* cfrc_body = I a + v x* (I v); w.crb still holds the per-body (not yet composite) inertia here */
-        T f[6], iv[6], t1[3], t2[3], t3[3];
-        cw_inert_mul(f, w.crb[b], a);
-        cw_inert_mul(iv, w.crb[b], v);
-        cw_cross(t1, v, iv); cw_cross(t2, v + 3, iv + 3); cw_cross(t3, v, iv + 3);
-        for (int k = 0; k < 3; k++) { f[k] += t1[k] + t2[k]; f[3 + k] += t3[k]; }
-        for (int k = 0; k < 6; k++) { w.u.p.cacc[b][k] = a[k]; w.u.p.cfrc[b][k] = f[k]; }
+        for (int k = 0; k < 6; k++) w.u.p.cvel[b][k] = v[k];
       }
     }
     CW_SYNC();
   }
+  /* pass 2 (lane = dof): cdof_dot = cvel_before_the_joint x cdof.  A joint's dofs all use the velocity before the joint
+   * (mj_comVel treats a ball joint as one unit), which is the parent body's cvel — except on the pelvis, whose three
+   * slides come one at a time (they add no angular velocity, so their own cdof_dot is exactly 0) before its ball joint,
+   * which therefore sees the linear velocity (qvel[0..2]) of the slides. */
+  CW_FOR_LANES {
+    const int d = lane;
+    T pre[6] = {0, 0, 0, 0, 0, 0};
+    if (d >= 6) { const int p = CM_body_parent[CM_dof_body[d]]; for (int k = 0; k < 6; k++) pre[k] = w.u.p.cvel[p][k]; }
+    else if (d >= 3) { pre[3] = qvel[0]; pre[4] = qvel[1]; pre[5] = qvel[2]; }
+    const T *cd = w.cdof[d];
+    T *o = w.u.p.cdd[d];
+    T t1[3], t2[3], t3[3];
+    cw_cross(t1, pre, cd); cw_cross(t2, pre, cd + 3); cw_cross(t3, pre + 3, cd);
+    for (int k = 0; k < 3; k++) { o[k] = t1[k]; o[3 + k] = t2[k] + t3[k]; }
+  }
+  CW_SYNC();
+  /* pass 3 (down): cacc[b] = cacc[parent] + sum cdof_dot * qvel (qacc = 0: bias forces) */
+  for (int lvl = 1; lvl <= CM_MAXLEVEL; lvl++) {
+    CW_FOR_LANES {
+      if (lane < CW_NB && CM_body_level[lane] == lvl) {
+        const int b = lane, p = CM_body_parent[b], da = CM_body_dofadr[b], nd = CM_body_dofnum[b];
+        T a[6];
+        for (int k = 0; k < 6; k++) a[k] = w.u.p.cacc[p][k];
+        for (int s = 0; s < nd; s++) {
+          const T qd = qvel[da + s];
+          for (int k = 0; k < 6; k++) a[k] += w.u.p.cdd[da + s][k] * qd;
+        }
+        for (int k = 0; k < 6; k++) w.u.p.cacc[b][k] = a[k];
+      }
+    }
+    CW_SYNC();
+  }
+  /* pass 4 (lane = body): cfrc_body = I a + v x* (I v); w.crb still holds the per-body (not yet composite) inertia here */
+  CW_FOR_LANES {
+    if (lane >= 1 && lane < CW_NB) {
+      const int b = lane;
+      T v[6], a[6], f[6], iv[6], t1[3], t2[3], t3[3];
+      for (int k = 0; k < 6; k++) { v[k] = w.u.p.cvel[b][k]; a[k] = w.u.p.cacc[b][k]; }
+      cw_inert_mul(f, w.crb[b], a);
+      cw_inert_mul(iv, w.crb[b], v);
+      cw_cross(t1, v, iv); cw_cross(t2, v + 3, iv + 3); cw_cross(t3, v, iv + 3);
+      for (int k = 0; k < 3; k++) { f[k] += t1[k] + t2[k]; f[3 + k] += t3[k]; }
+      for (int k = 0; k < 6; k++) w.u.p.cfrc[b][k] = f[k];
+    }
+  }
+  CW_SYNC();
+  /* pass 5 (up): parents gather their children's wrenches, deepest level first */
   for (int lvl = CM_MAXLEVEL - 1; lvl >= 1; lvl--) {
     CW_FOR_LANES {
       if (lane < CW_NB && CM_body_level[lane] == lvl) {
         const int nc = CM_body_nchild[lane];
+        T acc[6];
+        for (int k = 0; k < 6; k++) acc[k] = w.u.p.cfrc[lane][k];
         for (int c = 0; c < nc; c++) {
           const int ch = CM_body_child[lane][c];
-          for (int k = 0; k < 6; k++) w.u.p.cfrc[lane][k] += w.u.p.cfrc[ch][k];
+          for (int k = 0; k < 6; k++) acc[k] += w.u.p.cfrc[ch][k];
         }
+        for (int k = 0; k < 6; k++) w.u.p.cfrc[lane][k] = acc[k];
       }
     }
     CW_SYNC();
