@@ -173,8 +173,10 @@ template <typename T> CW_FN void cw_sincos(T x, T *s, T *c) { cw_sincos_o(x, s, 
 template <typename T> CW_FN T cw_exp(T x) { return cw_exp_o(x); }
 template <typename T> CW_FN T cw_tan(T x) { return cw_tan_o(x); }
 template <typename T> CW_FN T cw_abs(T x) { return x < 0 ? -x : x; }
-template <typename T> CW_FN T cw_min(T a, T b) { return a < b ? a : b; }
-template <typename T> CW_FN T cw_max(T a, T b) { return a > b ? a : b; }
+CW_FN float cw_min(float a, float b) { return fminf(a, b); } /* one FMNMX instead of compare + select */
+CW_FN float cw_max(float a, float b) { return fmaxf(a, b); }
+CW_FN double cw_min(double a, double b) { return a < b ? a : b; }
+CW_FN double cw_max(double a, double b) { return a > b ? a : b; }
 
 template <typename T> CW_FN void cw_cross(T *r, const T *a, const T *b) {
   T x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
@@ -951,8 +953,10 @@ template <typename T> CW_NOINL void cw_mj_step(CassieWs<T> &w, bool integrate, i
        * applies column i of A to its own residual — no shared-memory traffic and no barrier inside the sweep. */
       const bool v0 = lane < n;
       T acol[CW_NEFC];
+      const int rowbase = lane * (lane + 1) / 2;
 #pragma unroll
-      for (int i = 0; i < CW_NEFC; i++) acol[i] = (v0 && i < n) ? w.Ap[cw_tri(lane, i)] : (T)0;
+      for (int i = 0; i < CW_NEFC; i++) /* packed lower triangle: (lane, i) sits in row max(lane, i); i is a compile-time constant */
+        acol[i] = (v0 && i < n) ? w.Ap[i <= lane ? rowbase + i : i * (i + 1) / 2 + lane] : (T)0;
       T f0 = v0 ? w.efc_f[lane] : (T)0;
       const T b0 = v0 ? w.efc_b[lane] : (T)0, di0 = v0 ? w.efc_dinv[lane] : (T)0;
       const T lb0 = (v0 && w.efc_type[lane] != 0) ? (T)0 : (T)-3.0e38; /* lower bound of the row's force */
@@ -961,8 +965,8 @@ template <typename T> CW_NOINL void cw_mj_step(CassieWs<T> &w, bool integrate, i
       for (int i = 0; i < CW_NEFC; i++) {
         const T fi = __shfl_sync(0xffffffffu, f0, i);
         sacc += acol[i] * fi;
-        if (i == lane) had0 = (T)0.5 * acol[i];
       }
+      had0 = v0 ? (T)0.5 * w.Ap[rowbase + lane] : (T)0;
       T cost = f0 * ((T)0.5 * sacc + b0);
       for (int o = 16; o > 0; o >>= 1) cost += __shfl_xor_sync(0xffffffffu, cost, o);
       T res0 = sacc + b0;
