@@ -181,7 +181,7 @@ template <typename T> CW_NOINL void cw_set_const(CassieWs<T> &w CW_LANE_PARAM) {
   cw_kinematics<T>(w, q0 CW_LANE_ARG);
   cw_crb<T>(w CW_LANE_ARG);
   cw_build_M<T>(w CW_LANE_ARG);
-  cw_factor<T>(w, (T)0 CW_LANE_ARG);
+  cw_factor<T, 1>(w, (T)0 CW_LANE_ARG);
   T tr = 0;
   for (int i = 0; i < CW_NV; i++) tr += w.Mdiag[i];
   CW_SYNC();

@@ -117,9 +117,12 @@ struct CassieWs {
   int sti[I_WORDS];
   T xpos[CW_NB][3], xmat[CW_NB][9];
   T qkeep[3][4]; /* world quaternions of the pelvis (imu site), left foot, right foot */
-  T cdof[CW_NV][6], crb[CW_NB][10]; /* crb: spatial inertia per body, turned into the composite inertia by cw_crb */
+  T cdof[CW_NV][6];
   T Ms[CM_MNNZ + 5]; /* tree-sparse strict lower triangle: entry (k, t-th ancestor of k) at CM_dof_rowptr[k] + t; holds the
                       * mass matrix after cw_build_M and U = D_k L[k][.] (unscaled rows of M = L^T D L) after cw_factor */
+  /* crb: spatial inertia per body, turned into the composite inertia by cw_crb; dead once M is built.  crb and Mdiag are
+   * adjacent on purpose: cw_factor<T, 2> keeps the rows of the second factor (M + h B) in these 292 words (cw_Ms2) */
+  T crb[CW_NB][10];
   T Mdiag[CW_NV], D[CW_NV], Dinv[CW_NV];
   union U { /* the collision / RNE scratch is dead before the first Jacobian row is written */
     T J[CW_NEFC][CW_NV + 1]; /* constraint Jacobian, later B = J L^-1 */
@@ -399,35 +402,55 @@ template <typename T> CW_FN void cw_build_M(CassieWs<T> &w CW_LANE_PARAM) {
 }
 
 /* sparse L^T D L (mj_factorM): M = L^T D L with the sparsity of the dof tree; rows are kept unscaled
- * (w.M[k][j] = D_k L[k][j]), w.Dinv[k] = 1/D_k.  hdamp = 0: factor M; hdamp = h: factor M + h diag(damping)
- * (mj_Euler's implicit damping).  The elimination itself is generated straight-line code (cassie_gen.h). */
-template <typename T> CW_NOINL void cw_factor(CassieWs<T> &w, T hdamp CW_LANE_PARAM) {
-  CW_FOR_LANES { w.D[lane] = w.Mdiag[lane] + hdamp * w.st[S_DAMPING + lane]; }
-  CW_SYNC();
+ * (Ms[k][j] = D_k L[k][j]), Dinv[k] = 1/D_k.
+ * NF = 1: factor M + hdamp * diag(damping) in place (w.Ms, w.Dinv; w.D is scratch).
+ * NF = 2: factor M (w.Ms, w.Dinv) AND M + hdamp * diag(damping) (mj_Euler's implicit damping; rows in cw_Ms2(w), inverse
+ *         pivots in w.D) in one pass: the two eliminations are independent, so interleaving them shares every index
+ *         computation and phase barrier and gives each lane two FMA chains instead of one.  w.vec[V_TMP] is scratch. */
+template <typename T> CW_FN T *cw_Ms2(CassieWs<T> &w) { return &w.crb[0][0]; }
+template <typename T, int NF> CW_NOINL void cw_factor(CassieWs<T> &w, T hdamp CW_LANE_PARAM) {
+  static_assert(sizeof(w.crb) + sizeof(w.Mdiag) >= sizeof(w.Ms), "second factor does not fit");
+  T *const Mp[2] = {w.Ms, cw_Ms2(w)};
+  T *const Dp[2] = {NF == 2 ? w.vec[V_TMP] : w.D, w.D}; /* running pivots */
+  if (NF == 1) {
+    CW_FOR_LANES { w.D[lane] = w.Mdiag[lane] + hdamp * w.st[S_DAMPING + lane]; }
+    CW_SYNC();
+  } else {
+    CW_FOR_LANES { const T m = w.Mdiag[lane]; Dp[0][lane] = m; Dp[1][lane] = m + hdamp * w.st[S_DAMPING + lane]; }
+    CW_SYNC(); /* Mdiag and crb are dead from here on: the copy below overwrites them */
+    CW_FOR_LANES { for (int k = lane; k < CM_MNNZ; k += 32) Mp[1][k] = Mp[0][k]; }
+    CW_SYNC();
+  }
   /* the two legs are independent sub-trees hanging off the 6 base dofs: eliminate dof 6+s and 19+s together.
    * Ancestors in increasing dof order are in root-to-leaf order, so the t-th set bit of a chain mask has rank 6 + t. */
   for (int s = 12; s >= 0; s--) {
     const int kL = 6 + s, kR = 19 + s;
     const unsigned legmask = CM_leg_ancmask[s];
-    const T dL = cw_rcp(w.D[kL]), dR = cw_rcp(w.D[kR]);
+    T dL[NF], dR[NF];
+    for (int f = 0; f < NF; f++) { dL[f] = cw_rcp(Dp[f][kL]); dR[f] = cw_rcp(Dp[f][kR]); }
     CW_FOR_LANES {
-      if (lane == 0) { w.Dinv[kL] = dL; w.Dinv[kR] = dR; }
+      if (lane == 0) { w.Dinv[kL] = dL[0]; w.Dinv[kR] = dR[0]; }
       if (lane >= 6) {
         const bool rt = lane >= 19;
         const int ll = lane - (rt ? 13 : 0);
         if ((legmask >> ll) & 1u) {
-          const T *rk = w.Ms + CM_dof_rowptr[rt ? kR : kL];
-          T *rl = w.Ms + CM_dof_rowptr[lane];
+          const int ok = CM_dof_rowptr[rt ? kR : kL], ol = CM_dof_rowptr[lane];
           const unsigned below = legmask & ((1u << ll) - 1u);
           const int rank = 6 + __builtin_popcount(below); /* rank of `lane` in k's chain = its own chain length */
-          const T a = rk[rank] * (rt ? dR : dL);
-          rl[0] -= a * rk[0]; rl[1] -= a * rk[1]; rl[2] -= a * rk[2];
-          rl[3] -= a * rk[3]; rl[4] -= a * rk[4]; rl[5] -= a * rk[5];
-          for (int t = 6; t < rank; t++) rl[t] -= a * rk[t];
-          w.D[lane] -= a * rk[rank];
+          T a[NF];
+          for (int f = 0; f < NF; f++) a[f] = Mp[f][ok + rank] * (rt ? dR[f] : dL[f]);
+          for (int t = 0; t < 6; t++)
+            for (int f = 0; f < NF; f++) Mp[f][ol + t] -= a[f] * Mp[f][ok + t];
+          for (int t = 6; t < rank; t++)
+            for (int f = 0; f < NF; f++) Mp[f][ol + t] -= a[f] * Mp[f][ok + t];
+          for (int f = 0; f < NF; f++) Dp[f][lane] -= a[f] * Mp[f][ok + rank];
         }
       }
     }
+    CW_SYNC();
+  }
+  if (NF == 2) { /* the leg pivots of the second factor are final: keep their inverses (in place) */
+    CW_FOR_LANES { if (lane >= 6) Dp[1][lane] = cw_rcp(Dp[1][lane]); }
     CW_SYNC();
   }
   /* Schur complement of both legs on the 6 base dofs, one (i, j <= i) entry per lane */
@@ -436,48 +459,59 @@ template <typename T> CW_NOINL void cw_factor(CassieWs<T> &w, T hdamp CW_LANE_PA
       int i = 0, rem = lane;
       while (rem > i) { rem -= i + 1; i++; }
       const int j = rem;
-      T acc = 0;
-      for (int k = 6; k < CW_NV; k++) { const T *rk = w.Ms + CM_dof_rowptr[k]; acc += rk[i] * rk[j] * w.Dinv[k]; }
-      if (i == j) w.D[i] -= acc; else w.Ms[CM_dof_rowptr[i] + j] -= acc;
+      T acc[NF];
+      for (int f = 0; f < NF; f++) acc[f] = 0;
+      for (int k = 6; k < CW_NV; k++) {
+        const int ok = CM_dof_rowptr[k];
+        acc[0] += Mp[0][ok + i] * Mp[0][ok + j] * w.Dinv[k];
+        if (NF == 2) acc[NF - 1] += Mp[NF - 1][ok + i] * Mp[NF - 1][ok + j] * Dp[NF - 1][k];
+      }
+      for (int f = 0; f < NF; f++) { if (i == j) Dp[f][i] -= acc[f]; else Mp[f][CM_dof_rowptr[i] + j] -= acc[f]; }
     }
   }
   CW_SYNC();
   for (int k = 5; k >= 1; k--) {
-    const T d = cw_rcp(w.D[k]);
-    const T *rk = w.Ms + CM_dof_rowptr[k];
+    T d[NF];
+    for (int f = 0; f < NF; f++) d[f] = cw_rcp(Dp[f][k]);
+    const int ok = CM_dof_rowptr[k];
     CW_FOR_LANES {
-      if (lane == 0) w.Dinv[k] = d;
+      if (lane == 0) w.Dinv[k] = d[0];
       if (lane < k) {
-        const T a = rk[lane] * d;
-        T *rl = w.Ms + CM_dof_rowptr[lane];
-        for (int j = 0; j < lane; j++) rl[j] -= a * rk[j];
-        w.D[lane] -= a * rk[lane];
+        const int ol = CM_dof_rowptr[lane];
+        for (int f = 0; f < NF; f++) {
+          const T a = Mp[f][ok + lane] * d[f];
+          for (int j = 0; j < lane; j++) Mp[f][ol + j] -= a * Mp[f][ok + j];
+          Dp[f][lane] -= a * Mp[f][ok + lane];
+        }
       }
     }
     CW_SYNC();
   }
   {
-    const T d = cw_rcp(w.D[0]);
-    CW_FOR_LANES { if (lane == 0) w.Dinv[0] = d; }
+    const T d = cw_rcp(Dp[0][0]);
+    CW_FOR_LANES {
+      if (lane == 0) w.Dinv[0] = d;
+      if (NF == 2 && lane < 6) Dp[NF - 1][lane] = cw_rcp(Dp[NF - 1][lane]);
+    }
     CW_SYNC();
   }
 }
 
-/* v <- L^-T v (in place, shared vector) */
-template <typename T> CW_NOINL void cw_solve_LT(CassieWs<T> &w, T *v CW_LANE_PARAM) {
+/* v <- L^-T v (in place, shared vector); Ms / Dinv select the factor */
+template <typename T> CW_NOINL void cw_solve_LT(const T *Ms, const T *Dinv, T *v CW_LANE_PARAM) {
   for (int k = CW_NV - 1; k >= 1; k--) {
     const unsigned mask = CM_dof_ancmask[k];
-    const T vk = v[k] * w.Dinv[k];
-    const T *rk = w.Ms + CM_dof_rowptr[k];
+    const T vk = v[k] * Dinv[k];
+    const T *rk = Ms + CM_dof_rowptr[k];
     CW_FOR_LANES { if ((mask >> lane) & 1u) v[lane] -= rk[CM_dof_nanc[lane]] * vk; }
     CW_SYNC();
   }
 }
 /* v <- L^-1 v: every dof has exactly one ancestor per depth, so 13 level sweeps suffice */
-template <typename T> CW_NOINL void cw_solve_L(CassieWs<T> &w, T *v CW_LANE_PARAM) {
+template <typename T> CW_NOINL void cw_solve_L(const T *Ms, const T *Dinv, T *v CW_LANE_PARAM) {
   for (int lvl = 0; lvl < CM_MAXANC; lvl++) {
     CW_FOR_LANES {
-      if (CM_dof_nanc[lane] > lvl) { const int j = CM_dof_anc[lane][lvl]; v[lane] -= w.Ms[CM_dof_rowptr[lane] + lvl] * w.Dinv[lane] * v[j]; }
+      if (CM_dof_nanc[lane] > lvl) { const int j = CM_dof_anc[lane][lvl]; v[lane] -= Ms[CM_dof_rowptr[lane] + lvl] * Dinv[lane] * v[j]; }
     }
     CW_SYNC();
   }
@@ -870,7 +904,8 @@ template <typename T> CW_NOINL void cw_mj_step(CassieWs<T> &w, bool integrate, i
   cw_rne<T>(w, qvel CW_LANE_ARG); /* before cw_crb: it reads the per-body inertias */
   cw_crb<T>(w CW_LANE_ARG);
   cw_build_M<T>(w CW_LANE_ARG);
-  cw_factor<T>(w, (T)0 CW_LANE_ARG);
+  if (integrate) cw_factor<T, 2>(w, h CW_LANE_ARG); /* M for the solves, M + h B for mj_Euler's implicit damping */
+  else cw_factor<T, 1>(w, (T)0 CW_LANE_ARG);
   if (flags & CW_BAR_FACTOR) CW_BLOCK_SYNC();
   cw_collision<T>(w CW_LANE_ARG);
   cw_make_constraint<T>(w, qpos, flags CW_LANE_ARG);
@@ -913,10 +948,10 @@ template <typename T> CW_NOINL void cw_mj_step(CassieWs<T> &w, bool integrate, i
   /* z = D^-1 L^-T qfrc_smooth ; qacc_smooth = L^-1 z */
   CW_FOR_LANES { w.vec[V_Z][lane] = w.vec[V_SMOOTH][lane]; }
   CW_SYNC();
-  cw_solve_LT<T>(w, w.vec[V_Z] CW_LANE_ARG);
+  cw_solve_LT<T>(w.Ms, w.Dinv, w.vec[V_Z] CW_LANE_ARG);
   CW_FOR_LANES { w.vec[V_Z][lane] *= w.Dinv[lane]; w.vec[V_QACCS][lane] = w.vec[V_Z][lane]; }
   CW_SYNC();
-  cw_solve_L<T>(w, w.vec[V_QACCS] CW_LANE_ARG);
+  cw_solve_L<T>(w.Ms, w.Dinv, w.vec[V_QACCS] CW_LANE_ARG);
   /* ---- constraints ---- */
   CW_FOR_LANES { w.vec[V_G][lane] = 0; }
   int iters = 0;
@@ -1045,7 +1080,7 @@ template <typename T> CW_NOINL void cw_mj_step(CassieWs<T> &w, bool integrate, i
   /* qacc = qacc_smooth + L^-1 D^-1 g */
   CW_FOR_LANES { w.vec[V_QACC][lane] = w.vec[V_G][lane] * w.Dinv[lane]; }
   CW_SYNC();
-  cw_solve_L<T>(w, w.vec[V_QACC] CW_LANE_ARG);
+  cw_solve_L<T>(w.Ms, w.Dinv, w.vec[V_QACC] CW_LANE_ARG);
   CW_FOR_LANES {
     w.vec[V_QACC][lane] += w.vec[V_QACCS][lane];
     if (lane == 0) { w.solver_iter = iters; }
@@ -1075,12 +1110,13 @@ template <typename T> CW_NOINL void cw_mj_step(CassieWs<T> &w, bool integrate, i
   }
   CW_SYNC();
   if (flags & CW_BAR_EULER) CW_BLOCK_SYNC();
-  cw_build_M<T>(w CW_LANE_ARG); /* the factor overwrote M in place: rebuild it from the (still valid) composite inertias */
-  cw_factor<T>(w, h CW_LANE_ARG);
-  cw_solve_LT<T>(w, w.vec[V_TMP] CW_LANE_ARG);
-  CW_FOR_LANES { w.vec[V_TMP][lane] *= w.Dinv[lane]; }
-  CW_SYNC();
-  cw_solve_L<T>(w, w.vec[V_TMP] CW_LANE_ARG);
+  { /* the second factor (M + h B) was computed together with the first: rows in cw_Ms2(w), inverse pivots in w.D */
+    const T *Ms2 = cw_Ms2(w), *Dinv2 = w.D;
+    cw_solve_LT<T>(Ms2, Dinv2, w.vec[V_TMP] CW_LANE_ARG);
+    CW_FOR_LANES { w.vec[V_TMP][lane] *= Dinv2[lane]; }
+    CW_SYNC();
+    cw_solve_L<T>(Ms2, Dinv2, w.vec[V_TMP] CW_LANE_ARG);
+  }
   CW_FOR_LANES {
     qvel[lane] += h * w.vec[V_TMP][lane];
     w.st[S_QACC_WS + lane] = w.vec[V_QACC][lane];
