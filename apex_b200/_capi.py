@@ -66,6 +66,8 @@ def lib():
         for f in (L.apex_mlp_backward_dx, L.apex_replay_gather, L.apex_td3_action, L.apex_td3_critic_loss, L.apex_td3_actor_grad,
                   L.apex_polyak):
             f.restype = i
+        L.apex_set_gemm_large_tiles.argtypes = [i]
+        L.apex_set_gemm_large_tiles.restype = None
         L.apex_col_moments.argtypes = [vp, i, i, vp, vp]
         L.apex_col_moments.restype = i
         for f in (L.apex_mlp_forward, L.apex_mlp_backward, L.apex_prepare_obs, L.apex_gaussian_sample, L.apex_ppo_loss,

@@ -88,11 +88,164 @@ __global__ void __launch_bounds__(256) k_gemm(int M, int N, int K, const float *
   }
 }
 
+/* Large-tile variant for the 256-wide layers (they carry ~97% of the learner's flops): 128 x 128 x 16 tile, 8 x 8 outputs per
+ * thread read from shared memory as float4, global loads of the next tile issued before the FMAs of the current one
+ * (register double buffering), k-contiguous operands fetched as float4.  Same operand conventions and epilogue as k_gemm. */
+#define LM 128
+#define LN 128
+#define LK 16
+__global__ void __launch_bounds__(256) k_gemm128(int M, int N, int K, const float *__restrict__ A, long sam, long sak,
+                                                 const float *__restrict__ B, long sbk, long sbn, float *__restrict__ C, long scm,
+                                                 long scn, const float *__restrict__ bias, int relu, const float *__restrict__ mask,
+                                                 long smm, long smn, int accumulate, int kchunk) {
+  __shared__ __align__(16) float As[LK][LM + 4];
+  __shared__ __align__(16) float Bs[LK][LN + 4];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * LM, n0 = blockIdx.x * LN;
+  const int kbeg = blockIdx.z * kchunk, kend = min(K, kbeg + kchunk);
+  /* vector path: operand contiguous along k, rows 16-byte aligned */
+  const bool a_vec = sak == 1 && (sam & 3) == 0 && ((size_t)A & 15) == 0 && (kbeg & 3) == 0;
+  const bool b_vec = sbk == 1 && (sbn & 3) == 0 && ((size_t)B & 15) == 0 && (kbeg & 3) == 0;
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; i++)
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc[i][j] = 0.f;
+  float ra[8], rb[8];
+  /* element e of a 128 x 16 operand tile handled by this thread: k-fast operands are walked (row, 4 k's) per float4,
+   * row-fast operands (row contiguous in memory) are walked with consecutive threads on consecutive rows */
+  auto load_tile = [&](int k0) {
+    if (a_vec) {
+#pragma unroll
+      for (int i = 0; i < 2; i++) {
+        const int q = tid + i * 256, m = q >> 2, k = (q & 3) * 4, gm = m0 + m, gk = k0 + k;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gm < M) {
+          if (gk + 3 < kend) v = *reinterpret_cast<const float4 *>(A + gm * sam + gk);
+          else { if (gk < kend) v.x = A[gm * sam + gk]; if (gk + 1 < kend) v.y = A[gm * sam + gk + 1]; if (gk + 2 < kend) v.z = A[gm * sam + gk + 2]; }
+        }
+        ra[4 * i] = v.x; ra[4 * i + 1] = v.y; ra[4 * i + 2] = v.z; ra[4 * i + 3] = v.w;
+      }
+    } else {
+      const bool kfast = sak == 1;
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const int e = tid + i * 256;
+        int m, k;
+        if (kfast) { k = e & (LK - 1); m = e >> 4; } else { m = e & (LM - 1); k = e >> 7; }
+        const int gm = m0 + m, gk = k0 + k;
+        ra[i] = (gm < M && gk < kend) ? A[gm * sam + gk * sak] : 0.f;
+      }
+    }
+    if (b_vec) {
+#pragma unroll
+      for (int i = 0; i < 2; i++) {
+        const int q = tid + i * 256, n = q >> 2, k = (q & 3) * 4, gn = n0 + n, gk = k0 + k;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gn < N) {
+          if (gk + 3 < kend) v = *reinterpret_cast<const float4 *>(B + gn * sbn + gk);
+          else { if (gk < kend) v.x = B[gn * sbn + gk]; if (gk + 1 < kend) v.y = B[gn * sbn + gk + 1]; if (gk + 2 < kend) v.z = B[gn * sbn + gk + 2]; }
+        }
+        rb[4 * i] = v.x; rb[4 * i + 1] = v.y; rb[4 * i + 2] = v.z; rb[4 * i + 3] = v.w;
+      }
+    } else {
+      const bool nfast = sbn == 1;
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const int e = tid + i * 256;
+        int n, k;
+        if (nfast) { n = e & (LN - 1); k = e >> 7; } else { k = e & (LK - 1); n = e >> 4; }
+        const int gn = n0 + n, gk = k0 + k;
+        rb[i] = (gn < N && gk < kend) ? B[gk * sbk + gn * sbn] : 0.f;
+      }
+    }
+  };
+  auto store_tile = [&]() {
+    if (a_vec) {
+#pragma unroll
+      for (int i = 0; i < 2; i++) {
+        const int q = tid + i * 256, m = q >> 2, k = (q & 3) * 4;
+        As[k][m] = ra[4 * i]; As[k + 1][m] = ra[4 * i + 1]; As[k + 2][m] = ra[4 * i + 2]; As[k + 3][m] = ra[4 * i + 3];
+      }
+    } else {
+      const bool kfast = sak == 1;
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const int e = tid + i * 256;
+        int m, k;
+        if (kfast) { k = e & (LK - 1); m = e >> 4; } else { m = e & (LM - 1); k = e >> 7; }
+        As[k][m] = ra[i];
+      }
+    }
+    if (b_vec) {
+#pragma unroll
+      for (int i = 0; i < 2; i++) {
+        const int q = tid + i * 256, n = q >> 2, k = (q & 3) * 4;
+        Bs[k][n] = rb[4 * i]; Bs[k + 1][n] = rb[4 * i + 1]; Bs[k + 2][n] = rb[4 * i + 2]; Bs[k + 3][n] = rb[4 * i + 3];
+      }
+    } else {
+      const bool nfast = sbn == 1;
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const int e = tid + i * 256;
+        int n, k;
+        if (nfast) { n = e & (LN - 1); k = e >> 7; } else { k = e & (LK - 1); n = e >> 4; }
+        Bs[k][n] = rb[i];
+      }
+    }
+  };
+  if (kbeg < kend) load_tile(kbeg);
+  for (int k0 = kbeg; k0 < kend; k0 += LK) {
+    store_tile();
+    __syncthreads();
+    if (k0 + LK < kend) load_tile(k0 + LK); /* in flight while the FMAs below run */
+#pragma unroll
+    for (int k = 0; k < LK; k++) {
+      /* thread (ty, tx) owns rows ty*4..+3 and 64+ty*4..+3, columns tx*4..+3 and 64+tx*4..+3: conflict-free float4 reads */
+      const float4 a0 = *reinterpret_cast<const float4 *>(&As[k][ty * 4]), a1 = *reinterpret_cast<const float4 *>(&As[k][64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4 *>(&Bs[k][tx * 4]), b1 = *reinterpret_cast<const float4 *>(&Bs[k][64 + tx * 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  const bool atomic = accumulate || gridDim.z > 1;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const int gm = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + i - 4);
+    if (gm >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const int gn = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + j - 4);
+      if (gn >= N) continue;
+      float v = acc[i][j];
+      if (bias && blockIdx.z == 0) v += bias[gn];
+      if (relu) v = fmaxf(v, 0.f);
+      if (mask) v = mask[gm * smm + gn * smn] > 0.f ? v : 0.f;
+      if (atomic) atomicAdd(&C[gm * scm + gn * scn], v); else C[gm * scm + gn * scn] = v;
+    }
+  }
+}
+
+int apex_gemm_large_tiles = 1; /* test hook: 0 forces the 64 x 64 kernel everywhere */
+extern "C" void apex_set_gemm_large_tiles(int on) { apex_gemm_large_tiles = on; }
+
 static int gemm(int M, int N, int K, const float *A, long sam, long sak, const float *B, long sbk, long sbn, float *C, long scm,
                 long scn, const float *bias, int relu, const float *mask, long smm, long smn, int accumulate, int splits,
                 cudaStream_t s) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   if (splits < 1) splits = 1;
+  if (apex_gemm_large_tiles && M >= 128 && N >= 128) {
+    int kchunk = ((K + splits - 1) / splits + LK - 1) / LK * LK;
+    splits = (K + kchunk - 1) / kchunk;
+    dim3 grid((N + LN - 1) / LN, (M + LM - 1) / LM, splits);
+    k_gemm128<<<grid, 256, 0, s>>>(M, N, K, A, sam, sak, B, sbk, sbn, C, scm, scn, bias, relu, mask, smm, smn, accumulate, kchunk);
+    return last_err();
+  }
   int kchunk = ((K + splits - 1) / splits + BK - 1) / BK * BK;
   splits = (K + kchunk - 1) / kchunk;
   dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, splits);

@@ -65,8 +65,11 @@ int apex_cassie_env_order(const int *sti, int n, int *order, void *stream);
 int apex_cassie_env_step_ordered(int dtype, void *st, int *sti, int n, const void *action, void *obs, void *reward, int *done,
                                  void *term_obs, int max_traj_len, const int *active, const void *traj, int traj_rows,
                                  int traj_len, const int *order, void *stream);
-/* tuning: environments (warps) per CTA of the step kernel, 1..14 (default 7 = two CTAs of 7 envs per SM; float64 is capped at 7) */
+/* tuning: environments (warps) per CTA of the step kernel, 1..15 (default 14 = one CTA of 14 envs per SM; float64 is capped at 7) */
 void apex_cassie_set_warps_per_cta(int w);
+/* tuning / experiments: extra CTA barriers inside a sub-step (bits 0x100 after the factorization, 0x200 before the solver,
+ * 0x400 after it, 0x800 before the Euler solve); the barrier at the start of every sub-step is always on.  Default 0. */
+void apex_cassie_set_barrier_mask(int mask);
 /* one raw mj_step (no wrapper, no env logic) on the stored state with S_CTRL as control; test hook */
 int apex_cassie_mj_step(int dtype, void *st, int *sti, int n, int flags, void *stream);
 

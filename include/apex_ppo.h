@@ -73,6 +73,9 @@ int apex_ars_policy(const float *obs, int n, int S, int H, int A, const float *t
 int apex_ars_update(float *theta, int P, const float *noise, const int64_t *idx, const float *weight, int ndir, float coef,
                     void *stream);
 
+/* test hook: 0 routes every GEMM through the 64 x 64 tile kernel, 1 (default) uses the 128 x 128 one when M, N >= 128 */
+void apex_set_gemm_large_tiles(int on);
+
 #ifdef __cplusplus
 }
 #endif

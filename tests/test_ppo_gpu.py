@@ -194,3 +194,44 @@ def test_get_normalization_params_matches_numpy_statistics():
     assert states.shape == (64 * 6, 50)
     assert np.allclose(mean, states.mean(0), rtol=1e-5, atol=1e-5)
     assert np.allclose(std, np.sqrt(states.var(0) + 1e-8), rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("rows,in_dim,out_dim", [(1000, 50, 10), (4096, 60, 1), (777, 256, 10)])
+def test_mlp_kernels_large_tiles_match_float64(rows, in_dim, out_dim):
+    """apex_mlp_forward / apex_mlp_backward at sizes that take the 128 x 128 tile GEMM (rows >= 128; ragged row counts, the
+    k = 50 first layer that cannot use float4 loads, split-k weight gradients) against a float64 torch evaluation, and
+    against the 64 x 64 kernel on the same inputs."""
+    from apex_b200 import _capi
+    L = _capi.lib()
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(rows)
+    r = lambda *s: torch.randn(s, device=dev, generator=g, dtype=torch.float32)
+    H = 256
+    x, w1, b1, w2, b2, w3, b3 = r(rows, in_dim), r(H, in_dim) * 0.1, r(H) * 0.1, r(H, H) * 0.06, r(H) * 0.1, r(out_dim, H) * 0.06, r(out_dim)
+    dy = r(rows, out_dim)
+    p = lambda t: t.data_ptr()
+
+    def run(large):
+        L.apex_set_gemm_large_tiles(int(large))
+        h1, h2, y = torch.zeros(rows, H, device=dev), torch.zeros(rows, H, device=dev), torch.zeros(rows, out_dim, device=dev)
+        dh2, dh1 = torch.zeros(rows, H, device=dev), torch.zeros(rows, H, device=dev)
+        gs = [torch.zeros_like(t) for t in (w1, b1, w2, b2, w3, b3)]
+        _capi.check(L.apex_mlp_forward(p(x), rows, in_dim, H, out_dim, p(w1), p(b1), p(w2), p(b2), p(w3), p(b3), p(h1), p(h2), p(y),
+                                       None), "fwd")
+        _capi.check(L.apex_mlp_backward(p(x), rows, in_dim, H, out_dim, p(w2), p(w3), p(h1), p(h2), p(dy), p(dh2), p(dh1),
+                                        *[p(t) for t in gs], None), "bwd")
+        torch.cuda.synchronize()
+        return [y] + gs
+    try:
+        big, small = run(True), run(False)
+    finally:
+        L.apex_set_gemm_large_tiles(1)
+    d = lambda t: t.double().requires_grad_(True)
+    X, W1, B1, W2, B2, W3, B3 = x.double(), d(w1), d(b1), d(w2), d(b2), d(w3), d(b3)
+    Y = torch.relu(torch.relu(X @ W1.T + B1) @ W2.T + B2) @ W3.T + B3
+    Y.backward(dy.double())
+    ref = [Y.detach(), W1.grad, B1.grad, W2.grad, B2.grad, W3.grad, B3.grad]
+    for name, a, b, c in zip(("y", "gw1", "gb1", "gw2", "gb2", "gw3", "gb3"), big, small, ref):
+        scale = float(c.abs().max()) + 1e-12
+        assert float((a.double() - c).abs().max()) < 2e-5 * scale, (name, "128-tile vs float64")
+        assert float((b.double() - c).abs().max()) < 2e-5 * scale, (name, "64-tile vs float64")
