@@ -240,6 +240,10 @@ static int gemm(int M, int N, int K, const float *A, long sam, long sak, const f
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   if (splits < 1) splits = 1;
   if (apex_gemm_large_tiles && M >= 128 && N >= 128) {
+    if (splits > 1) { /* split-k: about one wave of CTAs; every extra split is another atomicAdd per output element */
+      const int tiles = ((N + LN - 1) / LN) * ((M + LM - 1) / LM);
+      splits = max(1, min(splits, (2 * 148 + tiles - 1) / tiles));
+    }
     int kchunk = ((K + splits - 1) / splits + LK - 1) / LK * LK;
     splits = (K + kchunk - 1) / kchunk;
     dim3 grid((N + LN - 1) / LN, (M + LM - 1) / LM, splits);
@@ -258,9 +262,14 @@ __global__ void k_colsum(int M, int N, const float *__restrict__ X, float *__res
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   const int mb = blockIdx.y * rows_per_block, me = min(M, mb + rows_per_block);
-  float s = 0.f;
-  for (int m = mb; m < me; m++) s += X[(long)m * N + n];
-  atomicAdd(&out[n], s);
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f; /* four independent loads in flight per thread: the kernel is a pure HBM stream */
+  int m = mb;
+  for (; m + 4 <= me; m += 4) {
+    const float *r = X + (long)m * N + n;
+    s0 += r[0]; s1 += r[N]; s2 += r[2L * N]; s3 += r[3L * N];
+  }
+  for (; m < me; m++) s0 += X[(long)m * N + n];
+  atomicAdd(&out[n], (s0 + s1) + (s2 + s3));
 }
 
 /* ===================================================================================================
@@ -284,7 +293,7 @@ extern "C" int apex_mlp_backward(const float *x, int rows, int in_dim, int hid, 
   cudaStream_t s = (cudaStream_t)stream;
   int rc;
   const int splits = 148; /* the weight gradients reduce over `rows`: split that dimension across the SMs */
-  const int rpb = 512;
+  const int rpb = 64;
   /* layer 3: gW3[o, k] += sum_r dy[r, o] h2[r, k];  dh2 = (dy W3) * (h2 > 0) */
   if ((rc = gemm(out_dim, hid, rows, dy, 1, out_dim, h2, hid, 1, gw3, hid, 1, nullptr, 0, nullptr, 0, 0, 1, splits, s))) return rc;
   k_colsum<<<dim3((out_dim + 63) / 64, (rows + rpb - 1) / rpb), 64, 0, s>>>(rows, out_dim, dy, gb3, rpb);
