@@ -423,6 +423,7 @@ template <typename T, int NF> CW_NOINL void cw_factor(CassieWs<T> &w, T hdamp CW
   }
   /* the two legs are independent sub-trees hanging off the 6 base dofs: eliminate dof 6+s and 19+s together.
    * Ancestors in increasing dof order are in root-to-leaf order, so the t-th set bit of a chain mask has rank 6 + t. */
+#pragma unroll
   for (int s = 12; s >= 0; s--) {
     const int kL = 6 + s, kR = 19 + s;
     const unsigned legmask = CM_leg_ancmask[s];
@@ -499,6 +500,7 @@ template <typename T, int NF> CW_NOINL void cw_factor(CassieWs<T> &w, T hdamp CW
 
 /* v <- L^-T v (in place, shared vector); Ms / Dinv select the factor */
 template <typename T> CW_NOINL void cw_solve_LT(const T *Ms, const T *Dinv, T *v CW_LANE_PARAM) {
+#pragma unroll /* k becomes a literal: the ancestor mask and the row offset fold into immediates instead of two table loads per phase */
   for (int k = CW_NV - 1; k >= 1; k--) {
     const unsigned mask = CM_dof_ancmask[k];
     const T vk = v[k] * Dinv[k];
@@ -767,11 +769,17 @@ template <typename T> CW_FN void cw_project(CassieWs<T> &w CW_LANE_PARAM) {
     if (c < n) {
       T bs[CW_NV];
       for (int i = 0; i < CW_NV; i++) bs[i] = w.u.J[c][i] * w.Dinv[i];
-      for (int rr = 0; rr <= c; rr++) {
+      /* A is symmetric: lane c computes the entries (c, c), (c, c-1), ... for n/2 + 1 rows, wrapping around — every unordered
+       * pair is covered exactly once and all lanes do the same amount of work (within one row), half the longest row
+       * of the triangle.  The lanes read different rows of J: row stride 33 words keeps that conflict-free. */
+      const int h = n / 2 + ((n & 1) || c >= n / 2 ? 1 : 0); /* even n: the upper lane of an antipodal pair computes it */
+      for (int t = 0; t < h; t++) {
+        int rr = c - t;
+        if (rr < 0) rr += n;
         T s = 0;
         for (int i = 0; i < CW_NV; i++) s += w.u.J[rr][i] * bs[i];
-        if (rr == c) { s += w.efc_R[c]; w.efc_dinv[c] = (T)1 / s; }
-        w.Ap[c * (c + 1) / 2 + rr] = s;
+        if (t == 0) { s += w.efc_R[c]; w.efc_dinv[c] = (T)1 / s; }
+        w.Ap[cw_tri(c, rr)] = s;
       }
     }
   }
