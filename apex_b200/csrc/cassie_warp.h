@@ -462,6 +462,7 @@ template <typename T, int NF> CW_NOINL void cw_factor(CassieWs<T> &w, T hdamp CW
       const int j = rem;
       T acc[NF];
       for (int f = 0; f < NF; f++) acc[f] = 0;
+#pragma unroll
       for (int k = 6; k < CW_NV; k++) {
         const int ok = CM_dof_rowptr[k];
         acc[0] += Mp[0][ok + i] * Mp[0][ok + j] * w.Dinv[k];
@@ -471,6 +472,7 @@ template <typename T, int NF> CW_NOINL void cw_factor(CassieWs<T> &w, T hdamp CW
     }
   }
   CW_SYNC();
+#pragma unroll
   for (int k = 5; k >= 1; k--) {
     T d[NF];
     for (int f = 0; f < NF; f++) d[f] = cw_rcp(Dp[f][k]);
@@ -511,6 +513,7 @@ template <typename T> CW_NOINL void cw_solve_LT(const T *Ms, const T *Dinv, T *v
 }
 /* v <- L^-1 v: every dof has exactly one ancestor per depth, so 13 level sweeps suffice */
 template <typename T> CW_NOINL void cw_solve_L(const T *Ms, const T *Dinv, T *v CW_LANE_PARAM) {
+#pragma unroll
   for (int lvl = 0; lvl < CM_MAXANC; lvl++) {
     CW_FOR_LANES {
       if (CM_dof_nanc[lane] > lvl) { const int j = CM_dof_anc[lane][lvl]; v[lane] -= Ms[CM_dof_rowptr[lane] + lvl] * Dinv[lane] * v[j]; }
@@ -639,6 +642,7 @@ template <typename T> CW_FN void cw_make_constraint(CassieWs<T> &w, const T *qpo
   int r = 0;
   const T org[3] = {w.xpos[1][0], w.xpos[1][1], w.xpos[1][2]};
   if (!(flags & 1)) {
+#pragma unroll
     for (int e = 0; e < CM_NEQ; e++) {
       const int b1 = CM_eq_body1[e], b2 = CM_eq_body2[e];
       T a1[3] = {(T)CMT(eq_anchor1)[e][0], (T)CMT(eq_anchor1)[e][1], (T)CMT(eq_anchor1)[e][2]};
@@ -666,6 +670,7 @@ template <typename T> CW_FN void cw_make_constraint(CassieWs<T> &w, const T *qpo
         crows += nrow; nckeep++;
       }
     /* joint limits */
+#pragma unroll
     for (int l = 0; l < 16; l++) {
       const int j = CW_LIM_JNT[l];
       const T q = qpos[CM_jnt_qposadr[j]];
