@@ -1020,21 +1020,25 @@ template <typename T> CW_NOINL void cw_mj_step(CassieWs<T> &w, bool integrate, i
       T res0 = sacc + b0;
       if (cost > 0) { f0 = 0; res0 = b0; }
       for (int it = 0; it < CM_ITERATIONS; it++) {
-        T imp = 0;
+        /* every lane evaluates its candidate at every row step; what it saw at its OWN step (new force, residual before
+         * the update) is captured by two selects and applied once per sweep */
+        T nf_own = f0, res_own = 0;
 #pragma unroll
         for (int i0 = 0; i0 < CW_NEFC; i0 += 4) {
           if (i0 >= n) break; /* tested once per 4 rows: a row >= n has di0 = 0 and a zero column, so its update is exactly 0 */
 #pragma unroll
           for (int i = i0; i < i0 + 4; i++) {
             const T nf = cw_max(f0 - res0 * di0, lb0);
-            const T dlo = nf - f0;
-            const T dl = __shfl_sync(0xffffffffu, dlo, i);
+            const T dl = __shfl_sync(0xffffffffu, nf - f0, i);
             const bool own = lane == i;
-            imp = own ? imp - dl * (dl * had0 + res0) : imp;
-            f0 = own ? nf : f0;
+            nf_own = own ? nf : nf_own;
+            res_own = own ? res0 : res_own;
             res0 += dl * acol[i];
           }
         }
+        const T dlo = nf_own - f0;
+        T imp = -dlo * (dlo * had0 + res_own);
+        f0 = nf_own;
         for (int o = 16; o > 0; o >>= 1) imp += __shfl_xor_sync(0xffffffffu, imp, o);
         iters = it + 1;
         if (imp * scale < (T)1e-8) break;
@@ -1117,8 +1121,10 @@ template <typename T> CW_NOINL void cw_mj_step(CassieWs<T> &w, bool integrate, i
   CW_FOR_LANES {
     const int j = lane;
     T s = w.vec[V_G][j];
-    for (int i = j + 1; i < CW_NV; i++)
-      if ((CM_dof_ancmask[i] >> j) & 1u) s += w.Ms[CM_dof_rowptr[i] + CM_dof_nanc[j]] * w.Dinv[i] * w.vec[V_G][i];
+    const int nj = CM_dof_nanc[j];
+#pragma unroll
+    for (int i = 1; i < CW_NV; i++) /* i is a literal after unrolling: mask and row offset are immediates; j is never its own ancestor */
+      if ((CM_dof_ancmask[i] >> j) & 1u) s += w.Ms[CM_dof_rowptr[i] + nj] * w.Dinv[i] * w.vec[V_G][i];
     w.vec[V_TMP][j] = s + w.vec[V_SMOOTH][j];
   }
   CW_SYNC();
