@@ -1020,9 +1020,9 @@ template <typename T> CW_NOINL void cw_mj_step(CassieWs<T> &w, bool integrate, i
       T res0 = sacc + b0;
       if (cost > 0) { f0 = 0; res0 = b0; }
       for (int it = 0; it < CM_ITERATIONS; it++) {
-        /* every lane evaluates its candidate at every row step; what it saw at its OWN step (new force, residual before
-         * the update) is captured by two selects and applied once per sweep */
-        T nf_own = f0, res_own = 0;
+        /* every lane evaluates its candidate at every row step; the residual it saw at its OWN step is captured by one
+         * select, and the row's new force / cost improvement are recomputed from it once per sweep */
+        T res_own = 0;
 #pragma unroll
         for (int i0 = 0; i0 < CW_NEFC; i0 += 4) {
           if (i0 >= n) break; /* tested once per 4 rows: a row >= n has di0 = 0 and a zero column, so its update is exactly 0 */
@@ -1031,11 +1031,11 @@ template <typename T> CW_NOINL void cw_mj_step(CassieWs<T> &w, bool integrate, i
             const T nf = cw_max(f0 - res0 * di0, lb0);
             const T dl = __shfl_sync(0xffffffffu, nf - f0, i);
             const bool own = lane == i;
-            nf_own = own ? nf : nf_own;
             res_own = own ? res0 : res_own;
             res0 += dl * acol[i];
           }
         }
+        const T nf_own = cw_max(f0 - res_own * di0, lb0); /* same expression, same operands as at the own step */
         const T dlo = nf_own - f0;
         T imp = -dlo * (dlo * had0 + res_own);
         f0 = nf_own;
