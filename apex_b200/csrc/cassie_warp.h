@@ -372,6 +372,23 @@ template <typename T> CW_FN void cw_kinematics(CassieWs<T> &w, const T *qpos CW_
 
 /* composite inertia (mj_crb): parents gather children, deepest level first; then M (lane = dof) */
 template <typename T> CW_FN void cw_crb(CassieWs<T> &w CW_LANE_PARAM) {
+#ifdef __CUDACC__
+  {
+    const int my_level = lane < CW_NB ? CM_body_level[lane] : -1, nc = lane < CW_NB ? CM_body_nchild[lane] : 0;
+    const int c0 = nc > 0 ? CM_body_child[lane][0] : 0, c1 = nc > 1 ? CM_body_child[lane][1] : 0, c2 = nc > 2 ? CM_body_child[lane][2] : 0;
+#pragma unroll
+    for (int lvl = CM_MAXLEVEL - 1; lvl >= 1; lvl--) {
+      if (my_level == lvl && nc > 0) {
+        T acc[10];
+        for (int k = 0; k < 10; k++) acc[k] = w.crb[lane][k] + w.crb[c0][k];
+        if (nc > 1) for (int k = 0; k < 10; k++) acc[k] += w.crb[c1][k];
+        if (nc > 2) for (int k = 0; k < 10; k++) acc[k] += w.crb[c2][k];
+        for (int k = 0; k < 10; k++) w.crb[lane][k] = acc[k];
+      }
+      CW_SYNC();
+    }
+  }
+#else
   for (int lvl = CM_MAXLEVEL - 1; lvl >= 1; lvl--) {
     CW_FOR_LANES {
       if (lane < CW_NB && CM_body_level[lane] == lvl) {
@@ -387,6 +404,7 @@ template <typename T> CW_FN void cw_crb(CassieWs<T> &w CW_LANE_PARAM) {
     }
     CW_SYNC();
   }
+#endif
 }
 /* M from the composite inertias (lane = dof): diagonal in Mdiag, ancestors' entries in the sparse rows */
 template <typename T> CW_FN void cw_build_M(CassieWs<T> &w CW_LANE_PARAM) {
@@ -794,29 +812,50 @@ template <typename T> CW_FN void cw_project(CassieWs<T> &w CW_LANE_PARAM) {
  * 6-vectors (two lanes are busy on most levels: one body per leg); everything heavy — cdof_dot for all 32 dofs, the body
  * wrench I a + v x* (I v) for all 26 bodies — is hoisted out of them and runs once at full width. */
 template <typename T> CW_FN void cw_rne(CassieWs<T> &w, const T *qvel CW_LANE_PARAM) {
-  /* pass 1 (down): cvel[b] = cvel[parent] + sum over b's dofs of cdof * qvel */
+  /* pass 1 (down): cvel[b] = cvel[parent] + sum over b's dofs of cdof * qvel.  The joint's own contribution is formed for
+   * all bodies at once and stays in the lane's registers; the level loop only adds the parent's value. */
+  T jv[6] = {0, 0, 0, 0, 0, 0};
+  int my_level = -1, my_parent = 0;
   CW_FOR_LANES {
     if (lane == 0) {
       for (int k = 0; k < 6; k++) { w.u.p.cvel[0][k] = 0; w.u.p.cacc[0][k] = 0; }
       w.u.p.cacc[0][5] = (T)(-CM_GRAVITY_Z);
     }
+#ifdef __CUDACC__
+    if (lane >= 1 && lane < CW_NB) {
+      my_level = CM_body_level[lane]; my_parent = CM_body_parent[lane];
+      const int da = CM_body_dofadr[lane], nd = CM_body_dofnum[lane];
+      for (int s = 0; s < nd; s++) {
+        const T qd = qvel[da + s];
+        for (int k = 0; k < 6; k++) jv[k] += w.cdof[da + s][k] * qd;
+      }
+    }
+#endif
   }
   CW_SYNC();
+#ifdef __CUDACC__
+#pragma unroll
+  for (int lvl = 1; lvl <= CM_MAXLEVEL; lvl++) {
+    if (my_level == lvl)
+      for (int k = 0; k < 6; k++) w.u.p.cvel[lane][k] = w.u.p.cvel[my_parent][k] + jv[k];
+    CW_SYNC();
+  }
+#else
   for (int lvl = 1; lvl <= CM_MAXLEVEL; lvl++) {
     CW_FOR_LANES {
       if (lane < CW_NB && CM_body_level[lane] == lvl) {
         const int b = lane, p = CM_body_parent[b], da = CM_body_dofadr[b], nd = CM_body_dofnum[b];
-        T v[6];
-        for (int k = 0; k < 6; k++) v[k] = w.u.p.cvel[p][k];
+        T v[6] = {0, 0, 0, 0, 0, 0};
         for (int s = 0; s < nd; s++) {
           const T qd = qvel[da + s];
           for (int k = 0; k < 6; k++) v[k] += w.cdof[da + s][k] * qd;
         }
-        for (int k = 0; k < 6; k++) w.u.p.cvel[b][k] = v[k];
+        for (int k = 0; k < 6; k++) w.u.p.cvel[b][k] = w.u.p.cvel[p][k] + v[k];
       }
     }
     CW_SYNC();
   }
+#endif
   /* pass 2 (lane = dof): cdof_dot = cvel_before_the_joint x cdof.  A joint's dofs all use the velocity before the joint
    * (mj_comVel treats a ball joint as one unit), which is the parent body's cvel — except on the pelvis, whose three
    * slides come one at a time (they add no angular velocity, so their own cdof_dot is exactly 0) before its ball joint,
@@ -833,22 +872,40 @@ template <typename T> CW_FN void cw_rne(CassieWs<T> &w, const T *qvel CW_LANE_PA
     for (int k = 0; k < 3; k++) { o[k] = t1[k]; o[3 + k] = t2[k] + t3[k]; }
   }
   CW_SYNC();
-  /* pass 3 (down): cacc[b] = cacc[parent] + sum cdof_dot * qvel (qacc = 0: bias forces) */
+  /* pass 3 (down): cacc[b] = cacc[parent] + sum cdof_dot * qvel (qacc = 0: bias forces), same scheme as pass 1 */
+#ifdef __CUDACC__
+  {
+    T ja[6] = {0, 0, 0, 0, 0, 0};
+    if (lane >= 1 && lane < CW_NB) {
+      const int da = CM_body_dofadr[lane], nd = CM_body_dofnum[lane];
+      for (int s = 0; s < nd; s++) {
+        const T qd = qvel[da + s];
+        for (int k = 0; k < 6; k++) ja[k] += w.u.p.cdd[da + s][k] * qd;
+      }
+    }
+#pragma unroll
+    for (int lvl = 1; lvl <= CM_MAXLEVEL; lvl++) {
+      if (my_level == lvl)
+        for (int k = 0; k < 6; k++) w.u.p.cacc[lane][k] = w.u.p.cacc[my_parent][k] + ja[k];
+      CW_SYNC();
+    }
+  }
+#else
   for (int lvl = 1; lvl <= CM_MAXLEVEL; lvl++) {
     CW_FOR_LANES {
       if (lane < CW_NB && CM_body_level[lane] == lvl) {
         const int b = lane, p = CM_body_parent[b], da = CM_body_dofadr[b], nd = CM_body_dofnum[b];
-        T a[6];
-        for (int k = 0; k < 6; k++) a[k] = w.u.p.cacc[p][k];
+        T a[6] = {0, 0, 0, 0, 0, 0};
         for (int s = 0; s < nd; s++) {
           const T qd = qvel[da + s];
           for (int k = 0; k < 6; k++) a[k] += w.u.p.cdd[da + s][k] * qd;
         }
-        for (int k = 0; k < 6; k++) w.u.p.cacc[b][k] = a[k];
+        for (int k = 0; k < 6; k++) w.u.p.cacc[b][k] = w.u.p.cacc[p][k] + a[k];
       }
     }
     CW_SYNC();
   }
+#endif
   /* pass 4 (lane = body): cfrc_body = I a + v x* (I v); w.crb still holds the per-body (not yet composite) inertia here */
   CW_FOR_LANES {
     if (lane >= 1 && lane < CW_NB) {
@@ -864,6 +921,23 @@ template <typename T> CW_FN void cw_rne(CassieWs<T> &w, const T *qvel CW_LANE_PA
   }
   CW_SYNC();
   /* pass 5 (up): parents gather their children's wrenches, deepest level first */
+#ifdef __CUDACC__
+  { /* child lists in registers, levels unrolled */
+    const int nc = lane < CW_NB ? CM_body_nchild[lane] : 0;
+    const int c0 = nc > 0 ? CM_body_child[lane][0] : 0, c1 = nc > 1 ? CM_body_child[lane][1] : 0, c2 = nc > 2 ? CM_body_child[lane][2] : 0;
+#pragma unroll
+    for (int lvl = CM_MAXLEVEL - 1; lvl >= 1; lvl--) {
+      if (my_level == lvl && nc > 0) {
+        T acc[6];
+        for (int k = 0; k < 6; k++) acc[k] = w.u.p.cfrc[lane][k] + w.u.p.cfrc[c0][k];
+        if (nc > 1) for (int k = 0; k < 6; k++) acc[k] += w.u.p.cfrc[c1][k];
+        if (nc > 2) for (int k = 0; k < 6; k++) acc[k] += w.u.p.cfrc[c2][k];
+        for (int k = 0; k < 6; k++) w.u.p.cfrc[lane][k] = acc[k];
+      }
+      CW_SYNC();
+    }
+  }
+#else
   for (int lvl = CM_MAXLEVEL - 1; lvl >= 1; lvl--) {
     CW_FOR_LANES {
       if (lane < CW_NB && CM_body_level[lane] == lvl) {
@@ -879,6 +953,7 @@ template <typename T> CW_FN void cw_rne(CassieWs<T> &w, const T *qvel CW_LANE_PA
     }
     CW_SYNC();
   }
+#endif
   CW_FOR_LANES { w.vec[V_BIAS][lane] = cw_dot6(w.cdof[lane], w.u.p.cfrc[CM_dof_body[lane]]); }
   CW_SYNC();
 }
