@@ -460,8 +460,11 @@ template <typename T, int NF> CW_NOINL void cw_factor(CassieWs<T> &w, T hdamp CW
           for (int f = 0; f < NF; f++) a[f] = Mp[f][ok + rank] * (rt ? dR[f] : dL[f]);
           for (int t = 0; t < 6; t++)
             for (int f = 0; f < NF; f++) Mp[f][ol + t] -= a[f] * Mp[f][ok + t];
-          for (int t = 6; t < rank; t++)
-            for (int f = 0; f < NF; f++) Mp[f][ol + t] -= a[f] * Mp[f][ok + t];
+          const int maxrank = 6 + __builtin_popcount(legmask); /* a literal once the phase loop is unrolled */
+#pragma unroll
+          for (int t = 6; t < 6 + 12; t++)
+            if (t < maxrank && t < rank)
+              for (int f = 0; f < NF; f++) Mp[f][ol + t] -= a[f] * Mp[f][ok + t];
           for (int f = 0; f < NF; f++) Dp[f][lane] -= a[f] * Mp[f][ok + rank];
         }
       }
