@@ -232,6 +232,8 @@ __global__ void __launch_bounds__(256) k_gemm128(int M, int N, int K, const floa
 }
 
 int apex_gemm_large_tiles = 1; /* test hook: 0 forces the 64 x 64 kernel everywhere */
+int apex_gemm_min_ctas = 148;   /* below one CTA per SM the 64 x 64 kernel (4x the CTAs) is the better fit: rollout-size GEMMs */
+extern "C" void apex_set_gemm_min_ctas(int n) { apex_gemm_min_ctas = n; }
 extern "C" void apex_set_gemm_large_tiles(int on) { apex_gemm_large_tiles = on; }
 
 static int gemm(int M, int N, int K, const float *A, long sam, long sak, const float *B, long sbk, long sbn, float *C, long scm,
@@ -239,7 +241,7 @@ static int gemm(int M, int N, int K, const float *A, long sam, long sak, const f
                 cudaStream_t s) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   if (splits < 1) splits = 1;
-  if (apex_gemm_large_tiles && M >= 128 && N >= 128) {
+  if (apex_gemm_large_tiles && M >= 128 && N >= 128 && (long)((M + LM - 1) / LM) * ((N + LN - 1) / LN) * splits >= apex_gemm_min_ctas) { /* enough 128-tiles to fill the SMs */
     if (splits > 1) { /* split-k: about one wave of CTAs; every extra split is another atomicAdd per output element */
       const int tiles = ((N + LN - 1) / LN) * ((M + LM - 1) / LM);
       splits = max(1, min(splits, (2 * 148 + tiles - 1) / tiles));

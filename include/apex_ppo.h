@@ -75,6 +75,8 @@ int apex_ars_update(float *theta, int P, const float *noise, const int64_t *idx,
 
 /* test hook: 0 routes every GEMM through the 64 x 64 tile kernel, 1 (default) uses the 128 x 128 one when M, N >= 128 */
 void apex_set_gemm_large_tiles(int on);
+/* tuning: minimum number of 128 x 128 tiles (x split-k) for the large-tile kernel to be chosen (default 148 = one per SM) */
+void apex_set_gemm_min_ctas(int n);
 
 #ifdef __cplusplus
 }

@@ -213,6 +213,7 @@ def test_mlp_kernels_large_tiles_match_float64(rows, in_dim, out_dim):
 
     def run(large):
         L.apex_set_gemm_large_tiles(int(large))
+        L.apex_set_gemm_min_ctas(1 if large else 148)
         h1, h2, y = torch.zeros(rows, H, device=dev), torch.zeros(rows, H, device=dev), torch.zeros(rows, out_dim, device=dev)
         dh2, dh1 = torch.zeros(rows, H, device=dev), torch.zeros(rows, H, device=dev)
         gs = [torch.zeros_like(t) for t in (w1, b1, w2, b2, w3, b3)]
@@ -226,6 +227,7 @@ def test_mlp_kernels_large_tiles_match_float64(rows, in_dim, out_dim):
         big, small = run(True), run(False)
     finally:
         L.apex_set_gemm_large_tiles(1)
+        L.apex_set_gemm_min_ctas(148)
     d = lambda t: t.double().requires_grad_(True)
     X, W1, B1, W2, B2, W3, B3 = x.double(), d(w1), d(b1), d(w2), d(b2), d(w3), d(b3)
     Y = torch.relu(torch.relu(X @ W1.T + B1) @ W2.T + B2) @ W3.T + B3
