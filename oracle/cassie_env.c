@@ -346,6 +346,7 @@ void ce_env_set_trajectory(ce_env_t *e, const double *table, int rows, int len) 
 void ce_batch_set_trajectory(ce_env_t *envs, int n, const double *table, int rows, int len) {
   for (int i = 0; i < n; i++) ce_env_set_trajectory(&envs[i], table, rows, len);
 }
+double ce_env_get_phase(const ce_env_t *e) { return e->phase; }
 void ce_env_set_command(ce_env_t *e, double speed, double side_speed, double phase) {
   e->speed = speed; e->side_speed = side_speed; e->phase = phase;
 }

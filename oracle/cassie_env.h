@@ -87,6 +87,7 @@ void ce_env_init(ce_env_t *e, uint32_t seed, uint32_t env_id, int dyn_rand);
 void ce_env_reset(ce_env_t *e, double *obs);
 void ce_env_set_trajectory(ce_env_t *e, const double *table, int rows, int len); /* switches the env to CassieTraj-v0 */
 void ce_batch_set_trajectory(ce_env_t *envs, int n, const double *table, int rows, int len);
+double ce_env_get_phase(const ce_env_t *e);
 void ce_env_set_command(ce_env_t *e, double speed, double side_speed, double phase); /* synthetic-input hook */
 void ce_env_step(ce_env_t *e, const double *action, double *obs, double *reward, int *done);
 void ce_env_obs(ce_env_t *e, double *obs);

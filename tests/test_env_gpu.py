@@ -158,3 +158,48 @@ def test_f32_and_f64_kernels_run_the_same_number_of_solver_sweeps():
         e32b.st.copy_(e64b.st.to(torch.float32)); e32b.sti.copy_(e64b.sti)
         e64b.step(act.to(e64b.device, torch.float64)); e32b.step(act.to(e32b.device))
     assert torch.equal(o32, e32b.obs)
+
+
+def test_reference_trained_policy_walks_on_the_gpu_kernel():
+    """Behavioural pin (SURVEY §8c item 3) on the product path: the reference's shipped policy (trained on the real MuJoCo stack;
+    weights in tests/golden/ref_policy_5k_retrain.npz) drives 96 float32 envs of the CUDA kernel at commanded speeds 0 .. 1.5 m/s
+    through apex_mlp_forward.  Nobody falls in 300 policy steps and every env walks at its commanded speed; the envs at 0.5 and
+    1.0 m/s end where the reference's own CassieEnv (over the oracle physics) ended."""
+    import os
+    from apex_b200 import _capi
+    from apex_b200.envs import BatchedCassieEnv
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_policy_5k_retrain.npz"))
+    dev = torch.device("cuda:0")
+    t = lambda k: torch.as_tensor(g[k], dtype=torch.float32, device=dev).contiguous()
+    w1, b1, w2, b2, w3, b3, mean, std = (t(k) for k in ("actor_layers.0.weight", "actor_layers.0.bias", "actor_layers.1.weight",
+                                                         "actor_layers.1.bias", "means.weight", "means.bias", "obs_mean", "obs_std"))
+    n = 96
+    env = BatchedCassieEnv(n, dtype=torch.float32, seed=3, dynamics_randomization=False, max_traj_len=0)
+    speed = torch.linspace(0.0, 1.5, n, device=dev)
+    speed[0], speed[1] = 0.5, 1.0
+    env.reset()
+    L = _capi.lib()
+    h1, h2, act = torch.zeros(n, 256, device=dev), torch.zeros(n, 256, device=dev), torch.zeros(n, 10, device=dev)
+    p = lambda x: x.data_ptr()
+    fallen = torch.zeros(n, dtype=torch.bool, device=dev)
+    obs = env.obs
+    for k in range(300):
+        env.set_command(speed=speed, side_speed=torch.zeros(n, device=dev))
+        if k == 0:
+            env.set_command(phase=torch.zeros(n, device=dev))
+        obs[:, 48] = speed  # the observation was written before the command override
+        obs[:, 49] = 0
+        x = ((obs[:, :49] - mean) / std).contiguous()
+        _capi.check(L.apex_mlp_forward(p(x), n, 49, 256, 10, p(w1), p(b1), p(w2), p(b2), p(w3), p(b3), p(h1), p(h2), p(act), None), "fwd")
+        obs, rew, done, _ = env.step(act)
+        fallen |= (done & 1).bool()
+    qpos = env.field("qpos", 35)
+    assert not bool(fallen.any()), fallen.nonzero().flatten().tolist()
+    assert bool(((qpos[:, 2] > 0.8) & (qpos[:, 2] < 1.1)).all())
+    walked, want = qpos[:, 0], speed * 300 * 0.025
+    sel = speed >= 0.3
+    assert float(((walked - want).abs() / want)[sel].max()) < 0.2, ((walked - want) / want)[sel]
+    runs = g["reference_env_runs"]
+    for i, v in ((0, 0.5), (1, 1.0)):
+        ref_x = float(runs[(runs[:, 0] == 50) & (runs[:, 1] == v)][0, 3])
+        assert abs(float(walked[i]) - ref_x) < 0.15 * ref_x, (v, float(walked[i]), ref_x)

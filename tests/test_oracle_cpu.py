@@ -324,3 +324,56 @@ def test_trajectory_loader_reads_the_reference_file():
     rows, n = load_trajectory("/root/reference/cassie/trajectory/stepdata.bin")
     table, tlen = _traj_table()
     assert n == tlen == 1682 and rows.shape == (34, 67) and np.array_equal(rows, table)
+
+
+def _ref_policy():
+    g = np.load(os.path.join(G, "ref_policy_5k_retrain.npz"))
+    W = [g["actor_layers.0.weight"], g["actor_layers.1.weight"], g["means.weight"]]
+    b = [g["actor_layers.0.bias"], g["actor_layers.1.bias"], g["means.bias"]]
+
+    def act(obs):  # Gaussian_FF_Actor.forward, deterministic (rl/policies/actor.py:186-203)
+        x = (np.asarray(obs[..., :49], dtype=np.float32) - g["obs_mean"]) / g["obs_std"]
+        x = np.maximum(x @ W[0].T + b[0], 0)
+        x = np.maximum(x @ W[1].T + b[1], 0)
+        return (x @ W[2].T + b[2]).astype(np.float64)
+    return act, g["reference_env_runs"]
+
+
+def test_reference_trained_policy_walks_in_the_oracle(L):
+    """Behavioural pin of the restated physics: the reference's own shipped policy
+    (trained_models/5k_retrain, trained on the real MuJoCo + Agility stack) must walk in the oracle env — 300 policy steps
+    without falling, at the commanded speed.  tests/golden/make_policy_golden.py recorded the same runs through the
+    reference's CassieEnv over the oracle ABI (x = 3.76 m after 300 steps at 0.5 m/s, simrate 50)."""
+    from tests.oracle_util import OracleEnv
+    act, runs = _ref_policy()
+    L.ce_env_set_command.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double]
+    for speed in (0.5, 1.0):
+        env = OracleEnv(False)
+        L.ce_env_reset(env.buf, dp(env.obs))
+        L.ce_env_set_command(env.buf, speed, 0.0, 0.0)
+        L.ce_env_obs(env.buf, dp(env.obs))
+        obs = env.obs.copy()
+        rew, done = C.c_double(0), C.c_int(0)
+        for t in range(300):
+            a = np.ascontiguousarray(act(obs))
+            L.ce_env_step(env.buf, dp(a), dp(env.obs), C.byref(rew), C.byref(done))
+            assert done.value == 0, (speed, t)
+            qpos, _ = env.qpos_qvel()
+            # hold the command: the env redraws it with small probability (cassie.py:483-491)
+            _set_speed(L, env, speed)
+            L.ce_env_obs(env.buf, dp(env.obs))
+            obs = env.obs.copy()
+        ref_x = float(runs[(runs[:, 0] == 50) & (runs[:, 1] == speed)][0, 3])
+        assert 0.8 < qpos[2] < 1.1, (speed, qpos[2])
+        assert abs(qpos[0] - speed * 7.5) < 0.2 * speed * 7.5, (speed, qpos[0])      # 300 steps x 25 ms at the commanded speed
+        assert abs(qpos[0] - ref_x) < 0.15 * ref_x, (speed, qpos[0], ref_x)          # and what the reference's own env logic gave
+
+
+def _set_speed(L, env, speed):
+    """speed / side_speed live right behind phase .. in ce_env_t; use the env's own hook with the current phase."""
+    import ctypes
+    from oracle import phys_ctypes as P
+    # ce_env_set_command(speed, side_speed, phase) overwrites the phase too: read it back first
+    L.ce_env_get_phase.restype = ctypes.c_double
+    ph = L.ce_env_get_phase(env.buf)
+    L.ce_env_set_command(env.buf, speed, 0.0, ph)
