@@ -66,6 +66,9 @@ def lib():
         for f in (L.apex_mlp_backward_dx, L.apex_replay_gather, L.apex_td3_action, L.apex_td3_critic_loss, L.apex_td3_actor_grad,
                   L.apex_polyak):
             f.restype = i
+        L.apex_tc_linear_forward.argtypes = [vp, i, i, vp, vp, i, i, vp, vp]
+        L.apex_mlp_forward_bf16.argtypes = [vp, i, i, i, i, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+        L.apex_tc_linear_forward.restype = L.apex_mlp_forward_bf16.restype = i
         L.apex_set_gemm_large_tiles.argtypes = [i]
         L.apex_set_gemm_large_tiles.restype = None
         L.apex_col_moments.argtypes = [vp, i, i, vp, vp]

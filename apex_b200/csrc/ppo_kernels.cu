@@ -289,6 +289,21 @@ extern "C" int apex_mlp_forward(const float *x, int rows, int in_dim, int hid, i
   return 0;
 }
 
+/* Same network, hidden 256 x 256 layer on the tensor cores (bf16 operands, float32 accumulate; csrc/tc_linear.cu).  The first
+ * layer (k = in_dim, not a multiple of 64) and the narrow head stay on the SIMT kernels.  Opt-in: precision = "bf16". */
+extern "C" int apex_tc_linear_forward(const float *x, int M, int K, const float *w, const float *bias, int N, int relu, float *y,
+                                      void *stream);
+extern "C" int apex_mlp_forward_bf16(const float *x, int rows, int in_dim, int hid, int out_dim, const float *w1, const float *b1,
+                                     const float *w2, const float *b2, const float *w3, const float *b3, float *h1, float *h2,
+                                     float *y, void *stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc;
+  if ((rc = gemm(rows, hid, in_dim, x, in_dim, 1, w1, 1, in_dim, h1, hid, 1, b1, 1, nullptr, 0, 0, 0, 1, s))) return rc;
+  if ((rc = apex_tc_linear_forward(h1, rows, hid, w2, b2, hid, 1, h2, stream))) return rc;
+  if ((rc = gemm(rows, out_dim, hid, h2, hid, 1, w3, 1, hid, y, out_dim, 1, b3, 0, nullptr, 0, 0, 0, 1, s))) return rc;
+  return 0;
+}
+
 extern "C" int apex_mlp_backward(const float *x, int rows, int in_dim, int hid, int out_dim, const float *w2, const float *w3,
                                  const float *h1, const float *h2, const float *dy, float *dh2, float *dh1, float *gw1, float *gb1,
                                  float *gw2, float *gb2, float *gw3, float *gb3, void *stream) {

@@ -1,0 +1,160 @@
+/* Hidden-layer GEMM on the 5th-generation tensor cores (sm_100a): y = act(x W^T + b) with bf16 operands and float32
+ * accumulation in tensor memory — the opt-in reduced-precision path for BASELINE config "PPO CassieTraj-v0 ... bf16"
+ * (the default learner stays float32 SIMT because the reference computes in float32, rl/policies/actor.py:142-215).
+ *
+ * Shape: one CTA per 128 rows of x; the whole weight matrix W [N <= 256, K] is the B operand, so the accumulator is a
+ * 128 x N float32 tile = N tensor-memory columns.  Per 64-wide k tile the CTA converts x and W (stored float32, row-major =
+ * K-major for both operands) to bf16 while staging them in shared memory in the canonical no-swizzle K-major layout
+ * (8 x 16-byte core matrices; LBO = 128 B between the k halves, SBO = 1024 B between 8-row groups), then ONE thread issues
+ * four tcgen05.mma.cta_group::1.kind::f16 (M = 128, N, K = 16) and commits them to an mbarrier; the epilogue reads the
+ * accumulator back with tcgen05.ld.32x32b (warp w owns TMEM lanes 32w .. 32w+31 = rows), adds the bias, applies ReLU and
+ * stores float32.  Single-stage on purpose (round 1): correctness and the descriptor plumbing first; TMA staging, a
+ * multi-stage ring and a fused layer-1/2/3 kernel are listed in DESIGN.md §6.
+ */
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+#define TC_M 128
+#define TC_KT 64 /* k elements per staged tile: 8 core matrices of 8 bf16 */
+#define TC_LBO 128
+#define TC_SBO 1024
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t addr) { /* cute::UMMA::SmemDescriptor, SWIZZLE_NONE, version 1 */
+  const uint64_t lo = (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((TC_LBO >> 4) & 0x3FFF) << 16);
+  const uint64_t hi = (uint64_t)((TC_SBO >> 4) & 0x3FFF) | (1ull << 14);
+  return lo | (hi << 32);
+}
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  } while (!ok);
+}
+
+/* 8 consecutive float32 -> 8 bf16 packed in 16 bytes */
+__device__ __forceinline__ uint4 pack8(const float4 a, const float4 b) {
+  __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x, a.y), p1 = __floats2bfloat162_rn(a.z, a.w);
+  __nv_bfloat162 p2 = __floats2bfloat162_rn(b.x, b.y), p3 = __floats2bfloat162_rn(b.z, b.w);
+  uint4 r;
+  r.x = *reinterpret_cast<uint32_t *>(&p0); r.y = *reinterpret_cast<uint32_t *>(&p1);
+  r.z = *reinterpret_cast<uint32_t *>(&p2); r.w = *reinterpret_cast<uint32_t *>(&p3);
+  return r;
+}
+
+/* stage `rows` x 64 float32 (row stride ld) as bf16 core matrices; rows beyond `valid` are zero */
+__device__ __forceinline__ void stage_tile(unsigned char *dst, const float *src, long ld, int rows, int valid, int tid, int nthreads) {
+  for (int q = tid; q < rows * 8; q += nthreads) { /* q -> (row, 8-element k chunk); consecutive threads walk a row: coalesced */
+    const int r = q >> 3, c = q & 7;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (r < valid) {
+      const float4 *p = reinterpret_cast<const float4 *>(src + (long)r * ld + c * 8);
+      v = pack8(p[0], p[1]);
+    }
+    *reinterpret_cast<uint4 *>(dst + (r >> 3) * TC_SBO + c * TC_LBO + (r & 7) * 16) = v;
+  }
+}
+
+template <int N>
+__global__ void __launch_bounds__(128) k_tc_linear(const float *__restrict__ x, int M, int K, const float *__restrict__ w,
+                                                   const float *__restrict__ bias, int relu, float *__restrict__ y) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char *sA = smem, *sB = smem + TC_M * TC_KT * 2;
+  __shared__ __align__(8) uint64_t mbar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.x * TC_M, valid = min(TC_M, M - m0);
+  const uint32_t bar = smem_u32(&mbar);
+  if (warp == 0) { /* one warp allocates N tensor-memory columns and publishes the base address */
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base_s)), "r"(N));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_base_s;
+  /* cute::UMMA::InstrDescriptor: D = F32 (bits 4-5 = 1), A = B = BF16 (bits 7-9, 10-12 = 1), both K-major, N >> 3 at 17, M >> 4 at 24 */
+  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+  uint32_t parity = 0;
+  for (int k0 = 0; k0 < K; k0 += TC_KT) {
+    stage_tile(sA, x + (long)m0 * K + k0, K, TC_M, valid, tid, 128);
+    stage_tile(sB, w + k0, K, N, N, tid, 128);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); /* generic-proxy stores -> visible to the tensor core (async proxy) */
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
+#pragma unroll
+      for (int kk = 0; kk < TC_KT / 16; kk++) { /* K = 16 per instruction = two core matrices along k */
+        const uint64_t da = tc_smem_desc(a0 + kk * 2 * TC_LBO), db = tc_smem_desc(b0 + kk * 2 * TC_LBO);
+        const uint32_t acc = (k0 > 0 || kk > 0) ? 1u : 0u;
+        asm volatile("{ .reg .pred p; setp.ne.b32 p, %4, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p; }"
+                     :: "r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+      }
+      /* arrives on the mbarrier when the MMAs above have completed (implies tcgen05.fence::before_thread_sync) */
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+    }
+    mbar_wait(bar, parity); /* every thread: the staged tile may be overwritten / the accumulator read after this */
+    parity ^= 1;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  }
+  /* epilogue: warp w reads TMEM lanes 32w .. 32w+31 (= rows), 8 columns per tcgen05.ld */
+  const int row = m0 + warp * 32 + lane;
+  const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+  for (int c = 0; c < N; c += 8) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr + (uint32_t)c));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    if (row < M) {
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        v[j] = __uint_as_float(r[j]) + (bias ? bias[c + j] : 0.f);
+        if (relu) v[j] = fmaxf(v[j], 0.f);
+      }
+      float4 *o = reinterpret_cast<float4 *>(y + (long)row * N + c);
+      o[0] = make_float4(v[0], v[1], v[2], v[3]);
+      o[1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(N));
+}
+
+extern "C" {
+
+/* y [M, N] = act(x [M, K] W^T + b), W [N, K] row-major (torch Linear), bf16 operands / float32 accumulate on tcgen05.
+ * Supported: N in {64, 128, 256}, K a multiple of 64, 16-byte aligned pointers.  Returns -1000 for anything else. */
+int apex_tc_linear_forward(const float *x, int M, int K, const float *w, const float *bias, int N, int relu, float *y, void *stream) {
+  if (M <= 0) return 0;
+  if (!x || !w || !y || K % TC_KT != 0 || (((size_t)x | (size_t)w | (size_t)y) & 15)) return -1000;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int grid = (M + TC_M - 1) / TC_M;
+  cudaError_t err;
+#define TC_LAUNCH(NN)                                                                                        \
+  {                                                                                                          \
+    const int smem = (TC_M + NN) * TC_KT * 2;                                                                \
+    err = cudaFuncSetAttribute(k_tc_linear<NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);          \
+    if (err != cudaSuccess) return -(int)err;                                                                \
+    k_tc_linear<NN><<<grid, 128, smem, s>>>(x, M, K, w, bias, relu, y);                                      \
+  }
+  if (N == 256) TC_LAUNCH(256)
+  else if (N == 128) TC_LAUNCH(128)
+  else if (N == 64) TC_LAUNCH(64)
+  else return -1000;
+  err = cudaGetLastError();
+  return err == cudaSuccess ? 0 : -(int)err;
+}
+
+} /* extern "C" */

@@ -73,6 +73,14 @@ int apex_ars_policy(const float *obs, int n, int S, int H, int A, const float *t
 int apex_ars_update(float *theta, int P, const float *noise, const int64_t *idx, const float *weight, int ndir, float coef,
                     void *stream);
 
+/* ---- tensor-core path (sm_100a tcgen05; opt-in reduced precision for BASELINE config "PPO CassieTraj-v0 ... bf16") ----
+ * y [M, N] = act(x [M, K] W^T + b): bf16 operands converted while staging, float32 accumulation in tensor memory, float32
+ * in / out.  N in {64, 128, 256}, K a multiple of 64, 16-byte aligned pointers; -1000 otherwise. */
+int apex_tc_linear_forward(const float *x, int M, int K, const float *w, const float *bias, int N, int relu, float *y, void *stream);
+/* apex_mlp_forward with the hidden hid x hid layer on apex_tc_linear_forward (hid in {64, 128, 256}) */
+int apex_mlp_forward_bf16(const float *x, int rows, int in_dim, int hid, int out_dim, const float *w1, const float *b1,
+                          const float *w2, const float *b2, const float *w3, const float *b3, float *h1, float *h2, float *y,
+                          void *stream);
 /* test hook: 0 routes every GEMM through the 64 x 64 tile kernel, 1 (default) uses the 128 x 128 one when M, N >= 128 */
 void apex_set_gemm_large_tiles(int on);
 /* tuning: minimum number of 128 x 128 tiles (x split-k) for the large-tile kernel to be chosen (default 148 = one per SM) */

@@ -237,3 +237,44 @@ def test_mlp_kernels_large_tiles_match_float64(rows, in_dim, out_dim):
         scale = float(c.abs().max()) + 1e-12
         assert float((a.double() - c).abs().max()) < 2e-5 * scale, (name, "128-tile vs float64")
         assert float((b.double() - c).abs().max()) < 2e-5 * scale, (name, "64-tile vs float64")
+
+
+@pytest.mark.parametrize("rows,N,K", [(128, 256, 256), (4133, 256, 256), (300, 128, 64), (1000, 64, 128)])
+def test_tcgen05_linear_matches_bf16_emulation(rows, N, K):
+    """apex_tc_linear_forward (tcgen05.mma kind::f16, TMEM accumulator) against the same arithmetic in torch: operands rounded to
+    bf16, float64 accumulation, bias, ReLU.  Tolerance 2e-5 of the output scale (float32 accumulation of K products)."""
+    from apex_b200 import _capi
+    L = _capi.lib()
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(rows + N)
+    x = torch.randn(rows, K, device=dev, generator=g)
+    w = torch.randn(N, K, device=dev, generator=g) * 0.1
+    b = torch.randn(N, device=dev, generator=g)
+    for relu in (0, 1):
+        y = torch.full((rows, N), float("nan"), device=dev)
+        _capi.check(L.apex_tc_linear_forward(x.data_ptr(), rows, K, w.data_ptr(), b.data_ptr(), N, relu, y.data_ptr(), None), "tc")
+        torch.cuda.synchronize()
+        ref = x.bfloat16().double() @ w.bfloat16().double().T + b.double()
+        if relu:
+            ref = torch.relu(ref)
+        err = float((y.double() - ref).abs().max())
+        assert err < 2e-5 * float(ref.abs().max()), (relu, err)
+
+
+def test_mlp_forward_bf16_close_to_float32():
+    from apex_b200 import _capi
+    L = _capi.lib()
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(3)
+    r = lambda *s: torch.randn(s, device=dev, generator=g, dtype=torch.float32)
+    rows, H = 4096, 256
+    x, w1, b1, w2, b2, w3, b3 = r(rows, 50), r(H, 50) * 0.1, r(H) * 0.1, r(H, H) * 0.06, r(H) * 0.1, r(10, H) * 0.06, r(10)
+    p = lambda t: t.data_ptr()
+    out = []
+    for fn in (L.apex_mlp_forward, L.apex_mlp_forward_bf16):
+        h1, h2, y = torch.zeros(rows, H, device=dev), torch.zeros(rows, H, device=dev), torch.zeros(rows, 10, device=dev)
+        _capi.check(fn(p(x), rows, 50, H, 10, p(w1), p(b1), p(w2), p(b2), p(w3), p(b3), p(h1), p(h2), p(y), None), "fwd")
+        out.append(y)
+    torch.cuda.synchronize()
+    scale = float(out[0].abs().max())
+    assert float((out[0] - out[1]).abs().max()) < 2e-2 * scale  # bf16 operands: ~3 significant digits
