@@ -48,12 +48,14 @@ __device__ __forceinline__ uint4 pack8(const float4 a, const float4 b) {
 
 /* stage `rows` x 64 float32 (row stride ld) as bf16 core matrices; rows beyond `valid` are zero */
 __device__ __forceinline__ void stage_tile(unsigned char *dst, const float *src, long ld, int rows, int valid, int tid, int nthreads) {
+  const bool vec = (((size_t)src | (size_t)(ld * 4)) & 15) == 0; /* 16-byte aligned rows -> float4 loads */
   for (int q = tid; q < rows * 8; q += nthreads) { /* q -> (row, 8-element k chunk); consecutive threads walk a row: coalesced */
     const int r = q >> 3, c = q & 7;
     uint4 v = make_uint4(0, 0, 0, 0);
     if (r < valid) {
-      const float4 *p = reinterpret_cast<const float4 *>(src + (long)r * ld + c * 8);
-      v = pack8(p[0], p[1]);
+      const float *p = src + (long)r * ld + c * 8;
+      if (vec) { const float4 *p4 = reinterpret_cast<const float4 *>(p); v = pack8(p4[0], p4[1]); }
+      else v = pack8(make_float4(p[0], p[1], p[2], p[3]), make_float4(p[4], p[5], p[6], p[7])); /* e.g. a weight matrix inside a flat parameter buffer */
     }
     *reinterpret_cast<uint4 *>(dst + (r >> 3) * TC_SBO + c * TC_LBO + (r & 7) * 16) = v;
   }
@@ -135,10 +137,10 @@ __global__ void __launch_bounds__(128) k_tc_linear(const float *__restrict__ x, 
 extern "C" {
 
 /* y [M, N] = act(x [M, K] W^T + b), W [N, K] row-major (torch Linear), bf16 operands / float32 accumulate on tcgen05.
- * Supported: N in {64, 128, 256}, K a multiple of 64, 16-byte aligned pointers.  Returns -1000 for anything else. */
+ * Supported: N in {64, 128, 256}, K a multiple of 64, y 16-byte aligned (x, W: any float alignment).  Returns -1000 for anything else. */
 int apex_tc_linear_forward(const float *x, int M, int K, const float *w, const float *bias, int N, int relu, float *y, void *stream) {
   if (M <= 0) return 0;
-  if (!x || !w || !y || K % TC_KT != 0 || (((size_t)x | (size_t)w | (size_t)y) & 15)) return -1000;
+  if (!x || !w || !y || K % TC_KT != 0 || ((size_t)y & 15)) return -1000;
   cudaStream_t s = (cudaStream_t)stream;
   const int grid = (M + TC_M - 1) / TC_M;
   cudaError_t err;

@@ -96,6 +96,12 @@ class PPO:
         self.mirror_coeff = 0.4 if args.get("mirror", True) else 0.0
         self.max_kl = args.get("max_kl", 0.02)  # ppo.py:449; None disables the early stop (fixed-work benchmarking)
         self.seed = int(args.get("seed", 0))
+        # "f32" (default: what the reference computes in) or "bf16": the forward 256 x 256 hidden layers (rollout inference and
+        # the update's forward pass) run on the tcgen05 tensor cores with bf16 operands / float32 accumulation; backward, first
+        # layer, heads, losses and Adam stay float32.  BASELINE config "PPO CassieTraj-v0 8192 envs/GPU bf16".
+        self.precision = args.get("precision", "f32")
+        if self.precision not in ("f32", "bf16"):
+            raise ValueError("precision must be 'f32' or 'bf16'")
         self.save_path = save_path
         self.total_steps = 0
         self.highest_reward = -1
@@ -174,8 +180,9 @@ class PPO:
                                         "critic_layers.1.bias", "network_out.weight", "network_out.bias")]
 
     def _mlp_fwd(self, ptrs, x, rows, out_dim, h1, h2, y):
-        _capi.check(self.L.apex_mlp_forward(_p(x), rows, self.obs_dim, self.hid, out_dim, ptrs[0][0], ptrs[1][0], ptrs[2][0],
-                                            ptrs[3][0], ptrs[4][0], ptrs[5][0], _p(h1), _p(h2), _p(y), self._s()), "mlp_forward")
+        fwd = self.L.apex_mlp_forward_bf16 if self.precision == "bf16" else self.L.apex_mlp_forward
+        _capi.check(fwd(_p(x), rows, self.obs_dim, self.hid, out_dim, ptrs[0][0], ptrs[1][0], ptrs[2][0], ptrs[3][0], ptrs[4][0],
+                        ptrs[5][0], _p(h1), _p(h2), _p(y), self._s()), "mlp_forward")
         self.launches += 3
 
     def _mlp_bwd(self, ptrs, x, rows, out_dim, h1, h2, dy, dh2, dh1):

@@ -278,3 +278,23 @@ def test_mlp_forward_bf16_close_to_float32():
     torch.cuda.synchronize()
     scale = float(out[0].abs().max())
     assert float((out[0] - out[1]).abs().max()) < 2e-2 * scale  # bf16 operands: ~3 significant digits
+
+
+def test_ppo_iteration_with_bf16_tensor_core_forward():
+    """precision="bf16": rollout inference and the update's forward pass use the tcgen05 hidden layer; one small iteration on
+    CassieTraj-v0 (BASELINE config 4's env) must give finite statistics close to the float32 iteration from the same seed."""
+    import os
+    from apex_b200.envs import BatchedCassieTrajEnv
+    from apex_b200.policies import Gaussian_FF_Actor, FF_V
+    from apex_b200.ppo import PPO
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "traj_walking_rows.npz"))
+    table = (np.ascontiguousarray(g["rows"], dtype=np.float64), int(g["traj_len"]))
+    res = {}
+    for prec in ("f32", "bf16"):
+        torch.manual_seed(0)
+        actor, critic = Gaussian_FF_Actor(50, 10, fixed_std=torch.ones(10) * float(np.exp(-1.5))), FF_V(50)
+        algo = PPO(dict(num_steps=256 * 16, minibatch_size=1024, epochs=1, seed=0, precision=prec, max_kl=None))
+        buf, scal = algo.train_iteration(lambda: BatchedCassieTrajEnv(256, table, seed=0), actor, critic)
+        assert all(np.isfinite(scal)) and bool(torch.isfinite(algo.flat).all())
+        res[prec] = (float(buf.rew.mean()), float(buf.val.abs().mean()), scal)
+    assert abs(res["bf16"][0] - res["f32"][0]) < 0.05 * abs(res["f32"][0]) + 1e-3  # same rollout up to bf16 action noise
