@@ -69,6 +69,8 @@ def lib():
         L.apex_tc_linear_forward.argtypes = [vp, i, i, vp, vp, i, i, vp, vp]
         L.apex_mlp_forward_bf16.argtypes = [vp, i, i, i, i, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
         L.apex_tc_linear_forward.restype = L.apex_mlp_forward_bf16.restype = i
+        L.apex_set_tc_persistent.argtypes = [i]
+        L.apex_set_tc_persistent.restype = None
         L.apex_set_gemm_large_tiles.argtypes = [i]
         L.apex_set_gemm_large_tiles.restype = None
         L.apex_col_moments.argtypes = [vp, i, i, vp, vp]

@@ -134,7 +134,149 @@ __global__ void __launch_bounds__(128) k_tc_linear(const float *__restrict__ x, 
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(N));
 }
 
+/* ---------------------------------------------------------------------------------------------------------------------
+ * Persistent, warp-specialised version (the one the library uses when W fits in shared memory as bf16: N * K <= 64 Ki):
+ *   - one CTA per SM walks the 128-row tiles; W is converted and staged ONCE per CTA and stays resident (128 KB for 256 x 256);
+ *   - warps 0-3 stage the next x tile (whole K, 64 KB) and one thread issues the K / 16 MMAs of the tile;
+ *   - warps 4-7 are the epilogue (TMEM lane quarter = warp % 4): tcgen05.ld 32 columns at a time, bias, ReLU, 128-byte stores;
+ *   - the accumulator is double-buffered in tensor memory (2 x N columns), so the epilogue of tile j overlaps the staging and
+ *     the MMAs of tile j + 1.  mbarriers: mma_done[b] (tcgen05.commit; also releases the x stage), tmem_free[b] (epilogue).
+ * Staging walks rows fastest (8 threads = one 128-byte core matrix: conflict-free shared stores; a warp still covers full
+ * 128-byte lines of each of its 8 rows in global memory).
+ * --------------------------------------------------------------------------------------------------------------------- */
+__device__ __forceinline__ void stage_rows_fast(unsigned char *dst, const float *src, long ld, int rows, int valid, int K, int tid,
+                                                int nthreads) {
+  const bool vec = (((size_t)src | (size_t)(ld * 4)) & 15) == 0;
+  const int CH = K >> 3, sbo = CH * TC_LBO, total = rows * CH; /* 8-element chunks per row; bytes per 8-row group */
+  constexpr int U = 16; /* chunks in flight per thread: U x 32 B x 128 threads = 64 KB per SM (HBM latency x per-SM bandwidth is ~35 KB) */
+  for (int q0 = tid; q0 < total; q0 += nthreads * U) {
+    float4 lo[U], hi[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) { /* all loads first */
+      const int q = q0 + u * nthreads, r = (q / (8 * CH)) * 8 + (q & 7), c = (q >> 3) % CH;
+      lo[u] = hi[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (q < total && r < valid) {
+        const float *p = src + (long)r * ld + c * 8;
+        if (vec) { lo[u] = reinterpret_cast<const float4 *>(p)[0]; hi[u] = reinterpret_cast<const float4 *>(p)[1]; }
+        else { lo[u] = make_float4(p[0], p[1], p[2], p[3]); hi[u] = make_float4(p[4], p[5], p[6], p[7]); }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) { /* then convert and store */
+      const int q = q0 + u * nthreads;
+      if (q < total) {
+        const int g = q / (8 * CH), c = (q >> 3) % CH;
+        *reinterpret_cast<uint4 *>(dst + g * sbo + c * TC_LBO + (q & 7) * 16) = pack8(lo[u], hi[u]);
+      }
+    }
+  }
+}
+__device__ __forceinline__ uint64_t tc_smem_desc2(uint32_t addr, uint32_t sbo) {
+  const uint64_t lo = (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((TC_LBO >> 4) & 0x3FFF) << 16);
+  const uint64_t hi = (uint64_t)((sbo >> 4) & 0x3FFF) | (1ull << 14);
+  return lo | (hi << 32);
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("{ .reg .b64 st; mbarrier.arrive.shared::cta.b64 st, [%0]; }" :: "r"(bar) : "memory");
+}
+
+template <int N>
+__global__ void __launch_bounds__(256, 1) k_tc_linear_persistent(const float *__restrict__ x, int M, int K, const float *__restrict__ w,
+                                                                 const float *__restrict__ bias, int relu, float *__restrict__ y) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char *sB = smem, *sA = smem + (size_t)N * K * 2;
+  __shared__ __align__(8) uint64_t bars[4]; /* mma_done[0..1], tmem_free[0..1] */
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tiles = (M + TC_M - 1) / TC_M;
+  const uint32_t sbo = (uint32_t)(K >> 3) * TC_LBO;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base_s)), "r"(2 * N));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&bars[0])));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&bars[1])));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 128;" :: "r"(smem_u32(&bars[2])));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 128;" :: "r"(smem_u32(&bars[3])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  stage_rows_fast(sB, w, K, N, N, K, tid, 256); /* the weights: once per CTA */
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+  if (warp < 4) {
+    /* ===== producers: stage x tile j, issue its MMAs ===== */
+    int j = 0;
+    for (int t = blockIdx.x; t < tiles; t += gridDim.x, j++) {
+      const int b = j & 1, m0 = t * TC_M;
+      if (j > 0) mbar_wait(smem_u32(&bars[(j - 1) & 1]), ((j - 1) >> 1) & 1); /* the MMAs of tile j - 1 have read the stage */
+      stage_rows_fast(sA, x + (long)m0 * K, K, TC_M, min(TC_M, M - m0), K, tid, 128);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("bar.sync 1, 128;" ::: "memory"); /* the four producer warps */
+      if (tid == 0) {
+        if (j >= 2) mbar_wait(smem_u32(&bars[2 + b]), ((j >> 1) - 1) & 1); /* the epilogue has drained accumulator b */
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB), d = tmem + (uint32_t)(b * N);
+        for (int kk = 0; kk < (K >> 4); kk++) {
+          const uint64_t da = tc_smem_desc2(a0 + kk * 2 * TC_LBO, sbo), db = tc_smem_desc2(b0 + kk * 2 * TC_LBO, sbo);
+          const uint32_t acc = kk > 0 ? 1u : 0u;
+          asm volatile("{ .reg .pred p; setp.ne.b32 p, %4, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p; }"
+                       :: "r"(d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(&bars[b])) : "memory");
+      }
+    }
+  } else {
+    /* ===== epilogue: accumulator b of tile j -> bias, ReLU, y ===== */
+    const int q = warp & 3;
+    int j = 0;
+    for (int t = blockIdx.x; t < tiles; t += gridDim.x, j++) {
+      const int b = j & 1, row = t * TC_M + q * 32 + lane;
+      mbar_wait(smem_u32(&bars[b]), (j >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * N);
+      for (int c = 0; c < N; c += 32) {
+        uint32_t r[32];
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                     "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                       "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+                       "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+                       "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                     : "r"(taddr + (uint32_t)c));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (row < M) {
+          float4 *o = reinterpret_cast<float4 *>(y + (long)row * N + c);
+#pragma unroll
+          for (int g4 = 0; g4 < 8; g4++) {
+            float v[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+              v[e] = __uint_as_float(r[4 * g4 + e]) + (bias ? __ldg(bias + c + 4 * g4 + e) : 0.f);
+              if (relu) v[e] = fmaxf(v[e], 0.f);
+            }
+            o[g4] = make_float4(v[0], v[1], v[2], v[3]);
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(smem_u32(&bars[2 + b])); /* 128 arrivals: accumulator b may be overwritten */
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(2 * N));
+}
+
+int apex_tc_persistent = 1; /* test hook: 0 forces the single-stage kernel */
+
 extern "C" {
+
+void apex_set_tc_persistent(int on) { apex_tc_persistent = on; }
 
 /* y [M, N] = act(x [M, K] W^T + b), W [N, K] row-major (torch Linear), bf16 operands / float32 accumulate on tcgen05.
  * Supported: N in {64, 128, 256}, K a multiple of 64, y 16-byte aligned (x, W: any float alignment).  Returns -1000 for anything else. */
@@ -151,9 +293,20 @@ int apex_tc_linear_forward(const float *x, int M, int K, const float *w, const f
     if (err != cudaSuccess) return -(int)err;                                                                \
     k_tc_linear<NN><<<grid, 128, smem, s>>>(x, M, K, w, bias, relu, y);                                      \
   }
-  if (N == 256) TC_LAUNCH(256)
-  else if (N == 128) TC_LAUNCH(128)
-  else if (N == 64) TC_LAUNCH(64)
+#define TC_LAUNCH_P(NN)                                                                                                 \
+  {                                                                                                                     \
+    const int smem = (NN + TC_M) * K * 2;                                                                               \
+    err = cudaFuncSetAttribute(k_tc_linear_persistent<NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);          \
+    if (err != cudaSuccess) return -(int)err;                                                                           \
+    int dev = 0, sms = 148;                                                                                             \
+    cudaGetDevice(&dev);                                                                                                \
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);                                                  \
+    k_tc_linear_persistent<NN><<<grid < sms ? grid : sms, 256, smem, s>>>(x, M, K, w, bias, relu, y);                   \
+  }
+  const bool persistent = apex_tc_persistent && (long)(N + TC_M) * K * 2 <= 200 * 1024;
+  if (N == 256) { if (persistent) TC_LAUNCH_P(256) else TC_LAUNCH(256) }
+  else if (N == 128) { if (persistent) TC_LAUNCH_P(128) else TC_LAUNCH(128) }
+  else if (N == 64) { if (persistent) TC_LAUNCH_P(64) else TC_LAUNCH(64) }
   else return -1000;
   err = cudaGetLastError();
   return err == cudaSuccess ? 0 : -(int)err;

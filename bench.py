@@ -33,6 +33,9 @@ def parse():
     ap.add_argument("--envs", type=int, default=N_ENVS)
     ap.add_argument("--horizon", type=int, default=HORIZON)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", default="f32", choices=["f32", "bf16"],
+                    help="bf16: forward 256x256 hidden layers on tcgen05 (BASELINE configs[3]); the headline config is f32")
+    ap.add_argument("--env", default="Cassie-v0", choices=["Cassie-v0", "CassieTraj-v0"])
     return ap.parse_args()
 
 
@@ -176,7 +179,7 @@ def main():
     args = parse()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
-    workload = f"PPO Cassie-v0 {args.envs} batched envs/GPU, {args.horizon}-step rollout, mb {MINIBATCH}, {EPOCHS} epochs"
+    workload = f"PPO {args.env} {args.envs} batched envs/GPU, {args.horizon}-step rollout, mb {MINIBATCH}, {EPOCHS} epochs"
 
     if args.impl == "reference":
         if rank != 0:
@@ -205,8 +208,14 @@ def main():
     actor = Gaussian_FF_Actor(50, 10, fixed_std=torch.ones(10) * float(np.exp(-1.5)), env_name="Cassie-v0")
     critic = FF_V(50)
     algo = PPO(dict(num_steps=args.envs * args.horizon, minibatch_size=MINIBATCH, epochs=EPOCHS, max_traj_len=400, seed=0,
-                    max_kl=None))  # fixed work per step: all epochs always run (the reference stops early when KL > 0.02)
-    env_fn = lambda: BatchedCassieEnv(args.envs, device=dev, seed=0, dynamics_randomization=True, env_id0=rank * args.envs)
+                    max_kl=None, precision=args.precision))  # fixed work per step: all epochs always run (the reference stops early when KL > 0.02)
+    if args.env == "CassieTraj-v0":  # the decimated reference trajectory ships as a test fixture (tests/golden/make_env_golden.py)
+        from apex_b200.envs import BatchedCassieTrajEnv
+        g = np.load(os.path.join(ROOT, "tests", "golden", "traj_walking_rows.npz"))
+        table = (np.ascontiguousarray(g["rows"], dtype=np.float64), int(g["traj_len"]))
+        env_fn = lambda: BatchedCassieTrajEnv(args.envs, table, device=dev, seed=0, dynamics_randomization=True, env_id0=rank * args.envs)
+    else:
+        env_fn = lambda: BatchedCassieEnv(args.envs, device=dev, seed=0, dynamics_randomization=True, env_id0=rank * args.envs)
     gen = torch.Generator(device=dev).manual_seed(1234)
 
     # pinned host copies of the parameters: the end-to-end step ships them in and reads them (and the losses) back
@@ -287,7 +296,8 @@ def main():
     achieved = ALGO_BYTES_PER_ENV_STEP * args.envs / (k_ms * 1e-3) / 1e9
     out = {"metric": "Cassie-v0 PPO env-steps/sec", "value": env_steps / (ms_step * 1e-3), "unit": "env-steps/s", "n_gpus": world,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "vs_baseline": None, "dtype": "f32" if args.precision == "f32" else "bf16 (forward hidden layers; rest f32)",
+           "data": "synthetic",
            "config": {"workload": workload, "envs_per_gpu": args.envs, "horizon": args.horizon, "simrate": 50,
                       "dynamics_randomization": True, "parallelism": f"dp{world}", "l2": "per-step state 4096 x 2.4 KB + "
                       "210 MB rollout buffer per iteration: inputs larger than L2 (126 MB)"},

@@ -77,6 +77,8 @@ int apex_ars_update(float *theta, int P, const float *noise, const int64_t *idx,
  * y [M, N] = act(x [M, K] W^T + b): bf16 operands converted while staging, float32 accumulation in tensor memory, float32
  * in / out.  N in {64, 128, 256}, K a multiple of 64, y 16-byte aligned; -1000 otherwise. */
 int apex_tc_linear_forward(const float *x, int M, int K, const float *w, const float *bias, int N, int relu, float *y, void *stream);
+/* test hook: 0 forces the single-stage tcgen05 kernel, 1 (default) the persistent warp-specialised one when W fits in shared memory */
+void apex_set_tc_persistent(int on);
 /* apex_mlp_forward with the hidden hid x hid layer on apex_tc_linear_forward (hid in {64, 128, 256}) */
 int apex_mlp_forward_bf16(const float *x, int rows, int in_dim, int hid, int out_dim, const float *w1, const float *b1,
                           const float *w2, const float *b2, const float *w3, const float *b3, float *h1, float *h2, float *y,
