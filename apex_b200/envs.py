@@ -150,3 +150,28 @@ class BatchedCassieTrajEnv(BatchedCassieEnv):
 
     def _traj_args(self):
         return self.traj_rows.data_ptr(), self.traj_rows.shape[0], self._traj_len
+
+
+def env_factory(path, command_profile="clock", input_profile="full", simrate=50, dynamics_randomization=True, mirror=False,
+                learn_gains=False, reward=None, history=0, no_delta=True, traj=None, ik_baseline=False, num_envs=4096,
+                trajectory=None, **kwargs):
+    """util/env.py:8-52 for the two environments of the hot path: returns an *uninstantiated* constructor (a zero-argument
+    callable), as the reference does because its workers build their own env.  `num_envs` is the batch the one GPU-resident
+    env object holds (the reference builds one env per Ray worker).  mirror=True needs no wrapper here: the mirror indices
+    (`mirrored_obs`, `mirrored_acts`, `clock_inds`) are attributes of the env and the signed-permutation gather of
+    rl/envs/wrappers.py:24-77 runs inside the learner kernels.  CassieTraj-v0 takes `trajectory` = path of the reference's
+    cassie/trajectory/stepdata.bin (or a (rows, length) pair, see load_trajectory)."""
+    from functools import partial
+    if learn_gains:
+        raise NotImplementedError("learn_gains is not on the kernel path")
+    reward = reward or "clock"
+    common = dict(command_profile=command_profile, input_profile=input_profile, simrate=simrate,
+                  dynamics_randomization=dynamics_randomization, reward=reward, history=history, **kwargs)
+    if path == "Cassie-v0":
+        return partial(BatchedCassieEnv, num_envs, **common)
+    if path == "CassieTraj-v0":
+        if trajectory is None:
+            raise ValueError("CassieTraj-v0 needs trajectory=<path to cassie/trajectory/stepdata.bin> (or a (rows, length) pair)")
+        return partial(BatchedCassieTrajEnv, num_envs, trajectory, traj=traj or "walking", no_delta=no_delta, ik_baseline=ik_baseline,
+                       **common)
+    raise NotImplementedError(f"{path}: only Cassie-v0 and CassieTraj-v0 are on the B200 path (SURVEY.md §8)")

@@ -259,10 +259,19 @@ def main():
                 kernel_events.append((s_, t_))
                 return out
             algo.env.step = wrapped
+            orig_sample = algo.sample_parallel
+
+            def wrapped_sample(*a, **k):  # rollout only (env + actor / critic inference + buffer writes + return scan)
+                s_, t_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s_.record(); out = orig_sample(*a, **k); t_.record()
+                rollout_events.append((s_, t_))
+                return out
+            algo.sample_parallel = wrapped_sample
         for _ in range(nsteps):
             step(e2e)
         if kernel_events is not None:
             algo.env.step = orig
+            algo.sample_parallel = orig_sample
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -271,11 +280,12 @@ def main():
         return float(ms) / nsteps, (algo.launches - l0) // nsteps
 
     clocks = ClockSampler(local) if rank == 0 else None
-    kev = []
+    kev, rollout_events = [], []
     ms_step, launches = timed(False, args.steps, kev)
     clk = clocks.stop() if clocks else None
     ms_e2e, _ = timed(True, max(1, min(args.steps, 2)))
     kms = [s.elapsed_time(t) for s, t in kev]
+    rms = [s.elapsed_time(t) for s, t in rollout_events]
     k_ms = sum(kms) / len(kms)
     env_steps = args.envs * args.horizon * world
     if rank != 0:
@@ -304,6 +314,8 @@ def main():
            "e2e": {"value": env_steps / (ms_e2e * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": n_params * 4,
                    "d2h_bytes_per_step": n_params * 4 + 48},
            "gpu_launches": launches, "clocks": clk,
+           "rollout_only": {"value": args.envs * args.horizon * world / (sum(rms) / len(rms) * 1e-3), "unit": "env-steps/s",
+                            "ms": sum(rms) / len(rms), "note": "rank 0's device time of sample_parallel inside the timed steps"},
            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                         "traffic": traffic, "kernel": "k_env_step<float>", "kernel_ms": k_ms, "peak_source": peak_src,
                         "kernel_share_of_step": sum(kms) / args.steps / ms_step,

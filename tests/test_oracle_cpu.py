@@ -377,3 +377,18 @@ def _set_speed(L, env, speed):
     L.ce_env_get_phase.restype = ctypes.c_double
     ph = L.ce_env_get_phase(env.buf)
     L.ce_env_set_command(env.buf, speed, 0.0, ph)
+
+
+def test_env_factory_mirrors_the_reference_signature():
+    """util/env.py:8: same positional / keyword arguments; returns a constructor, builds nothing (no GPU needed)."""
+    from functools import partial
+    from apex_b200.envs import env_factory, BatchedCassieEnv, BatchedCassieTrajEnv
+    fn = env_factory("Cassie-v0", command_profile="clock", input_profile="full", simrate=50, dynamics_randomization=True, mirror=True,
+                     learn_gains=False, reward="clock", history=0, no_delta=True, traj=None, ik_baseline=False)
+    assert isinstance(fn, partial) and fn.func is BatchedCassieEnv and fn.keywords["dynamics_randomization"] is True
+    fn = env_factory("CassieTraj-v0", traj="walking", trajectory=_traj_table(), num_envs=8)
+    assert fn.func is BatchedCassieTrajEnv and fn.args[0] == 8
+    with pytest.raises(NotImplementedError):
+        env_factory("CassiePlayground-v0")
+    with pytest.raises(ValueError):
+        env_factory("CassieTraj-v0")
