@@ -1102,10 +1102,10 @@ template <typename T> CW_NOINL void cw_mj_step(CassieWs<T> &w, bool integrate, i
          * select, and the row's new force / cost improvement are recomputed from it once per sweep */
         T res_own = 0;
 #pragma unroll
-        for (int i0 = 0; i0 < CW_NEFC; i0 += 4) {
-          if (i0 >= n) break; /* tested once per 4 rows: a row >= n has di0 = 0 and a zero column, so its update is exactly 0 */
+        for (int i0 = 0; i0 < CW_NEFC; i0 += 2) {
+          if (i0 >= n) break; /* tested once per 2 rows: a row >= n has di0 = 0 and a zero column, so its update is exactly 0 */
 #pragma unroll
-          for (int i = i0; i < i0 + 4; i++) {
+          for (int i = i0; i < i0 + 2; i++) {
             const T nf = cw_max(f0 - res0 * di0, lb0);
             const T dl = __shfl_sync(0xffffffffu, nf - f0, i);
             const bool own = lane == i;
