@@ -6,6 +6,8 @@
  * velocity filters, IMU copy — SURVEY.md Appendix C) and (2) the Cassie-v0 environment of
  * cassie/cassie.py (step :389-496, step_simulation :293-351, reset :523-680, get_full_state :787-859),
  * cassie/rewards/clock_rewards.py:6-110 and cassie/phase_function.py:5-136.
+ * The env layer (step / reset / get_full_state / clock_reward, Cassie-v0 and CassieTraj-v0) IS pinned: episodes recorded from the
+ * reference's own Python over oracle/cassiemujoco_abi.c replay through this file to 1e-14 (tests/golden/make_env_golden.py).
  * Physics underneath: oracle/cassie_phys.c.  PARITY UNPINNED against the closed Agility blocks
  * (pd_input_step / cassie_core_sim_step / state_output_step): software safeties are not restated and the
  * state estimator is replaced by an ideal one (sensor pass-through) — see DESIGN.md.

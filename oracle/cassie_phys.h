@@ -7,6 +7,8 @@
  * golden step vector exists in the reference tree; this file follows the published MuJoCo-2.0 computation
  * (mj_step1/mj_step2: kinematics, CRBA, RNE, passive, collision, soft constraints, PGS, semi-implicit Euler).
  * Weak pins: init-pose loop-closure residual, stepdata.bin integrator identity, energy/momentum properties (tests/).
+ * Behavioural pin: the reference's shipped policy trained_models/5k_retrain (trained on the real MuJoCo stack) walks on this
+ * physics at its commanded speed (tests/golden/make_policy_golden.py, tests/test_oracle_cpu.py, tests/test_env_gpu.py).
  */
 #ifndef CASSIE_PHYS_H
 #define CASSIE_PHYS_H
