@@ -7,6 +7,7 @@ and both targets are Polyak-averaged.  Here the ring is one [capacity, 2S+A+2] f
 row gather inside apex_replay_gather, and every arithmetic step is a kernel of apex_b200/csrc/ppo_kernels.cu.
 """
 import torch
+import torch.distributed as dist
 
 from . import _capi
 from .policies import FF_Actor, Dual_Q_Critic, flatten_modules
@@ -122,8 +123,14 @@ class TD3:
         gp, pp = self.grad.data_ptr() + 4 * off, self.flat.data_ptr() + 4 * off
         mp, vp = self.adam_m.data_ptr() + 4 * off, self.adam_v.data_ptr() + 4 * off
         self._opt[which] += 1
+        gscale = 1.0
+        if dist.is_initialized() and dist.get_world_size() > 1:
+            # data parallel: every rank samples its own replay shard; ONE all-reduce of this network's flattened
+            # gradient per optimizer step, averaged inside the Adam kernel
+            dist.all_reduce(self.grad[off:off + n])
+            gscale = 1.0 / dist.get_world_size()
         # torch.optim.Adam defaults (eps 1e-8), no gradient clipping in TD3: max_norm = inf
-        _capi.check(self.L.apex_adam_step(pp, gp, mp, vp, n, self.sumsq.data_ptr(), 1.0, 3.0e38, float(lr), 0.9, 0.999, 1e-8,
+        _capi.check(self.L.apex_adam_step(pp, gp, mp, vp, n, self.sumsq.data_ptr(), gscale, 3.0e38, float(lr), 0.9, 0.999, 1e-8,
                                           self._opt[which], self._s()), "adam")
         self.launches += 1
 
