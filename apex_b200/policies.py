@@ -134,3 +134,29 @@ def flatten_modules(modules, device):
         index.append((name, off, tuple(p.shape)))
         off += n
     return flat, grad, index
+
+
+def load_reference_checkpoint(path, map_location="cpu"):
+    """Load a whole-module checkpoint written by the reference (`torch.save(policy, "actor.pt")`, rl/algos/ppo.py:129-137;
+    e.g. trained_models/*/actor.pt) WITHOUT the reference on the import path: the pickle names the classes
+    rl.policies.actor.Gaussian_FF_Actor / FF_Actor and rl.policies.critic.FF_V / Dual_Q_Critic, which are resolved to the classes
+    of this module (same parameter names, same attributes obs_mean / obs_std / fixed_std)."""
+    import pickle
+    import sys
+    import types
+
+    here = sys.modules[__name__]
+    table = {("rl.policies.actor", "Gaussian_FF_Actor"): Gaussian_FF_Actor, ("rl.policies.actor", "FF_Actor"): FF_Actor,
+             ("rl.policies.critic", "FF_V"): FF_V, ("rl.policies.critic", "Dual_Q_Critic"): Dual_Q_Critic}
+
+    class _Unpickler(pickle.Unpickler):
+        def find_class(self, module, name):
+            if (module, name) in table:
+                return table[(module, name)]
+            if module.startswith("rl.policies"):
+                raise pickle.UnpicklingError(f"{module}.{name} is not on the B200 path (feed-forward actors / critics only)")
+            return super().find_class(module, name)
+    shim = types.ModuleType("apex_b200_ref_pickle")
+    shim.Unpickler, shim.load, shim.loads = _Unpickler, pickle.load, pickle.loads
+    shim.__name__ = "pickle"
+    return torch.load(path, map_location=map_location, pickle_module=shim, weights_only=False)

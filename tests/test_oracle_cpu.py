@@ -392,3 +392,22 @@ def test_env_factory_mirrors_the_reference_signature():
         env_factory("CassiePlayground-v0")
     with pytest.raises(ValueError):
         env_factory("CassieTraj-v0")
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/trained_models/5k_retrain/actor.pt"), reason="reference tree not mounted")
+def test_reference_checkpoints_load_without_the_reference_package():
+    """trained_models/5k_retrain/{actor,critic}.pt are whole-module pickles of rl.policies.*; load_reference_checkpoint resolves
+    them to apex_b200.policies classes (nothing from /root/reference on sys.path) and the actor computes what the fixture says."""
+    import sys
+    import torch
+    from apex_b200.policies import load_reference_checkpoint, Gaussian_FF_Actor, FF_V
+    assert not any(p.rstrip("/") == "/root/reference" for p in sys.path)
+    actor = load_reference_checkpoint("/root/reference/trained_models/5k_retrain/actor.pt")
+    critic = load_reference_checkpoint("/root/reference/trained_models/5k_retrain/critic.pt")
+    assert isinstance(actor, Gaussian_FF_Actor) and isinstance(critic, FF_V)
+    act, _ = _ref_policy()
+    obs = np.random.default_rng(0).normal(size=(5, 50))
+    with torch.no_grad():
+        got = actor(torch.as_tensor(obs[:, :49], dtype=torch.float32), deterministic=True).numpy()
+    assert np.abs(got - act(obs)).max() < 1e-5
+    assert critic(torch.zeros(1, 49)).shape == (1, 1)
