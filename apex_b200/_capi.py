@@ -67,8 +67,11 @@ def lib():
                   L.apex_polyak):
             f.restype = i
         L.apex_tc_linear_forward.argtypes = [vp, i, i, vp, vp, i, i, vp, vp]
-        L.apex_mlp_forward_bf16.argtypes = [vp, i, i, i, i, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
-        L.apex_tc_linear_forward.restype = L.apex_mlp_forward_bf16.restype = i
+        L.apex_mlp_forward_bf16.argtypes = [vp, i, i, i, i, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_long, vp]
+        L.apex_tc_linear_tiled.argtypes = [vp, i, i, vp, vp, vp, i, i, vp, vp]
+        L.apex_mlp_bf16_scratch_bytes.argtypes = [i, i]
+        L.apex_mlp_bf16_scratch_bytes.restype = C.c_long
+        L.apex_tc_linear_forward.restype = L.apex_mlp_forward_bf16.restype = L.apex_tc_linear_tiled.restype = i
         L.apex_set_tc_persistent.argtypes = [i]
         L.apex_set_tc_persistent.restype = None
         L.apex_set_gemm_large_tiles.argtypes = [i]

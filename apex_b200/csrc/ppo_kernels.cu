@@ -24,13 +24,29 @@ static inline int last_err() { cudaError_t e = cudaGetLastError(); return e == c
  * GEMM  C[M,N] (+)= A[M,K] * B[K,N] with arbitrary element strides; epilogue: + bias[n], relu, * (mask > 0)
  * split over K through blockIdx.z (atomicAdd accumulation when gridDim.z > 1 or accumulate != 0)
  * =================================================================================================== */
+/* Side output of a forward GEMM for the tensor-core path (csrc/tc_linear.cu): the activations once more, as bf16, already in
+ * the shared-memory image the next layer's tcgen05.mma reads — per 128-row tile, per 128-wide k half, K-major 8 x 16-byte core
+ * matrices (SBO 2048 B) — so that layer can fetch a tile with plain bulk copies (TMA) instead of converting float32 on the fly.
+ * Offset in bf16 elements of (row m, column n) for a matrix with `kdim` columns (a multiple of 128): */
+#include <cuda_bf16.h>
+__device__ __forceinline__ long tc_tiled_off(int m, int n, int kdim) {
+  const int t = m >> 7, r = m & 127, h = n >> 7, kk = n & 127;
+  return (long)t * 128 * kdim + (long)h * (128 * 128) + (r >> 3) * 1024 + (kk >> 3) * 64 + (r & 7) * 8 + (kk & 7);
+}
+__device__ __forceinline__ void tc_side_store4(__nv_bfloat16 *side, int kdim, int m, int n, float a, float b, float c, float d) {
+  __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d); /* n is a multiple of 4: 8 contiguous bytes */
+  uint2 v;
+  v.x = *reinterpret_cast<unsigned *>(&lo); v.y = *reinterpret_cast<unsigned *>(&hi);
+  *reinterpret_cast<uint2 *>(side + tc_tiled_off(m, n, kdim)) = v;
+}
+
 #define BM 64
 #define BN 64
 #define BK 16
 __global__ void __launch_bounds__(256) k_gemm(int M, int N, int K, const float *__restrict__ A, long sam, long sak,
                                               const float *__restrict__ B, long sbk, long sbn, float *__restrict__ C, long scm,
                                               long scn, const float *__restrict__ bias, int relu, const float *__restrict__ mask,
-                                              long smm, long smn, int accumulate, int kchunk) {
+                                              long smm, long smn, int accumulate, int kchunk, __nv_bfloat16 *side, int side_k) {
   __shared__ float As[BK][BM + 4];
   __shared__ float Bs[BK][BN + 4];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -75,6 +91,7 @@ __global__ void __launch_bounds__(256) k_gemm(int M, int N, int K, const float *
   for (int i = 0; i < 4; i++) {
     const int gm = m0 + ty * 4 + i;
     if (gm >= M) continue;
+    float sv[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int j = 0; j < 4; j++) {
       const int gn = n0 + tx * 4 + j;
@@ -84,7 +101,9 @@ __global__ void __launch_bounds__(256) k_gemm(int M, int N, int K, const float *
       if (relu) v = fmaxf(v, 0.f);
       if (mask) v = mask[gm * smm + gn * smn] > 0.f ? v : 0.f;
       if (atomic) atomicAdd(&C[gm * scm + gn * scn], v); else C[gm * scm + gn * scn] = v;
+      sv[j] = v;
     }
+    if (side && n0 + tx * 4 + 3 < N) tc_side_store4(side, side_k, gm, n0 + tx * 4, sv[0], sv[1], sv[2], sv[3]);
   }
 }
 
@@ -97,7 +116,7 @@ __global__ void __launch_bounds__(256) k_gemm(int M, int N, int K, const float *
 __global__ void __launch_bounds__(256) k_gemm128(int M, int N, int K, const float *__restrict__ A, long sam, long sak,
                                                  const float *__restrict__ B, long sbk, long sbn, float *__restrict__ C, long scm,
                                                  long scn, const float *__restrict__ bias, int relu, const float *__restrict__ mask,
-                                                 long smm, long smn, int accumulate, int kchunk) {
+                                                 long smm, long smn, int accumulate, int kchunk, __nv_bfloat16 *side, int side_k) {
   __shared__ __align__(16) float As[LK][LM + 4];
   __shared__ __align__(16) float Bs[LK][LN + 4];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -218,6 +237,7 @@ __global__ void __launch_bounds__(256) k_gemm128(int M, int N, int K, const floa
   for (int i = 0; i < 8; i++) {
     const int gm = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + i - 4);
     if (gm >= M) continue;
+    float sv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int j = 0; j < 8; j++) {
       const int gn = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + j - 4);
@@ -227,6 +247,11 @@ __global__ void __launch_bounds__(256) k_gemm128(int M, int N, int K, const floa
       if (relu) v = fmaxf(v, 0.f);
       if (mask) v = mask[gm * smm + gn * smn] > 0.f ? v : 0.f;
       if (atomic) atomicAdd(&C[gm * scm + gn * scn], v); else C[gm * scm + gn * scn] = v;
+      sv[j] = v;
+    }
+    if (side) {
+      if (n0 + tx * 4 + 3 < N) tc_side_store4(side, side_k, gm, n0 + tx * 4, sv[0], sv[1], sv[2], sv[3]);
+      if (n0 + 64 + tx * 4 + 3 < N) tc_side_store4(side, side_k, gm, n0 + 64 + tx * 4, sv[4], sv[5], sv[6], sv[7]);
     }
   }
 }
@@ -238,7 +263,7 @@ extern "C" void apex_set_gemm_large_tiles(int on) { apex_gemm_large_tiles = on; 
 
 static int gemm(int M, int N, int K, const float *A, long sam, long sak, const float *B, long sbk, long sbn, float *C, long scm,
                 long scn, const float *bias, int relu, const float *mask, long smm, long smn, int accumulate, int splits,
-                cudaStream_t s) {
+                cudaStream_t s, __nv_bfloat16 *side = nullptr, int side_k = 0) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   if (splits < 1) splits = 1;
   if (apex_gemm_large_tiles && M >= 128 && N >= 128 && (long)((M + LM - 1) / LM) * ((N + LN - 1) / LN) * splits >= apex_gemm_min_ctas) { /* enough 128-tiles to fill the SMs */
@@ -249,13 +274,13 @@ static int gemm(int M, int N, int K, const float *A, long sam, long sak, const f
     int kchunk = ((K + splits - 1) / splits + LK - 1) / LK * LK;
     splits = (K + kchunk - 1) / kchunk;
     dim3 grid((N + LN - 1) / LN, (M + LM - 1) / LM, splits);
-    k_gemm128<<<grid, 256, 0, s>>>(M, N, K, A, sam, sak, B, sbk, sbn, C, scm, scn, bias, relu, mask, smm, smn, accumulate, kchunk);
+    k_gemm128<<<grid, 256, 0, s>>>(M, N, K, A, sam, sak, B, sbk, sbn, C, scm, scn, bias, relu, mask, smm, smn, accumulate, kchunk, side, side_k);
     return last_err();
   }
   int kchunk = ((K + splits - 1) / splits + BK - 1) / BK * BK;
   splits = (K + kchunk - 1) / kchunk;
   dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, splits);
-  k_gemm<<<grid, 256, 0, s>>>(M, N, K, A, sam, sak, B, sbk, sbn, C, scm, scn, bias, relu, mask, smm, smn, accumulate, kchunk);
+  k_gemm<<<grid, 256, 0, s>>>(M, N, K, A, sam, sak, B, sbk, sbn, C, scm, scn, bias, relu, mask, smm, smn, accumulate, kchunk, side, side_k);
   return last_err();
 }
 
@@ -293,13 +318,24 @@ extern "C" int apex_mlp_forward(const float *x, int rows, int in_dim, int hid, i
  * layer (k = in_dim, not a multiple of 64) and the narrow head stay on the SIMT kernels.  Opt-in: precision = "bf16". */
 extern "C" int apex_tc_linear_forward(const float *x, int M, int K, const float *w, const float *bias, int N, int relu, float *y,
                                       void *stream);
+extern "C" int apex_tc_linear_tiled(const void *xt, int M, int K, const float *w, void *wt_scratch, const float *bias, int N, int relu,
+                                    float *y, void *stream);
+extern "C" long apex_mlp_bf16_scratch_bytes(int rows, int hid);
 extern "C" int apex_mlp_forward_bf16(const float *x, int rows, int in_dim, int hid, int out_dim, const float *w1, const float *b1,
                                      const float *w2, const float *b2, const float *w3, const float *b3, float *h1, float *h2,
-                                     float *y, void *stream) {
+                                     float *y, void *scratch, long scratch_bytes, void *stream) {
   cudaStream_t s = (cudaStream_t)stream;
   int rc;
-  if ((rc = gemm(rows, hid, in_dim, x, in_dim, 1, w1, 1, in_dim, h1, hid, 1, b1, 1, nullptr, 0, 0, 0, 1, s))) return rc;
-  if ((rc = apex_tc_linear_forward(h1, rows, hid, w2, b2, hid, 1, h2, stream))) return rc;
+  const bool tma = scratch && scratch_bytes >= apex_mlp_bf16_scratch_bytes(rows, hid) && hid % 128 == 0 && hid <= 256 &&
+                   ((size_t)scratch & 15) == 0;
+  if (tma) { /* layer 1 writes h1 twice: float32 for the backward pass, tiled bf16 for the tensor core */
+    __nv_bfloat16 *h1t = (__nv_bfloat16 *)scratch, *w2t = h1t + (long)(rows + 127) / 128 * 128 * hid;
+    if ((rc = gemm(rows, hid, in_dim, x, in_dim, 1, w1, 1, in_dim, h1, hid, 1, b1, 1, nullptr, 0, 0, 0, 1, s, h1t, hid))) return rc;
+    if ((rc = apex_tc_linear_tiled(h1t, rows, hid, w2, w2t, b2, hid, 1, h2, stream))) return rc;
+  } else {
+    if ((rc = gemm(rows, hid, in_dim, x, in_dim, 1, w1, 1, in_dim, h1, hid, 1, b1, 1, nullptr, 0, 0, 0, 1, s))) return rc;
+    if ((rc = apex_tc_linear_forward(h1, rows, hid, w2, b2, hid, 1, h2, stream))) return rc;
+  }
   if ((rc = gemm(rows, out_dim, hid, h2, hid, 1, w3, 1, hid, y, out_dim, 1, b3, 0, nullptr, 0, 0, 0, 1, s))) return rc;
   return 0;
 }

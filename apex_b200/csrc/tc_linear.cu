@@ -272,11 +272,187 @@ __global__ void __launch_bounds__(256, 1) k_tc_linear_persistent(const float *__
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(2 * N));
 }
 
+/* ---------------------------------------------------------------------------------------------------------------------
+ * TMA version, used inside apex_mlp_forward_bf16: the producing layer's epilogue already wrote the activations as bf16 in
+ * the tiled shared-memory image (ppo_kernels.cu: tc_tiled_off), and the weights are converted to the same image once per
+ * call, so every operand reaches shared memory by cp.async.bulk (the bulk-copy engine; no thread touches the data):
+ *   warp 0 / one lane   producer: W (N x K bf16, 128 KB) once, then a ring of three 32 KB stages (128 rows x 128 k) of x;
+ *   warp 1 / one lane   MMA issuer: per stage 8 x tcgen05.mma (M 128, N, K 16), tcgen05.commit -> stage empty; per tile -> mma_done;
+ *   warps 4-7           epilogue (as above), accumulator double-buffered in TMEM.
+ * K is a multiple of 128 and N * K * 2 + 3 * 32 KB must fit in shared memory (256 x 256: 224 KB).
+ * --------------------------------------------------------------------------------------------------------------------- */
+#define TC_STAGE_BYTES 32768
+#define TC_NSTAGE 3
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("{ .reg .b64 st; mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1; }" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+template <int N>
+__global__ void __launch_bounds__(256, 1) k_tc_linear_tma(const __nv_bfloat16 *__restrict__ xt, int M, int K, const __nv_bfloat16 *__restrict__ wt,
+                                                          const float *__restrict__ bias, int relu, float *__restrict__ y) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char *sB = smem, *sA = smem + (size_t)N * K * 2;
+  __shared__ __align__(8) uint64_t bars[2 * TC_NSTAGE + 5]; /* full[3], empty[3], fullB, mma_done[2], tmem_free[2] */
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tiles = (M + TC_M - 1) / TC_M, halves = K >> 7;
+  uint32_t full[TC_NSTAGE], empty[TC_NSTAGE];
+  for (int i = 0; i < TC_NSTAGE; i++) { full[i] = smem_u32(&bars[i]); empty[i] = smem_u32(&bars[TC_NSTAGE + i]); }
+  const uint32_t fullB = smem_u32(&bars[2 * TC_NSTAGE]);
+  const uint32_t mma_done[2] = {smem_u32(&bars[2 * TC_NSTAGE + 1]), smem_u32(&bars[2 * TC_NSTAGE + 2])};
+  const uint32_t tmem_free[2] = {smem_u32(&bars[2 * TC_NSTAGE + 3]), smem_u32(&bars[2 * TC_NSTAGE + 4])};
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base_s)), "r"(2 * N));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  if (tid == 0) {
+    for (int i = 0; i < 2 * TC_NSTAGE + 3; i++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&bars[i])));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 128;" :: "r"(tmem_free[0]));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 128;" :: "r"(tmem_free[1]));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+  if (warp == 0) {
+    if (lane == 0) { /* ===== bulk-copy producer ===== */
+      const uint32_t wbytes = (uint32_t)N * K * 2;
+      mbar_expect_tx(fullB, wbytes);
+      for (uint32_t o = 0; o < wbytes; o += 16384) bulk_g2s(smem_u32(sB) + o, reinterpret_cast<const unsigned char *>(wt) + o, 16384, fullB);
+      int u = 0; /* stage uses so far */
+      for (int t = blockIdx.x; t < tiles; t += gridDim.x)
+        for (int h = 0; h < halves; h++, u++) {
+          const int st = u % TC_NSTAGE;
+          if (u >= TC_NSTAGE) mbar_wait(empty[st], ((u / TC_NSTAGE) - 1) & 1); /* the MMAs that read this stage have completed */
+          mbar_expect_tx(full[st], TC_STAGE_BYTES);
+          const unsigned char *src = reinterpret_cast<const unsigned char *>(xt) + ((size_t)t * halves + h) * TC_STAGE_BYTES;
+          bulk_g2s(smem_u32(sA) + st * TC_STAGE_BYTES, src, 16384, full[st]);
+          bulk_g2s(smem_u32(sA) + st * TC_STAGE_BYTES + 16384, src + 16384, 16384, full[st]);
+        }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) { /* ===== MMA issuer ===== */
+      mbar_wait(fullB, 0);
+      const uint32_t b0 = smem_u32(sB), sboB = (uint32_t)(K >> 3) * TC_LBO;
+      int u = 0, j = 0;
+      for (int t = blockIdx.x; t < tiles; t += gridDim.x, j++) {
+        const int b = j & 1;
+        if (j >= 2) mbar_wait(tmem_free[b], ((j >> 1) - 1) & 1); /* the epilogue has drained accumulator b */
+        const uint32_t d = tmem + (uint32_t)(b * N);
+        for (int h = 0; h < halves; h++, u++) {
+          const int st = u % TC_NSTAGE;
+          mbar_wait(full[st], (u / TC_NSTAGE) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t a0 = smem_u32(sA) + st * TC_STAGE_BYTES;
+#pragma unroll
+          for (int kk = 0; kk < 8; kk++) {
+            const uint64_t da = tc_smem_desc2(a0 + kk * 2 * TC_LBO, 2048), db = tc_smem_desc2(b0 + (h * 8 + kk) * 2 * TC_LBO, sboB);
+            const uint32_t acc = (h > 0 || kk > 0) ? 1u : 0u;
+            asm volatile("{ .reg .pred p; setp.ne.b32 p, %4, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p; }"
+                         :: "r"(d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+          }
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(empty[st]) : "memory");
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(mma_done[b]) : "memory");
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    /* ===== epilogue ===== */
+    const int q = warp & 3;
+    int j = 0;
+    for (int t = blockIdx.x; t < tiles; t += gridDim.x, j++) {
+      const int b = j & 1, row = t * TC_M + q * 32 + lane;
+      mbar_wait(mma_done[b], (j >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * N);
+      for (int c = 0; c < N; c += 32) {
+        uint32_t r[32];
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                     "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                       "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+                       "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+                       "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                     : "r"(taddr + (uint32_t)c));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (row < M) {
+          float4 *o = reinterpret_cast<float4 *>(y + (long)row * N + c);
+#pragma unroll
+          for (int g4 = 0; g4 < 8; g4++) {
+            float v[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+              v[e] = __uint_as_float(r[4 * g4 + e]) + (bias ? __ldg(bias + c + 4 * g4 + e) : 0.f);
+              if (relu) v[e] = fmaxf(v[e], 0.f);
+            }
+            o[g4] = make_float4(v[0], v[1], v[2], v[3]);
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(tmem_free[b]);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(2 * N));
+}
+
+/* W [N, K] float32 row-major -> bf16 core-matrix image (one block of N rows: SBO = K / 8 * 128 B) */
+__global__ void k_w_to_tiled(const float *__restrict__ w, int N, int K, __nv_bfloat16 *__restrict__ wt) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x, CH = K >> 3;
+  if (q >= N * CH) return;
+  const int n = q / CH, c = q % CH;
+  const float *p = w + (long)n * K + c * 8;
+  const uint4 v = pack8(make_float4(p[0], p[1], p[2], p[3]), make_float4(p[4], p[5], p[6], p[7]));
+  *reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(wt) + (size_t)(n >> 3) * CH * TC_LBO + c * TC_LBO + (n & 7) * 16) = v;
+}
+
 int apex_tc_persistent = 1; /* test hook: 0 forces the single-stage kernel */
 
 extern "C" {
 
 void apex_set_tc_persistent(int on) { apex_tc_persistent = on; }
+
+/* bytes of caller-owned scratch apex_mlp_forward_bf16 needs for `rows` rows and a hid x hid hidden layer: the tiled bf16 image of
+ * h1 (rows padded to 128) followed by the tiled bf16 image of W2.  Zero it once: padding rows are read by the tensor core. */
+long apex_mlp_bf16_scratch_bytes(int rows, int hid) { return ((long)(rows + 127) / 128 * 128 * hid + (long)hid * hid) * 2; }
+
+/* y = act(x W^T + b) with x given as the tiled bf16 image `xt` (written by the producing GEMM's side output) and W converted here.
+ * N = 256 or 128, K a multiple of 128, N * K * 2 + 96 KB of shared memory must fit. */
+int apex_tc_linear_tiled(const void *xt, int M, int K, const float *w, void *wt_scratch, const float *bias, int N, int relu, float *y,
+                         void *stream) {
+  if (M <= 0) return 0;
+  if (!xt || !w || !wt_scratch || !y || K % 128 != 0 || ((size_t)y & 15) || ((size_t)xt & 15) || ((size_t)wt_scratch & 15)) return -1000;
+  const long smem = (long)N * K * 2 + TC_NSTAGE * TC_STAGE_BYTES;
+  if (smem > 227 * 1024 || (N != 256 && N != 128)) return -1000;
+  cudaStream_t s = (cudaStream_t)stream;
+  k_w_to_tiled<<<(N * (K >> 3) + 255) / 256, 256, 0, s>>>(w, N, K, (__nv_bfloat16 *)wt_scratch);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int tiles = (M + TC_M - 1) / TC_M, grid = tiles < sms ? tiles : sms;
+  cudaError_t err;
+  if (N == 256) {
+    err = cudaFuncSetAttribute(k_tc_linear_tma<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return -(int)err;
+    k_tc_linear_tma<256><<<grid, 256, smem, s>>>((const __nv_bfloat16 *)xt, M, K, (const __nv_bfloat16 *)wt_scratch, bias, relu, y);
+  } else {
+    err = cudaFuncSetAttribute(k_tc_linear_tma<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return -(int)err;
+    k_tc_linear_tma<128><<<grid, 256, smem, s>>>((const __nv_bfloat16 *)xt, M, K, (const __nv_bfloat16 *)wt_scratch, bias, relu, y);
+  }
+  err = cudaGetLastError();
+  return err == cudaSuccess ? 0 : -(int)err;
+}
 
 /* y [M, N] = act(x [M, K] W^T + b), W [N, K] row-major (torch Linear), bf16 operands / float32 accumulate on tcgen05.
  * Supported: N in {64, 128, 256}, K a multiple of 64, y 16-byte aligned (x, W: any float alignment).  Returns -1000 for anything else. */

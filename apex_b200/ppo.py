@@ -180,9 +180,16 @@ class PPO:
                                         "critic_layers.1.bias", "network_out.weight", "network_out.bias")]
 
     def _mlp_fwd(self, ptrs, x, rows, out_dim, h1, h2, y):
-        fwd = self.L.apex_mlp_forward_bf16 if self.precision == "bf16" else self.L.apex_mlp_forward
-        _capi.check(fwd(_p(x), rows, self.obs_dim, self.hid, out_dim, ptrs[0][0], ptrs[1][0], ptrs[2][0], ptrs[3][0], ptrs[4][0],
-                        ptrs[5][0], _p(h1), _p(h2), _p(y), self._s()), "mlp_forward")
+        args = (_p(x), rows, self.obs_dim, self.hid, out_dim, ptrs[0][0], ptrs[1][0], ptrs[2][0], ptrs[3][0], ptrs[4][0], ptrs[5][0],
+                _p(h1), _p(h2), _p(y))
+        if self.precision == "bf16":
+            need = self.L.apex_mlp_bf16_scratch_bytes(rows, self.hid)
+            if getattr(self, "_tc_scratch", None) is None or self._tc_scratch.numel() < need:
+                self._tc_scratch = torch.zeros(need, dtype=torch.uint8, device=self.device)  # zeroed once: padding rows stay 0
+            _capi.check(self.L.apex_mlp_forward_bf16(*args, self._tc_scratch.data_ptr(), self._tc_scratch.numel(), self._s()),
+                        "mlp_forward_bf16")
+        else:
+            _capi.check(self.L.apex_mlp_forward(*args, self._s()), "mlp_forward")
         self.launches += 3
 
     def _mlp_bwd(self, ptrs, x, rows, out_dim, h1, h2, dy, dh2, dh1):

@@ -79,10 +79,17 @@ int apex_ars_update(float *theta, int P, const float *noise, const int64_t *idx,
 int apex_tc_linear_forward(const float *x, int M, int K, const float *w, const float *bias, int N, int relu, float *y, void *stream);
 /* test hook: 0 forces the single-stage tcgen05 kernel, 1 (default) the persistent warp-specialised one when W fits in shared memory */
 void apex_set_tc_persistent(int on);
-/* apex_mlp_forward with the hidden hid x hid layer on apex_tc_linear_forward (hid in {64, 128, 256}) */
+/* apex_mlp_forward with the hidden hid x hid layer on the tensor cores.  With `scratch` (caller-owned, zero-initialised once,
+ * >= apex_mlp_bf16_scratch_bytes(rows, hid) bytes, 16-byte aligned; hid 128 or 256) layer 1 also writes h1 as bf16 in the tiled
+ * shared-memory image and the hidden layer fetches its operands with cp.async.bulk (TMA); without it (NULL) the hidden layer
+ * converts float32 h1 on the fly (apex_tc_linear_forward). */
+long apex_mlp_bf16_scratch_bytes(int rows, int hid);
 int apex_mlp_forward_bf16(const float *x, int rows, int in_dim, int hid, int out_dim, const float *w1, const float *b1,
                           const float *w2, const float *b2, const float *w3, const float *b3, float *h1, float *h2, float *y,
-                          void *stream);
+                          void *scratch, long scratch_bytes, void *stream);
+/* the TMA hidden layer on its own: xt = tiled bf16 image of x [M, K] (rows padded to 128), wt_scratch = N * K * 2 bytes */
+int apex_tc_linear_tiled(const void *xt, int M, int K, const float *w, void *wt_scratch, const float *bias, int N, int relu, float *y,
+                         void *stream);
 /* test hook: 0 routes every GEMM through the 64 x 64 tile kernel, 1 (default) uses the 128 x 128 one when M, N >= 128 */
 void apex_set_gemm_large_tiles(int on);
 /* tuning: minimum number of 128 x 128 tiles (x split-k) for the large-tile kernel to be chosen (default 148 = one per SM) */

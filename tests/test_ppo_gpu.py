@@ -264,23 +264,38 @@ def test_tcgen05_linear_matches_bf16_emulation(rows, N, K, persistent):
         assert err < 2e-5 * float(ref.abs().max()), (relu, err)
 
 
-def test_mlp_forward_bf16_close_to_float32():
+@pytest.mark.parametrize("rows", [128, 4096, 70001])
+def test_mlp_forward_bf16_close_to_float32(rows):
+    """apex_mlp_forward_bf16, both routes (TMA from the tiled bf16 side output of layer 1; float32 h1 converted on the fly),
+    against (a) the same arithmetic in torch: h1 float32, rounded to bf16 with W2, float64 accumulate; (b) the float32 MLP."""
     from apex_b200 import _capi
     L = _capi.lib()
     dev = torch.device("cuda:0")
     g = torch.Generator(device=dev).manual_seed(3)
     r = lambda *s: torch.randn(s, device=dev, generator=g, dtype=torch.float32)
-    rows, H = 4096, 256
+    H = 256
     x, w1, b1, w2, b2, w3, b3 = r(rows, 50), r(H, 50) * 0.1, r(H) * 0.1, r(H, H) * 0.06, r(H) * 0.1, r(10, H) * 0.06, r(10)
     p = lambda t: t.data_ptr()
-    out = []
-    for fn in (L.apex_mlp_forward, L.apex_mlp_forward_bf16):
+
+    def run(kind):
         h1, h2, y = torch.zeros(rows, H, device=dev), torch.zeros(rows, H, device=dev), torch.zeros(rows, 10, device=dev)
-        _capi.check(fn(p(x), rows, 50, H, 10, p(w1), p(b1), p(w2), p(b2), p(w3), p(b3), p(h1), p(h2), p(y), None), "fwd")
-        out.append(y)
-    torch.cuda.synchronize()
-    scale = float(out[0].abs().max())
-    assert float((out[0] - out[1]).abs().max()) < 2e-2 * scale  # bf16 operands: ~3 significant digits
+        a = (p(x), rows, 50, H, 10, p(w1), p(b1), p(w2), p(b2), p(w3), p(b3), p(h1), p(h2), p(y))
+        if kind == "f32":
+            _capi.check(L.apex_mlp_forward(*a, None), "fwd")
+        elif kind == "tma":
+            scratch = torch.zeros(L.apex_mlp_bf16_scratch_bytes(rows, H), dtype=torch.uint8, device=dev)
+            _capi.check(L.apex_mlp_forward_bf16(*a, p(scratch), scratch.numel(), None), "fwd_tma")
+        else:
+            _capi.check(L.apex_mlp_forward_bf16(*a, None, 0, None), "fwd_convert")
+        torch.cuda.synchronize()
+        return h1, h2, y
+    h1f, h2f, yf = run("f32")
+    ref_h2 = torch.relu(h1f.bfloat16().double() @ w2.bfloat16().double().T + b2.double())
+    for kind in ("tma", "convert"):
+        h1, h2, y = run(kind)
+        assert torch.equal(h1, h1f), kind
+        assert float((h2.double() - ref_h2).abs().max()) < 2e-5 * float(ref_h2.abs().max()), kind
+        assert float((y - yf).abs().max()) < 2e-2 * float(yf.abs().max()), kind  # bf16 operands: ~3 significant digits
 
 
 def test_ppo_iteration_with_bf16_tensor_core_forward():

@@ -29,7 +29,12 @@ for rows in (4096, 65536):
         return e0.elapsed_time(e1) / n * 1e3
     t_tc = timeit(lambda: L.apex_tc_linear_forward(p(x), rows, H, p(w), p(b), H, 1, p(y), None))
     t_f32 = timeit(lambda: L.apex_mlp_forward(p(x50), rows, 50, H, 10, p(w1), p(b1), p(w), p(b), p(w3), p(b3), p(h1), p(y), p(y2), None))
-    t_bf = timeit(lambda: L.apex_mlp_forward_bf16(p(x50), rows, 50, H, 10, p(w1), p(b1), p(w), p(b), p(w3), p(b3), p(h1), p(y), p(y2), None))
+    t_bf = timeit(lambda: L.apex_mlp_forward_bf16(p(x50), rows, 50, H, 10, p(w1), p(b1), p(w), p(b), p(w3), p(b3), p(h1), p(y), p(y2), None, 0, None))
+    scratch = torch.zeros(L.apex_mlp_bf16_scratch_bytes(rows, H), dtype=torch.uint8, device=dev)
+    t_tma = timeit(lambda: L.apex_mlp_forward_bf16(p(x50), rows, 50, H, 10, p(w1), p(b1), p(w), p(b), p(w3), p(b3), p(h1), p(y), p(y2), p(scratch), scratch.numel(), None))
+    wt = scratch[-H * H * 2:]
+    t_layer = timeit(lambda: L.apex_tc_linear_tiled(p(scratch), rows, H, p(w), p(wt), p(b), H, 1, p(y), None))
     fl = 2.0 * rows * H * H
     print(f"rows {rows}: tcgen05 hidden layer {t_tc:.1f} us = {fl / t_tc / 1e6:.1f} TFLOP/s; whole MLP forward float32 {t_f32:.1f} us, "
-          f"with tcgen05 hidden layer {t_bf:.1f} us")
+          f"with tcgen05 hidden layer (convert on the fly) {t_bf:.1f} us, (TMA from tiled bf16) {t_tma:.1f} us; "
+          f"TMA hidden layer alone {t_layer:.1f} us = {fl / t_layer / 1e6:.1f} TFLOP/s")
