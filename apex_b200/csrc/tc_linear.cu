@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(256, 1) k_tc_linear_persistent(const float *__
  * call, so every operand reaches shared memory by cp.async.bulk (the bulk-copy engine; no thread touches the data):
  *   warp 0 / one lane   producer: W (N x K bf16, 128 KB) once, then a ring of three 32 KB stages (128 rows x 128 k) of x;
  *   warp 1 / one lane   MMA issuer: per stage 8 x tcgen05.mma (M 128, N, K 16), tcgen05.commit -> stage empty; per tile -> mma_done;
- *   warps 4-7           epilogue (as above), accumulator double-buffered in TMEM.
+ *   warps 4-11          epilogue: TMEM lane quarter = warp % 4, column half = (warp - 4) / 4; accumulator double-buffered in TMEM.
  * K is a multiple of 128 and N * K * 2 + 3 * 32 KB must fit in shared memory (256 x 256: 224 KB).
  * --------------------------------------------------------------------------------------------------------------------- */
 #define TC_STAGE_BYTES 32768
@@ -292,7 +292,7 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
 }
 
 template <int N>
-__global__ void __launch_bounds__(256, 1) k_tc_linear_tma(const __nv_bfloat16 *__restrict__ xt, int M, int K, const __nv_bfloat16 *__restrict__ wt,
+__global__ void __launch_bounds__(384, 1) k_tc_linear_tma(const __nv_bfloat16 *__restrict__ xt, int M, int K, const __nv_bfloat16 *__restrict__ wt,
                                                           const float *__restrict__ bias, int relu, float *__restrict__ y) {
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char *sB = smem, *sA = smem + (size_t)N * K * 2;
@@ -311,8 +311,8 @@ __global__ void __launch_bounds__(256, 1) k_tc_linear_tma(const __nv_bfloat16 *_
   }
   if (tid == 0) {
     for (int i = 0; i < 2 * TC_NSTAGE + 3; i++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&bars[i])));
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 128;" :: "r"(tmem_free[0]));
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 128;" :: "r"(tmem_free[1]));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 256;" :: "r"(tmem_free[0])); /* eight epilogue warps */
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 256;" :: "r"(tmem_free[1]));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -365,15 +365,15 @@ __global__ void __launch_bounds__(256, 1) k_tc_linear_tma(const __nv_bfloat16 *_
     }
     __syncwarp();
   } else if (warp >= 4) {
-    /* ===== epilogue ===== */
-    const int q = warp & 3;
+    /* ===== epilogue: warps 4-11; warp % 4 = TMEM lane quarter (rows), (warp - 4) / 4 = column half ===== */
+    const int q = warp & 3, c_lo = ((warp - 4) >> 2) * (N / 2), c_hi = c_lo + N / 2;
     int j = 0;
     for (int t = blockIdx.x; t < tiles; t += gridDim.x, j++) {
       const int b = j & 1, row = t * TC_M + q * 32 + lane;
       mbar_wait(mma_done[b], (j >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * N);
-      for (int c = 0; c < N; c += 32) {
+      for (int c = c_lo; c < c_hi; c += 32) {
         uint32_t r[32];
         asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
                      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
@@ -444,11 +444,11 @@ int apex_tc_linear_tiled(const void *xt, int M, int K, const float *w, void *wt_
   if (N == 256) {
     err = cudaFuncSetAttribute(k_tc_linear_tma<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return -(int)err;
-    k_tc_linear_tma<256><<<grid, 256, smem, s>>>((const __nv_bfloat16 *)xt, M, K, (const __nv_bfloat16 *)wt_scratch, bias, relu, y);
+    k_tc_linear_tma<256><<<grid, 384, smem, s>>>((const __nv_bfloat16 *)xt, M, K, (const __nv_bfloat16 *)wt_scratch, bias, relu, y);
   } else {
     err = cudaFuncSetAttribute(k_tc_linear_tma<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return -(int)err;
-    k_tc_linear_tma<128><<<grid, 256, smem, s>>>((const __nv_bfloat16 *)xt, M, K, (const __nv_bfloat16 *)wt_scratch, bias, relu, y);
+    k_tc_linear_tma<128><<<grid, 384, smem, s>>>((const __nv_bfloat16 *)xt, M, K, (const __nv_bfloat16 *)wt_scratch, bias, relu, y);
   }
   err = cudaGetLastError();
   return err == cudaSuccess ? 0 : -(int)err;
