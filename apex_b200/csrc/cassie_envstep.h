@@ -87,10 +87,11 @@ template <typename T> CW_NOINL void cw_sim_step_pd(CassieWs<T> &w, int bar CW_LA
       w.y[Y_TACC + 0] = (1 - 2 * (yq * yq + z * z)) * a0 + 2 * (x * yq - qw * z) * a1 + 2 * (x * z + qw * yq) * a2;
       w.y[Y_TACC + 1] = 2 * (x * yq + qw * z) * a0 + (1 - 2 * (x * x + z * z)) * a1 + 2 * (yq * z - qw * x) * a2;
       w.y[Y_TACC + 2] = 2 * (x * z - qw * yq) * a0 + 2 * (yq * z + qw * x) * a1 + (1 - 2 * (x * x + yq * yq)) * a2 + (T)CM_GRAVITY_Z;
-      w.sti[I_DRIVEINIT] = 1; w.sti[I_JOINTINIT] = 1;
     }
   }
   CW_SYNC();
+  /* after the barrier: every lane has read dinit / jinit (the uniform loads at the top of this function) */
+  CW_FOR_LANES { if (lane == 0) { w.sti[I_DRIVEINIT] = 1; w.sti[I_JOINTINIT] = 1; } }
   cw_mj_step<T>(w, true, bar CW_LANE_ARG);
 }
 

@@ -734,6 +734,7 @@ template <typename T> CW_FN void cw_make_constraint(CassieWs<T> &w, const T *qpo
       }
       r += nrow;
     }
+    CW_SYNC(); /* every lane is past the loops that read w.ncon as their bound */
     CW_FOR_LANES { if (lane == 0) w.ncon = nc; }
   } else {
     CW_FOR_LANES { if (lane == 0) w.ncon = 0; }
