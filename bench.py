@@ -303,6 +303,13 @@ def main():
         traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_r01.json")))["dram_bytes_per_launch_4096"]
     except Exception:
         pass
+    issue = None
+    try:  # what actually binds the kernel (ncu --set full of the same kernel, committed summary)
+        prof = json.load(open(os.path.join(ROOT, "profiles", "ncu_envstep_r01_final.json")))
+        issue = {"issue_slots_active_pct": prof["issue_active_pct"], "busiest_pipe": "lsu", "busiest_pipe_pct": prof["pipe_pct"]["lsu"],
+                 "active_lanes_per_instruction": prof["active_lanes_per_instruction"], "source": "profiles/ncu_envstep_r01_final.json"}
+    except Exception:
+        pass
     achieved = ALGO_BYTES_PER_ENV_STEP * args.envs / (k_ms * 1e-3) / 1e9
     out = {"metric": "Cassie-v0 PPO env-steps/sec", "value": env_steps / (ms_step * 1e-3), "unit": "env-steps/s", "n_gpus": world,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -318,7 +325,7 @@ def main():
                             "ms": sum(rms) / len(rms), "note": "rank 0's device time of sample_parallel inside the timed steps"},
            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                         "traffic": traffic, "kernel": "k_env_step<float>", "kernel_ms": k_ms, "peak_source": peak_src,
-                        "kernel_share_of_step": sum(kms) / args.steps / ms_step,
+                        "kernel_share_of_step": sum(kms) / args.steps / ms_step, "compute_side": issue,
                         "note": "dynamics kernel is FP32-issue/latency bound (SURVEY.md §8d): HBM fraction is expected << 1%"}}
     if not args.no_cpu_baseline:
         v, cores, sample, _ = cpu_arm(1, 1)
