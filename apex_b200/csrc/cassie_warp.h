@@ -1098,6 +1098,12 @@ template <typename T> CW_NOINL void cw_mj_step(CassieWs<T> &w, bool integrate, i
       for (int o = 16; o > 0; o >>= 1) cost += __shfl_xor_sync(0xffffffffu, cost, o);
       T res0 = sacc + b0;
       if (cost > 0) { f0 = 0; res0 = b0; }
+      /* The row update in increment form: new f = max(f - res / A_ii, lb)  <=>  df = max(-res / A_ii, lb - f).  With
+       * ndi0 = -1 / A_ii and g0 = lb - f (a constant -3e38 for the unbounded equality rows, -f for the rows with f >= 0) a row
+       * step is one multiply and one max before the broadcast. */
+      const T ndi0 = -di0;
+      const bool bounded = lb0 == (T)0;
+      T g0 = bounded ? -f0 : lb0;
       for (int it = 0; it < CM_ITERATIONS; it++) {
         /* every lane evaluates its candidate at every row step; the residual it saw at its OWN step is captured by one
          * select, and the row's new force / cost improvement are recomputed from it once per sweep */
@@ -1107,17 +1113,16 @@ template <typename T> CW_NOINL void cw_mj_step(CassieWs<T> &w, bool integrate, i
           if (i0 >= n) break; /* tested once per 2 rows: a row >= n has di0 = 0 and a zero column, so its update is exactly 0 */
 #pragma unroll
           for (int i = i0; i < i0 + 2; i++) {
-            const T nf = cw_max(f0 - res0 * di0, lb0);
-            const T dl = __shfl_sync(0xffffffffu, nf - f0, i);
+            const T dl = __shfl_sync(0xffffffffu, cw_max(res0 * ndi0, g0), i);
             const bool own = lane == i;
             res_own = own ? res0 : res_own;
             res0 += dl * acol[i];
           }
         }
-        const T nf_own = cw_max(f0 - res_own * di0, lb0); /* same expression, same operands as at the own step */
-        const T dlo = nf_own - f0;
+        const T dlo = cw_max(res_own * ndi0, g0); /* same expression, same operands as at the own step */
         T imp = -dlo * (dlo * had0 + res_own);
-        f0 = nf_own;
+        f0 += dlo;
+        if (bounded) { f0 = cw_max(f0, (T)0); g0 = -f0; }
         for (int o = 16; o > 0; o >>= 1) imp += __shfl_xor_sync(0xffffffffu, imp, o);
         iters = it + 1;
         if (imp * scale < (T)1e-8) break;
