@@ -164,6 +164,7 @@ static int env_init_impl(int dtype, void *st, int *sti, int n, unsigned seed, in
 }
 
 static int env_reset_impl(int dtype, void *st, int *sti, int n, void *obs, const void *traj, int traj_rows, int traj_len, void *stream) {
+  if (n <= 0) return 0; /* an empty batch is a no-op whatever the pointers are */
   if (!obs) return -1000;
   const CassieTraj<float> tf = {(const float *)traj, traj_rows, traj_len};
   const CassieTraj<double> td = {(const double *)traj, traj_rows, traj_len};
@@ -177,6 +178,7 @@ static int env_reset_impl(int dtype, void *st, int *sti, int n, void *obs, const
 static int env_step_impl(int dtype, void *st, int *sti, int n, const void *action, void *obs, void *reward, int *done,
                          void *term_obs, int max_traj_len, const int *active, const void *traj, int traj_rows, int traj_len,
                          const int *order, void *stream) {
+  if (n <= 0) return 0;
   if (!action || !obs || !reward || !done) return -1000;
   int wpb = apex_cassie_warps_per_cta;
   if (dtype == 1 && wpb > 7) wpb = 7;

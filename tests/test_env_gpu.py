@@ -204,3 +204,30 @@ def test_reference_trained_policy_walks_on_the_gpu_kernel():
     for i, v in ((0, 0.5), (1, 1.0)):
         ref_x = float(runs[(runs[:, 0] == 50) & (runs[:, 1] == v)][0, 3])
         assert abs(float(walked[i]) - ref_x) < 0.15 * ref_x, (v, float(walked[i]), ref_x)
+
+
+def test_env_edge_cases():
+    """Ragged and degenerate batches through the C-ABI: n = 1 (one warp in a CTA of 14 slots), n = 15 (one full CTA + one env),
+    n = 0 (a no-op that returns 0), an all-inactive mask (nothing moves, done = 4), and max_traj_len = 1 (every step ends an
+    episode and resets in-kernel)."""
+    from apex_b200 import _capi
+    from apex_b200.envs import BatchedCassieEnv
+    L = _capi.lib()
+    ref = BatchedCassieEnv(15, dtype=torch.float64, seed=9, dynamics_randomization=True)
+    ref.reset()
+    act = torch.randn((15, 10), dtype=torch.float64, device=ref.device, generator=torch.Generator(device=ref.device).manual_seed(1)) * 0.2
+    o15 = ref.step(act)[0].clone()
+    one = BatchedCassieEnv(1, dtype=torch.float64, seed=9, dynamics_randomization=True)  # env id 0 of the same job
+    one.reset()
+    o1 = one.step(act[:1])[0]
+    assert torch.equal(o1[0], o15[0])  # an env's results do not depend on the batch it is stepped in
+    assert L.apex_cassie_env_step(1, None, None, 0, None, None, None, None, None, 0, None) == 0  # n = 0
+    st0, rew0 = ref.st.clone(), ref.rew.clone()
+    mask = torch.zeros(15, dtype=torch.int32, device=ref.device)
+    _, rew, done, _ = ref.step(act, active=mask)
+    assert torch.equal(ref.st, st0) and bool((done == 4).all()) and bool((rew == 0).all())
+    short = BatchedCassieEnv(15, dtype=torch.float32, seed=9, dynamics_randomization=False, max_traj_len=1)
+    short.reset()
+    for _ in range(3):
+        _, _, done, _ = short.step(act.float())
+        assert bool(((done & 2) != 0).all()) and bool((short.field("time") == 0).all())  # time-out flag set, env already reset
