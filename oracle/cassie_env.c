@@ -132,10 +132,14 @@ NOFMA void ce_clock_knots(double swing, double stance, double x[8], double *phas
 }
 static const double CLOCK_Y[4][8] = { /* reward "clock": have_incentive, stance_mode "zero" (cassie.py:88,218-224) */
     {-1, -1, 0, 0, 1, 1, 0, 0}, {1, 1, 0, 0, -1, -1, 0, 0}, {1, 1, 0, 0, -1, -1, 0, 0}, {-1, -1, 0, 0, 1, 1, 0, 0}};
-double ce_clock_eval(double swing, double stance, int which, double phase) {
+double ce_clock_eval(double swing, double stance, int which, double phase) { return ce_clock_eval_mode(swing, stance, 0, which, phase); }
+/* stance_mode 0 "zero" (what reward "clock" trains with, cassie.py:219), 1 "grounded" (what reset_for_test installs, cassie.py:701):
+ * the double-stance knots 2, 3, 6, 7 carry +1 on the force clocks and -1 on the velocity clocks (phase_function.py:53-56, 96-98) */
+double ce_clock_eval_mode(double swing, double stance, int stance_mode, int which, double phase) {
   double x[8], P;
   ce_clock_knots(swing, stance, x, &P);
-  const double *yv = CLOCK_Y[which];
+  double yv[8];
+  for (int k = 0; k < 8; k++) yv[k] = (stance_mode == 1 && (k & 2)) ? ((which & 1) ? -1.0 : 1.0) : CLOCK_Y[which][k];
   double xa, xb, ya, yb;
   if (phase < x[0]) { xa = x[7] - P; ya = yv[7]; xb = x[0]; yb = yv[0]; }
   else if (phase >= x[7]) { xa = x[7]; ya = yv[7]; xb = x[0] + P; yb = yv[0]; }
@@ -253,10 +257,10 @@ double ce_env_reward(ce_env_t *e, const double *action) { /* clock_reward, cassi
   pelvis_acc *= 0.25;
   double pelvis_motion = straight_diff + height_diff + pelvis_acc;
   /* the env stores create_phase_reward's (right, left) pair as (left_clock, right_clock) — cassie.py:559 */
-  double left_frc_clock = ce_clock_eval(e->swing_duration, e->stance_duration, 0, e->phase);
-  double left_vel_clock = ce_clock_eval(e->swing_duration, e->stance_duration, 1, e->phase);
-  double right_frc_clock = ce_clock_eval(e->swing_duration, e->stance_duration, 2, e->phase);
-  double right_vel_clock = ce_clock_eval(e->swing_duration, e->stance_duration, 3, e->phase);
+  double left_frc_clock = ce_clock_eval_mode(e->swing_duration, e->stance_duration, e->stance_mode, 0, e->phase);
+  double left_vel_clock = ce_clock_eval_mode(e->swing_duration, e->stance_duration, e->stance_mode, 1, e->phase);
+  double right_frc_clock = ce_clock_eval_mode(e->swing_duration, e->stance_duration, e->stance_mode, 2, e->phase);
+  double right_vel_clock = ce_clock_eval_mode(e->swing_duration, e->stance_duration, e->stance_mode, 3, e->phase);
   double foot_frc_score = tan(PI / 4 * left_frc_clock * nlf) + tan(PI / 4 * right_frc_clock * nrf);
   double foot_vel_score = tan(PI / 4 * left_vel_clock * nlv) + tan(PI / 4 * right_vel_clock * nrv);
   double hip_roll_penalty = fabs(qvel[6]) + fabs(qvel[13]);
@@ -426,6 +430,45 @@ void ce_env_reset_with(ce_env_t *e, const ce_reset_draws_t *dr, double *obs) { /
   e->l_foot_orient_cost = e->r_foot_orient_cost = e->hiproll_cost = e->hiproll_act = 0;
   ce_env_obs(e, obs);
 }
+
+/* CassieEnv.reset_for_test(full_reset=True) (cassie.py:682-733): the start state of the evaluation tools
+ * (tools/test_commands.py:69, tools/eval_perturb.py:31,89).  A fresh simulator (cassie_sim_full_reset: mj_resetData, which
+ * also clears xfrc_applied, plus re-initialised wrapper blocks), the synthetic cassie_state of reset_cassie_state
+ * (cassie.py:735-746), default dynamics, zero encoder noise, phase 0, speed 0, the 0.15 / 0.25 s clock.  Kept from before,
+ * as in the reference: side_speed, pd_in_t u, prev_action / prev_torque, motor torques, foot flags, last_pelvis_pos. */
+void ce_env_reset_for_test(ce_env_t *e, double *obs) {
+  e->phase = 0; e->time = 0; e->counter = 0; e->orient_add = 0; e->phase_add = 1; e->speed = 0;
+  e->swing_duration = 0.15; e->stance_duration = 0.25; e->stance_mode = 1; /* sticks: reset() never sets it back (cassie.py:548-559) */
+  double x[8];
+  ce_clock_knots(e->swing_duration, e->stance_duration, x, &e->phaselen);
+  memset(&e->d, 0, sizeof(e->d));
+  memset(e->delay, 0, sizeof(e->delay)); memset(e->drive_hist, 0, sizeof(e->drive_hist)); e->drive_init = 0;
+  memset(e->jx, 0, sizeof(e->jx)); memset(e->jy, 0, sizeof(e->jy)); e->joint_init = 0;
+  memset(e->o_mpos, 0, sizeof(e->o_mpos)); memset(e->o_mvel, 0, sizeof(e->o_mvel)); memset(e->o_mtorque, 0, sizeof(e->o_mtorque));
+  memset(e->o_jpos, 0, sizeof(e->o_jpos)); memset(e->o_jvel, 0, sizeof(e->o_jvel)); memset(e->o_quat, 0, sizeof(e->o_quat));
+  memset(e->o_gyro, 0, sizeof(e->o_gyro)); memset(e->o_acc, 0, sizeof(e->o_acc)); memset(e->o_ppos, 0, sizeof(e->o_ppos));
+  memset(e->o_pvel, 0, sizeof(e->o_pvel));
+  cp_model_default(&e->m);
+  memcpy(e->d.qpos, CM_qpos_init, sizeof(e->d.qpos));
+  cp_data_reset(&e->m, &e->d);
+  static const double MPOS[10] = {0.0045, 0, 0.4973, -1.1997, -1.5968, 0.0045, 0, 0.4973, -1.1997, -1.5968};
+  static const double JPOS[6] = {0, 1.4267, -1.5968, 0, 1.4267, -1.5968};
+  ce_state_out_t *y = &e->y;
+  y->pelvis_pos[0] = 0; y->pelvis_pos[1] = 0; y->pelvis_pos[2] = 1.01;
+  y->pelvis_quat[0] = 1; y->pelvis_quat[1] = y->pelvis_quat[2] = y->pelvis_quat[3] = 0;
+  memset(y->pelvis_rotvel, 0, sizeof(y->pelvis_rotvel)); memset(y->pelvis_transvel, 0, sizeof(y->pelvis_transvel));
+  memset(y->pelvis_transacc, 0, sizeof(y->pelvis_transacc));
+  y->terrain_height = 0;
+  memcpy(y->motor_pos, MPOS, sizeof(MPOS)); memset(y->motor_vel, 0, sizeof(y->motor_vel));
+  memcpy(y->joint_pos, JPOS, sizeof(JPOS)); memset(y->joint_vel, 0, sizeof(y->joint_vel));
+  memset(e->menc_noise, 0, sizeof(e->menc_noise)); memset(e->jenc_noise, 0, sizeof(e->jenc_noise));
+  ce_env_obs(e, obs);
+}
+/* sim.apply_force(xfrc, "cassie-pelvis") (cassiemujoco.py:99-103): stays applied until overwritten */
+void ce_env_apply_force(ce_env_t *e, const double xfrc[6]) { memcpy(e->d.xfrc_pelvis, xfrc, sizeof(e->d.xfrc_pelvis)); }
+void ce_env_set_phase_add(ce_env_t *e, double phase_add) { e->phase_add = phase_add; }
+void ce_env_set_speed(ce_env_t *e, double speed) { e->speed = speed; }
+double ce_env_sim_time(const ce_env_t *e) { return e->d.time; }
 
 void ce_env_reset(ce_env_t *e, double *obs) {
   ce_reset_draws_t dr;

@@ -56,6 +56,7 @@ typedef struct {
   int variant;
   const double *traj;
   int traj_rows, traj_len;
+  int stance_mode; /* 0 "zero" (reward "clock", cassie.py:219), 1 "grounded" once reset_for_test has run (cassie.py:701) */
 } ce_env_t;
 
 /* The random draws of one reset / one step (cassie.py:523-680, :483-491).  ce_env_reset / ce_env_step fill them from the
@@ -85,12 +86,18 @@ void ce_sim_step_pd(ce_env_t *e, const ce_pd_in_t *u, ce_state_out_t *y); /* cas
 void ce_clock_knots(double swing, double stance, double x[8], double *phaselen);
 void ce_clock_from_speed(double speed, double *swing, double *stance, double *phaselen); /* cassie.py:556-559 */
 double ce_clock_eval(double swing, double stance, int which, double phase); /* which: 0 r_frc 1 r_vel 2 l_frc 3 l_vel */
+double ce_clock_eval_mode(double swing, double stance, int stance_mode, int which, double phase);
 void ce_env_init(ce_env_t *e, uint32_t seed, uint32_t env_id, int dyn_rand);
 void ce_env_reset(ce_env_t *e, double *obs);
 void ce_env_set_trajectory(ce_env_t *e, const double *table, int rows, int len); /* switches the env to CassieTraj-v0 */
 void ce_batch_set_trajectory(ce_env_t *envs, int n, const double *table, int rows, int len);
 double ce_env_get_phase(const ce_env_t *e);
 void ce_env_set_command(ce_env_t *e, double speed, double side_speed, double phase); /* synthetic-input hook */
+void ce_env_reset_for_test(ce_env_t *e, double *obs);            /* CassieEnv.reset_for_test(full_reset=True), cassie.py:682-733 */
+void ce_env_apply_force(ce_env_t *e, const double xfrc[6]);      /* sim.apply_force on the pelvis, cassiemujoco.py:99-103 */
+void ce_env_set_phase_add(ce_env_t *e, double phase_add);        /* env.phase_add (tools/test_commands.py:84-87) */
+void ce_env_set_speed(ce_env_t *e, double speed);                /* env.speed = ... (tools/test_commands.py:70,81) */
+double ce_env_sim_time(const ce_env_t *e);                       /* sim.time() */
 void ce_env_step(ce_env_t *e, const double *action, double *obs, double *reward, int *done);
 void ce_env_obs(ce_env_t *e, double *obs);
 double ce_env_reward(ce_env_t *e, const double *action);

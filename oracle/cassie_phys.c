@@ -638,6 +638,17 @@ void cp_step2(const cp_model_t *m, cp_data_t *d) {
   }
   for (int i = 0; i < NV; i++) {
     d->qfrc_smooth[i] = d->qfrc_passive[i] - d->qfrc_bias[i] + d->qfrc_actuator[i];
+  }
+  { /* mj_xfrcAccumulate for the pelvis: the wrench (f, tau) at xipos, moved to the reference point org, projected on the
+     * pelvis' own six dofs (it has no ancestors): qfrc_i += cdof_ang_i . (tau + (xipos - org) x f) + cdof_lin_i . f */
+    const double *f = d->xfrc_pelvis, *tau = d->xfrc_pelvis + 3;
+    double r[3] = {d->xipos[1][0] - d->org[0], d->xipos[1][1] - d->org[1], d->xipos[1][2] - d->org[2]};
+    double t[3] = {tau[0] + r[1] * f[2] - r[2] * f[1], tau[1] + r[2] * f[0] - r[0] * f[2], tau[2] + r[0] * f[1] - r[1] * f[0]};
+    for (int i = 0; i < 6; i++)
+      d->qfrc_smooth[i] += d->cdof[i][0] * t[0] + d->cdof[i][1] * t[1] + d->cdof[i][2] * t[2] +
+                           d->cdof[i][3] * f[0] + d->cdof[i][4] * f[1] + d->cdof[i][5] * f[2];
+  }
+  for (int i = 0; i < NV; i++) {
     d->qacc_smooth[i] = d->qfrc_smooth[i];
   }
   chol_solve(d->L, d->qacc_smooth);

@@ -68,6 +68,9 @@ typedef struct {
   /* sensor snapshot: positions/velocities from step1, accelerometer from step2 */
   double sens_actpos[CM_NU], sens_actvel[CM_NU], sens_jpos[6], sens_quat[4], sens_gyro[3], sens_acc[3];
   double sens_pelvis_pos[3], sens_pelvis_vel[3];
+  /* mjData.xfrc_applied of the pelvis body: (force, torque), world axes, applied at the body's centre of mass.  The one body
+   * the reference pushes (cassiemujoco.py:99-103 apply_force default, tools/eval_perturb.py:60); kept across steps */
+  double xfrc_pelvis[6];
 } cp_data_t;
 
 #ifdef __cplusplus

@@ -12,7 +12,7 @@
  *
  * Implemented: the hot subset the Cassie-v0 env calls (cassie_mujoco_init, cassie_sim_init/free/step_pd/time/qpos/
  * qvel/qacc/xquat/foot_forces/foot_positions, the dof_damping / body_mass / body_ipos / geom_friction / geom_quat /
- * geom_rgba getters and setters, set_const, full_reset).  Everything else (visualiser, UDP, packing, the stand-alone
+ * geom_rgba getters and setters, set_const, full_reset, apply_force on the pelvis).  Everything else (visualiser, UDP, packing, the stand-alone
  * Agility blocks, height fields) is an inert stub: it exists so the import succeeds.
  */
 #include <stdbool.h>
@@ -127,7 +127,9 @@ void cassie_sim_foot_positions(const cassie_sim_t *c, double cpos[6]) { cp_foot_
 void cassie_sim_foot_velocities(const cassie_sim_t *c, double cvel[12]) { (void)c; memset(cvel, 0, 12 * sizeof(double)); }
 void cassie_sim_foot_orient(const cassie_sim_t *c, double corient[4]) { memcpy(corient, c->e.d.xquat[13], 4 * sizeof(double)); }
 void cassie_sim_body_velocities(const cassie_sim_t *c, double cvel[6], const char *name) { (void)c; (void)name; memset(cvel, 0, 6 * sizeof(double)); }
-void cassie_sim_apply_force(cassie_sim_t *c, double xfrc[6], const char *name) { (void)c; (void)xfrc; (void)name; }
+void cassie_sim_apply_force(cassie_sim_t *c, double xfrc[6], const char *name) { /* only the body the reference pushes */
+  if (name && strcmp(name, "cassie-pelvis") == 0) ce_env_apply_force(&c->e, xfrc);
+}
 double *cassie_sim_xquat(cassie_sim_t *c, const char *name) { /* mj_name2id on the three bodies the env asks for */
   int b = 0;
   if (name && strcmp(name, "cassie-pelvis") == 0) b = 1;

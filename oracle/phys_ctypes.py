@@ -35,7 +35,7 @@ class Data(C.Structure):
         ("qfrc_passive", D * NV), ("qfrc_actuator", D * NV), ("qfrc_smooth", D * NV), ("qacc_smooth", D * NV),
         ("qfrc_constraint", D * NV), ("solver_iter", C.c_int), ("sens_actpos", D * NU), ("sens_actvel", D * NU),
         ("sens_jpos", D * 6), ("sens_quat", D * 4), ("sens_gyro", D * 3), ("sens_acc", D * 3),
-        ("sens_pelvis_pos", D * 3), ("sens_pelvis_vel", D * 3)]
+        ("sens_pelvis_pos", D * 3), ("sens_pelvis_vel", D * 3), ("xfrc_pelvis", D * 6)]
 
 
 def build(force=False):

@@ -84,3 +84,28 @@ class OracleEnv:
         base = C.addressof(self.buf) + C.sizeof(P.Model)
         d = P.Data.from_address(base)
         return np.array(d.qpos[:]), np.array(d.qvel[:])
+
+    # ---- what the reference's evaluation tools do to an env (tools/test_commands.py, tools/eval_perturb.py)
+    def reset_for_test(self):
+        self.L.ce_env_reset_for_test(self.buf, dp(self.obs))
+        return self.obs.copy()
+
+    def apply_force(self, xfrc):
+        x = np.ascontiguousarray(xfrc, dtype=np.float64)
+        self.L.ce_env_apply_force(self.buf, dp(x))
+
+    def set_speed(self, speed):
+        self.L.ce_env_set_speed.argtypes = [C.c_void_p, C.c_double]
+        self.L.ce_env_set_speed(self.buf, float(speed))
+
+    def set_phase_add(self, phase_add):
+        self.L.ce_env_set_phase_add.argtypes = [C.c_void_p, C.c_double]
+        self.L.ce_env_set_phase_add(self.buf, float(phase_add))
+
+    def sim_time(self):
+        self.L.ce_env_sim_time.restype = C.c_double
+        return self.L.ce_env_sim_time(self.buf)
+
+    def phase(self):
+        self.L.ce_env_get_phase.restype = C.c_double
+        return self.L.ce_env_get_phase(self.buf)

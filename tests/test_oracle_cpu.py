@@ -118,6 +118,52 @@ def test_momentum_and_bias_consistency(L):
         flags.value = 0
 
 
+def test_applied_wrench_on_the_pelvis_changes_momentum_as_it_should(L):
+    """mjData.xfrc_applied on the pelvis (sim.apply_force, tools/eval_perturb.py:60): with no constraints and no damping the
+    linear momentum changes by (m g + F) t and the angular momentum about the COM by the integral of tau + (r_pelvis - com) x F."""
+    m, d = _fresh(L)
+    flags = C.c_int.in_dll(L, "cp_debug_flags")
+    flags.value = 1
+    try:
+        for i in range(32):
+            m.dof_damping[i] = 0
+        F, tau = np.array([30.0, -20.0, 10.0]), np.array([2.0, -3.0, 4.0])
+        for k in range(3):
+            d.xfrc_pelvis[k], d.xfrc_pelvis[3 + k] = F[k], tau[k]
+        src = open(os.path.join(ROOT, "oracle", "cassie_model.h")).read()
+        mm = re.search(r"CM_body_inertia\[[^=]*=\s*\{(.*?)\};", src, re.S)
+        inert = np.array([float(x) for x in re.findall(r"-?\d+\.?\d*(?:e-?\d+)?", mm.group(1))]).reshape(26, 6)
+        mass = np.array(m.body_mass)
+
+        def mom():
+            xi, xm, cv, org = np.array(d.xipos), np.array(d.xmat).reshape(26, 3, 3), np.array(d.cvel), np.array(d.org)
+            com = (mass[:, None] * xi).sum(0) / mass.sum()
+            p, Lc = np.zeros(3), np.zeros(3)
+            for b in range(1, 26):
+                w = cv[b, :3]
+                vb = cv[b, 3:] + np.cross(w, xi[b] - org)
+                I = inert[b]
+                Ib = np.array([[I[0], I[3], I[4]], [I[3], I[1], I[5]], [I[4], I[5], I[2]]])
+                p += mass[b] * vb
+                Lc += np.cross(xi[b] - com, mass[b] * vb) + xm[b] @ Ib @ xm[b].T @ w
+            return p, Lc, tau + np.cross(xi[1] - com, F)
+        L.cp_step1(C.byref(m), C.byref(d))
+        p0, L0, t0 = mom()
+        impulse, n, h = np.zeros(3), 200, 0.0005
+        for _ in range(n):
+            L.cp_step(C.byref(m), C.byref(d))
+            L.cp_step1(C.byref(m), C.byref(d))
+            p1, L1, t1 = mom()
+            impulse += 0.5 * (t0 + t1) * h
+            t0 = t1
+        assert np.abs((p1 - p0) - (np.array([0, 0, -9.81 * mass.sum()]) + F) * n * h).max() < 2e-3
+        assert np.abs((L1 - L0) - impulse).max() < 3e-3 and np.abs(impulse).min() > 0.1
+    finally:
+        flags.value = 0
+        for k in range(6):
+            d.xfrc_pelvis[k] = 0
+
+
 def test_standing_contact_forces_support_weight(L):
     """Zero-action PD stance: once the feet are down the vertical contact force carries the 33.3 kg robot."""
     n = 1
@@ -265,6 +311,54 @@ def test_env_layer_matches_the_reference_python(tag, dyn, traj):
             assert err.max() < 1e-9, (ep, k, int(err.argmax()), err.max())
             t += 1
     assert t == len(f("reward")) and f("done").sum() >= 1  # at least one episode ends by falling
+
+
+def _eval_schedule():
+    """The schedule tests/golden/make_eval_golden.py drove the reference env with (imported from that script)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_eval_golden", os.path.join(G, "make_eval_golden.py"))
+    src = open(os.path.join(G, "make_eval_golden.py")).read()
+    ns = {}
+    for line in src.splitlines():  # the five constant tables only: the script itself imports the reference tree
+        if line.split(" = ")[0] in ("SPEED", "PHASE_ADD", "FORCE", "RESET_AT", "STEPS"):
+            exec(line, ns)
+    return ns
+
+
+@pytest.mark.parametrize("tag,dyn", [("plain", False), ("dynrand", True)])
+def test_eval_entry_points_match_the_reference_python(tag, dyn):
+    """reset_for_test(full_reset=True), env.speed / env.phase_add assignments, sim.apply_force on the pelvis and sim.time()
+    (what tools/test_commands.py and tools/eval_perturb.py do to a CassieEnv), recorded from the reference's
+    cassie/cassie.py over oracle/cassiemujoco_abi.c and replayed through oracle/cassie_env.c."""
+    from tests.oracle_util import OracleEnv
+    g = np.load(os.path.join(G, "eval_episodes.npz"))
+    f = lambda k: g[f"{tag}.{k}"]
+    sch = _eval_schedule()
+    env = OracleEnv(dyn)
+    env.reset_with(f("pre_reset_scalar"), f("pre_reset_damping"), f("pre_reset_mass"), f("pre_reset_friction"), f("pre_reset_tilt"),
+                   f("pre_reset_menc_noise"), f("pre_reset_jenc_noise"))
+    for a, h, v in zip(f("pre_action"), f("pre_hit"), f("pre_val")):
+        env.step_with(a, h, v)
+    nreset = 0
+    for t in range(sch["STEPS"]):
+        if t in sch["RESET_AT"]:
+            obs = env.reset_for_test()
+            assert np.abs(obs - f("reset_obs")[nreset]).max() < 1e-12, (t, int(np.abs(obs - f("reset_obs")[nreset]).argmax()))
+            assert np.abs(env.qpos_qvel()[0] - f("reset_qpos")[nreset]).max() < 1e-14
+            nreset += 1
+        if t in sch["SPEED"]:
+            env.set_speed(sch["SPEED"][t])
+        if t in sch["PHASE_ADD"]:
+            env.set_phase_add(sch["PHASE_ADD"][t])
+        if t in sch["FORCE"]:
+            env.apply_force(sch["FORCE"][t])
+        obs, rew, done = env.step_with(f("action")[t], f("step_hit")[t], f("step_val")[t])
+        qpos, qvel = env.qpos_qvel()
+        assert np.abs(qpos - f("qpos")[t]).max() < 1e-10 and np.abs(qvel - f("qvel")[t]).max() < 1e-8, t
+        assert done == f("done")[t] and abs(rew - f("reward")[t]) < 1e-10, t
+        assert np.abs(obs - f("obs")[t]).max() < 1e-9, (t, int(np.abs(obs - f("obs")[t]).argmax()))
+        assert env.phase() == f("phase")[t] and abs(env.sim_time() - f("sim_time")[t]) < 1e-15, t
+    assert nreset == 2
 
 
 def test_reference_abi_exports_all_103_symbols():
