@@ -36,6 +36,16 @@ template <typename T> __global__ void __launch_bounds__(32) k_env_reset(T *st, i
   ws_store(w, st + (size_t)e * S_WORDS, sti + (size_t)e * I_WORDS, lane);
 }
 
+template <typename T> __global__ void __launch_bounds__(32) k_env_reset_for_test(T *st, int *sti, int n, T *obs, const int *active) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  CassieWs<T> &w = *reinterpret_cast<CassieWs<T> *>(smem);
+  const int e = blockIdx.x, lane = threadIdx.x;
+  if (e >= n || (active && !active[e])) return;
+  ws_load(w, st + (size_t)e * S_WORDS, sti + (size_t)e * I_WORDS, lane);
+  cw_env_reset_for_test<T>(w, obs + (size_t)e * CW_OBS, lane);
+  ws_store(w, st + (size_t)e * S_WORDS, sti + (size_t)e * I_WORDS, lane);
+}
+
 /* W warps (= W envs) per CTA; the CTA barrier inside cw_env_step's sub-step loop must be reached by every warp, so
  * warps past the end of the batch run the barriers only. */
 template <typename T>
@@ -136,10 +146,11 @@ int apex_cassie_layout(const char *name) {
       {"stance", S_STANCE}, {"prev_action", S_PREV_ACTION}, {"prev_torque", S_PREV_TORQUE}, {"menc_noise", S_MENC},
       {"jenc_noise", S_JENC}, {"last_pelvis_pos", S_LASTPELVIS}, {"dof_damping", S_DAMPING}, {"body_mass", S_MASS},
       {"friction", S_FRICTION}, {"floor_quat", S_FLOORQ}, {"dof_invweight0", S_DOFINVW}, {"body_invweight0", S_BODYINVW},
-      {"meaninertia", S_MEANINERTIA}, {"footvel", S_FOOTVEL},
+      {"meaninertia", S_MEANINERTIA}, {"footvel", S_FOOTVEL}, {"xfrc_applied", S_XFRC}, {"phase_add", S_PHASEADD},
       {"drive_hist", I_DRIVEHIST}, {"time", I_TIME}, {"counter", I_COUNTER}, {"has_prev", I_HASPREV}, {"has_u", I_HASU},
       {"drive_init", I_DRIVEINIT}, {"joint_init", I_JOINTINIT}, {"flags", I_FLAGS}, {"stepcount", I_STEPCOUNT}, {"rng_ctr", I_RNGCTR},
-      {"env_id", I_ENVID}, {"seed", I_SEED}, {"dyn_rand", I_DYNRAND}, {"solver_iter", I_SOLVER_ITER}, {"ncon", I_NCON}, {"nefc", I_NEFC}, {"variant", I_VARIANT}, {"phase_floor", I_PHASEFLOOR}, {"cost", I_COST}};
+      {"env_id", I_ENVID}, {"seed", I_SEED}, {"dyn_rand", I_DYNRAND}, {"solver_iter", I_SOLVER_ITER}, {"ncon", I_NCON}, {"nefc", I_NEFC}, {"variant", I_VARIANT}, {"phase_floor", I_PHASEFLOOR}, {"cost", I_COST},
+      {"stance_mode", I_STANCEMODE}, {"sim_steps", I_SIMSTEPS}, {"hold_commands", I_HOLDCMD}};
   for (size_t i = 0; i < sizeof(tab) / sizeof(tab[0]); i++)
     if (strcmp(tab[i].n, name) == 0) return tab[i].off;
   return -1;
@@ -200,6 +211,16 @@ int apex_cassie_env_init(int dtype, void *st, int *sti, int n, unsigned seed, in
 }
 int apex_cassie_env_reset(int dtype, void *st, int *sti, int n, void *obs, void *stream) {
   return env_reset_impl(dtype, st, sti, n, obs, nullptr, 0, 0, stream);
+}
+/* CassieEnv.reset_for_test(full_reset=True) for the envs whose active flag is set (all when active is NULL) */
+int apex_cassie_env_reset_for_test(int dtype, void *st, int *sti, int n, void *obs, const int *active, void *stream) {
+  if (n <= 0) return 0;
+  if (!obs) return -1000;
+  DISPATCH(
+      if ((rc = prep(k_env_reset_for_test<float>, sizeof(CassieWs<float>)))) return rc;
+      (k_env_reset_for_test<float><<<n, 32, sizeof(CassieWs<float>), s>>>((float *)st, sti, n, (float *)obs, active)),
+      if ((rc = prep(k_env_reset_for_test<double>, sizeof(CassieWs<double>)))) return rc;
+      (k_env_reset_for_test<double><<<n, 32, sizeof(CassieWs<double>), s>>>((double *)st, sti, n, (double *)obs, active)))
 }
 int apex_cassie_env_step(int dtype, void *st, int *sti, int n, const void *action, void *obs, void *reward, int *done,
                          void *term_obs, int max_traj_len, void *stream) {

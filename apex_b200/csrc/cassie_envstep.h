@@ -105,14 +105,19 @@ template <typename T> CW_FN void cw_clock_knots(T swing, T stance, T *x, T *phas
   }
   *phaselen = seg[4] * F;
 }
-template <typename T> CW_FN T cw_clock_eval(const T *x, T P, int which, T phase) {
+/* knot value k of clock `which`; stance_mode 1 ("grounded", installed by reset_for_test, cassie.py:701) puts +1 on the force
+ * clocks and -1 on the velocity clocks at the double-stance knots 2, 3, 6, 7 (phase_function.py:53-56, 96-98) */
+template <typename T> CW_FN T cw_clock_y(int which, int k, int mode) {
+  return (mode == 1 && (k & 2)) ? ((which & 1) ? (T)-1 : (T)1) : (T)CWT(CW_CLOCK_Y)[which][k];
+}
+template <typename T> CW_FN T cw_clock_eval(const T *x, T P, int which, T phase, int mode) {
   T xa, xb, ya, yb;
-  if (phase < x[0]) { xa = x[7] - P; ya = (T)CWT(CW_CLOCK_Y)[which][7]; xb = x[0]; yb = (T)CWT(CW_CLOCK_Y)[which][0]; }
-  else if (phase >= x[7]) { xa = x[7]; ya = (T)CWT(CW_CLOCK_Y)[which][7]; xb = x[0] + P; yb = (T)CWT(CW_CLOCK_Y)[which][0]; }
+  if (phase < x[0]) { xa = x[7] - P; ya = cw_clock_y<T>(which, 7, mode); xb = x[0]; yb = cw_clock_y<T>(which, 0, mode); }
+  else if (phase >= x[7]) { xa = x[7]; ya = cw_clock_y<T>(which, 7, mode); xb = x[0] + P; yb = cw_clock_y<T>(which, 0, mode); }
   else {
     int k = 0;
     while (k < 6 && phase >= x[k + 1]) k++;
-    xa = x[k]; xb = x[k + 1]; ya = (T)CWT(CW_CLOCK_Y)[which][k]; yb = (T)CWT(CW_CLOCK_Y)[which][k + 1];
+    xa = x[k]; xb = x[k + 1]; ya = cw_clock_y<T>(which, k, mode); yb = cw_clock_y<T>(which, k + 1, mode);
   }
   const T t = (phase - xa) / (xb - xa);
   return ya + (yb - ya) * t * t * (3 - 2 * t);
@@ -246,7 +251,7 @@ template <typename T> CW_NOINL void cw_env_init(CassieWs<T> &w, uint32_t seed, u
     for (int k = lane; k < CM_NQ; k += 32) w.st[S_QPOS + k] = (T)CMT(qpos_init)[k];
     if (lane == 0) {
       w.st[S_FRICTION] = 1; w.st[S_FLOORQ] = 1;
-      w.st[S_PHASELEN] = 32; w.sti[I_PHASEFLOOR] = 32;
+      w.st[S_PHASELEN] = 32; w.sti[I_PHASEFLOOR] = 32; w.st[S_PHASEADD] = 1;
       w.sti[I_SEED] = (int)seed; w.sti[I_ENVID] = (int)env_id; w.sti[I_DYNRAND] = dyn_rand;
     }
   }
@@ -369,6 +374,53 @@ template <typename T> CW_NOINL void cw_env_reset(CassieWs<T> &w, T *obs_out, con
     if (lane == 0) {
       w.st[S_ORIENT] = 0; w.st[S_SPEED] = speed1; w.st[S_SIDE] = side1;
       w.sti[I_RNGCTR] = (int)(ctr0 + (uint32_t)((nd + 2 + 3) >> 2));
+      w.sti[I_SIMSTEPS] = 1; /* cassie_sim_set_const zeroed the time, then the one sub-step above */
+    }
+  }
+  CW_SYNC();
+  cw_env_obs<T>(w, obs_out CW_LANE_ARG);
+}
+
+/* ---------- CassieEnv.reset_for_test(full_reset=True) (cassie.py:682-733) ----------
+ * The start state of tools/test_commands.py:69 and tools/eval_perturb.py:31,89.  A fresh simulator (cassie_sim_full_reset:
+ * mjData cleared incl. xfrc_applied, wrapper blocks re-initialised), default dynamics, zero encoder noise, phase 0, speed 0,
+ * phase_add 1, the 0.15 / 0.25 s "grounded" clock, and an observation built from the synthetic cassie_state of
+ * reset_cassie_state (cassie.py:735-746) rather than from the simulator.  Kept, as in the reference: side_speed, the PD
+ * target u, prev_action / prev_torque, foot flags, last_pelvis_pos, the RNG stream. */
+template <typename T> CW_NOINL void cw_env_reset_for_test(CassieWs<T> &w, T *obs_out CW_LANE_PARAM) {
+  CW_FOR_LANES {
+    for (int k = S_QVEL + lane; k < S_UPTARGET; k += 32) w.st[k] = 0; /* qvel, warm start, ctrl, sensors, delay line, filters */
+    for (int k = lane; k < CM_NQ; k += 32) w.st[S_QPOS + k] = (T)CMT(qpos_init)[k];
+    for (int k = lane; k < 90; k += 32) w.sti[I_DRIVEHIST + k] = 0;
+    w.st[S_DAMPING + lane] = (T)CMT(dof_damping)[lane];
+    if (lane < CW_NB) w.st[S_MASS + lane] = (T)CMT(body_mass)[lane];
+    if (lane < 10) w.st[S_MENC + lane] = 0;
+    else if (lane < 16) w.st[S_JENC + lane - 10] = 0;
+    else if (lane < 22) w.st[S_XFRC + lane - 16] = 0;
+    else if (lane < 26) w.st[S_FLOORQ + lane - 22] = lane == 22 ? (T)1 : (T)0;
+    if (lane == 31) {
+      w.st[S_FRICTION] = 1;
+      w.st[S_PHASE] = 0; w.st[S_SPEED] = 0; w.st[S_ORIENT] = 0; w.st[S_PHASEADD] = 1;
+      w.st[S_SWING] = (T)0.15; w.st[S_STANCE] = (T)0.25; w.st[S_PHASELEN] = 32; w.sti[I_PHASEFLOOR] = 32; /* (0.3 + 0.5) * 40 */
+      w.sti[I_TIME] = 0; w.sti[I_COUNTER] = 0; w.sti[I_DRIVEINIT] = 0; w.sti[I_JOINTINIT] = 0;
+      w.sti[I_STANCEMODE] = 1; w.sti[I_SIMSTEPS] = 0;
+    }
+  }
+  CW_SYNC();
+  cw_set_const<T>(w CW_LANE_ARG);
+  cw_mj_step<T>(w, false, 0 CW_LANE_ARG);
+  T fp[6];
+  cw_foot_positions<T>(w, fp);
+  CW_SYNC();
+  CW_FOR_LANES {
+    if (lane < 6) w.st[S_FOOTPOS + lane] = fp[lane];
+    for (int k = lane; k < Y_WORDS; k += 32) {
+      T v = 0;
+      if (k == Y_PPOS + 2) v = (T)1.01;
+      else if (k == Y_QUAT) v = 1;
+      else if (k >= Y_MPOS && k < Y_MPOS + 10) v = (T)CWT(CW_OFFSET)[k - Y_MPOS];
+      else if (k >= Y_JPOS && k < Y_JPOS + 6) { const int j = (k - Y_JPOS) % 3; v = j == 0 ? (T)0 : (j == 1 ? (T)1.4267 : (T)-1.5968); }
+      w.y[k] = v;
     }
   }
   CW_SYNC();
@@ -419,10 +471,14 @@ template <typename T> CW_NOINL void cw_env_step(CassieWs<T> &w, T *obs_out, T *r
   const T height = qpos[2];
   const int time = w.sti[I_TIME] + 1;
   int counter = w.sti[I_COUNTER];
-  T phase = w.st[S_PHASE] + (T)1;
+  T phase = w.st[S_PHASE] + w.st[S_PHASEADD];
   const T plen = w.st[S_PHASELEN];
   int wrapped = 0;
-  if ((int)phase > w.sti[I_PHASEFLOOR]) { phase = 0; counter++; wrapped = 1; } /* phase > phaselen for an integer phase */
+  { /* phase > phaselen: decided on floor(phaselen) from float64 when the phase is an integer (training: phase_add = 1), on the
+     * stored period only inside the last unit interval (phase_add = 1.5, tools/test_commands.py:84-87) */
+    const int ip = (int)phase, pf = w.sti[I_PHASEFLOOR];
+    if (ip > pf || (ip == pf && phase > plen)) { phase = 0; counter++; wrapped = 1; }
+  }
   int done = (height < (T)0.4 || height > (T)3.0) ? 1 : 0;
   const int hasprev = w.sti[I_HASPREV];
   /* clock_reward */
@@ -445,8 +501,9 @@ template <typename T> CW_NOINL void cw_env_step(CassieWs<T> &w, T *obs_out, T *r
     const T pelvis_motion = straight_diff + height_diff + pelvis_acc;
     T x[8], P;
     cw_clock_knots<T>(w.st[S_SWING], w.st[S_STANCE], x, &P);
-    const T lfc = cw_clock_eval<T>(x, P, 0, phase), lvc = cw_clock_eval<T>(x, P, 1, phase);
-    const T rfc = cw_clock_eval<T>(x, P, 2, phase), rvc = cw_clock_eval<T>(x, P, 3, phase);
+    const int sm = w.sti[I_STANCEMODE];
+    const T lfc = cw_clock_eval<T>(x, P, 0, phase, sm), lvc = cw_clock_eval<T>(x, P, 1, phase, sm);
+    const T rfc = cw_clock_eval<T>(x, P, 2, phase, sm), rvc = cw_clock_eval<T>(x, P, 3, phase, sm);
     const T q4 = (T)(CW_PI / 4);
     const T foot_frc_score = cw_tan<T>(q4 * lfc * nlf) + cw_tan<T>(q4 * rfc * nrf);
     const T foot_vel_score = cw_tan<T>(q4 * lvc * nlv) + cw_tan<T>(q4 * rvc * nrv);
@@ -471,9 +528,11 @@ template <typename T> CW_NOINL void cw_env_step(CassieWs<T> &w, T *obs_out, T *r
   cw_philox(seed, env, ctr, tr);
   cw_philox(seed, env, ctr + 1, va);
   T orient = w.st[S_ORIENT], speed = w.st[S_SPEED], side = w.st[S_SIDE];
-  if ((uint32_t)(((uint64_t)tr[0] * 300) >> 32) == 0) orient += (T)-0.2 + (T)0.4 * cw_u01<T>(va[0]);
-  if ((uint32_t)(((uint64_t)tr[1] * 100) >> 32) == 0) speed = cw_min(cw_max((T)-0.3 + (T)4.3 * cw_u01<T>(va[1]), (T)-0.3), (T)4.0);
-  if ((uint32_t)(((uint64_t)tr[2] * 300) >> 32) == 0) side = (T)-0.3 + (T)0.6 * cw_u01<T>(va[2]);
+  if (!w.sti[I_HOLDCMD]) { /* the stream advances either way, so switching the hold off later resumes the same draws */
+    if ((uint32_t)(((uint64_t)tr[0] * 300) >> 32) == 0) orient += (T)-0.2 + (T)0.4 * cw_u01<T>(va[0]);
+    if ((uint32_t)(((uint64_t)tr[1] * 100) >> 32) == 0) speed = cw_min(cw_max((T)-0.3 + (T)4.3 * cw_u01<T>(va[1]), (T)-0.3), (T)4.0);
+    if ((uint32_t)(((uint64_t)tr[2] * 300) >> 32) == 0) side = (T)-0.3 + (T)0.6 * cw_u01<T>(va[2]);
+  }
   CW_SYNC();
   CW_FOR_LANES {
     if (lane < 10) { w.st[S_PREV_ACTION + lane] = w.action[lane]; w.st[S_PREV_TORQUE + lane] = w.y[Y_MTORQUE + lane]; }
@@ -482,6 +541,7 @@ template <typename T> CW_NOINL void cw_env_step(CassieWs<T> &w, T *obs_out, T *r
       w.sti[I_TIME] = time; w.sti[I_COUNTER] = counter; w.sti[I_HASPREV] = 1; w.sti[I_RNGCTR] = (int)(ctr + 2);
       w.st[S_PHASE] = phase; w.st[S_ORIENT] = orient; w.st[S_SPEED] = speed; w.st[S_SIDE] = side;
       w.sti[I_SOLVER_ITER] = w.solver_iter; w.sti[I_NCON] = w.ncon; w.sti[I_NEFC] = w.nefc; w.sti[I_COST] = cost;
+      w.sti[I_SIMSTEPS] += CW_SIMRATE;
     }
   }
   CW_SYNC();

@@ -90,6 +90,8 @@ enum {
   S_PREV_ACTION = 290, S_PREV_TORQUE = 300, S_MENC = 310, S_JENC = 320, S_LASTPELVIS = 326,
   S_DAMPING = 329, S_MASS = 361, S_FRICTION = 387, S_FLOORQ = 388, S_DOFINVW = 392, S_BODYINVW = 424, S_MEANINERTIA = 450,
   S_FOOTVEL = 451, /* l_foot_vel(3), r_foot_vel(3) of the last sub-step */
+  S_XFRC = 457,    /* mjData.xfrc_applied of the pelvis: force(3), torque(3), world axes, at the body's centre of mass */
+  S_PHASEADD = 463, /* env.phase_add: 1 in training, 1.5 above 1.4 m/s in tools/test_commands.py:84-87 */
   S_WORDS = 464
 };
 /* persistent per-env record: int words */
@@ -97,7 +99,11 @@ enum {
   I_DRIVEHIST = 0, I_TIME = 90, I_COUNTER = 91, I_HASPREV = 92, I_HASU = 93, I_DRIVEINIT = 94, I_JOINTINIT = 95,
   I_FLAGS = 96, I_STEPCOUNT = 97, I_RNGCTR = 98, I_ENVID = 99, I_SEED = 100, I_DYNRAND = 101, I_SOLVER_ITER = 102,
   I_NCON = 103, I_NEFC = 104, I_VARIANT = 105 /* 0 Cassie-v0, 1 CassieTraj-v0 */, I_PHASEFLOOR = 106 /* floor(phaselen), from float64 */,
-  I_COST = 107 /* sum over the last env step's sub-steps of solver_iter * nefc: load-balancing key */, I_WORDS = 112
+  I_COST = 107 /* sum over the last env step's sub-steps of solver_iter * nefc: load-balancing key */,
+  I_STANCEMODE = 108 /* clock reward's stance_mode: 0 "zero", 1 "grounded" once reset_for_test has run (cassie.py:219,701) */,
+  I_SIMSTEPS = 109 /* physics sub-steps since the simulator was last reset: sim.time() = that many additions of 0.0005 */,
+  I_HOLDCMD = 110 /* != 0: env.step skips its random command changes (cassie.py:483-491); deterministic evaluation */,
+  I_WORDS = 112
 };
 /* state_out slice (workspace only) */
 enum { Y_PPOS = 0, Y_QUAT = 3, Y_ROTVEL = 7, Y_TVEL = 10, Y_TACC = 13, Y_MPOS = 16, Y_MVEL = 26, Y_MTORQUE = 36, Y_JPOS = 46, Y_JVEL = 52, Y_WORDS = 58 };
@@ -1034,6 +1040,21 @@ template <typename T> CW_NOINL void cw_mj_step(CassieWs<T> &w, bool integrate, i
       const T cm = (T)CMT(act_ctrlmax)[lane];
       c = cw_min(cw_max(c, -cm), cm);
       w.vec[V_SMOOTH][CM_act_dof[lane]] += (T)CMT(act_gear)[lane] * c;
+    } else if (lane >= 26) {
+      /* mj_xfrcAccumulate for the pelvis (the body sim.apply_force pushes): wrench (f, tau) at xipos moved to org = pelvis
+       * origin and projected on the pelvis' six dofs: slides take f, the ball takes R^T (tau + (xipos - org) x f) */
+      const int a = lane - 26;
+      const T *f = w.st + S_XFRC, *tau = w.st + S_XFRC + 3;
+      T v;
+      if (a < 3) v = f[a];
+      else {
+        const T ip[3] = {(T)CMT(body_ipos)[1][0], (T)CMT(body_ipos)[1][1], (T)CMT(body_ipos)[1][2]};
+        T r[3], t[3];
+        cw_mulv(r, w.xmat[1], ip);
+        cw_cross(t, r, f);
+        v = w.cdof[a][0] * (tau[0] + t[0]) + w.cdof[a][1] * (tau[1] + t[1]) + w.cdof[a][2] * (tau[2] + t[2]);
+      }
+      w.vec[V_SMOOTH][a] += v;
     }
   }
   CW_SYNC();

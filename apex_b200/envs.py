@@ -65,7 +65,8 @@ class BatchedCassieEnv:
         """View of a named field of the persistent state (tests, command overrides)."""
         off = _lib.layout(name)
         ints = name in ("drive_hist", "time", "counter", "has_prev", "has_u", "drive_init", "joint_init", "flags", "stepcount",
-                        "rng_ctr", "env_id", "seed", "dyn_rand", "solver_iter", "ncon", "nefc", "variant", "phase_floor", "cost")
+                        "rng_ctr", "env_id", "seed", "dyn_rand", "solver_iter", "ncon", "nefc", "variant", "phase_floor", "cost",
+                        "stance_mode", "sim_steps", "hold_commands")
         return (self.sti if ints else self.st)[:, off:off + width]
 
     def reset(self):
@@ -73,6 +74,33 @@ class BatchedCassieEnv:
             _lib.check(self.L.apex_cassie_env_reset(self.dt, self.st.data_ptr(), self.sti.data_ptr(), self.num_envs,
                                                     self.obs.data_ptr(), self._stream()), "env_reset")
         return self.obs
+
+    def reset_for_test(self, full_reset=True, active=None):
+        """CassieEnv.reset_for_test(full_reset=True) (cassie/cassie.py:682-733) for every env (or those with active != 0): the
+        start state of the evaluation tools.  full_reset=False (a sub-step on the running simulator) is not on that path."""
+        if not full_reset:
+            raise NotImplementedError("the evaluation tools call reset_for_test(full_reset=True) (tools/test_commands.py:69)")
+        with torch.cuda.device(self.device):
+            _lib.check(self.L.apex_cassie_env_reset_for_test(self.dt, self.st.data_ptr(), self.sti.data_ptr(), self.num_envs,
+                                                             self.obs.data_ptr(), None if active is None else active.data_ptr(),
+                                                             self._stream()), "env_reset_for_test")
+        return self.obs
+
+    def apply_force(self, xfrc, body_name="cassie-pelvis"):
+        """sim.apply_force (cassie/cassiemujoco/cassiemujoco.py:99-103) per env: xfrc [N, 6] or [6] = force(3) + torque(3) in
+        world axes at the body's centre of mass; stays applied until overwritten.  The pelvis is the one body the tools push."""
+        if body_name != "cassie-pelvis":
+            raise NotImplementedError("only the pelvis carries xfrc_applied in the kernel")
+        self.field("xfrc_applied", 6)[:] = torch.as_tensor(xfrc, dtype=self.dtype, device=self.device)
+
+    def sim_time(self):
+        """sim.time() per env, float64 [N]: mjData.time after `sim_steps` additions of the 0.0005 s timestep (summed the way
+        MuJoCo does, one addition per sub-step, so thresholds such as `curr_time < start_t + 0.2` flip where the reference's do)."""
+        steps = self.field("sim_steps")[:, 0].long()
+        need = int(steps.max().item()) + 1
+        if getattr(self, "_time_table", None) is None or self._time_table.numel() < need:
+            self._time_table = torch.as_tensor(sim_time_table(max(need, 1 << 16)), device=self.device)
+        return self._time_table[steps]
 
     def _traj_args(self):
         return None, 0, 0
@@ -104,6 +132,11 @@ class BatchedCassieEnv:
         for name, val in (("speed", speed), ("side_speed", side_speed), ("phase", phase)):
             if val is not None:
                 self.field(name)[:, 0] = torch.as_tensor(val, dtype=self.dtype, device=self.device)
+
+
+def sim_time_table(n):
+    """t[k] = mjData.time after k sub-steps: k sequential float64 additions of 0.0005."""
+    return np.concatenate([[0.0], np.cumsum(np.full(n, 0.0005, dtype=np.float64))])
 
 
 def load_trajectory(path, simrate=50):

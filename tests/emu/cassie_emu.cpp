@@ -36,6 +36,16 @@ template <typename T> static void store(const CassieWs<T> &w, T *st, int *sti) {
     }                                                                                                               \
     delete w;                                                                                                       \
   }                                                                                                                 \
+  extern "C" void emu_reset_for_test_##SUF(T *st, int *sti, int n, T *obs) {                                        \
+    CassieWs<T> *w = new CassieWs<T>();                                                                             \
+    for (int e = 0; e < n; e++) {                                                                                   \
+      memset(w, 0, sizeof(*w));                                                                                     \
+      load(*w, st + (size_t)e * S_WORDS, sti + (size_t)e * I_WORDS);                                                \
+      cw_env_reset_for_test<T>(*w, obs + (size_t)e * CW_OBS);                                                       \
+      store(*w, st + (size_t)e * S_WORDS, sti + (size_t)e * I_WORDS);                                               \
+    }                                                                                                               \
+    delete w;                                                                                                       \
+  }                                                                                                                 \
   extern "C" void emu_step_##SUF(T *st, int *sti, int n, const T *act, T *obs, T *rew, int *done, T *term_obs,      \
                                  int max_traj_len, const T *traj, int traj_rows, int traj_len) {                    \
     const CassieTraj<T> tr = {traj, traj_rows, traj_len};                                                           \
@@ -89,6 +99,12 @@ DEFINE(double, f64)
 DEFINE(float, f32)
 
 extern "C" void emu_clock_from_speed(double speed, double *out) { cw_clock_from_speed(speed, out, out + 1, out + 2); }
+extern "C" int emu_layout(const char *name) {
+  const struct { const char *n; int off; } tab[] = {{"speed", S_SPEED}, {"phase_add", S_PHASEADD}, {"xfrc_applied", S_XFRC}, {"phase", S_PHASE},
+                                                    {"qpos", S_QPOS}, {"qvel", S_QVEL}, {"sim_steps", I_SIMSTEPS}, {"stance_mode", I_STANCEMODE}, {"hold_commands", I_HOLDCMD}};
+  for (size_t i = 0; i < sizeof(tab) / sizeof(tab[0]); i++) if (strcmp(tab[i].n, name) == 0) return tab[i].off;
+  return -1;
+}
 extern "C" int emu_state_words(void) { return S_WORDS; }
 extern "C" int emu_istate_words(void) { return I_WORDS; }
 extern "C" int emu_ws_bytes(int f64) { return f64 ? (int)sizeof(CassieWs<double>) : (int)sizeof(CassieWs<float>); }

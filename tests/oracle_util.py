@@ -109,3 +109,58 @@ class OracleEnv:
     def phase(self):
         self.L.ce_env_get_phase.restype = C.c_double
         return self.L.ce_env_get_phase(self.buf)
+
+
+class OracleBatchedEnv:
+    """The batched-env contract apex_b200/evaluate.py drives (reset_for_test / step / field / apply_force / sim_time), served
+    by N oracle envs on the CPU: lets the CPU suite check the evaluation tools' host logic against results of the reference's
+    own tools (tests/golden/make_evaltools_golden.py).  The env's random command changes are off (no hits injected), like in
+    that script.  Observations carry float32 values (the reference wraps them in torch.Tensor before anything reads them)."""
+
+    def __init__(self, n):
+        import torch
+        self.torch, self.num_envs, self.device, self.dtype = torch, n, torch.device("cpu"), torch.float64
+        self.envs = [OracleEnv(False) for _ in range(n)]
+        self.L = self.envs[0].L
+        self.L.ce_env_set_command.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double]
+        self.max_traj_len = 0
+        self.f = {"speed": torch.zeros(n, 1, dtype=torch.float64), "side_speed": torch.zeros(n, 1, dtype=torch.float64),
+                  "phase_add": torch.ones(n, 1, dtype=torch.float64), "xfrc_applied": torch.zeros(n, 6, dtype=torch.float64),
+                  "qpos": torch.zeros(n, 35, dtype=torch.float64), "sim_steps": torch.zeros(n, 1, dtype=torch.int64),
+                  "hold_commands": torch.zeros(n, 1, dtype=torch.int32)}
+        self.obs = torch.zeros(n, 50, dtype=torch.float64)
+        for e in self.envs:  # use the env once, as a tool's env_fn() + first episode would
+            self.L.ce_env_reset(e.buf, dp(e.obs))
+
+    def field(self, name, width=1):
+        return self.f[name]
+
+    def _pull(self, i):
+        e = self.envs[i]
+        self.obs[i] = self.torch.as_tensor(e.obs.astype(np.float32).astype(np.float64))
+        self.f["qpos"][i] = self.torch.as_tensor(e.qpos_qvel()[0])
+
+    def reset_for_test(self, full_reset=True, active=None):
+        assert full_reset
+        for i, e in enumerate(self.envs):
+            if active is None or int(active[i]):
+                e.reset_for_test()
+                self.f["speed"][i], self.f["phase_add"][i], self.f["xfrc_applied"][i], self.f["sim_steps"][i] = 0.0, 1.0, 0.0, 0
+                self._pull(i)
+        return self.obs
+
+    def apply_force(self, xfrc, body_name="cassie-pelvis"):
+        self.f["xfrc_applied"][:] = self.torch.as_tensor(xfrc, dtype=self.torch.float64)
+
+    def step(self, action, active=None):
+        a = np.asarray(action.detach().cpu().numpy(), dtype=np.float64)
+        for i, e in enumerate(self.envs):
+            if active is not None and not int(active[i]):
+                continue
+            self.L.ce_env_set_command(e.buf, float(self.f["speed"][i, 0]), float(self.f["side_speed"][i, 0]), e.phase())
+            e.set_phase_add(float(self.f["phase_add"][i, 0]))
+            e.apply_force(self.f["xfrc_applied"][i].numpy())
+            e.step_with(a[i], [0, 0, 0], [0.0, 0.0, 0.0])
+            self.f["sim_steps"][i] += 50
+            self._pull(i)
+        return self.obs, None, None, {}

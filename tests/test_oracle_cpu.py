@@ -223,6 +223,75 @@ def test_kernel_source_matches_oracle_f64(L, emu, variant):
         assert ndone >= n  # the time-limit path (and its reset) was exercised
 
 
+def test_kernel_source_eval_entry_points_match_oracle_f64(L, emu):
+    """reset_for_test, speed / phase_add assignments, the pelvis wrench and the sub-step counter in the kernel source (host
+    build) against the oracle, on the schedule of tests/golden/make_eval_golden.py; the env is used first (a dyn-rand episode
+    start and a few steps) so the state reset_for_test keeps is non-trivial."""
+    SW, IW = emu.emu_state_words(), emu.emu_istate_words()
+    sch = _eval_schedule()
+    off = lambda name: emu.emu_layout(name.encode())
+    for f in (L.ce_env_set_speed, L.ce_env_set_phase_add):
+        f.argtypes = [C.c_void_p, C.c_double]
+    L.ce_env_sim_time.restype = C.c_double
+    L.ce_env_get_phase.restype = C.c_double
+    times = np.concatenate([[0.0], np.cumsum(np.full(4000, 0.0005))])  # sim.time() after k sub-steps
+    for dyn in (0, 1):
+        buf = (C.c_char * L.ce_sizeof_env())()
+        L.ce_batch_init(buf, 1, C.c_uint(31), dyn, 1)
+        st, sti = np.zeros((1, SW)), np.zeros((1, IW), dtype=np.int32)
+        emu.emu_init_f64(dp(st), dp(sti), 1, C.c_uint(31), dyn, 0)
+        oobs, orew, odone = np.zeros((1, 50)), np.zeros(1), np.zeros(1, dtype=np.int32)
+        eobs, erew, edone = np.zeros((1, 50)), np.zeros(1), np.zeros(1, dtype=np.int32)
+        L.ce_batch_reset(buf, 1, dp(oobs), 1)
+        emu.emu_reset_f64(dp(st), dp(sti), 1, dp(eobs), None, 0, 0)
+        rng = np.random.default_rng(3)
+        for t in range(-5, sch["STEPS"]):
+            if t in sch["RESET_AT"]:
+                L.ce_env_reset_for_test(buf, dp(oobs))
+                emu.emu_reset_for_test_f64(dp(st), dp(sti), 1, dp(eobs))
+                assert np.abs(oobs - eobs).max() < 1e-12
+            if t in sch["SPEED"]:
+                L.ce_env_set_speed(buf, sch["SPEED"][t])
+                st[0, off("speed")] = sch["SPEED"][t]
+            if t in sch["PHASE_ADD"]:
+                L.ce_env_set_phase_add(buf, sch["PHASE_ADD"][t])
+                st[0, off("phase_add")] = sch["PHASE_ADD"][t]
+            if t in sch["FORCE"]:
+                x = np.array(sch["FORCE"][t], dtype=np.float64)
+                L.ce_env_apply_force(buf, dp(x))
+                st[0, off("xfrc_applied"):off("xfrc_applied") + 6] = x
+            act = rng.normal(size=(1, 10)) * 0.1
+            L.ce_batch_step(buf, 1, dp(act), dp(oobs), dp(orew), dp(odone), 0, None, 1)
+            emu.emu_step_f64(dp(st), dp(sti), 1, dp(act), dp(eobs), dp(erew), dp(edone), None, 0, None, 0, 0)
+            assert odone[0] == edone[0], t
+            assert np.abs(oobs - eobs).max() < 1e-9 and abs(orew[0] - erew[0]) < 1e-10, (t, np.abs(oobs - eobs).max(), orew[0] - erew[0])
+            assert st[0, off("phase")] == L.ce_env_get_phase(buf), t
+            assert times[sti[0, off("sim_steps")]] == L.ce_env_sim_time(buf), t
+
+
+def test_kernel_source_hold_commands(L, emu):
+    """hold_commands != 0: env.step skips its random command changes (the evaluation tools' deterministic mode) — the kernel
+    source then follows the oracle stepped with no hits injected, and the command fields stay what they were set to."""
+    from tests.oracle_util import OracleEnv
+    SW, IW = emu.emu_state_words(), emu.emu_istate_words()
+    off = lambda name: emu.emu_layout(name.encode())
+    env = OracleEnv(False)
+    st, sti = np.zeros((1, SW)), np.zeros((1, IW), dtype=np.int32)
+    emu.emu_init_f64(dp(st), dp(sti), 1, C.c_uint(0), 0, 0)
+    eobs, erew, edone = np.zeros((1, 50)), np.zeros(1), np.zeros(1, dtype=np.int32)
+    env.reset_for_test()
+    emu.emu_reset_for_test_f64(dp(st), dp(sti), 1, dp(eobs))
+    env.set_speed(0.7)
+    st[0, off("speed")], sti[0, off("hold_commands")] = 0.7, 1
+    rng = np.random.default_rng(5)
+    for t in range(150):  # 150 steps: the 1/100 speed redraw would have hit with probability 0.78
+        act = rng.normal(size=(1, 10)) * 0.05
+        obs, rew, done = env.step_with(act[0], [0, 0, 0], [0.0, 0.0, 0.0])
+        emu.emu_step_f64(dp(st), dp(sti), 1, dp(act), dp(eobs), dp(erew), dp(edone), None, 0, None, 0, 0)
+        assert np.abs(obs - eobs[0]).max() < 1e-8 and abs(rew - erew[0]) < 1e-9 and done == edone[0], t
+        assert st[0, off("speed")] == 0.7
+
+
 def test_kernel_source_f32_close_to_f64(emu):
     SW, IW = emu.emu_state_words(), emu.emu_istate_words()
     n = 4
@@ -359,6 +428,65 @@ def test_eval_entry_points_match_the_reference_python(tag, dyn):
         assert np.abs(obs - f("obs")[t]).max() < 1e-9, (t, int(np.abs(obs - f("obs")[t]).argmax()))
         assert env.phase() == f("phase")[t] and abs(env.sim_time() - f("sim_time")[t]) < 1e-15, t
     assert nreset == 2
+
+
+def _torch_ref_actor():
+    """The reference's shipped 5k_retrain actor (weights in tests/golden/ref_policy_5k_retrain.npz) as a float32 torch module."""
+    import torch
+    from apex_b200.policies import Gaussian_FF_Actor
+    g = np.load(os.path.join(G, "ref_policy_5k_retrain.npz"))
+    actor = Gaussian_FF_Actor(49, 10, fixed_std=torch.ones(10), normc_init=False)
+    actor.load_state_dict({k: torch.as_tensor(g[k]) for k in actor.state_dict()})
+    actor.obs_mean, actor.obs_std = torch.as_tensor(g["obs_mean"]), torch.as_tensor(g["obs_std"])
+    return actor.eval()
+
+
+def _rowwise(actor):
+    """policy(obs [N, 50]) -> [N, 10], one row at a time in float32 like the tools' `policy(state, True)` on a torch.Tensor."""
+    import torch
+
+    def policy(obs):
+        with torch.no_grad():
+            return torch.stack([actor(o[:49].float(), True) for o in obs]).double()
+    return policy
+
+
+def test_eval_commands_tool_matches_the_reference_tool():
+    """apex_b200.evaluate.eval_commands (batched, lockstep) over the oracle env against tools/test_commands.py's
+    eval_worker.run_test run by the reference itself on the same four schedules (tests/golden/make_evaltools_golden.py): three
+    trials pass, the one that ramps to 2.9 m/s falls with the same failure record."""
+    from apex_b200 import evaluate
+    from tests.oracle_util import OracleBatchedEnv
+    g = np.load(os.path.join(G, "evaltools.npz"))
+    env = OracleBatchedEnv(len(g["speed_schedule"]))
+    data = evaluate.eval_commands(env, _rowwise(_torch_ref_actor()), g["speed_schedule"], g["orient_schedule"], num_steps=int(g["num_steps"]),
+                                  max_speed=3, min_speed=0)
+    assert data.shape == g["command_rows"].shape
+    assert np.abs(data - g["command_rows"]).max() < 1e-12, (data, g["command_rows"])
+    st = evaluate.report_stats(data)
+    assert st["pass_rate"] == 0.75 and st["orient_failures"] + st["speed_failures"] == 1
+
+
+def test_perturb_tool_matches_the_reference_tool():
+    """apex_b200.evaluate.perturb_trials / compute_perturbs over the oracle env against tools/eval_perturb.py's
+    perturb_worker.perturb_test_angle run by the reference: same largest-survived push for the same (direction, phase) cases."""
+    from apex_b200 import evaluate
+    from tests.oracle_util import OracleBatchedEnv
+    g = np.load(os.path.join(G, "evaltools.npz"))
+    policy = _rowwise(_torch_ref_actor())
+    start, incr = float(g["perturb_start"]), float(g["perturb_incr"])
+    dirs = -2 * np.pi * np.linspace(0, 1, 5)
+    for (d, ph), want in zip(g["perturb_cases"][:2], g["max_force"][:2]):
+        sizes = np.array([want, want + incr])  # the last survived size and the first failing one
+        env = OracleBatchedEnv(2)
+        failed = evaluate.perturb_trials(env, policy, np.full(2, dirs[d]), np.full(2, ph), sizes, num_phases=33, wait_time=float(g["perturb_wait_time"]),
+                                         perturb_duration=float(g["perturb_duration"]))
+        assert list(failed) == ([False, True] if want >= start else [True, True]), (d, ph, want, failed)
+    # the ladder search on one pair, two sizes per round
+    d, ph, want = int(g["perturb_cases"][1][0]), int(g["perturb_cases"][1][1]), float(g["max_force"][1])
+    out = evaluate.compute_perturbs(lambda n: OracleBatchedEnv(n), policy, wait_time=float(g["perturb_wait_time"]), perturb_duration=float(g["perturb_duration"]),
+                                    perturb_size=start, perturb_incr=incr, num_angles=4, phases=[ph], ladder=2, max_rounds=4)
+    assert out[d, ph] == want, (out[:, ph], want)
 
 
 def test_reference_abi_exports_all_103_symbols():
