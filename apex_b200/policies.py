@@ -160,3 +160,54 @@ def load_reference_checkpoint(path, map_location="cpu"):
     shim.Unpickler, shim.load, shim.loads = _Unpickler, pickle.load, pickle.loads
     shim.__name__ = "pickle"
     return torch.load(path, map_location=map_location, pickle_module=shim, weights_only=False)
+
+
+_REF_CLASS = {"Gaussian_FF_Actor": "rl.policies.actor", "FF_Actor": "rl.policies.actor", "FF_V": "rl.policies.critic",
+              "Dual_Q_Critic": "rl.policies.critic"}
+
+
+def save_reference_checkpoint(module, path):
+    """Write `module` the way the reference does — `torch.save(policy, "actor.pt")`, a whole-module pickle (rl/algos/ppo.py:129-137)
+    — naming the REFERENCE's classes (rl.policies.actor.Gaussian_FF_Actor, rl.policies.critic.FF_V, ...), so that the reference's
+    own tooling (`torch.load` in apex.py:257-280, tools/*) opens it with its own code, and load_reference_checkpoint opens it here.
+    The instance carries the attributes the reference's methods read beyond ours (nonlinearity, bounded, action, normc_init, the
+    Welford fields of rl/policies/base.py:17-27).  The reference package need not be importable: for the duration of the write
+    stand-in modules own those names."""
+    import sys
+    import types
+
+    name = type(module).__name__
+    if name not in _REF_CLASS:
+        raise TypeError(f"{name} has no reference counterpart")
+    modname = _REF_CLASS[name]
+    import copy
+    shim_cls = type(name, (nn.Module,), {"__module__": modname})
+    inst = shim_cls.__new__(shim_cls)
+    host = copy.deepcopy(module).to("cpu")  # the reference saves CPU modules; ours may live in one flat device buffer
+    for p_ in host.parameters():
+        p_.data = p_.data.clone()            # compact storage: a view would drag the whole flat buffer into the file
+        p_.grad = None
+    inst.__dict__ = dict(host.__dict__)
+    for k, v in list(inst.__dict__.items()):
+        if torch.is_tensor(v):
+            inst.__dict__[k] = v.detach().cpu().clone()
+    extra = {"is_recurrent": False, "welford_state_mean": torch.zeros(1), "welford_state_mean_diff": torch.ones(1), "welford_state_n": 1,
+             "nonlinearity": torch.nn.functional.relu, "normc_init": False}
+    if name == "Gaussian_FF_Actor":
+        extra.update(action=None, bounded=False, learn_std=False)
+    if name in ("FF_V", "Dual_Q_Critic"):
+        extra.update(welford_reward_mean=0.0, welford_reward_mean_diff=1.0, welford_reward_n=1)
+    for k, v in extra.items():
+        inst.__dict__.setdefault(k, v)
+    saved = {k: sys.modules.get(k) for k in ("rl", "rl.policies", modname)}
+    try:
+        for k in saved:
+            sys.modules[k] = types.ModuleType(k)
+        setattr(sys.modules[modname], name, shim_cls)
+        torch.save(inst, path)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v

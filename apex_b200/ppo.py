@@ -344,6 +344,9 @@ class PPO:
         return buf, self.optimize(buf, generator)
 
     def save(self, policy, critic):
+        """rl/algos/ppo.py:129-137: whole-module actor.pt / critic.pt, written under the reference's class names so that the
+        reference's tools (apex.py eval, tools/*) open them with their own code (policies.save_reference_checkpoint)."""
+        from .policies import save_reference_checkpoint
         os.makedirs(self.save_path, exist_ok=True)
-        torch.save(policy, os.path.join(self.save_path, "actor.pt"))
-        torch.save(critic, os.path.join(self.save_path, "critic.pt"))
+        save_reference_checkpoint(policy, os.path.join(self.save_path, "actor.pt"))
+        save_reference_checkpoint(critic, os.path.join(self.save_path, "critic.pt"))

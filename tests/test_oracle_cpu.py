@@ -4,6 +4,7 @@ import ctypes as C
 import os
 import re
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -633,3 +634,121 @@ def test_reference_checkpoints_load_without_the_reference_package():
         got = actor(torch.as_tensor(obs[:, :49], dtype=torch.float32), deterministic=True).numpy()
     assert np.abs(got - act(obs)).max() < 1e-5
     assert critic(torch.zeros(1, 49)).shape == (1, 1)
+
+
+# ---------------------------------------------------------------- checkpoint / log compatibility
+def _toy_nets():
+    import torch
+    from apex_b200.policies import FF_V, Gaussian_FF_Actor
+    torch.manual_seed(0)
+    a = Gaussian_FF_Actor(50, 10, fixed_std=torch.ones(10) * 0.13)
+    a.obs_mean, a.obs_std = torch.randn(50), torch.rand(50) + 0.5
+    c = FF_V(50)
+    c.obs_mean, c.obs_std = a.obs_mean, a.obs_std
+    return a, c
+
+
+def test_checkpoints_round_trip_under_the_reference_class_names(tmp_path):
+    """PPO.save's files name rl.policies.actor.Gaussian_FF_Actor / rl.policies.critic.FF_V (what the reference's torch.load
+    expects, rl/algos/ppo.py:129-137) without the reference being importable, and load back here bit-identically."""
+    import pickletools
+    import zipfile
+    import torch
+    from apex_b200.policies import load_reference_checkpoint, save_reference_checkpoint
+    from apex_b200.policies import flatten_modules
+    a, c = _toy_nets()
+    flat, _, _ = flatten_modules([a, c], "cpu")  # as PPO.attach leaves them: every parameter a view of one flat buffer
+    save_reference_checkpoint(a, str(tmp_path / "actor.pt"))
+    save_reference_checkpoint(c, str(tmp_path / "critic.pt"))
+    assert os.path.getsize(tmp_path / "critic.pt") < 4 * flat.numel()  # the critic's file does not drag the actor's weights along
+    assert "rl" not in sys.modules and "rl.policies.actor" not in sys.modules  # the stand-in modules are gone again
+    with zipfile.ZipFile(tmp_path / "actor.pt") as z:
+        pkl = z.read([n for n in z.namelist() if n.endswith("data.pkl")][0])
+    names = {arg for op, arg, _ in pickletools.genops(pkl) if op.name in ("GLOBAL", "STACK_GLOBAL", "SHORT_BINUNICODE", "BINUNICODE")}
+    blob = " ".join(str(n) for n in names)
+    assert "rl.policies.actor" in blob and "Gaussian_FF_Actor" in blob and "apex_b200" not in blob
+    x = torch.randn(5, 50)
+    a2, c2 = load_reference_checkpoint(str(tmp_path / "actor.pt")), load_reference_checkpoint(str(tmp_path / "critic.pt"))
+    assert torch.equal(a2(x), a(x)) and torch.equal(c2(x), c(x)) and torch.equal(a2.fixed_std, a.fixed_std)
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/rl/policies/actor.py"), reason="reference tree not mounted")
+def test_reference_opens_our_checkpoints_with_its_own_classes(tmp_path):
+    """The reference's own code path — torch.load with rl.policies on sys.path (apex.py:257-280) — in a subprocess: its classes,
+    its forward, our numbers."""
+    import torch
+    from apex_b200.policies import save_reference_checkpoint
+    a, c = _toy_nets()
+    save_reference_checkpoint(a, str(tmp_path / "actor.pt"))
+    save_reference_checkpoint(c, str(tmp_path / "critic.pt"))
+    x = torch.randn(7, 50)
+    torch.save({"x": x, "ya": a(x), "yc": c(x)}, str(tmp_path / "io.pt"))
+    code = f'''
+import sys, torch
+sys.path.insert(0, "/root/reference")
+a = torch.load("{tmp_path}/actor.pt", weights_only=False); c = torch.load("{tmp_path}/critic.pt", weights_only=False)
+io = torch.load("{tmp_path}/io.pt")
+import rl.policies.actor as A, rl.policies.critic as Cr
+assert type(a) is A.Gaussian_FF_Actor and type(c) is Cr.FF_V
+assert torch.equal(a(io["x"], True), io["ya"]) and torch.equal(c(io["x"]), io["yc"])
+assert a.distribution(io["x"]).mean.shape == (7, 10) and not a.is_recurrent
+print("ok")
+'''
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stderr[-2000:]
+
+
+def test_scalar_log_is_a_valid_event_file(tmp_path):
+    """apex_b200/log.py: CRC-32C known answer, the TFRecord framing read back with every checksum verified, the reference's
+    thirteen PPO tags (rl/algos/ppo.py:486-499), experiment.info / experiment.pkl as util/log.py:52-63 writes them."""
+    import argparse
+    import pickle
+    from apex_b200 import log
+    assert log.crc32c(b"123456789") == 0xE3069283 and log.crc32c(b"") == 0
+    args = argparse.Namespace(seed=3, logdir=str(tmp_path), env_name="Cassie-v0", run_name=None, lr=1e-4, num_procs=4, previous=None)
+    lg = log.create_logger(args)
+    assert os.path.dirname(lg.dir) == str(tmp_path / "Cassie-v0") and lg.dir.endswith("-seed3") and len(os.path.basename(lg.dir)) == 6 + 6
+    for itr in range(3):
+        log.log_ppo_iteration(lg, itr, *[itr + 0.5 * k for k in range(13)])
+    lg.close()
+    rows = log.read_scalars(lg.path)
+    assert len(rows) == 39 and [r[1] for r in rows[:13]] == list(log.PPO_SCALARS)
+    assert rows[13 + 4] == (1, "Train/Mean Entropy", 3.0) and rows[-1] == (2, "Misc/Termination Threshold", 8.0)
+    raw = open(lg.path, "rb").read()
+    assert b"brain.Event:2" in raw[:64]
+    info = open(os.path.join(lg.dir, "experiment.info")).read().splitlines()
+    assert info == ["env_name: Cassie-v0", "lr: 0.0001", "num_procs: 4", "previous: None"]
+    assert pickle.load(open(os.path.join(lg.dir, "experiment.pkl"), "rb")) == args
+    named = log.create_logger(argparse.Namespace(seed=1, logdir=str(tmp_path), env_name="Cassie-v0", run_name="myrun"))
+    assert named.dir == str(tmp_path / "Cassie-v0" / "myrun")
+    named.close()
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/util/log.py"), reason="reference tree not mounted")
+def test_run_directory_matches_the_reference_logger(tmp_path):
+    """util/log.py:11-70 itself (SummaryWriter replaced by a stand-in: tensorboard is not installed) must choose the same
+    directory and write the same experiment.info for the same arguments."""
+    code = f'''
+import sys, types, argparse
+tb = types.ModuleType("torch.utils.tensorboard")
+class SummaryWriter:
+    def __init__(self, d, flush_secs=None): self.d = d
+tb.SummaryWriter = SummaryWriter
+import torch.utils
+sys.modules["torch.utils.tensorboard"] = tb
+sys.path.insert(0, "/root/reference")
+from util.log import create_logger
+args = argparse.Namespace(seed=3, logdir="{tmp_path}/ref", env_name="Cassie-v0", run_name=None, lr=1e-4, num_procs=4, previous=None, exchange_reward=None)
+print(create_logger(args).dir)
+'''
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    ref_dir = r.stdout.strip().splitlines()[-1]
+    import argparse
+    from apex_b200 import log
+    args = argparse.Namespace(seed=3, logdir=str(tmp_path / "ours"), env_name="Cassie-v0", run_name=None, lr=1e-4, num_procs=4, previous=None,
+                              exchange_reward=None)
+    lg = log.create_logger(args)
+    lg.close()
+    assert os.path.basename(lg.dir) == os.path.basename(ref_dir), (lg.dir, ref_dir)
+    assert open(os.path.join(lg.dir, "experiment.info")).read() == open(os.path.join(ref_dir, "experiment.info")).read()
