@@ -164,8 +164,17 @@ void ce_env_init(ce_env_t *e, uint32_t seed, uint32_t env_id, int dyn_rand) {
 }
 
 void ce_clock_from_speed(double speed, double *swing, double *stance, double *phaselen);
+void ce_clock_from_speed_signed(double speed, double *swing, double *stance, double *phaselen);
 static void set_clock(ce_env_t *e, double speed) { /* cassie.py:556-559 */
   ce_clock_from_speed(speed, &e->swing_duration, &e->stance_duration, &e->phaselen);
+}
+/* update_speed's variant (cassie.py:763-765): the same expressions on the signed speed — reset() takes abs(), update_speed does not */
+NOFMA void ce_clock_from_speed_signed(double speed, double *swing, double *stance, double *phaselen) {
+  double total = (0.9 - 0.25 / 3.0 * speed) / 2;
+  *swing = (0.30 + ((0.70 - 0.30) / 3) * speed) * total;
+  *stance = (0.70 - ((0.70 - 0.30) / 3) * speed) * total;
+  double x[8];
+  ce_clock_knots(*swing, *stance, x, phaselen);
 }
 NOFMA void ce_clock_from_speed(double speed, double *swing, double *stance, double *phaselen) {
   double total = (0.9 - 0.25 / 3.0 * fabs(speed)) / 2;
@@ -436,38 +445,83 @@ void ce_env_reset_with(ce_env_t *e, const ce_reset_draws_t *dr, double *obs) { /
  * also clears xfrc_applied, plus re-initialised wrapper blocks), the synthetic cassie_state of reset_cassie_state
  * (cassie.py:735-746), default dynamics, zero encoder noise, phase 0, speed 0, the 0.15 / 0.25 s clock.  Kept from before,
  * as in the reference: side_speed, pd_in_t u, prev_action / prev_torque, motor torques, foot flags, last_pelvis_pos. */
-void ce_env_reset_for_test(ce_env_t *e, double *obs) {
+void ce_env_reset_for_test(ce_env_t *e, double *obs) { ce_env_reset_for_test_mode(e, 1, obs); }
+/* full_reset = 0 (the default of the reference's signature; what 5k_test.py:64 calls on a just-constructed simulator): the
+ * simulator keeps running, last_pelvis_pos is taken and cassie_state comes from one sub-step with the current pd_in_t
+ * (cassie.py:704-714).  In both modes the dynamics go back to the defaults only when the env randomises them (cassie.py:719-724):
+ * a model edited from outside (friction, foot mass, floor tilt in 5k_test.py:47-49) survives, as it does in the real library,
+ * whose cassie_sim_full_reset resets mjData and the wrapper blocks but not the mjModel. */
+void ce_env_reset_for_test_mode(ce_env_t *e, int full_reset, double *obs) {
   e->phase = 0; e->time = 0; e->counter = 0; e->orient_add = 0; e->phase_add = 1; e->speed = 0;
   e->swing_duration = 0.15; e->stance_duration = 0.25; e->stance_mode = 1; /* sticks: reset() never sets it back (cassie.py:548-559) */
   double x[8];
   ce_clock_knots(e->swing_duration, e->stance_duration, x, &e->phaselen);
-  memset(&e->d, 0, sizeof(e->d));
-  memset(e->delay, 0, sizeof(e->delay)); memset(e->drive_hist, 0, sizeof(e->drive_hist)); e->drive_init = 0;
-  memset(e->jx, 0, sizeof(e->jx)); memset(e->jy, 0, sizeof(e->jy)); e->joint_init = 0;
-  memset(e->o_mpos, 0, sizeof(e->o_mpos)); memset(e->o_mvel, 0, sizeof(e->o_mvel)); memset(e->o_mtorque, 0, sizeof(e->o_mtorque));
-  memset(e->o_jpos, 0, sizeof(e->o_jpos)); memset(e->o_jvel, 0, sizeof(e->o_jvel)); memset(e->o_quat, 0, sizeof(e->o_quat));
-  memset(e->o_gyro, 0, sizeof(e->o_gyro)); memset(e->o_acc, 0, sizeof(e->o_acc)); memset(e->o_ppos, 0, sizeof(e->o_ppos));
-  memset(e->o_pvel, 0, sizeof(e->o_pvel));
-  cp_model_default(&e->m);
-  memcpy(e->d.qpos, CM_qpos_init, sizeof(e->d.qpos));
-  cp_data_reset(&e->m, &e->d);
-  static const double MPOS[10] = {0.0045, 0, 0.4973, -1.1997, -1.5968, 0.0045, 0, 0.4973, -1.1997, -1.5968};
-  static const double JPOS[6] = {0, 1.4267, -1.5968, 0, 1.4267, -1.5968};
-  ce_state_out_t *y = &e->y;
-  y->pelvis_pos[0] = 0; y->pelvis_pos[1] = 0; y->pelvis_pos[2] = 1.01;
-  y->pelvis_quat[0] = 1; y->pelvis_quat[1] = y->pelvis_quat[2] = y->pelvis_quat[3] = 0;
-  memset(y->pelvis_rotvel, 0, sizeof(y->pelvis_rotvel)); memset(y->pelvis_transvel, 0, sizeof(y->pelvis_transvel));
-  memset(y->pelvis_transacc, 0, sizeof(y->pelvis_transacc));
-  y->terrain_height = 0;
-  memcpy(y->motor_pos, MPOS, sizeof(MPOS)); memset(y->motor_vel, 0, sizeof(y->motor_vel));
-  memcpy(y->joint_pos, JPOS, sizeof(JPOS)); memset(y->joint_vel, 0, sizeof(y->joint_vel));
-  memset(e->menc_noise, 0, sizeof(e->menc_noise)); memset(e->jenc_noise, 0, sizeof(e->jenc_noise));
+  if (!full_reset) {
+    memcpy(e->last_pelvis_pos, e->d.qpos, sizeof(e->last_pelvis_pos));
+    e->l_foot_frc = e->r_foot_frc = 0;
+    e->l_foot_orient_cost = e->r_foot_orient_cost = 0;
+    ce_sim_step_pd(e, &e->u, &e->y);
+  } else {
+    memset(&e->d, 0, sizeof(e->d));
+    memset(e->delay, 0, sizeof(e->delay)); memset(e->drive_hist, 0, sizeof(e->drive_hist)); e->drive_init = 0;
+    memset(e->jx, 0, sizeof(e->jx)); memset(e->jy, 0, sizeof(e->jy)); e->joint_init = 0;
+    memset(e->o_mpos, 0, sizeof(e->o_mpos)); memset(e->o_mvel, 0, sizeof(e->o_mvel)); memset(e->o_mtorque, 0, sizeof(e->o_mtorque));
+    memset(e->o_jpos, 0, sizeof(e->o_jpos)); memset(e->o_jvel, 0, sizeof(e->o_jvel)); memset(e->o_quat, 0, sizeof(e->o_quat));
+    memset(e->o_gyro, 0, sizeof(e->o_gyro)); memset(e->o_acc, 0, sizeof(e->o_acc)); memset(e->o_ppos, 0, sizeof(e->o_ppos));
+    memset(e->o_pvel, 0, sizeof(e->o_pvel));
+    memcpy(e->d.qpos, CM_qpos_init, sizeof(e->d.qpos));
+    cp_data_reset(&e->m, &e->d);
+    static const double MPOS[10] = {0.0045, 0, 0.4973, -1.1997, -1.5968, 0.0045, 0, 0.4973, -1.1997, -1.5968};
+    static const double JPOS[6] = {0, 1.4267, -1.5968, 0, 1.4267, -1.5968};
+    ce_state_out_t *y = &e->y;
+    y->pelvis_pos[0] = 0; y->pelvis_pos[1] = 0; y->pelvis_pos[2] = 1.01;
+    y->pelvis_quat[0] = 1; y->pelvis_quat[1] = y->pelvis_quat[2] = y->pelvis_quat[3] = 0;
+    memset(y->pelvis_rotvel, 0, sizeof(y->pelvis_rotvel)); memset(y->pelvis_transvel, 0, sizeof(y->pelvis_transvel));
+    memset(y->pelvis_transacc, 0, sizeof(y->pelvis_transacc));
+    y->terrain_height = 0;
+    memcpy(y->motor_pos, MPOS, sizeof(MPOS)); memset(y->motor_vel, 0, sizeof(y->motor_vel));
+    memcpy(y->joint_pos, JPOS, sizeof(JPOS)); memset(y->joint_vel, 0, sizeof(y->joint_vel));
+  }
+  if (e->dyn_rand) {
+    cp_model_default(&e->m);
+    memset(e->menc_noise, 0, sizeof(e->menc_noise)); memset(e->jenc_noise, 0, sizeof(e->jenc_noise));
+  }
+  ce_env_obs(e, obs);
+}
+/* CassieEnv.update_speed (cassie.py:751-768, clock command profile): clip, rebuild the clock from the speed with the current
+ * stance mode, rescale the phase to the new period and truncate it */
+void ce_env_update_speed(ce_env_t *e, double new_speed, double new_side_speed) {
+  e->speed = fmin(fmax(new_speed, -0.3), 4.0);
+  e->side_speed = fmin(fmax(new_side_speed, -0.3), 0.3);
+  double old = e->phaselen;
+  ce_clock_from_speed_signed(e->speed, &e->swing_duration, &e->stance_duration, &e->phaselen);
+  e->phase = (double)(long)(e->phaselen * e->phase / old);
+}
+/* CassieEnv.step_basic (cassie.py:499-521): the sub-steps of step() without the bookkeeping for the reward, no reward, no
+ * done flag, no random command changes */
+void ce_env_step_basic(ce_env_t *e, const double *action, double *obs) {
+  for (int i = 0; i < CE_ACT; i++) {
+    int k = i % 5;
+    e->u.torque[i] = 0; e->u.dtarget[i] = 0;
+    e->u.pgain[i] = PGAIN[k]; e->u.dgain[i] = DGAIN[k];
+    e->u.ptarget[i] = action[i] + OFFSET[i] - e->menc_noise[i];
+  }
+  for (int s = 0; s < 50; s++) ce_sim_step_pd(e, &e->u, &e->y);
+  e->time += 1;
+  e->phase += e->phase_add;
+  if (e->phase > e->phaselen) {
+    memcpy(e->last_pelvis_pos, e->d.qpos, sizeof(e->last_pelvis_pos));
+    e->phase = 0;
+    e->counter += 1;
+  }
   ce_env_obs(e, obs);
 }
 /* sim.apply_force(xfrc, "cassie-pelvis") (cassiemujoco.py:99-103): stays applied until overwritten */
 void ce_env_apply_force(ce_env_t *e, const double xfrc[6]) { memcpy(e->d.xfrc_pelvis, xfrc, sizeof(e->d.xfrc_pelvis)); }
 void ce_env_set_phase_add(ce_env_t *e, double phase_add) { e->phase_add = phase_add; }
 void ce_env_set_speed(ce_env_t *e, double speed) { e->speed = speed; }
+void ce_env_set_orient_add(ce_env_t *e, double orient_add) { e->orient_add = orient_add; }
+cp_model_t *ce_env_model(ce_env_t *e) { return &e->m; }
 double ce_env_sim_time(const ce_env_t *e) { return e->d.time; }
 
 void ce_env_reset(ce_env_t *e, double *obs) {

@@ -94,9 +94,15 @@ void ce_batch_set_trajectory(ce_env_t *envs, int n, const double *table, int row
 double ce_env_get_phase(const ce_env_t *e);
 void ce_env_set_command(ce_env_t *e, double speed, double side_speed, double phase); /* synthetic-input hook */
 void ce_env_reset_for_test(ce_env_t *e, double *obs);            /* CassieEnv.reset_for_test(full_reset=True), cassie.py:682-733 */
+void ce_env_reset_for_test_mode(ce_env_t *e, int full_reset, double *obs); /* full_reset=False: 5k_test.py:64 */
+void ce_env_update_speed(ce_env_t *e, double new_speed, double new_side_speed); /* CassieEnv.update_speed, cassie.py:751-768 */
+void ce_env_step_basic(ce_env_t *e, const double *action, double *obs);        /* CassieEnv.step_basic, cassie.py:499-521 */
+void ce_clock_from_speed_signed(double speed, double *swing, double *stance, double *phaselen);
 void ce_env_apply_force(ce_env_t *e, const double xfrc[6]);      /* sim.apply_force on the pelvis, cassiemujoco.py:99-103 */
 void ce_env_set_phase_add(ce_env_t *e, double phase_add);        /* env.phase_add (tools/test_commands.py:84-87) */
 void ce_env_set_speed(ce_env_t *e, double speed);                /* env.speed = ... (tools/test_commands.py:70,81) */
+void ce_env_set_orient_add(ce_env_t *e, double orient_add);      /* env.orient_add = ... (5k_test.py:67) */
+cp_model_t *ce_env_model(ce_env_t *e);                           /* the env's model, for edits like 5k_test.py:46-49 */
 double ce_env_sim_time(const ce_env_t *e);                       /* sim.time() */
 void ce_env_step(ce_env_t *e, const double *action, double *obs, double *reward, int *done);
 void ce_env_obs(ce_env_t *e, double *obs);

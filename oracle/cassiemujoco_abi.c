@@ -141,9 +141,14 @@ void cassie_sim_clear_forces(cassie_sim_t *c) { (void)c; }
 void cassie_sim_hold(cassie_sim_t *c) { (void)c; }
 void cassie_sim_release(cassie_sim_t *c) { (void)c; }
 void cassie_sim_radio(cassie_sim_t *c, double channels[16]) { (void)c; (void)channels; }
-void cassie_sim_full_reset(cassie_sim_t *c) {
+void cassie_sim_full_reset(cassie_sim_t *c) { /* mj_resetData + fresh wrapper blocks; the (possibly edited) model is kept */
   cassie_sim_t *fresh = cassie_sim_init(NULL, false);
-  if (fresh) { memcpy(c, fresh, sizeof(*c)); free(fresh); }
+  if (!fresh) return;
+  cp_model_t m = c->e.m;
+  c->e = fresh->e;
+  c->e.m = m;
+  cp_data_reset(&c->e.m, &c->e.d);
+  free(fresh);
 }
 int32_t cassie_sim_get_hfield_nrow(cassie_sim_t *c) { (void)c; return 0; }
 int32_t cassie_sim_get_hfield_ncol(cassie_sim_t *c) { (void)c; return 0; }
@@ -158,17 +163,24 @@ double *cassie_sim_dof_damping(cassie_sim_t *c) { return c->e.m.dof_damping; }
 void cassie_sim_set_dof_damping(cassie_sim_t *c, double *damp) { memcpy(c->e.m.dof_damping, damp, sizeof(c->e.m.dof_damping)); }
 double *cassie_sim_body_mass(cassie_sim_t *c) { return c->e.m.body_mass; }
 void cassie_sim_set_body_mass(cassie_sim_t *c, double *mass) { memcpy(c->e.m.body_mass, mass, sizeof(c->e.m.body_mass)); }
-void cassie_sim_set_body_name_mass(cassie_sim_t *c, const char *name, double mass) { (void)c; (void)name; (void)mass; }
+void cassie_sim_set_body_name_mass(cassie_sim_t *c, const char *name, double mass) { /* the bodies 5k_test.py:48-49 edits */
+  if (name && strcmp(name, "left-foot") == 0) c->e.m.body_mass[13] = mass;
+  else if (name && strcmp(name, "right-foot") == 0) c->e.m.body_mass[25] = mass;
+}
 double *cassie_sim_body_ipos(cassie_sim_t *c) { return &c->e.m.body_ipos[0][0]; }
 void cassie_sim_set_body_ipos(cassie_sim_t *c, double *ipos) { memcpy(c->e.m.body_ipos, ipos, sizeof(c->e.m.body_ipos)); }
 double *cassie_sim_geom_friction(cassie_sim_t *c) { return c->geom_friction; }
 void cassie_sim_set_geom_friction(cassie_sim_t *c, double *fric) { memcpy(c->geom_friction, fric, sizeof(c->geom_friction)); sync_floor(c); }
-void cassie_sim_set_geom_name_friction(cassie_sim_t *c, const char *name, double *fric) { (void)c; (void)name; (void)fric; }
+void cassie_sim_set_geom_name_friction(cassie_sim_t *c, const char *name, double *fric) { /* geom 0 = floor (5k_test.py:47) */
+  if (name && strcmp(name, "floor") == 0) { memcpy(c->geom_friction, fric, 3 * sizeof(double)); sync_floor(c); }
+}
 float *cassie_sim_geom_rgba(cassie_sim_t *c) { return c->geom_rgba; }
 void cassie_sim_set_geom_rgba(cassie_sim_t *c, float *rgba) { memcpy(c->geom_rgba, rgba, sizeof(c->geom_rgba)); }
 double *cassie_sim_geom_quat(cassie_sim_t *c) { return c->geom_quat; }
 void cassie_sim_set_geom_quat(cassie_sim_t *c, double *quat) { memcpy(c->geom_quat, quat, sizeof(c->geom_quat)); sync_floor(c); }
-void cassie_sim_set_geom_name_quat(cassie_sim_t *c, const char *name, double *quat) { (void)c; (void)name; (void)quat; }
+void cassie_sim_set_geom_name_quat(cassie_sim_t *c, const char *name, double *quat) { /* floor tilt (5k_test.py:46, cassie.py:727) */
+  if (name && strcmp(name, "floor") == 0) { memcpy(c->geom_quat, quat, 4 * sizeof(double)); sync_floor(c); }
+}
 /* cassie_sim_set_const @0x7330: mj_setConst, then the fixed start pose, zero velocity, time 0, mj_forward */
 void cassie_sim_set_const(cassie_sim_t *c) {
   cp_set_const(&c->e.m);

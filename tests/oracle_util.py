@@ -164,3 +164,18 @@ class OracleBatchedEnv:
             self.f["sim_steps"][i] += 50
             self._pull(i)
         return self.obs, None, None, {}
+
+
+def oracle_env_5k(case_quat, friction, foot_mass):
+    """A fresh oracle env set up like 5k_test.py:28-64: new simulator, floor tilt / friction, foot masses, reset_for_test()."""
+    env = OracleEnv(False)
+    L = env.L
+    L.ce_env_model.restype = C.c_void_p
+    m = P.Model.from_address(L.ce_env_model(env.buf))
+    for k in range(4):
+        m.floor_quat[k] = float(case_quat[k])
+    for k in range(3):
+        m.floor_friction[k] = float(friction[k])
+    m.body_mass[13] = m.body_mass[25] = float(foot_mass)
+    L.ce_env_reset_for_test_mode(env.buf, 0, dp(env.obs))
+    return env

@@ -490,6 +490,38 @@ def test_perturb_tool_matches_the_reference_tool():
     assert out[d, ph] == want, (out[:, ph], want)
 
 
+@pytest.mark.parametrize("case", [0, 1, 2, 3])
+def test_5k_inner_loop_matches_the_reference_python(L, case):
+    """5k_test.py:19-75's per-trial loop — new simulator, floor tilt / friction / foot mass edits, reset_for_test()
+    (full_reset=False), then update_speed + orient_add + step_basic per mission command — recorded from the reference's
+    CassieEnv (tests/golden/make_5k_golden.py) and replayed through oracle/cassie_env.c.  Includes the reference's phase
+    arithmetic in update_speed: phase = int(phaselen * phase / old_phaselen) truncates 14.999... to 14, so with a constant
+    0.5 m/s command the phase sticks at 15 (case 3) and the shipped policy falls — reproduced, not repaired."""
+    from tests.oracle_util import oracle_env_5k
+    g = np.load(os.path.join(G, "test5k.npz"))
+    f = lambda k: g[f"case{case}.{k}"]
+    env = oracle_env_5k(f("floor_quat"), f("friction"), f("foot_mass"))
+    actor = _torch_ref_actor()
+    import torch
+    L.ce_env_update_speed.argtypes = [C.c_void_p, C.c_double, C.c_double]
+    L.ce_env_set_orient_add.argtypes = [C.c_void_p, C.c_double]
+    assert np.abs(env.obs - f("obs")[0]).max() < 1e-12 and np.abs(env.qpos_qvel()[0] - f("qpos")[0]).max() < 1e-13
+    speeds = g["speeds"] if case != 3 else np.full(len(g["speeds"]), 0.5)
+    n = int(f("steps"))
+    for i in range(n):
+        L.ce_env_update_speed(env.buf, float(speeds[i]), 0.0)
+        L.ce_env_set_orient_add(env.buf, float(g["orients"][i]))
+        with torch.no_grad():
+            a = actor(torch.as_tensor(f("obs")[i], dtype=torch.float32)[:49], True).numpy().astype(np.float64)
+        L.ce_env_step_basic(env.buf, dp(np.ascontiguousarray(a)), dp(env.obs))
+        assert env.phase() == f("phase")[i + 1], (i, env.phase(), f("phase")[i + 1])
+        assert np.abs(env.qpos_qvel()[0] - f("qpos")[i + 1]).max() < 1e-9, i
+        assert np.abs(env.obs - f("obs")[i + 1]).max() < 1e-8, (i, int(np.abs(env.obs - f("obs")[i + 1]).argmax()))
+    assert (env.qpos_qvel()[0][2] < 0.4) == (not bool(f("passed")))
+    if case == 3:
+        assert list(f("phase")[15:40]) == [15.0] * 25
+
+
 def test_reference_abi_exports_all_103_symbols():
     """oracle/cassiemujoco_abi.c must export every name cassie/cassiemujoco/cassiemujoco_ctypes.py binds at import."""
     import ctypes
