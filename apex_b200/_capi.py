@@ -27,7 +27,7 @@ def lib():
         L.apex_cassie_env_init.argtypes = [i, vp, ip, i, u, i, i, vp]
         L.apex_cassie_env_reset.argtypes = [i, vp, ip, i, vp, vp]
         L.apex_cassie_env_step.argtypes = [i, vp, ip, i, vp, vp, vp, ip, vp, i, vp]
-        L.apex_cassie_env_reset_for_test.argtypes = [i, vp, ip, i, vp, vp, vp]
+        L.apex_cassie_env_reset_for_test.argtypes = [i, vp, ip, i, vp, vp, i, vp]
         L.apex_cassie_env_reset_for_test.restype = i
         L.apex_cassie_mj_step.argtypes = [i, vp, ip, i, i, vp]
         for f in (L.apex_cassie_env_init, L.apex_cassie_env_reset, L.apex_cassie_env_step, L.apex_cassie_mj_step):

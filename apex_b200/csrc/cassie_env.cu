@@ -36,13 +36,13 @@ template <typename T> __global__ void __launch_bounds__(32) k_env_reset(T *st, i
   ws_store(w, st + (size_t)e * S_WORDS, sti + (size_t)e * I_WORDS, lane);
 }
 
-template <typename T> __global__ void __launch_bounds__(32) k_env_reset_for_test(T *st, int *sti, int n, T *obs, const int *active) {
+template <typename T> __global__ void __launch_bounds__(32) k_env_reset_for_test(T *st, int *sti, int n, T *obs, const int *active, int full) {
   extern __shared__ __align__(16) unsigned char smem[];
   CassieWs<T> &w = *reinterpret_cast<CassieWs<T> *>(smem);
   const int e = blockIdx.x, lane = threadIdx.x;
   if (e >= n || (active && !active[e])) return;
   ws_load(w, st + (size_t)e * S_WORDS, sti + (size_t)e * I_WORDS, lane);
-  cw_env_reset_for_test<T>(w, obs + (size_t)e * CW_OBS, lane);
+  cw_env_reset_for_test<T>(w, obs + (size_t)e * CW_OBS, full, lane);
   ws_store(w, st + (size_t)e * S_WORDS, sti + (size_t)e * I_WORDS, lane);
 }
 
@@ -212,15 +212,15 @@ int apex_cassie_env_init(int dtype, void *st, int *sti, int n, unsigned seed, in
 int apex_cassie_env_reset(int dtype, void *st, int *sti, int n, void *obs, void *stream) {
   return env_reset_impl(dtype, st, sti, n, obs, nullptr, 0, 0, stream);
 }
-/* CassieEnv.reset_for_test(full_reset=True) for the envs whose active flag is set (all when active is NULL) */
-int apex_cassie_env_reset_for_test(int dtype, void *st, int *sti, int n, void *obs, const int *active, void *stream) {
+/* CassieEnv.reset_for_test(full_reset) for the envs whose active flag is set (all when active is NULL) */
+int apex_cassie_env_reset_for_test(int dtype, void *st, int *sti, int n, void *obs, const int *active, int full_reset, void *stream) {
   if (n <= 0) return 0;
   if (!obs) return -1000;
   DISPATCH(
       if ((rc = prep(k_env_reset_for_test<float>, sizeof(CassieWs<float>)))) return rc;
-      (k_env_reset_for_test<float><<<n, 32, sizeof(CassieWs<float>), s>>>((float *)st, sti, n, (float *)obs, active)),
+      (k_env_reset_for_test<float><<<n, 32, sizeof(CassieWs<float>), s>>>((float *)st, sti, n, (float *)obs, active, full_reset)),
       if ((rc = prep(k_env_reset_for_test<double>, sizeof(CassieWs<double>)))) return rc;
-      (k_env_reset_for_test<double><<<n, 32, sizeof(CassieWs<double>), s>>>((double *)st, sti, n, (double *)obs, active)))
+      (k_env_reset_for_test<double><<<n, 32, sizeof(CassieWs<double>), s>>>((double *)st, sti, n, (double *)obs, active, full_reset)))
 }
 int apex_cassie_env_step(int dtype, void *st, int *sti, int n, const void *action, void *obs, void *reward, int *done,
                          void *term_obs, int max_traj_len, void *stream) {

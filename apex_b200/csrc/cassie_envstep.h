@@ -386,43 +386,64 @@ template <typename T> CW_NOINL void cw_env_reset(CassieWs<T> &w, T *obs_out, con
  * mjData cleared incl. xfrc_applied, wrapper blocks re-initialised), default dynamics, zero encoder noise, phase 0, speed 0,
  * phase_add 1, the 0.15 / 0.25 s "grounded" clock, and an observation built from the synthetic cassie_state of
  * reset_cassie_state (cassie.py:735-746) rather than from the simulator.  Kept, as in the reference: side_speed, the PD
- * target u, prev_action / prev_torque, foot flags, last_pelvis_pos, the RNG stream. */
-template <typename T> CW_NOINL void cw_env_reset_for_test(CassieWs<T> &w, T *obs_out CW_LANE_PARAM) {
+ * target u, prev_action / prev_torque, foot flags, last_pelvis_pos, the RNG stream.
+ * full = 0 is the signature's default (5k_test.py:64 calls it on a just-constructed simulator): no simulator reset, see below. */
+template <typename T> CW_NOINL void cw_env_reset_for_test(CassieWs<T> &w, T *obs_out, int full CW_LANE_PARAM) {
+  const int dyn = w.sti[I_DYNRAND];
+  CW_SYNC();
   CW_FOR_LANES {
-    for (int k = S_QVEL + lane; k < S_UPTARGET; k += 32) w.st[k] = 0; /* qvel, warm start, ctrl, sensors, delay line, filters */
-    for (int k = lane; k < CM_NQ; k += 32) w.st[S_QPOS + k] = (T)CMT(qpos_init)[k];
-    for (int k = lane; k < 90; k += 32) w.sti[I_DRIVEHIST + k] = 0;
-    w.st[S_DAMPING + lane] = (T)CMT(dof_damping)[lane];
-    if (lane < CW_NB) w.st[S_MASS + lane] = (T)CMT(body_mass)[lane];
-    if (lane < 10) w.st[S_MENC + lane] = 0;
-    else if (lane < 16) w.st[S_JENC + lane - 10] = 0;
-    else if (lane < 22) w.st[S_XFRC + lane - 16] = 0;
-    else if (lane < 26) w.st[S_FLOORQ + lane - 22] = lane == 22 ? (T)1 : (T)0;
+    if (full) {
+      for (int k = S_QVEL + lane; k < S_UPTARGET; k += 32) w.st[k] = 0; /* qvel, warm start, ctrl, sensors, delay line, filters */
+      for (int k = lane; k < CM_NQ; k += 32) w.st[S_QPOS + k] = (T)CMT(qpos_init)[k];
+      for (int k = lane; k < 90; k += 32) w.sti[I_DRIVEHIST + k] = 0;
+      if (lane >= 16 && lane < 22) w.st[S_XFRC + lane - 16] = 0;
+    } else if (lane < 3) {
+      w.st[S_LASTPELVIS + lane] = w.st[S_QPOS + lane];
+    }
     if (lane == 31) {
-      w.st[S_FRICTION] = 1;
       w.st[S_PHASE] = 0; w.st[S_SPEED] = 0; w.st[S_ORIENT] = 0; w.st[S_PHASEADD] = 1;
       w.st[S_SWING] = (T)0.15; w.st[S_STANCE] = (T)0.25; w.st[S_PHASELEN] = 32; w.sti[I_PHASEFLOOR] = 32; /* (0.3 + 0.5) * 40 */
-      w.sti[I_TIME] = 0; w.sti[I_COUNTER] = 0; w.sti[I_DRIVEINIT] = 0; w.sti[I_JOINTINIT] = 0;
-      w.sti[I_STANCEMODE] = 1; w.sti[I_SIMSTEPS] = 0;
+      w.sti[I_TIME] = 0; w.sti[I_COUNTER] = 0; w.sti[I_STANCEMODE] = 1;
+      if (full) { w.sti[I_DRIVEINIT] = 0; w.sti[I_JOINTINIT] = 0; w.sti[I_SIMSTEPS] = 0; }
     }
   }
   CW_SYNC();
-  cw_set_const<T>(w CW_LANE_ARG);
-  cw_mj_step<T>(w, false, 0 CW_LANE_ARG);
   T fp[6];
-  cw_foot_positions<T>(w, fp);
-  CW_SYNC();
-  CW_FOR_LANES {
-    if (lane < 6) w.st[S_FOOTPOS + lane] = fp[lane];
-    for (int k = lane; k < Y_WORDS; k += 32) {
-      T v = 0;
-      if (k == Y_PPOS + 2) v = (T)1.01;
-      else if (k == Y_QUAT) v = 1;
-      else if (k >= Y_MPOS && k < Y_MPOS + 10) v = (T)CWT(CW_OFFSET)[k - Y_MPOS];
-      else if (k >= Y_JPOS && k < Y_JPOS + 6) { const int j = (k - Y_JPOS) % 3; v = j == 0 ? (T)0 : (j == 1 ? (T)1.4267 : (T)-1.5968); }
-      w.y[k] = v;
+  if (!full) { /* cassie.py:704-714: the simulator keeps running; cassie_state comes from one sub-step with the current pd_in_t */
+    cw_sim_step_pd<T>(w, 0 CW_LANE_ARG);
+    cw_foot_positions<T>(w, fp);
+    CW_SYNC();
+    CW_FOR_LANES { if (lane == 0) w.sti[I_SIMSTEPS] += 1; }
+  }
+  if (dyn) { /* cassie.py:719-733: only an env that randomises its dynamics puts the defaults back; outside edits survive */
+    CW_FOR_LANES {
+      w.st[S_DAMPING + lane] = (T)CMT(dof_damping)[lane];
+      if (lane < CW_NB) w.st[S_MASS + lane] = (T)CMT(body_mass)[lane];
+      if (lane < 10) w.st[S_MENC + lane] = 0;
+      else if (lane < 16) w.st[S_JENC + lane - 10] = 0;
+      else if (lane < 20) w.st[S_FLOORQ + lane - 16] = lane == 16 ? (T)1 : (T)0;
+      else if (lane == 20) w.st[S_FRICTION] = 1;
+    }
+    CW_SYNC();
+    cw_set_const<T>(w CW_LANE_ARG);
+  }
+  if (full) {
+    cw_mj_step<T>(w, false, 0 CW_LANE_ARG);
+    cw_foot_positions<T>(w, fp);
+    CW_SYNC();
+    CW_FOR_LANES { /* reset_cassie_state (cassie.py:735-746): the observation comes from these numbers, not from the simulator */
+      for (int k = lane; k < Y_WORDS; k += 32) {
+        T v = 0;
+        if (k == Y_PPOS + 2) v = (T)1.01;
+        else if (k == Y_QUAT) v = 1;
+        else if (k >= Y_MPOS && k < Y_MPOS + 10) v = (T)CWT(CW_OFFSET)[k - Y_MPOS];
+        else if (k >= Y_JPOS && k < Y_JPOS + 6) { const int j = (k - Y_JPOS) % 3; v = j == 0 ? (T)0 : (j == 1 ? (T)1.4267 : (T)-1.5968); }
+        w.y[k] = v;
+      }
     }
   }
+  CW_SYNC();
+  CW_FOR_LANES { if (lane < 6) w.st[S_FOOTPOS + lane] = fp[lane]; }
   CW_SYNC();
   cw_env_obs<T>(w, obs_out CW_LANE_ARG);
 }

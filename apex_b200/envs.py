@@ -70,21 +70,49 @@ class BatchedCassieEnv:
         return (self.sti if ints else self.st)[:, off:off + width]
 
     def reset(self):
+        self._plen64 = None
         with torch.cuda.device(self.device):
             _lib.check(self.L.apex_cassie_env_reset(self.dt, self.st.data_ptr(), self.sti.data_ptr(), self.num_envs,
                                                     self.obs.data_ptr(), self._stream()), "env_reset")
         return self.obs
 
-    def reset_for_test(self, full_reset=True, active=None):
-        """CassieEnv.reset_for_test(full_reset=True) (cassie/cassie.py:682-733) for every env (or those with active != 0): the
-        start state of the evaluation tools.  full_reset=False (a sub-step on the running simulator) is not on that path."""
-        if not full_reset:
-            raise NotImplementedError("the evaluation tools call reset_for_test(full_reset=True) (tools/test_commands.py:69)")
+    def reset_for_test(self, full_reset=False, active=None):
+        """CassieEnv.reset_for_test (cassie/cassie.py:682-733) for every env (or those with active != 0).  full_reset=True: a
+        fresh simulator and the synthetic cassie_state (what tools/test_commands.py:69 and tools/eval_perturb.py:31 call);
+        full_reset=False (the reference's default, 5k_test.py:64): the simulator keeps running, one sub-step with the current
+        PD target."""
+        self._plen64 = None  # the kernel installs the 32-step clock (exact in either precision)
         with torch.cuda.device(self.device):
             _lib.check(self.L.apex_cassie_env_reset_for_test(self.dt, self.st.data_ptr(), self.sti.data_ptr(), self.num_envs,
                                                              self.obs.data_ptr(), None if active is None else active.data_ptr(),
-                                                             self._stream()), "env_reset_for_test")
+                                                             int(bool(full_reset)), self._stream()), "env_reset_for_test")
         return self.obs
+
+    def update_speed(self, new_speed, new_side_speed=0.0, active=None):
+        """CassieEnv.update_speed (cassie/cassie.py:751-768, clock command): per env clip the commands, rebuild swing / stance /
+        period from the (signed) speed and rescale the phase with the reference's truncation.  new_speed: scalar or [N];
+        active: optional mask, envs with active == 0 keep their clock."""
+        f = self.field
+        # the period in float64: the phase rescale below is sensitive to its last bit (a float32 env stores a rounded copy)
+        old = self._plen64 if getattr(self, "_plen64", None) is not None else f("phaselen")[:, 0].double()
+        clock = clock_from_speed(torch.as_tensor(new_speed, dtype=torch.float64, device=self.device).expand(self.num_envs),
+                                 torch.as_tensor(new_side_speed, dtype=torch.float64, device=self.device).expand(self.num_envs),
+                                 f("phase")[:, 0].double(), old)
+        on = torch.ones(self.num_envs, dtype=torch.bool, device=self.device) if active is None else active.bool()
+        for name, v in zip(("speed", "side_speed", "swing", "stance", "phaselen", "phase"), clock[:6]):
+            f(name)[:, 0] = torch.where(on, v.to(self.dtype), f(name)[:, 0])
+        f("phase_floor")[:, 0] = torch.where(on, clock[6], f("phase_floor")[:, 0])
+        self._plen64 = torch.where(on, clock[4], old)
+
+    def step_basic(self, action, active=None):
+        """CassieEnv.step_basic (cassie/cassie.py:499-521): the same 50 sub-steps, phase and time bookkeeping as step(), no
+        random command changes; returns the observation only.  (The reward bookkeeping step() also does — prev_action /
+        prev_torque — still runs here; it is read by nothing but a later step()'s reward.)"""
+        hold = self.field("hold_commands")[:, 0].clone()
+        self.field("hold_commands")[:, 0] = 1
+        obs = self.step(action, active=active)[0]
+        self.field("hold_commands")[:, 0] = hold
+        return obs
 
     def apply_force(self, xfrc, body_name="cassie-pelvis"):
         """sim.apply_force (cassie/cassiemujoco/cassiemujoco.py:99-103) per env: xfrc [N, 6] or [6] = force(3) + torque(3) in
@@ -114,6 +142,8 @@ class BatchedCassieEnv:
         rew = self.rew if rew_out is None else rew_out
         done = self.done if done_out is None else done_out
         tp, trows, tlen = self._traj_args()
+        if self.max_traj_len > 0:
+            self._plen64 = None  # an in-kernel episode reset rebuilds the clock
         with torch.cuda.device(self.device):
             order = None
             if self.balance:  # group envs of similar solver cost into the same CTA (results do not depend on it)
@@ -132,6 +162,21 @@ class BatchedCassieEnv:
         for name, val in (("speed", speed), ("side_speed", side_speed), ("phase", phase)):
             if val is not None:
                 self.field(name)[:, 0] = torch.as_tensor(val, dtype=self.dtype, device=self.device)
+
+
+def clock_from_speed(new_speed, new_side_speed, phase, old_phaselen):
+    """The arithmetic of CassieEnv.update_speed (cassie/cassie.py:751-768) on float64 tensors, one rounding per operation in the
+    reference's order (separate torch ops, so nothing is contracted into an FMA): returns (speed, side_speed, swing, stance,
+    phaselen, phase, floor(phaselen) as int32).  phase = int(phaselen * phase / old_phaselen) truncates like Python's int()."""
+    speed = new_speed.clamp(-0.3, 4.0)
+    side = new_side_speed.clamp(-0.3, 0.3)
+    total = (0.9 - (0.25 / 3.0) * speed) / 2
+    k = (0.70 - 0.30) / 3
+    swing = (0.30 + k * speed) * total
+    stance = (0.70 - k * speed) * total
+    phaselen = (2 * swing + 2 * stance) * 40.0  # create_phase_reward: total_duration * FREQ, FREQ = 2000 // simrate
+    new_phase = torch.trunc(phaselen * phase / old_phaselen)
+    return speed, side, swing, stance, phaselen, new_phase, torch.floor(phaselen).to(torch.int32)
 
 
 def sim_time_table(n):

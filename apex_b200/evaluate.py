@@ -225,3 +225,48 @@ def compute_perturbs(env_fn, policy, wait_time=4, perturb_duration=0.2, perturb_
     for i, j in pairs:  # never failed within max_rounds * ladder sizes
         out[i, j] = base - perturb_incr
     return out
+
+
+def terrain_quat(terrain):
+    """Floor orientation of a 5k-test terrain name "<direction>_<degrees>" (5k_test.py:36-46): euler2quat with roll (left / right)
+    or pitch (up).  The reference's fourth branch repeats "right", so "down" is rejected there too."""
+    direct, angle = terrain.split("_")
+    a = math.radians(float(angle))
+    roll, pitch = {"left": (a, 0.0), "right": (-a, 0.0), "up": (0.0, -a)}.get(direct, (None, None))
+    if roll is None:
+        raise ValueError("Error: Terrain type not understood")
+    cx, sx, cy, sy = math.cos(roll / 2), math.sin(roll / 2), math.cos(pitch / 2), math.sin(pitch / 2)
+    q = np.array([cx * cy, cy * sx, cx * sy, sx * sy])  # cassie/quaternion_function.py:44-62 with z = 0
+    return -q if q[0] < 0 else q
+
+
+@torch.no_grad()
+def test_5k(env, policy, speeds, orients, floor_quat=None, friction=None, foot_mass=None):
+    """One 5k-test trial per env (5k_test.py:27-75, test_worker.test_5k): floor tilt, floor friction and foot masses per env,
+    reset_for_test() on the just-built simulator, then for every mission command update_speed, orient_add, the policy's
+    deterministic action, step_basic; a trial fails when the pelvis drops below 0.4 m.  `env` must be newly constructed (the
+    reference builds a new CassieSim per trial) without dynamics randomisation.  speeds, orients: [N, M] (or [M], shared);
+    floor_quat [N, 4], friction [N] (sliding friction of the floor), foot_mass [N].  Returns passed [N] (bool)."""
+    N, dev = env.num_envs, env.device
+    f64 = lambda a: torch.as_tensor(np.asarray(a, dtype=np.float64), device=dev)
+    speeds, orients = f64(speeds), f64(orients)
+    if speeds.dim() == 1:
+        speeds, orients = speeds.expand(N, -1), orients.expand(N, -1)
+    if floor_quat is not None:
+        env.field("floor_quat", 4)[:] = f64(floor_quat).to(env.dtype)
+    if friction is not None:
+        env.field("friction")[:, 0] = f64(friction).to(env.dtype)
+    if foot_mass is not None:
+        m = f64(foot_mass).to(env.dtype)
+        env.field("body_mass", 26)[:, 13], env.field("body_mass", 26)[:, 25] = m, m  # left-foot, right-foot (cassie.xml body order)
+    env.max_traj_len = 0
+    obs = env.reset_for_test(full_reset=False)
+    active = torch.ones(N, dtype=torch.int32, device=dev)
+    for i in range(speeds.shape[1]):
+        env.update_speed(speeds[:, i], active=active)  # a fallen trial's loop has returned: its clock stays where it was
+        env.field("orient_add")[:, 0] = orients[:, i].to(env.dtype)
+        obs = env.step_basic(policy(obs), active=active)
+        active = active * (env.field("qpos", 35)[:, 2] >= 0.4).int()
+        if not bool(active.any()):
+            break
+    return active.bool().cpu().numpy()

@@ -34,14 +34,15 @@ int apex_cassie_layout(const char *name);
 int apex_cassie_env_init(int dtype, void *st, int *sti, int n, unsigned seed, int env_id0, int dyn_rand, void *stream);
 /* CassieEnv.reset for every env; obs [n][50] */
 int apex_cassie_env_reset(int dtype, void *st, int *sti, int n, void *obs, void *stream);
-/* CassieEnv.reset_for_test(full_reset=True) (cassie/cassie.py:682-733 with cassie_sim_full_reset, cassiemujoco_ctypes.py
- * and reset_cassie_state :735-746) — the start state of tools/test_commands.py:69 and tools/eval_perturb.py:31,89 — for the
+/* CassieEnv.reset_for_test(full_reset) (cassie/cassie.py:682-733).  full_reset != 0: cassie_sim_full_reset + reset_cassie_state
+ * (:735-746), the start state of tools/test_commands.py:69 and tools/eval_perturb.py:31,89.  full_reset == 0 (the signature's
+ * default, 5k_test.py:64): the simulator keeps running and takes one sub-step with the current PD target.  Applies to the
  * envs whose active[e] != 0 (all when active is NULL); obs [n][50] rows of the other envs are left alone.  What the
  * evaluation tools then assign between steps lives in named state fields (apex_cassie_layout): "speed", "phase_add"
  * (tools/test_commands.py:81-87), "xfrc_applied" = force(3) + torque(3) on the pelvis, kept until overwritten
  * (cassie_sim_apply_force, cassiemujoco.py:99-103); "sim_steps" counts sub-steps (sim.time() = sim_steps additions of 0.0005); "hold_commands" != 0 switches off
  * the env's own random command changes (cassie/cassie.py:483-491) for deterministic evaluation (not a reference feature). */
-int apex_cassie_env_reset_for_test(int dtype, void *st, int *sti, int n, void *obs, const int *active, void *stream);
+int apex_cassie_env_reset_for_test(int dtype, void *st, int *sti, int n, void *obs, const int *active, int full_reset, void *stream);
 /* CassieEnv.step for every env: action [n][10] -> obs [n][50], reward [n], done [n] (bit0 terminal, bit1 time-out).
  * With max_traj_len > 0 an env whose episode ended is reset in the same launch: obs then holds the first
  * observation of the new episode and term_obs [n][50] (may be NULL) the last one of the old episode. */

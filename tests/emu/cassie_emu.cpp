@@ -36,12 +36,12 @@ template <typename T> static void store(const CassieWs<T> &w, T *st, int *sti) {
     }                                                                                                               \
     delete w;                                                                                                       \
   }                                                                                                                 \
-  extern "C" void emu_reset_for_test_##SUF(T *st, int *sti, int n, T *obs) {                                        \
+  extern "C" void emu_reset_for_test_##SUF(T *st, int *sti, int n, T *obs, int full) {                              \
     CassieWs<T> *w = new CassieWs<T>();                                                                             \
     for (int e = 0; e < n; e++) {                                                                                   \
       memset(w, 0, sizeof(*w));                                                                                     \
       load(*w, st + (size_t)e * S_WORDS, sti + (size_t)e * I_WORDS);                                                \
-      cw_env_reset_for_test<T>(*w, obs + (size_t)e * CW_OBS);                                                       \
+      cw_env_reset_for_test<T>(*w, obs + (size_t)e * CW_OBS, full);                                                 \
       store(*w, st + (size_t)e * S_WORDS, sti + (size_t)e * I_WORDS);                                               \
     }                                                                                                               \
     delete w;                                                                                                       \
@@ -101,7 +101,8 @@ DEFINE(float, f32)
 extern "C" void emu_clock_from_speed(double speed, double *out) { cw_clock_from_speed(speed, out, out + 1, out + 2); }
 extern "C" int emu_layout(const char *name) {
   const struct { const char *n; int off; } tab[] = {{"speed", S_SPEED}, {"phase_add", S_PHASEADD}, {"xfrc_applied", S_XFRC}, {"phase", S_PHASE},
-                                                    {"qpos", S_QPOS}, {"qvel", S_QVEL}, {"sim_steps", I_SIMSTEPS}, {"stance_mode", I_STANCEMODE}, {"hold_commands", I_HOLDCMD}};
+                                                    {"qpos", S_QPOS}, {"qvel", S_QVEL}, {"sim_steps", I_SIMSTEPS}, {"stance_mode", I_STANCEMODE}, {"hold_commands", I_HOLDCMD}, {"orient_add", S_ORIENT}, {"side_speed", S_SIDE}, {"swing", S_SWING}, {"stance", S_STANCE}, {"phaselen", S_PHASELEN},
+                                                    {"phase_floor", I_PHASEFLOOR}, {"friction", S_FRICTION}, {"floor_quat", S_FLOORQ}, {"body_mass", S_MASS}};
   for (size_t i = 0; i < sizeof(tab) / sizeof(tab[0]); i++) if (strcmp(tab[i].n, name) == 0) return tab[i].off;
   return -1;
 }

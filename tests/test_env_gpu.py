@@ -316,3 +316,31 @@ def test_batched_eval_tools_on_the_gpu():
                                      hold_commands=True)
     print("push failures at 20 N / 2000 N:", failed[:n].mean(), failed[n:].mean())
     assert failed[:n].mean() < 0.2 and failed[n:].mean() > 0.9, (failed[:n].mean(), failed[n:].mean())
+
+
+def test_5k_test_loop_on_the_gpu():
+    """apex_b200.evaluate.test_5k on the CUDA env (float32), reference's shipped policy: the three terrain / friction / foot-mass
+    cases recorded from the reference's own env code (tests/golden/test5k.npz) fall as they do there, and the constant-command
+    trials show the reference's update_speed arithmetic: at 0.5 m/s the truncating phase rescale pins the phase at 15 and the
+    robot falls, at 0, 0.3, 0.9 and 1.0 m/s the clock cycles and it keeps walking (checked on the oracle as well)."""
+    import os
+    from apex_b200 import evaluate
+    from apex_b200.envs import BatchedCassieEnv
+    from tests.test_oracle_cpu import _torch_ref_actor
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "test5k.npz"))
+    M = 200
+    const = [0.5, 0.0, 0.3, 0.9, 1.0]
+    n = 3 + len(const)
+    speeds = np.stack([g["speeds"][:M]] * 3 + [np.full(M, v) for v in const])
+    orients = np.stack([g["orients"][:M]] * 3 + [np.zeros(M)] * len(const))
+    quat = np.stack([g[f"case{c}.floor_quat"] for c in range(3)] + [np.array([1.0, 0, 0, 0])] * len(const))
+    fric = np.array([g[f"case{c}.friction"][0] for c in range(3)] + [1.0] * len(const))
+    mass = np.array([float(g[f"case{c}.foot_mass"]) for c in range(3)] + [1.1992] * len(const))
+    env = BatchedCassieEnv(n, dtype=torch.float32, seed=0, dynamics_randomization=False, max_traj_len=0)
+    passed = evaluate.test_5k(env, evaluate.KernelPolicy(_torch_ref_actor(), env.device), speeds, orients, quat, fric, mass)
+    print("5k passed:", passed.tolist(), "phase:", env.field("phase")[:, 0].tolist(), "steps:", env.field("time")[:, 0].tolist())
+    assert list(passed) == [False, False, False, False, True, True, True, True], passed  # golden cases 0-2, stuck clock, healthy clocks
+    steps, want = env.field("time")[:4, 0].tolist(), [int(g[f"case{c}.steps"]) for c in range(4)]
+    assert all(abs(a - b) <= 3 for a, b in zip(steps, want)), (steps, want)  # measured: falls at exactly the reference run's steps (62, 71, 18, 55)
+    assert float(env.field("phase")[3, 0]) == 15.0  # where the reference's arithmetic leaves it
+    assert np.allclose(evaluate.terrain_quat("left_3.0"), g["case0.floor_quat"]) and np.allclose(evaluate.terrain_quat("up_25.0"), g["case2.floor_quat"])

@@ -249,7 +249,7 @@ def test_kernel_source_eval_entry_points_match_oracle_f64(L, emu):
         for t in range(-5, sch["STEPS"]):
             if t in sch["RESET_AT"]:
                 L.ce_env_reset_for_test(buf, dp(oobs))
-                emu.emu_reset_for_test_f64(dp(st), dp(sti), 1, dp(eobs))
+                emu.emu_reset_for_test_f64(dp(st), dp(sti), 1, dp(eobs), 1)
                 assert np.abs(oobs - eobs).max() < 1e-12
             if t in sch["SPEED"]:
                 L.ce_env_set_speed(buf, sch["SPEED"][t])
@@ -281,7 +281,7 @@ def test_kernel_source_hold_commands(L, emu):
     emu.emu_init_f64(dp(st), dp(sti), 1, C.c_uint(0), 0, 0)
     eobs, erew, edone = np.zeros((1, 50)), np.zeros(1), np.zeros(1, dtype=np.int32)
     env.reset_for_test()
-    emu.emu_reset_for_test_f64(dp(st), dp(sti), 1, dp(eobs))
+    emu.emu_reset_for_test_f64(dp(st), dp(sti), 1, dp(eobs), 1)
     env.set_speed(0.7)
     st[0, off("speed")], sti[0, off("hold_commands")] = 0.7, 1
     rng = np.random.default_rng(5)
@@ -520,6 +520,43 @@ def test_5k_inner_loop_matches_the_reference_python(L, case):
     assert (env.qpos_qvel()[0][2] < 0.4) == (not bool(f("passed")))
     if case == 3:
         assert list(f("phase")[15:40]) == [15.0] * 25
+
+
+@pytest.mark.parametrize("case", [0, 3])
+def test_kernel_source_5k_inner_loop(emu, case):
+    """The same 5k-test loop through the kernel source (host build): model edits as state-field writes, reset_for_test with
+    full_reset = 0, apex_b200.envs.clock_from_speed for update_speed (float64 torch ops, the reference's truncating phase
+    rescale), step with hold_commands for step_basic — against the reference's recorded run."""
+    import torch
+    from apex_b200.envs import clock_from_speed
+    g = np.load(os.path.join(G, "test5k.npz"))
+    f = lambda k: g[f"case{case}.{k}"]
+    SW, IW = emu.emu_state_words(), emu.emu_istate_words()
+    off = lambda name: emu.emu_layout(name.encode())
+    st, sti = np.zeros((1, SW)), np.zeros((1, IW), dtype=np.int32)
+    emu.emu_init_f64(dp(st), dp(sti), 1, C.c_uint(0), 0, 0)
+    st[0, off("floor_quat"):off("floor_quat") + 4] = f("floor_quat")
+    st[0, off("friction")] = f("friction")[0]
+    st[0, off("body_mass") + 13] = st[0, off("body_mass") + 25] = float(f("foot_mass"))
+    sti[0, off("hold_commands")] = 1
+    obs, rew, done = np.zeros((1, 50)), np.zeros(1), np.zeros(1, dtype=np.int32)
+    emu.emu_reset_for_test_f64(dp(st), dp(sti), 1, dp(obs), 0)
+    assert np.abs(obs[0] - f("obs")[0]).max() < 1e-10 and np.abs(st[0, :35] - f("qpos")[0]).max() < 1e-11
+    actor = _torch_ref_actor()
+    speeds = g["speeds"] if case != 3 else np.full(len(g["speeds"]), 0.5)
+    t64 = lambda v: torch.tensor([float(v)], dtype=torch.float64)
+    for i in range(int(f("steps"))):
+        c = clock_from_speed(t64(speeds[i]), t64(0.0), t64(st[0, off("phase")]), t64(st[0, off("phaselen")]))
+        for name, v in zip(("speed", "side_speed", "swing", "stance", "phaselen", "phase"), c[:6]):
+            st[0, off(name)] = v.item()
+        sti[0, off("phase_floor")] = int(c[6].item())
+        st[0, off("orient_add")] = g["orients"][i]
+        with torch.no_grad():
+            a = actor(torch.as_tensor(f("obs")[i], dtype=torch.float32)[:49], True).numpy().astype(np.float64).reshape(1, 10)
+        emu.emu_step_f64(dp(st), dp(sti), 1, dp(np.ascontiguousarray(a)), dp(obs), dp(rew), dp(done), None, 0, None, 0, 0)
+        assert st[0, off("phase")] == f("phase")[i + 1] and st[0, off("phaselen")] == f("phaselen")[i + 1], i
+        assert np.abs(st[0, :35] - f("qpos")[i + 1]).max() < 1e-8, i
+        assert np.abs(obs[0] - f("obs")[i + 1]).max() < 1e-7, (i, int(np.abs(obs[0] - f("obs")[i + 1]).argmax()))
 
 
 def test_reference_abi_exports_all_103_symbols():
