@@ -241,17 +241,19 @@ def terrain_quat(terrain):
 
 
 @torch.no_grad()
-def test_5k(env, policy, speeds, orients, floor_quat=None, friction=None, foot_mass=None):
+def test_5k(env, policy, speeds, orients, floor_quat=None, friction=None, foot_mass=None, lengths=None):
     """One 5k-test trial per env (5k_test.py:27-75, test_worker.test_5k): floor tilt, floor friction and foot masses per env,
     reset_for_test() on the just-built simulator, then for every mission command update_speed, orient_add, the policy's
     deterministic action, step_basic; a trial fails when the pelvis drops below 0.4 m.  `env` must be newly constructed (the
-    reference builds a new CassieSim per trial) without dynamics randomisation.  speeds, orients: [N, M] (or [M], shared);
-    floor_quat [N, 4], friction [N] (sliding friction of the floor), foot_mass [N].  Returns passed [N] (bool)."""
+    reference builds a new CassieSim per trial) without dynamics randomisation.  speeds, orients: [N, M] (or [M], shared), with
+    lengths [N] when missions differ in length; floor_quat [N, 4], friction [N] (sliding friction of the floor), foot_mass [N].
+    Returns passed [N] (bool)."""
     N, dev = env.num_envs, env.device
     f64 = lambda a: torch.as_tensor(np.asarray(a, dtype=np.float64), device=dev)
     speeds, orients = f64(speeds), f64(orients)
     if speeds.dim() == 1:
         speeds, orients = speeds.expand(N, -1), orients.expand(N, -1)
+    lengths = torch.full((N,), speeds.shape[1], device=dev) if lengths is None else torch.as_tensor(np.asarray(lengths), device=dev)
     if floor_quat is not None:
         env.field("floor_quat", 4)[:] = f64(floor_quat).to(env.dtype)
     if friction is not None:
@@ -261,12 +263,62 @@ def test_5k(env, policy, speeds, orients, floor_quat=None, friction=None, foot_m
         env.field("body_mass", 26)[:, 13], env.field("body_mass", 26)[:, 25] = m, m  # left-foot, right-foot (cassie.xml body order)
     env.max_traj_len = 0
     obs = env.reset_for_test(full_reset=False)
-    active = torch.ones(N, dtype=torch.int32, device=dev)
+    fallen = torch.zeros(N, dtype=torch.bool, device=dev)
     for i in range(speeds.shape[1]):
-        env.update_speed(speeds[:, i], active=active)  # a fallen trial's loop has returned: its clock stays where it was
-        env.field("orient_add")[:, 0] = orients[:, i].to(env.dtype)
-        obs = env.step_basic(policy(obs), active=active)
-        active = active * (env.field("qpos", 35)[:, 2] >= 0.4).int()
+        active = (~fallen & (i < lengths)).int()
         if not bool(active.any()):
             break
-    return active.bool().cpu().numpy()
+        env.update_speed(speeds[:, i], active=active)  # a finished trial's loop has returned: its clock stays where it was
+        oa = env.field("orient_add")
+        oa[:, 0] = torch.where(active.bool(), orients[:, i].to(oa.dtype), oa[:, 0])
+        obs = env.step_basic(policy(obs), active=active)
+        fallen |= active.bool() & (env.field("qpos", 35)[:, 2] < 0.4)
+    return (~fallen).cpu().numpy()
+
+
+def load_mission(path):
+    """cassie/missions/<name>/command_trajectory_<speed>.pkl: a pickled dict with 'speed' and 'orient' command arrays (and
+    'compos', unused by the test)."""
+    import pickle
+    with open(path, "rb") as f:
+        d = pickle.load(f)
+    return np.asarray(d["speed"], dtype=np.float64), np.asarray(d["orient"], dtype=np.float64)
+
+
+def grid_5k(env_fn, policy, mission_dict, terrains, missions, mission_speeds, frictions, masses, batch=None):
+    """The grid of 5k_test.py:296-387: every (terrain, mission, mission speed, friction, foot mass) combination in the reference's
+    order, `batch` trials per batched env (all at once when None).  env_fn(n) builds a NEW env of n envs; mission_dict maps
+    mission + str(speed) to (speeds, orients) (load_mission).  terrains: "cassie.xml" (flat) or "<left|right|up>_<deg>"; the
+    height-field terrains (*.npy on cassie_hfield.xml) are not in the kernel.  Returns the six lists the reference pickles into
+    5k_test.pkl: [pass_data, terrain_data, mission_data, mission_speed_data, friction_data, mass_data]."""
+    args = [(mission, ms, terrain, np.asarray(fr, dtype=np.float64), float(mass))
+            for terrain in terrains for mission in missions for ms in mission_speeds for fr in frictions for mass in masses]
+    for _, _, terrain, _, _ in args:
+        if terrain.endswith(".npy"):
+            raise NotImplementedError("height-field terrains (cassie_hfield.xml) are outside the kernel's model")
+    passed = []
+    step = len(args) if batch is None else int(batch)
+    for k in range(0, len(args), step):
+        chunk = args[k:k + step]
+        cmds = [mission_dict[m + str(ms)] for m, ms, _, _, _ in chunk]
+        lengths = np.array([len(c[0]) for c in cmds])
+        sp, orr = np.zeros((len(chunk), lengths.max())), np.zeros((len(chunk), lengths.max()))
+        for r, c in enumerate(cmds):
+            sp[r, :lengths[r]], orr[r, :lengths[r]] = c[0], c[1]
+        quat = np.stack([np.array([1.0, 0, 0, 0]) if t.endswith(".xml") else terrain_quat(t) for _, _, t, _, _ in chunk])
+        passed += list(test_5k(env_fn(len(chunk)), policy, sp, orr, quat, [a[3][0] for a in chunk], [a[4] for a in chunk], lengths))
+    return [[bool(p) for p in passed], [a[2] for a in args], [a[0] for a in args], [a[1] for a in args], [a[3] for a in args], [a[4] for a in args]]
+
+
+def calc_stats_5k(pass_data, terrain_data, mission_data, mission_speed_data, friction_data, mass_data):
+    """5k_test.py:130-182: overall pass rate and the pass rate per terrain, per mission x speed, per friction, per foot mass."""
+    import os
+    ok = np.asarray(pass_data, dtype=np.float64)
+    rate = lambda idx: float(ok[idx].sum() / len(idx))
+    sel = lambda data, x: [i for i, v in enumerate(data) if (np.all(v == x) if isinstance(x, np.ndarray) else v == x)]
+    terrain = {os.path.basename(t): rate(sel(terrain_data, t)) for t in set(terrain_data)}
+    mission = {"{} {}".format(m, s): rate([i for i in sel(mission_data, m) if mission_speed_data[i] == s])
+               for m in set(mission_data) for s in set(mission_speed_data)}
+    fric = {np.array2string(fr): rate(sel(friction_data, fr)) for fr in np.unique(np.asarray(friction_data), axis=0)}
+    mass = {str(round(m, 6)): rate(sel(mass_data, m)) for m in set(mass_data)}
+    return float(ok.sum() / len(ok)), terrain, mission, fric, mass

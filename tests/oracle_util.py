@@ -117,7 +117,7 @@ class OracleBatchedEnv:
     own tools (tests/golden/make_evaltools_golden.py).  The env's random command changes are off (no hits injected), like in
     that script.  Observations carry float32 values (the reference wraps them in torch.Tensor before anything reads them)."""
 
-    def __init__(self, n):
+    def __init__(self, n, fresh=False):
         import torch
         self.torch, self.num_envs, self.device, self.dtype = torch, n, torch.device("cpu"), torch.float64
         self.envs = [OracleEnv(False) for _ in range(n)]
@@ -127,10 +127,19 @@ class OracleBatchedEnv:
         self.f = {"speed": torch.zeros(n, 1, dtype=torch.float64), "side_speed": torch.zeros(n, 1, dtype=torch.float64),
                   "phase_add": torch.ones(n, 1, dtype=torch.float64), "xfrc_applied": torch.zeros(n, 6, dtype=torch.float64),
                   "qpos": torch.zeros(n, 35, dtype=torch.float64), "sim_steps": torch.zeros(n, 1, dtype=torch.int64),
-                  "hold_commands": torch.zeros(n, 1, dtype=torch.int32)}
+                  "hold_commands": torch.zeros(n, 1, dtype=torch.int32), "orient_add": torch.zeros(n, 1, dtype=torch.float64),
+                  "floor_quat": torch.tensor([[1.0, 0, 0, 0]] * n, dtype=torch.float64), "friction": torch.ones(n, 1, dtype=torch.float64),
+                  "body_mass": torch.tensor([list(P.Model.from_address(self._model(e)).body_mass) for e in self.envs], dtype=torch.float64)}
         self.obs = torch.zeros(n, 50, dtype=torch.float64)
-        for e in self.envs:  # use the env once, as a tool's env_fn() + first episode would
-            self.L.ce_env_reset(e.buf, dp(e.obs))
+        self.L.ce_env_update_speed.argtypes = [C.c_void_p, C.c_double, C.c_double]
+        self.L.ce_env_set_orient_add.argtypes = [C.c_void_p, C.c_double]
+        if not fresh:
+            for e in self.envs:  # use the env once, as a tool's env_fn() + first episode would
+                self.L.ce_env_reset(e.buf, dp(e.obs))
+
+    def _model(self, e):
+        self.L.ce_env_model.restype = C.c_void_p
+        return self.L.ce_env_model(e.buf)
 
     def field(self, name, width=1):
         return self.f[name]
@@ -140,13 +149,37 @@ class OracleBatchedEnv:
         self.obs[i] = self.torch.as_tensor(e.obs.astype(np.float32).astype(np.float64))
         self.f["qpos"][i] = self.torch.as_tensor(e.qpos_qvel()[0])
 
-    def reset_for_test(self, full_reset=True, active=None):
-        assert full_reset
+    def reset_for_test(self, full_reset=False, active=None):
         for i, e in enumerate(self.envs):
             if active is None or int(active[i]):
-                e.reset_for_test()
-                self.f["speed"][i], self.f["phase_add"][i], self.f["xfrc_applied"][i], self.f["sim_steps"][i] = 0.0, 1.0, 0.0, 0
+                m = P.Model.from_address(self._model(e))  # outside edits of the model (5k_test.py:46-49) arrive through the fields
+                for k in range(4):
+                    m.floor_quat[k] = float(self.f["floor_quat"][i, k])
+                m.floor_friction[0] = float(self.f["friction"][i, 0])
+                m.body_mass[13], m.body_mass[25] = float(self.f["body_mass"][i, 13]), float(self.f["body_mass"][i, 25])
+                self.L.ce_env_reset_for_test_mode(e.buf, int(bool(full_reset)), dp(e.obs))
+                self.f["speed"][i], self.f["phase_add"][i], self.f["orient_add"][i] = 0.0, 1.0, 0.0
+                if full_reset:
+                    self.f["xfrc_applied"][i], self.f["sim_steps"][i] = 0.0, 0
                 self._pull(i)
+        return self.obs
+
+    def update_speed(self, new_speed, new_side_speed=0.0, active=None):
+        v = self.torch.as_tensor(new_speed, dtype=self.torch.float64).expand(self.num_envs)
+        for i, e in enumerate(self.envs):
+            if active is None or int(active[i]):
+                self.L.ce_env_update_speed(e.buf, float(v[i]), float(new_side_speed))
+                self.f["speed"][i, 0] = min(max(float(v[i]), -0.3), 4.0)
+
+    def step_basic(self, action, active=None):
+        a = np.asarray(action.detach().cpu().numpy(), dtype=np.float64)
+        for i, e in enumerate(self.envs):
+            if active is not None and not int(active[i]):
+                continue
+            self.L.ce_env_set_orient_add(e.buf, float(self.f["orient_add"][i, 0]))
+            self.L.ce_env_step_basic(e.buf, dp(np.ascontiguousarray(a[i])), dp(e.obs))
+            self.f["sim_steps"][i] += 50
+            self._pull(i)
         return self.obs
 
     def apply_force(self, xfrc, body_name="cassie-pelvis"):

@@ -559,6 +559,43 @@ def test_kernel_source_5k_inner_loop(emu, case):
         assert np.abs(obs[0] - f("obs")[i + 1]).max() < 1e-7, (i, int(np.abs(obs[0] - f("obs")[i + 1]).argmax()))
 
 
+def test_5k_tool_matches_the_reference_runs():
+    """apex_b200.evaluate.test_5k / grid_5k / calc_stats_5k (batched) over the oracle env: the four set-ups recorded from the
+    reference's env code fall exactly where they fell there; missions of different length in one batch; the grid comes back in
+    the reference's order with its six lists."""
+    from apex_b200 import evaluate
+    from tests.oracle_util import OracleBatchedEnv
+    g = np.load(os.path.join(G, "test5k.npz"))
+    policy = _rowwise(_torch_ref_actor())
+    M = len(g["speeds"])
+    speeds = np.stack([g["speeds"]] * 3 + [np.full(M, 0.5)])
+    orients = np.stack([g["orients"]] * 4)
+    env = OracleBatchedEnv(4, fresh=True)
+    passed = evaluate.test_5k(env, policy, speeds, orients, np.stack([g[f"case{c}.floor_quat"] for c in range(4)]),
+                              [g[f"case{c}.friction"][0] for c in range(4)], [float(g[f"case{c}.foot_mass"]) for c in range(4)],
+                              lengths=[M, M, M, 30])  # the last trial's mission ends before the stuck clock makes it fall (step 55)
+    assert list(passed) == [False, False, False, True]
+    steps = [int(env.f["sim_steps"][i, 0]) // 50 for i in range(4)]  # reset_for_test's own sub-step is not a multiple of 50
+    assert steps == [int(g["case0.steps"]), int(g["case1.steps"]), int(g["case2.steps"]), 30], steps
+    for c in range(3):
+        assert np.abs(env.f["qpos"][c].numpy() - g[f"case{c}.qpos"][-1]).max() < 1e-6, c
+    short = (np.full(40, 0.3), np.zeros(40))
+    made = []
+
+    def env_fn(n):
+        made.append(n)
+        return OracleBatchedEnv(n, fresh=True)
+    out = evaluate.grid_5k(env_fn, policy, {"a0.3": short, "b0.3": (np.full(25, 0.9), np.zeros(25))}, ["cassie.xml", "up_25"], ["a", "b"], [0.3],
+                           [np.array([1, 5e-3, 1e-4]), np.array([0.3, 5e-3, 1e-4])], [1.1992], batch=5)
+    assert made == [5, 3] and len(out) == 6 and len(out[0]) == 8
+    assert out[1] == ["cassie.xml"] * 4 + ["up_25"] * 4 and out[2] == ["a", "a", "b", "b"] * 2 and out[5] == [1.1992] * 8
+    assert out[0][:4] == [True] * 4 and out[0][5] is False  # flat ground passes; 25 degrees uphill on a slippery floor does not
+    avg, terr, mis, fric, mass = evaluate.calc_stats_5k(*out)
+    assert terr["cassie.xml"] == 1.0 and terr["up_25"] < 1.0 and set(mis) == {"a 0.3", "b 0.3"} and len(fric) == 2 and list(mass) == ["1.1992"]
+    with pytest.raises(NotImplementedError):
+        evaluate.grid_5k(env_fn, policy, {}, ["noise1.npy"], ["a"], [0.3], [np.ones(3)], [1.0])
+
+
 def test_reference_abi_exports_all_103_symbols():
     """oracle/cassiemujoco_abi.c must export every name cassie/cassiemujoco/cassiemujoco_ctypes.py binds at import."""
     import ctypes
