@@ -322,3 +322,28 @@ def calc_stats_5k(pass_data, terrain_data, mission_data, mission_speed_data, fri
     fric = {np.array2string(fr): rate(sel(friction_data, fr)) for fr in np.unique(np.asarray(friction_data), axis=0)}
     mass = {str(round(m, 6)): rate(sel(mass_data, m)) for m in set(mass_data)}
     return float(ok.sum() / len(ok)), terrain, mission, fric, mass
+
+
+def rank_slice(n, rank=None, world=None):
+    """Contiguous block of trials [lo, hi) of `n` for this rank (one process per GPU; ceil(n / world) per rank)."""
+    import torch.distributed as dist
+    if rank is None:
+        rank, world = (dist.get_rank(), dist.get_world_size()) if dist.is_initialized() else (0, 1)
+    per = -(-n // world)
+    return min(rank * per, n), min((rank + 1) * per, n)
+
+
+def eval_commands_sharded(env_fn, policy, speed_schedule, orient_schedule, **kw):
+    """eval_commands with the trials split across the ranks of the torch.distributed job (the role Ray's worker pool plays in
+    eval_commands_multi, tools/test_commands.py:125-172): every rank evaluates its block on its own GPU — no data-path collective,
+    trials are independent — and the result rows are exchanged once at the end, so every rank returns the full [N, 6] array in
+    trial order.  env_fn(n) builds this rank's batched env."""
+    import torch.distributed as dist
+    speed_schedule, orient_schedule = np.asarray(speed_schedule), np.asarray(orient_schedule)
+    lo, hi = rank_slice(len(speed_schedule))
+    local = eval_commands(env_fn(hi - lo), policy, speed_schedule[lo:hi], orient_schedule[lo:hi], **kw) if hi > lo else np.zeros((0, 6))
+    if not (dist.is_initialized() and dist.get_world_size() > 1):
+        return local
+    parts = [None] * dist.get_world_size()
+    dist.all_gather_object(parts, local)
+    return np.concatenate(parts, axis=0)

@@ -59,3 +59,33 @@ def test_two_rank_gradient_and_moment_allreduce():
     out = mgr.dict()
     mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
     assert all(out[r] for r in range(world))
+
+
+def _eval_worker(rank, world, port, out):
+    """Two ranks share the four command trials the reference's own tool was run on (tests/golden/evaltools.npz)."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    from apex_b200 import evaluate
+    from tests.oracle_util import OracleBatchedEnv
+    from tests.test_oracle_cpu import G, _rowwise, _torch_ref_actor
+    g = np.load(os.path.join(G, "evaltools.npz"))
+    made = []
+
+    def env_fn(n):
+        made.append(n)
+        return OracleBatchedEnv(n)
+    data = evaluate.eval_commands_sharded(env_fn, _rowwise(_torch_ref_actor()), g["speed_schedule"], g["orient_schedule"],
+                                          num_steps=int(g["num_steps"]), max_speed=3, min_speed=0)
+    out[rank] = bool(made == [2] and data.shape == (4, 6) and np.abs(data - g["command_rows"]).max() < 1e-12
+                     and evaluate.rank_slice(5, 1, 2) == (3, 5) and evaluate.rank_slice(1, 1, 2) == (1, 1))
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharded_eval_commands():
+    """Trials shard across ranks with no data-path collective; one exchange of result rows; same rows as the reference's tool."""
+    world, port = 2, _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_eval_worker, args=(world, port, out), nprocs=world, join=True)
+    assert all(out[r] for r in range(world))

@@ -385,8 +385,6 @@ def test_env_layer_matches_the_reference_python(tag, dyn, traj):
 
 def _eval_schedule():
     """The schedule tests/golden/make_eval_golden.py drove the reference env with (imported from that script)."""
-    import importlib.util
-    spec = importlib.util.spec_from_file_location("make_eval_golden", os.path.join(G, "make_eval_golden.py"))
     src = open(os.path.join(G, "make_eval_golden.py")).read()
     ns = {}
     for line in src.splitlines():  # the five constant tables only: the script itself imports the reference tree
