@@ -16,7 +16,22 @@ from . import _capi as _lib
 _DT = {torch.float32: 0, torch.float64: 1}
 
 
+def _command_attr(name):
+    """env.<name> as the reference's tools use it (env.speed = 0.5, env.orient_add += d, env.phase_add = 1.5; cassie/cassie.py:
+    110-125, tools/test_commands.py:70-87): reads give the per-env values [N], writes take a scalar or [N]."""
+    def get(self):
+        return self.field(name)[:, 0]
+
+    def put(self, value):
+        col = self.field(name)[:, 0]
+        col[:] = torch.as_tensor(value, device=col.device).to(col.dtype)
+    return property(get, put)
+
+
 class BatchedCassieEnv:
+    speed, side_speed, orient_add = _command_attr("speed"), _command_attr("side_speed"), _command_attr("orient_add")
+    phase, phase_add, phaselen = _command_attr("phase"), _command_attr("phase_add"), _command_attr("phaselen")
+
     def __init__(self, num_envs, device="cuda:0", dtype=torch.float32, seed=0, dynamics_randomization=True, simrate=50,
                  command_profile="clock", input_profile="full", reward="clock", max_traj_len=400, env_id0=0, history=0, balance=True,
                  **kwargs):

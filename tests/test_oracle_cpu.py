@@ -706,6 +706,26 @@ def _set_speed(L, env, speed):
     L.ce_env_set_command(env.buf, speed, 0.0, ph)
 
 
+def test_command_attributes_of_the_batched_env():
+    """env.speed / side_speed / orient_add / phase_add / phase / phaselen (the attributes the reference's tools assign,
+    SURVEY §8 b2) are views of the state record: checked on a host-memory record (the record layout comes from the library,
+    no kernel runs)."""
+    import torch
+    from apex_b200 import _capi
+    from apex_b200.envs import BatchedCassieEnv
+    L = _capi.lib()
+    env = object.__new__(BatchedCassieEnv)
+    env.st = torch.zeros((3, L.apex_cassie_state_words()), dtype=torch.float32)
+    env.sti = torch.zeros((3, L.apex_cassie_istate_words()), dtype=torch.int32)
+    env.speed = 0.5
+    env.orient_add = torch.tensor([0.1, 0.2, 0.3])
+    env.orient_add += 1.0
+    env.phase_add = 1.5
+    assert env.speed.tolist() == [0.5] * 3 and torch.allclose(env.orient_add, torch.tensor([1.1, 1.2, 1.3]))
+    assert env.st[:, _capi.layout("speed")].tolist() == [0.5] * 3 and env.st[1, _capi.layout("phase_add")] == 1.5
+    assert float(env.st.sum()) == pytest.approx(1.5 + 3.6 + 4.5)  # nothing else was touched
+
+
 def test_env_factory_mirrors_the_reference_signature():
     """util/env.py:8: same positional / keyword arguments; returns a constructor, builds nothing (no GPU needed)."""
     from functools import partial
