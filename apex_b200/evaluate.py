@@ -15,6 +15,8 @@ Reference (file:line in /root/reference):
 The env contract is the batched one (apex_b200.envs.BatchedCassieEnv): reset_for_test(active=), step(action, active=),
 field(name, width), apply_force(xfrc), sim_time(), num_envs, device, dtype.  `policy` is any callable mapping the observation
 tensor [N, D] on env.device to actions [N, 10]; KernelPolicy runs a Gaussian_FF_Actor through the library's own MLP kernels.
+The tools take the env over: they set max_traj_len = 0 (no in-kernel episode resets; a fallen trial is masked out instead) and
+the hold_commands field, and leave both that way — use an env built for evaluation, not the training one.
 Trials are independent, so results do not depend on how they are batched; like the reference's, they are stochastic through
 the env's own random command changes (cassie/cassie.py:483-491).
 """
