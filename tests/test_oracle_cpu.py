@@ -653,6 +653,39 @@ def test_trajectory_loader_reads_the_reference_file():
     assert n == tlen == 1682 and rows.shape == (34, 67) and np.array_equal(rows, table)
 
 
+@pytest.mark.skipif(not os.path.exists("/root/reference/cassie/trajectory/stepdata.bin"), reason="reference tree not mounted")
+def test_recorded_trajectory_one_step_prediction(L):
+    """Weak pin of the restated physics against a recording of the real simulator: the 2 kHz log
+    cassie/trajectory/stepdata.bin (float32 precision; its floor is the plane z = 0, cassie.xml's is z = -0.01, so the pelvis is
+    lowered by 1 cm; the recorded motor torques are applied as they stand, the log's delay-line alignment is unknown).  From
+    each recorded (qpos, qvel) the oracle's one-step velocity must land near the next recorded velocity: pelvis translation to
+    2e-4 m/s rms (a fifth of the rms change per step), pelvis rotation better than "no change", both feet in contact throughout."""
+    data = np.fromfile("/root/reference/cassie/trajectory/stepdata.bin", dtype=np.double).reshape(-1, 98)
+    qpos, qvel, tau = data[:, 1:36].copy(), data[:, 36:68], data[:, 68:78]
+    qpos[:, 2] -= 0.01
+    m, d = _fresh(L)
+    gear = np.array([25, 25, 16, 16, 50] * 2, float)
+    res, chg, ncon = [], [], []
+    for t in range(20, 1600, 5):
+        ws = (qvel[t] - qvel[t - 1]) / 0.0005
+        for i in range(35):
+            d.qpos[i] = qpos[t, i]
+        for i in range(32):
+            d.qvel[i], d.qacc_warmstart[i] = qvel[t, i], ws[i]
+        for i in range(10):
+            d.ctrl[i] = tau[t, i] / gear[i]
+        L.cp_step(C.byref(m), C.byref(d))
+        res.append(np.array(d.qvel[:]) - qvel[t + 1])
+        chg.append(qvel[t + 1] - qvel[t])
+        ncon.append(d.ncon)
+    res, chg = np.array(res), np.array(chg)
+    rms = lambda a: float(np.sqrt((a ** 2).mean()))
+    assert min(ncon) >= 1 and np.mean(ncon) > 1.5
+    assert rms(res[:, :3]) < 2e-4 and rms(res[:, :3]) < 0.25 * rms(chg[:, :3]), (rms(res[:, :3]), rms(chg[:, :3]))
+    assert rms(res[:, 3:6]) < 0.5 * rms(chg[:, 3:6]), (rms(res[:, 3:6]), rms(chg[:, 3:6]))
+    assert rms(res[:, [8, 21]]) < 0.3 * rms(chg[:, [8, 21]])  # hip pitch, the dofs that carry the gait
+
+
 def _ref_policy():
     g = np.load(os.path.join(G, "ref_policy_5k_retrain.npz"))
     W = [g["actor_layers.0.weight"], g["actor_layers.1.weight"], g["means.weight"]]
