@@ -317,22 +317,3 @@ def test_ppo_iteration_with_bf16_tensor_core_forward():
         res[prec] = (float(buf.rew.mean()), float(buf.val.abs().mean()), scal)
     assert abs(res["bf16"][0] - res["f32"][0]) < 0.05 * abs(res["f32"][0]) + 1e-3  # same rollout up to bf16 action noise
 
-
-def test_column_moments_merge_like_the_reference_known_answer_test():
-    """The reference's only assert-based test, rl/envs/normalize.py:208-225 (test_runningmeanstd): statistics accumulated over
-    chunks of 3, 4 and 5 rows (1 and 2 columns) equal mean / variance of the concatenation.  Here the accumulator is
-    apex_col_moments (sum and sum of squares per column in float64, what get_normalization_params and its all-reduce use)."""
-    from apex_b200 import _capi
-    L = _capi.lib()
-    g = torch.Generator().manual_seed(0)
-    for dim in (1, 2):
-        chunks = [torch.randn((n, dim), generator=g) for n in (3, 4, 5)]
-        mom = torch.zeros(2 * dim, dtype=torch.float64, device="cuda:0")
-        for c in chunks:
-            x = c.cuda().contiguous()
-            _capi.check(L.apex_col_moments(x.data_ptr(), x.shape[0], dim, mom.data_ptr(), None), "col_moments")
-        torch.cuda.synchronize()
-        x = torch.cat(chunks).double()
-        mean = mom[:dim].cpu() / x.shape[0]
-        var = mom[dim:].cpu() / x.shape[0] - mean * mean
-        assert torch.allclose(mean, x.mean(0), atol=1e-12) and torch.allclose(var, x.var(0, unbiased=False), atol=1e-12)
