@@ -75,23 +75,3 @@ def test_replay_buffer_ring_and_gather():
     row = rb.storage[idx]
     assert torch.equal(st, row[:, :4]) and torch.equal(nx, row[:, 4:8]) and torch.equal(sa, torch.cat([row[:, :4], row[:, 8:10]], 1))
     assert torch.equal(r, row[:, 10]) and torch.equal(nd, 1 - row[:, 11])
-
-
-def test_column_moments_merge_like_the_reference_known_answer_test():
-    """The reference's only assert-based test, rl/envs/normalize.py:208-225 (test_runningmeanstd): statistics accumulated over
-    chunks of 3, 4 and 5 rows (1 and 2 columns) equal mean / variance of the concatenation.  Here the accumulator is
-    apex_col_moments (sum and sum of squares per column in float64, what get_normalization_params and its all-reduce use)."""
-    from apex_b200 import _capi
-    L = _capi.lib()
-    g = torch.Generator().manual_seed(0)
-    for dim in (1, 2):
-        chunks = [torch.randn((n, dim), generator=g) for n in (3, 4, 5)]
-        mom = torch.zeros(2 * dim, dtype=torch.float64, device="cuda:0")
-        for c in chunks:
-            x = c.cuda().contiguous()
-            _capi.check(L.apex_col_moments(x.data_ptr(), x.shape[0], dim, mom.data_ptr(), None), "col_moments")
-        torch.cuda.synchronize()
-        x = torch.cat(chunks).double()
-        mean = mom[:dim].cpu() / x.shape[0]
-        var = mom[dim:].cpu() / x.shape[0] - mean * mean
-        assert torch.allclose(mean, x.mean(0), atol=1e-12) and torch.allclose(var, x.var(0, unbiased=False), atol=1e-12)
