@@ -467,6 +467,9 @@ template <typename T> CW_NOINL void cw_env_step(CassieWs<T> &w, T *obs_out, T *r
     for (int k = 0; k < 3; k++) { lfv[k] = (fp1[k] - fp0[k]) / (T)0.0005; rfv[k] = (fp1[3 + k] - fp0[3 + k]) / (T)0.0005; }
     cw_foot_forces<T>(w, &lz, &rz);
     cost += w.solver_iter * w.nefc;
+#ifdef CW_HOST_STATS /* tests/emu only: per-sub-step solver statistics for tools/solver_stats.py */
+    cw_host_stats(w.solver_iter, w.nefc, w.ncon);
+#endif
     int fl = w.sti[I_FLAGS], sc = w.sti[I_STEPCOUNT];
     { /* the reference tests the LEFT force for both feet (cassie.py:338,348) */
       int lh = fl & 1, rh = (fl >> 1) & 1, ls = (fl >> 2) & 1, rs = (fl >> 3) & 1;

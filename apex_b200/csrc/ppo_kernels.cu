@@ -422,11 +422,13 @@ __global__ void k_gaussian_sample(const float *__restrict__ mu, const float *__r
     sincosf(6.283185307179586f * u2, &sn, &cs);
     const float e[2] = {rad * cs, rad * sn};
     for (int k = 0; k < 2 && j + k < adim; k++) {
-      const float sd = sigma[j + k] * anneal, m = mu[(long)r * adim + j + k];
+      /* the action is drawn with sd * anneal (actor.py:196-200) but pi_old's log-probability is old_policy.distribution(),
+       * i.e. the un-annealed fixed_std (ppo.py:296-300, actor.py:211-213): the stored value must match what k_ppo_loss evaluates */
+      const float sd0 = sigma[j + k], sd = sd0 * anneal, m = mu[(long)r * adim + j + k];
       const float a = m + sd * e[k];
       act[(long)r * adim + j + k] = a;
-      const float z = (a - m) / sd;
-      lp += -0.5f * z * z - logf(sd) - 0.9189385332046727f;
+      const float z = (a - m) / sd0;
+      lp += -0.5f * z * z - logf(sd0) - 0.9189385332046727f;
     }
   }
   logp[r] = lp;

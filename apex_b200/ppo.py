@@ -83,7 +83,11 @@ class PPO:
     def __init__(self, args, save_path=None):
         self.env_name = args.get("env_name", "Cassie-v0")
         self.gamma = args.get("gamma", 0.99)
-        self.lam = args.get("lam", 1.0)  # the reference parses --lam but its returns are lam = 1 (ppo.py:73-89)
+        # The reference parses --lam (default 0.95) and never uses it: its returns are gamma-discounted Monte-Carlo sums with a
+        # bootstrap, i.e. lam = 1 (ppo.py:73-89).  Passing the reference's args dict must therefore not change the returns:
+        # `lam` is honoured only together with an explicit use_gae=True (not a reference flag).
+        self.use_gae = bool(args.get("use_gae", False))
+        self.lam = float(args.get("lam", 1.0)) if self.use_gae else 1.0
         self.lr = args.get("lr", 1e-4)
         self.eps = args.get("eps", 1e-5)
         self.entropy_coeff = args.get("entropy_coeff", 0.0)
@@ -112,6 +116,7 @@ class PPO:
         self.buf = None
         self._opt_step = [0, 0]
         self._sample_calls = 0
+        self._stats_reduced = True
         self.launches = 0  # kernels of ours launched (bench.py reports it)
 
     # ------------------------------------------------------------------ setup
@@ -207,6 +212,9 @@ class PPO:
         env, N = self.env, self.env.num_envs
         env.max_traj_len = int(max_traj_len)
         T = max(1, math.ceil(min_steps / N))
+        if T > 512:  # apex_gae_scan composes the horizon in one 512-step scan per env
+            raise ValueError(f"num_steps={min_steps} over {N} envs is a horizon of {T} > 512 steps per env: use more envs "
+                             f"(>= {math.ceil(min_steps / 512)}) or fewer steps per iteration")
         if self.buf is None or self.buf.T != T:
             self.buf = RolloutBuffer(T, N, self.obs_dim, self.act_dim, self.device)
         buf = self.buf
@@ -282,6 +290,7 @@ class PPO:
         self._mlp_fwd(cp, self.mb_raw, B, 1, self.mb_g1, self.mb_g2, self.mb_v)
         self.launches += 2  # prepare_obs, ppo_loss
         self.stats.zero_()
+        self._stats_reduced = False
         self.grad.zero_()
         self.sumsq.zero_()
         _capi.check(L.apex_ppo_loss(B, self.act_dim, _p(self.mb_mu), _p(self.mb_mu[B:]) if mirror else None, _p(idx),
@@ -309,7 +318,12 @@ class PPO:
         self.launches += 6
 
     def minibatch_scalars(self):
-        """(actor_loss, entropy, critic_loss, ratio, kl, mirror_loss) of the last minibatch — one device->host read."""
+        """(actor_loss, entropy, critic_loss, ratio, kl, mirror_loss) of the last minibatch — one device->host read.
+        With world_size > 1 the sums are all-reduced first (once per minibatch at most), so every rank reads the same global
+        scalars: the KL early stop of optimize() must be the same decision on all ranks or their collectives go out of step."""
+        if self.world > 1 and not self._stats_reduced:
+            dist.all_reduce(self.stats)
+            self._stats_reduced = True
         st = self.stats.tolist()
         cnt = max(st[5], 1.0)
         ent = float((0.5 + 0.5 * math.log(2 * math.pi) + torch.log(self.sigma)).mean())

@@ -136,14 +136,16 @@ class TD3:
 
     @torch.no_grad()
     def train(self, replay_buffer, iterations, batch_size=100, discount=0.99, tau=0.005, policy_noise=0.2, noise_clip=0.5,
-              policy_freq=2, indices=None, noises=None, generator=None, reference_action_alias=True):
+              policy_freq=2, indices=None, noises=None, generator=None, reference_action_alias=False):
         """sync_td3.py:133-209.  `indices` / `noises` (lists of tensors) override the sampled rows / smoothing noise
         (parity tests feed the reference's own draws).
 
         reference_action_alias: the reference builds `action` and `noise` with torch.FloatTensor(u) (sync_td3.py:142,149);
         the legacy constructor ALIASES the numpy array u, so noise.normal_() overwrites the sampled actions in place and
-        the critics are evaluated at Q(s, raw noise), not Q(s, a).  True (default) reproduces that result exactly
-        (tests/golden/td3_update.npz is the reference's own output); False trains on the stored actions."""
+        the critics are evaluated at Q(s, raw noise), not Q(s, a) — but ONLY when u is already float32.  The reference's
+        own collection path stores `action + np.random.normal(0, act_noise)` (sync_td3.py:77), a float64 array, which
+        torch.FloatTensor copies: real training evaluates Q(s, a).  False (default) is therefore the reference's actual
+        behaviour; True reproduces the aliasing case (tests/golden/td3_update.npz was recorded with float32 actions)."""
         L, s, S, A, B = self.L, self._s(), self.S, self.A, batch_size
         self._ensure(B)
         a, at = self._ptrs(0, self.A_NAMES), self._ptrs(2, self.A_NAMES)

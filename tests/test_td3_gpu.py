@@ -9,7 +9,7 @@ pytestmark = pytest.mark.gpu
 G = os.path.join(os.path.dirname(__file__), "golden")
 
 
-def _run_td3(g, iters):
+def _run_td3(g, iters, alias=True):
     from apex_b200.td3 import TD3, ReplayBuffer
     S, A, B = 50, 10, 64
     algo = TD3(S, A, 1.0, 1e-3, 1e-3)
@@ -21,7 +21,7 @@ def _run_td3(g, iters):
     inds = [torch.as_tensor(i, dtype=torch.int64, device="cuda:0") for i in g["inds"]]
     noises = [torch.as_tensor(n, dtype=torch.float32, device="cuda:0").contiguous() for n in g["noises"]]
     q1, q2, q_loss = algo.train(rb, iters, batch_size=B, discount=0.99, tau=0.005, policy_noise=0.2, noise_clip=0.5, policy_freq=2,
-                                indices=inds, noises=noises)
+                                indices=inds, noises=noises, reference_action_alias=alias)
     return algo, q_loss
 
 
