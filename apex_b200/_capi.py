@@ -3,7 +3,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "libapex_b200.so")
+# APEX_B200_LIB: developer override used by tools/build_variant.sh to A/B kernel builds on the GPU box
+_LIB_PATH = os.environ.get("APEX_B200_LIB") or os.path.join(_HERE, "libapex_b200.so")
 _lib = None
 
 

@@ -135,7 +135,7 @@ struct CassieWs {
     CassieWsPre<T> p;
   } u;
   T Ap[CW_NEFC * (CW_NEFC + 1) / 2]; /* A = J M^-1 J^T + R, packed lower triangle: A(i, j), i >= j, at i (i + 1) / 2 + j */
-  T efc_R[CW_NEFC], efc_aref[CW_NEFC]; /* row construction parks diagApprox in efc_R and the violation in efc_aref */
+  alignas(16) T efc_R[CW_NEFC], efc_aref[CW_NEFC]; /* row construction parks diagApprox in efc_R and the violation in efc_aref */
   T efc_b[CW_NEFC], efc_f[CW_NEFC], efc_dinv[CW_NEFC];
 #ifndef __CUDACC__
   T efc_res[CW_NEFC]; /* host test build only: on the GPU the PGS residual lives in registers */
@@ -163,6 +163,10 @@ CW_FN double cw_tan_o(double x) { return tan(x); }
 CW_FN float cw_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 CW_FN double cw_rcp(double x) { return 1.0 / x; }
 CW_FN int cw_ctz(unsigned m) { return __ffs((int)m) - 1; }
+CW_FN float cw_mul_rn(float a, float b) { return __fmul_rn(a, b); } /* never contracted into a neighbouring add */
+CW_FN double cw_mul_rn(double a, double b) { return __dmul_rn(a, b); }
+CW_FN float cw_fma_rn(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+CW_FN double cw_fma_rn(double a, double b, double c) { return __fma_rn(a, b, c); }
 #else
 CW_FN int cw_ctz(unsigned m) { return __builtin_ctz(m); }
 CW_FN float cw_rcp(float x) { return 1.0f / x; }
@@ -1119,35 +1123,81 @@ template <typename T> CW_NOINL void cw_mj_step(CassieWs<T> &w, bool integrate, i
       for (int o = 16; o > 0; o >>= 1) cost += __shfl_xor_sync(0xffffffffu, cost, o);
       T res0 = sacc + b0;
       if (cost > 0) { f0 = 0; res0 = b0; }
-      /* The row update in increment form: new f = max(f - res / A_ii, lb)  <=>  df = max(-res / A_ii, lb - f).  With
-       * ndi0 = -1 / A_ii and g0 = lb - f (a constant -3e38 for the unbounded equality rows, -f for the rows with f >= 0) a row
-       * step is one multiply and one max before the broadcast. */
+      /* Blocked Gauss-Seidel, same update sequence as mj_solPGS.  The row update in increment form:
+       * new f = max(f - res / A_ii, lb)  <=>  df = max(s, g) with s = res * (-1 / A_ii) and g = lb - f (-3e38 for the unbounded
+       * equality rows, -f for the rows with f >= 0).  Every lane keeps its residual pre-scaled (s) and its column of A scaled
+       * by its own -1 / A_ii.  Rows are taken four at a time: ONE round of shuffles gathers the four s, every lane then runs the
+       * four dependent row steps in its own registers (the 4 x 4 diagonal block of A, pre-scaled like the columns, and the rows'
+       * g are read from shared memory with uniform 16-byte loads) and finally applies the four increments to its own s.
+       * The dependent chain per row is one FMA and one MAX instead of a shuffle round trip.  The connect rows (0 .. 11: whenever
+       * there are rows at all, cw_make_constraint seats the 12 equality rows first) are unbounded: their MAX is a no-op. */
       const T ndi0 = -di0;
       const bool bounded = lb0 == (T)0;
       T g0 = bounded ? -f0 : lb0;
-      for (int it = 0; it < CM_ITERATIONS; it++) {
-        /* every lane evaluates its candidate at every row step; the residual it saw at its OWN step is captured by one
-         * select, and the row's new force / cost improvement are recomputed from it once per sweep */
-        T res_own = 0;
-#pragma unroll
-        for (int i0 = 0; i0 < CW_NEFC; i0 += 2) {
-          if (i0 >= n) break; /* tested once per 2 rows: a row >= n has di0 = 0 and a zero column, so its update is exactly 0 */
-#pragma unroll
-          for (int i = i0; i < i0 + 2; i++) {
-            const T dl = __shfl_sync(0xffffffffu, cw_max(res0 * ndi0, g0), i);
-            const bool own = lane == i;
-            res_own = own ? res0 : res_own;
-            res0 += dl * acol[i];
-          }
-        }
-        const T dlo = cw_max(res_own * ndi0, g0); /* same expression, same operands as at the own step */
-        T imp = -dlo * (dlo * had0 + res_own);
-        f0 += dlo;
-        if (bounded) { f0 = cw_max(f0, (T)0); g0 = -f0; }
-        for (int o = 16; o > 0; o >>= 1) imp += __shfl_xor_sync(0xffffffffu, imp, o);
-        iters = it + 1;
-        if (imp * scale < (T)1e-8) break;
+      const T aii0 = v0 ? w.Ap[rowbase + lane] : (T)0;
+      T (*pblk)[16] = reinterpret_cast<T (*)[16]>(w.efc_R); /* efc_R, efc_aref, efc_b, efc_f: consumed above, 128 words */
+      __syncwarp();
+      {
+        const int kb = lane >> 2, jb = lane & 3;
+        pblk[kb][8 + jb] = v0 ? g0 : (T)0;
+        /* c(j, j') = A(4 kb + j, 4 kb + j') * ndi(j'), j < j': written by the lane of the later row j' (it knows its own ndi) */
+        const T *arow = w.Ap + rowbase + 4 * kb; /* A(lane, 4 kb + j), j < jb: inside the lower triangle */
+        if (jb == 1) pblk[kb][0] = v0 ? arow[0] * ndi0 : (T)0;
+        if (jb == 2) { pblk[kb][1] = v0 ? arow[0] * ndi0 : (T)0; pblk[kb][3] = v0 ? arow[1] * ndi0 : (T)0; }
+        if (jb == 3) { pblk[kb][2] = v0 ? arow[0] * ndi0 : (T)0; pblk[kb][4] = v0 ? arow[1] * ndi0 : (T)0; pblk[kb][5] = v0 ? arow[2] * ndi0 : (T)0; }
       }
+      T sres = res0 * ndi0;
+#pragma unroll
+      for (int i = 0; i < CW_NEFC; i++) acol[i] *= ndi0;
+      __syncwarp();
+      const int myblk = lane >> 2;
+      const bool j1 = (lane & 3) == 1, j2 = (lane & 3) == 2, j3 = (lane & 3) == 3;
+      for (int it = 0; it < CM_ITERATIONS; it++) {
+        T s_own = 0;
+#pragma unroll
+        for (int k = 0; k < CW_NEFC / 4; k++) {
+          if (4 * k >= n) break;
+          const T r0 = __shfl_sync(0xffffffffu, sres, 4 * k), r1 = __shfl_sync(0xffffffffu, sres, 4 * k + 1);
+          const T r2 = __shfl_sync(0xffffffffu, sres, 4 * k + 2), r3 = __shfl_sync(0xffffffffu, sres, 4 * k + 3);
+          const T *pb = pblk[k];
+          T s1 = r1, s2 = r2, s3 = r3, d0, d1, d2, d3;
+          if (k < 3) { /* equality rows: df = s */
+            d0 = r0;
+            s1 = cw_fma_rn(d0, pb[0], s1); s2 = cw_fma_rn(d0, pb[1], s2); s3 = cw_fma_rn(d0, pb[2], s3);
+            d1 = s1;
+            s2 = cw_fma_rn(d1, pb[3], s2); s3 = cw_fma_rn(d1, pb[4], s3);
+            d2 = s2;
+            s3 = cw_fma_rn(d2, pb[5], s3);
+            d3 = s3;
+          } else {
+            d0 = cw_max(r0, pb[8]);
+            s1 = cw_fma_rn(d0, pb[0], s1); s2 = cw_fma_rn(d0, pb[1], s2); s3 = cw_fma_rn(d0, pb[2], s3);
+            d1 = cw_max(s1, pb[9]);
+            s2 = cw_fma_rn(d1, pb[3], s2); s3 = cw_fma_rn(d1, pb[4], s3);
+            d2 = cw_max(s2, pb[10]);
+            s3 = cw_fma_rn(d2, pb[5], s3);
+            d3 = cw_max(s3, pb[11]);
+          }
+          sres = cw_fma_rn(d0, acol[4 * k], sres);
+          sres = cw_fma_rn(d1, acol[4 * k + 1], sres);
+          sres = cw_fma_rn(d2, acol[4 * k + 2], sres);
+          sres = cw_fma_rn(d3, acol[4 * k + 3], sres);
+          T ss = j1 ? s1 : r0;
+          ss = j2 ? s2 : ss;
+          ss = j3 ? s3 : ss;
+          s_own = myblk == k ? ss : s_own;
+        }
+        /* the lane's own row: same expression, same operands as at its step inside the block */
+        const T dlo = cw_max(s_own, g0);
+        T imp = dlo * aii0 * (s_own - (T)0.5 * dlo); /* = -dl (0.5 A_ii dl + res) with res = -s A_ii */
+        f0 += dlo;
+        if (bounded) { f0 = cw_max(f0, (T)0); g0 = -f0; pblk[myblk][8 + (lane & 3)] = g0; }
+        iters = it + 1;
+        for (int o = 16; o > 0; o >>= 1) imp += __shfl_xor_sync(0xffffffffu, imp, o);
+        if (imp * scale < (T)1e-8) break;
+        __syncwarp();
+      }
+      __syncwarp();
       if (v0) w.efc_f[lane] = f0;
       __syncwarp();
     }
