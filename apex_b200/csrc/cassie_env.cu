@@ -57,15 +57,29 @@ __global__ void __launch_bounds__(sizeof(T) == 4 ? 480 : 224) k_env_step(T *st, 
   const int slot = blockIdx.x * wpb + warp;
   /* order (optional): slot -> env, envs of similar solver cost share a CTA (and its per-sub-step barrier), dearest first */
   const int e = slot < n ? (order ? order[slot] : slot) : n;
+  /* the CTA's mbarrier (split barrier, CW_SPLIT) sits behind the workspaces: one arrival per warp and phase */
+  const unsigned bar_addr = (unsigned)__cvta_generic_to_shared(smem + (size_t)wpb * sizeof(CassieWs<T>));
+  if (bar_mask & CW_SPLIT) {
+    if (threadIdx.x == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_addr), "r"(wpb) : "memory");
+    __syncthreads();
+  }
   if (e >= n || (active && !active[e])) { /* idle slot: keep the CTA barriers company, touch nothing */
     if (e < n && lane == 0) { reward[e] = 0; done[e] = 4; }
-    const int nbar = CW_SIMRATE * (1 + __popc(bar_mask & CW_BAR_ALL));
-    for (int s = 0; s < nbar; s++) __syncthreads();
+    if (bar_mask & CW_SPLIT) {
+      for (int s = 0; s < CW_SIMRATE; s++) {
+        if (s > 0) cw_mbar_wait(bar_addr, (unsigned)((s - 1) & 1));
+        __syncwarp();
+        cw_mbar_arrive(bar_addr, lane);
+      }
+    } else {
+      const int nbar = CW_SIMRATE * (1 + __popc(bar_mask & CW_BAR_ALL));
+      for (int s = 0; s < nbar; s++) __syncthreads();
+    }
     return;
   }
   ws_load(w, st + (size_t)e * S_WORDS, sti + (size_t)e * I_WORDS, lane);
   if (lane < CW_ACT) w.action[lane] = action[(size_t)e * CW_ACT + lane];
-  if (lane == 0) w.bar_mask = bar_mask;
+  if (lane == 0) { w.bar_mask = bar_mask; w.bar_addr = bar_addr; }
   __syncwarp();
   T rew; int dn;
   T *o = obs + (size_t)e * CW_OBS;
@@ -131,7 +145,7 @@ extern "C" {
 int apex_cassie_warps_per_cta = 14;
 void apex_cassie_set_warps_per_cta(int w) { apex_cassie_warps_per_cta = w; }
 int apex_cassie_bar_mask = 0;
-void apex_cassie_set_barrier_mask(int m) { apex_cassie_bar_mask = m & CW_BAR_ALL; }
+void apex_cassie_set_barrier_mask(int m) { apex_cassie_bar_mask = m & CW_BAR_MASK; }
 
 int apex_cassie_state_words(void) { return S_WORDS; }
 int apex_cassie_istate_words(void) { return I_WORDS; }
@@ -198,11 +212,11 @@ static int env_step_impl(int dtype, void *st, int *sti, int n, const void *actio
   const CassieTraj<float> tf = {(const float *)traj, traj_rows, traj_len};
   const CassieTraj<double> td = {(const double *)traj, traj_rows, traj_len};
   DISPATCH(
-      if ((rc = prep(k_env_step<float>, wpb * sizeof(CassieWs<float>)))) return rc;
-      (k_env_step<float><<<(n + wpb - 1) / wpb, 32 * wpb, wpb * sizeof(CassieWs<float>), s>>>((float *)st, sti, n, (const float *)action, (float *)obs,
+      if ((rc = prep(k_env_step<float>, wpb * sizeof(CassieWs<float>) + 16))) return rc;
+      (k_env_step<float><<<(n + wpb - 1) / wpb, 32 * wpb, wpb * sizeof(CassieWs<float>) + 16, s>>>((float *)st, sti, n, (const float *)action, (float *)obs,
                                                                 (float *)reward, done, (float *)term_obs, max_traj_len, active, tf, order, apex_cassie_bar_mask)),
-      if ((rc = prep(k_env_step<double>, wpb * sizeof(CassieWs<double>)))) return rc;
-      (k_env_step<double><<<(n + wpb - 1) / wpb, 32 * wpb, wpb * sizeof(CassieWs<double>), s>>>((double *)st, sti, n, (const double *)action, (double *)obs,
+      if ((rc = prep(k_env_step<double>, wpb * sizeof(CassieWs<double>) + 16))) return rc;
+      (k_env_step<double><<<(n + wpb - 1) / wpb, 32 * wpb, wpb * sizeof(CassieWs<double>) + 16, s>>>((double *)st, sti, n, (const double *)action, (double *)obs,
                                                                   (double *)reward, done, (double *)term_obs, max_traj_len, active, td, order, apex_cassie_bar_mask)))
 }
 

@@ -24,6 +24,7 @@
 #ifndef CASSIE_WARP_H
 #define CASSIE_WARP_H
 #include <stdint.h>
+#include <stddef.h>
 #include <math.h>
 
 #ifdef __CUDACC__
@@ -56,6 +57,19 @@ template <> struct CmSel<float> { template <class D, class F> CW_MEMBER_FN const
 #define CMT(name) (CmSel<T>::get(CM_##name, CM_##name##_f32))
 
 #ifdef __CUDACC__
+__device__ __forceinline__ void cw_mbar_arrive(unsigned addr, int lane) {
+  if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ void cw_mbar_wait(unsigned addr, unsigned parity) {
+  asm volatile("{\n.reg .pred p;\nCW_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra CW_DONE;\nbra CW_WAIT;\nCW_DONE:\n}" ::"r"(addr), "r"(parity) : "memory");
+}
+#define CW_SPLIT_WAIT_AT(point) do { if ((flags & (CW_SPLIT | CW_SPLIT_WAIT)) == (CW_SPLIT | CW_SPLIT_WAIT) && CW_SPLIT_POINT(flags) == (point)) { __syncwarp(); cw_mbar_wait(w.bar_addr, (flags & CW_SPLIT_PARITY) ? 1u : 0u); } } while (0)
+#define CW_SPLIT_ARRIVE() do { if (flags & CW_SPLIT) { __syncwarp(); cw_mbar_arrive(w.bar_addr, lane); } } while (0)
+#else
+#define CW_SPLIT_WAIT_AT(point) ((void)0)
+#define CW_SPLIT_ARRIVE() ((void)0)
+#endif
+#ifdef __CUDACC__
 #define CW_LANE_PARAM , const int lane
 #define CW_LANE_ARG , lane
 #else
@@ -69,6 +83,16 @@ template <> struct CmSel<float> { template <class D, class F> CW_MEMBER_FN const
 #define CW_BAR_POST 0x400
 #define CW_BAR_EULER 0x800
 #define CW_BAR_ALL 0xF00
+/* Split barrier (step kernel only).  A warp ARRIVES when its solver is done (the only part of a sub-step whose length differs
+ * between envs) and WAITS for everybody's arrival of the previous sub-step at a later point of its own next sub-step, selected
+ * by CW_SPLIT_POINT: 0 top of the sub-step, 1 after the kinematics, 2 after the bias forces, 3 after the factorisation.  The
+ * warps of a CTA then stay within one sub-step of each other (they share the instruction cache), but a warp whose solver was
+ * quick this time works ahead through the common tail instead of idling, and the slack averages over the sub-steps. */
+#define CW_SPLIT 0x1000
+#define CW_SPLIT_POINT(f) (((f) >> 13) & 3)
+#define CW_SPLIT_WAIT 0x8000   /* this sub-step has a predecessor to wait for */
+#define CW_SPLIT_PARITY 0x10000 /* parity of the phase to wait for */
+#define CW_BAR_MASK 0x7F00     /* what apex_cassie_set_barrier_mask may set */
 #define CW_NB CM_NBODY
 #define CW_NV CM_NV
 #define CW_NEFC 32 /* constraint-row capacity (njmax analogue): 12 equality + limits + contacts */
@@ -124,12 +148,14 @@ struct CassieWs {
   T xpos[CW_NB][3], xmat[CW_NB][9];
   T qkeep[3][4]; /* world quaternions of the pelvis (imu site), left foot, right foot */
   T cdof[CW_NV][6];
-  T Ms[CM_MNNZ + 5]; /* tree-sparse strict lower triangle: entry (k, t-th ancestor of k) at CM_dof_rowptr[k] + t; holds the
+  alignas(16) T Ms[CM_MNNZ + 8]; /* tree-sparse strict lower triangle: entry (k, t-th ancestor of k) at CM_dof_rowptr[k] + t; holds the
                       * mass matrix after cw_build_M and U = D_k L[k][.] (unscaled rows of M = L^T D L) after cw_factor */
   /* crb: spatial inertia per body, turned into the composite inertia by cw_crb; dead once M is built.  crb and Mdiag are
    * adjacent on purpose: cw_factor<T, 2> keeps the rows of the second factor (M + h B) in these 292 words (cw_Ms2) */
-  T crb[CW_NB][10];
-  T Mdiag[CW_NV], D[CW_NV], Dinv[CW_NV];
+  alignas(16) T crb[CW_NB][10];
+  T Mdiag[CW_NV];
+  T Ms2_tail[CM_MNNZ + 8 - CW_NB * 10 - CW_NV]; /* the second factor's rows run on from crb and Mdiag into here */
+  T D[CW_NV], Dinv[CW_NV];
   union U { /* the collision / RNE scratch is dead before the first Jacobian row is written */
     T J[CW_NEFC][CW_NV + 1]; /* constraint Jacobian, later B = J L^-1 */
     CassieWsPre<T> p;
@@ -143,7 +169,8 @@ struct CassieWs {
   int efc_type[CW_NEFC];
   T vec[V_NVEC][CW_NV];
   int ncon, nefc, solver_iter;
-  int bar_mask; /* extra CTA barriers inside a sub-step (CW_BAR_* bits), GPU build: keeps the CTA's warps on the same code */
+  int bar_mask; /* CTA synchronisation inside a sub-step (CW_BAR_* / CW_SPLIT bits), GPU build: keeps the CTA's warps on the same code */
+  unsigned bar_addr; /* shared-memory address of the CTA's mbarrier (split barrier) */
   T con_pos[CW_NCON][3], con_frame[CW_NCON][9], con_dist[CW_NCON], con_mu[CW_NCON];
   int con_geom[CW_NCON], con_geom1[CW_NCON], con_dim[CW_NCON], con_adr[CW_NCON];
   T y[Y_WORDS];
@@ -169,6 +196,7 @@ CW_FN float cw_fma_rn(float a, float b, float c) { return __fmaf_rn(a, b, c); }
 CW_FN double cw_fma_rn(double a, double b, double c) { return __fma_rn(a, b, c); }
 #else
 CW_FN int cw_ctz(unsigned m) { return __builtin_ctz(m); }
+
 CW_FN float cw_rcp(float x) { return 1.0f / x; }
 CW_FN double cw_rcp(double x) { return 1.0 / x; }
 #endif
@@ -436,8 +464,129 @@ template <typename T> CW_FN void cw_build_M(CassieWs<T> &w CW_LANE_PARAM) {
  *         pivots in w.D) in one pass: the two eliminations are independent, so interleaving them shares every index
  *         computation and phase barrier and gives each lane two FMA chains instead of one.  w.vec[V_TMP] is scratch. */
 template <typename T> CW_FN T *cw_Ms2(CassieWs<T> &w) { return &w.crb[0][0]; }
+/* Second half of cw_factor: Schur complement of both legs on the 6 base dofs, one (i, j <= i) entry per lane, then the base
+ * dofs' own elimination.  The leg rows (unscaled) are in M0 / M1, their inverse pivots in w.Dinv / D1; D0 / D1 hold the base
+ * dofs' running pivots. */
+template <typename T, int NF> CW_FN void cw_factor_base(CassieWs<T> &w, T *M0, T *M1, T *D0, T *D1 CW_LANE_PARAM) {
+  T *const Mp[2] = {M0, M1};
+  T *const Dp[2] = {D0, D1};
+  /* Schur complement of both legs on the 6 base dofs, one (i, j <= i) entry per lane */
+  CW_FOR_LANES {
+    if (lane < 21) {
+      int i = 0, rem = lane;
+      while (rem > i) { rem -= i + 1; i++; }
+      const int j = rem;
+      T acc[NF];
+      for (int f = 0; f < NF; f++) acc[f] = 0;
+#pragma unroll
+      for (int k = 6; k < CW_NV; k++) {
+        const int ok = CM_dof_rowptr[k];
+        acc[0] += Mp[0][ok + i] * Mp[0][ok + j] * w.Dinv[k];
+        if (NF == 2) acc[NF - 1] += Mp[NF - 1][ok + i] * Mp[NF - 1][ok + j] * Dp[NF - 1][k];
+      }
+      for (int f = 0; f < NF; f++) { if (i == j) Dp[f][i] -= acc[f]; else Mp[f][CM_dof_rowptr[i] + j] -= acc[f]; }
+    }
+  }
+  CW_SYNC();
+#pragma unroll
+  for (int k = 5; k >= 1; k--) {
+    T d[NF];
+    for (int f = 0; f < NF; f++) d[f] = cw_rcp(Dp[f][k]);
+    const int ok = CM_dof_rowptr[k];
+    CW_FOR_LANES {
+      if (lane == 0) w.Dinv[k] = d[0];
+      if (lane < k) {
+        const int ol = CM_dof_rowptr[lane];
+        for (int f = 0; f < NF; f++) {
+          const T a = Mp[f][ok + lane] * d[f];
+          for (int j = 0; j < lane; j++) Mp[f][ol + j] -= a * Mp[f][ok + j];
+          Dp[f][lane] -= a * Mp[f][ok + lane];
+        }
+      }
+    }
+    CW_SYNC();
+  }
+  {
+    const T d = cw_rcp(Dp[0][0]);
+    CW_FOR_LANES {
+      if (lane == 0) w.Dinv[0] = d;
+      if (NF == 2 && lane < 6) Dp[NF - 1][lane] = cw_rcp(Dp[NF - 1][lane]);
+    }
+    CW_SYNC();
+  }
+}
+
+#ifdef __CUDACC__
+/* 4 consecutive reals at a 4-word-aligned offset: one 16-byte (float) or two 16-byte (double) shared-memory accesses */
+__device__ __forceinline__ void cw_ld4(float *d, const float *s) { const float4 v = *reinterpret_cast<const float4 *>(s); d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w; }
+__device__ __forceinline__ void cw_st4(float *d, const float *s) { *reinterpret_cast<float4 *>(d) = make_float4(s[0], s[1], s[2], s[3]); }
+__device__ __forceinline__ void cw_ld4(double *d, const double *s) {
+  const double2 a = *reinterpret_cast<const double2 *>(s), b = *reinterpret_cast<const double2 *>(s + 2);
+  d[0] = a.x; d[1] = a.y; d[2] = b.x; d[3] = b.y;
+}
+__device__ __forceinline__ void cw_st4(double *d, const double *s) {
+  *reinterpret_cast<double2 *>(d) = make_double2(s[0], s[1]); *reinterpret_cast<double2 *>(d + 2) = make_double2(s[2], s[3]);
+}
+/* cw_factor<T, 2> on the device.  The 26 leg dofs keep their own rows of BOTH factors in registers through the 13 leg phases
+ * (lane = dof; row = 6 base entries + up to 12 leg ancestors).  A phase's two pivot rows (dof 6 + s and 19 + s) are written
+ * to shared memory once, when they are final — where the solves will look for them anyway — and every lane of that leg reads
+ * them back with 16-byte uniform loads; its multiplier is the pivot row's entry at the lane's own rank.  Against the
+ * shared-memory formulation (3 accesses per multiply-add) that is ~1/6 of the shared-memory instructions. */
+template <typename T> __device__ __noinline__ void cw_factor2_dev(CassieWs<T> &w, T hdamp, const int lane) {
+  T *const M0 = w.Ms, *const M1 = cw_Ms2(w);
+  T *const D0 = w.vec[V_TMP], *const D1 = w.D;
+  const bool leg = lane >= 6, rt = lane >= 19;
+  const int ll = lane - (rt ? 13 : 0); /* the left leg's dof with the same role (CM_leg_ancmask is indexed by it) */
+  const int rank = CM_dof_nanc[lane], own = CM_dof_rowptr[lane];
+  T r0[20], r1[20]; /* own row of the first / second factor; entries >= rank are scratch (kept finite) */
+  T d0 = w.Mdiag[lane], d1 = d0 + hdamp * w.st[S_DAMPING + lane];
+#pragma unroll
+  for (int v = 0; v < 5; v++) {
+    if (leg && 4 * v < rank) cw_ld4(r0 + 4 * v, M0 + own + 4 * v);
+#pragma unroll
+    for (int t = 4 * v; t < 4 * v + 4; t++) { r0[t] = (leg && t < rank) ? r0[t] : (T)0; r1[t] = r0[t]; }
+  }
+  const T base_copy = lane < 16 ? M0[lane] : (T)0; /* the base dofs' rows (15 words) of the second factor */
+  __syncwarp(); /* Mdiag and crb are dead from here on: the second factor's rows overwrite them */
+  if (lane < 16) M1[lane] = base_copy;
+  if (!leg) { D0[lane] = d0; D1[lane] = d1; }
+  T *const mine0 = M0 + own, *const mine1 = M1 + own;
+  const T *const legrow0 = M0 + (rt ? CM_LEG_ROWSPAN : 0), *const legrow1 = M1 + (rt ? CM_LEG_ROWSPAN : 0);
+#pragma unroll
+  for (int s = 12; s >= 0; s--) {
+    const unsigned legmask = CM_leg_ancmask[s];
+    const int len = 6 + __builtin_popcount(legmask), okL = CM_dof_rowptr[6 + s]; /* literals once the phase loop is unrolled */
+    if (ll == 6 + s) { /* this lane's dof is the pivot of its leg: its rows and pivots are final */
+#pragma unroll
+      for (int v = 0; 4 * v < len; v++) { cw_st4(mine0 + 4 * v, r0 + 4 * v); cw_st4(mine1 + 4 * v, r1 + 4 * v); }
+      w.Dinv[lane] = cw_rcp(d0);
+      D1[lane] = cw_rcp(d1);
+    }
+    const int src = (rt ? 19 : 6) + s;
+    const T di0 = cw_rcp(__shfl_sync(0xffffffffu, d0, src)), di1 = cw_rcp(__shfl_sync(0xffffffffu, d1, src));
+    __syncwarp();
+    T p0[20], p1[20];
+#pragma unroll
+    for (int v = 0; 4 * v < len; v++) { cw_ld4(p0 + 4 * v, legrow0 + okL + 4 * v); cw_ld4(p1 + 4 * v, legrow1 + okL + 4 * v); }
+    const bool part = leg && ((legmask >> ll) & 1u);
+    /* entry (pivot, this dof); a lane that is no ancestor of the pivot reads some unrelated word (possibly not even finite) */
+    const T e0 = part ? legrow0[okL + rank] : (T)0, e1 = part ? legrow1[okL + rank] : (T)0;
+    const T a0 = e0 * di0, a1 = e1 * di1;
+#pragma unroll
+    for (int t = 0; t < len; t++) { r0[t] -= a0 * p0[t]; r1[t] -= a1 * p1[t]; }
+    d0 -= a0 * e0; d1 -= a1 * e1;
+  }
+  __syncwarp();
+  cw_factor_base<T, 2>(w, M0, M1, D0, D1, lane);
+}
+#endif
 template <typename T, int NF> CW_NOINL void cw_factor(CassieWs<T> &w, T hdamp CW_LANE_PARAM) {
-  static_assert(sizeof(w.crb) + sizeof(w.Mdiag) >= sizeof(w.Ms), "second factor does not fit");
+#ifdef __CUDACC__
+  if (NF == 2) { cw_factor2_dev<T>(w, hdamp, lane); return; }
+#endif
+  static_assert(sizeof(w.crb) + sizeof(w.Mdiag) + sizeof(w.Ms2_tail) >= sizeof(w.Ms), "second factor does not fit");
+  static_assert(offsetof(CassieWs<T>, Mdiag) == offsetof(CassieWs<T>, crb) + sizeof(w.crb) &&
+                offsetof(CassieWs<T>, Ms2_tail) == offsetof(CassieWs<T>, Mdiag) + sizeof(w.Mdiag), "second factor's storage is not contiguous");
   T *const Mp[2] = {w.Ms, cw_Ms2(w)};
   T *const Dp[2] = {NF == 2 ? w.vec[V_TMP] : w.D, w.D}; /* running pivots */
   if (NF == 1) {
@@ -485,50 +634,7 @@ template <typename T, int NF> CW_NOINL void cw_factor(CassieWs<T> &w, T hdamp CW
     CW_FOR_LANES { if (lane >= 6) Dp[1][lane] = cw_rcp(Dp[1][lane]); }
     CW_SYNC();
   }
-  /* Schur complement of both legs on the 6 base dofs, one (i, j <= i) entry per lane */
-  CW_FOR_LANES {
-    if (lane < 21) {
-      int i = 0, rem = lane;
-      while (rem > i) { rem -= i + 1; i++; }
-      const int j = rem;
-      T acc[NF];
-      for (int f = 0; f < NF; f++) acc[f] = 0;
-#pragma unroll
-      for (int k = 6; k < CW_NV; k++) {
-        const int ok = CM_dof_rowptr[k];
-        acc[0] += Mp[0][ok + i] * Mp[0][ok + j] * w.Dinv[k];
-        if (NF == 2) acc[NF - 1] += Mp[NF - 1][ok + i] * Mp[NF - 1][ok + j] * Dp[NF - 1][k];
-      }
-      for (int f = 0; f < NF; f++) { if (i == j) Dp[f][i] -= acc[f]; else Mp[f][CM_dof_rowptr[i] + j] -= acc[f]; }
-    }
-  }
-  CW_SYNC();
-#pragma unroll
-  for (int k = 5; k >= 1; k--) {
-    T d[NF];
-    for (int f = 0; f < NF; f++) d[f] = cw_rcp(Dp[f][k]);
-    const int ok = CM_dof_rowptr[k];
-    CW_FOR_LANES {
-      if (lane == 0) w.Dinv[k] = d[0];
-      if (lane < k) {
-        const int ol = CM_dof_rowptr[lane];
-        for (int f = 0; f < NF; f++) {
-          const T a = Mp[f][ok + lane] * d[f];
-          for (int j = 0; j < lane; j++) Mp[f][ol + j] -= a * Mp[f][ok + j];
-          Dp[f][lane] -= a * Mp[f][ok + lane];
-        }
-      }
-    }
-    CW_SYNC();
-  }
-  {
-    const T d = cw_rcp(Dp[0][0]);
-    CW_FOR_LANES {
-      if (lane == 0) w.Dinv[0] = d;
-      if (NF == 2 && lane < 6) Dp[NF - 1][lane] = cw_rcp(Dp[NF - 1][lane]);
-    }
-    CW_SYNC();
-  }
+  cw_factor_base<T, NF>(w, Mp[0], Mp[1], Dp[0], Dp[1] CW_LANE_ARG);
 }
 
 /* v <- L^-T v (in place, shared vector); Ms / Dinv select the factor */
@@ -1003,11 +1109,14 @@ template <typename T> CW_NOINL void cw_mj_step(CassieWs<T> &w, bool integrate, i
   const T h = (T)CM_TIMESTEP;
   /* ---- step1 ---- */
   cw_kinematics<T>(w, qpos CW_LANE_ARG);
+  CW_SPLIT_WAIT_AT(1);
   cw_rne<T>(w, qvel CW_LANE_ARG); /* before cw_crb: it reads the per-body inertias */
+  CW_SPLIT_WAIT_AT(2);
   cw_crb<T>(w CW_LANE_ARG);
   cw_build_M<T>(w CW_LANE_ARG);
   if (integrate) cw_factor<T, 2>(w, h CW_LANE_ARG); /* M for the solves, M + h B for mj_Euler's implicit damping */
   else cw_factor<T, 1>(w, (T)0 CW_LANE_ARG);
+  CW_SPLIT_WAIT_AT(3);
   if (flags & CW_BAR_FACTOR) CW_BLOCK_SYNC();
   cw_collision<T>(w CW_LANE_ARG);
   cw_make_constraint<T>(w, qpos, flags CW_LANE_ARG);
@@ -1249,6 +1358,7 @@ template <typename T> CW_NOINL void cw_mj_step(CassieWs<T> &w, bool integrate, i
   }
   CW_SYNC();
   if (flags & CW_BAR_POST) CW_BLOCK_SYNC(); /* the solver's length varies per env: realign before the common tail */
+  CW_SPLIT_ARRIVE();
   /* qacc = qacc_smooth + L^-1 D^-1 g */
   CW_FOR_LANES { w.vec[V_QACC][lane] = w.vec[V_G][lane] * w.Dinv[lane]; }
   CW_SYNC();

@@ -335,10 +335,10 @@ def emit(m):
     o.append(f'#define CM_MAXANC {maxd}\n')
     o.append(arr1('CM_dof_nanc', [len(a) for a in anc], 'int'))
     o.append(arr2('CM_dof_anc', [a + [-1] * (maxd - len(a)) for a in anc], 'int'))
-    rp = [0]
-    for a in anc:
-        rp.append(rp[-1] + len(a))
+    rp = row_pointers(anc)
     o.append(f'#define CM_MNNZ {rp[-1]}\n')
+    o.append(f'#define CM_LEG_ROWSPAN {rp[19] - rp[6]} /* CM_dof_rowptr[19 + s] - CM_dof_rowptr[6 + s]: the two legs have the same row layout */\n')
+    assert all(rp[19 + s_] - rp[6 + s_] == rp[19] - rp[6] for s_ in range(13))
     o.append(arr1('CM_dof_rowptr', rp, 'int'))
     o.append(arr1('CM_dof_ancmask', [sum(1 << k for k in a) for a in anc], 'unsigned'))
     # last dof on the path to each body (bodies without dofs inherit their parent's)
@@ -365,6 +365,18 @@ def emit(m):
     return ''.join(o)
 
 
+def row_pointers(anc):
+    """Start of every dof's row in the tree-sparse storage (nv + 1 entries; the last one is the total size).  The six base
+    rows are packed; every leg row starts on a multiple of four words so that a row can be moved with 16-byte accesses."""
+    rp = [0]
+    for i, a in enumerate(anc):
+        end = rp[-1] + len(a)
+        if i + 1 >= 6:
+            end = (end + 3) // 4 * 4
+        rp.append(end)
+    return rp
+
+
 def emit_gen(m):
     """Straight-line code for the sparse L^T D L factorisation and the row half-solve (indices are compile-time)."""
     D = m.dofs
@@ -388,9 +400,7 @@ def emit_gen(m):
         masks.append(sum(1 << a for a in anc[kL] if a >= 6))
     o.append('CM_ARRAY unsigned CM_leg_ancmask[13] = {' + ', '.join(f'{x}u' for x in masks) + '};\n\n')
     # ---- half solve: y <- L^-T y with y in registers ----
-    rowptr = [0]
-    for a in anc:
-        rowptr.append(rowptr[-1] + len(a))
+    rowptr = row_pointers(anc)
     o.append('/* y <- L^-T y for one row held in registers (all indices compile-time) */\n')
     o.append('template <typename T> CW_FN void cw_half_solve_regs(const CassieWs<T> &w, T *y) {\n')
     for k in range(nv - 1, 0, -1):
