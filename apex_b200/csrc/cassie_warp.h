@@ -639,6 +639,36 @@ template <typename T, int NF> CW_NOINL void cw_factor(CassieWs<T> &w, T hdamp CW
 
 /* v <- L^-T v (in place, shared vector); Ms / Dinv select the factor */
 template <typename T> CW_NOINL void cw_solve_LT(const T *Ms, const T *Dinv, T *v CW_LANE_PARAM) {
+#ifdef __CUDACC__
+  /* device: the vector lives in one register per lane (lane = dof).  The two legs hang off the 6 base dofs independently, so
+   * dof 6 + s and 19 + s are eliminated in the same phase: the pivots' scaled values travel by shuffle, every lane reads its
+   * own matrix entry (row of the pivot, column = the lane's rank) from shared memory; 13 leg phases + 5 base phases. */
+  {
+    const bool rt = lane >= 19, base = lane < 6;
+    const int ll = lane - (rt ? 13 : 0), rank = CM_dof_nanc[lane];
+    const T dinv = Dinv[lane];
+    T x = v[lane];
+    const T *const colL = Ms + (base ? lane : rank + (rt ? CM_LEG_ROWSPAN : 0)); /* + row of the left pivot: the entry of this lane's leg */
+    const T *const colR = Ms + CM_LEG_ROWSPAN + lane;                              /* base lanes only: entry of the right pivot */
+#pragma unroll
+    for (int s = 12; s >= 0; s--) {
+      const unsigned legmask = CM_leg_ancmask[s];
+      const int okL = CM_dof_rowptr[6 + s];
+      const T xs = x * dinv;
+      const T vL = __shfl_sync(0xffffffffu, xs, 6 + s), vR = __shfl_sync(0xffffffffu, xs, 19 + s);
+      const bool part = base || ((legmask >> ll) & 1u);
+      if (part) x -= colL[okL] * (rt ? vR : vL);
+      if (base) x -= colR[okL] * vR;
+    }
+#pragma unroll
+    for (int k = 5; k >= 1; k--) {
+      const T vk = __shfl_sync(0xffffffffu, x * dinv, k);
+      if (lane < k) x -= Ms[CM_dof_rowptr[k] + lane] * vk;
+    }
+    v[lane] = x;
+    __syncwarp();
+  }
+#else
 #pragma unroll /* k becomes a literal: the ancestor mask and the row offset fold into immediates instead of two table loads per phase */
   for (int k = CW_NV - 1; k >= 1; k--) {
     const unsigned mask = CM_dof_ancmask[k];
@@ -647,9 +677,26 @@ template <typename T> CW_NOINL void cw_solve_LT(const T *Ms, const T *Dinv, T *v
     CW_FOR_LANES { if ((mask >> lane) & 1u) v[lane] -= rk[CM_dof_nanc[lane]] * vk; }
     CW_SYNC();
   }
+#endif
 }
 /* v <- L^-1 v: every dof has exactly one ancestor per depth, so 13 level sweeps suffice */
 template <typename T> CW_NOINL void cw_solve_L(const T *Ms, const T *Dinv, T *v CW_LANE_PARAM) {
+#ifdef __CUDACC__
+  { /* device: register-resident vector; the ancestor's value comes by shuffle (depth < 6: the base dof of that number) */
+    const int na = CM_dof_nanc[lane];
+    const T dinv = Dinv[lane];
+    const T *const row = Ms + CM_dof_rowptr[lane];
+    T x = v[lane];
+#pragma unroll
+    for (int lvl = 0; lvl < CM_MAXANC; lvl++) {
+      const int j = lvl < 6 ? lvl : CM_dof_anc[lane][lvl];
+      const T xj = __shfl_sync(0xffffffffu, x, j & 31);
+      if (na > lvl) x -= row[lvl] * dinv * xj;
+    }
+    v[lane] = x;
+    __syncwarp();
+  }
+#else
 #pragma unroll
   for (int lvl = 0; lvl < CM_MAXANC; lvl++) {
     CW_FOR_LANES {
@@ -657,6 +704,7 @@ template <typename T> CW_NOINL void cw_solve_L(const T *Ms, const T *Dinv, T *v 
     }
     CW_SYNC();
   }
+#endif
 }
 
 /* translational Jacobian column of a point (offset from org) on body b for dof = lane */
@@ -1185,12 +1233,28 @@ template <typename T> CW_NOINL void cw_mj_step(CassieWs<T> &w, bool integrate, i
   if (n > 0) {
     cw_project<T>(w CW_LANE_ARG);
     /* L qacc_warmstart (so that J a = B (L a)) */
+#ifdef __CUDACC__
+    { /* one ancestor per depth: its value comes by shuffle (depth < 6: the base dof of that number) */
+      const int na = CM_dof_nanc[lane];
+      const T *const row = w.Ms + CM_dof_rowptr[lane];
+      const T aw = w.st[S_QACC_WS + lane];
+      T acc = 0;
+#pragma unroll
+      for (int lvl = 0; lvl < CM_MAXANC; lvl++) {
+        const int j = lvl < 6 ? lvl : CM_dof_anc[lane][lvl];
+        const T xj = __shfl_sync(0xffffffffu, aw, j & 31);
+        if (na > lvl) acc += row[lvl] * xj;
+      }
+      w.vec[V_TMP][lane] = aw + acc * w.Dinv[lane];
+    }
+#else
     CW_FOR_LANES {
       const int i = lane, na = CM_dof_nanc[i];
       T acc = 0;
       for (int t = 0; t < na; t++) { const int j = CM_dof_anc[i][t]; acc += w.Ms[CM_dof_rowptr[i] + t] * w.st[S_QACC_WS + j]; }
       w.vec[V_TMP][i] = w.st[S_QACC_WS + i] + acc * w.Dinv[i];
     }
+#endif
     CW_SYNC();
     CW_FOR_LANES {
       const int row = lane;
@@ -1383,6 +1447,29 @@ template <typename T> CW_NOINL void cw_mj_step(CassieWs<T> &w, bool integrate, i
   }
   if (!integrate) { CW_SYNC(); return; }
   /* ---- Euler, implicit in damping: (M + h B) a' = qfrc_smooth + J^T f, J^T f = L^T g ---- */
+#ifdef __CUDACC__
+  { /* (L^T g)_j = g_j + sum over the descendants i of j of U_i[rank_j] g_i / D_i: same phase structure as cw_solve_LT, no chain */
+    const bool rt = lane >= 19, base = lane < 6;
+    const int ll = lane - (rt ? 13 : 0), rank = CM_dof_nanc[lane];
+    const T g = w.vec[V_G][lane], gs = g * w.Dinv[lane];
+    T sacc = g;
+    const T *const colL = w.Ms + (base ? lane : rank + (rt ? CM_LEG_ROWSPAN : 0)), *const colR = w.Ms + CM_LEG_ROWSPAN + lane;
+#pragma unroll
+    for (int s = 12; s >= 0; s--) {
+      const unsigned legmask = CM_leg_ancmask[s];
+      const int okL = CM_dof_rowptr[6 + s];
+      const T vL = __shfl_sync(0xffffffffu, gs, 6 + s), vR = __shfl_sync(0xffffffffu, gs, 19 + s);
+      if (base || ((legmask >> ll) & 1u)) sacc += colL[okL] * (rt ? vR : vL);
+      if (base) sacc += colR[okL] * vR;
+    }
+#pragma unroll
+    for (int k = 5; k >= 1; k--) {
+      const T vk = __shfl_sync(0xffffffffu, gs, k);
+      if (lane < k) sacc += w.Ms[CM_dof_rowptr[k] + lane] * vk;
+    }
+    w.vec[V_TMP][lane] = sacc + w.vec[V_SMOOTH][lane];
+  }
+#else
   CW_FOR_LANES {
     const int j = lane;
     T s = w.vec[V_G][j];
@@ -1392,6 +1479,7 @@ template <typename T> CW_NOINL void cw_mj_step(CassieWs<T> &w, bool integrate, i
       if ((CM_dof_ancmask[i] >> j) & 1u) s += w.Ms[CM_dof_rowptr[i] + nj] * w.Dinv[i] * w.vec[V_G][i];
     w.vec[V_TMP][j] = s + w.vec[V_SMOOTH][j];
   }
+#endif
   CW_SYNC();
   if (flags & CW_BAR_EULER) CW_BLOCK_SYNC();
   { /* the second factor (M + h B) was computed together with the first: rows in cw_Ms2(w), inverse pivots in w.D */
