@@ -656,14 +656,17 @@ template <typename T> CW_NOINL void cw_solve_LT(const T *Ms, const T *Dinv, T *v
       const int okL = CM_dof_rowptr[6 + s];
       const T xs = x * dinv;
       const T vL = __shfl_sync(0xffffffffu, xs, 6 + s), vR = __shfl_sync(0xffffffffu, xs, 19 + s);
+      /* branch-free: both loads hit valid words for every lane; a lane the pivot does not touch multiplies by 0 */
       const bool part = base || ((legmask >> ll) & 1u);
-      if (part) x -= colL[okL] * (rt ? vR : vL);
-      if (base) x -= colR[okL] * vR;
+      const T cL = colL[okL], cR = colR[okL];
+      x -= (part ? cL : (T)0) * (rt ? vR : vL);
+      x -= (base ? cR : (T)0) * vR;
     }
 #pragma unroll
     for (int k = 5; k >= 1; k--) {
       const T vk = __shfl_sync(0xffffffffu, x * dinv, k);
-      if (lane < k) x -= Ms[CM_dof_rowptr[k] + lane] * vk;
+      const T c = Ms[CM_dof_rowptr[k] + (lane & 7)];
+      x -= (lane < k ? c : (T)0) * vk;
     }
     v[lane] = x;
     __syncwarp();
@@ -691,7 +694,8 @@ template <typename T> CW_NOINL void cw_solve_L(const T *Ms, const T *Dinv, T *v 
     for (int lvl = 0; lvl < CM_MAXANC; lvl++) {
       const int j = lvl < 6 ? lvl : CM_dof_anc[lane][lvl];
       const T xj = __shfl_sync(0xffffffffu, x, j & 31);
-      if (na > lvl) x -= row[lvl] * dinv * xj;
+      const T c = row[lvl] * dinv; /* a valid word for every lane (the rows are at least 13 words from the end of the storage) */
+      x -= (na > lvl ? c : (T)0) * xj;
     }
     v[lane] = x;
     __syncwarp();
@@ -1243,7 +1247,8 @@ template <typename T> CW_NOINL void cw_mj_step(CassieWs<T> &w, bool integrate, i
       for (int lvl = 0; lvl < CM_MAXANC; lvl++) {
         const int j = lvl < 6 ? lvl : CM_dof_anc[lane][lvl];
         const T xj = __shfl_sync(0xffffffffu, aw, j & 31);
-        if (na > lvl) acc += row[lvl] * xj;
+        const T c = row[lvl];
+        acc += (na > lvl ? c : (T)0) * xj;
       }
       w.vec[V_TMP][lane] = aw + acc * w.Dinv[lane];
     }
@@ -1367,7 +1372,11 @@ template <typename T> CW_NOINL void cw_mj_step(CassieWs<T> &w, bool integrate, i
         if (bounded) { f0 = cw_max(f0, (T)0); g0 = -f0; pblk[myblk][8 + (lane & 3)] = g0; }
         iters = it + 1;
         for (int o = 16; o > 0; o >>= 1) imp += __shfl_xor_sync(0xffffffffu, imp, o);
+#ifdef CW_EXP_FIXED_SWEEPS /* timing experiment only (tools/build_variant.sh): every env runs the same number of sweeps */
+        if (it + 1 >= CW_EXP_FIXED_SWEEPS) break;
+#else
         if (imp * scale < (T)1e-8) break;
+#endif
         __syncwarp();
       }
       __syncwarp();
@@ -1459,13 +1468,15 @@ template <typename T> CW_NOINL void cw_mj_step(CassieWs<T> &w, bool integrate, i
       const unsigned legmask = CM_leg_ancmask[s];
       const int okL = CM_dof_rowptr[6 + s];
       const T vL = __shfl_sync(0xffffffffu, gs, 6 + s), vR = __shfl_sync(0xffffffffu, gs, 19 + s);
-      if (base || ((legmask >> ll) & 1u)) sacc += colL[okL] * (rt ? vR : vL);
-      if (base) sacc += colR[okL] * vR;
+      const T cL = colL[okL], cR = colR[okL];
+      sacc += ((base || ((legmask >> ll) & 1u)) ? cL : (T)0) * (rt ? vR : vL);
+      sacc += (base ? cR : (T)0) * vR;
     }
 #pragma unroll
     for (int k = 5; k >= 1; k--) {
       const T vk = __shfl_sync(0xffffffffu, gs, k);
-      if (lane < k) sacc += w.Ms[CM_dof_rowptr[k] + lane] * vk;
+      const T c = w.Ms[CM_dof_rowptr[k] + (lane & 7)];
+      sacc += (lane < k ? c : (T)0) * vk;
     }
     w.vec[V_TMP][lane] = sacc + w.vec[V_SMOOTH][lane];
   }
