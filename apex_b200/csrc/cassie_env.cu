@@ -4,6 +4,9 @@
 #include <string.h>
 #include "cassie_envstep.h"
 #include "../../include/apex_cassie.h"
+#ifndef CW_STEP_THREADS_F32
+#define CW_STEP_THREADS_F32 480 /* launch bound of the float32 step kernel: 15 warps -> 128 registers per thread */
+#endif
 
 template <typename T> __device__ __forceinline__ void ws_load(CassieWs<T> &w, const T *st, const int *sti, int lane) {
   for (int k = lane; k < S_WORDS; k += 32) w.st[k] = st[k];
@@ -49,7 +52,7 @@ template <typename T> __global__ void __launch_bounds__(32) k_env_reset_for_test
 /* W warps (= W envs) per CTA; the CTA barrier inside cw_env_step's sub-step loop must be reached by every warp, so
  * warps past the end of the batch run the barriers only. */
 template <typename T>
-__global__ void __launch_bounds__(sizeof(T) == 4 ? 480 : 224) k_env_step(T *st, int *sti, int n, const T *action, T *obs, T *reward, int *done, T *term_obs, int max_traj_len,
+__global__ void __launch_bounds__(sizeof(T) == 4 ? CW_STEP_THREADS_F32 : 224) k_env_step(T *st, int *sti, int n, const T *action, T *obs, T *reward, int *done, T *term_obs, int max_traj_len,
                            const int *active, CassieTraj<T> traj, const int *order, int bar_mask) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
@@ -164,7 +167,7 @@ int apex_cassie_layout(const char *name) {
       {"drive_hist", I_DRIVEHIST}, {"time", I_TIME}, {"counter", I_COUNTER}, {"has_prev", I_HASPREV}, {"has_u", I_HASU},
       {"drive_init", I_DRIVEINIT}, {"joint_init", I_JOINTINIT}, {"flags", I_FLAGS}, {"stepcount", I_STEPCOUNT}, {"rng_ctr", I_RNGCTR},
       {"env_id", I_ENVID}, {"seed", I_SEED}, {"dyn_rand", I_DYNRAND}, {"solver_iter", I_SOLVER_ITER}, {"ncon", I_NCON}, {"nefc", I_NEFC}, {"variant", I_VARIANT}, {"phase_floor", I_PHASEFLOOR}, {"cost", I_COST},
-      {"stance_mode", I_STANCEMODE}, {"sim_steps", I_SIMSTEPS}, {"hold_commands", I_HOLDCMD}};
+      {"stance_mode", I_STANCEMODE}, {"sim_steps", I_SIMSTEPS}, {"hold_commands", I_HOLDCMD}, {"q_lo", S_QLO}, {"sens_count", I_SENSCNT}, {"overflow", I_OVERFLOW}};
   for (size_t i = 0; i < sizeof(tab) / sizeof(tab[0]); i++)
     if (strcmp(tab[i].n, name) == 0) return tab[i].off;
   return -1;

@@ -48,7 +48,7 @@ template <typename T> CW_NOINL void cw_sim_step_pd(CassieWs<T> &w, int bar CW_LA
       w.y[Y_MTORQUE + i] = gear * dl[5];
       /* drive encoder, @0x7fe0-0x8137 */
       const T N = (T)(1 << CM_drive_bits[i]);
-      const int32_t c = (int32_t)(w.st[S_SENS_ACTPOS + i] / (T)CW_TWO_PI * N);
+      const int32_t c = w.sti[I_SENSCNT + i]; /* = (int32_t)(actuatorpos / 2 pi * N), taken in float64 by cw_mj_step's sensor stage */
       int *hist = w.sti + I_DRIVEHIST + 9 * i;
       if (!dinit) for (int k = 0; k < 9; k++) hist[k] = c;
       for (int k = 8; k > 0; k--) hist[k] = hist[k - 1];
@@ -63,7 +63,7 @@ template <typename T> CW_NOINL void cw_sim_step_pd(CassieWs<T> &w, int bar CW_LA
       /* joint encoder + IIR differentiator, @0x81a0-0x82b7, constants .rodata @0x2f2d8-0x2f2f0 */
       const int s = lane - CM_NU;
       const T N = (T)(1 << CM_jsens_bits[s]);
-      const int32_t c = (int32_t)(w.st[S_SENS_JPOS + s] / (T)CW_TWO_PI * N);
+      const int32_t c = w.sti[I_SENSCNT + CM_NU + s];
       const T x = (T)c * ((T)CW_TWO_PI / N);
       T *jx = w.st + S_JX + 4 * s, *jy = w.st + S_JY + 2 * s;
       if (!jinit) { for (int k = 0; k < 4; k++) jx[k] = x; jy[0] = jy[1] = 0; }
@@ -344,6 +344,7 @@ template <typename T> CW_NOINL void cw_env_reset(CassieWs<T> &w, T *obs_out, con
   CW_FOR_LANES {
     for (int k = lane; k < CM_NQ; k += 32) w.st[S_QPOS + k] = (T)CMT(qpos_init)[k];
     w.st[S_QVEL + lane] = 0;
+    for (int k = lane; k < CM_NQ + CM_NV; k += 32) w.st[S_QLO + k] = 0;
     if (lane == 0) { w.st[S_PHASE] = phase; w.sti[I_TIME] = 0; w.sti[I_COUNTER] = 0; }
   }
   CW_SYNC();
@@ -396,6 +397,8 @@ template <typename T> CW_NOINL void cw_env_reset_for_test(CassieWs<T> &w, T *obs
       for (int k = S_QVEL + lane; k < S_UPTARGET; k += 32) w.st[k] = 0; /* qvel, warm start, ctrl, sensors, delay line, filters */
       for (int k = lane; k < CM_NQ; k += 32) w.st[S_QPOS + k] = (T)CMT(qpos_init)[k];
       for (int k = lane; k < 90; k += 32) w.sti[I_DRIVEHIST + k] = 0;
+      for (int k = lane; k < CM_NQ + CM_NV; k += 32) w.st[S_QLO + k] = 0;
+      if (lane < 16) w.sti[I_SENSCNT + lane] = 0;
       if (lane >= 16 && lane < 22) w.st[S_XFRC + lane - 16] = 0;
     } else if (lane < 3) {
       w.st[S_LASTPELVIS + lane] = w.st[S_QPOS + lane];

@@ -103,6 +103,7 @@ __device__ __forceinline__ void cw_mbar_wait(unsigned addr, unsigned parity) {
 #define CW_LFOOT 13
 #define CW_RFOOT 25
 #define CW_FOOT_Z_OFFSET 0.0550841 /* libcassiemujoco.so .rodata @0x2f2b8 */
+#define CW_TWO_PI_D 6.283185307179586
 
 /* persistent per-env record: real words */
 enum {
@@ -116,7 +117,11 @@ enum {
   S_FOOTVEL = 451, /* l_foot_vel(3), r_foot_vel(3) of the last sub-step */
   S_XFRC = 457,    /* mjData.xfrc_applied of the pelvis: force(3), torque(3), world axes, at the body's centre of mass */
   S_PHASEADD = 463, /* env.phase_add: 1 in training, 1.5 above 1.4 m/s in tools/test_commands.py:84-87 */
-  S_WORDS = 464
+  S_QLO = 464,      /* float32 kernel: low-order parts of qpos (35) and qvel (32); the state is the unevaluated sum st[S_QPOS + k] +
+                     * st[S_QLO + k].  mj_Euler's two accumulations run compensated (the per-sub-step increments are ~1e-4 of the
+                     * values, so plain float32 adds lose most of their bits) and the encoder counts are taken from the sum in
+                     * float64, like the float64 kernel takes them from its qpos.  All zeros in the float64 kernel. */
+  S_WORDS = 532
 };
 /* persistent per-env record: int words */
 enum {
@@ -127,7 +132,12 @@ enum {
   I_STANCEMODE = 108 /* clock reward's stance_mode: 0 "zero", 1 "grounded" once reset_for_test has run (cassie.py:219,701) */,
   I_SIMSTEPS = 109 /* physics sub-steps since the simulator was last reset: sim.time() = that many additions of 0.0005 */,
   I_HOLDCMD = 110 /* != 0: env.step skips its random command changes (cassie.py:483-491); deterministic evaluation */,
-  I_WORDS = 112
+  I_OVERFLOW = 111 /* sub-steps (since init) in which the row / contact capacity (CW_NEFC, CW_NCON) dropped something: a penetrating
+                    * candidate beyond the 6th contact, a contact that did not fit behind the rows already seated, or an active
+                    * joint limit that found the row budget full */,
+  I_SENSCNT = 112 /* encoder counts of the 10 drives and 6 joints taken from the state at the start of the last mj_step (the sensor
+                   * values cassie_sim_step_ethercat quantises, @0x7fe0-0x82b7), computed in float64 whatever T is */,
+  I_WORDS = 128
 };
 /* state_out slice (workspace only) */
 enum { Y_PPOS = 0, Y_QUAT = 3, Y_ROTVEL = 7, Y_TVEL = 10, Y_TACC = 13, Y_MPOS = 16, Y_MVEL = 26, Y_MTORQUE = 36, Y_JPOS = 46, Y_JVEL = 52, Y_WORDS = 58 };
@@ -169,6 +179,7 @@ struct CassieWs {
   int efc_type[CW_NEFC];
   T vec[V_NVEC][CW_NV];
   int ncon, nefc, solver_iter;
+  int dropped; /* this sub-step lost a contact or a limit row to the capacity (see I_OVERFLOW) */
   int bar_mask; /* CTA synchronisation inside a sub-step (CW_BAR_* / CW_SPLIT bits), GPU build: keeps the CTA's warps on the same code */
   unsigned bar_addr; /* shared-memory address of the CTA's mbarrier (split barrier) */
   T con_pos[CW_NCON][3], con_frame[CW_NCON][9], con_dist[CW_NCON], con_mu[CW_NCON];
@@ -219,6 +230,33 @@ CW_FN float cw_max(float a, float b) { return fmaxf(a, b); }
 CW_FN double cw_min(double a, double b) { return a < b ? a : b; }
 CW_FN double cw_max(double a, double b) { return a > b ? a : b; }
 
+/* hi + lo += h * a.  float: error-free product (FMA) and TwoSum, the rounding errors go to lo (a compensated accumulation: the
+ * sum of 50 sub-step increments is as good as its float64 value rounded once); double: a plain accumulation, lo stays 0. */
+CW_FN float cw_fmaf_host(float a, float b, float c) { return fmaf(a, b, c); }
+CW_FN void cw_acc_add(double &hi, double &lo, double h, double a) { hi += h * a; (void)lo; }
+CW_FN void cw_acc_add(float &hi, float &lo, float h, float a) {
+#ifdef CW_EXP_PLAIN_F32_EULER /* measurement only (tools/build_variant.sh): what the compensation buys */
+  hi += h * a; (void)lo; return;
+#endif
+#ifdef __CUDA_ARCH__
+  const float p = __fmul_rn(h, a), pe = __fmaf_rn(h, a, -p);
+  const float t = __fadd_rn(lo, __fadd_rn(p, pe)); /* |lo| <= ulp(hi) / 2 and the increment are both small next to hi */
+  const float s = __fadd_rn(hi, t), bb = __fadd_rn(s, -hi);
+  lo = __fadd_rn(__fadd_rn(hi, -__fadd_rn(s, -bb)), __fadd_rn(t, -bb));
+  hi = s;
+#else
+  volatile float p = h * a;
+  const float pe = cw_fmaf_host(h, a, -p);
+  volatile float t = lo + (p + pe);
+  volatile float s = hi + t;
+  volatile float bb = s - hi;
+  volatile float e1 = s - bb;
+  volatile float e2 = hi - e1;
+  volatile float e3 = t - bb;
+  lo = e2 + e3;
+  hi = s;
+#endif
+}
 template <typename T> CW_FN void cw_cross(T *r, const T *a, const T *b) {
   T x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
   r[0] = x; r[1] = y; r[2] = z;
@@ -821,7 +859,13 @@ template <typename T> CW_FN void cw_collision(CassieWs<T> &w CW_LANE_PARAM) {
       nc++;
     }
   }
-  CW_FOR_LANES { if (lane == 0) w.ncon = nc; }
+  int npen = 0; /* penetrating candidates: more than were seated = capacity overflow (recorded by cw_make_constraint) */
+#ifdef __CUDA_ARCH__
+  npen = __popc(__ballot_sync(0xffffffffu, lane < 26 && w.u.p.cand_dist[lane] < 0));
+#else
+  for (int s = 0; s < 26; s++) npen += w.u.p.cand_dist[s] < 0 ? 1 : 0;
+#endif
+  CW_FOR_LANES { if (lane == 0) { w.ncon = nc; w.dropped = npen > nc ? 1 : 0; } }
   CW_SYNC();
 }
 
@@ -851,13 +895,15 @@ template <typename T> CW_FN void cw_make_constraint(CassieWs<T> &w, const T *qpo
       r += 3;
     }
     /* row budget: contacts (feet first) are seated before joint limits, whole contacts at a time */
-    int nckeep = 0, crows = 0;
-    if (!(flags & 2))
+    int nckeep = 0, crows = 0, dropped = w.dropped;
+    if (!(flags & 2)) {
       for (int c = 0; c < w.ncon; c++) {
         const int nrow = w.con_dim[c] == 3 ? 4 : 1;
         if (r + crows + nrow > CW_NEFC) break;
         crows += nrow; nckeep++;
       }
+      if (nckeep < w.ncon) dropped = 1;
+    }
     /* joint limits */
 #pragma unroll
     for (int l = 0; l < 16; l++) {
@@ -872,7 +918,7 @@ template <typename T> CW_FN void cw_make_constraint(CassieWs<T> &w, const T *qpo
             if (lane == 0) { w.efc_aref[r] = dist; w.efc_R[r] = w.st[S_DOFINVW + da]; w.efc_type[r] = 1; }
           }
           r++;
-        }
+        } else if (dist < 0) dropped = 1;
       }
     }
     /* contacts */
@@ -903,7 +949,7 @@ template <typename T> CW_FN void cw_make_constraint(CassieWs<T> &w, const T *qpo
       r += nrow;
     }
     CW_SYNC(); /* every lane is past the loops that read w.ncon as their bound */
-    CW_FOR_LANES { if (lane == 0) w.ncon = nc; }
+    CW_FOR_LANES { if (lane == 0) { w.ncon = nc; if (dropped) w.sti[I_OVERFLOW] += 1; } }
   } else {
     CW_FOR_LANES { if (lane == 0) w.ncon = 0; }
   }
@@ -1176,10 +1222,17 @@ template <typename T> CW_NOINL void cw_mj_step(CassieWs<T> &w, bool integrate, i
   /* sensors (positions / velocities) for the next wrapper call */
   CW_FOR_LANES {
     if (lane < CM_NU) {
-      w.st[S_SENS_ACTPOS + lane] = (T)CMT(act_gear)[lane] * qpos[CM_act_qposadr[lane]];
+      const int qa = CM_act_qposadr[lane];
+      w.st[S_SENS_ACTPOS + lane] = (T)CMT(act_gear)[lane] * qpos[qa];
       w.st[S_SENS_ACTVEL + lane] = (T)CMT(act_gear)[lane] * qvel[CM_act_dof[lane]];
+      /* encoder count, truncation toward 0 (@0x7fe0-0x8137): same operations, in float64, on hi + lo */
+      const double q = (double)qpos[qa] + (double)w.st[S_QLO + qa];
+      w.sti[I_SENSCNT + lane] = (int32_t)(CM_act_gear[lane] * q / CW_TWO_PI_D * (double)(1 << CM_drive_bits[lane]));
     } else if (lane < CM_NU + 6) {
-      w.st[S_SENS_JPOS + lane - CM_NU] = qpos[CM_jsens_qposadr[lane - CM_NU]];
+      const int qa = CM_jsens_qposadr[lane - CM_NU];
+      w.st[S_SENS_JPOS + lane - CM_NU] = qpos[qa];
+      const double q = (double)qpos[qa] + (double)w.st[S_QLO + qa];
+      w.sti[I_SENSCNT + lane] = (int32_t)(q / CW_TWO_PI_D * (double)(1 << CM_jsens_bits[lane - CM_NU]));
     } else if (lane < CM_NU + 10) {
       w.st[S_SENS_QUAT + lane - CM_NU - 6] = w.qkeep[0][lane - CM_NU - 6];
     } else if (lane < CM_NU + 13) {
@@ -1501,14 +1554,16 @@ template <typename T> CW_NOINL void cw_mj_step(CassieWs<T> &w, bool integrate, i
     cw_solve_L<T>(Ms2, Dinv2, w.vec[V_TMP] CW_LANE_ARG);
   }
   CW_FOR_LANES {
-    qvel[lane] += h * w.vec[V_TMP][lane];
+    cw_acc_add(qvel[lane], w.st[S_QLO + CM_NQ + lane], h, w.vec[V_TMP][lane]);
     w.st[S_QACC_WS + lane] = w.vec[V_QACC][lane];
   }
   CW_SYNC();
   CW_FOR_LANES {
     const int i = lane, j = CM_dof_jnt[i];
     if (CM_jnt_type[j] != 2) {
-      qpos[CM_dof_qposadr[i]] += h * qvel[i];
+      const int qa = CM_dof_qposadr[i];
+      /* q += h (v_hi + v_lo): the low part of the velocity is far below the position's last bit, but it is free here */
+      cw_acc_add(qpos[qa], w.st[S_QLO + qa], h, qvel[i]);
     } else if (i == CM_jnt_dofadr[j]) {
       const int qa = CM_jnt_qposadr[j];
       T wv[3] = {qvel[i], qvel[i + 1], qvel[i + 2]};

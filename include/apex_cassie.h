@@ -13,6 +13,20 @@
  * no hidden allocations; `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
  * dtype 0 = float32, 1 = float64 (applies to st, action, obs, reward, term_obs).
  * Return value: 0 on success, a negative cudaError_t otherwise (-1000 = bad argument).
+ *
+ * Capacity (MuJoCo's njmax / nconmax analogue; the CPU oracle applies the same rules, so parity holds across an overflow):
+ * at most 6 contacts and 32 constraint rows per env and sub-step.  Collision candidates are taken in a fixed priority order
+ * (the four foot end-spheres first, then tarsus, shin, hip capsules, pelvis, then the 9 left x right capsule pairs); a
+ * penetrating candidate beyond the 6th is dropped.  Rows: the 12 connect rows are always seated; contacts come next in that
+ * order, whole contacts at a time (4 pyramid rows for floor contacts, 1 for a capsule pair), until one does not fit in
+ * 32 - 12 = 20 rows — it and the later ones are dropped; active joint limits take whatever rows the contacts leave and are
+ * dropped when none are left.  Every sub-step in which anything was dropped increments the env's "overflow" counter
+ * (apex_cassie_layout("overflow"), int state).  Measured: 0 overflows in 10,240,000 sub-steps of 4096 randomised envs driven
+ * with N(0, 0.3) actions through 4041 falls (tests/test_env_gpu.py::test_env_f64_matches_oracle_full_size).
+ *
+ * float32 records carry the low-order parts of qpos / qvel ("q_lo", 67 words): the state is hi + lo, mj_Euler accumulates
+ * compensated and the encoder counts ("sens_count", int state) are taken from hi + lo in float64.  A caller that overwrites
+ * "qpos" / "qvel" must zero (or set) the matching "q_lo" words.
  */
 #ifndef APEX_CASSIE_H
 #define APEX_CASSIE_H

@@ -329,7 +329,7 @@ def test_capi_exports_every_declared_symbol():
     for nme in set(names):
         assert hasattr(lib, nme), nme
     lib.apex_cassie_layout.argtypes = [C.c_char_p]
-    assert lib.apex_cassie_state_words() == 464 and lib.apex_cassie_istate_words() == 112
+    assert lib.apex_cassie_state_words() == 532 and lib.apex_cassie_istate_words() == 128
     assert lib.apex_cassie_layout(b"qvel") == 35 and lib.apex_cassie_layout(b"nope") == -1
 
 
