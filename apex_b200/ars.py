@@ -91,6 +91,12 @@ class ARS:
         L, s = self.L, self._s()
         om = None if obs_mean is None else obs_mean.data_ptr()
         osd = None if obs_std is None else obs_std.data_ptr()
+        # "everybody has fallen" is polled without stalling the launch queue: every 16 steps the live count is copied to pinned
+        # host memory behind an event, and the loop stops at the first step that finds a completed copy reading 0
+        if getattr(self, "_live_host", None) is None:
+            self._live_host = torch.zeros(1, dtype=torch.int64).pin_memory()
+            self._live_event = torch.cuda.Event()
+        pending = False
         for t in range(int(traj_len)):
             _capi.check(L.apex_ars_policy(obs.data_ptr(), n, self.S, self.H, self.A, self.theta.data_ptr(), self.noise.data_ptr(),
                                           idx_loc.data_ptr(), self.dir.data_ptr(), self.sign.data_ptr(), om, osd,
@@ -101,8 +107,14 @@ class ARS:
             ret += torch.where(alive, rew.double() - reward_shift, torch.zeros_like(ret))
             steps += alive
             active = (alive & ((done & 3) == 0)).to(torch.int32)
-            if t % 16 == 15 and int(active.sum()) == 0:
-                break
+            if pending and self._live_event.query():
+                pending = False
+                if int(self._live_host[0]) == 0:
+                    break
+            if t % 16 == 15 and not pending:
+                self._live_host.copy_(active.sum(dtype=torch.int64).view(1), non_blocking=True)
+                self._live_event.record()
+                pending = True
         r = ret.view(self.local_deltas, 2, self.rollouts).mean(dim=2)  # [dir, (+, -)]
         if self.world > 1:
             allr = [torch.zeros_like(r) for _ in range(self.world)]

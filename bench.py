@@ -33,6 +33,7 @@ def parse():
     ap.add_argument("--envs", type=int, default=N_ENVS)
     ap.add_argument("--horizon", type=int, default=HORIZON)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the cfg3 / cfg4 / cfg5 measurements (BASELINE.json configs 3-5)")
     ap.add_argument("--precision", default="f32", choices=["f32", "bf16"],
                     help="bf16: forward 256x256 hidden layers on tcgen05 (BASELINE configs[3]); the headline config is f32")
     ap.add_argument("--env", default="Cassie-v0", choices=["Cassie-v0", "CassieTraj-v0"])
@@ -62,6 +63,16 @@ class CpuReference:
         torch.set_num_threads(threads)
         self.actor = Gaussian_FF_Actor(50, 10, fixed_std=torch.ones(10) * float(np.exp(-1.5)))
         self.critic = FF_V(50)
+        mobs = [0.1, 1, -2, 3, -4, -10, -11, 12, 13, 14, -5, -6, 7, 8, 9, 15, -16, 17, -18, 19, -20, -26, -27, 28, 29, 30, -21, -22,
+                23, 24, 25, 31, -32, 33, 37, 38, 39, 34, 35, 36, 43, 44, 45, 40, 41, 42, 46, 47, 48, 49]  # cassie/cassie.py:244
+        macts = [-5, -6, 7, 8, 9, -0.1, -1, 2, 3, 4]  # cassie/cassie.py:69
+
+        def table(m):  # (x @ M)[j] = sign * x[src]  (rl/envs/wrappers.py:70-77)
+            src, sign = [0] * len(m), [0.0] * len(m)
+            for i, v in enumerate(m):
+                src[int(abs(v))], sign[int(abs(v))] = i, (1.0 if v > 0 else -1.0)
+            return torch.tensor(src), torch.tensor(sign)
+        (self.m_obs_src, self.m_obs_sign), (self.m_act_src, self.m_act_sign) = table(mobs), table(macts)
         self.aopt = torch.optim.Adam(self.actor.parameters(), lr=1e-4, eps=1e-5)
         self.copt = torch.optim.Adam(self.critic.parameters(), lr=1e-4, eps=1e-5)
 
@@ -109,6 +120,11 @@ class CpuReference:
                 ratio = (logp - old_logp[idx]).exp()
                 a_loss = -torch.min(ratio * adv[idx], ratio.clamp(0.8, 1.2) * adv[idx]).mean()
                 c_loss = 0.5 * (ret_t[idx] - self.critic(obs_t[idx])).pow(2).mean()
+                # mirror loss (ppo.py:303-325): 0.4 * mean((pi(s) - M_a pi(M_o s))^2), clock entries of M_o s sign-flipped
+                mo = obs_t[idx][:, self.m_obs_src] * self.m_obs_sign
+                mo[:, 46:48] = -obs_t[idx][:, 46:48]
+                mirrored = self.actor(mo, deterministic=True)[:, self.m_act_src] * self.m_act_sign
+                a_loss = a_loss + 0.4 * (pdf.mean - mirrored).pow(2).mean()
                 self.aopt.zero_grad(); a_loss.backward()
                 torch.nn.utils.clip_grad_norm_(self.actor.parameters(), 0.05); self.aopt.step()
                 self.copt.zero_grad(); c_loss.backward()
@@ -133,8 +149,9 @@ def cpu_arm(steps, warmup, target_seconds=10.0):
     for _ in range(steps):
         done += ref.iteration(T, max(64, (n_envs * T) // 4), EPOCHS)
     dt = time.perf_counter() - t0
-    sample = (f"{steps} x PPO iteration of {n_envs} envs x {T} steps (oracle C port of physics+env with OpenMP, torch-CPU MLPs "
-              f"and update, {cores} threads)")
+    sample = (f"{steps} x PPO iteration of {n_envs} envs x {T} steps = {n_envs * T} env steps each (oracle C port of physics+env with "
+              f"OpenMP, torch-CPU MLPs; update = {EPOCHS} epochs of minibatches of {max(64, (n_envs * T) // 4)} with the clipped-ratio, "
+              f"value and mirror losses, clip-norm, Adam; {cores} threads)")
     return done / dt, cores, sample, dt / steps
 
 
@@ -175,6 +192,103 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons)}
 
 
+def reference_python_arm(seconds=12.0):
+    """cpu_baseline.reference_python: the reference's own rl/algos/ppo.py sample_parallel from baseline/_ref on this host."""
+    try:
+        out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ref_python_arm.py"), str(os.cpu_count() or 1), str(seconds)],
+                             capture_output=True, text=True, timeout=240)
+        return json.loads(out.stdout.strip().splitlines()[-1])
+    except Exception as e:  # the arm is optional evidence: never let it take the bench line down
+        return {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# The other BASELINE.json configs, measured in the same run so that BENCH / SCALE carry them (keys cfg3, cfg4, cfg5)
+# ----------------------------------------------------------------------------------------------------------------
+def device_ms(fn, dev, world):
+    """fn() timed on the device between barriers, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out = fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms), out
+
+
+def extra_cfg3_td3(dev):
+    """configs[2]: TD3 on a 1M-transition device replay ring; batch sweep (rl/algos/sync_td3.py:133-209)."""
+    import torch
+    from apex_b200.td3 import TD3, ReplayBuffer
+    rb = ReplayBuffer(50, 10, max_size=1_000_000, device=dev)
+    g = torch.Generator(device=dev).manual_seed(0)
+    rb.storage.copy_(torch.rand(rb.storage.shape, generator=g, device=dev) * 2 - 1)
+    rb.storage[:, -1] = (rb.storage[:, -1] > 0.9).float()
+    rb.size, rb.ptr = rb.max_size, 0
+    algo = TD3(50, 10, 1.0, a_lr=3e-4, c_lr=1e-3, device=dev)
+    sweep = []
+    for batch, reps in ((256, 100), (4096, 100), (65536, 20)):
+        algo.train(rb, 4, batch_size=batch, generator=g)
+        l0 = algo.launches
+        ms, _ = device_ms(lambda: algo.train(rb, reps, batch_size=batch, generator=g), dev, 1)
+        sweep.append({"batch": batch, "ms_per_update": ms / reps, "updates_per_s": reps * 1e3 / ms, "samples_per_s": batch * reps * 1e3 / ms,
+                      "replay_gather_GBps": batch * 112 * 4 * 2 * reps / ms / 1e6, "launches_per_update": (algo.launches - l0) / reps})
+    del rb, algo
+    torch.cuda.empty_cache()
+    return {"workload": "TD3 Cassie-v0 sizes (50 / 10 / 256 x 256), replay ring 1,000,000 x 112 f32 = 448 MB in HBM, uniform sampling with "
+                        "replacement, one train() iteration = critic step (+ actor step and Polyak every 2nd)", "dtype": "f32",
+            "metric": "TD3 updates/s", "sweep": sweep}
+
+
+def extra_cfg4_traj(dev, rank, world):
+    """configs[3]: PPO CassieTraj-v0, 8192 envs per GPU, bf16 hidden layers on tcgen05, gradient all-reduce per optimizer step."""
+    import numpy as np
+    import torch
+    from apex_b200.envs import BatchedCassieTrajEnv
+    from apex_b200.policies import Gaussian_FF_Actor, FF_V
+    from apex_b200.ppo import PPO
+    n, T = 8192, HORIZON
+    g = np.load(os.path.join(ROOT, "tests", "golden", "traj_walking_rows.npz"))
+    table = (np.ascontiguousarray(g["rows"], dtype=np.float64), int(g["traj_len"]))
+    torch.manual_seed(0)
+    actor, critic = Gaussian_FF_Actor(50, 10, fixed_std=torch.ones(10) * float(np.exp(-1.5)), env_name="CassieTraj-v0"), FF_V(50)
+    algo = PPO(dict(num_steps=n * T, minibatch_size=MINIBATCH, epochs=EPOCHS, max_traj_len=400, seed=0, max_kl=None, precision="bf16"))
+    env_fn = lambda: BatchedCassieTrajEnv(n, table, device=dev, seed=0, dynamics_randomization=True, env_id0=rank * n)
+    gen = torch.Generator(device=dev).manual_seed(99)
+    algo.train_iteration(env_fn, actor, critic, generator=gen)
+    ms, _ = device_ms(lambda: algo.train_iteration(env_fn, actor, critic, generator=gen), dev, world)
+    del algo, actor, critic
+    torch.cuda.empty_cache()
+    return {"workload": f"PPO CassieTraj-v0 {n} envs/GPU x {T} steps, mb {MINIBATCH}, {EPOCHS} epochs, bf16 tcgen05 forward hidden layers, "
+                        f"gradient all-reduce per optimizer step, {world} GPU(s)", "dtype": "bf16 (forward hidden layers; rest f32)",
+            "metric": "env-steps/s", "value": n * T * world / (ms * 1e-3), "ms_per_iteration": ms, "iterations_timed": 1, "n_gpus": world}
+
+
+def extra_cfg5_ars(dev, rank, world):
+    """configs[4]: ARS, 512 directions x 2 signs x 16 rollouts sharded over the ranks (rl/algos/ars.py:122-157)."""
+    import torch
+    from apex_b200.ars import ARS, Linear_Actor
+    from apex_b200.envs import BatchedCassieEnv
+    algo = ARS(lambda: Linear_Actor(50, 10, 32), lambda m: BatchedCassieEnv(m, device=dev, seed=1, env_id0=rank * m), deltas=512, rollouts=16,
+               step_size=0.02, std=0.0075, seed=3)
+    algo.step(traj_len=16)
+    ms, steps = device_ms(lambda: algo.step(traj_len=400), dev, world)
+    envs = algo.env.num_envs
+    del algo
+    torch.cuda.empty_cache()
+    return {"workload": f"ARS Cassie-v0, 512 directions x 2 x 16 rollouts = 16384 episodes per iteration ({envs} envs/GPU), linear 50-32-10 "
+                        f"policy per env, sigma 0.0075, horizon 400, all-gather of the [512, 2] return table, {world} GPU(s)", "dtype": "f32",
+            "metric": "env-steps/s", "value": steps / (ms * 1e-3), "env_steps": steps, "ms_per_iteration": ms, "iterations_timed": 1,
+            "n_gpus": world}
+
+
 def main():
     args = parse()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
@@ -185,11 +299,14 @@ def main():
         if rank != 0:
             return
         v, cores, sample, per = cpu_arm(args.steps, args.warmup)
+        cpu = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample,
+               "reference_python": reference_python_arm()}
         print(json.dumps({"impl": "reference", "metric": "Cassie-v0 PPO env-steps/sec", "value": v, "unit": "env-steps/s",
                           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per * 1e3,
                           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                          "config": {"workload": workload, "note": "CPU arm: bounded sample of the same PPO iteration"},
-                          "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
+                          "config": {"workload": workload, "note": "CPU arm: bounded sample of the same PPO iteration (rollout + return "
+                                     "scan + update with mirror loss), all host threads"},
+                          "cpu_baseline": cpu,
                           "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
 
@@ -218,11 +335,18 @@ def main():
         env_fn = lambda: BatchedCassieEnv(args.envs, device=dev, seed=0, dynamics_randomization=True, env_id0=rank * args.envs)
     gen = torch.Generator(device=dev).manual_seed(1234)
 
-    # pinned host copies of the parameters: the end-to-end step ships them in and reads them (and the losses) back
+    # End-to-end step = the call a user makes (PPO.train_iteration) with host buffers on both sides: the parameters come from
+    # pinned host memory, and what a training loop reads every iteration goes back: the updated parameters (checkpoint), the
+    # loss statistics and the rollout's rewards / done flags (episode returns and lengths for the log).
     n_params = sum(p.numel() for p in actor.parameters()) + sum(p.numel() for p in critic.parameters())
     host_in = torch.zeros(n_params, dtype=torch.float32).pin_memory()
     host_out = torch.zeros(n_params, dtype=torch.float32).pin_memory()
     host_stats = torch.zeros(6, dtype=torch.float64).pin_memory()
+    T = max(1, -(-args.envs * args.horizon // args.envs))
+    host_rew = torch.zeros((T, args.envs), dtype=torch.float32).pin_memory()
+    host_done = torch.zeros((T, args.envs), dtype=torch.int32).pin_memory()
+    h2d_bytes = n_params * 4
+    d2h_bytes = n_params * 4 + 48 + host_rew.numel() * 4 + host_done.numel() * 4
 
     def step(e2e):
         if e2e:
@@ -231,6 +355,8 @@ def main():
         if e2e:
             host_out.copy_(algo.flat, non_blocking=True)
             host_stats.copy_(algo.stats, non_blocking=True)
+            host_rew.copy_(buf.rew, non_blocking=True)
+            host_done.copy_(buf.done, non_blocking=True)
             torch.cuda.current_stream().synchronize()
             host_in.copy_(host_out)
         return scal
@@ -245,33 +371,13 @@ def main():
     for _ in range(max(0, args.warmup - 1)):
         step(False)
 
-    def timed(e2e, nsteps, kernel_events=None):
+    def timed(e2e, nsteps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = algo.launches
         e0.record()
-        if kernel_events is not None:
-            orig = algo.env.step
-
-            def wrapped(*a, **k):
-                s_, t_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                s_.record(); out = orig(*a, **k); t_.record()
-                kernel_events.append((s_, t_))
-                return out
-            algo.env.step = wrapped
-            orig_sample = algo.sample_parallel
-
-            def wrapped_sample(*a, **k):  # rollout only (env + actor / critic inference + buffer writes + return scan)
-                s_, t_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                s_.record(); out = orig_sample(*a, **k); t_.record()
-                rollout_events.append((s_, t_))
-                return out
-            algo.sample_parallel = wrapped_sample
         for _ in range(nsteps):
             step(e2e)
-        if kernel_events is not None:
-            algo.env.step = orig
-            algo.sample_parallel = orig_sample
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -279,15 +385,48 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms) / nsteps, (algo.launches - l0) // nsteps
 
+    # pass 1: the headline value, K steps, nothing but the steps inside the timed region
     clocks = ClockSampler(local) if rank == 0 else None
-    kev, rollout_events = [], []
-    ms_step, launches = timed(False, args.steps, kev)
+    ms_step, launches = timed(False, args.steps)
     clk = clocks.stop() if clocks else None
-    ms_e2e, _ = timed(True, max(1, min(args.steps, 2)))
+    # pass 2: the same K steps end to end (host buffers in and out every step)
+    ms_e2e, _ = timed(True, args.steps)
+    # pass 3 (instrumentation, not part of either number): one step with CUDA events around every env-step launch and around the
+    # rollout, on the launching stream — the dominant kernel's live duration for the roofline and its share of the step
+    kev, rollout_events = [], []
+    orig_step, orig_sample = algo.env.step, algo.sample_parallel
+
+    def wrapped(*a, **k):
+        s_, t_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s_.record(); out = orig_step(*a, **k); t_.record()
+        kev.append((s_, t_))
+        return out
+
+    def wrapped_sample(*a, **k):  # rollout only (env + actor / critic inference + buffer writes + return scan)
+        s_, t_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s_.record(); out = orig_sample(*a, **k); t_.record()
+        rollout_events.append((s_, t_))
+        return out
+    algo.env.step, algo.sample_parallel = wrapped, wrapped_sample
+    ms_instr, _ = timed(False, 1)
+    algo.env.step, algo.sample_parallel = orig_step, orig_sample
     kms = [s.elapsed_time(t) for s, t in kev]
     rms = [s.elapsed_time(t) for s, t in rollout_events]
     k_ms = sum(kms) / len(kms)
     env_steps = args.envs * args.horizon * world
+
+    extras = {}
+    if not args.no_extras:
+        del algo
+        torch.cuda.empty_cache()
+        for key, fn in (("cfg3", (lambda: extra_cfg3_td3(dev)) if world == 1 else None), ("cfg4", lambda: extra_cfg4_traj(dev, rank, world)),
+                        ("cfg5", lambda: extra_cfg5_ars(dev, rank, world))):
+            if fn is None:
+                continue
+            try:
+                extras[key] = fn()
+            except Exception as e:  # an extra must never take the headline line down; every rank fails or succeeds alike
+                extras[key] = {"error": f"{type(e).__name__}: {e}"[:300]}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -298,38 +437,44 @@ def main():
     except Exception:
         pass
     peak, peak_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
-    traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_r01.json")))["dram_bytes_per_launch_4096"]
-    except Exception:
-        pass
-    issue = None
-    try:  # what actually binds the kernel (ncu --set full of the same kernel, committed summary)
-        prof = json.load(open(os.path.join(ROOT, "profiles", "ncu_envstep_r01_final.json")))
-        issue = {"issue_slots_active_pct": prof["issue_active_pct"], "busiest_pipe": "lsu", "busiest_pipe_pct": prof["pipe_pct"]["lsu"],
-                 "active_lanes_per_instruction": prof["active_lanes_per_instruction"], "source": "profiles/ncu_envstep_r01_final.json"}
+    prof = {}
+    try:  # ncu --set full of the same kernel on the same workload (committed summary): DRAM traffic, issue utilisation, flop count
+        prof = json.load(open(os.path.join(ROOT, "profiles", "roofline_r02.json")))
     except Exception:
         pass
     achieved = ALGO_BYTES_PER_ENV_STEP * args.envs / (k_ms * 1e-3) / 1e9
+    compute = None
+    if prof.get("flops_per_env_step"):
+        fl = prof["flops_per_env_step"]
+        ach = fl * args.envs / (k_ms * 1e-3) / 1e12
+        compute = {"flops_per_env_step": fl, "achieved_tflops": ach, "fp32_peak_tflops": prof.get("fp32_peak_tflops"),
+                   "frac": ach / prof["fp32_peak_tflops"] if prof.get("fp32_peak_tflops") else None,
+                   "issue_slots_active_pct": prof.get("issue_active_pct"), "source": "profiles/roofline_r02.json (instrumented oracle flop "
+                   "count; ncu issue utilisation of the committed capture)"}
     out = {"metric": "Cassie-v0 PPO env-steps/sec", "value": env_steps / (ms_step * 1e-3), "unit": "env-steps/s", "n_gpus": world,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f32" if args.precision == "f32" else "bf16 (forward hidden layers; rest f32)",
            "data": "synthetic",
            "config": {"workload": workload, "envs_per_gpu": args.envs, "horizon": args.horizon, "simrate": 50,
-                      "dynamics_randomization": True, "parallelism": f"dp{world}", "l2": "per-step state 4096 x 2.4 KB + "
+                      "dynamics_randomization": True, "parallelism": f"dp{world}", "l2": "per-step state 4096 x 2.6 KB + "
                       "210 MB rollout buffer per iteration: inputs larger than L2 (126 MB)"},
-           "e2e": {"value": env_steps / (ms_e2e * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": n_params * 4,
-                   "d2h_bytes_per_step": n_params * 4 + 48},
+           "e2e": {"value": env_steps / (ms_e2e * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": h2d_bytes,
+                   "d2h_bytes_per_step": d2h_bytes, "steps": args.steps,
+                   "note": "PPO.train_iteration with the parameters shipped from pinned host memory and parameters, loss statistics, "
+                           "rewards and done flags read back to the host every step"},
            "gpu_launches": launches, "clocks": clk,
            "rollout_only": {"value": args.envs * args.horizon * world / (sum(rms) / len(rms) * 1e-3), "unit": "env-steps/s",
-                            "ms": sum(rms) / len(rms), "note": "rank 0's device time of sample_parallel inside the timed steps"},
+                            "ms": sum(rms) / len(rms), "note": "rank 0's device time of sample_parallel in the instrumented step"},
            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                        "traffic": traffic, "kernel": "k_env_step<float>", "kernel_ms": k_ms, "peak_source": peak_src,
-                        "kernel_share_of_step": sum(kms) / args.steps / ms_step, "compute_side": issue,
-                        "note": "dynamics kernel is FP32-issue/latency bound (SURVEY.md §8d): HBM fraction is expected << 1%"}}
-    if not args.no_cpu_baseline:
+                        "traffic": prof.get("dram_bytes_per_launch_4096"), "kernel": "k_env_step<float>", "kernel_ms": k_ms,
+                        "peak_source": peak_src, "kernel_share_of_step": sum(kms) / ms_instr, "compute": compute,
+                        "note": "kernel_ms and the share come from a separate instrumented step (CUDA events around each launch); "
+                                "the dynamics kernel is FP32-issue/latency bound (SURVEY.md §8d): HBM fraction is expected << 1%"}}
+    out.update(extras)
+    if not args.no_cpu_baseline and world == 1:
         v, cores, sample, _ = cpu_arm(1, 1)
-        out["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample}
+        out["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample,
+                               "reference_python": reference_python_arm()}
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

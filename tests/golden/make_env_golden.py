@@ -26,7 +26,7 @@ import types
 
 import numpy as np
 
-REF = "/root/reference"
+REF = os.environ.get("APEX_REF_ROOT", "/root/reference")  # tools/ref_python_arm.py points this at baseline/_ref on the GPU box
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 
