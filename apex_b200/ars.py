@@ -38,9 +38,25 @@ class Linear_Actor(nn.Module):
         return self.action
 
 
+def shard_of(idx_all, rank, world):
+    """This rank's contiguous share of the job's direction indices (every rank draws the same index stream)."""
+    local = idx_all.shape[0] // world
+    return idx_all[rank * local:(rank + 1) * local]
+
+
+def gather_direction_returns(r):
+    """[local_deltas, 2] (+, -) returns of this rank -> [deltas, 2] of the whole job, in direction order (rank-major, matching
+    shard_of).  The one exchange of an ARS iteration."""
+    if not (dist.is_initialized() and dist.get_world_size() > 1):
+        return r
+    allr = [torch.zeros_like(r) for _ in range(dist.get_world_size())]
+    dist.all_gather(allr, r.contiguous())
+    return torch.cat(allr, dim=0)
+
+
 class ARS:
     def __init__(self, policy_thunk, env_thunk, step_size=0.02, std=0.0075, deltas=32, workers=4, top_n=None, seed=0,
-                 redis_addr=None, rollouts=1, noise_count=25000000):
+                 redis_addr=None, rollouts=1, noise_count=25000000, noise=None):
         self.std, self.num_deltas, self.step_size = std, deltas, step_size
         self.top_n = deltas if top_n is None else top_n
         self.rollouts = rollouts
@@ -62,8 +78,11 @@ class ARS:
             p.data = self.theta[off:off + n].view(p.shape)
             off += n
         self.S, self.H, self.A = self.policy.l1.in_features, self.policy.l1.out_features, self.policy.l2.out_features
-        g = torch.Generator(device=dev).manual_seed(seed)
-        self.noise = torch.randn(noise_count, generator=g, device=dev, dtype=torch.float32) * std  # create_shared_noise
+        if noise is not None:  # a caller-supplied table (already scaled by std, like create_shared_noise's): parity tests
+            self.noise = torch.as_tensor(noise, dtype=torch.float32, device=dev).contiguous()
+        else:
+            g = torch.Generator(device=dev).manual_seed(seed)
+            self.noise = torch.randn(noise_count, generator=g, device=dev, dtype=torch.float32) * std  # create_shared_noise
         self.idx_gen = torch.Generator(device="cpu").manual_seed(seed + 7)
         n = self.env.num_envs
         e = torch.arange(n, device=dev)
@@ -81,7 +100,7 @@ class ARS:
         env, dev, n = self.env, self.device, self.env.num_envs
         # SharedNoiseTable.get_random_idx for every direction of the whole job (same stream on every rank)
         idx_all = torch.randint(0, self.noise.numel() - self.P + 1, (self.num_deltas,), generator=self.idx_gen, dtype=torch.int64)
-        idx_loc = idx_all[self.rank * self.local_deltas:(self.rank + 1) * self.local_deltas].to(dev)
+        idx_loc = shard_of(idx_all, self.rank, self.world).to(dev)
         idx_all = idx_all.to(dev)
         env.max_traj_len = 0  # no auto-reset: one episode per env
         obs = env.reset()
@@ -116,14 +135,17 @@ class ARS:
                 self._live_event.record()
                 pending = True
         r = ret.view(self.local_deltas, 2, self.rollouts).mean(dim=2)  # [dir, (+, -)]
+        r = gather_direction_returns(r)
+        tot = steps.sum().clone()
         if self.world > 1:
-            allr = [torch.zeros_like(r) for _ in range(self.world)]
-            dist.all_gather(allr, r)
-            r = torch.cat(allr, dim=0)
-            tot = steps.sum().clone()
             dist.all_reduce(tot)
-        else:
-            tot = steps.sum()
+        self.update(idx_all, r)
+        return int(tot)
+
+    @torch.no_grad()
+    def update(self, idx_all, r):
+        """ars.py:141-156: theta += step_size / (top_n * std(r+ U r-) * std) * sum_d (r+_d - r-_d) delta_d with delta_d =
+        noise[idx_d : idx_d + P]; `r` is the [deltas, 2] table of (+, -) returns of the whole job."""
         self.last_returns = r
         r_pos, r_neg = r[:, 0], r[:, 1]
         r_std = r.reshape(-1).std(unbiased=False)  # np.std(r_pos + r_neg): concatenated lists, population std
@@ -134,7 +156,6 @@ class ARS:
             mask[keep] = 1.0
             weight = weight * mask
         coef = float(self.step_size / (self.top_n * float(r_std) * self.std))
-        _capi.check(L.apex_ars_update(self.theta.data_ptr(), self.P, self.noise.data_ptr(), idx_all.data_ptr(),
-                                      weight.contiguous().data_ptr(), self.num_deltas, coef, s), "ars_update")
+        _capi.check(self.L.apex_ars_update(self.theta.data_ptr(), self.P, self.noise.data_ptr(), idx_all.data_ptr(),
+                                           weight.contiguous().data_ptr(), self.num_deltas, coef, self._s()), "ars_update")
         self.launches += 1
-        return int(tot)

@@ -85,9 +85,9 @@ class PPO:
         self.gamma = args.get("gamma", 0.99)
         # The reference parses --lam (default 0.95) and never uses it: its returns are gamma-discounted Monte-Carlo sums with a
         # bootstrap, i.e. lam = 1 (ppo.py:73-89).  Passing the reference's args dict must therefore not change the returns:
-        # `lam` is honoured only together with an explicit use_gae=True (not a reference flag).
-        self.use_gae = bool(args.get("use_gae", False))
-        self.lam = float(args.get("lam", 1.0)) if self.use_gae else 1.0
+        # neither `lam` nor the reference's (equally unused) `use_gae` flag has any effect; GAE(lambda) is an explicit opt-in under
+        # a key the reference does not have: apex_gae_lambda.
+        self.lam = float(args.get("apex_gae_lambda", 1.0))
         self.lr = args.get("lr", 1e-4)
         self.eps = args.get("eps", 1e-5)
         self.entropy_coeff = args.get("entropy_coeff", 0.0)
@@ -357,6 +357,87 @@ class PPO:
         self.total_steps += len(buf) * self.world
         return buf, self.optimize(buf, generator)
 
+    def train(self, env_fn, policy, critic, n_itr, logger=None, anneal_rate=1.0):
+        """rl/algos/ppo.py:347-505 on the batched backend: per iteration the exploration-noise anneal (:385-386) and the
+        termination-threshold curriculum (:387-388, 458-462; the env ignores the threshold, as the reference's does), a rollout of
+        num_steps, advantage normalisation, `epochs` of shuffled minibatches with the KL early stop, an evaluation rollout of
+        num_steps // 2 (`deterministic=True` is ignored by the reference's sample(): the evaluation is stochastic there too), the
+        thirteen scalars under the reference's tags, and actor.pt / critic.pt whenever the evaluation return improves."""
+        import time
+        from .log import log_ppo_iteration
+        curr_anneal, curr_thresh, start_itr, ep_counter, do_term = 1.0, 0.0, 0, 0, False
+        start = time.time()
+        gen = None
+        for itr in range(n_itr):
+            print("********** Iteration {} ************".format(itr))
+            t0 = time.time()
+            if self.highest_reward > (2 / 3) * self.max_traj_len and curr_anneal > 0.5:
+                curr_anneal *= anneal_rate
+            if do_term and curr_thresh < 0.35:
+                curr_thresh = .1 * 1.0006 ** (itr - start_itr)
+            batch = self.sample_parallel(env_fn, policy, critic, self.num_steps, self.max_traj_len, anneal=curr_anneal, term_thresh=curr_thresh)
+            torch.cuda.synchronize(self.device)
+            if gen is None:
+                gen = torch.Generator(device=self.device).manual_seed(self.seed + 1)
+            samp_time = time.time() - t0
+            print("time elapsed: {:.2f} s".format(time.time() - start))
+            print("sample time elapsed: {:.2f} s".format(samp_time))
+            self.normalize_advantages(batch)
+            print("timesteps in batch: %i" % (len(batch) * self.world))
+            self.total_steps += len(batch) * self.world
+            t0 = time.time()
+            losses, kl, entropy = [], 0.0, 0.0
+            n, mb = len(batch), min(self.minibatch_size or len(batch), len(batch))
+            for epoch in range(self.epochs):
+                perm = torch.randperm(n, device=self.device, generator=gen)
+                acc = torch.zeros(6, dtype=torch.float64, device=self.device)
+                cnt = 0
+                for i in range(0, n - mb + 1, mb):
+                    self.update_minibatch(batch, perm[i:i + mb])
+                    acc += self.stats  # sums of this rank's minibatches; the epoch mean is formed once, below
+                    cnt += 1
+                last = self.minibatch_scalars()  # (all-reduced) scalars of the epoch's last minibatch: the early-stop KL (:449)
+                if self.world > 1:
+                    dist.all_reduce(acc)
+                a = acc.tolist()
+                c = max(a[5], 1.0)
+                losses = [-a[0] / c, last[1], a[1] / c, a[2] / c, a[3] / (c * self.act_dim), self.mirror_coeff * a[4] / (c * self.act_dim)]
+                print(' '.join(["%g" % x for x in losses]))
+                kl, entropy = last[4], last[1]
+                if self.max_kl is not None and kl > self.max_kl:
+                    print("Max kl reached, stopping optimization early.")
+                    break
+            torch.cuda.synchronize(self.device)
+            opt_time = time.time() - t0
+            print("optimizer time elapsed: {:.2f} s".format(opt_time))
+            ep_lens, ep_rets = batch.ep_lens, batch.ep_returns
+            avg_ep_len = float(np.mean(ep_lens)) if ep_lens else float(self.max_traj_len)
+            avg_batch_reward = float(np.mean(ep_rets)) if ep_rets else float("nan")
+            if avg_ep_len >= self.max_traj_len * 0.75:
+                ep_counter += 1
+            if not do_term and ep_counter > 50:
+                do_term, start_itr = True, itr
+            t0 = time.time()
+            main_buf, self.buf = self.buf, getattr(self, "_eval_buf", None)  # the evaluation rollout has its own (shorter) buffer
+            test = self.sample_parallel(env_fn, policy, critic, self.num_steps // 2, self.max_traj_len, deterministic=True)
+            test_rets = test.ep_returns
+            self._eval_buf, self.buf = self.buf, main_buf
+            torch.cuda.synchronize(self.device)
+            eval_time = time.time() - t0
+            print("evaluate time elapsed: {:.2f} s".format(eval_time))
+            avg_eval_reward = float(np.mean(test_rets)) if test_rets else float("nan")
+            sys_out = ("-" * 37 + "\n" + "| %15s | %15s |\n" * 5 + "-" * 37 + "\n") % (
+                'Return (test)', avg_eval_reward, 'Return (batch)', avg_batch_reward, 'Mean Eplen', avg_ep_len, 'Mean KL Div', "%8.3g" % kl,
+                'Mean Entropy', "%8.3g" % entropy)
+            print(sys_out, end="")
+            if logger is not None and self.rank == 0:
+                log_ppo_iteration(logger, itr, avg_eval_reward, avg_batch_reward, avg_ep_len, kl, entropy, losses[2], losses[0], losses[5],
+                                  self.total_steps, samp_time, opt_time, eval_time, curr_thresh)
+            if self.highest_reward < avg_eval_reward:
+                self.highest_reward = avg_eval_reward
+                if self.save_path is not None and self.rank == 0:
+                    self.save(policy, critic)
+
     def save(self, policy, critic):
         """rl/algos/ppo.py:129-137: whole-module actor.pt / critic.pt, written under the reference's class names so that the
         reference's tools (apex.py eval, tools/*) open them with their own code (policies.save_reference_checkpoint)."""
@@ -364,3 +445,56 @@ class PPO:
         os.makedirs(self.save_path, exist_ok=True)
         save_reference_checkpoint(policy, os.path.join(self.save_path, "actor.pt"))
         save_reference_checkpoint(critic, os.path.join(self.save_path, "critic.pt"))
+
+
+def run_experiment(args):
+    """rl/algos/ppo.py:507-584 on the batched backend, driven by the reference's `apex.py ppo` argument namespace (same names).
+    What differs: `num_procs` becomes the env batch only through apex_num_envs (default 4096 envs on this rank's GPU) — the
+    rollout horizon is ceil(num_steps / num_envs) steps of every env — and recurrent / learn_stddev / bounded are refused (LSTM
+    policies and a learned std are outside the hot path)."""
+    from .envs import env_factory
+    from .log import create_logger
+    from .normalize import get_normalization_params
+    from .policies import Gaussian_FF_Actor, FF_V, load_reference_checkpoint
+    if getattr(args, "recurrent", False) or getattr(args, "learn_stddev", False) or getattr(args, "bounded", False):
+        raise NotImplementedError("recurrent / learn_stddev / bounded policies are not on the B200 path")
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    dev = torch.device("cuda", torch.cuda.current_device())
+    n_envs = int(getattr(args, "apex_num_envs", 4096))
+    env_fn = env_factory(args.env_name, simrate=args.simrate, command_profile=args.command_profile, input_profile=args.input_profile,
+                         learn_gains=args.learn_gains, dynamics_randomization=args.dyn_random, reward=args.reward, history=args.history,
+                         mirror=args.mirror, ik_baseline=args.ik_baseline, no_delta=args.no_delta, traj=args.traj, num_envs=n_envs,
+                         trajectory=getattr(args, "apex_trajectory", None), device=dev, seed=args.seed, env_id0=rank * n_envs)
+    probe = env_fn()
+    obs_dim, action_dim = probe.observation_space.shape[0], probe.action_space.shape[0]
+    del probe
+    torch.manual_seed(args.seed)
+    np.random.seed(args.seed)
+    if getattr(args, "previous", None) is not None:
+        policy = load_reference_checkpoint(os.path.join(args.previous, "actor.pt"))
+        critic = load_reference_checkpoint(os.path.join(args.previous, "critic.pt"))
+        print("loaded model from {}".format(args.previous))
+    else:
+        policy = Gaussian_FF_Actor(obs_dim, action_dim, fixed_std=torch.ones(action_dim) * float(np.exp(args.std_dev)), env_name=args.env_name)
+        critic = FF_V(obs_dim)
+        with torch.no_grad():
+            mean, std = get_normalization_params(iter=args.input_norm_steps, noise_std=1, policy=policy, env_fn=env_fn, procs=args.num_procs,
+                                                 seed=args.seed)
+        policy.obs_mean, policy.obs_std = torch.Tensor(mean), torch.Tensor(std)
+        critic.obs_mean, critic.obs_std = policy.obs_mean, policy.obs_std
+    policy.train()
+    critic.train()
+    print("obs_dim: {}, action_dim: {}".format(obs_dim, action_dim))
+    logger = create_logger(args) if rank == 0 else None
+    algo = PPO(args=vars(args), save_path=logger.dir if logger is not None else None)
+    print()
+    print("Synchronous Distributed Proximal Policy Optimization (batched envs on the GPU):")
+    for k in ("run_name", "max_traj_len", "seed", "lr", "eps", "lam", "gamma", "std_dev", "entropy_coeff", "clip", "minibatch_size", "epochs",
+              "num_steps", "use_gae", "max_grad_norm"):
+        print(" | {:15s} {}".format(k + ":", getattr(args, k, None)))
+    print(" | {:15s} {}".format("envs per GPU:", n_envs))
+    print()
+    algo.train(env_fn, policy, critic, args.n_itr, logger=logger, anneal_rate=args.anneal)
+    if logger is not None:
+        logger.close()
+    return algo, policy, critic

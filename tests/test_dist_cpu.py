@@ -89,3 +89,34 @@ def test_two_rank_sharded_eval_commands():
     out = mgr.dict()
     mp.spawn(_eval_worker, args=(world, port, out), nprocs=world, join=True)
     assert all(out[r] for r in range(world))
+
+
+def _ars_worker(rank, port, out):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=2)
+    # ARS.step's exchange, through the functions it calls (apex_b200/ars.py): directions sharded by rank, [local, 2] return tables
+    # all-gathered in direction order; every rank draws the same index stream and slices its own share
+    from apex_b200.ars import gather_direction_returns, shard_of
+    deltas = 8
+    gen = torch.Generator(device="cpu").manual_seed(10)
+    idx_all = torch.randint(0, 1000, (deltas,), generator=gen, dtype=torch.int64)
+    idx_loc = shard_of(idx_all, rank, 2)
+    r = torch.stack([idx_loc.double() * 0.5, idx_loc.double() * 0.25], dim=1)  # returns that identify their direction
+    full = gather_direction_returns(r)
+    ok = bool(torch.equal(full[:, 0], idx_all.double() * 0.5)) and bool(torch.equal(full[:, 1], idx_all.double() * 0.25))
+    out[rank] = ok
+    dist.destroy_process_group()
+
+
+def test_ars_return_table_gathers_in_direction_order():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    out = ctx.Manager().dict()
+    port = 29600 + os.getpid() % 1000
+    ps = [ctx.Process(target=_ars_worker, args=(r, port, out)) for r in range(2)]
+    for p in ps:
+        p.start()
+    for p in ps:
+        p.join(timeout=120)
+    assert all(p.exitcode == 0 for p in ps) and out[0] and out[1]

@@ -75,3 +75,12 @@ def test_replay_buffer_ring_and_gather():
     row = rb.storage[idx]
     assert torch.equal(st, row[:, :4]) and torch.equal(nx, row[:, 4:8]) and torch.equal(sa, torch.cat([row[:, :4], row[:, 8:10]], 1))
     assert torch.equal(r, row[:, 10]) and torch.equal(nd, 1 - row[:, 11])
+
+
+def test_td3_train_matches_reference_with_float64_replay_actions():
+    """The reference's real collection path stores float64 actions (sync_td3.py:77), so torch.FloatTensor(u) copies and the
+    critics see Q(s, a): TD3.train's default (reference_action_alias=False) against tests/golden/td3_update_f64act.npz."""
+    g = np.load(os.path.join(G, "td3_update_f64act.npz"))
+    algo, q_loss = _run_td3(g, 2, alias=False)
+    assert abs(q_loss - float(g["q_loss"])) < 1e-4 * max(1.0, abs(float(g["q_loss"]))), (q_loss, float(g["q_loss"]))
+    _check_params(g, algo, 2)
