@@ -1357,7 +1357,7 @@ template <typename T> CW_NOINL void cw_mj_step(CassieWs<T> &w, bool integrate, i
       /* Blocked Gauss-Seidel, same update sequence as mj_solPGS.  The row update in increment form:
        * new f = max(f - res / A_ii, lb)  <=>  df = max(s, g) with s = res * (-1 / A_ii) and g = lb - f (-3e38 for the unbounded
        * equality rows, -f for the rows with f >= 0).  Every lane keeps its residual pre-scaled (s) and its column of A scaled
-       * by its own -1 / A_ii.  Rows are taken four at a time: ONE round of shuffles gathers the four s, every lane then runs the
+       * by its own -1 / A_ii.  Rows are taken four at a time: ONE gather fetches the four s, every lane then runs the
        * four dependent row steps in its own registers (the 4 x 4 diagonal block of A, pre-scaled like the columns, and the rows'
        * g are read from shared memory with uniform 16-byte loads) and finally applies the four increments to its own s.
        * The dependent chain per row is one FMA and one MAX instead of a shuffle round trip.  The connect rows (0 .. 11: whenever
@@ -1381,6 +1381,8 @@ template <typename T> CW_NOINL void cw_mj_step(CassieWs<T> &w, bool integrate, i
 #pragma unroll
       for (int i = 0; i < CW_NEFC; i++) acol[i] *= ndi0;
       __syncwarp();
+      T *const sbuf = w.efc_dinv; /* consumed above (di0) */
+      (void)sbuf;
       const int myblk = lane >> 2;
       const bool j1 = (lane & 3) == 1, j2 = (lane & 3) == 2, j3 = (lane & 3) == 3;
       for (int it = 0; it < CM_ITERATIONS; it++) {
@@ -1388,8 +1390,18 @@ template <typename T> CW_NOINL void cw_mj_step(CassieWs<T> &w, bool integrate, i
 #pragma unroll
         for (int k = 0; k < CW_NEFC / 4; k++) {
           if (4 * k >= n) break;
+#ifndef CW_PGS_GATHER_SHFL /* the four residuals of the block through shared memory: one store and one 16-byte uniform load
+                            * instead of four shuffles (measured 1.4 % faster on the whole kernel) */
+          sbuf[lane] = sres;
+          __syncwarp();
+          T rr4[4];
+          cw_ld4(rr4, sbuf + 4 * k);
+          const T r0 = rr4[0], r1 = rr4[1], r2 = rr4[2], r3 = rr4[3];
+          __syncwarp();
+#else
           const T r0 = __shfl_sync(0xffffffffu, sres, 4 * k), r1 = __shfl_sync(0xffffffffu, sres, 4 * k + 1);
           const T r2 = __shfl_sync(0xffffffffu, sres, 4 * k + 2), r3 = __shfl_sync(0xffffffffu, sres, 4 * k + 3);
+#endif
           const T *pb = pblk[k];
           T s1 = r1, s2 = r2, s3 = r3, d0, d1, d2, d3;
           if (k < 3) { /* equality rows: df = s */
