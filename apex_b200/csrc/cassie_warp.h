@@ -840,8 +840,26 @@ template <typename T> CW_FN void cw_collision(CassieWs<T> &w CW_LANE_PARAM) {
     }
   }
   CW_SYNC();
-  /* uniform compaction in priority order */
-  int nc = 0;
+  /* compaction in priority order */
+  int nc = 0, npen = 0; /* npen: penetrating candidates; more than were seated = capacity overflow (recorded by cw_make_constraint) */
+#ifdef __CUDA_ARCH__
+  { /* device: one ballot finds the penetrating candidates; lane c builds contact c from the c-th of them, all contacts at once */
+    const unsigned pen = __ballot_sync(0xffffffffu, lane < 26 && w.u.p.cand_dist[lane] < 0);
+    npen = __popc(pen);
+    nc = npen < CW_NCON ? npen : CW_NCON;
+    if (lane < nc) {
+      const int s = (int)__fns(pen, 0, lane + 1);
+      T fr[9];
+      for (int k = 0; k < 3; k++) { w.con_pos[lane][k] = w.u.p.cand_pos[s][k]; fr[k] = w.u.p.cand_n[s][k]; fr[3 + k] = w.u.p.cand_hint[s][k]; fr[6 + k] = 0; }
+      cw_make_frame(fr);
+      for (int k = 0; k < 9; k++) w.con_frame[lane][k] = fr[k];
+      w.con_dist[lane] = w.u.p.cand_dist[s];
+      if (s < 17) { w.con_geom[lane] = CW_CAND_GEOM[s]; w.con_geom1[lane] = -1; w.con_dim[lane] = 3; w.con_mu[lane] = w.st[S_FRICTION]; }
+      else { w.con_geom[lane] = CW_PAIR_G2[s - 17]; w.con_geom1[lane] = CW_PAIR_G1[s - 17]; w.con_dim[lane] = 1; w.con_mu[lane] = 0; }
+      w.con_adr[lane] = -1;
+    }
+  }
+#else
   for (int s = 0; s < 26 && nc < CW_NCON; s++) {
     if (w.u.p.cand_dist[s] < 0) {
       CW_FOR_LANES {
@@ -859,10 +877,6 @@ template <typename T> CW_FN void cw_collision(CassieWs<T> &w CW_LANE_PARAM) {
       nc++;
     }
   }
-  int npen = 0; /* penetrating candidates: more than were seated = capacity overflow (recorded by cw_make_constraint) */
-#ifdef __CUDA_ARCH__
-  npen = __popc(__ballot_sync(0xffffffffu, lane < 26 && w.u.p.cand_dist[lane] < 0));
-#else
   for (int s = 0; s < 26; s++) npen += w.u.p.cand_dist[s] < 0 ? 1 : 0;
 #endif
   CW_FOR_LANES { if (lane == 0) { w.ncon = nc; w.dropped = npen > nc ? 1 : 0; } }
@@ -905,6 +919,24 @@ template <typename T> CW_FN void cw_make_constraint(CassieWs<T> &w, const T *qpo
       if (nckeep < w.ncon) dropped = 1;
     }
     /* joint limits */
+#ifdef __CUDA_ARCH__
+    { /* device: lane = (limited joint, side) pair in the reference order; one ballot, then only the violated ones are visited */
+      const int jl = CW_LIM_JNT[lane >> 1], sidel = (lane & 1) ? 1 : -1;
+      const T distl = (T)sidel * ((T)CMT(jnt_range)[jl][lane & 1] - qpos[CM_jnt_qposadr[jl]]);
+      unsigned viol = __ballot_sync(0xffffffffu, distl < 0);
+      while (viol) {
+        const int l = cw_ctz(viol);
+        viol &= viol - 1;
+        if (r + crows < CW_NEFC) {
+          const int da = CM_jnt_dofadr[CW_LIM_JNT[l >> 1]];
+          const T dist = __shfl_sync(0xffffffffu, distl, l);
+          w.u.J[r][lane] = (lane == da) ? ((l & 1) ? (T)-1 : (T)1) : (T)0;
+          if (lane == 0) { w.efc_aref[r] = dist; w.efc_R[r] = w.st[S_DOFINVW + da]; w.efc_type[r] = 1; }
+          r++;
+        } else dropped = 1;
+      }
+    }
+#else
 #pragma unroll
     for (int l = 0; l < 16; l++) {
       const int j = CW_LIM_JNT[l];
@@ -921,6 +953,7 @@ template <typename T> CW_FN void cw_make_constraint(CassieWs<T> &w, const T *qpo
         } else if (dist < 0) dropped = 1;
       }
     }
+#endif
     /* contacts */
     const int nc = nckeep;
     for (int c = 0; c < nc; c++) {
