@@ -177,7 +177,7 @@ struct CassieWs {
   T efc_res[CW_NEFC]; /* host test build only: on the GPU the PGS residual lives in registers */
 #endif
   int efc_type[CW_NEFC];
-  T vec[V_NVEC][CW_NV];
+  alignas(16) T vec[V_NVEC][CW_NV];
   int ncon, nefc, solver_iter;
   int dropped; /* this sub-step lost a contact or a limit row to the capacity (see I_OVERFLOW) */
   int bar_mask; /* CTA synchronisation inside a sub-step (CW_BAR_* / CW_SPLIT bits), GPU build: keeps the CTA's warps on the same code */
@@ -1414,23 +1414,27 @@ template <typename T> CW_NOINL void cw_mj_step(CassieWs<T> &w, bool integrate, i
 #pragma unroll
       for (int i = 0; i < CW_NEFC; i++) acol[i] *= ndi0;
       __syncwarp();
-      T *const sbuf = w.efc_dinv; /* consumed above (di0) */
+      T *const sbuf = w.vec[V_G]; /* V_G and V_TMP (64 words): the warm start is consumed, g = B^T f is formed after the solver */
+      T *const sown = w.efc_dinv; /* consumed above (di0) */
       (void)sbuf;
       const int myblk = lane >> 2;
+#ifdef CW_PGS_CAPTURE_SEL
       const bool j1 = (lane & 3) == 1, j2 = (lane & 3) == 2, j3 = (lane & 3) == 3;
+#endif
       for (int it = 0; it < CM_ITERATIONS; it++) {
         T s_own = 0;
 #pragma unroll
         for (int k = 0; k < CW_NEFC / 4; k++) {
           if (4 * k >= n) break;
 #ifndef CW_PGS_GATHER_SHFL /* the four residuals of the block through shared memory: one store and one 16-byte uniform load
-                            * instead of four shuffles (measured 1.4 % faster on the whole kernel) */
-          sbuf[lane] = sres;
+                            * instead of four shuffles (measured 1.4 % faster on the whole kernel); two buffers alternate, so
+                            * the barrier of block k + 1 also orders block k's loads before the stores of block k + 2 */
+          T *const sb = sbuf + 32 * (k & 1);
+          sb[lane] = sres;
           __syncwarp();
           T rr4[4];
-          cw_ld4(rr4, sbuf + 4 * k);
+          cw_ld4(rr4, sb + 4 * k);
           const T r0 = rr4[0], r1 = rr4[1], r2 = rr4[2], r3 = rr4[3];
-          __syncwarp();
 #else
           const T r0 = __shfl_sync(0xffffffffu, sres, 4 * k), r1 = __shfl_sync(0xffffffffu, sres, 4 * k + 1);
           const T r2 = __shfl_sync(0xffffffffu, sres, 4 * k + 2), r3 = __shfl_sync(0xffffffffu, sres, 4 * k + 3);
@@ -1458,11 +1462,19 @@ template <typename T> CW_NOINL void cw_mj_step(CassieWs<T> &w, bool integrate, i
           sres = cw_fma_rn(d1, acol[4 * k + 1], sres);
           sres = cw_fma_rn(d2, acol[4 * k + 2], sres);
           sres = cw_fma_rn(d3, acol[4 * k + 3], sres);
+#ifdef CW_PGS_CAPTURE_SEL
           T ss = j1 ? s1 : r0;
           ss = j2 ? s2 : ss;
           ss = j3 ? s3 : ss;
           s_own = myblk == k ? ss : s_own;
+#else
+          if (lane == 0) { const T at_step[4] = {r0, s1, s2, s3}; cw_st4(sown + 4 * k, at_step); } /* what each row saw at its step */
+#endif
         }
+#ifndef CW_PGS_CAPTURE_SEL
+        __syncwarp();
+        s_own = v0 ? sown[lane] : (T)0;
+#endif
         /* the lane's own row: same expression, same operands as at its step inside the block */
         const T dlo = cw_max(s_own, g0);
         T imp = dlo * aii0 * (s_own - (T)0.5 * dlo); /* = -dl (0.5 A_ii dl + res) with res = -s A_ii */
