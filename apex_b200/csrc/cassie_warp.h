@@ -1481,11 +1481,22 @@ template <typename T> CW_NOINL void cw_mj_step(CassieWs<T> &w, bool integrate, i
         f0 += dlo;
         if (bounded) { f0 = cw_max(f0, (T)0); g0 = -f0; pblk[myblk][8 + (lane & 3)] = g0; }
         iters = it + 1;
+#ifdef CW_PGS_BUTTERFLY
         for (int o = 16; o > 0; o >>= 1) imp += __shfl_xor_sync(0xffffffffu, imp, o);
+        const bool converged = imp * scale < (T)1e-8;
+#else
+        /* sum over the rows of improvement * scale < 1e-8, decided in fixed point with ONE warp reduction (redux.sync) instead of
+         * a 5-stage shuffle butterfly: each row's (non-negative) term is truncated to a multiple of 2^-50 and capped at 2^-24
+         * (a row at the cap alone is 6e-8 > 1e-8, so capping never turns "continue" into "stop"); the truncation moves the sum
+         * by < 32 * 2^-50 = 3e-14, far below the float64 rounding noise of the sweep itself relative to the 1e-8 threshold */
+        const T qs = cw_min(cw_max(imp * scale, (T)0) * (T)1125899906842624.0, (T)67108864.0); /* 2^50, 2^26 */
+        const unsigned total = __reduce_add_sync(0xffffffffu, (unsigned)qs);
+        const bool converged = total < 11258999u; /* 1e-8 * 2^50 = 11258999.07 */
+#endif
 #ifdef CW_EXP_FIXED_SWEEPS /* timing experiment only (tools/build_variant.sh): every env runs the same number of sweeps */
         if (it + 1 >= CW_EXP_FIXED_SWEEPS) break;
 #else
-        if (imp * scale < (T)1e-8) break;
+        if (converged) break;
 #endif
         __syncwarp();
       }
