@@ -1485,13 +1485,18 @@ template <typename T> CW_NOINL void cw_mj_step(CassieWs<T> &w, bool integrate, i
         for (int o = 16; o > 0; o >>= 1) imp += __shfl_xor_sync(0xffffffffu, imp, o);
         const bool converged = imp * scale < (T)1e-8;
 #else
-        /* sum over the rows of improvement * scale < 1e-8, decided in fixed point with ONE warp reduction (redux.sync) instead of
-         * a 5-stage shuffle butterfly: each row's (non-negative) term is truncated to a multiple of 2^-50 and capped at 2^-24
-         * (a row at the cap alone is 6e-8 > 1e-8, so capping never turns "continue" into "stop"); the truncation moves the sum
-         * by < 32 * 2^-50 = 3e-14, far below the float64 rounding noise of the sweep itself relative to the 1e-8 threshold */
-        const T qs = cw_min(cw_max(imp * scale, (T)0) * (T)1125899906842624.0, (T)67108864.0); /* 2^50, 2^26 */
-        const unsigned total = __reduce_add_sync(0xffffffffu, (unsigned)qs);
-        const bool converged = total < 11258999u; /* 1e-8 * 2^50 = 11258999.07 */
+        /* sum over the rows of improvement * scale < 1e-8, decided in fixed point with two warp reductions (redux.sync) instead
+         * of a 5-stage shuffle butterfly.  Each row's (non-negative) term x = improvement * scale * 2^50 is capped at 2^26 (a row
+         * at the cap alone is 6e-8 > 1e-8, so capping never turns "continue" into "stop") and split into trunc(x) and
+         * trunc(frac(x) * 2^24); the two sums give the total to 32 units of 2^-74, i.e. to 3e-14 of the threshold: the sweep
+         * count can differ from the unquantised test's about once in 1e13 solves. */
+        const T xq = cw_min(cw_max(imp * scale, (T)0) * (T)1125899906842624.0, (T)67108864.0); /* 2^50, 2^26 */
+        const unsigned qhi = (unsigned)xq;
+        const unsigned qlo = (unsigned)((xq - (T)qhi) * (T)16777216.0); /* 2^24 */
+        const unsigned thi = __reduce_add_sync(0xffffffffu, qhi), tlo = __reduce_add_sync(0xffffffffu, qlo);
+        /* 1e-8 * 2^50 = 11258999.0684...: 0.06842624 * 2^24 = 1148001.8 */
+        const unsigned long long tot = ((unsigned long long)thi << 24) + tlo;
+        const bool converged = tot < ((11258999ull << 24) + 1148002ull);
 #endif
 #ifdef CW_EXP_FIXED_SWEEPS /* timing experiment only (tools/build_variant.sh): every env runs the same number of sweeps */
         if (it + 1 >= CW_EXP_FIXED_SWEEPS) break;
