@@ -38,8 +38,8 @@ template <typename T> CW_NOINL void cw_sim_step_pd(CassieWs<T> &w, int bar CW_LA
       const T ucmd = (T)0 + pg * (w.st[S_UPTARGET + i] - w.st[S_OMPOS + i]) + dg * ((T)0 - w.st[S_OMVEL + i]);
       /* motor model, @0x7d30-0x7eaa */
       const T wv = w.st[S_SENS_ACTVEL + i], wmax = (T)CMT(act_rpm)[i] * (T)CW_TWO_PI / (T)60.0, tmax = (T)CMT(act_ctrlmax)[i];
-      const T tlim = cw_max(cw_min(2 * tmax * (1 - cw_abs(wv) / wmax), tmax), (T)0);
-      T tau = cw_min(cw_abs(ucmd / gear), tlim);
+      const T tlim = cw_max(cw_min(2 * tmax * (1 - cw_div(cw_abs(wv), wmax)), tmax), (T)0);
+      T tau = cw_min(cw_abs(cw_div(ucmd, gear)), tlim);
       if (ucmd < 0 || (ucmd == 0 && 1 / ucmd < 0)) tau = -tau; /* copysign */
       T *dl = w.st + S_DELAY + 6 * i;
       for (int k = 5; k > 0; k--) dl[k] = dl[k - 1];
@@ -55,8 +55,8 @@ template <typename T> CW_NOINL void cw_sim_step_pd(CassieWs<T> &w, int bar CW_LA
       hist[0] = c;
       uint32_t acc = 0;
       for (int k = 0; k < 9; k++) acc += (uint32_t)CW_FIR_W[k] * (uint32_t)hist[k];
-      const T mpos = (T)c * ((T)CW_TWO_PI / N) / gear;
-      const T mvel = (T)(int32_t)acc * ((T)CW_TWO_PI / N / gear) / (T)CW_PI;
+      const T mpos = cw_div((T)c * ((T)CW_TWO_PI / N), gear);
+      const T mvel = cw_div((T)(int32_t)acc * cw_div((T)CW_TWO_PI / N, gear), (T)CW_PI);
       w.st[S_OMPOS + i] = mpos; w.st[S_OMVEL + i] = mvel;
       w.y[Y_MPOS + i] = mpos; w.y[Y_MVEL + i] = mvel;
     } else if (lane < CM_NU + 6) {
@@ -471,7 +471,7 @@ template <typename T> CW_NOINL void cw_env_step(CassieWs<T> &w, T *obs_out, T *r
     for (int k = 0; k < 6; k++) fp0[k] = w.st[S_FOOTPOS + k];
     cw_sim_step_pd<T>(w, bar CW_LANE_ARG);
     cw_foot_positions<T>(w, fp1);
-    for (int k = 0; k < 3; k++) { lfv[k] = (fp1[k] - fp0[k]) / (T)0.0005; rfv[k] = (fp1[3 + k] - fp0[3 + k]) / (T)0.0005; }
+    for (int k = 0; k < 3; k++) { lfv[k] = cw_div(fp1[k] - fp0[k], (T)0.0005); rfv[k] = cw_div(fp1[3 + k] - fp0[3 + k], (T)0.0005); }
     cw_foot_forces<T>(w, &lz, &rz);
     cost += w.solver_iter * w.nefc;
 #ifdef CW_HOST_STATS /* tests/emu only: per-sub-step solver statistics for tools/solver_stats.py */

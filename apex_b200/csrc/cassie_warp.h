@@ -220,7 +220,26 @@ CW_FN double cw_dadd(double a, double b) { return __dadd_rn(a, b); }
 CW_FN double cw_dmul(double a, double b) { volatile double r = a * b; return r; }
 CW_FN double cw_dadd(double a, double b) { volatile double r = a + b; return r; }
 #endif
-template <typename T> CW_FN T cw_sqrt(T x) { return cw_sqrt_o(x); }
+/* Division, square root and reciprocal square root of the float32 kernel: one special-function instruction (1-2 ulp) and, for the
+ * reciprocal square root, one Newton step, instead of the IEEE sequences (10-20 instructions with a slow path each); the
+ * float64 instantiation and the host build keep the exact forms, so the oracle comparison is untouched. */
+#ifdef __CUDA_ARCH__
+CW_FN float cw_div(float a, float b) { return a * cw_rcp(b); }
+CW_FN float cw_sqrt_fast(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+CW_FN float cw_rsqrt(float x) {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r * (1.5f - 0.5f * x * r * r);
+}
+#else
+CW_FN float cw_div(float a, float b) { return a / b; }
+CW_FN float cw_sqrt_fast(float x) { return sqrtf(x); }
+CW_FN float cw_rsqrt(float x) { return 1.0f / sqrtf(x); }
+#endif
+CW_FN double cw_div(double a, double b) { return a / b; }
+CW_FN double cw_sqrt_fast(double x) { return sqrt(x); }
+CW_FN double cw_rsqrt(double x) { return 1.0 / sqrt(x); }
+template <typename T> CW_FN T cw_sqrt(T x) { return cw_sqrt_fast(x); }
 template <typename T> CW_FN void cw_sincos(T x, T *s, T *c) { cw_sincos_o(x, s, c); }
 template <typename T> CW_FN T cw_exp(T x) { return cw_exp_o(x); }
 template <typename T> CW_FN T cw_tan(T x) { return cw_tan_o(x); }
@@ -270,9 +289,9 @@ template <typename T> CW_FN void cw_qmul(T *r, const T *a, const T *b) {
   r[0] = w; r[1] = x; r[2] = y; r[3] = z;
 }
 template <typename T> CW_FN void cw_qnorm(T *q) {
-  T n = cw_sqrt<T>(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
-  if (n < (T)1e-15) { q[0] = 1; q[1] = q[2] = q[3] = 0; return; }
-  T inv = (T)1 / n;
+  const T n2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+  if (n2 < (T)1e-30) { q[0] = 1; q[1] = q[2] = q[3] = 0; return; }
+  const T inv = cw_rsqrt(n2);
   q[0] *= inv; q[1] *= inv; q[2] *= inv; q[3] *= inv;
 }
 template <typename T> CW_FN void cw_qmat(T *R, const T *q) {
@@ -771,7 +790,7 @@ template <typename T> CW_FN void cw_make_frame(T *fr) { /* mju_makeFrame */
     for (int k = 0; k < 3; k++) t1[k] -= d * n[k];
     l = cw_sqrt<T>(cw_dot3(t1, t1));
   }
-  const T inv = (T)1 / l;
+  const T inv = cw_rcp(l);
   for (int k = 0; k < 3; k++) t1[k] *= inv;
   cw_cross(t2, n, t1);
 }
@@ -818,7 +837,7 @@ template <typename T> CW_FN void cw_collision(CassieWs<T> &w CW_LANE_PARAM) {
       const T h1 = (T)CMT(geom_halflen)[g1], h2 = (T)CMT(geom_halflen)[g2], r1 = (T)CMT(geom_radius)[g1], r2 = (T)CMT(geom_radius)[g2];
       T r[3] = {c1[0] - c2[0], c1[1] - c2[1], c1[2] - c2[2]};
       const T b = cw_dot3(a1, a2), c = cw_dot3(a1, r), f = cw_dot3(a2, r), den = 1 - b * b;
-      T ss = den > (T)1e-12 ? (b * f - c) / den : (T)0;
+      T ss = den > (T)1e-12 ? cw_div(b * f - c, den) : (T)0;
       ss = cw_min(cw_max(ss, -h1), h1);
       T tt = b * ss + f;
       tt = cw_min(cw_max(tt, -h2), h2);
@@ -829,7 +848,7 @@ template <typename T> CW_FN void cw_collision(CassieWs<T> &w CW_LANE_PARAM) {
       const T len = cw_sqrt<T>(cw_dot3(nn, nn)), dist = len - r1 - r2;
       if (dist < 0 && len > (T)1e-15) {
         w.u.p.cand_dist[lane] = dist;
-        const T inv = (T)1 / len;
+        const T inv = cw_rcp(len);
         for (int k = 0; k < 3; k++) {
           nn[k] *= inv;
           w.u.p.cand_pos[lane][k] = p1[k] + nn[k] * (r1 + (T)0.5 * dist);
@@ -1006,7 +1025,7 @@ template <typename T> CW_FN void cw_make_constraint(CassieWs<T> &w, const T *qpo
       if (tc < (T)(2 * CM_TIMESTEP)) tc = (T)(2 * CM_TIMESTEP);
       const T dmax = (T)CM_SOLIMP_DMAX;
       const T Kc = (T)1 / (dmax * dmax * tc * tc * dr * dr), Bc = (T)2 / (dmax * tc);
-      w.efc_R[row] = cw_max((T)1e-15, (1 - imp) / imp * w.efc_R[row]); /* efc_R held diagApprox until here */
+      w.efc_R[row] = cw_max((T)1e-15, cw_div(1 - imp, imp) * w.efc_R[row]); /* efc_R held diagApprox until here */
       T jv = 0;
       for (int i = 0; i < CW_NV; i++) jv += w.u.J[row][i] * w.st[S_QVEL + i];
       w.efc_aref[row] = -Bc * jv - Kc * imp * pos; /* reference acceleration (mj_referenceConstraint) */
@@ -1052,7 +1071,7 @@ template <typename T> CW_FN void cw_project(CassieWs<T> &w CW_LANE_PARAM) {
         if (rr < 0) rr += n;
         T s = 0;
         for (int i = 0; i < CW_NV; i++) s += w.u.J[rr][i] * bs[i];
-        if (t == 0) { s += w.efc_R[c]; w.efc_dinv[c] = (T)1 / s; }
+        if (t == 0) { s += w.efc_R[c]; w.efc_dinv[c] = cw_rcp(s); }
         w.Ap[cw_tri(c, rr)] = s;
       }
     }
@@ -1355,13 +1374,13 @@ template <typename T> CW_NOINL void cw_mj_step(CassieWs<T> &w, bool integrate, i
         for (int i = 0; i < CW_NV; i++) { ja += w.u.J[row][i] * w.vec[V_Z][i]; jw += w.u.J[row][i] * w.vec[V_TMP][i]; }
         const T aref = w.efc_aref[row];
         w.efc_b[row] = ja - aref;
-        f = -(jw - aref) / w.efc_R[row];
+        f = -cw_div(jw - aref, w.efc_R[row]);
         if (w.efc_type[row] != 0 && f < 0) f = 0;
       }
       w.efc_f[row] = f;
     }
     CW_SYNC();
-    const T scale = (T)1 / (w.st[S_MEANINERTIA] * (T)CW_NV);
+    const T scale = cw_rcp(w.st[S_MEANINERTIA] * (T)CW_NV);
 #ifdef __CUDA_ARCH__
     { /* device path.  Row `lane` of the dual problem lives in lane `lane`'s registers together with column `lane` of A
        * (= row `lane`, A is symmetric).  Warm-start cost (mj_solPGS: keep the warm start only if it beats f = 0), then
@@ -1644,7 +1663,7 @@ template <typename T> CW_NOINL void cw_mj_step(CassieWs<T> &w, bool integrate, i
       if (ang > (T)1e-15) {
         T s, c, dq[4], qn[4], q0[4] = {qpos[qa], qpos[qa + 1], qpos[qa + 2], qpos[qa + 3]};
         cw_sincos<T>((T)0.5 * ang, &s, &c);
-        const T inv = s / nrm;
+        const T inv = cw_div(s, nrm);
         dq[0] = c; dq[1] = wv[0] * inv; dq[2] = wv[1] * inv; dq[3] = wv[2] * inv;
         cw_qmul(qn, q0, dq);
         cw_qnorm(qn);
