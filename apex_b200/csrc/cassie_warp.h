@@ -1104,10 +1104,21 @@ template <typename T> CW_FN void cw_rne(CassieWs<T> &w, const T *qvel CW_LANE_PA
   }
   CW_SYNC();
 #ifdef __CUDACC__
+  /* path sums down the tree by pointer jumping: 4 rounds of "add the partial sum of my 2^r-th ancestor" (CM_body_jump; a path
+   * shorter than that points at lane 31, no body, which carries zeros) instead of 9 level sweeps through shared memory */
+  const unsigned jump = CM_body_jump[lane];
+  {
 #pragma unroll
-  for (int lvl = 1; lvl <= CM_MAXLEVEL; lvl++) {
-    if (my_level == lvl)
-      for (int k = 0; k < 6; k++) w.u.p.cvel[lane][k] = w.u.p.cvel[my_parent][k] + jv[k];
+    for (int r = 0; r < 4; r++) {
+      const int a = (int)((jump >> (8 * r)) & 31u);
+      T t[6];
+#pragma unroll
+      for (int k = 0; k < 6; k++) t[k] = __shfl_sync(0xffffffffu, jv[k], a);
+#pragma unroll
+      for (int k = 0; k < 6; k++) jv[k] += t[k];
+    }
+    if (lane >= 1 && lane < CW_NB)
+      for (int k = 0; k < 6; k++) w.u.p.cvel[lane][k] = jv[k];
     CW_SYNC();
   }
 #else
@@ -1153,12 +1164,19 @@ template <typename T> CW_FN void cw_rne(CassieWs<T> &w, const T *qvel CW_LANE_PA
         for (int k = 0; k < 6; k++) ja[k] += w.u.p.cdd[da + s][k] * qd;
       }
     }
+    if (lane == 0) ja[5] = (T)(-CM_GRAVITY_Z); /* the world's acceleration: gravity enters the recursion here */
 #pragma unroll
-    for (int lvl = 1; lvl <= CM_MAXLEVEL; lvl++) {
-      if (my_level == lvl)
-        for (int k = 0; k < 6; k++) w.u.p.cacc[lane][k] = w.u.p.cacc[my_parent][k] + ja[k];
-      CW_SYNC();
+    for (int r = 0; r < 4; r++) {
+      const int a = (int)((jump >> (8 * r)) & 31u);
+      T t[6];
+#pragma unroll
+      for (int k = 0; k < 6; k++) t[k] = __shfl_sync(0xffffffffu, ja[k], a);
+#pragma unroll
+      for (int k = 0; k < 6; k++) ja[k] += t[k];
     }
+    if (lane >= 1 && lane < CW_NB)
+      for (int k = 0; k < 6; k++) w.u.p.cacc[lane][k] = ja[k];
+    CW_SYNC();
   }
 #else
   for (int lvl = 1; lvl <= CM_MAXLEVEL; lvl++) {

@@ -358,6 +358,21 @@ def emit(m):
     o.append(f'#define CM_MAXCHILD {mk}\n')
     o.append(arr1('CM_body_nchild', [0] + [len(k) for k in kids[1:]], 'int'))
     o.append(arr2('CM_body_child', [[-1] * mk] + [k + [-1] * (mk - len(k)) for k in kids[1:]], 'int'))
+    # pointer-jumping table for path sums down the body tree: byte r of entry b = the 2^r-th ancestor of body b, 31 where the
+    # path is shorter (lane 31 is no body and carries zeros); 4 rounds cover the 10 bodies of the longest path
+    def nth_parent(b, n_):
+        for _ in range(n_):
+            if b <= 0:
+                return 31
+            b = B[b]['parent']
+        return b
+    jump = []
+    for b_ in range(32):
+        if b_ >= len(B):
+            jump.append(31 | 31 << 8 | 31 << 16 | 31 << 24)
+        else:
+            jump.append(sum((nth_parent(b_, 1 << r_) & 0xff) << (8 * r_) for r_ in range(4)))
+    o.append(arr1('CM_body_jump', jump, 'unsigned'))
     ddepth = [len(a) for a in anc]
     o.append(arr1('CM_dof_armature_f', [d['armature'] for d in D]))
     o.append(arr1('CM_dof_qposadr', [J[d['jnt']]['qposadr'] + (i - J[d['jnt']]['dofadr'] if J[d['jnt']]['type'] != 2 else 0) for i, d in enumerate(D)], 'int'))
