@@ -341,6 +341,62 @@ template <typename T> CW_FN T cw_u01(uint32_t x) { return (T)(x >> 8) * (T)(1.0 
  * position stage: kinematics, cdof, cinert (mj_kinematics + mj_comPos), lane = body, one tree level per phase
  * ===================================================================================================== */
 template <typename T> CW_FN void cw_kinematics(CassieWs<T> &w, const T *qpos CW_LANE_PARAM) {
+#ifdef __CUDACC__
+  { /* device: every lane holds the pose of its body relative to an ancestor, (q, p): x_anc = p + R(q) x_body.  It starts as
+     * the pose in the parent (body_quat * joint rotation, body_pos; the pelvis: its free joint; world and the idle lanes: the
+     * identity) and 4 rounds of pointer jumping compose it with the partial product of the 2^r-th ancestor (CM_body_jump), which
+     * replaces the 8 level sweeps through shared memory.  Quaternions are re-normalised after every composition. */
+    T q[4] = {1, 0, 0, 0}, p[3] = {0, 0, 0};
+    if (lane == 1) {
+      q[0] = qpos[3]; q[1] = qpos[4]; q[2] = qpos[5]; q[3] = qpos[6];
+      cw_qnorm(q);
+      for (int k = 0; k < 3; k++) p[k] = qpos[k];
+    } else if (lane >= 2 && lane < CW_NB) {
+      const int b = lane, j = CM_body_jnt[b];
+      for (int k = 0; k < 4; k++) q[k] = (T)CMT(body_quat)[b][k];
+      for (int k = 0; k < 3; k++) p[k] = (T)CMT(body_pos)[b][k];
+      if (j >= 0) {
+        const int qa = CM_jnt_qposadr[j];
+        T qj[4], qn[4];
+        if (CM_jnt_type[j] == 1) {
+          T s, c;
+          cw_sincos<T>((T)0.5 * (qpos[qa] - (T)CMT(qpos0)[qa]), &s, &c);
+          qj[0] = c; qj[1] = (T)CMT(jnt_axis)[j][0] * s; qj[2] = (T)CMT(jnt_axis)[j][1] * s; qj[3] = (T)CMT(jnt_axis)[j][2] * s;
+        } else {
+          qj[0] = qpos[qa]; qj[1] = qpos[qa + 1]; qj[2] = qpos[qa + 2]; qj[3] = qpos[qa + 3];
+          cw_qnorm(qj);
+        }
+        cw_qmul(qn, q, qj);
+        for (int k = 0; k < 4; k++) q[k] = qn[k];
+      }
+    }
+    const unsigned jump = CM_body_jump[lane];
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      const int a = (int)((jump >> (8 * r)) & 31u);
+      T aq[4], ap[3], nq[4], t1[3], t2[3];
+#pragma unroll
+      for (int k = 0; k < 4; k++) aq[k] = __shfl_sync(0xffffffffu, q[k], a);
+#pragma unroll
+      for (int k = 0; k < 3; k++) ap[k] = __shfl_sync(0xffffffffu, p[k], a);
+      cw_cross(t1, aq + 1, p);
+      cw_cross(t2, aq + 1, t1);
+      for (int k = 0; k < 3; k++) p[k] = ap[k] + p[k] + 2 * (aq[0] * t1[k] + t2[k]); /* p_anc + R(q_anc) p */
+      cw_qmul(nq, aq, q);
+      cw_qnorm(nq);
+      for (int k = 0; k < 4; k++) q[k] = nq[k];
+    }
+    if (lane < CW_NB) {
+      for (int k = 0; k < 3; k++) w.xpos[lane][k] = p[k];
+      cw_qmat(w.xmat[lane], q);
+      if (lane == 1) for (int k = 0; k < 4; k++) w.qkeep[0][k] = q[k];
+      if (lane == CW_LFOOT) for (int k = 0; k < 4; k++) w.qkeep[1][k] = q[k];
+      if (lane == CW_RFOOT) for (int k = 0; k < 4; k++) w.qkeep[2][k] = q[k];
+      if (lane == 0) for (int k = 0; k < 10; k++) w.crb[0][k] = 0;
+    }
+    CW_SYNC();
+  }
+#else
   CW_FOR_LANES {
     if (lane == 0) {
       for (int k = 0; k < 3; k++) w.xpos[0][k] = 0;
@@ -409,6 +465,7 @@ template <typename T> CW_FN void cw_kinematics(CassieWs<T> &w, const T *qpos CW_
     }
   }
   CW_SYNC();
+#endif
   /* cdof and cinert about org = pelvis origin */
   CW_FOR_LANES {
     if (lane >= 1 && lane < CW_NB) {
