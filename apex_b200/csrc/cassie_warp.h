@@ -522,23 +522,43 @@ template <typename T> CW_FN void cw_kinematics(CassieWs<T> &w, const T *qpos CW_
   CW_SYNC();
 }
 
+#ifdef __CUDACC__
+/* Sum over the subtree of the lane's body, for NVAL values at once.  Bodies are numbered depth-first, so the subtree is the
+ * lane range [lane, lane + size): window sums of length 2, 4, 8, 16 are built by doubling (4 shuffle-down rounds) and the
+ * subtree's window is assembled from the binary digits of its size (5 lane-indexed shuffles), instead of 8 level sweeps through
+ * shared memory.  Lanes that are no body must pass zeros; size 0 gives 0. */
+template <typename T, int NVAL> __device__ __forceinline__ void cw_subtree_sum(T (&v)[NVAL], int lane, int size) {
+  T w1[NVAL], w2[NVAL], w3[NVAL], w4[NVAL];
+#pragma unroll
+  for (int k = 0; k < NVAL; k++) w1[k] = v[k] + __shfl_down_sync(0xffffffffu, v[k], 1);
+#pragma unroll
+  for (int k = 0; k < NVAL; k++) w2[k] = w1[k] + __shfl_down_sync(0xffffffffu, w1[k], 2);
+#pragma unroll
+  for (int k = 0; k < NVAL; k++) w3[k] = w2[k] + __shfl_down_sync(0xffffffffu, w2[k], 4);
+#pragma unroll
+  for (int k = 0; k < NVAL; k++) w4[k] = w3[k] + __shfl_down_sync(0xffffffffu, w3[k], 8);
+  const int p16 = lane, p8 = p16 + (size & 16), p4 = p8 + (size & 8), p2 = p4 + (size & 4), p1 = p2 + (size & 2);
+  const bool b16 = size & 16, b8 = size & 8, b4 = size & 4, b2 = size & 2, b1 = size & 1;
+#pragma unroll
+  for (int k = 0; k < NVAL; k++) {
+    const T t16 = __shfl_sync(0xffffffffu, w4[k], p16 & 31), t8 = __shfl_sync(0xffffffffu, w3[k], p8 & 31);
+    const T t4 = __shfl_sync(0xffffffffu, w2[k], p4 & 31), t2 = __shfl_sync(0xffffffffu, w1[k], p2 & 31);
+    const T t1 = __shfl_sync(0xffffffffu, v[k], p1 & 31);
+    v[k] = (b16 ? t16 : (T)0) + (b8 ? t8 : (T)0) + (b4 ? t4 : (T)0) + (b2 ? t2 : (T)0) + (b1 ? t1 : (T)0);
+  }
+}
+#endif
 /* composite inertia (mj_crb): parents gather children, deepest level first; then M (lane = dof) */
 template <typename T> CW_FN void cw_crb(CassieWs<T> &w CW_LANE_PARAM) {
 #ifdef __CUDACC__
-  {
-    const int my_level = lane < CW_NB ? CM_body_level[lane] : -1, nc = lane < CW_NB ? CM_body_nchild[lane] : 0;
-    const int c0 = nc > 0 ? CM_body_child[lane][0] : 0, c1 = nc > 1 ? CM_body_child[lane][1] : 0, c2 = nc > 2 ? CM_body_child[lane][2] : 0;
-#pragma unroll
-    for (int lvl = CM_MAXLEVEL - 1; lvl >= 1; lvl--) {
-      if (my_level == lvl && nc > 0) {
-        T acc[10];
-        for (int k = 0; k < 10; k++) acc[k] = w.crb[lane][k] + w.crb[c0][k];
-        if (nc > 1) for (int k = 0; k < 10; k++) acc[k] += w.crb[c1][k];
-        if (nc > 2) for (int k = 0; k < 10; k++) acc[k] += w.crb[c2][k];
-        for (int k = 0; k < 10; k++) w.crb[lane][k] = acc[k];
-      }
-      CW_SYNC();
-    }
+  { /* composite inertia = sum of the spatial inertias (all about the same origin) over the body's subtree */
+    T v[10];
+    const bool body = lane >= 1 && lane < CW_NB;
+    for (int k = 0; k < 10; k++) v[k] = body ? w.crb[lane][k] : (T)0;
+    cw_subtree_sum<T, 10>(v, lane, body ? CM_body_subtree[lane] : 0);
+    CW_SYNC();
+    if (body) for (int k = 0; k < 10; k++) w.crb[lane][k] = v[k];
+    CW_SYNC();
   }
 #else
   for (int lvl = CM_MAXLEVEL - 1; lvl >= 1; lvl--) {
@@ -1267,20 +1287,14 @@ template <typename T> CW_FN void cw_rne(CassieWs<T> &w, const T *qvel CW_LANE_PA
   CW_SYNC();
   /* pass 5 (up): parents gather their children's wrenches, deepest level first */
 #ifdef __CUDACC__
-  { /* child lists in registers, levels unrolled */
-    const int nc = lane < CW_NB ? CM_body_nchild[lane] : 0;
-    const int c0 = nc > 0 ? CM_body_child[lane][0] : 0, c1 = nc > 1 ? CM_body_child[lane][1] : 0, c2 = nc > 2 ? CM_body_child[lane][2] : 0;
-#pragma unroll
-    for (int lvl = CM_MAXLEVEL - 1; lvl >= 1; lvl--) {
-      if (my_level == lvl && nc > 0) {
-        T acc[6];
-        for (int k = 0; k < 6; k++) acc[k] = w.u.p.cfrc[lane][k] + w.u.p.cfrc[c0][k];
-        if (nc > 1) for (int k = 0; k < 6; k++) acc[k] += w.u.p.cfrc[c1][k];
-        if (nc > 2) for (int k = 0; k < 6; k++) acc[k] += w.u.p.cfrc[c2][k];
-        for (int k = 0; k < 6; k++) w.u.p.cfrc[lane][k] = acc[k];
-      }
-      CW_SYNC();
-    }
+  { /* the wrench a joint transmits = sum of the body wrenches over the subtree it carries */
+    T v[6];
+    const bool body = lane >= 1 && lane < CW_NB;
+    for (int k = 0; k < 6; k++) v[k] = body ? w.u.p.cfrc[lane][k] : (T)0;
+    cw_subtree_sum<T, 6>(v, lane, body ? CM_body_subtree[lane] : 0);
+    CW_SYNC();
+    if (body) for (int k = 0; k < 6; k++) w.u.p.cfrc[lane][k] = v[k];
+    CW_SYNC();
   }
 #else
   for (int lvl = CM_MAXLEVEL - 1; lvl >= 1; lvl--) {

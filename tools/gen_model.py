@@ -373,6 +373,13 @@ def emit(m):
         else:
             jump.append(sum((nth_parent(b_, 1 << r_) & 0xff) << (8 * r_) for r_ in range(4)))
     o.append(arr1('CM_body_jump', jump, 'unsigned'))
+    # bodies are numbered depth-first, so a body's subtree is the contiguous range [b, b + CM_body_subtree[b])
+    sub = [1] * len(B)
+    for b_ in range(len(B) - 1, 0, -1):
+        sub[B[b_]['parent']] += sub[b_]
+    for b_ in range(1, len(B)):
+        assert all(B[c_]['parent'] >= b_ for c_ in range(b_ + 1, b_ + sub[b_])) and (b_ + sub[b_] == len(B) or B[b_ + sub[b_]]['parent'] < b_)
+    o.append(arr1('CM_body_subtree', sub + [0] * (32 - len(B)), 'int'))
     ddepth = [len(a) for a in anc]
     o.append(arr1('CM_dof_armature_f', [d['armature'] for d in D]))
     o.append(arr1('CM_dof_qposadr', [J[d['jnt']]['qposadr'] + (i - J[d['jnt']]['dofadr'] if J[d['jnt']]['type'] != 2 else 0) for i, d in enumerate(D)], 'int'))
