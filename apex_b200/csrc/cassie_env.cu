@@ -150,6 +150,14 @@ void apex_cassie_set_warps_per_cta(int w) { apex_cassie_warps_per_cta = w; }
 int apex_cassie_bar_mask = 0;
 void apex_cassie_set_barrier_mask(int m) { apex_cassie_bar_mask = m & CW_BAR_MASK; }
 
+#ifdef CW_PROFILE
+/* profiling builds: read (and clear) the per-phase clock totals accumulated by CW_MARK */
+int apex_cassie_prof_read(unsigned long long *out32) {
+  unsigned long long zero[32] = {0};
+  if (cudaMemcpyFromSymbol(out32, cw_prof, sizeof(zero)) != cudaSuccess) return -1;
+  return cudaMemcpyToSymbol(cw_prof, zero, sizeof(zero)) == cudaSuccess ? 0 : -1;
+}
+#endif
 int apex_cassie_state_words(void) { return S_WORDS; }
 int apex_cassie_istate_words(void) { return I_WORDS; }
 

@@ -461,11 +461,14 @@ template <typename T> CW_NOINL void cw_env_step(CassieWs<T> &w, T *obs_out, T *r
   T lfrc = 0, rfrc = 0, lori = 0, rori = 0, lfv[3] = {0, 0, 0}, rfv[3] = {0, 0, 0};
   int cost = 0;
   const int bar0 = w.bar_mask & CW_BAR_MASK;
+  CW_MARK_START();
   for (int s = 0; s < CW_SIMRATE; s++) {
     /* sub-step s waits (somewhere, CW_SPLIT_POINT) for everybody's arrival of sub-step s - 1 = barrier phase s - 1 */
     const int flags = bar0 | (s > 0 ? CW_SPLIT_WAIT : 0) | (((s - 1) & 1) ? CW_SPLIT_PARITY : 0);
     const int bar = flags;
+    CW_MARK(14); /* Euler + integration + per-sub-step env bookkeeping */
     if (!(flags & CW_SPLIT)) CW_BLOCK_SYNC();
+    CW_MARK(15); /* waiting at the CTA barrier */
     CW_SPLIT_WAIT_AT(0);
     T fp0[6], fp1[6], lz, rz;
     for (int k = 0; k < 6; k++) fp0[k] = w.st[S_FOOTPOS + k];

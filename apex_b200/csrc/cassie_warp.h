@@ -69,6 +69,18 @@ __device__ __forceinline__ void cw_mbar_wait(unsigned addr, unsigned parity) {
 #define CW_SPLIT_WAIT_AT(point) ((void)0)
 #define CW_SPLIT_ARRIVE() ((void)0)
 #endif
+/* In-situ phase timing (profiling builds only, -DCW_PROFILE; tools/build_variant.sh): lane 0 of every warp accumulates the
+ * SM clock between phase marks into cw_prof[phase]; tools/phase_clock.py prints the shares. */
+#if defined(CW_PROFILE) && defined(__CUDACC__)
+__device__ unsigned long long cw_prof[32];
+#endif
+#if defined(CW_PROFILE) && defined(__CUDA_ARCH__)
+#define CW_MARK(idx) do { if (lane == 0) { const long long t_ = clock64(); atomicAdd(&cw_prof[idx], (unsigned long long)(t_ - w.prof_t)); w.prof_t = t_; } } while (0)
+#define CW_MARK_START() do { if (lane == 0) w.prof_t = clock64(); } while (0)
+#else
+#define CW_MARK(idx) ((void)0)
+#define CW_MARK_START() ((void)0)
+#endif
 #ifdef __CUDACC__
 #define CW_LANE_PARAM , const int lane
 #define CW_LANE_ARG , lane
@@ -182,6 +194,9 @@ struct CassieWs {
   int dropped; /* this sub-step lost a contact or a limit row to the capacity (see I_OVERFLOW) */
   int bar_mask; /* CTA synchronisation inside a sub-step (CW_BAR_* / CW_SPLIT bits), GPU build: keeps the CTA's warps on the same code */
   unsigned bar_addr; /* shared-memory address of the CTA's mbarrier (split barrier) */
+#ifdef CW_PROFILE
+  long long prof_t;
+#endif
   T con_pos[CW_NCON][3], con_frame[CW_NCON][9], con_dist[CW_NCON], con_mu[CW_NCON];
   int con_geom[CW_NCON], con_geom1[CW_NCON], con_dim[CW_NCON], con_adr[CW_NCON];
   T y[Y_WORDS];
@@ -672,10 +687,10 @@ template <typename T> __device__ __noinline__ void cw_factor2_dev(CassieWs<T> &w
   const bool leg = lane >= 6, rt = lane >= 19;
   const int ll = lane - (rt ? 13 : 0); /* the left leg's dof with the same role (CM_leg_ancmask is indexed by it) */
   const int rank = CM_dof_nanc[lane], own = CM_dof_rowptr[lane];
-  T r0[20], r1[20]; /* own row of the first / second factor; entries >= rank are scratch (kept finite) */
+  T r0[16], r1[16]; /* own row of the first / second factor (at most 13 entries); entries >= rank are scratch (kept finite) */
   T d0 = w.Mdiag[lane], d1 = d0 + hdamp * w.st[S_DAMPING + lane];
 #pragma unroll
-  for (int v = 0; v < 5; v++) {
+  for (int v = 0; v < 4; v++) {
     if (leg && 4 * v < rank) cw_ld4(r0 + 4 * v, M0 + own + 4 * v);
 #pragma unroll
     for (int t = 4 * v; t < 4 * v + 4; t++) { r0[t] = (leg && t < rank) ? r0[t] : (T)0; r1[t] = r0[t]; }
@@ -686,31 +701,48 @@ template <typename T> __device__ __noinline__ void cw_factor2_dev(CassieWs<T> &w
   if (!leg) { D0[lane] = d0; D1[lane] = d1; }
   T *const mine0 = M0 + own, *const mine1 = M1 + own;
   const T *const legrow0 = M0 + (rt ? CM_LEG_ROWSPAN : 0), *const legrow1 = M1 + (rt ? CM_LEG_ROWSPAN : 0);
+  /* Elimination order: leaves first.  Dofs of equal HEIGHT in a leg's dof tree (longest way down to a leaf) are no ancestors of
+   * each other, so they are eliminated in the same phase — 8 phases instead of 13 pivots in sequence: {achilles z, heel spring,
+   * plantar rod, foot}, {achilles y, foot crank}, {achilles x, tarsus}, shin, knee, hip pitch, hip yaw, hip roll (leg-local dof
+   * numbers below).  A phase publishes its pivot rows (and inverse pivots) once, then every lane applies each of them. */
+  constexpr int NPH = 8;
+  constexpr int PH[NPH][4] = {{5, 9, 11, 12}, {4, 10, -1, -1}, {3, 8, -1, -1}, {7, -1, -1, -1}, {6, -1, -1, -1}, {2, -1, -1, -1},
+                              {1, -1, -1, -1}, {0, -1, -1, -1}};
+  const int sidx = ll - 6; /* leg-local dof number, negative on the base lanes */
+  const T *const dinv0 = w.Dinv + (rt ? 13 : 0), *const dinv1 = D1 + (rt ? 13 : 0);
 #pragma unroll
-  for (int s = 12; s >= 0; s--) {
-    const unsigned legmask = CM_leg_ancmask[s];
-    const int len = 6 + __builtin_popcount(legmask), okL = CM_dof_rowptr[6 + s]; /* literals once the phase loop is unrolled */
-    if (ll == 6 + s) { /* this lane's dof is the pivot of its leg: its rows and pivots are final */
+  for (int ph = 0; ph < NPH; ph++) {
+    unsigned phmask = 0;
 #pragma unroll
-      for (int v = 0; 4 * v < len; v++) { cw_st4(mine0 + 4 * v, r0 + 4 * v); cw_st4(mine1 + 4 * v, r1 + 4 * v); }
+    for (int q = 0; q < 4; q++) if (PH[ph][q] >= 0) phmask |= 1u << PH[ph][q];
+    if (leg && ((phmask >> sidx) & 1u)) { /* this lane's dof is a pivot of the phase: its rows and pivots are final */
+#pragma unroll
+      for (int v = 0; v < 4; v++) if (4 * v < rank) { cw_st4(mine0 + 4 * v, r0 + 4 * v); cw_st4(mine1 + 4 * v, r1 + 4 * v); }
       w.Dinv[lane] = cw_rcp(d0);
       D1[lane] = cw_rcp(d1);
     }
-    const int src = (rt ? 19 : 6) + s;
-    const T di0 = cw_rcp(__shfl_sync(0xffffffffu, d0, src)), di1 = cw_rcp(__shfl_sync(0xffffffffu, d1, src));
     __syncwarp();
-    T p0[20], p1[20];
 #pragma unroll
-    for (int v = 0; 4 * v < len; v++) { cw_ld4(p0 + 4 * v, legrow0 + okL + 4 * v); cw_ld4(p1 + 4 * v, legrow1 + okL + 4 * v); }
-    const bool part = leg && ((legmask >> ll) & 1u);
-    /* entry (pivot, this dof); a lane that is no ancestor of the pivot reads some unrelated word (possibly not even finite) */
-    const T e0 = part ? legrow0[okL + rank] : (T)0, e1 = part ? legrow1[okL + rank] : (T)0;
-    const T a0 = e0 * di0, a1 = e1 * di1;
+    for (int q = 0; q < 4; q++) {
+      if (PH[ph][q] < 0) continue;
+      const int s = PH[ph][q];
+      const unsigned legmask = CM_leg_ancmask[s];
+      const int len = 6 + __builtin_popcount(legmask), okL = CM_dof_rowptr[6 + s]; /* literals: everything is unrolled */
+      const T di0 = dinv0[6 + s], di1 = dinv1[6 + s];
+      T p0[16], p1[16];
 #pragma unroll
-    for (int t = 0; t < len; t++) { r0[t] -= a0 * p0[t]; r1[t] -= a1 * p1[t]; }
-    d0 -= a0 * e0; d1 -= a1 * e1;
+      for (int v = 0; 4 * v < len; v++) { cw_ld4(p0 + 4 * v, legrow0 + okL + 4 * v); cw_ld4(p1 + 4 * v, legrow1 + okL + 4 * v); }
+      const bool part = leg && ((legmask >> ll) & 1u);
+      /* entry (pivot, this dof); a lane that is no ancestor of the pivot reads some unrelated word (possibly not even finite) */
+      const T e0 = part ? legrow0[okL + rank] : (T)0, e1 = part ? legrow1[okL + rank] : (T)0;
+      const T a0 = e0 * di0, a1 = e1 * di1;
+#pragma unroll
+      for (int t = 0; t < len; t++) { r0[t] -= a0 * p0[t]; r1[t] -= a1 * p1[t]; }
+      d0 -= a0 * e0; d1 -= a1 * e1;
+    }
   }
   __syncwarp();
+  CW_MARK(17); /* leg phases of the factorisation */
   cw_factor_base<T, 2>(w, M0, M1, D0, D1, lane);
 }
 #endif
@@ -1134,6 +1166,7 @@ template <typename T> CW_FN void cw_project(CassieWs<T> &w CW_LANE_PARAM) {
     }
   }
   CW_SYNC();
+  CW_MARK(16); /* half solve of the rows (counted inside "project" as well unless read separately) */
   CW_FOR_LANES {
     const int c = lane;
     if (c < n) {
@@ -1347,18 +1380,26 @@ template <typename T> CW_NOINL void cw_mj_step(CassieWs<T> &w, bool integrate, i
   T *qpos = w.st + S_QPOS, *qvel = w.st + S_QVEL;
   const T h = (T)CM_TIMESTEP;
   /* ---- step1 ---- */
+  CW_MARK(0); /* wrapper + env bookkeeping since the last mark */
   cw_kinematics<T>(w, qpos CW_LANE_ARG);
+  CW_MARK(1);
   CW_SPLIT_WAIT_AT(1);
   cw_rne<T>(w, qvel CW_LANE_ARG); /* before cw_crb: it reads the per-body inertias */
+  CW_MARK(2);
   CW_SPLIT_WAIT_AT(2);
   cw_crb<T>(w CW_LANE_ARG);
+  CW_MARK(3);
   cw_build_M<T>(w CW_LANE_ARG);
+  CW_MARK(4);
   if (integrate) cw_factor<T, 2>(w, h CW_LANE_ARG); /* M for the solves, M + h B for mj_Euler's implicit damping */
   else cw_factor<T, 1>(w, (T)0 CW_LANE_ARG);
+  CW_MARK(5);
   CW_SPLIT_WAIT_AT(3);
   if (flags & CW_BAR_FACTOR) CW_BLOCK_SYNC();
   cw_collision<T>(w CW_LANE_ARG);
+  CW_MARK(6);
   cw_make_constraint<T>(w, qpos, flags CW_LANE_ARG);
+  CW_MARK(7);
   const int n = w.nefc;
   /* sensors (positions / velocities) for the next wrapper call */
   CW_FOR_LANES {
@@ -1424,12 +1465,14 @@ template <typename T> CW_NOINL void cw_mj_step(CassieWs<T> &w, bool integrate, i
   CW_FOR_LANES { w.vec[V_Z][lane] *= w.Dinv[lane]; w.vec[V_QACCS][lane] = w.vec[V_Z][lane]; }
   CW_SYNC();
   cw_solve_L<T>(w.Ms, w.Dinv, w.vec[V_QACCS] CW_LANE_ARG);
+  CW_MARK(8); /* sensors, smooth forces, the two solves for qacc_smooth */
   /* ---- constraints ---- */
   CW_FOR_LANES { w.vec[V_G][lane] = 0; }
   int iters = 0;
   if (flags & CW_BAR_SOLVE) CW_BLOCK_SYNC();
   if (n > 0) {
     cw_project<T>(w CW_LANE_ARG);
+    CW_MARK(9);
     /* L qacc_warmstart (so that J a = B (L a)) */
 #ifdef __CUDACC__
     { /* one ancestor per depth: its value comes by shuffle (depth < 6: the base dof of that number) */
@@ -1475,6 +1518,7 @@ template <typename T> CW_NOINL void cw_mj_step(CassieWs<T> &w, bool integrate, i
        * (= row `lane`, A is symmetric).  Warm-start cost (mj_solPGS: keep the warm start only if it beats f = 0), then
        * PGS sweeps in residual-update form: the row owner computes the update, ONE shuffle broadcasts it and every lane
        * applies column i of A to its own residual — no shared-memory traffic and no barrier inside the sweep. */
+      CW_MARK(10); /* warm start: L a, B z, B (L a) */
       const bool v0 = lane < n;
       T acol[CW_NEFC];
       const int rowbase = lane * (lane + 1) / 2;
@@ -1526,6 +1570,7 @@ template <typename T> CW_NOINL void cw_mj_step(CassieWs<T> &w, bool integrate, i
       T *const sown = w.efc_dinv; /* consumed above (di0) */
       (void)sbuf;
       const int myblk = lane >> 2;
+      CW_MARK(11); /* solver set-up: column of A, warm-start cost, block parameters */
 #ifdef CW_PGS_CAPTURE_SEL
       const bool j1 = (lane & 3) == 1, j2 = (lane & 3) == 2, j3 = (lane & 3) == 3;
 #endif
@@ -1616,6 +1661,7 @@ template <typename T> CW_NOINL void cw_mj_step(CassieWs<T> &w, bool integrate, i
       __syncwarp();
       if (v0) w.efc_f[lane] = f0;
       __syncwarp();
+      CW_MARK(12); /* PGS sweeps */
     }
 #else
     /* residual res = A f + b and warm-start cost (mj_solPGS start: keep the warm start only if it beats f = 0) */
@@ -1688,6 +1734,7 @@ template <typename T> CW_NOINL void cw_mj_step(CassieWs<T> &w, bool integrate, i
     CW_SYNC();
     CW_FOR_LANES { if (lane < 3) w.st[S_SENS_ACC + lane] = out[lane]; }
   }
+  CW_MARK(13); /* g = B^T f, qacc, accelerometer */
   if (!integrate) { CW_SYNC(); return; }
   /* ---- Euler, implicit in damping: (M + h B) a' = qfrc_smooth + J^T f, J^T f = L^T g ---- */
 #ifdef __CUDACC__
