@@ -743,7 +743,44 @@ template <typename T> __device__ __noinline__ void cw_factor2_dev(CassieWs<T> &w
   }
   __syncwarp();
   CW_MARK(17); /* leg phases of the factorisation */
-  cw_factor_base<T, 2>(w, M0, M1, D0, D1, lane);
+  /* The 6 base dofs: one entry (i, j <= i) of their 6 x 6 block per lane, both factors, in registers.  First the Schur
+   * complement of the two legs (the leg rows and inverse pivots are in shared memory by now), then the block's own elimination
+   * as symmetric rank-1 updates E(l, j) -= E(k, l) E(k, j) / E(k, k), k = 5 .. 1, whose three operands come by shuffle. */
+  {
+    int bi = 0, rem = lane;
+    while (rem > bi) { rem -= bi + 1; bi++; }
+    const int bj = rem;
+    const bool ent = lane < 21;
+    T e0 = 0, e1 = 0;
+    if (ent) {
+      T a00 = 0, a01 = 0, a10 = 0, a11 = 0; /* two partial sums per factor: half the dependent chain */
+#pragma unroll
+      for (int k = 6; k < CW_NV; k += 2) {
+        const int ok = CM_dof_rowptr[k], ok2 = CM_dof_rowptr[k + 1];
+        a00 += M0[ok + bi] * M0[ok + bj] * w.Dinv[k];
+        a10 += M1[ok + bi] * M1[ok + bj] * D1[k];
+        a01 += M0[ok2 + bi] * M0[ok2 + bj] * w.Dinv[k + 1];
+        a11 += M1[ok2 + bi] * M1[ok2 + bj] * D1[k + 1];
+      }
+      const int at = CM_dof_rowptr[bi] + bj;
+      e0 = (bi == bj ? D0[bi] : M0[at]) - (a00 + a01);
+      e1 = (bi == bj ? D1[bi] : M1[at]) - (a10 + a11);
+    }
+#pragma unroll
+    for (int k = 5; k >= 1; k--) {
+      const int lkk = k * (k + 1) / 2 + k, lkl = k * (k + 1) / 2 + bi, lkj = k * (k + 1) / 2 + bj;
+      const T p0 = __shfl_sync(0xffffffffu, e0, lkk), p1 = __shfl_sync(0xffffffffu, e1, lkk);
+      const T l0 = __shfl_sync(0xffffffffu, e0, lkl & 31), l1 = __shfl_sync(0xffffffffu, e1, lkl & 31);
+      const T j0 = __shfl_sync(0xffffffffu, e0, lkj & 31), j1 = __shfl_sync(0xffffffffu, e1, lkj & 31);
+      if (ent && bi < k) { e0 -= l0 * cw_rcp(p0) * j0; e1 -= l1 * cw_rcp(p1) * j1; }
+    }
+    __syncwarp();
+    if (ent) {
+      if (bi == bj) { w.Dinv[bi] = cw_rcp(e0); D1[bi] = cw_rcp(e1); }
+      else { const int at = CM_dof_rowptr[bi] + bj; M0[at] = e0; M1[at] = e1; }
+    }
+    __syncwarp();
+  }
 }
 #endif
 template <typename T, int NF> CW_NOINL void cw_factor(CassieWs<T> &w, T hdamp CW_LANE_PARAM) {
