@@ -449,8 +449,13 @@ def main():
         ach = fl * args.envs / (k_ms * 1e-3) / 1e12
         compute = {"flops_per_env_step": fl, "achieved_tflops": ach, "fp32_peak_tflops": prof.get("fp32_peak_tflops"),
                    "frac": ach / prof["fp32_peak_tflops"] if prof.get("fp32_peak_tflops") else None,
-                   "issue_slots_active_pct": prof.get("issue_active_pct"), "source": "profiles/roofline_r02.json (instrumented oracle flop "
-                   "count; ncu issue utilisation of the committed capture)"}
+                   "executed_flops_per_env_step": prof.get("executed_flops_per_env_step"),
+                   "executed_tflops": (prof["executed_flops_per_env_step"] * args.envs / (k_ms * 1e-3) / 1e12
+                                       if prof.get("executed_flops_per_env_step") else None),
+                   "issue_slots_active_pct": prof.get("issue_active_pct"),
+                   "source": "profiles/roofline_r02.json: flops_per_env_step = algorithmic count (tools/flop_count.cpp, counting scalar "
+                             "through the kernel source), executed = ncu thread-level FP op counters of the committed capture (includes the "
+                             "redundant lanes of the in-lane solver chains); both divided by this run's live kernel time"}
     out = {"metric": "Cassie-v0 PPO env-steps/sec", "value": env_steps / (ms_step * 1e-3), "unit": "env-steps/s", "n_gpus": world,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f32" if args.precision == "f32" else "bf16 (forward hidden layers; rest f32)",

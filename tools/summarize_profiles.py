@@ -1,5 +1,6 @@
 """Turn the ncu reports / launch list under gpurun_out/ into the small JSON summaries committed under profiles/.
-Usage: python tools/summarize_profiles.py <tag> <envstep.ncu-rep> <envs in that launch> [<launches.csv>] [<gemm.ncu-rep>]"""
+Usage: python tools/summarize_profiles.py <tag> <envstep.ncu-rep> <envs in that launch> [<launches.csv>] [<gemm.ncu-rep>]
+The library the report was taken from is looked up next to the report (lib.so, tools/gpu_prof.sh) before the in-tree one."""
 import csv
 import json
 import os
@@ -52,7 +53,8 @@ s["envs_in_launch"] = envs
 s["warp_instructions_per_env_substep"] = s["warp_instructions"] / (envs * 50)
 # per-function shares from tools/ncu_lines.py
 txt = subprocess.run([sys.executable, os.path.join(os.path.dirname(__file__), "ncu_lines.py"), rep,
-                      os.path.join(os.path.dirname(OUT), "apex_b200", "libapex_b200.so"), "k_env_stepIfE", "5"], capture_output=True, text=True).stdout
+                      (os.path.join(os.path.dirname(rep), "lib.so") if os.path.exists(os.path.join(os.path.dirname(rep), "lib.so"))
+                       else os.path.join(os.path.dirname(OUT), "apex_b200", "libapex_b200.so")), "k_env_stepIfE", "5"], capture_output=True, text=True).stdout
 fn = {}
 for line in txt.split("---- by function ----")[-1].splitlines():
     m = re.match(r"\s*([\d.]+)% smp\s+([\d.]+)% ins\s+(\S+)", line)
@@ -60,13 +62,17 @@ for line in txt.split("---- by function ----")[-1].splitlines():
         fn[m.group(3).split(":")[-1]] = {"samples_pct": float(m.group(1)), "instructions_pct": float(m.group(2))}
 s["by_function"] = dict(list(fn.items())[:16])
 s["note"] = ("cw_env_step's samples are the per-sub-step CTA barrier; cw_Ms2 labels cw_factor<T,2> (the line table points at its "
-             "first inlined helper); cw_mj_step's own lines are the PGS loop plus glue")
+             "first inlined helper); cw_mj_step's own lines are the PGS loop plus glue; in round 2 cw_factor_base also collects "
+             "cw_factor2_dev and cw_kinematics collects cw_subtree_sum (the line table points at the preceding definition)")
 json.dump(s, open(os.path.join(OUT, f"ncu_envstep_{tag}.json"), "w"), indent=1)
 print(json.dumps({k: s[k] for k in ("duration_ms", "issue_active_pct", "warp_instructions_per_env_substep", "stalls_pct")}, indent=1))
 dram = s["dram_read_bytes"] + s["dram_write_bytes"]
-json.dump({"kernel": "k_env_step<float>", "source": f"profiles/ncu_envstep_{tag}.json (ncu --set full, {envs} envs in the launch)",
-           f"dram_bytes_per_launch_{envs}": dram, "dram_bytes_per_launch_4096": dram * 4096 / envs,
-           "algorithmic_bytes_per_launch_4096": 2608 * 4096}, open(os.path.join(OUT, "roofline_r01.json"), "w"), indent=1)
+roof_path = os.path.join(OUT, "roofline_r02.json")
+roof = json.load(open(roof_path)) if os.path.exists(roof_path) else {}
+roof.update({"kernel": "k_env_step<float>", "ncu_source": f"profiles/ncu_envstep_{tag}.json (ncu --set full, {envs} envs in the launch)",
+             "dram_bytes_per_launch_4096": dram * 4096 / envs, "algorithmic_bytes_per_launch_4096": 2608 * 4096,
+             "issue_active_pct": s["issue_active_pct"], "kernel_ms_under_ncu": s["duration_ms"]})
+json.dump(roof, open(roof_path, "w"), indent=1)
 if launches:
     rows = list(csv.reader(l for l in open(launches) if not l.startswith("==")))
     hdr = rows[0]
@@ -80,8 +86,8 @@ if launches:
         k = re.sub(r"\(.*", "", r[iK])
         agg[k][0] += 1; agg[k][1] += v
     tot = sum(v[1] for v in agg.values())
-    out = {"source": "ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 800 -c 1200 on `python bench.py --steps 1 "
-                     "--warmup 1 --horizon 32 --no-cpu-baseline` (a 32-step horizon keeps the capture to minutes; rollout and update both "
+    out = {"source": "ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 1400 -c 1400 on `python bench.py --steps 1 "
+                     "--warmup 1 --horizon 32 --no-cpu-baseline --no-extras` (a 32-step horizon keeps the capture to minutes; rollout and update both "
                      "scale with the horizon, so the shares carry over to the 256-step bench).  Per-launch times under ncu are cold and "
                      "serialised: compare shares, not absolutes.", "launches": sum(v[0] for v in agg.values()), "total_ms": tot / 1e3,
            "kernels": [{"kernel": k, "launches": n, "total_ms": t / 1e3, "share": round(t / tot, 4), "avg_us": t / n}
