@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""`python apex.py ppo ...` on the B200 backend: the flag surface of the reference's apex.py (:16-39 common flags, :214-250
+"""`python apex.py ppo ...` / `python apex.py eval --path RUN_DIR` on the B200 backend: the flag surface of the reference's apex.py (:16-39 common flags, :214-250
 `ppo` flags; same names, types and defaults) in front of apex_b200.ppo.run_experiment.  Only the `ppo` sub-command of the hot
 path is provided; additions are prefixed apex_: --apex_num_envs (env batch per GPU, default 4096) and
 --apex_trajectory (stepdata.bin for CassieTraj-v0).  Under torchrun every rank trains on its own env shard and the gradients
@@ -56,17 +56,67 @@ PPO_FLAGS = [
 ]
 
 
+EVAL_FLAGS = [  # apex.py:261-268; the visualiser-only switches are accepted and ignored (there is no window on a GPU box)
+    ("--path", dict(type=str, default="./trained_models/nodelta_neutral_StateEst_symmetry_speed0-3_freq1-2/")),
+    ("--traj_len", dict(default=400, type=int)),
+    ("--history", dict(default=0, type=int)),
+    ("--mission", dict(default="default", type=str)),
+    ("--terrain", dict(default=None, type=str)),
+    ("--debug", dict(default=False, action="store_true")),
+    ("--no_stats", dict(dest="stats", default=True, action="store_false")),
+    ("--no_viz", dict(default=False, action="store_true")),
+    ("--apex_num_envs", dict(type=int, default=256)),
+    ("--apex_trajectory", dict(type=str, default=None)),
+]
+
+
 def parse(argv):
-    if len(argv) < 2 or argv[1] != "ppo":
-        sys.exit("usage: apex.py ppo [flags]   (the other sub-commands of the reference's apex.py are outside the B200 hot path)")
-    ap = argparse.ArgumentParser(prog="apex.py ppo")
-    for flag, kw in COMMON + PPO_FLAGS:
+    if len(argv) < 2 or argv[1] not in ("ppo", "eval"):
+        sys.exit("usage: apex.py {ppo,eval} [flags]   (the other sub-commands of the reference's apex.py are outside the B200 hot path)")
+    ap = argparse.ArgumentParser(prog="apex.py " + argv[1])
+    for flag, kw in (COMMON + PPO_FLAGS if argv[1] == "ppo" else EVAL_FLAGS):
         ap.add_argument(flag, **kw)
-    return ap.parse_args(argv[2:])
+    args = ap.parse_args(argv[2:])
+    args.command = argv[1]
+    return args
+
+
+def evaluate(args):
+    """`apex.py eval --path RUN_DIR` (apex.py:257-280) without the visualiser: load actor.pt and the run's experiment.pkl, build
+    the env the run was trained on and roll the deterministic policy for traj_len steps in --apex_num_envs envs at once; prints
+    what EvalProcessClass's statistics print: mean return and episode length (+ the fraction of envs that never fell)."""
+    import pickle
+    import torch
+    from apex_b200 import evaluate as ev
+    from apex_b200.envs import env_factory
+    from apex_b200.policies import load_reference_checkpoint
+    run_args = pickle.load(open(os.path.join(args.path, "experiment.pkl"), "rb"))
+    policy = load_reference_checkpoint(os.path.join(args.path, "actor.pt"))
+    g = lambda k, d=None: getattr(run_args, k, d)
+    env = env_factory(g("env_name", "Cassie-v0"), simrate=g("simrate", 50), command_profile=g("command_profile", "clock"),
+                      input_profile=g("input_profile", "full"), dynamics_randomization=g("dyn_random", True), reward=g("reward"),
+                      history=g("history", 0), no_delta=g("no_delta", True), traj=g("traj", "walking"), num_envs=args.apex_num_envs,
+                      trajectory=args.apex_trajectory, max_traj_len=0)()
+    pol = ev.KernelPolicy(policy, env.device)
+    obs = env.reset()
+    n = env.num_envs
+    alive = torch.ones(n, dtype=torch.bool, device=env.device)
+    ret = torch.zeros(n, dtype=torch.float64, device=env.device)
+    length = torch.zeros(n, dtype=torch.int64, device=env.device)
+    for _ in range(int(args.traj_len)):
+        obs, rew, done, _ = env.step(pol(obs), active=alive.to(torch.int32))
+        ret += torch.where(alive, rew.double(), torch.zeros_like(ret))
+        length += alive
+        alive &= (done & 3) == 0
+    out = {"envs": n, "mean_return": float(ret.mean()), "mean_eplen": float(length.double().mean()), "survived": float(alive.double().mean())}
+    print("eval: {envs} envs, mean return {mean_return:.2f}, mean episode length {mean_eplen:.1f}, survived {survived:.1%}".format(**out))
+    return out
 
 
 def main(argv=None):
     args = parse(sys.argv if argv is None else argv)
+    if args.command == "eval":
+        return evaluate(args)
     import torch
     import torch.distributed as dist
     if "RANK" in os.environ and not dist.is_initialized():

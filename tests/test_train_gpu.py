@@ -46,6 +46,27 @@ def test_run_experiment_writes_the_reference_run_directory(tmp_path):
         assert tuple(a.obs_mean.shape) == (50,) and a.means.weight.shape == (10, 256)
 
 
+def test_apex_eval_rolls_a_saved_run(tmp_path):
+    """`apex.py eval --path RUN_DIR` (apex.py:257-280, headless): a run directory written by run_experiment is read back
+    (experiment.pkl + actor.pt) and rolled deterministically; every env lives at least one step and at most traj_len."""
+    import importlib.util
+    from apex_b200.ppo import run_experiment
+    from apex_b200 import log
+    args = _cli_args(tmp_path)
+    algo, policy, critic = run_experiment(args)
+    run_dir, _ = log.run_directory(args)
+    if not os.path.exists(os.path.join(run_dir, "actor.pt")):
+        algo.save(policy, critic)
+    spec = importlib.util.spec_from_file_location("apex_cli", os.path.join(ROOT, "apex.py"))
+    cli = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(cli)
+    out = cli.main(["apex.py", "eval", "--path", run_dir, "--traj_len", "30", "--apex_num_envs", "32"])
+    assert out["envs"] == 32 and 1.0 <= out["mean_eplen"] <= 30.0 and np.isfinite(out["mean_return"])
+    assert 0.0 <= out["survived"] <= 1.0
+    again = cli.main(["apex.py", "eval", "--path", run_dir, "--traj_len", "30", "--apex_num_envs", "32"])
+    assert again == out  # deterministic policy, seeded env
+
+
 def _two_rank_worker(rank, port, out):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
