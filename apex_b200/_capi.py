@@ -79,6 +79,16 @@ def lib():
         L.apex_set_tc_persistent.restype = None
         L.apex_set_gemm_large_tiles.argtypes = [i]
         L.apex_set_gemm_large_tiles.restype = None
+        L.apex_set_head_kernels.argtypes = [i]
+        L.apex_set_head_kernels.restype = None
+        L.apex_set_tc_mode.argtypes = [i]
+        L.apex_set_tc_mode.restype = None
+        L.apex_get_tc_mode.restype = i
+        L.apex_set_tc_min_rows.argtypes = [i]
+        L.apex_set_tc_min_rows.restype = None
+        L.apex_tc3_linear.argtypes = [vp, lng, i, i, vp, lng, lng, vp, i, vp, lng, vp, lng, i, vp]
+        L.apex_tc3_outer.argtypes = [vp, lng, vp, lng, i, lng, vp, lng, i, i, vp]
+        L.apex_tc3_linear.restype = L.apex_tc3_outer.restype = i
         L.apex_col_moments.argtypes = [vp, i, i, vp, vp]
         L.apex_col_moments.restype = i
         for f in (L.apex_mlp_forward, L.apex_mlp_backward, L.apex_prepare_obs, L.apex_gaussian_sample, L.apex_ppo_loss,

@@ -261,11 +261,33 @@ int apex_gemm_min_ctas = 148;   /* below one CTA per SM the 64 x 64 kernel (4x t
 extern "C" void apex_set_gemm_min_ctas(int n) { apex_gemm_min_ctas = n; }
 extern "C" void apex_set_gemm_large_tiles(int on) { apex_gemm_large_tiles = on; }
 
+/* Tensor-core routes for the 256-wide layers (csrc/tc_gemm3.cu): apex_tc_mode = 3 (default) computes them as split-tf32
+ * ("3xTF32": float32-accurate), 1 as plain TF32, 0 keeps every GEMM on the SIMT kernels below. */
+extern "C" int apex_tc3_linear(const float *A, long lda, int M, int K, const float *w, long swn, long swk, const float *bias, int relu,
+                               const float *mask, long ldmask, float *C, long ldc, int passes, void *stream);
+extern "C" int apex_tc3_outer(const float *A, long lda, const float *B, long ldb, int nb, long R, float *C, long ldc, int accumulate,
+                              int passes, void *stream);
+int apex_tc_mode = 3;
+int apex_tc_min_rows = 1024; /* below this the SIMT 64 x 64 kernel's launch is the cheaper one */
+extern "C" void apex_set_tc_mode(int mode) { apex_tc_mode = (mode == 1 || mode == 3) ? mode : 0; }
+extern "C" int apex_get_tc_mode(void) { return apex_tc_mode; }
+extern "C" void apex_set_tc_min_rows(int rows) { apex_tc_min_rows = rows; }
+
 static int gemm(int M, int N, int K, const float *A, long sam, long sak, const float *B, long sbk, long sbn, float *C, long scm,
                 long scn, const float *bias, int relu, const float *mask, long smm, long smn, int accumulate, int splits,
                 cudaStream_t s, __nv_bfloat16 *side = nullptr, int side_k = 0) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   if (splits < 1) splits = 1;
+  if (apex_tc_mode && !side && scn == 1) {
+    /* C [M, 256] = epi(A [M, K] W^T), rows of A contiguous: forward (W row-major [256, K]) and dX (W^T) of a 256-wide layer */
+    if (N == 256 && K <= 1024 && M >= apex_tc_min_rows && sak == 1 && !accumulate && splits == 1 && (scm & 3) == 0 &&
+        (((size_t)C | (size_t)bias) & 15) == 0 && (!mask || (smn == 1 && (smm & 3) == 0 && ((size_t)mask & 15) == 0)))
+      return apex_tc3_linear(A, sam, M, K, B, sbn, sbk, bias, relu, mask, smm, C, scm, apex_tc_mode, (void *)s);
+    /* C [256, N] += A^T B over K rows: the weight gradient of a layer with 256 outputs and 256 or <= 64 inputs */
+    if (M == 256 && (N <= 64 || (N == 256 && (scm & 3) == 0 && ((size_t)C & 15) == 0)) && K >= apex_tc_min_rows && sam == 1 && sbn == 1 &&
+        !bias && !relu && !mask)
+      return apex_tc3_outer(A, sak, B, sbk, N, K, C, scm, accumulate, apex_tc_mode, (void *)s);
+  }
   if (apex_gemm_large_tiles && M >= 128 && N >= 128 && (long)((M + LM - 1) / LM) * ((N + LN - 1) / LN) * splits >= apex_gemm_min_ctas) { /* enough 128-tiles to fill the SMs */
     if (splits > 1) { /* split-k: about one wave of CTAs; every extra split is another atomicAdd per output element */
       const int tiles = ((N + LN - 1) / LN) * ((M + LM - 1) / LM);
@@ -282,6 +304,20 @@ static int gemm(int M, int N, int K, const float *A, long sam, long sak, const f
   dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, splits);
   k_gemm<<<grid, 256, 0, s>>>(M, N, K, A, sam, sak, B, sbk, sbn, C, scm, scn, bias, relu, mask, smm, smn, accumulate, kchunk, side, side_k);
   return last_err();
+}
+
+/* streaming kernels for the narrow output layer (csrc/mlp_head.cu); return 1 when the shape is not covered */
+int apex_head_forward(const float *h2, long rows, int hid, int out_dim, const float *w3, const float *b3, float *y, cudaStream_t s);
+int apex_head_backward(const float *h2, const float *dy, const float *w3, long rows, int hid, int out_dim, float *dh2, float *gw3,
+                       float *gb3, cudaStream_t s);
+int apex_head_kernels = 1; /* test hook: 0 sends the output layer through the GEMM kernels */
+extern "C" void apex_set_head_kernels(int on) { apex_head_kernels = on; }
+
+static int head_fwd(int rows, int hid, int out_dim, const float *h2, const float *w3, const float *b3, float *y, cudaStream_t s) {
+  int rc = 1;
+  if (apex_head_kernels && rows >= 1024) rc = apex_head_forward(h2, rows, hid, out_dim, w3, b3, y, s);
+  if (rc == 1) rc = gemm(rows, out_dim, hid, h2, hid, 1, w3, 1, hid, y, out_dim, 1, b3, 0, nullptr, 0, 0, 0, 1, s);
+  return rc;
 }
 
 /* column sums: out[n] += sum_m X[m, n] (bias gradients) */
@@ -310,7 +346,7 @@ extern "C" int apex_mlp_forward(const float *x, int rows, int in_dim, int hid, i
   /* torch Linear: y = x W^T + b, W [out, in] row-major  ->  B(k, n) = W[n * in + k] */
   if ((rc = gemm(rows, hid, in_dim, x, in_dim, 1, w1, 1, in_dim, h1, hid, 1, b1, 1, nullptr, 0, 0, 0, 1, s))) return rc;
   if ((rc = gemm(rows, hid, hid, h1, hid, 1, w2, 1, hid, h2, hid, 1, b2, 1, nullptr, 0, 0, 0, 1, s))) return rc;
-  if ((rc = gemm(rows, out_dim, hid, h2, hid, 1, w3, 1, hid, y, out_dim, 1, b3, 0, nullptr, 0, 0, 0, 1, s))) return rc;
+  if ((rc = head_fwd(rows, hid, out_dim, h2, w3, b3, y, s))) return rc;
   return 0;
 }
 
@@ -336,7 +372,7 @@ extern "C" int apex_mlp_forward_bf16(const float *x, int rows, int in_dim, int h
     if ((rc = gemm(rows, hid, in_dim, x, in_dim, 1, w1, 1, in_dim, h1, hid, 1, b1, 1, nullptr, 0, 0, 0, 1, s))) return rc;
     if ((rc = apex_tc_linear_forward(h1, rows, hid, w2, b2, hid, 1, h2, stream))) return rc;
   }
-  if ((rc = gemm(rows, out_dim, hid, h2, hid, 1, w3, 1, hid, y, out_dim, 1, b3, 0, nullptr, 0, 0, 0, 1, s))) return rc;
+  if ((rc = head_fwd(rows, hid, out_dim, h2, w3, b3, y, s))) return rc;
   return 0;
 }
 
@@ -348,9 +384,13 @@ extern "C" int apex_mlp_backward(const float *x, int rows, int in_dim, int hid, 
   const int splits = 148; /* the weight gradients reduce over `rows`: split that dimension across the SMs */
   const int rpb = 64;
   /* layer 3: gW3[o, k] += sum_r dy[r, o] h2[r, k];  dh2 = (dy W3) * (h2 > 0) */
-  if ((rc = gemm(out_dim, hid, rows, dy, 1, out_dim, h2, hid, 1, gw3, hid, 1, nullptr, 0, nullptr, 0, 0, 1, splits, s))) return rc;
-  k_colsum<<<dim3((out_dim + 63) / 64, (rows + rpb - 1) / rpb), 64, 0, s>>>(rows, out_dim, dy, gb3, rpb);
-  if ((rc = gemm(rows, hid, out_dim, dy, out_dim, 1, w3, hid, 1, dh2, hid, 1, nullptr, 0, h2, hid, 1, 0, 1, s))) return rc;
+  rc = (apex_head_kernels && rows >= 1024) ? apex_head_backward(h2, dy, w3, rows, hid, out_dim, dh2, gw3, gb3, s) : 1;
+  if (rc < 0) return rc;
+  if (rc == 1) {
+    if ((rc = gemm(out_dim, hid, rows, dy, 1, out_dim, h2, hid, 1, gw3, hid, 1, nullptr, 0, nullptr, 0, 0, 1, splits, s))) return rc;
+    k_colsum<<<dim3((out_dim + 63) / 64, (rows + rpb - 1) / rpb), 64, 0, s>>>(rows, out_dim, dy, gb3, rpb);
+    if ((rc = gemm(rows, hid, out_dim, dy, out_dim, 1, w3, hid, 1, dh2, hid, 1, nullptr, 0, h2, hid, 1, 0, 1, s))) return rc;
+  }
   /* layer 2 */
   if ((rc = gemm(hid, hid, rows, dh2, 1, hid, h1, hid, 1, gw2, hid, 1, nullptr, 0, nullptr, 0, 0, 1, splits, s))) return rc;
   k_colsum<<<dim3((hid + 63) / 64, (rows + rpb - 1) / rpb), 64, 0, s>>>(rows, hid, dh2, gb2, rpb);
@@ -699,11 +739,16 @@ extern "C" int apex_mlp_backward_dx(const float *x, int rows, int in_dim, int hi
   cudaStream_t s = (cudaStream_t)stream;
   int rc;
   const int splits = 148, rpb = 512;
-  if (want_wgrads) {
-    if ((rc = gemm(out_dim, hid, rows, dy, 1, out_dim, h2, hid, 1, gw3, hid, 1, nullptr, 0, nullptr, 0, 0, 1, splits, s))) return rc;
-    k_colsum<<<dim3((out_dim + 63) / 64, (rows + rpb - 1) / rpb), 64, 0, s>>>(rows, out_dim, dy, gb3, rpb);
+  rc = (apex_head_kernels && rows >= 1024) ? apex_head_backward(h2, dy, w3, rows, hid, out_dim, dh2, want_wgrads ? gw3 : nullptr,
+                                                                 want_wgrads ? gb3 : nullptr, s) : 1;
+  if (rc < 0) return rc;
+  if (rc == 1) {
+    if (want_wgrads) {
+      if ((rc = gemm(out_dim, hid, rows, dy, 1, out_dim, h2, hid, 1, gw3, hid, 1, nullptr, 0, nullptr, 0, 0, 1, splits, s))) return rc;
+      k_colsum<<<dim3((out_dim + 63) / 64, (rows + rpb - 1) / rpb), 64, 0, s>>>(rows, out_dim, dy, gb3, rpb);
+    }
+    if ((rc = gemm(rows, hid, out_dim, dy, out_dim, 1, w3, hid, 1, dh2, hid, 1, nullptr, 0, h2, hid, 1, 0, 1, s))) return rc;
   }
-  if ((rc = gemm(rows, hid, out_dim, dy, out_dim, 1, w3, hid, 1, dh2, hid, 1, nullptr, 0, h2, hid, 1, 0, 1, s))) return rc;
   if (want_wgrads) {
     if ((rc = gemm(hid, hid, rows, dh2, 1, hid, h1, hid, 1, gw2, hid, 1, nullptr, 0, nullptr, 0, 0, 1, splits, s))) return rc;
     k_colsum<<<dim3((hid + 63) / 64, (rows + rpb - 1) / rpb), 64, 0, s>>>(rows, hid, dh2, gb2, rpb);

@@ -90,6 +90,25 @@ int apex_mlp_forward_bf16(const float *x, int rows, int in_dim, int hid, int out
 /* the TMA hidden layer on its own: xt = tiled bf16 image of x [M, K] (rows padded to 128), wt_scratch = N * K * 2 bytes */
 int apex_tc_linear_tiled(const void *xt, int M, int K, const float *w, void *wt_scratch, const float *bias, int N, int relu, float *y,
                          void *stream);
+/* ---- float32-accurate tensor-core path (csrc/tc_gemm3.cu): tcgen05 kind::tf32 with every operand split as hi + lo (two tf32
+ * terms) and three products per k step ("3xTF32"), used by apex_mlp_forward / apex_mlp_backward for the 256-wide layers
+ * (rl/policies/actor.py:142-215: the reference's default 256 x 256 hidden layers) when rows >= apex_set_tc_min_rows (1024).
+ * mode 3 (default) = split, 1 = plain TF32 (10-bit mantissa), 0 = SIMT float32 kernels everywhere. */
+void apex_set_tc_mode(int mode);
+int apex_get_tc_mode(void);
+void apex_set_tc_min_rows(int rows);
+/* C [M, 256] = epi(A [M, K] W^T), W(n, k) = w[n * swn + k * swk]; epi = + bias[n], ReLU, zero where mask[m, n] <= 0 (each
+ * optional).  Any K <= 1024 (zero-padded to a multiple of 64 on chip); C, mask, bias 16-byte aligned, ldc / ldmask multiples of 4;
+ * passes 1 or 3. */
+int apex_tc3_linear(const float *A, long lda, int M, int K, const float *w, long swn, long swk, const float *bias, int relu,
+                    const float *mask, long ldmask, float *C, long ldc, int passes, void *stream);
+/* C [256, nb] (+)= A [R, 256]^T B [R, nb], nb = 256 or <= 64 (weight gradient: reduction over the R rows, one CTA per SM, float
+ * atomics into C) */
+int apex_tc3_outer(const float *A, long lda, const float *B, long ldb, int nb, long R, float *C, long ldc, int accumulate, int passes,
+                   void *stream);
+/* test hook: 0 sends the narrow output layer (256 -> 10 / 1) through the GEMM kernels instead of the streaming kernels of
+ * csrc/mlp_head.cu (forward; backward = dh2, gW3 and gb3 in one pass over h2) */
+void apex_set_head_kernels(int on);
 /* test hook: 0 routes every GEMM through the 64 x 64 tile kernel, 1 (default) uses the 128 x 128 one when M, N >= 128 */
 void apex_set_gemm_large_tiles(int on);
 /* tuning: minimum number of 128 x 128 tiles (x split-k) for the large-tile kernel to be chosen (default 148 = one per SM) */

@@ -290,10 +290,11 @@ def test_mlp_forward_bf16_close_to_float32(rows):
         torch.cuda.synchronize()
         return h1, h2, y
     h1f, h2f, yf = run("f32")
-    ref_h2 = torch.relu(h1f.bfloat16().double() @ w2.bfloat16().double().T + b2.double())
     for kind in ("tma", "convert"):
         h1, h2, y = run(kind)
-        assert torch.equal(h1, h1f), kind
+        # layer 1 is float32 on every route (SIMT with the tiled side output for "tma", split-tf32 tensor cores otherwise)
+        assert float((h1 - h1f).abs().max()) < 4e-6 * float(h1f.abs().max()), kind
+        ref_h2 = torch.relu(h1.bfloat16().double() @ w2.bfloat16().double().T + b2.double())
         assert float((h2.double() - ref_h2).abs().max()) < 2e-5 * float(ref_h2.abs().max()), kind
         assert float((y - yf).abs().max()) < 2e-2 * float(yf.abs().max()), kind  # bf16 operands: ~3 significant digits
 
