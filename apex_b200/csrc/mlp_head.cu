@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(256, 2) k_head_bwd(const float *__restrict__ h
   float gb[O];
 #pragma unroll
   for (int o = 0; o < O; o++) {
-    w[o] = __ldg(reinterpret_cast<const float4 *>(w3 + o * K + k0));
+    w[o] = make_float4(__ldg(w3 + o * K + k0), __ldg(w3 + o * K + k0 + 1), __ldg(w3 + o * K + k0 + 2), __ldg(w3 + o * K + k0 + 3)); /* any 4-byte offset */
     g[o] = make_float4(0.f, 0.f, 0.f, 0.f);
     gb[o] = 0.f;
   }
@@ -132,7 +132,7 @@ int apex_head_forward(const float *h2, long rows, int hid, int out_dim, const fl
 /* dh2 = (dy W3) * (h2 > 0) and, when gw3 != NULL, gw3 += dy^T h2, gb3 += column sums of dy */
 int apex_head_backward(const float *h2, const float *dy, const float *w3, long rows, int hid, int out_dim, float *dh2, float *gw3,
                        float *gb3, cudaStream_t s) {
-  if (hid != 256 || (out_dim != 1 && out_dim != 10) || (((size_t)h2 | (size_t)dh2 | (size_t)w3) & 15)) return 1;
+  if (hid != 256 || (out_dim != 1 && out_dim != 10) || (((size_t)h2 | (size_t)dh2) & 15)) return 1;
   const int blocks = 2 * sms();
   long rpb = (rows + blocks - 1) / blocks;
   rpb = (rpb + 3) / 4 * 4;

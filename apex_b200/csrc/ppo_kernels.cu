@@ -281,10 +281,10 @@ static int gemm(int M, int N, int K, const float *A, long sam, long sak, const f
   if (apex_tc_mode && !side && scn == 1) {
     /* C [M, 256] = epi(A [M, K] W^T), rows of A contiguous: forward (W row-major [256, K]) and dX (W^T) of a 256-wide layer */
     if (N == 256 && K <= 1024 && M >= apex_tc_min_rows && sak == 1 && !accumulate && splits == 1 && (scm & 3) == 0 &&
-        (((size_t)C | (size_t)bias) & 15) == 0 && (!mask || (smn == 1 && (smm & 3) == 0 && ((size_t)mask & 15) == 0)))
+        ((size_t)C & 15) == 0 && (!mask || (smn == 1 && (smm & 3) == 0 && ((size_t)mask & 15) == 0)))
       return apex_tc3_linear(A, sam, M, K, B, sbn, sbk, bias, relu, mask, smm, C, scm, apex_tc_mode, (void *)s);
     /* C [256, N] += A^T B over K rows: the weight gradient of a layer with 256 outputs and 256 or <= 64 inputs */
-    if (M == 256 && (N <= 64 || (N == 256 && (scm & 3) == 0 && ((size_t)C & 15) == 0)) && K >= apex_tc_min_rows && sam == 1 && sbn == 1 &&
+    if (M == 256 && (N <= 64 || N == 256) && K >= apex_tc_min_rows && sam == 1 && sbn == 1 &&
         !bias && !relu && !mask)
       return apex_tc3_outer(A, sak, B, sbk, N, K, C, scm, accumulate, apex_tc_mode, (void *)s);
   }

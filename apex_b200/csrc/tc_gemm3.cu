@@ -117,6 +117,7 @@ k_tc3_nt(const float *__restrict__ A, long lda, int M, int Kv, int K, const floa
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ __align__(8) uint64_t bars[10]; /* fullA(2), fullB(2), empty(2), mma_done(2), tmem_free(2) */
   __shared__ uint32_t tmem_base_s;
+  __shared__ __align__(16) float sbias[NT_N]; /* staged once: the bias may sit at any 4-byte offset of a flat parameter buffer */
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int tiles = (M + 127) >> 7, KSL = K / NT_KS;
   const uint32_t bar0 = s_u32(&bars[0]);
@@ -136,6 +137,7 @@ k_tc3_nt(const float *__restrict__ A, long lda, int M, int Kv, int K, const floa
     mbar_init(tmem_free(0), 256); mbar_init(tmem_free(1), 256);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (tid < NT_N) sbias[tid] = bias ? bias[tid] : 0.f;
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -171,7 +173,7 @@ k_tc3_nt(const float *__restrict__ A, long lda, int M, int Kv, int K, const floa
           st_shared16(stg + lane * 128 + ((g4 ^ (lane & 7)) << 4), make_float4(__uint_as_float(r[4 * g4]), __uint_as_float(r[4 * g4 + 1]),
                                                                                 __uint_as_float(r[4 * g4 + 2]), __uint_as_float(r[4 * g4 + 3])));
         __syncwarp();
-        const float4 b4 = bias ? __ldg(reinterpret_cast<const float4 *>(bias + c) + ch) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 b4 = *reinterpret_cast<const float4 *>(&sbias[c + 4 * ch]);
 #pragma unroll
         for (int i = 0; i < 8; i++) {
           const int rr = rsub + 4 * i;
@@ -410,12 +412,13 @@ k_tc3_tn(const float *__restrict__ A, long lda, const float *__restrict__ B, lon
     mbar_wait(done, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * NB);
+    const bool c_vec = (((size_t)C & 15) == 0) && (ldc & 3) == 0; /* e.g. the critic's gradients start 8 bytes into a 16-byte line */
     constexpr int NCH = NB / 32;
     for (int cc = 0; cc < ((dbg & 4) ? 0 : NCH); cc++) {
       const int c = ((cc + blockIdx.x) % NCH) * 32;
       uint32_t r[32];
       TMEM_LD32(r, taddr + (uint32_t)c);
-      if (NB == 256) { /* nb = 256, 16-byte aligned rows */
+      if (NB == 256 && c_vec) { /* 16-byte aligned rows: vector atomics */
         float4 *o = reinterpret_cast<float4 *>(C + (long)m * ldc + c);
 #pragma unroll
         for (int g4 = 0; g4 < 8; g4++)
@@ -469,7 +472,7 @@ int apex_tc3_linear(const float *A, long lda, int M, int K, const float *w, long
                     const float *mask, long ldmask, float *C, long ldc, int passes, void *stream) {
   if (M <= 0) return 0;
   if (!A || !w || !C || K < 1 || K > 1024 || (passes != 1 && passes != 3)) return -1000;
-  if (((size_t)C | (size_t)mask | (size_t)bias) & 15 || (ldc | ldmask) & 3) return -1000;
+  if (((size_t)C | (size_t)mask) & 15 || (ldc | ldmask) & 3) return -1000;
   const int Kp = (K + 63) / 64 * 64;
   const bool vec = (((size_t)A & 15) == 0) && (lda & 3) == 0 && (K & 3) == 0;
   cudaStream_t s = (cudaStream_t)stream;
@@ -494,12 +497,10 @@ int apex_tc3_linear(const float *A, long lda, int M, int K, const float *w, long
 }
 
 /* C [256, nb] (+)= A [R, 256]^T B [R, nb] on tcgen05 kind::tf32 (nb = 256, or <= 64: the first layer's weight gradient), the
- * reduction over the R rows split across one CTA per SM; accumulate = 0 zeroes C first.  nb = 256 needs C 16-byte aligned and ldc
- * a multiple of 4. */
+ * reduction over the R rows split across one CTA per SM; accumulate = 0 zeroes C first. */
 int apex_tc3_outer(const float *A, long lda, const float *B, long ldb, int nb, long R, float *C, long ldc, int accumulate, int passes,
                    void *stream) {
   if (!A || !B || !C || (passes != 1 && passes != 3) || nb < 1 || (nb > 64 && nb != 256)) return -1000;
-  if (nb == 256 && (((size_t)C & 15) || (ldc & 3))) return -1000;
   cudaStream_t s = (cudaStream_t)stream;
   cudaError_t err;
   if (!accumulate) {

@@ -104,8 +104,12 @@ class PPO:
         # the update's forward pass) run on the tcgen05 tensor cores with bf16 operands / float32 accumulation; backward, first
         # layer, heads, losses and Adam stay float32.  BASELINE config "PPO CassieTraj-v0 8192 envs/GPU bf16".
         self.precision = args.get("precision", "f32")
-        if self.precision not in ("f32", "bf16"):
-            raise ValueError("precision must be 'f32' or 'bf16'")
+        if self.precision not in ("f32", "tf32", "bf16"):
+            raise ValueError("precision must be 'f32', 'tf32' or 'bf16'")
+        # The 256-wide layers run on the tcgen05 tensor cores in every precision (csrc/tc_gemm3.cu).  "f32": operands split in
+        # two tf32 terms, three products per k step — float32-accurate (tc_mode 3); "tf32" / "bf16": one product (tc_mode 1; with
+        # "bf16" the forward hidden layer additionally uses bf16 operands).  tc_mode=0 keeps every GEMM on the SIMT kernels.
+        self.tc_mode = int(args.get("tc_mode", 3 if self.precision == "f32" else 1))
         self.save_path = save_path
         self.total_steps = 0
         self.highest_reward = -1
@@ -187,6 +191,7 @@ class PPO:
     def _mlp_fwd(self, ptrs, x, rows, out_dim, h1, h2, y):
         args = (_p(x), rows, self.obs_dim, self.hid, out_dim, ptrs[0][0], ptrs[1][0], ptrs[2][0], ptrs[3][0], ptrs[4][0], ptrs[5][0],
                 _p(h1), _p(h2), _p(y))
+        self.L.apex_set_tc_mode(self.tc_mode)
         if self.precision == "bf16":
             need = self.L.apex_mlp_bf16_scratch_bytes(rows, self.hid)
             if getattr(self, "_tc_scratch", None) is None or self._tc_scratch.numel() < need:
@@ -195,13 +200,14 @@ class PPO:
                         "mlp_forward_bf16")
         else:
             _capi.check(self.L.apex_mlp_forward(*args, self._s()), "mlp_forward")
-        self.launches += 3
+        self.launches += 5 if (self.tc_mode and rows >= 1024) else 3  # tensor-core layers launch the weight-image kernel too
 
     def _mlp_bwd(self, ptrs, x, rows, out_dim, h1, h2, dy, dh2, dh1):
+        self.L.apex_set_tc_mode(self.tc_mode)
         _capi.check(self.L.apex_mlp_backward(_p(x), rows, self.obs_dim, self.hid, out_dim, ptrs[2][0], ptrs[4][0], _p(h1), _p(h2),
                                              _p(dy), _p(dh2), _p(dh1), ptrs[0][1], ptrs[1][1], ptrs[2][1], ptrs[3][1], ptrs[4][1],
                                              ptrs[5][1], self._s()), "mlp_backward")
-        self.launches += 8
+        self.launches += 7 if rows >= 1024 else 8  # fused output-layer backward (one kernel instead of three)
 
     # ------------------------------------------------------------------ sampling
     @torch.no_grad()

@@ -34,8 +34,11 @@ def parse():
     ap.add_argument("--horizon", type=int, default=HORIZON)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the cfg3 / cfg4 / cfg5 measurements (BASELINE.json configs 3-5)")
-    ap.add_argument("--precision", default="f32", choices=["f32", "bf16"],
-                    help="bf16: forward 256x256 hidden layers on tcgen05 (BASELINE configs[3]); the headline config is f32")
+    ap.add_argument("--precision", default="f32", choices=["f32", "tf32", "bf16"],
+                    help="f32 (headline): 256-wide learner GEMMs as split-tf32 on tcgen05 (float32-accurate); tf32: one product per "
+                         "k step; bf16: additionally bf16 operands in the forward hidden layer (BASELINE configs[3])")
+    ap.add_argument("--tc-mode", type=int, default=None, choices=[0, 1, 3],
+                    help="override the tensor-core mode of the learner (0 = SIMT float32 GEMMs everywhere)")
     ap.add_argument("--env", default="Cassie-v0", choices=["Cassie-v0", "CassieTraj-v0"])
     return ap.parse_args()
 
@@ -266,8 +269,9 @@ def extra_cfg4_traj(dev, rank, world):
     ms, _ = device_ms(lambda: algo.train_iteration(env_fn, actor, critic, generator=gen), dev, world)
     del algo, actor, critic
     torch.cuda.empty_cache()
-    return {"workload": f"PPO CassieTraj-v0 {n} envs/GPU x {T} steps, mb {MINIBATCH}, {EPOCHS} epochs, bf16 tcgen05 forward hidden layers, "
-                        f"gradient all-reduce per optimizer step, {world} GPU(s)", "dtype": "bf16 (forward hidden layers; rest f32)",
+    return {"workload": f"PPO CassieTraj-v0 {n} envs/GPU x {T} steps, mb {MINIBATCH}, {EPOCHS} epochs, bf16 tcgen05 forward hidden layers, tf32 tcgen05 "
+                        f"backward / first-layer GEMMs, gradient all-reduce per optimizer step, {world} GPU(s)",
+            "dtype": "bf16 (forward hidden layers; tf32 backward GEMMs; rest f32)",
             "metric": "env-steps/s", "value": n * T * world / (ms * 1e-3), "ms_per_iteration": ms, "iterations_timed": 1, "n_gpus": world}
 
 
@@ -325,7 +329,7 @@ def main():
     actor = Gaussian_FF_Actor(50, 10, fixed_std=torch.ones(10) * float(np.exp(-1.5)), env_name="Cassie-v0")
     critic = FF_V(50)
     algo = PPO(dict(num_steps=args.envs * args.horizon, minibatch_size=MINIBATCH, epochs=EPOCHS, max_traj_len=400, seed=0,
-                    max_kl=None, precision=args.precision))  # fixed work per step: all epochs always run (the reference stops early when KL > 0.02)
+                    max_kl=None, precision=args.precision, **({} if args.tc_mode is None else {"tc_mode": args.tc_mode})))  # fixed work per step: all epochs always run (the reference stops early when KL > 0.02)
     if args.env == "CassieTraj-v0":  # the decimated reference trajectory ships as a test fixture (tests/golden/make_env_golden.py)
         from apex_b200.envs import BatchedCassieTrajEnv
         g = np.load(os.path.join(ROOT, "tests", "golden", "traj_walking_rows.npz"))
@@ -415,6 +419,7 @@ def main():
     k_ms = sum(kms) / len(kms)
     env_steps = args.envs * args.horizon * world
 
+    tc_mode = algo.tc_mode
     extras = {}
     if not args.no_extras:
         del algo
@@ -458,7 +463,8 @@ def main():
                              "redundant lanes of the in-lane solver chains); both divided by this run's live kernel time"}
     out = {"metric": "Cassie-v0 PPO env-steps/sec", "value": env_steps / (ms_step * 1e-3), "unit": "env-steps/s", "n_gpus": world,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-           "vs_baseline": None, "dtype": "f32" if args.precision == "f32" else "bf16 (forward hidden layers; rest f32)",
+           "vs_baseline": None, "dtype": {"f32": "f32", "tf32": "tf32 tensor-core learner GEMMs; rest f32",
+                                          "bf16": "bf16 (forward hidden layers; tf32 backward GEMMs; rest f32)"}[args.precision],
            "data": "synthetic",
            "config": {"workload": workload, "envs_per_gpu": args.envs, "horizon": args.horizon, "simrate": 50,
                       "dynamics_randomization": True, "parallelism": f"dp{world}", "l2": "per-step state 4096 x 2.6 KB + "
@@ -468,6 +474,10 @@ def main():
                    "note": "PPO.train_iteration with the parameters shipped from pinned host memory and parameters, loss statistics, "
                            "rewards and done flags read back to the host every step"},
            "gpu_launches": launches, "clocks": clk,
+           "learner": {"tc_mode": tc_mode, "update_ms": ms_instr - sum(rms) / len(rms),
+                       "note": "tc_mode 3: the 256-wide layers (forward, dX, dW; first layer k = 50 padded) on tcgen05 kind::tf32 with "
+                               "every operand split as hi + lo and three products per k step (float32-accurate, csrc/tc_gemm3.cu); "
+                               "1: one product per k step; 0: SIMT float32 GEMMs.  update_ms = instrumented step minus its rollout"},
            "rollout_only": {"value": args.envs * args.horizon * world / (sum(rms) / len(rms) * 1e-3), "unit": "env-steps/s",
                             "ms": sum(rms) / len(rms), "note": "rank 0's device time of sample_parallel in the instrumented step"},
            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -98,7 +98,7 @@ void apex_set_tc_mode(int mode);
 int apex_get_tc_mode(void);
 void apex_set_tc_min_rows(int rows);
 /* C [M, 256] = epi(A [M, K] W^T), W(n, k) = w[n * swn + k * swk]; epi = + bias[n], ReLU, zero where mask[m, n] <= 0 (each
- * optional).  Any K <= 1024 (zero-padded to a multiple of 64 on chip); C, mask, bias 16-byte aligned, ldc / ldmask multiples of 4;
+ * optional).  Any K <= 1024 (zero-padded to a multiple of 64 on chip); C and mask 16-byte aligned, ldc / ldmask multiples of 4;
  * passes 1 or 3. */
 int apex_tc3_linear(const float *A, long lda, int M, int K, const float *w, long swn, long swk, const float *bias, int relu,
                     const float *mask, long ldmask, float *C, long ldc, int passes, void *stream);

@@ -163,3 +163,38 @@ def test_first_layer_shapes(passes):
     scaleg = dh.double().abs().t() @ x.double().abs() + 1e-30
     errg = ((G.double() - refg).abs() / scaleg).max().item()
     assert errg < tol, errg
+
+
+def test_parameters_at_any_float_offset():
+    """The critic's parameters start 8 bytes into a 16-byte line of the flat parameter buffer (81,418 actor floats precede them):
+    weights, biases and weight gradients at odd float offsets must take the tensor-core / streaming routes and give the same
+    result as 16-byte aligned copies."""
+    L, capi = _lib()
+    rows, din, hid, dout = 4096, 50, 256, 1
+    g = torch.Generator(device="cuda").manual_seed(21)
+    f = dict(device="cuda", generator=g)
+    x, dy = torch.randn(rows, din, **f), torch.randn(rows, dout, **f)
+    shapes = [(hid, din), (hid,), (hid, hid), (hid,), (dout, hid), (dout,)]
+    vals = [torch.randn(*s, **f) / 8 for s in shapes]
+    out = {}
+    for off in (0, 2):
+        n = sum(v.numel() for v in vals)
+        flat, grad = torch.zeros(n + 8, device="cuda"), torch.zeros(n + 8, device="cuda")
+        ptr, views, gviews = off, [], []
+        for v in vals:
+            views.append(flat[ptr:ptr + v.numel()].view_as(v)); views[-1].copy_(v)
+            gviews.append(grad[ptr:ptr + v.numel()].view_as(v))
+            ptr += v.numel()
+        assert (views[0].data_ptr() % 16 == 0) == (off == 0)
+        w1, b1, w2, b2, w3, b3 = views
+        h1, h2, y = (torch.empty(rows, k, device="cuda") for k in (hid, hid, dout))
+        capi.check(L.apex_mlp_forward(x.data_ptr(), rows, din, hid, dout, w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(),
+                                      w3.data_ptr(), b3.data_ptr(), h1.data_ptr(), h2.data_ptr(), y.data_ptr(), _s()), "fwd")
+        dh2, dh1 = torch.empty(rows, hid, device="cuda"), torch.empty(rows, hid, device="cuda")
+        gw1, gb1, gw2, gb2, gw3, gb3 = gviews
+        capi.check(L.apex_mlp_backward(x.data_ptr(), rows, din, hid, dout, w2.data_ptr(), w3.data_ptr(), h1.data_ptr(), h2.data_ptr(),
+                                       dy.data_ptr(), dh2.data_ptr(), dh1.data_ptr(), gw1.data_ptr(), gb1.data_ptr(), gw2.data_ptr(),
+                                       gb2.data_ptr(), gw3.data_ptr(), gb3.data_ptr(), _s()), "bwd")
+        out[off] = [t.clone() for t in (y, dh1, gw1, gb1, gw2, gb2, gw3, gb3)]
+    for a, b in zip(out[0], out[2]):
+        assert torch.allclose(a, b, rtol=1e-5, atol=2e-6 * float(a.abs().max())), float((a - b).abs().max())
