@@ -309,7 +309,14 @@ class PPO:
         self._mlp_bwd(cp, self.mb_raw, B, 1, self.mb_g1, self.mb_g2, self.mb_dv, self.mb_dh2, self.mb_dh1)
         gscale = 1.0
         if self.world > 1:  # one all-reduce of the flattened actor+critic gradient per optimizer step
+            ev = getattr(self, "collective_events", None)  # bench.py's instrumented pass: device time of the NCCL all-reduces
+            if ev is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
             dist.all_reduce(self.grad)
+            if ev is not None:
+                e1.record()
+                ev.append((e0, e1))
             gscale = 1.0 / self.world
         na, nt = self.n_actor, self.n_total
         gp, pp, mp, vp = self.grad.data_ptr(), self.flat.data_ptr(), self.adam_m.data_ptr(), self.adam_v.data_ptr()

@@ -412,8 +412,17 @@ def main():
         rollout_events.append((s_, t_))
         return out
     algo.env.step, algo.sample_parallel = wrapped, wrapped_sample
+    algo.collective_events = []
     ms_instr, _ = timed(False, 1)
     algo.env.step, algo.sample_parallel = orig_step, orig_sample
+    nccl = None
+    if world > 1:  # one all-reduce of the flattened actor + critic gradient per optimizer step
+        cms = [a.elapsed_time(b) for a, b in algo.collective_events]
+        nccl = {"grad_allreduce_calls": len(cms), "grad_allreduce_ms_total": sum(cms), "bytes_per_call": int(algo.grad.numel()) * 4,
+                "share_of_step": sum(cms) / ms_instr,
+                "note": "rank 0's device time between events around dist.all_reduce(grad) in the instrumented step (includes waiting "
+                        "for the slowest rank's backward pass)"}
+    algo.collective_events = None
     kms = [s.elapsed_time(t) for s, t in kev]
     rms = [s.elapsed_time(t) for s, t in rollout_events]
     k_ms = sum(kms) / len(kms)
@@ -473,7 +482,7 @@ def main():
                    "d2h_bytes_per_step": d2h_bytes, "steps": args.steps,
                    "note": "PPO.train_iteration with the parameters shipped from pinned host memory and parameters, loss statistics, "
                            "rewards and done flags read back to the host every step"},
-           "gpu_launches": launches, "clocks": clk,
+           "gpu_launches": launches, "clocks": clk, "nccl": nccl,
            "learner": {"tc_mode": tc_mode, "update_ms": ms_instr - sum(rms) / len(rms),
                        "note": "tc_mode 3: the 256-wide layers (forward, dX, dW; first layer k = 50 padded) on tcgen05 kind::tf32 with "
                                "every operand split as hi + lo and three products per k step (float32-accurate, csrc/tc_gemm3.cu); "
