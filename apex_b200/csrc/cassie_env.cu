@@ -35,7 +35,7 @@ template <typename T> __global__ void __launch_bounds__(32) k_env_reset(T *st, i
   const int e = blockIdx.x, lane = threadIdx.x;
   if (e >= n) return;
   ws_load(w, st + (size_t)e * S_WORDS, sti + (size_t)e * I_WORDS, lane);
-  cw_env_reset<T>(w, obs + (size_t)e * CW_OBS, traj, lane);
+  cw_env_reset<T>(w, obs + (size_t)e * cw_obs_dim(w.sti[I_VARIANT]), traj, lane);
   ws_store(w, st + (size_t)e * S_WORDS, sti + (size_t)e * I_WORDS, lane);
 }
 
@@ -45,7 +45,7 @@ template <typename T> __global__ void __launch_bounds__(32) k_env_reset_for_test
   const int e = blockIdx.x, lane = threadIdx.x;
   if (e >= n || (active && !active[e])) return;
   ws_load(w, st + (size_t)e * S_WORDS, sti + (size_t)e * I_WORDS, lane);
-  cw_env_reset_for_test<T>(w, obs + (size_t)e * CW_OBS, full, lane);
+  cw_env_reset_for_test<T>(w, obs + (size_t)e * cw_obs_dim(w.sti[I_VARIANT]), full, lane);
   ws_store(w, st + (size_t)e * S_WORDS, sti + (size_t)e * I_WORDS, lane);
 }
 
@@ -85,14 +85,15 @@ __global__ void __launch_bounds__(sizeof(T) == 4 ? CW_STEP_THREADS_F32 : 224) k_
   if (lane == 0) { w.bar_mask = bar_mask; w.bar_addr = bar_addr; }
   __syncwarp();
   T rew; int dn;
-  T *o = obs + (size_t)e * CW_OBS;
+  const int od = cw_obs_dim(w.sti[I_VARIANT]);
+  T *o = obs + (size_t)e * od;
   cw_env_step<T>(w, o, &rew, &dn, lane);
   int flag = dn ? 1 : 0;
   if (!dn && max_traj_len > 0 && w.sti[I_TIME] >= max_traj_len) flag |= 2;
   if (lane == 0) { reward[e] = rew; done[e] = flag; }
   if (flag && max_traj_len > 0) {
     __syncwarp();
-    if (term_obs) for (int k = lane; k < CW_OBS; k += 32) term_obs[(size_t)e * CW_OBS + k] = o[k];
+    if (term_obs) for (int k = lane; k < od; k += 32) term_obs[(size_t)e * od + k] = o[k];
     __syncwarp();
     cw_env_reset<T>(w, o, traj, lane);
   }

@@ -107,9 +107,12 @@ template <typename T> CW_FN void cw_clock_knots(T swing, T stance, T *x, T *phas
 }
 /* knot value k of clock `which`; stance_mode 1 ("grounded", installed by reset_for_test, cassie.py:701) puts +1 on the force
  * clocks and -1 on the velocity clocks at the double-stance knots 2, 3, 6, 7 (phase_function.py:53-56, 96-98) */
-template <typename T> CW_FN T cw_clock_y(int which, int k, int mode) {
-  return (mode == 1 && (k & 2)) ? ((which & 1) ? (T)-1 : (T)1) : (T)CWT(CW_CLOCK_Y)[which][k];
+template <typename T> CW_FN T cw_clock_y(int which, int k, int mode) { /* mode 2 "aerial": the opposite signs (phase_function.py:38-46) */
+  return (mode && (k & 2)) ? (((which & 1) != (mode == 2)) ? (T)-1 : (T)1) : (T)CWT(CW_CLOCK_Y)[which][k];
 }
+CW_FN int cw_env_variant(int v) { return v & 0xFF; }
+CW_FN int cw_cmd_profile(int v) { return (v >> 8) & 0xFF; }
+CW_FN int cw_obs_dim(int v) { return cw_cmd_profile(v) ? CW_OBS_PHASE : CW_OBS; }
 template <typename T> CW_FN T cw_clock_eval(const T *x, T P, int which, T phase, int mode) {
   T xa, xb, ya, yb;
   if (phase < x[0]) { xa = x[7] - P; ya = cw_clock_y<T>(which, 7, mode); xb = x[0]; yb = cw_clock_y<T>(which, 0, mode); }
@@ -156,8 +159,9 @@ template <typename T> CW_NOINL void cw_env_obs(CassieWs<T> &w, T *obs_out CW_LAN
   }
   T sp, cp;
   cw_sincos<T>((T)CW_TWO_PI * w.st[S_PHASE] / w.st[S_PHASELEN], &sp, &cp);
+  const int prof = cw_cmd_profile(w.sti[I_VARIANT]), nobs = prof ? CW_OBS_PHASE : CW_OBS, sm = w.sti[I_STANCEMODE];
   CW_FOR_LANES {
-    for (int o = lane; o < CW_OBS; o += 32) {
+    for (int o = lane; o < nobs; o += 32) {
       T v;
       if (o == 0) v = w.y[Y_PPOS + 2] - (T)0;
       else if (o < 5) v = no[o - 1];
@@ -170,8 +174,11 @@ template <typename T> CW_NOINL void cw_env_obs(CassieWs<T> &w, T *obs_out CW_LAN
       else if (o < 46) v = w.y[Y_JVEL + o - 40];
       else if (o == 46) v = sp;
       else if (o == 47) v = cp;
-      else if (o == 48) v = w.st[S_SPEED];
-      else v = w.st[S_SIDE];
+      else if (!prof) v = o == 48 ? w.st[S_SPEED] : w.st[S_SIDE];
+      else if (o == 48) v = w.st[S_SWING];
+      else if (o == 49) v = w.st[S_STANCE];
+      else if (o < 53) v = (T)(sm == (o == 50 ? 1 : (o == 51 ? 2 : 0))); /* encode_stance_mode: grounded, aerial, zero */
+      else v = o == 53 ? w.st[S_SPEED] : w.st[S_SIDE];
       obs_out[o] = v;
     }
   }
@@ -299,15 +306,39 @@ template <typename T> CW_FN void cw_set_clock(CassieWs<T> &w, T speed CW_LANE_PA
 /* ---------- CassieEnv.reset / CassieTrajEnv.reset ---------- */
 template <typename T> CW_NOINL void cw_env_reset(CassieWs<T> &w, T *obs_out, const CassieTraj<T> &traj CW_LANE_PARAM) {
   const uint32_t seed = (uint32_t)w.sti[I_SEED], env = (uint32_t)w.sti[I_ENVID], ctr0 = (uint32_t)w.sti[I_RNGCTR];
-  const int dyn = w.sti[I_DYNRAND], variant = w.sti[I_VARIANT];
+  const int dyn = w.sti[I_DYNRAND], variant = cw_env_variant(w.sti[I_VARIANT]), prof = cw_cmd_profile(w.sti[I_VARIANT]);
   /* Cassie-v0: speed ~ U[-0.3, 4] (cassie.py:525); CassieTraj-v0: random.randint(0, 40) / 10 (cassie_traj.py:608) */
   const T speed0 = variant == 0 ? cw_uniform<T>(cw_draw(seed, env, ctr0, 0), -0.3, 4.0)
                                 : (T)(uint32_t)(((uint64_t)cw_draw(seed, env, ctr0, 0) * 41u) >> 32) / (T)10;
-  cw_set_clock<T>(w, speed0 CW_LANE_ARG);
+  int nd = dyn ? 81 : 3; /* draws 0 .. nd + 1 belong to the clock profile (the last two: the second command draw) */
+  if (prof) {
+    /* command_profile "phase" (cassie.py:529-545): draws nd + 2 .. nd + 5 give swing / stance duration and the stance mode
+     * (random.randint(1, 50) / 100, randint(1, 30) / 100; "library": total = randint(3, 6) / 10, ratio = randint(2, 8) / 10 and the
+     * clock's speed randint(0, 30) / 10, which only this block would read) and np.random.choice(["grounded", "aerial", "zero"]) */
+    const uint32_t u0 = cw_draw(seed, env, ctr0, nd + 2), u1 = cw_draw(seed, env, ctr0, nd + 3), u2 = cw_draw(seed, env, ctr0, nd + 4);
+    double swing, stance;
+    if (prof == 2) {
+      const double total = (double)(3u + (uint32_t)(((uint64_t)u0 * 4u) >> 32)) / 10, ratio = (double)(2u + (uint32_t)(((uint64_t)u1 * 7u) >> 32)) / 10;
+      swing = cw_dmul(total, ratio);
+      stance = cw_dadd(total, -swing);
+    } else {
+      swing = (double)(1u + (uint32_t)(((uint64_t)u0 * 50u) >> 32)) / 100;
+      stance = (double)(1u + (uint32_t)(((uint64_t)u1 * 30u) >> 32)) / 100;
+    }
+    const uint32_t c = (uint32_t)(((uint64_t)u2 * 3u) >> 32);
+    const double P = cw_dmul(cw_dadd(cw_dmul(2, swing), cw_dmul(2, stance)), 40.0); /* create_phase_reward: total_duration * FREQ */
+    CW_FOR_LANES {
+      if (lane == 0) {
+        w.st[S_SWING] = (T)swing; w.st[S_STANCE] = (T)stance; w.st[S_PHASELEN] = (T)P;
+        w.sti[I_PHASEFLOOR] = (int)floor(P);
+        w.sti[I_STANCEMODE] = c == 0 ? 1 : (c == 1 ? 2 : 0);
+      }
+    }
+    CW_SYNC();
+  } else cw_set_clock<T>(w, speed0 CW_LANE_ARG);
   const T plen = w.st[S_PHASELEN];
   const uint32_t nph = (uint32_t)w.sti[I_PHASEFLOOR] + 1u;
   const T phase = (T)(uint32_t)(((uint64_t)cw_draw(seed, env, ctr0, 2) * nph) >> 32);
-  int nd = 3;
   if (dyn) {
     CW_FOR_LANES {
       { /* damping: pelvis, heel spring, plantar rod keep defaults (cassie.py:548-574) */
@@ -337,7 +368,6 @@ template <typename T> CW_NOINL void cw_env_reset(CassieWs<T> &w, T *obs_out, con
       else if (lane < 16) w.st[S_JENC + lane - 10] = cw_uniform<T>(cw_draw(seed, env, ctr0, 75 + lane - 10), -0.01, 0.01);
     }
     CW_SYNC();
-    nd = 81;
     cw_set_const<T>(w CW_LANE_ARG);
   }
   /* cassie_sim_set_const @0x7330: fixed pose, zero velocity, mj_forward */
@@ -374,7 +404,7 @@ template <typename T> CW_NOINL void cw_env_reset(CassieWs<T> &w, T *obs_out, con
     if (lane < 6) w.st[S_FOOTPOS + lane] = fp[lane];
     if (lane == 0) {
       w.st[S_ORIENT] = 0; w.st[S_SPEED] = speed1; w.st[S_SIDE] = side1;
-      w.sti[I_RNGCTR] = (int)(ctr0 + (uint32_t)((nd + 2 + 3) >> 2));
+      w.sti[I_RNGCTR] = (int)(ctr0 + (uint32_t)((nd + (prof ? 6 : 2) + 3) >> 2));
       w.sti[I_SIMSTEPS] = 1; /* cassie_sim_set_const zeroed the time, then the one sub-step above */
     }
   }

@@ -110,6 +110,7 @@ __device__ unsigned long long cw_prof[32];
 #define CW_NEFC 32 /* constraint-row capacity (njmax analogue): 12 equality + limits + contacts */
 #define CW_NCON 6
 #define CW_OBS 50
+#define CW_OBS_PHASE 55 /* command_profile "phase": clock 2, swing, stance, one-hot stance mode 3, speed 2 (cassie.py:267-271, 805-808) */
 #define CW_ACT 10
 #define CW_SIMRATE 50
 #define CW_LFOOT 13
@@ -139,9 +140,9 @@ enum {
 enum {
   I_DRIVEHIST = 0, I_TIME = 90, I_COUNTER = 91, I_HASPREV = 92, I_HASU = 93, I_DRIVEINIT = 94, I_JOINTINIT = 95,
   I_FLAGS = 96, I_STEPCOUNT = 97, I_RNGCTR = 98, I_ENVID = 99, I_SEED = 100, I_DYNRAND = 101, I_SOLVER_ITER = 102,
-  I_NCON = 103, I_NEFC = 104, I_VARIANT = 105 /* 0 Cassie-v0, 1 CassieTraj-v0 */, I_PHASEFLOOR = 106 /* floor(phaselen), from float64 */,
+  I_NCON = 103, I_NEFC = 104, I_VARIANT = 105 /* bits 0-7: 0 Cassie-v0, 1 CassieTraj-v0; bits 8-15: command profile 0 clock, 1 phase, 2 phase (library) */, I_PHASEFLOOR = 106 /* floor(phaselen), from float64 */,
   I_COST = 107 /* sum over the last env step's sub-steps of solver_iter * nefc: load-balancing key */,
-  I_STANCEMODE = 108 /* clock reward's stance_mode: 0 "zero", 1 "grounded" once reset_for_test has run (cassie.py:219,701) */,
+  I_STANCEMODE = 108 /* clock reward's stance_mode: 0 "zero", 1 "grounded" (also once reset_for_test has run, cassie.py:219,701), 2 "aerial" */,
   I_SIMSTEPS = 109 /* physics sub-steps since the simulator was last reset: sim.time() = that many additions of 0.0005 */,
   I_HOLDCMD = 110 /* != 0: env.step skips its random command changes (cassie.py:483-491); deterministic evaluation */,
   I_OVERFLOW = 111 /* sub-steps (since init) in which the row / contact capacity (CW_NEFC, CW_NCON) dropped something: a penetrating

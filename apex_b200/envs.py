@@ -35,8 +35,17 @@ class BatchedCassieEnv:
     def __init__(self, num_envs, device="cuda:0", dtype=torch.float32, seed=0, dynamics_randomization=True, simrate=50,
                  command_profile="clock", input_profile="full", reward="clock", max_traj_len=400, env_id0=0, history=0, balance=True,
                  **kwargs):
-        if simrate != 50 or command_profile != "clock" or input_profile != "full" or history != 0:
-            raise NotImplementedError("kernel is specialised for simrate=50, clock command, full input, history=0")
+        if simrate != 50 or command_profile not in ("clock", "phase") or input_profile != "full" or history != 0:
+            raise NotImplementedError("kernel is specialised for simrate=50, clock / phase command, full input, history=0")
+        # command_profile "phase" (cassie.py:184-198): the reward name only selects the phase input mode ("library" in the name) and
+        # becomes "clock"; "no_speed" / "early" variants are not on the kernel path
+        if command_profile == "phase":
+            if reward not in ("clock", "library_clock", "library"):
+                raise NotImplementedError("phase command profile: reward 'clock' (every part random) or 'library_clock'")
+            self._cmd_profile = 2 if "library" in reward else 1
+            reward = "clock"
+        else:
+            self._cmd_profile = 0
         if reward not in ("clock",):
             raise NotImplementedError("only the 'clock' reward (cassie/rewards/clock_rewards.py:6) is implemented")
         self.L = _lib.lib()
@@ -52,21 +61,26 @@ class BatchedCassieEnv:
         # cassie/cassie.py:236-265 (full input profile, clock command)
         base = [0.1, 1, -2, 3, -4, -10, -11, 12, 13, 14, -5, -6, 7, 8, 9, 15, -16, 17, -18, 19, -20, -26, -27, 28, 29, 30, -21,
                 -22, 23, 24, 25, 31, -32, 33, 37, 38, 39, 34, 35, 36, 43, 44, 45, 40, 41, 42]
-        self.mirrored_obs = base + [46, 47, 48, 49]
+        # clock: clock 2 + speed 2; phase: clock 2 + swing, stance + one-hot stance mode 3 + speed 2 (cassie.py:261-271): appended
+        # entries mirror onto themselves
+        self.obs_dim = 46 + (9 if self._cmd_profile else 4)
+        self.mirrored_obs = base + list(range(46, self.obs_dim))
         self.clock_inds = [46, 47]
         self.mirrored_acts = [-5, -6, 7, 8, 9, -0.1, -1, 2, 3, 4]
-        self.observation_space = np.zeros(50)
+        self.observation_space = np.zeros(self.obs_dim)
         self.action_space = np.zeros(10)
         n = self.num_envs
         self.st = torch.zeros((n, self.L.apex_cassie_state_words()), dtype=dtype, device=self.device)
         self.sti = torch.zeros((n, self.L.apex_cassie_istate_words()), dtype=torch.int32, device=self.device)
-        self.obs = torch.zeros((n, 50), dtype=dtype, device=self.device)
-        self.term_obs = torch.zeros((n, 50), dtype=dtype, device=self.device)
+        self.obs = torch.zeros((n, self.obs_dim), dtype=dtype, device=self.device)
+        self.term_obs = torch.zeros((n, self.obs_dim), dtype=dtype, device=self.device)
         self.rew = torch.zeros((n,), dtype=dtype, device=self.device)
         self.done = torch.zeros((n,), dtype=torch.int32, device=self.device)
         self.balance = bool(balance)
         self.order = torch.arange(n, dtype=torch.int32, device=self.device)
         self._init_state(int(seed) & 0xFFFFFFFF, int(env_id0))
+        if self._cmd_profile:  # bits 8-15 of the variant word select the command profile: observation width, reset draws
+            self.field("variant")[:, 0] |= self._cmd_profile << 8
 
     def _init_state(self, seed, env_id0):
         with torch.cuda.device(self.device):
@@ -107,6 +121,8 @@ class BatchedCassieEnv:
         """CassieEnv.update_speed (cassie/cassie.py:751-768, clock command): per env clip the commands, rebuild swing / stance /
         period from the (signed) speed and rescale the phase with the reference's truncation.  new_speed: scalar or [N];
         active: optional mask, envs with active == 0 keep their clock."""
+        if self._cmd_profile:
+            raise NotImplementedError("update_speed for the phase command profile (cassie.py:756-762) is not on the kernel path")
         f = self.field
         # the period in float64: the phase rescale below is sensitive to its last bit (a float32 env stores a rounded copy)
         old = self._plen64 if getattr(self, "_plen64", None) is not None else f("phaselen")[:, 0].double()
@@ -149,7 +165,7 @@ class BatchedCassieEnv:
         return None, 0, 0
 
     def step(self, action, f_term=0, rew_out=None, done_out=None, active=None):
-        """action [N, 10] on the device -> (obs [N, 50], reward [N], done [N] int32 (bit0 terminal, bit1 time-out), {}).
+        """action [N, 10] on the device -> (obs [N, 50] (55 with the phase command profile), reward [N], done [N] int32 (bit0 terminal, bit1 time-out), {}).
         rew_out / done_out: optional contiguous device tensors that receive reward and done (e.g. rollout-buffer rows).
         active: optional int32 mask, envs with active == 0 are skipped (done = 4)."""
         a = action.to(device=self.device, dtype=self.dtype).contiguous()

@@ -36,6 +36,12 @@ extern "C" {
 
 #define APEX_CASSIE_OBS 50
 #define APEX_CASSIE_ACT 10
+/* command_profile "phase" (cassie/cassie.py:184-198, 267-271, 529-545, 805-808): set bits 8-15 of the int field "variant"
+ * (apex_cassie_layout("variant")) of every env to 1 (swing / stance duration and stance mode drawn at random on reset) or 2
+ * (the "library" mode: total duration, swing ratio, speed) after apex_cassie_env_init.  Observation rows are then
+ * APEX_CASSIE_OBS_PHASE wide — [46 robot state | sin, cos clock | swing, stance duration | one-hot stance mode (grounded, aerial,
+ * zero) | speed, side speed] — in every obs / term_obs argument below, and the clock reward uses the drawn durations and mode. */
+#define APEX_CASSIE_OBS_PHASE 55
 
 /* size of the per-env persistent record: st is [n][state_words] reals, sti is [n][istate_words] int32 */
 int apex_cassie_state_words(void);

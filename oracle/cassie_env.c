@@ -139,7 +139,10 @@ double ce_clock_eval_mode(double swing, double stance, int stance_mode, int whic
   double x[8], P;
   ce_clock_knots(swing, stance, x, &P);
   double yv[8];
-  for (int k = 0; k < 8; k++) yv[k] = (stance_mode == 1 && (k & 2)) ? ((which & 1) ? -1.0 : 1.0) : CLOCK_Y[which][k];
+  /* double-stance knots 2, 3, 6, 7 (phase_function.py:38-56, 85-103): "grounded" +1 on the force clocks, -1 on the velocity clocks;
+   * "aerial" the opposite; "zero" 0 */
+  for (int k = 0; k < 8; k++)
+    yv[k] = (stance_mode && (k & 2)) ? (((which & 1) != (stance_mode == 2)) ? -1.0 : 1.0) : CLOCK_Y[which][k];
   double xa, xb, ya, yb;
   if (phase < x[0]) { xa = x[7] - P; ya = yv[7]; xb = x[0]; yb = yv[0]; }
   else if (phase >= x[7]) { xa = x[7]; ya = yv[7]; xb = x[0] + P; yb = yv[0]; }
@@ -162,6 +165,8 @@ void ce_env_init(ce_env_t *e, uint32_t seed, uint32_t env_id, int dyn_rand) {
   e->seed = seed; e->env_id = env_id; e->rng_ctr = 0; e->dyn_rand = dyn_rand;
   e->phaselen = 32; e->phase_add = 1;
 }
+void ce_env_set_command_profile(ce_env_t *e, int cmd_profile) { e->cmd_profile = cmd_profile; }
+int ce_env_obs_dim(const ce_env_t *e) { return e->cmd_profile ? CE_OBS_PHASE : CE_OBS; }
 
 void ce_clock_from_speed(double speed, double *swing, double *stance, double *phaselen);
 void ce_clock_from_speed_signed(double speed, double *swing, double *stance, double *phaselen);
@@ -221,6 +226,13 @@ void ce_env_obs(ce_env_t *e, double *obs) { /* get_full_state, cassie.py:787-859
   for (int k = 0; k < 6; k++) obs[o++] = y->joint_vel[k];
   obs[o++] = sin(TWO_PI * e->phase / e->phaselen);
   obs[o++] = cos(TWO_PI * e->phase / e->phaselen);
+  if (e->cmd_profile) { /* cassie.py:805-808, encode_stance_mode (phase_function.py:138-144): grounded, aerial, zero */
+    obs[o++] = e->swing_duration;
+    obs[o++] = e->stance_duration;
+    obs[o++] = e->stance_mode == 1;
+    obs[o++] = e->stance_mode == 2;
+    obs[o++] = e->stance_mode == 0;
+  }
   obs[o++] = e->speed;
   obs[o++] = e->side_speed;
 }
@@ -391,12 +403,33 @@ static void draw_reset(ce_env_t *e, ce_reset_draws_t *dr) {
   }
   dr->speed1 = rng_uniform(&r, -0.3, 4.0);
   dr->side_speed1 = rng_uniform(&r, -0.3, 0.3);
+  dr->swing = -1;
+  if (e->cmd_profile) /* drawn last, and only for the phase command profile: the clock profile's stream is unchanged */
+    for (int k = 0; k < 4; k++) dr->phase_u32s[k] = rng_u32(&r);
 }
+static uint32_t scale_u32(uint32_t u, uint32_t n) { return (uint32_t)(((uint64_t)u * n) >> 32); }
 
 void ce_env_reset_with(ce_env_t *e, const ce_reset_draws_t *dr, double *obs) { /* cassie.py:523-680 */
   e->speed = dr->speed0;
   e->side_speed = dr->side_speed0;
-  set_clock(e, e->speed);
+  if (e->cmd_profile) { /* cassie.py:529-545 */
+    if (dr->swing >= 0) { e->swing_duration = dr->swing; e->stance_duration = dr->stance; e->stance_mode = dr->stance_mode; }
+    else if (e->cmd_profile == 2) { /* "library": speed randint(0, 30) / 10, total randint(3, 6) / 10, ratio randint(2, 8) / 10 */
+      e->speed = (double)scale_u32(dr->phase_u32s[3], 31) / 10;
+      double total = (double)(3 + scale_u32(dr->phase_u32s[0], 4)) / 10, ratio = (double)(2 + scale_u32(dr->phase_u32s[1], 7)) / 10;
+      e->swing_duration = total * ratio;
+      e->stance_duration = total - e->swing_duration;
+    } else { /* randint(1, 50) / 100, randint(1, 30) / 100 */
+      e->swing_duration = (double)(1 + scale_u32(dr->phase_u32s[0], 50)) / 100;
+      e->stance_duration = (double)(1 + scale_u32(dr->phase_u32s[1], 30)) / 100;
+    }
+    if (dr->swing < 0) { /* np.random.choice(["grounded", "aerial", "zero"]) -> 1, 2, 0 */
+      const uint32_t c = scale_u32(dr->phase_u32s[2], 3);
+      e->stance_mode = c == 0 ? 1 : (c == 1 ? 2 : 0);
+    }
+    double x[8];
+    ce_clock_knots(e->swing_duration, e->stance_duration, x, &e->phaselen); /* create_phase_reward: phaselength = total * FREQ */
+  } else set_clock(e, e->speed);
   e->phase = dr->phase >= 0 ? (double)dr->phase /* random.randint(0, floor(phaselen)), cassie.py:561 */
                             : (double)(uint32_t)(((uint64_t)dr->phase_u32 * ((uint32_t)floor(e->phaselen) + 1)) >> 32);
   e->time = 0; e->counter = 0;
@@ -539,20 +572,21 @@ void ce_batch_init(ce_env_t *envs, int n, uint32_t seed, int dyn_rand, int nthre
 }
 void ce_batch_reset(ce_env_t *envs, int n, double *obs, int nthreads) {
 #pragma omp parallel for num_threads(nthreads) schedule(static)
-  for (int i = 0; i < n; i++) ce_env_reset(&envs[i], obs + (size_t)i * CE_OBS);
+  for (int i = 0; i < n; i++) ce_env_reset(&envs[i], obs + (size_t)i * ce_env_obs_dim(&envs[0]));
 }
 void ce_batch_step(ce_env_t *envs, int n, const double *actions, double *obs, double *rew, int *done, int max_traj_len,
                    double *term_obs, int nthreads) {
+  const int od = n > 0 ? ce_env_obs_dim(&envs[0]) : CE_OBS;
 #pragma omp parallel for num_threads(nthreads) schedule(dynamic, 1)
   for (int i = 0; i < n; i++) {
     int dn;
-    ce_env_step(&envs[i], actions + (size_t)i * CE_ACT, obs + (size_t)i * CE_OBS, rew + i, &dn);
+    ce_env_step(&envs[i], actions + (size_t)i * CE_ACT, obs + (size_t)i * od, rew + i, &dn);
     int flag = dn ? 1 : 0;
     if (!dn && max_traj_len > 0 && envs[i].time >= max_traj_len) flag |= 2;
     done[i] = flag;
     if (flag && max_traj_len > 0) {
-      if (term_obs) memcpy(term_obs + (size_t)i * CE_OBS, obs + (size_t)i * CE_OBS, sizeof(double) * CE_OBS);
-      ce_env_reset(&envs[i], obs + (size_t)i * CE_OBS);
+      if (term_obs) memcpy(term_obs + (size_t)i * od, obs + (size_t)i * od, sizeof(double) * od);
+      ce_env_reset(&envs[i], obs + (size_t)i * od);
     }
   }
 }

@@ -17,7 +17,8 @@
 #include <stdint.h>
 #include "cassie_phys.h"
 
-#define CE_OBS 50
+#define CE_OBS 50       /* clock command profile, full input profile */
+#define CE_OBS_PHASE 55 /* phase command profile: clock 2, swing, stance, one-hot stance mode 3, speed 2 (cassie.py:267-271, 805-808) */
 #define CE_ACT 10
 
 typedef struct { /* the slice of state_out_t (include/state_out_t.h:24-78) the env reads */
@@ -56,7 +57,9 @@ typedef struct {
   int variant;
   const double *traj;
   int traj_rows, traj_len;
-  int stance_mode; /* 0 "zero" (reward "clock", cassie.py:219), 1 "grounded" once reset_for_test has run (cassie.py:701) */
+  int stance_mode; /* 0 "zero" (reward "clock", cassie.py:219), 1 "grounded" (also installed by reset_for_test, cassie.py:701), 2 "aerial" */
+  int cmd_profile; /* 0 command_profile "clock"; 1 "phase" (reset draws swing / stance / stance mode, cassie.py:540-545); 2 "phase" with
+                    * phase_input_mode "library" (reward name contains "library", cassie.py:529-539, 188-191) */
 } ce_env_t;
 
 /* The random draws of one reset / one step (cassie.py:523-680, :483-491).  ce_env_reset / ce_env_step fill them from the
@@ -68,6 +71,11 @@ typedef struct {
   uint32_t phase_u32;
   double damping[CM_NV], mass[CM_NBODY], friction[3], roll, pitch, menc_noise[10], jenc_noise[6]; /* dyn_rand only */
   double speed1, side_speed1; /* second command draw (cassie.py:669-670) */
+  /* command_profile "phase" (cassie.py:529-545): swing / stance durations and stance mode as the reference drew them (swing >= 0),
+   * or swing < 0: derive them from the four raw draws below */
+  double swing, stance;
+  int stance_mode;
+  uint32_t phase_u32s[4];
 } ce_reset_draws_t;
 typedef struct {
   int hit[3];                 /* randint(300) == 0, randint(100) == 0, randint(300) == 0 */
@@ -88,6 +96,8 @@ void ce_clock_from_speed(double speed, double *swing, double *stance, double *ph
 double ce_clock_eval(double swing, double stance, int which, double phase); /* which: 0 r_frc 1 r_vel 2 l_frc 3 l_vel */
 double ce_clock_eval_mode(double swing, double stance, int stance_mode, int which, double phase);
 void ce_env_init(ce_env_t *e, uint32_t seed, uint32_t env_id, int dyn_rand);
+void ce_env_set_command_profile(ce_env_t *e, int cmd_profile); /* 0 clock, 1 phase, 2 phase (library) */
+int ce_env_obs_dim(const ce_env_t *e);
 void ce_env_reset(ce_env_t *e, double *obs);
 void ce_env_set_trajectory(ce_env_t *e, const double *table, int rows, int len); /* switches the env to CassieTraj-v0 */
 void ce_batch_set_trajectory(ce_env_t *envs, int n, const double *table, int rows, int len);

@@ -13,18 +13,23 @@ def dp(a):
 class OracleBatch:
     """N oracle environments (oracle/cassie_env.c) stepped on the host."""
 
-    def __init__(self, n, seed, dyn_rand, threads=8, trajectory=None):
+    def __init__(self, n, seed, dyn_rand, threads=8, trajectory=None, command_profile=0):
         self.L = P.lib()
         self.n, self.threads = n, threads
-        self.buf = (C.c_char * (self.L.ce_sizeof_env() * n))()
+        size = self.L.ce_sizeof_env()
+        self.buf = (C.c_char * (size * n))()
         self.L.ce_batch_init(self.buf, n, C.c_uint(seed), int(dyn_rand), threads)
+        if command_profile:  # 1 phase, 2 phase (library)
+            for i in range(n):
+                self.L.ce_env_set_command_profile(C.c_void_p(C.addressof(self.buf) + i * size), int(command_profile))
         if trajectory is not None:  # CassieTraj-v0
             self.table, tlen = trajectory
             self.L.ce_batch_set_trajectory(self.buf, n, dp(self.table), self.table.shape[0], int(tlen))
-        self.obs = np.zeros((n, 50))
+        od = 55 if command_profile else 50
+        self.obs = np.zeros((n, od))
         self.rew = np.zeros(n)
         self.done = np.zeros(n, dtype=np.int32)
-        self.term_obs = np.zeros((n, 50))
+        self.term_obs = np.zeros((n, od))
 
     def reset(self):
         self.L.ce_batch_reset(self.buf, self.n, dp(self.obs), self.threads)
@@ -41,7 +46,8 @@ class ResetDraws(C.Structure):  # ce_reset_draws_t (oracle/cassie_env.h)
     _fields_ = [("speed0", C.c_double), ("side_speed0", C.c_double), ("phase", C.c_int), ("phase_u32", C.c_uint32),
                 ("damping", C.c_double * 32), ("mass", C.c_double * 26), ("friction", C.c_double * 3), ("roll", C.c_double),
                 ("pitch", C.c_double), ("menc_noise", C.c_double * 10), ("jenc_noise", C.c_double * 6),
-                ("speed1", C.c_double), ("side_speed1", C.c_double)]
+                ("speed1", C.c_double), ("side_speed1", C.c_double),
+                ("swing", C.c_double), ("stance", C.c_double), ("stance_mode", C.c_int), ("phase_u32s", C.c_uint32 * 4)]
 
 
 class StepDraws(C.Structure):  # ce_step_draws_t
@@ -51,19 +57,23 @@ class StepDraws(C.Structure):  # ce_step_draws_t
 class OracleEnv:
     """One oracle environment driven with injected draws (replay of episodes recorded from the reference's CassieEnv)."""
 
-    def __init__(self, dyn_rand, trajectory=None):
+    def __init__(self, dyn_rand, trajectory=None, command_profile=0):
         self.L = P.lib()
         self.buf = (C.c_char * self.L.ce_sizeof_env())()
         self.L.ce_env_init(self.buf, C.c_uint(0), C.c_uint(0), int(dyn_rand))
+        self.L.ce_env_set_command_profile(self.buf, int(command_profile))  # 0 clock, 1 phase, 2 phase (library)
         if trajectory is not None:  # CassieTraj-v0: (decimated table [rows, 67], rows of the full trajectory)
             self.table, tlen = trajectory
             self.L.ce_env_set_trajectory(self.buf, dp(self.table), self.table.shape[0], int(tlen))
         self.env = C.cast(self.buf, C.c_void_p)
-        self.obs = np.zeros(50)
+        self.obs = np.zeros(self.L.ce_env_obs_dim(self.buf))
 
-    def reset_with(self, scalar, damping, mass, friction, tilt, menc, jenc):
+    def reset_with(self, scalar, damping, mass, friction, tilt, menc, jenc, phase=None):
         d = ResetDraws()
         d.speed0, d.side_speed0, d.phase, d.speed1, d.side_speed1 = scalar[0], scalar[1], int(scalar[2]), scalar[4], scalar[5]
+        d.swing = -1.0
+        if phase is not None:  # command_profile "phase": (swing, stance, stance mode) as the reference drew them
+            d.swing, d.stance, d.stance_mode = float(phase[0]), float(phase[1]), int(phase[2])
         d.damping[:], d.mass[:], d.friction[:] = list(damping), list(mass), list(friction)
         d.roll, d.pitch = tilt
         d.menc_noise[:], d.jenc_noise[:] = list(menc), list(jenc)

@@ -8,10 +8,11 @@ from tests.oracle_util import OracleBatch
 pytestmark = pytest.mark.gpu
 
 
-def _run(dtype, dyn, n=16, steps=12, seed=11):
+def _run(dtype, dyn, n=16, steps=12, seed=11, command_profile="clock", reward="clock", max_traj_len=400):
     from apex_b200.envs import BatchedCassieEnv
-    env = BatchedCassieEnv(n, dtype=dtype, seed=seed, dynamics_randomization=dyn)
-    ora = OracleBatch(n, seed, dyn)
+    env = BatchedCassieEnv(n, dtype=dtype, seed=seed, dynamics_randomization=dyn, command_profile=command_profile, reward=reward,
+                           max_traj_len=max_traj_len)
+    ora = OracleBatch(n, seed, dyn, command_profile=env._cmd_profile)
     o_g = env.reset().cpu().numpy().astype(np.float64)
     o_c = ora.reset().copy()
     rng = np.random.default_rng(3)
@@ -19,7 +20,7 @@ def _run(dtype, dyn, n=16, steps=12, seed=11):
     for k in range(steps):
         act = rng.normal(size=(n, 10)) * 0.3
         og, rg, dg, _ = env.step(torch.as_tensor(act, dtype=dtype, device=env.device))
-        oc, rc, dc = ora.step(act)
+        oc, rc, dc = ora.step(act, max_traj_len)
         og, rg, dg = og.cpu().numpy().astype(np.float64), rg.cpu().numpy().astype(np.float64), dg.cpu().numpy()
         out["done_mismatch"] += int((dg != dc).sum())
         out["obs"].append(np.linalg.norm(og - oc, axis=1) / np.linalg.norm(oc, axis=1))
@@ -42,6 +43,40 @@ def test_env_f64_dynrand_matches_oracle():
     assert out["done_mismatch"] == 0
     assert np.max(out["obs"]) < 1e-8, np.max(out["obs"])
     assert np.max(out["rew"]) < 1e-8
+
+
+@pytest.mark.parametrize("reward,dyn", [("clock", False), ("clock", True), ("library_clock", True)])
+def test_phase_command_profile_f64_matches_oracle(reward, dyn):
+    """command_profile="phase" (the oracle side is pinned to the reference's own Python by
+    tests/test_oracle_cpu.py::test_phase_command_profile_matches_the_reference_python): 55-wide observations with the drawn swing /
+    stance durations and the one-hot stance mode, the clock reward for all three stance modes, in-kernel episode resets that redraw
+    them (time limit 6 so that every env resets twice), both phase input modes."""
+    n = 48
+    out, env = _run(torch.float64, dyn=dyn, n=n, steps=14, seed=23, command_profile="phase", reward=reward, max_traj_len=6)
+    assert env.obs.shape == (n, 55) and len(env.mirrored_obs) == 55 and env.observation_space.shape == (55,)
+    assert out["reset"] < 1e-10
+    assert out["done_mismatch"] == 0
+    assert np.max(out["obs"]) < 1e-8, np.max(out["obs"])
+    assert np.max(out["rew"]) < 1e-8
+    o = env.obs.cpu().numpy()
+    assert (o[:, 50:53].sum(1) == 1).all() and len({tuple(r) for r in o[:, 50:53]}) == 3  # all three stance modes are drawn
+    if reward == "clock":
+        assert o[:, 48].min() >= 0.01 and o[:, 48].max() <= 0.5 + 1e-12 and o[:, 49].max() <= 0.3 + 1e-12
+    else:
+        assert (o[:, 48] + o[:, 49]).max() <= 0.6 + 1e-9 and (o[:, 48] + o[:, 49]).min() >= 0.3 - 1e-9
+
+
+def test_phase_command_profile_trains():
+    """One small PPO iteration on the 55-wide observations (actor / critic first layers of width 55, mirror table of 55 entries)."""
+    from apex_b200.envs import BatchedCassieEnv
+    from apex_b200.policies import Gaussian_FF_Actor, FF_V
+    from apex_b200.ppo import PPO
+    torch.manual_seed(0)
+    actor, critic = Gaussian_FF_Actor(55, 10, fixed_std=torch.ones(10) * float(np.exp(-1.5))), FF_V(55)
+    algo = PPO(dict(num_steps=128 * 16, minibatch_size=512, epochs=1, seed=0))
+    buf, scal = algo.train_iteration(lambda: BatchedCassieEnv(128, device="cuda:0", seed=0, command_profile="phase"), actor, critic)
+    assert all(np.isfinite(scal)) and torch.isfinite(algo.flat).all()
+    assert buf.obs.shape[-1] == 55
 
 
 def test_env_f32_one_step_close_to_oracle():

@@ -383,6 +383,42 @@ def test_env_layer_matches_the_reference_python(tag, dyn, traj):
     assert t == len(f("reward")) and f("done").sum() >= 1  # at least one episode ends by falling
 
 
+@pytest.mark.parametrize("tag,dyn,profile", [("phase_plain", False, 1), ("phase_dynrand", True, 1), ("library_plain", False, 2)])
+def test_phase_command_profile_matches_the_reference_python(tag, dyn, profile):
+    """command_profile="phase" (SURVEY §8f rank 4): 55 observations (clock, swing / stance duration, one-hot stance mode, speeds;
+    cassie.py:267-271, 805-808), reset drawing the swing / stance durations and the stance mode (cassie.py:529-545, both the
+    every-part-random and the "library" mode) and the clock reward built for them (phase_function.py, grounded / aerial / zero),
+    recorded from the reference's cassie/cassie.py (tests/golden/make_env_golden_phase.py) and replayed through
+    oracle/cassie_env.c with the reference's draws injected."""
+    from tests.oracle_util import OracleEnv
+    g = np.load(os.path.join(G, "env_episodes_phase.npz"))
+    f = lambda k: g[f"{tag}.{k}"]
+    env = OracleEnv(dyn, command_profile=profile)
+    assert env.obs.shape == (55,) and f("obs").shape[1] == 55
+    assert {int(m) for m in f("reset_phase")[:, 2]} >= ({0, 1, 2} if tag != "phase_dynrand" else {0, 1})
+    t = 0
+    for ep, n in enumerate(f("ep_len")):
+        obs = env.reset_with(f("reset_scalar")[ep], f("reset_damping")[ep], f("reset_mass")[ep], f("reset_friction")[ep],
+                             f("reset_tilt")[ep], f("reset_menc")[ep], f("reset_jenc")[ep], phase=f("reset_phase")[ep])
+        assert np.abs(obs - f("reset_obs")[ep]).max() < 1e-10, (ep, int(np.abs(obs - f("reset_obs")[ep]).argmax()))
+        for k in range(n):
+            obs, rew, done = env.step_with(f("action")[t], f("step_hit")[t], f("step_val")[t])
+            qpos, qvel = env.qpos_qvel()
+            assert np.abs(qpos - f("qpos")[t]).max() < 1e-10 and np.abs(qvel - f("qvel")[t]).max() < 1e-8, (ep, k)
+            assert done == f("done")[t], (ep, k)
+            assert abs(rew - f("reward")[t]) < 1e-10, (ep, k, rew, f("reward")[t])
+            err = np.abs(obs - f("obs")[t])
+            assert err.max() < 1e-9, (ep, k, int(err.argmax()), err.max())
+            t += 1
+    assert t == len(f("reward")) and f("done").sum() >= 1
+    # the env's own draws (no injection) stay inside the reference's ranges
+    own = OracleEnv(dyn, command_profile=profile)
+    own.L.ce_env_reset(own.buf, own.obs.ctypes.data_as(__import__("ctypes").c_void_p))
+    swing, stance = own.obs[48], own.obs[49]
+    assert (0.06 - 1e-9 <= swing <= 0.48 + 1e-9 and swing + stance <= 0.6 + 1e-9) if profile == 2 else (0.01 <= swing <= 0.5 and 0.01 <= stance <= 0.3)
+    assert own.obs[50:53].sum() == 1.0
+
+
 def _eval_schedule():
     """The schedule tests/golden/make_eval_golden.py drove the reference env with (imported from that script)."""
     src = open(os.path.join(G, "make_eval_golden.py")).read()
