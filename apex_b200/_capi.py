@@ -79,6 +79,11 @@ def lib():
         L.apex_set_tc_persistent.restype = None
         L.apex_set_gemm_large_tiles.argtypes = [i]
         L.apex_set_gemm_large_tiles.restype = None
+        L.apex_adam_step_dev.argtypes = [vp, vp, vp, vp, i, vp, fl, fl, fl, fl, fl, fl, vp, vp]
+        L.apex_td3_action_dev.argtypes = [vp, vp, i, i, i, fl, fl, fl, u, vp, vp, vp, vp]
+        L.apex_replay_sample.argtypes = [vp, i, vp, u, vp, vp]
+        L.apex_counter_add.argtypes = [vp, i, vp]
+        L.apex_adam_step_dev.restype = L.apex_td3_action_dev.restype = L.apex_replay_sample.restype = L.apex_counter_add.restype = i
         L.apex_set_head_kernels.argtypes = [i]
         L.apex_set_head_kernels.restype = None
         L.apex_set_tc_mode.argtypes = [i]

@@ -587,6 +587,34 @@ __global__ void k_adam(float *__restrict__ p, const float *__restrict__ g, float
   p[i] -= (lr / bc1) * (mi / denom);
 }
 
+/* The same step with the Adam step count read from device memory: an optimizer step that sits inside a CUDA graph (TD3 at the
+ * reference's batch of 256 is launch-bound) cannot take the count by value. */
+__global__ void k_adam_dev(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m, float *__restrict__ v, int n,
+                           const double *__restrict__ sumsq, float gscale, float max_norm, float lr, float beta1, float beta2, float eps,
+                           const int *__restrict__ step) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float t = (float)(*step), bc1 = 1.f - powf(beta1, t), bc2 = 1.f - powf(beta2, t);
+  const float norm = sqrtf((float)(*sumsq)) * gscale;
+  const float coef = fminf(max_norm / (norm + 1e-6f), 1.0f);
+  const float gi = g[i] * gscale * coef;
+  const float mi = beta1 * m[i] + (1.f - beta1) * gi, vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+  m[i] = mi; v[i] = vi;
+  const float denom = sqrtf(vi) / sqrtf(bc2) + eps;
+  p[i] -= (lr / bc1) * (mi / denom);
+}
+extern "C" int apex_adam_step_dev(float *p, const float *g, float *m, float *v, int n, const double *sumsq, float gscale, float max_norm,
+                                  float lr, float beta1, float beta2, float eps, const int *step_dev, void *stream) {
+  if (n <= 0) return 0;
+  k_adam_dev<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, sumsq, gscale, max_norm, lr, beta1, beta2, eps, step_dev);
+  return last_err();
+}
+__global__ void k_counter_add(int *c, int inc) { *c += inc; }
+extern "C" int apex_counter_add(int *counter_dev, int inc, void *stream) {
+  k_counter_add<<<1, 1, 0, (cudaStream_t)stream>>>(counter_dev, inc);
+  return last_err();
+}
+
 extern "C" int apex_grad_sumsq(const float *g, int n, double *out, void *stream) {
   if (n <= 0) return 0;
   k_sumsq<<<min(148, (n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(g, n, out);
@@ -791,9 +819,10 @@ extern "C" int apex_replay_gather(const float *storage, const int64_t *idx, int 
  * tanh_out (optional) receives tanh(pre) for the backward pass. */
 __global__ void k_td3_action(const float *__restrict__ pre, const float *__restrict__ state, const float *__restrict__ noise, int rows,
                              int S, int A, float max_a, float policy_noise, float noise_clip, uint32_t seed, uint32_t step,
-                             float *__restrict__ sa, float *__restrict__ tanh_out) {
+                             float *__restrict__ sa, float *__restrict__ tanh_out, const int *__restrict__ step_dev) {
   const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long)rows * (S + A)) return;
+  if (step_dev) step = (uint32_t)*step_dev; /* CUDA-graph replays: the Philox counter lives in device memory */
   const int r = (int)(t / (S + A)), j = (int)(t % (S + A));
   if (j < S) { sa[t] = state[(long)r * S + j]; return; }
   const int a = j - S;
@@ -816,7 +845,30 @@ extern "C" int apex_td3_action(const float *pre, const float *state, const float
   if (rows <= 0) return 0;
   const long tot = (long)rows * (S + A);
   k_td3_action<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(pre, state, noise, rows, S, A, max_a, policy_noise,
-                                                                              noise_clip, seed, step, sa, tanh_out);
+                                                                              noise_clip, seed, step, sa, tanh_out, nullptr);
+  return last_err();
+}
+extern "C" int apex_td3_action_dev(const float *pre, const float *state, int rows, int S, int A, float max_a, float policy_noise,
+                                   float noise_clip, unsigned seed, const int *step_dev, float *sa, float *tanh_out, void *stream) {
+  if (rows <= 0) return 0;
+  const long tot = (long)rows * (S + A);
+  k_td3_action<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(pre, state, nullptr, rows, S, A, max_a, policy_noise,
+                                                                              noise_clip, seed, 0u, sa, tanh_out, step_dev);
+  return last_err();
+}
+/* ReplayBuffer.sample's np.random.randint(0, len(storage), batch_size) (rl/utils/remote_replay.py:78-79) on the device: uniform rows
+ * with replacement from Philox(seed, i, *ctr_dev), the buffer's fill level read from device memory (both change between graph replays) */
+__global__ void k_replay_sample(int64_t *__restrict__ idx, int rows, const int *__restrict__ size_dev, uint32_t seed,
+                                const int *__restrict__ ctr_dev) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows) return;
+  uint32_t u[4];
+  philox4(seed ^ 0x5bd1e995u, (uint32_t)i, (uint32_t)*ctr_dev, 0u, u);
+  idx[i] = (int64_t)(((uint64_t)u[0] * (uint64_t)(uint32_t)*size_dev) >> 32);
+}
+extern "C" int apex_replay_sample(int64_t *idx, int rows, const int *size_dev, unsigned seed, const int *ctr_dev, void *stream) {
+  if (rows <= 0) return 0;
+  k_replay_sample<<<(rows + 255) / 256, 256, 0, (cudaStream_t)stream>>>(idx, rows, size_dev, seed, ctr_dev);
   return last_err();
 }
 

@@ -481,11 +481,15 @@ int apex_tc3_linear(const float *A, long lda, int M, int K, const float *w, long
   cudaError_t err = cudaSuccess;
   const int units = (Kp / NT_KS) * NT_N * 8;
   k_tc3_w_image<<<(units + 255) / 256, 256, 0, s>>>(w, swn, swk, K, Kp, img);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
   const int tiles = (M + 127) / 128, sms = sm_count(), grid = tiles < sms ? tiles : sms;
   const int smem = 2 * NT_STAGE + 8 * 4096; /* two stages + the epilogue's staging tiles */
 #define NT_LAUNCH(P, V)                                                                                                   \
   {                                                                                                                       \
-    err = cudaFuncSetAttribute(k_tc3_nt<P, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);                        \
+    static bool attr_set[64]; /* once per instantiation and device: nothing but launches remains for a later CUDA-graph capture */ \
+    if (!attr_set[dev]) { err = cudaFuncSetAttribute(k_tc3_nt<P, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr_set[dev] = err == cudaSuccess; } \
     if (err == cudaSuccess)                                                                                               \
       k_tc3_nt<P, V><<<grid, NT_THREADS, smem, s>>>(A, lda, M, K, Kp, img, bias, relu, mask, ldmask, C, ldc, tc3_debug); \
   }
@@ -512,9 +516,14 @@ int apex_tc3_outer(const float *A, long lda, const float *B, long ldb, int nb, l
   long rpc = (R + sms - 1) / sms;
   rpc = (rpc + TN_KS - 1) / TN_KS * TN_KS;
   const int grid = (int)((R + rpc - 1) / rpc), smem = TN_NSTAGE * TN_STAGE;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
 #define TN_LAUNCH(P, NBT)                                                                                               \
   {                                                                                                                     \
-    err = cudaFuncSetAttribute(k_tc3_tn<P, NBT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);                    \
+    static bool attr_set[64];                                                                                           \
+    err = cudaSuccess;                                                                                                  \
+    if (!attr_set[dev]) { err = cudaFuncSetAttribute(k_tc3_tn<P, NBT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr_set[dev] = err == cudaSuccess; } \
     if (err == cudaSuccess) k_tc3_tn<P, NBT><<<grid, TN_THREADS, smem, s>>>(A, lda, B, ldb, nb, R, (int)rpc, C, ldc, tc3_debug); \
   }
   if (passes == 3) { if (nb == 256) TN_LAUNCH(3, 256) else TN_LAUNCH(3, 64) }

@@ -235,18 +235,26 @@ def extra_cfg3_td3(dev):
     rb.storage.copy_(torch.rand(rb.storage.shape, generator=g, device=dev) * 2 - 1)
     rb.storage[:, -1] = (rb.storage[:, -1] > 0.9).float()
     rb.size, rb.ptr = rb.max_size, 0
+    rb.size_dev.fill_(rb.size)
     algo = TD3(50, 10, 1.0, a_lr=3e-4, c_lr=1e-3, device=dev)
     sweep = []
     for batch, reps in ((256, 100), (4096, 100), (65536, 20)):
+        # eager: TD3.train (host-side sampling and counters, ~50 launches per update); graph: TD3.train_device replaying a captured
+        # CUDA graph of policy_freq = 2 iterations (device-side sampler and step counters)
         algo.train(rb, 4, batch_size=batch, generator=g)
         l0 = algo.launches
-        ms, _ = device_ms(lambda: algo.train(rb, reps, batch_size=batch, generator=g), dev, 1)
+        ms_eager, _ = device_ms(lambda: algo.train(rb, reps, batch_size=batch, generator=g), dev, 1)
+        lpu = (algo.launches - l0) / reps
+        algo.train_device(rb, 4, batch_size=batch)
+        ms, _ = device_ms(lambda: algo.train_device(rb, reps, batch_size=batch), dev, 1)
         sweep.append({"batch": batch, "ms_per_update": ms / reps, "updates_per_s": reps * 1e3 / ms, "samples_per_s": batch * reps * 1e3 / ms,
-                      "replay_gather_GBps": batch * 112 * 4 * 2 * reps / ms / 1e6, "launches_per_update": (algo.launches - l0) / reps})
+                      "replay_gather_GBps": batch * 112 * 4 * 2 * reps / ms / 1e6, "launches_per_update": lpu,
+                      "eager_ms_per_update": ms_eager / reps, "graph_replays_per_update": 0.5})
     del rb, algo
     torch.cuda.empty_cache()
     return {"workload": "TD3 Cassie-v0 sizes (50 / 10 / 256 x 256), replay ring 1,000,000 x 112 f32 = 448 MB in HBM, uniform sampling with "
-                        "replacement, one train() iteration = critic step (+ actor step and Polyak every 2nd)", "dtype": "f32",
+                        "replacement, one train() iteration = critic step (+ actor step and Polyak every 2nd); ms_per_update = CUDA-graph replay of two "
+                        "iterations (TD3.train_device), eager_ms_per_update = the same kernels launched one by one (TD3.train)", "dtype": "f32",
             "metric": "TD3 updates/s", "sweep": sweep}
 
 

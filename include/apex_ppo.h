@@ -60,6 +60,17 @@ int apex_replay_gather(const float *storage, const int64_t *idx, int rows, int S
 /* sa = [state | clamp(max_a tanh(pre) + clamp(noise, +-noise_clip), +-max_a)]; noise: explicit [rows, A] or Philox N(0, policy_noise) */
 int apex_td3_action(const float *pre, const float *state, const float *noise, int rows, int S, int A, float max_a, float policy_noise,
                     float noise_clip, unsigned seed, unsigned step, float *sa, float *tanh_out, void *stream);
+/* CUDA-graph friendly forms (TD3 at the reference's batch of 256 is launch-bound: TD3.train(use_graph=True) captures policy_freq
+ * iterations once and replays them): counters that change between replays are read from device memory.
+ * apex_adam_step_dev: Adam with the step count at *step_dev; apex_td3_action_dev: smoothing noise from Philox(seed, row, *step_dev);
+ * apex_replay_sample: idx[i] uniform in [0, *size_dev) from Philox(seed, i, *ctr_dev) (remote_replay.py:78-79: sampling with
+ * replacement); apex_counter_add: *counter_dev += inc. */
+int apex_adam_step_dev(float *p, const float *g, float *m, float *v, int n, const double *sumsq, float gscale, float max_norm, float lr,
+                       float beta1, float beta2, float eps, const int *step_dev, void *stream);
+int apex_td3_action_dev(const float *pre, const float *state, int rows, int S, int A, float max_a, float policy_noise, float noise_clip,
+                        unsigned seed, const int *step_dev, float *sa, float *tanh_out, void *stream);
+int apex_replay_sample(int64_t *idx, int rows, const int *size_dev, unsigned seed, const int *ctr_dev, void *stream);
+int apex_counter_add(int *counter_dev, int inc, void *stream);
 /* twin-Q target and MSE gradients; stats[3] (double, +=): loss, sum Q1, sum Q2 */
 int apex_td3_critic_loss(int rows, const float *q1, const float *q2, const float *q1t, const float *q2t, const float *reward,
                          const float *notdone, float discount, float *dq1, float *dq2, double *stats, void *stream);

@@ -84,3 +84,32 @@ def test_td3_train_matches_reference_with_float64_replay_actions():
     algo, q_loss = _run_td3(g, 2, alias=False)
     assert abs(q_loss - float(g["q_loss"])) < 1e-4 * max(1.0, abs(float(g["q_loss"]))), (q_loss, float(g["q_loss"]))
     _check_params(g, algo, 2)
+
+
+def test_graph_replay_equals_the_eager_device_path():
+    """TD3.train_device: the captured CUDA graph of policy_freq iterations (device-side sampler and step counters) must do what
+    the same kernels launched one by one do — same rows sampled, same noise, same Adam step counts — over several replays, with
+    the replay buffer growing in between (the fill level is read from device memory)."""
+    from apex_b200.td3 import TD3, ReplayBuffer
+    dev = torch.device("cuda:0")
+    S, A, B = 50, 10, 256
+    res = []
+    for use_graph in (False, True):
+        torch.manual_seed(4)
+        g = torch.Generator(device=dev).manual_seed(9)
+        rb = ReplayBuffer(S, A, max_size=20000, device=dev)
+        algo = TD3(S, A, 1.0, a_lr=3e-4, c_lr=1e-3, device=dev, seed=5)
+        outs = []
+        for chunk in range(3):
+            n = 3000
+            rb.add(torch.randn(n, S, device=dev, generator=g), torch.randn(n, S, device=dev, generator=g),
+                   torch.rand(n, A, device=dev, generator=g) * 2 - 1, torch.randn(n, device=dev, generator=g),
+                   (torch.rand(n, device=dev, generator=g) > 0.9).float())
+            outs.append(algo.train_device(rb, 6, batch_size=B, use_graph=use_graph))
+        assert int(algo.b_idx.max()) < rb.size and int(algo.b_idx.min()) >= 0
+        res.append((algo.flat.clone(), list(algo._opt), outs, algo.ctr.tolist()))
+    (pa, oa, la, ca), (pb, ob, lb, cb) = res
+    assert oa == ob == [9, 18] and ca == cb and ca[2] == 18
+    assert torch.allclose(pa, pb, rtol=1e-4, atol=1e-6), float((pa - pb).abs().max())  # float atomics in the weight gradients
+    for x, y in zip(la, lb):
+        assert np.allclose(x, y, rtol=1e-4, atol=1e-6)
