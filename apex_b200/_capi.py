@@ -79,6 +79,8 @@ def lib():
         L.apex_set_tc_persistent.restype = None
         L.apex_set_gemm_large_tiles.argtypes = [i]
         L.apex_set_gemm_large_tiles.restype = None
+        L.apex_gaussian_sample_dev.argtypes = [vp, vp, vp, i, i, u, u, vp, vp, vp]
+        L.apex_gaussian_sample_dev.restype = i
         L.apex_adam_step_dev.argtypes = [vp, vp, vp, vp, i, vp, fl, fl, fl, fl, fl, fl, vp, vp]
         L.apex_td3_action_dev.argtypes = [vp, vp, i, i, i, fl, fl, fl, u, vp, vp, vp, vp]
         L.apex_replay_sample.argtypes = [vp, i, vp, u, vp, vp]

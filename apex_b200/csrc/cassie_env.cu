@@ -135,8 +135,21 @@ __global__ void __launch_bounds__(1024) k_env_order(const int *sti, int n, int s
 }
 
 template <typename K> static int prep(K kernel, size_t smem) {
+  /* once per kernel, device and size: a launch that is being captured into a CUDA graph (PPO's rollout graph) then consists of the
+   * launch alone */
+  static struct { const void *fn; int dev; size_t smem; } seen[64];
+  static int nseen = 0;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int k = 0;
+  for (; k < nseen; k++)
+    if (seen[k].fn == (const void *)kernel && seen[k].dev == dev) break;
+  if (k < nseen && smem <= seen[k].smem) return 0;
   cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  return err == cudaSuccess ? 0 : -(int)err;
+  if (err != cudaSuccess) return -(int)err;
+  if (k == nseen && nseen < 64) nseen++;
+  if (k < 64) { seen[k].fn = (const void *)kernel; seen[k].dev = dev; seen[k].smem = smem; }
+  return 0;
 }
 static int finish() {
   cudaError_t err = cudaGetLastError();

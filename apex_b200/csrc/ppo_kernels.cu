@@ -449,9 +449,11 @@ __device__ __forceinline__ void philox4(uint32_t seed, uint32_t a, uint32_t b, u
 }
 
 __global__ void k_gaussian_sample(const float *__restrict__ mu, const float *__restrict__ sigma, float anneal, int rows, int adim,
-                                  uint32_t seed, uint32_t step, uint32_t row0, float *__restrict__ act, float *__restrict__ logp) {
+                                  uint32_t seed, uint32_t step, uint32_t row0, float *__restrict__ act, float *__restrict__ logp,
+                                  const uint32_t *__restrict__ dyn) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= rows) return;
+  if (dyn) { seed = dyn[0]; anneal = __uint_as_float(dyn[1]); } /* CUDA-graph replays of a rollout: what changes per rollout is in device memory */
   float lp = 0.f;
   for (int j = 0; j < adim; j += 2) {
     uint32_t u[4];
@@ -477,7 +479,15 @@ __global__ void k_gaussian_sample(const float *__restrict__ mu, const float *__r
 extern "C" int apex_gaussian_sample(const float *mu, const float *sigma, float anneal, int rows, int adim, unsigned seed,
                                     unsigned step, unsigned row0, float *act, float *logp, void *stream) {
   if (rows <= 0) return 0;
-  k_gaussian_sample<<<(rows + 127) / 128, 128, 0, (cudaStream_t)stream>>>(mu, sigma, anneal, rows, adim, seed, step, row0, act, logp);
+  k_gaussian_sample<<<(rows + 127) / 128, 128, 0, (cudaStream_t)stream>>>(mu, sigma, anneal, rows, adim, seed, step, row0, act, logp, nullptr);
+  return last_err();
+}
+/* the same with (seed, anneal as float bits) read from dyn[0..1] in device memory */
+extern "C" int apex_gaussian_sample_dev(const float *mu, const float *sigma, const unsigned *dyn, int rows, int adim, unsigned step,
+                                        unsigned row0, float *act, float *logp, void *stream) {
+  if (rows <= 0) return 0;
+  if (!dyn) return -1000;
+  k_gaussian_sample<<<(rows + 127) / 128, 128, 0, (cudaStream_t)stream>>>(mu, sigma, 1.f, rows, adim, 0u, step, row0, act, logp, dyn);
   return last_err();
 }
 
@@ -699,7 +709,11 @@ extern "C" int apex_gae_scan(int T, int N, const float *rew, const float *val, c
   if (T <= 0 || N <= 0) return 0;
   if (T > SCAN_TMAX) return -1000;
   const size_t smem = (size_t)T * 33 * 2 * sizeof(float);
-  CK(cudaFuncSetAttribute(k_gae_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static size_t smem_set[64]; /* per device: the attribute is raised outside of any later CUDA-graph capture */
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  if (smem > smem_set[dev]) { CK(cudaFuncSetAttribute(k_gae_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); smem_set[dev] = smem; }
   k_gae_scan<<<(N + 31) / 32, 1024, smem, (cudaStream_t)stream>>>(T, N, rew, val, done, term_val, last_val, gamma, lam, ret, adv);
   return last_err();
 }

@@ -15,6 +15,7 @@ the hand-written kernels in apex_b200/csrc (no autograd, no cuBLAS).  With world
 the flattened actor+critic gradient is all-reduced once per optimizer step over NCCL.
 """
 import math
+import struct
 import os
 
 import numpy as np
@@ -110,6 +111,11 @@ class PPO:
         # two tf32 terms, three products per k step — float32-accurate (tc_mode 3); "tf32" / "bf16": one product (tc_mode 1; with
         # "bf16" the forward hidden layer additionally uses bf16 operands).  tc_mode=0 keeps every GEMM on the SIMT kernels.
         self.tc_mode = int(args.get("tc_mode", 3 if self.precision == "f32" else 1))
+        # One CUDA graph per rollout shape: the T steps of sample_parallel (observation copy, actor / critic inference, sampling, env
+        # step) and the return scan are captured once and replayed every iteration (~7,900 launches for 256 steps); the Philox seed
+        # and the exploration-noise anneal, the only things that change between rollouts, are read from device memory.
+        self.graph_rollout = bool(args.get("graph_rollout", True))
+        self._roll_graphs, self._roll_seen, self._bufs = {}, set(), {}
         self.save_path = save_path
         self.total_steps = 0
         self.highest_reward = -1
@@ -221,34 +227,62 @@ class PPO:
         if T > 512:  # apex_gae_scan composes the horizon in one 512-step scan per env
             raise ValueError(f"num_steps={min_steps} over {N} envs is a horizon of {T} > 512 steps per env: use more envs "
                              f"(>= {math.ceil(min_steps / 512)}) or fewer steps per iteration")
-        if self.buf is None or self.buf.T != T:
-            self.buf = RolloutBuffer(T, N, self.obs_dim, self.act_dim, self.device)
-        buf = self.buf
+        if T not in self._bufs:  # one buffer per horizon (PPO.train alternates between the training and the evaluation rollout)
+            if len(self._bufs) >= 2:
+                self._bufs.clear()
+                self._roll_graphs.clear()  # captured graphs hold the old buffers' addresses
+                self._roll_seen.clear()
+            self._bufs[T] = RolloutBuffer(T, N, self.obs_dim, self.act_dim, self.device)
+        buf = self.buf = self._bufs[T]
         if self.cur_obs is None:
             self.cur_obs = env.reset()
             self.launches += 1
-        ap, cp = self._actor_ptrs(), self._critic_ptrs()
-        L, s = self.L, self._s()
         self._sample_calls += 1
         seed = (self.seed * 0x9E3779B1 + 0x5BD1E995 * self._sample_calls) & 0xFFFFFFFF
+        if getattr(self, "_roll_dyn", None) is None:
+            self._roll_dyn = torch.zeros(2, dtype=torch.int32, device=self.device)
+        bits = struct.unpack("<i", struct.pack("<f", float(anneal)))[0]
+        self._roll_dyn.copy_(torch.tensor([seed - (1 << 32) if seed >= (1 << 31) else seed, bits], dtype=torch.int32))
+        key = (T, N, int(max_traj_len), self.tc_mode, self.precision)
+        if self.graph_rollout and key in self._roll_graphs:
+            g, per = self._roll_graphs[key]
+            g.replay()
+            self.launches += per
+        elif self.graph_rollout and key in self._roll_seen:  # second rollout of this shape: everything lazily allocated exists by now
+            torch.cuda.current_stream(self.device).synchronize()
+            g, n0 = torch.cuda.CUDAGraph(), self.launches
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                self._rollout_body(buf, T, N)
+            self._roll_graphs[key] = (g, self.launches - n0)
+            g.replay()
+        else:
+            self._roll_seen.add(key)
+            self._rollout_body(buf, T, N)
+        self.cur_obs = env.obs
+        return buf
+
+    def _rollout_body(self, buf, T, N):
+        """The launches of one rollout; every pointer is persistent (buffer rows, env state, scratch), the seed and the anneal factor
+        come from self._roll_dyn — so the sequence can be captured once and replayed."""
+        env, L, s = self.env, self.L, self._s()
+        ap, cp = self._actor_ptrs(), self._critic_ptrs()
+        cur = env.obs
         for t in range(T):
             obs_t = buf.obs[t]
-            obs_t.copy_(self.cur_obs)
+            obs_t.copy_(cur)
             _capi.check(L.apex_prepare_obs(_p(obs_t), None, N, self.obs_dim, _p(self.obs_mean), _p(self.obs_std), None, None, None,
                                            None, _p(self.xn), None, s), "prepare_obs")
             self._mlp_fwd(ap, self.xn, N, self.act_dim, self.h[0], self.h[1], buf.mu[t])
             self._mlp_fwd(cp, obs_t, N, 1, self.h[2], self.h[3], buf.val[t])  # critic in train mode: raw obs (critic.py:66)
-            _capi.check(L.apex_gaussian_sample(_p(buf.mu[t]), _p(self.sigma), float(anneal), N, self.act_dim, seed, t,
-                                               self.rank * N, _p(buf.act[t]), _p(buf.logp[t]), s), "gaussian_sample")
-            obs, _, _, _ = env.step(buf.act[t], rew_out=buf.rew[t], done_out=buf.done[t])
+            _capi.check(L.apex_gaussian_sample_dev(_p(buf.mu[t]), _p(self.sigma), _p(self._roll_dyn), N, self.act_dim, t,
+                                                   self.rank * N, _p(buf.act[t]), _p(buf.logp[t]), s), "gaussian_sample")
+            cur, _, _, _ = env.step(buf.act[t], rew_out=buf.rew[t], done_out=buf.done[t])
             self._mlp_fwd(cp, env.term_obs, N, 1, self.h[2], self.h[3], buf.term_val[t])  # V(s_T) of time-limit cuts
-            self.cur_obs = obs
             self.launches += 3 + int(getattr(env, "balance", False))
-        self._mlp_fwd(cp, self.cur_obs, N, 1, self.h[2], self.h[3], buf.last_val)
+        self._mlp_fwd(cp, cur, N, 1, self.h[2], self.h[3], buf.last_val)
         _capi.check(L.apex_gae_scan(T, N, _p(buf.rew), _p(buf.val), _p(buf.done), _p(buf.term_val), _p(buf.last_val),
                                     float(self.gamma), float(self.lam), _p(buf.ret), _p(buf.adv), s), "gae_scan")
         self.launches += 1
-        return buf
 
     @torch.no_grad()
     def normalize_advantages(self, buf):

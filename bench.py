@@ -421,7 +421,9 @@ def main():
         return out
     algo.env.step, algo.sample_parallel = wrapped, wrapped_sample
     algo.collective_events = []
+    graph_rollout, algo.graph_rollout = algo.graph_rollout, False  # per-launch events need the launches one by one, not the graph replay
     ms_instr, _ = timed(False, 1)
+    algo.graph_rollout = graph_rollout
     algo.env.step, algo.sample_parallel = orig_step, orig_sample
     nccl = None
     if world > 1:  # one all-reduce of the flattened actor + critic gradient per optimizer step
@@ -491,6 +493,8 @@ def main():
                    "note": "PPO.train_iteration with the parameters shipped from pinned host memory and parameters, loss statistics, "
                            "rewards and done flags read back to the host every step"},
            "gpu_launches": launches, "clocks": clk, "nccl": nccl,
+           "rollout_graph": {"enabled": graph_rollout, "note": "value and e2e replay one CUDA graph per rollout (256 steps x ~31 launches "
+                             "+ return scan); the instrumented step below launches the same kernels one by one"},
            "learner": {"tc_mode": tc_mode, "update_ms": ms_instr - sum(rms) / len(rms),
                        "note": "tc_mode 3: the 256-wide layers (forward, dX, dW; first layer k = 50 padded) on tcgen05 kind::tf32 with "
                                "every operand split as hi + lo and three products per k step (float32-accurate, csrc/tc_gemm3.cu); "

@@ -37,6 +37,11 @@ int apex_ppo_loss(int rows, int adim, const float *mu, const float *mu_mir, cons
                   const float *oldlogp_all, const float *adv_all, const float *ret_all, const float *oldmu_all, const float *value,
                   const float *sigma, float clip, float mirror_coeff, const int *amir_src, const float *amir_sign, float *dmu,
                   float *dmu_mir, float *dvalue, double *stats, void *stream);
+/* apex_gaussian_sample with (seed, anneal as float bits) read from dyn[0..1] in device memory: PPO.sample_parallel captures a whole
+ * rollout (T steps of observation copy, actor / critic inference, sampling, env step; then the return scan) as one CUDA graph and
+ * replays it every iteration — only these two words change between replays */
+int apex_gaussian_sample_dev(const float *mu, const float *sigma, const unsigned *dyn, int rows, int adim, unsigned step, unsigned row0,
+                             float *act, float *logp, void *stream);
 int apex_grad_sumsq(const float *g, int n, double *out, void *stream); /* out += sum g^2 */
 int apex_adam_step(float *p, const float *g, float *m, float *v, int n, const double *sumsq, float gscale, float max_norm, float lr,
                    float beta1, float beta2, float eps, int step, void *stream);
