@@ -138,6 +138,7 @@ class PPO:
         policy.to(dev)
         critic.to(dev)
         self.flat, self.grad, index = flatten_modules([policy, critic], dev)
+        self._opt_dev = torch.full((1,), int(self._opt_step[0]), dtype=torch.int32, device=dev)
         self.off = {name: off for name, off, _ in index}
         self.n_actor = sum(p.numel() for p in policy.parameters())
         self.n_total = self.flat.numel()
@@ -300,6 +301,7 @@ class PPO:
             return
         f = dict(dtype=torch.float32, device=self.device)
         self._mbB = B
+        self._epoch_graphs, self._epoch_seen = {}, set()  # captured epochs hold the old minibatch buffers' addresses
         self.mb_x = torch.zeros((2 * B, self.obs_dim), **f)  # [normalised obs ; normalised mirrored obs]
         self.mb_raw = torch.zeros((B, self.obs_dim), **f)
         self.mb_h1 = torch.zeros((2 * B, self.hid), **f)
@@ -356,13 +358,17 @@ class PPO:
         gp, pp, mp, vp = self.grad.data_ptr(), self.flat.data_ptr(), self.adam_m.data_ptr(), self.adam_v.data_ptr()
         _capi.check(L.apex_grad_sumsq(gp, na, self.sumsq.data_ptr(), s), "sumsq")
         _capi.check(L.apex_grad_sumsq(gp + 4 * na, nt - na, self.sumsq.data_ptr() + 8, s), "sumsq")
+        # the Adam step count lives in device memory (self._opt_dev, one counter: actor and critic always step together), so that
+        # a whole epoch of optimizer steps can be replayed from a CUDA graph; self._opt_step is its host mirror
         self._opt_step[0] += 1
         self._opt_step[1] += 1
-        _capi.check(L.apex_adam_step(pp, gp, mp, vp, na, self.sumsq.data_ptr(), gscale, float(self.grad_clip), float(self.lr),
-                                     0.9, 0.999, float(self.eps), self._opt_step[0], s), "adam")
-        _capi.check(L.apex_adam_step(pp + 4 * na, gp + 4 * na, mp + 4 * na, vp + 4 * na, nt - na, self.sumsq.data_ptr() + 8, gscale,
-                                     float(self.grad_clip), float(self.lr), 0.9, 0.999, float(self.eps), self._opt_step[1], s), "adam")
-        self.launches += 6
+        cdev = self._opt_dev.data_ptr()
+        _capi.check(L.apex_counter_add(cdev, 1, s), "counter_add")
+        _capi.check(L.apex_adam_step_dev(pp, gp, mp, vp, na, self.sumsq.data_ptr(), gscale, float(self.grad_clip), float(self.lr),
+                                         0.9, 0.999, float(self.eps), cdev, s), "adam")
+        _capi.check(L.apex_adam_step_dev(pp + 4 * na, gp + 4 * na, mp + 4 * na, vp + 4 * na, nt - na, self.sumsq.data_ptr() + 8, gscale,
+                                         float(self.grad_clip), float(self.lr), 0.9, 0.999, float(self.eps), cdev, s), "adam")
+        self.launches += 7
 
     def minibatch_scalars(self):
         """(actor_loss, entropy, critic_loss, ratio, kl, mirror_loss) of the last minibatch — one device->host read.
@@ -384,15 +390,55 @@ class PPO:
         self.update_minibatch(self.buf, obs_batch)
         return self.minibatch_scalars()
 
-    def optimize(self, buf, generator=None):
-        """epochs x shuffled minibatches with drop_last, KL early stop on the last minibatch (ppo.py:407-451)."""
+    def _epoch_body(self, buf, n, mb):
+        for i in range(0, n - mb + 1, mb):
+            self.update_minibatch(buf, self._perm[i:i + mb])
+            self._acc += self.stats  # sums over this rank's minibatches of the epoch
+
+    @torch.no_grad()
+    def run_epoch(self, buf, generator=None):
+        """One epoch of shuffled minibatches with drop_last (ppo.py:407-447).  The permutation is copied into a persistent index
+        buffer, so every minibatch is a fixed slice of it and the launches of an epoch (32 optimizer steps x ~40 kernels in the
+        benchmark config) are identical from epoch to epoch: single-GPU runs capture them once as a CUDA graph and replay it
+        (data-parallel runs all-reduce between kernels and launch them one by one).  self._acc holds the epoch's summed statistics."""
         n = len(buf)
         mb = min(self.minibatch_size or n, n)
+        if getattr(self, "_perm", None) is None or self._perm.numel() != n:
+            self._perm = torch.zeros(n, dtype=torch.int64, device=self.device)
+            self._acc = torch.zeros(6, dtype=torch.float64, device=self.device)
+            self._epoch_graphs, self._epoch_seen = {}, set()
+        self._perm.copy_(torch.randperm(n, device=self.device, generator=generator))
+        self._acc.zero_()
+        self._ensure_mb(mb)
+        steps = len(range(0, n - mb + 1, mb))
+        key = (buf.obs.data_ptr(), n, mb, self.tc_mode, self.precision, float(self.lr), float(self.clip), float(self.grad_clip),
+               float(self.eps), float(self.mirror_coeff))
+        use_graph = self.graph_rollout and self.world == 1
+        if use_graph and key in self._epoch_graphs:
+            g, per = self._epoch_graphs[key]
+            g.replay()
+            self.launches += per
+            self._opt_step[0] += steps
+            self._opt_step[1] += steps
+            self._stats_reduced = False
+        elif use_graph and key in self._epoch_seen:
+            torch.cuda.current_stream(self.device).synchronize()
+            g, n0, o0 = torch.cuda.CUDAGraph(), self.launches, list(self._opt_step)
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                self._epoch_body(buf, n, mb)
+            self._epoch_graphs[key] = (g, self.launches - n0)
+            self._opt_step = [o0[0] + steps, o0[1] + steps]
+            g.replay()
+        else:
+            self._epoch_seen.add(key)
+            self._epoch_body(buf, n, mb)
+        return steps
+
+    def optimize(self, buf, generator=None):
+        """epochs x shuffled minibatches with drop_last, KL early stop on the last minibatch (ppo.py:407-451)."""
         scalars = None
         for epoch in range(self.epochs):
-            perm = torch.randperm(n, device=self.device, generator=generator)
-            for i in range(0, n - mb + 1, mb):
-                self.update_minibatch(buf, perm[i:i + mb])
+            self.run_epoch(buf, generator)
             scalars = self.minibatch_scalars()
             if self.max_kl is not None and scalars[4] > self.max_kl:
                 break
@@ -436,13 +482,8 @@ class PPO:
             losses, kl, entropy = [], 0.0, 0.0
             n, mb = len(batch), min(self.minibatch_size or len(batch), len(batch))
             for epoch in range(self.epochs):
-                perm = torch.randperm(n, device=self.device, generator=gen)
-                acc = torch.zeros(6, dtype=torch.float64, device=self.device)
-                cnt = 0
-                for i in range(0, n - mb + 1, mb):
-                    self.update_minibatch(batch, perm[i:i + mb])
-                    acc += self.stats  # sums of this rank's minibatches; the epoch mean is formed once, below
-                    cnt += 1
+                self.run_epoch(batch, gen)  # sums of this rank's minibatches in self._acc; the epoch mean is formed once, below
+                acc = self._acc.clone()
                 last = self.minibatch_scalars()  # (all-reduced) scalars of the epoch's last minibatch: the early-stop KL (:449)
                 if self.world > 1:
                     dist.all_reduce(acc)

@@ -494,7 +494,8 @@ def main():
                            "rewards and done flags read back to the host every step"},
            "gpu_launches": launches, "clocks": clk, "nccl": nccl,
            "rollout_graph": {"enabled": graph_rollout, "note": "value and e2e replay one CUDA graph per rollout (256 steps x ~31 launches "
-                             "+ return scan); the instrumented step below launches the same kernels one by one"},
+                             "+ return scan) and, on one GPU, one per update epoch (32 optimizer steps x ~42 launches); the instrumented "
+                             "step (kernel_ms, rollout_only, learner.update_ms) launches the same kernels one by one"},
            "learner": {"tc_mode": tc_mode, "update_ms": ms_instr - sum(rms) / len(rms),
                        "note": "tc_mode 3: the 256-wide layers (forward, dX, dW; first layer k = 50 padded) on tcgen05 kind::tf32 with "
                                "every operand split as hi + lo and three products per k step (float32-accurate, csrc/tc_gemm3.cu); "
