@@ -273,7 +273,8 @@ def extra_cfg4_traj(dev, rank, world):
     algo = PPO(dict(num_steps=n * T, minibatch_size=MINIBATCH, epochs=EPOCHS, max_traj_len=400, seed=0, max_kl=None, precision="bf16"))
     env_fn = lambda: BatchedCassieTrajEnv(n, table, device=dev, seed=0, dynamics_randomization=True, env_id0=rank * n)
     gen = torch.Generator(device=dev).manual_seed(99)
-    algo.train_iteration(env_fn, actor, critic, generator=gen)
+    for _ in range(2):  # the first iteration runs eagerly, the second captures the rollout (and epoch) CUDA graphs; the timed one replays
+        algo.train_iteration(env_fn, actor, critic, generator=gen)
     ms, _ = device_ms(lambda: algo.train_iteration(env_fn, actor, critic, generator=gen), dev, world)
     del algo, actor, critic
     torch.cuda.empty_cache()
