@@ -413,6 +413,9 @@ class PPO:
         steps = len(range(0, n - mb + 1, mb))
         key = (buf.obs.data_ptr(), n, mb, self.tc_mode, self.precision, float(self.lr), float(self.clip), float(self.grad_clip),
                float(self.eps), float(self.mirror_coeff))
+        # one GPU only: with several ranks the NCCL all-reduce sits between the kernels of every optimizer step; capturing it works,
+        # but tearing the process group down with such graphs alive hung the ranks at exit (measured at 2 GPUs), so data-parallel
+        # runs launch the update kernel by kernel
         use_graph = self.graph_rollout and self.world == 1
         if use_graph and key in self._epoch_graphs:
             g, per = self._epoch_graphs[key]
