@@ -113,6 +113,7 @@ template <typename T> CW_FN T cw_clock_y(int which, int k, int mode) { /* mode 2
 CW_FN int cw_env_variant(int v) { return v & 0xFF; }
 CW_FN int cw_cmd_profile(int v) { return (v >> 8) & 0xFF; }
 CW_FN int cw_obs_dim(int v) { return cw_cmd_profile(v) ? CW_OBS_PHASE : CW_OBS; }
+CW_FN int cw_reward_kind(int v) { return (v >> 16) & 0xFF; } /* 0 clock_reward, 1 early_clock_reward, 2 no_speed_clock_reward */
 template <typename T> CW_FN T cw_clock_eval(const T *x, T P, int which, T phase, int mode) {
   T xa, xb, ya, yb;
   if (phase < x[0]) { xa = x[7] - P; ya = cw_clock_y<T>(which, 7, mode); xb = x[0]; yb = cw_clock_y<T>(which, 0, mode); }
@@ -549,10 +550,12 @@ template <typename T> CW_NOINL void cw_env_step(CassieWs<T> &w, T *obs_out, T *r
   T reward;
   {
     const T speed = w.st[S_SPEED];
-    const T nlf = cw_min(lfrc, (T)250) / (T)250, nrf = cw_min(rfrc, (T)250) / (T)250;
-    const T nlv = cw_min(cw_sqrt<T>(cw_dot3(lfv, lfv)), (T)2.0) / (T)2.0, nrv = cw_min(cw_sqrt<T>(cw_dot3(rfv, rfv)), (T)2.0) / (T)2.0;
-    const T com_orient_error = 10 * (1 - qpos[3] * qpos[3]);
-    const T foot_orient_error = 10 * (lori + rori);
+    const int kind = cw_reward_kind(w.sti[I_VARIANT]); /* clock_rewards.py:6 (0), :119 early (1), :225 no_speed (2) */
+    const T mfrc = kind == 1 ? (T)350 : (T)250, mvel = kind == 0 ? (T)2.0 : (T)3.0, ow = kind == 1 ? (T)1 : (T)10;
+    const T nlf = cw_min(lfrc, mfrc) / mfrc, nrf = cw_min(rfrc, mfrc) / mfrc;
+    const T nlv = cw_min(cw_sqrt<T>(cw_dot3(lfv, lfv)), mvel) / mvel, nrv = cw_min(cw_sqrt<T>(cw_dot3(rfv, rfv)), mvel) / mvel;
+    const T com_orient_error = ow * (1 - qpos[3] * qpos[3]);
+    const T foot_orient_error = ow * (lori + rori);
     const T com_vel_error = cw_abs(qvel[0] - speed);
     T straight_diff = cw_abs(qpos[1]);
     if (straight_diff < (T)0.05) straight_diff = 0;
@@ -562,6 +565,7 @@ template <typename T> CW_NOINL void cw_env_step(CassieWs<T> &w, T *obs_out, T *r
     T pelvis_acc = 0;
     for (int k = 0; k < 3; k++) pelvis_acc += cw_abs(w.y[Y_ROTVEL + k]) + cw_abs(w.y[Y_TACC + k]);
     pelvis_acc *= (T)0.25;
+    if (kind == 1) pelvis_acc = 0;
     const T pelvis_motion = straight_diff + height_diff + pelvis_acc;
     T x[8], P;
     cw_clock_knots<T>(w.st[S_SWING], w.st[S_STANCE], x, &P);
@@ -569,8 +573,14 @@ template <typename T> CW_NOINL void cw_env_step(CassieWs<T> &w, T *obs_out, T *r
     const T lfc = cw_clock_eval<T>(x, P, 0, phase, sm), lvc = cw_clock_eval<T>(x, P, 1, phase, sm);
     const T rfc = cw_clock_eval<T>(x, P, 2, phase, sm), rvc = cw_clock_eval<T>(x, P, 3, phase, sm);
     const T q4 = (T)(CW_PI / 4);
-    const T foot_frc_score = cw_tan<T>(q4 * lfc * nlf) + cw_tan<T>(q4 * rfc * nrf);
-    const T foot_vel_score = cw_tan<T>(q4 * lvc * nlv) + cw_tan<T>(q4 * rvc * nrv);
+    T foot_frc_score, foot_vel_score;
+    if (kind == 1) { /* tanh(x) = 1 - 2 / (exp(2 x) + 1) */
+      foot_frc_score = cw_tanh<T>(lfc * nlf) + cw_tanh<T>(rfc * nrf);
+      foot_vel_score = cw_tanh<T>(lvc * nlv) + cw_tanh<T>(rvc * nrv);
+    } else {
+      foot_frc_score = cw_tan<T>(q4 * lfc * nlf) + cw_tan<T>(q4 * rfc * nrf);
+      foot_vel_score = cw_tan<T>(q4 * lvc * nlv) + cw_tan<T>(q4 * rvc * nrv);
+    }
     const T hip_roll_penalty = cw_abs(qvel[6]) + cw_abs(qvel[13]);
     T torque_penalty = 0, action_penalty = 0;
     for (int k = 0; k < 10; k++) {
@@ -581,9 +591,15 @@ template <typename T> CW_NOINL void cw_env_step(CassieWs<T> &w, T *obs_out, T *r
     }
     torque_penalty = (T)0.25 * (torque_penalty / 10);
     action_penalty = 5 * action_penalty / 10;
-    reward = (T)0.200 * foot_frc_score + (T)0.200 * foot_vel_score + (T)0.200 * cw_exp<T>(-(com_orient_error + foot_orient_error)) +
-             (T)0.150 * cw_exp<T>(-pelvis_motion) + (T)0.150 * cw_exp<T>(-com_vel_error) + (T)0.050 * cw_exp<T>(-hip_roll_penalty) +
-             (T)0.025 * cw_exp<T>(-torque_penalty) + (T)0.025 * cw_exp<T>(-action_penalty);
+    const T e_or = cw_exp<T>(-(com_orient_error + foot_orient_error)), e_pm = cw_exp<T>(-pelvis_motion), e_cv = cw_exp<T>(-com_vel_error);
+    const T e_hr = cw_exp<T>(-hip_roll_penalty), e_tq = cw_exp<T>(-torque_penalty), e_ac = cw_exp<T>(-action_penalty);
+    if (kind == 1) reward = (T)0.250 * foot_frc_score + (T)0.350 * foot_vel_score + (T)0.200 * e_cv + (T)0.100 * e_or + (T)0.100 * e_pm;
+    else if (kind == 2)
+      reward = (T)0.250 * foot_frc_score + (T)0.250 * foot_vel_score + (T)0.225 * e_or + (T)0.175 * e_pm + (T)0.050 * e_hr + (T)0.025 * e_tq +
+               (T)0.025 * e_ac;
+    else
+      reward = (T)0.200 * foot_frc_score + (T)0.200 * foot_vel_score + (T)0.200 * e_or + (T)0.150 * e_pm + (T)0.150 * e_cv + (T)0.050 * e_hr +
+               (T)0.025 * e_tq + (T)0.025 * e_ac;
   }
   if (reward < (T)-99.0) done = 1;
   /* random command changes (cassie.py:483-491) */

@@ -140,7 +140,7 @@ enum {
 enum {
   I_DRIVEHIST = 0, I_TIME = 90, I_COUNTER = 91, I_HASPREV = 92, I_HASU = 93, I_DRIVEINIT = 94, I_JOINTINIT = 95,
   I_FLAGS = 96, I_STEPCOUNT = 97, I_RNGCTR = 98, I_ENVID = 99, I_SEED = 100, I_DYNRAND = 101, I_SOLVER_ITER = 102,
-  I_NCON = 103, I_NEFC = 104, I_VARIANT = 105 /* bits 0-7: 0 Cassie-v0, 1 CassieTraj-v0; bits 8-15: command profile 0 clock, 1 phase, 2 phase (library) */, I_PHASEFLOOR = 106 /* floor(phaselen), from float64 */,
+  I_NCON = 103, I_NEFC = 104, I_VARIANT = 105 /* bits 0-7: 0 Cassie-v0, 1 CassieTraj-v0; bits 8-15: command profile 0 clock, 1 phase, 2 phase (library); bits 16-23: reward 0 clock, 1 early, 2 no_speed */, I_PHASEFLOOR = 106 /* floor(phaselen), from float64 */,
   I_COST = 107 /* sum over the last env step's sub-steps of solver_iter * nefc: load-balancing key */,
   I_STANCEMODE = 108 /* clock reward's stance_mode: 0 "zero", 1 "grounded" (also once reset_for_test has run, cassie.py:219,701), 2 "aerial" */,
   I_SIMSTEPS = 109 /* physics sub-steps since the simulator was last reset: sim.time() = that many additions of 0.0005 */,
@@ -259,6 +259,9 @@ template <typename T> CW_FN T cw_sqrt(T x) { return cw_sqrt_fast(x); }
 template <typename T> CW_FN void cw_sincos(T x, T *s, T *c) { cw_sincos_o(x, s, c); }
 template <typename T> CW_FN T cw_exp(T x) { return cw_exp_o(x); }
 template <typename T> CW_FN T cw_tan(T x) { return cw_tan_o(x); }
+CW_FN float cw_tanh_o(float x) { return tanhf(x); }
+CW_FN double cw_tanh_o(double x) { return tanh(x); }
+template <typename T> CW_FN T cw_tanh(T x) { return cw_tanh_o(x); }
 template <typename T> CW_FN T cw_abs(T x) { return x < 0 ? -x : x; }
 CW_FN float cw_min(float a, float b) { return fminf(a, b); } /* one FMNMX instead of compare + select */
 CW_FN float cw_max(float a, float b) { return fmaxf(a, b); }

@@ -37,17 +37,28 @@ class BatchedCassieEnv:
                  **kwargs):
         if simrate != 50 or command_profile not in ("clock", "phase") or input_profile != "full" or history != 0:
             raise NotImplementedError("kernel is specialised for simrate=50, clock / phase command, full input, history=0")
-        # command_profile "phase" (cassie.py:184-198): the reward name only selects the phase input mode ("library" in the name) and
-        # becomes "clock"; "no_speed" / "early" variants are not on the kernel path
+        # The reward NAME configures the clock reward the way cassie.py:176-232 parses it:
+        #   command_profile "phase": "library" in the name -> library phase inputs, "no_speed" -> no_speed_clock_reward, "early" ->
+        #     early_clock_reward; the stance mode is drawn on every reset;
+        #   command_profile "clock": "grounded" / "aerial" in the name -> that stance mode (else "zero"), "early" -> early_clock_reward
+        #     ("switch" names behave like "clock" in the reference: set_up_clock_reward renames them, so reset's `== "switch_clock"`
+        #     branch, cassie.py:549-554, never runs).
+        # "max_vel" (max_vel_clock_reward) and "load" (pickled clocks) are not on the kernel path.
+        reward = reward or "clock"
+        if "clock" not in reward and reward not in ("library", "no_speed", "early"):
+            raise NotImplementedError("only the clock reward family (cassie/rewards/clock_rewards.py) is implemented")
+        if "max_vel" in reward or "load" in reward or "no_incentive" in reward:
+            raise NotImplementedError("max_vel_clock_reward / loaded clocks / no_incentive clocks are not on the kernel path")
+        self._reward_kind = 1 if "early" in reward else 0
+        self._stance0 = 0
         if command_profile == "phase":
-            if reward not in ("clock", "library_clock", "library"):
-                raise NotImplementedError("phase command profile: reward 'clock' (every part random) or 'library_clock'")
             self._cmd_profile = 2 if "library" in reward else 1
-            reward = "clock"
+            if "no_speed" in reward:  # reward_func "no_speed_clock" is dispatched before the early flag is looked at (cassie.py:771-780)
+                self._reward_kind = 2
         else:
             self._cmd_profile = 0
-        if reward not in ("clock",):
-            raise NotImplementedError("only the 'clock' reward (cassie/rewards/clock_rewards.py:6) is implemented")
+            self._stance0 = 1 if "grounded" in reward else (2 if "aerial" in reward else 0)
+        reward = "clock"
         self.L = _lib.lib()
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -79,8 +90,12 @@ class BatchedCassieEnv:
         self.balance = bool(balance)
         self.order = torch.arange(n, dtype=torch.int32, device=self.device)
         self._init_state(int(seed) & 0xFFFFFFFF, int(env_id0))
-        if self._cmd_profile:  # bits 8-15 of the variant word select the command profile: observation width, reset draws
-            self.field("variant")[:, 0] |= self._cmd_profile << 8
+        # variant word: bits 8-15 command profile (observation width, reset draws), 16-23 reward kind
+        extra = (self._cmd_profile << 8) | (self._reward_kind << 16)
+        if extra:
+            self.field("variant")[:, 0] |= extra
+        if self._stance0:
+            self.field("stance_mode")[:, 0] = self._stance0
 
     def _init_state(self, seed, env_id0):
         with torch.cuda.device(self.device):

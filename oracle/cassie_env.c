@@ -167,6 +167,7 @@ void ce_env_init(ce_env_t *e, uint32_t seed, uint32_t env_id, int dyn_rand) {
 }
 void ce_env_set_command_profile(ce_env_t *e, int cmd_profile) { e->cmd_profile = cmd_profile; }
 int ce_env_obs_dim(const ce_env_t *e) { return e->cmd_profile ? CE_OBS_PHASE : CE_OBS; }
+void ce_env_set_reward(ce_env_t *e, int reward_kind, int stance_mode) { e->reward_kind = reward_kind; e->stance_mode = stance_mode; }
 
 void ce_clock_from_speed(double speed, double *swing, double *stance, double *phaselen);
 void ce_clock_from_speed_signed(double speed, double *swing, double *stance, double *phaselen);
@@ -259,15 +260,16 @@ static void step_simulation(ce_env_t *e, const double *action) { /* cassie.py:29
   if (e->r_swing && fl > 0) e->r_swing = 0; else if (!e->r_swing && fp1[5] >= 0) e->r_swing = 1;
 }
 
-double ce_env_reward(ce_env_t *e, const double *action) { /* clock_reward, cassie/rewards/clock_rewards.py:6-110 */
+double ce_env_reward(ce_env_t *e, const double *action) { /* clock_reward / early_clock_reward / no_speed_clock_reward, clock_rewards.py:6, 119, 225 */
   const double *qpos = e->d.qpos, *qvel = e->d.qvel;
-  const double max_frc = 250, max_vel = 2.0;
+  const int kind = e->reward_kind;
+  const double max_frc = kind == 1 ? 350 : 250, max_vel = kind == 0 ? 2.0 : 3.0, ow = kind == 1 ? 1 : 10;
   double nlf = fmin(e->l_foot_frc, max_frc) / max_frc, nrf = fmin(e->r_foot_frc, max_frc) / max_frc;
   double lv = sqrt(e->l_foot_vel[0] * e->l_foot_vel[0] + e->l_foot_vel[1] * e->l_foot_vel[1] + e->l_foot_vel[2] * e->l_foot_vel[2]);
   double rv = sqrt(e->r_foot_vel[0] * e->r_foot_vel[0] + e->r_foot_vel[1] * e->r_foot_vel[1] + e->r_foot_vel[2] * e->r_foot_vel[2]);
   double nlv = fmin(lv, max_vel) / max_vel, nrv = fmin(rv, max_vel) / max_vel;
-  double com_orient_error = 10 * (1 - qpos[3] * qpos[3]);
-  double foot_orient_error = 10 * (e->l_foot_orient_cost + e->r_foot_orient_cost);
+  double com_orient_error = ow * (1 - qpos[3] * qpos[3]);
+  double foot_orient_error = ow * (e->l_foot_orient_cost + e->r_foot_orient_cost);
   double com_vel_error = fabs(qvel[0] - e->speed);
   double straight_diff = fabs(qpos[1]);
   if (straight_diff < 0.05) straight_diff = 0;
@@ -276,6 +278,7 @@ double ce_env_reward(ce_env_t *e, const double *action) { /* clock_reward, cassi
   double pelvis_acc = 0;
   for (int k = 0; k < 3; k++) pelvis_acc += fabs(e->y.pelvis_rotvel[k]) + fabs(e->y.pelvis_transacc[k]);
   pelvis_acc *= 0.25;
+  if (kind == 1) pelvis_acc = 0; /* early_clock_reward drops the acceleration term (:162-163) */
   double pelvis_motion = straight_diff + height_diff + pelvis_acc;
   /* the env stores create_phase_reward's (right, left) pair as (left_clock, right_clock) — cassie.py:559 */
   double left_frc_clock = ce_clock_eval_mode(e->swing_duration, e->stance_duration, e->stance_mode, 0, e->phase);
@@ -284,6 +287,10 @@ double ce_env_reward(ce_env_t *e, const double *action) { /* clock_reward, cassi
   double right_vel_clock = ce_clock_eval_mode(e->swing_duration, e->stance_duration, e->stance_mode, 3, e->phase);
   double foot_frc_score = tan(PI / 4 * left_frc_clock * nlf) + tan(PI / 4 * right_frc_clock * nrf);
   double foot_vel_score = tan(PI / 4 * left_vel_clock * nlv) + tan(PI / 4 * right_vel_clock * nrv);
+  if (kind == 1) { /* tanh scores (:175-178) */
+    foot_frc_score = tanh(left_frc_clock * nlf) + tanh(right_frc_clock * nrf);
+    foot_vel_score = tanh(left_vel_clock * nlv) + tanh(right_vel_clock * nrv);
+  }
   double hip_roll_penalty = fabs(qvel[6]) + fabs(qvel[13]);
   double torque_penalty = 0, action_penalty = 0;
   for (int k = 0; k < 10; k++) {
@@ -292,6 +299,12 @@ double ce_env_reward(ce_env_t *e, const double *action) { /* clock_reward, cassi
   }
   torque_penalty = 0.25 * (torque_penalty / 10);
   action_penalty = 5 * action_penalty / 10;
+  if (kind == 1)
+    return 0.250 * foot_frc_score + 0.350 * foot_vel_score + 0.200 * exp(-com_vel_error) +
+           0.100 * exp(-(com_orient_error + foot_orient_error)) + 0.100 * exp(-pelvis_motion);
+  if (kind == 2)
+    return 0.250 * foot_frc_score + 0.250 * foot_vel_score + 0.225 * exp(-(com_orient_error + foot_orient_error)) +
+           0.175 * exp(-pelvis_motion) + 0.050 * exp(-hip_roll_penalty) + 0.025 * exp(-torque_penalty) + 0.025 * exp(-action_penalty);
   return 0.200 * foot_frc_score + 0.200 * foot_vel_score + 0.200 * exp(-(com_orient_error + foot_orient_error)) +
          0.150 * exp(-pelvis_motion) + 0.150 * exp(-com_vel_error) + 0.050 * exp(-hip_roll_penalty) +
          0.025 * exp(-torque_penalty) + 0.025 * exp(-action_penalty);

@@ -93,6 +93,22 @@ def main():
             print(tag, "episode lengths", r["ep_len"], "done flags", int(r["done"].sum()), "swing/stance/mode", r["reset_phase"].tolist())
         res["mirrored_obs"] = np.array(env.mirrored_obs, dtype=np.float64)
         res["clock_inds"] = np.array(env.clock_inds)
+        # reward-name variants of the clock reward family (cassie.py:176-232, 771-780; cassie/rewards/clock_rewards.py:6, 119, 225)
+        for tag, profile, reward, kind in (("phase_nospeed", "phase", "no_speed_clock", 2), ("phase_early", "phase", "early_clock", 1),
+                                           ("clock_aerial_early", "clock", "early_aerial_clock", 1), ("clock_grounded", "clock", "grounded_clock", 0)):
+            G.parse_reset = (lambda calls, d, traj=False: parse_reset_phase(calls, d, False)) if profile == "phase" else ORIG_PARSE_RESET
+            np.random.seed(901 + kind)
+            random.seed(17 + kind)
+            rng = np.random.default_rng(41 + kind)
+            env = CassieEnv(simrate=50, command_profile=profile, input_profile="full", dynamics_randomization=False, reward=reward)
+            assert env.reward_func == ("no_speed_clock" if kind == 2 else "clock") and env.early_reward == ("early" in reward)
+            extra.clear()
+            r = G.record(env, False, n_episodes=4, steps_per_episode=8, rng=rng, hit_boost=True)
+            r["reset_phase"] = np.array(extra) if profile == "phase" else np.zeros((4, 3))
+            r["stance_mode"] = np.array(MODES[env.stance_mode])
+            for k, v in r.items():
+                res[f"{tag}.{k}"] = v
+            print(tag, "episode lengths", r["ep_len"], "reward range", r["reward"].min(), r["reward"].max(), "stance mode", env.stance_mode)
         np.savez_compressed(os.path.join(HERE, "env_episodes_phase.npz"), **res)
     finally:
         os.chdir(cwd)

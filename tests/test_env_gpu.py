@@ -12,7 +12,7 @@ def _run(dtype, dyn, n=16, steps=12, seed=11, command_profile="clock", reward="c
     from apex_b200.envs import BatchedCassieEnv
     env = BatchedCassieEnv(n, dtype=dtype, seed=seed, dynamics_randomization=dyn, command_profile=command_profile, reward=reward,
                            max_traj_len=max_traj_len)
-    ora = OracleBatch(n, seed, dyn, command_profile=env._cmd_profile)
+    ora = OracleBatch(n, seed, dyn, command_profile=env._cmd_profile, reward_kind=env._reward_kind, stance_mode=env._stance0)
     o_g = env.reset().cpu().numpy().astype(np.float64)
     o_c = ora.reset().copy()
     rng = np.random.default_rng(3)
@@ -64,6 +64,16 @@ def test_phase_command_profile_f64_matches_oracle(reward, dyn):
         assert o[:, 48].min() >= 0.01 and o[:, 48].max() <= 0.5 + 1e-12 and o[:, 49].max() <= 0.3 + 1e-12
     else:
         assert (o[:, 48] + o[:, 49]).max() <= 0.6 + 1e-9 and (o[:, 48] + o[:, 49]).min() >= 0.3 - 1e-9
+
+
+@pytest.mark.parametrize("profile,reward", [("phase", "no_speed_clock"), ("phase", "early_clock"), ("clock", "early_aerial_clock"),
+                                            ("clock", "grounded_clock")])
+def test_reward_name_variants_f64_match_oracle(profile, reward):
+    """no_speed_clock_reward / early_clock_reward / the grounded and aerial clocks of the clock profile (the oracle side is pinned
+    to the reference's Python by tests/test_oracle_cpu.py::test_reward_name_variants_match_the_reference_python)."""
+    out, env = _run(torch.float64, dyn=True, n=32, steps=12, seed=29, command_profile=profile, reward=reward, max_traj_len=7)
+    assert out["reset"] < 1e-10 and out["done_mismatch"] == 0
+    assert np.max(out["obs"]) < 1e-8 and np.max(out["rew"]) < 1e-8, (np.max(out["obs"]), np.max(out["rew"]))
 
 
 def test_phase_command_profile_trains():

@@ -383,6 +383,30 @@ def test_env_layer_matches_the_reference_python(tag, dyn, traj):
     assert t == len(f("reward")) and f("done").sum() >= 1  # at least one episode ends by falling
 
 
+@pytest.mark.parametrize("tag,profile,kind,stance", [("phase_nospeed", 1, 2, 0), ("phase_early", 1, 1, 0), ("clock_aerial_early", 0, 1, 2),
+                                                      ("clock_grounded", 0, 0, 1)])
+def test_reward_name_variants_match_the_reference_python(tag, profile, kind, stance):
+    """The reward names cassie.py:176-232 parses: no_speed_clock_reward (phase profile), early_clock_reward (either profile), the
+    "grounded" / "aerial" stance modes of the clock profile — episodes recorded from the reference's cassie.py +
+    cassie/rewards/clock_rewards.py (tests/golden/make_env_golden_phase.py) replayed through oracle/cassie_env.c."""
+    from tests.oracle_util import OracleEnv
+    g = np.load(os.path.join(G, "env_episodes_phase.npz"))
+    f = lambda k: g[f"{tag}.{k}"]
+    assert int(f("stance_mode")) == stance or profile == 1
+    env = OracleEnv(False, command_profile=profile, reward_kind=kind, stance_mode=stance)
+    t = 0
+    for ep, n in enumerate(f("ep_len")):
+        obs = env.reset_with(f("reset_scalar")[ep], f("reset_damping")[ep], f("reset_mass")[ep], f("reset_friction")[ep],
+                             f("reset_tilt")[ep], f("reset_menc")[ep], f("reset_jenc")[ep], phase=f("reset_phase")[ep] if profile else None)
+        assert np.abs(obs - f("reset_obs")[ep]).max() < 1e-10
+        for k in range(n):
+            obs, rew, done = env.step_with(f("action")[t], f("step_hit")[t], f("step_val")[t])
+            assert done == f("done")[t] and abs(rew - f("reward")[t]) < 1e-10, (ep, k, rew, f("reward")[t])
+            assert np.abs(obs - f("obs")[t]).max() < 1e-9
+            t += 1
+    assert t == len(f("reward"))
+
+
 @pytest.mark.parametrize("tag,dyn,profile", [("phase_plain", False, 1), ("phase_dynrand", True, 1), ("library_plain", False, 2)])
 def test_phase_command_profile_matches_the_reference_python(tag, dyn, profile):
     """command_profile="phase" (SURVEY §8f rank 4): 55 observations (clock, swing / stance duration, one-hot stance mode, speeds;

@@ -2,7 +2,7 @@
 # bench.py under torchrun on N GPUs (the driver's launch line), short run
 n=${1:-2}; steps=${2:-2}
 mkdir -p gpurun_out/bn$n
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $n --steps $steps --warmup 3 > gpurun_out/bn$n/bench.json 2> gpurun_out/bn$n/bench.err
+timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $n --steps $steps --warmup 3 > gpurun_out/bn$n/bench.json 2> gpurun_out/bn$n/bench.err
 tail -c 800 gpurun_out/bn$n/bench.err
 python - <<PY
 import json
