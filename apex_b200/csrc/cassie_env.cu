@@ -21,7 +21,9 @@ template <typename T> __device__ __forceinline__ void ws_store(const CassieWs<T>
 
 template <typename T> __global__ void __launch_bounds__(32) k_env_init(T *st, int *sti, int n, unsigned seed, int env_id0, int dyn, int variant) {
   extern __shared__ __align__(16) unsigned char smem[];
-  CassieWs<T> &w = *reinterpret_cast<CassieWs<T> *>(smem);
+  cw_tabs_fill<T>(reinterpret_cast<CwTabs<T> *>(smem), threadIdx.x, blockDim.x); /* the model tables in front, then the workspace */
+  __syncthreads();
+  CassieWs<T> &w = *reinterpret_cast<CassieWs<T> *>(smem + CW_TABS_BYTES(T));
   const int e = blockIdx.x, lane = threadIdx.x;
   if (e >= n) return;
   cw_env_init<T>(w, seed, (unsigned)(env_id0 + e), dyn, lane);
@@ -31,7 +33,9 @@ template <typename T> __global__ void __launch_bounds__(32) k_env_init(T *st, in
 
 template <typename T> __global__ void __launch_bounds__(32) k_env_reset(T *st, int *sti, int n, T *obs, CassieTraj<T> traj) {
   extern __shared__ __align__(16) unsigned char smem[];
-  CassieWs<T> &w = *reinterpret_cast<CassieWs<T> *>(smem);
+  cw_tabs_fill<T>(reinterpret_cast<CwTabs<T> *>(smem), threadIdx.x, blockDim.x); /* the model tables in front, then the workspace */
+  __syncthreads();
+  CassieWs<T> &w = *reinterpret_cast<CassieWs<T> *>(smem + CW_TABS_BYTES(T));
   const int e = blockIdx.x, lane = threadIdx.x;
   if (e >= n) return;
   ws_load(w, st + (size_t)e * S_WORDS, sti + (size_t)e * I_WORDS, lane);
@@ -41,7 +45,9 @@ template <typename T> __global__ void __launch_bounds__(32) k_env_reset(T *st, i
 
 template <typename T> __global__ void __launch_bounds__(32) k_env_reset_for_test(T *st, int *sti, int n, T *obs, const int *active, int full) {
   extern __shared__ __align__(16) unsigned char smem[];
-  CassieWs<T> &w = *reinterpret_cast<CassieWs<T> *>(smem);
+  cw_tabs_fill<T>(reinterpret_cast<CwTabs<T> *>(smem), threadIdx.x, blockDim.x); /* the model tables in front, then the workspace */
+  __syncthreads();
+  CassieWs<T> &w = *reinterpret_cast<CassieWs<T> *>(smem + CW_TABS_BYTES(T));
   const int e = blockIdx.x, lane = threadIdx.x;
   if (e >= n || (active && !active[e])) return;
   ws_load(w, st + (size_t)e * S_WORDS, sti + (size_t)e * I_WORDS, lane);
@@ -56,12 +62,14 @@ __global__ void __launch_bounds__(sizeof(T) == 4 ? CW_STEP_THREADS_F32 : 224) k_
                            const int *active, CassieTraj<T> traj, const int *order, int bar_mask) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
-  CassieWs<T> &w = reinterpret_cast<CassieWs<T> *>(smem)[warp];
+  cw_tabs_fill<T>(reinterpret_cast<CwTabs<T> *>(smem), threadIdx.x, blockDim.x); /* per-CTA copy of the model tables (cassie_tabs.h) */
+  __syncthreads();
+  CassieWs<T> &w = reinterpret_cast<CassieWs<T> *>(smem + CW_TABS_BYTES(T))[warp];
   const int slot = blockIdx.x * wpb + warp;
   /* order (optional): slot -> env, envs of similar solver cost share a CTA (and its per-sub-step barrier), dearest first */
   const int e = slot < n ? (order ? order[slot] : slot) : n;
   /* the CTA's mbarrier (split barrier, CW_SPLIT) sits behind the workspaces: one arrival per warp and phase */
-  const unsigned bar_addr = (unsigned)__cvta_generic_to_shared(smem + (size_t)wpb * sizeof(CassieWs<T>));
+  const unsigned bar_addr = (unsigned)__cvta_generic_to_shared(smem + CW_TABS_BYTES(T) + (size_t)wpb * sizeof(CassieWs<T>));
   if (bar_mask & CW_SPLIT) {
     if (threadIdx.x == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_addr), "r"(wpb) : "memory");
     __syncthreads();
@@ -102,7 +110,9 @@ __global__ void __launch_bounds__(sizeof(T) == 4 ? CW_STEP_THREADS_F32 : 224) k_
 
 template <typename T> __global__ void __launch_bounds__(32) k_mj_step(T *st, int *sti, int n, int flags) {
   extern __shared__ __align__(16) unsigned char smem[];
-  CassieWs<T> &w = *reinterpret_cast<CassieWs<T> *>(smem);
+  cw_tabs_fill<T>(reinterpret_cast<CwTabs<T> *>(smem), threadIdx.x, blockDim.x); /* the model tables in front, then the workspace */
+  __syncthreads();
+  CassieWs<T> &w = *reinterpret_cast<CassieWs<T> *>(smem + CW_TABS_BYTES(T));
   const int e = blockIdx.x, lane = threadIdx.x;
   if (e >= n) return;
   ws_load(w, st + (size_t)e * S_WORDS, sti + (size_t)e * I_WORDS, lane);
@@ -207,10 +217,10 @@ int apex_cassie_layout(const char *name) {
 
 static int env_init_impl(int dtype, void *st, int *sti, int n, unsigned seed, int env_id0, int dyn_rand, int variant, void *stream) {
   DISPATCH(
-      if ((rc = prep(k_env_init<float>, sizeof(CassieWs<float>)))) return rc;
-      (k_env_init<float><<<n, 32, sizeof(CassieWs<float>), s>>>((float *)st, sti, n, seed, env_id0, dyn_rand, variant)),
-      if ((rc = prep(k_env_init<double>, sizeof(CassieWs<double>)))) return rc;
-      (k_env_init<double><<<n, 32, sizeof(CassieWs<double>), s>>>((double *)st, sti, n, seed, env_id0, dyn_rand, variant)))
+      if ((rc = prep(k_env_init<float>, (sizeof(CassieWs<float>) + CW_TABS_BYTES(float))))) return rc;
+      (k_env_init<float><<<n, 32, (sizeof(CassieWs<float>) + CW_TABS_BYTES(float)), s>>>((float *)st, sti, n, seed, env_id0, dyn_rand, variant)),
+      if ((rc = prep(k_env_init<double>, (sizeof(CassieWs<double>) + CW_TABS_BYTES(double))))) return rc;
+      (k_env_init<double><<<n, 32, (sizeof(CassieWs<double>) + CW_TABS_BYTES(double)), s>>>((double *)st, sti, n, seed, env_id0, dyn_rand, variant)))
 }
 
 static int env_reset_impl(int dtype, void *st, int *sti, int n, void *obs, const void *traj, int traj_rows, int traj_len, void *stream) {
@@ -219,10 +229,10 @@ static int env_reset_impl(int dtype, void *st, int *sti, int n, void *obs, const
   const CassieTraj<float> tf = {(const float *)traj, traj_rows, traj_len};
   const CassieTraj<double> td = {(const double *)traj, traj_rows, traj_len};
   DISPATCH(
-      if ((rc = prep(k_env_reset<float>, sizeof(CassieWs<float>)))) return rc;
-      (k_env_reset<float><<<n, 32, sizeof(CassieWs<float>), s>>>((float *)st, sti, n, (float *)obs, tf)),
-      if ((rc = prep(k_env_reset<double>, sizeof(CassieWs<double>)))) return rc;
-      (k_env_reset<double><<<n, 32, sizeof(CassieWs<double>), s>>>((double *)st, sti, n, (double *)obs, td)))
+      if ((rc = prep(k_env_reset<float>, (sizeof(CassieWs<float>) + CW_TABS_BYTES(float))))) return rc;
+      (k_env_reset<float><<<n, 32, (sizeof(CassieWs<float>) + CW_TABS_BYTES(float)), s>>>((float *)st, sti, n, (float *)obs, tf)),
+      if ((rc = prep(k_env_reset<double>, (sizeof(CassieWs<double>) + CW_TABS_BYTES(double))))) return rc;
+      (k_env_reset<double><<<n, 32, (sizeof(CassieWs<double>) + CW_TABS_BYTES(double)), s>>>((double *)st, sti, n, (double *)obs, td)))
 }
 
 static int env_step_impl(int dtype, void *st, int *sti, int n, const void *action, void *obs, void *reward, int *done,
@@ -237,11 +247,11 @@ static int env_step_impl(int dtype, void *st, int *sti, int n, const void *actio
   const CassieTraj<float> tf = {(const float *)traj, traj_rows, traj_len};
   const CassieTraj<double> td = {(const double *)traj, traj_rows, traj_len};
   DISPATCH(
-      if ((rc = prep(k_env_step<float>, wpb * sizeof(CassieWs<float>) + 16))) return rc;
-      (k_env_step<float><<<(n + wpb - 1) / wpb, 32 * wpb, wpb * sizeof(CassieWs<float>) + 16, s>>>((float *)st, sti, n, (const float *)action, (float *)obs,
+      if ((rc = prep(k_env_step<float>, wpb * sizeof(CassieWs<float>) + CW_TABS_BYTES(float) + 16))) return rc;
+      (k_env_step<float><<<(n + wpb - 1) / wpb, 32 * wpb, wpb * sizeof(CassieWs<float>) + CW_TABS_BYTES(float) + 16, s>>>((float *)st, sti, n, (const float *)action, (float *)obs,
                                                                 (float *)reward, done, (float *)term_obs, max_traj_len, active, tf, order, apex_cassie_bar_mask)),
-      if ((rc = prep(k_env_step<double>, wpb * sizeof(CassieWs<double>) + 16))) return rc;
-      (k_env_step<double><<<(n + wpb - 1) / wpb, 32 * wpb, wpb * sizeof(CassieWs<double>) + 16, s>>>((double *)st, sti, n, (const double *)action, (double *)obs,
+      if ((rc = prep(k_env_step<double>, wpb * sizeof(CassieWs<double>) + CW_TABS_BYTES(double) + 16))) return rc;
+      (k_env_step<double><<<(n + wpb - 1) / wpb, 32 * wpb, wpb * sizeof(CassieWs<double>) + CW_TABS_BYTES(double) + 16, s>>>((double *)st, sti, n, (const double *)action, (double *)obs,
                                                                   (double *)reward, done, (double *)term_obs, max_traj_len, active, td, order, apex_cassie_bar_mask)))
 }
 
@@ -256,10 +266,10 @@ int apex_cassie_env_reset_for_test(int dtype, void *st, int *sti, int n, void *o
   if (n <= 0) return 0;
   if (!obs) return -1000;
   DISPATCH(
-      if ((rc = prep(k_env_reset_for_test<float>, sizeof(CassieWs<float>)))) return rc;
-      (k_env_reset_for_test<float><<<n, 32, sizeof(CassieWs<float>), s>>>((float *)st, sti, n, (float *)obs, active, full_reset)),
-      if ((rc = prep(k_env_reset_for_test<double>, sizeof(CassieWs<double>)))) return rc;
-      (k_env_reset_for_test<double><<<n, 32, sizeof(CassieWs<double>), s>>>((double *)st, sti, n, (double *)obs, active, full_reset)))
+      if ((rc = prep(k_env_reset_for_test<float>, (sizeof(CassieWs<float>) + CW_TABS_BYTES(float))))) return rc;
+      (k_env_reset_for_test<float><<<n, 32, (sizeof(CassieWs<float>) + CW_TABS_BYTES(float)), s>>>((float *)st, sti, n, (float *)obs, active, full_reset)),
+      if ((rc = prep(k_env_reset_for_test<double>, (sizeof(CassieWs<double>) + CW_TABS_BYTES(double))))) return rc;
+      (k_env_reset_for_test<double><<<n, 32, (sizeof(CassieWs<double>) + CW_TABS_BYTES(double)), s>>>((double *)st, sti, n, (double *)obs, active, full_reset)))
 }
 int apex_cassie_env_step(int dtype, void *st, int *sti, int n, const void *action, void *obs, void *reward, int *done,
                          void *term_obs, int max_traj_len, void *stream) {
@@ -307,10 +317,10 @@ int apex_cassie_env_step_ordered(int dtype, void *st, int *sti, int n, const voi
 
 int apex_cassie_mj_step(int dtype, void *st, int *sti, int n, int flags, void *stream) {
   DISPATCH(
-      if ((rc = prep(k_mj_step<float>, sizeof(CassieWs<float>)))) return rc;
-      (k_mj_step<float><<<n, 32, sizeof(CassieWs<float>), s>>>((float *)st, sti, n, flags)),
-      if ((rc = prep(k_mj_step<double>, sizeof(CassieWs<double>)))) return rc;
-      (k_mj_step<double><<<n, 32, sizeof(CassieWs<double>), s>>>((double *)st, sti, n, flags)))
+      if ((rc = prep(k_mj_step<float>, (sizeof(CassieWs<float>) + CW_TABS_BYTES(float))))) return rc;
+      (k_mj_step<float><<<n, 32, (sizeof(CassieWs<float>) + CW_TABS_BYTES(float)), s>>>((float *)st, sti, n, flags)),
+      if ((rc = prep(k_mj_step<double>, (sizeof(CassieWs<double>) + CW_TABS_BYTES(double))))) return rc;
+      (k_mj_step<double><<<n, 32, (sizeof(CassieWs<double>) + CW_TABS_BYTES(double)), s>>>((double *)st, sti, n, flags)))
 }
 
 } /* extern "C" */

@@ -32,12 +32,12 @@ template <typename T> CW_NOINL void cw_sim_step_pd(CassieWs<T> &w, int bar CW_LA
   CW_FOR_LANES {
     if (lane < CM_NU) {
       const int i = lane;
-      const T gear = (T)CMT(act_gear)[i];
+      const T gear = (T)CMTS(act_gear)[i];
       /* pd_input_step on the previous call's cassie_out */
       const T pg = hasu ? (T)CWT(CW_PGAIN)[i % 5] : (T)0, dg = hasu ? (T)CWT(CW_DGAIN)[i % 5] : (T)0;
       const T ucmd = (T)0 + pg * (w.st[S_UPTARGET + i] - w.st[S_OMPOS + i]) + dg * ((T)0 - w.st[S_OMVEL + i]);
       /* motor model, @0x7d30-0x7eaa */
-      const T wv = w.st[S_SENS_ACTVEL + i], wmax = (T)CMT(act_rpm)[i] * (T)CW_TWO_PI / (T)60.0, tmax = (T)CMT(act_ctrlmax)[i];
+      const T wv = w.st[S_SENS_ACTVEL + i], wmax = (T)CMTS(act_rpm)[i] * (T)CW_TWO_PI / (T)60.0, tmax = (T)CMTS(act_ctrlmax)[i];
       const T tlim = cw_max(cw_min(2 * tmax * (1 - cw_div(cw_abs(wv), wmax)), tmax), (T)0);
       T tau = cw_min(cw_abs(cw_div(ucmd, gear)), tlim);
       if (ucmd < 0 || (ucmd == 0 && 1 / ucmd < 0)) tau = -tau; /* copysign */
@@ -47,7 +47,7 @@ template <typename T> CW_NOINL void cw_sim_step_pd(CassieWs<T> &w, int bar CW_LA
       w.st[S_CTRL + i] = dl[5];
       w.y[Y_MTORQUE + i] = gear * dl[5];
       /* drive encoder, @0x7fe0-0x8137 */
-      const T N = (T)(1 << CM_drive_bits[i]);
+      const T N = (T)(1 << CMS(drive_bits)[i]);
       const int32_t c = w.sti[I_SENSCNT + i]; /* = (int32_t)(actuatorpos / 2 pi * N), taken in float64 by cw_mj_step's sensor stage */
       int *hist = w.sti + I_DRIVEHIST + 9 * i;
       if (!dinit) for (int k = 0; k < 9; k++) hist[k] = c;
@@ -62,7 +62,7 @@ template <typename T> CW_NOINL void cw_sim_step_pd(CassieWs<T> &w, int bar CW_LA
     } else if (lane < CM_NU + 6) {
       /* joint encoder + IIR differentiator, @0x81a0-0x82b7, constants .rodata @0x2f2d8-0x2f2f0 */
       const int s = lane - CM_NU;
-      const T N = (T)(1 << CM_jsens_bits[s]);
+      const T N = (T)(1 << CMS(jsens_bits)[s]);
       const int32_t c = w.sti[I_SENSCNT + CM_NU + s];
       const T x = (T)c * ((T)CW_TWO_PI / N);
       T *jx = w.st + S_JX + 4 * s, *jy = w.st + S_JY + 2 * s;
@@ -190,7 +190,7 @@ template <typename T> CW_NOINL void cw_env_obs(CassieWs<T> &w, T *obs_out CW_LAN
 template <typename T> CW_NOINL void cw_set_const(CassieWs<T> &w CW_LANE_PARAM) {
   /* stage the 35-long qpos0 in the (currently unused) packed-A storage; J is not safe: kinematics' scratch overlays it */
   T *q0 = w.Ap;
-  CW_FOR_LANES { for (int k = lane; k < CM_NQ; k += 32) q0[k] = (T)CMT(qpos0)[k]; }
+  CW_FOR_LANES { for (int k = lane; k < CM_NQ; k += 32) q0[k] = (T)CMTS(qpos0)[k]; }
   CW_SYNC();
   cw_kinematics<T>(w, q0 CW_LANE_ARG);
   cw_crb<T>(w CW_LANE_ARG);
@@ -211,9 +211,9 @@ template <typename T> CW_NOINL void cw_set_const(CassieWs<T> &w CW_LANE_PARAM) {
   }
   CW_SYNC();
   CW_FOR_LANES {
-    const int j = CM_dof_jnt[lane];
+    const int j = CMS(dof_jnt)[lane];
     T v = w.vec[V_TMP][lane];
-    if (CM_jnt_type[j] == 2) { const int da = CM_jnt_dofadr[j]; v = (w.vec[V_TMP][da] + w.vec[V_TMP][da + 1] + w.vec[V_TMP][da + 2]) / (T)3; }
+    if (CMS(jnt_type)[j] == 2) { const int da = CMS(jnt_dofadr)[j]; v = (w.vec[V_TMP][da] + w.vec[V_TMP][da + 1] + w.vec[V_TMP][da + 2]) / (T)3; }
     w.st[S_DOFINVW + lane] = v;
     if (lane == 0) w.st[S_BODYINVW] = 0;
   }
@@ -223,7 +223,7 @@ template <typename T> CW_NOINL void cw_set_const(CassieWs<T> &w CW_LANE_PARAM) {
     const int nb = (CW_NB - b0) < 10 ? (CW_NB - b0) : 10;
     for (int bb = 0; bb < nb; bb++) {
       const int b = b0 + bb;
-      T ip[3] = {(T)CMT(body_ipos)[b][0], (T)CMT(body_ipos)[b][1], (T)CMT(body_ipos)[b][2]}, off[3];
+      T ip[3] = {(T)CMTS(body_ipos)[b][0], (T)CMTS(body_ipos)[b][1], (T)CMTS(body_ipos)[b][2]}, off[3];
       cw_mulv(off, w.xmat[b], ip);
       for (int k = 0; k < 3; k++) off[k] += w.xpos[b][k] - org[k];
       CW_FOR_LANES {
@@ -630,3 +630,4 @@ template <typename T> CW_NOINL void cw_env_step(CassieWs<T> &w, T *obs_out, T *r
   cw_env_obs<T>(w, obs_out CW_LANE_ARG);
 }
 #endif
+#include "cassie_tabs_fill.h"

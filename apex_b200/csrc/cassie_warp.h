@@ -55,6 +55,22 @@ template <typename T> struct CmSel;
 template <> struct CmSel<double> { template <class D, class F> CW_MEMBER_FN const D &get(const D &d, const F &) { return d; } };
 template <> struct CmSel<float> { template <class D, class F> CW_MEMBER_FN const F &get(const D &, const F &f) { return f; } };
 #define CMT(name) (CmSel<T>::get(CM_##name, CM_##name##_f32))
+/* CMS(name) / CMTS(name): the same tables where the index is only known at run time (per-lane body / dof / joint / geom tables).
+ * On the device they are read from a per-CTA copy in shared memory (CwTabs<T>, csrc/cassie_tabs.h, at the start of the dynamic
+ * shared memory; every kernel fills it once with cw_tabs_fill): as `static __device__ const` arrays they were LDG.E.CONSTANT loads
+ * through the ~8 KB of L1 the workspaces leave, a 64-bit address computation each and 6 % of the step kernel's stall samples.
+ * Accesses with compile-time indices keep using CM_name / CMT(name), which fold into immediates. */
+#ifdef __CUDACC__
+template <typename T> struct CwTabs;
+extern __shared__ __align__(16) unsigned char cw_dyn_smem[];
+template <typename T> __device__ __forceinline__ const CwTabs<T> *cw_tabs() { return reinterpret_cast<const CwTabs<T> *>(cw_dyn_smem); }
+#define CMS(name) (cw_tabs<T>()->name)
+#define CMTS(name) (cw_tabs<T>()->name)
+#else
+#define CMS(name) CMS_HOST_##name
+#define CMTS(name) CMT(name)
+#endif
+#include "cassie_tabs.h"
 
 #ifdef __CUDACC__
 __device__ __forceinline__ void cw_mbar_arrive(unsigned addr, int lane) {
@@ -371,16 +387,16 @@ template <typename T> CW_FN void cw_kinematics(CassieWs<T> &w, const T *qpos CW_
       cw_qnorm(q);
       for (int k = 0; k < 3; k++) p[k] = qpos[k];
     } else if (lane >= 2 && lane < CW_NB) {
-      const int b = lane, j = CM_body_jnt[b];
-      for (int k = 0; k < 4; k++) q[k] = (T)CMT(body_quat)[b][k];
-      for (int k = 0; k < 3; k++) p[k] = (T)CMT(body_pos)[b][k];
+      const int b = lane, j = CMS(body_jnt)[b];
+      for (int k = 0; k < 4; k++) q[k] = (T)CMTS(body_quat)[b][k];
+      for (int k = 0; k < 3; k++) p[k] = (T)CMTS(body_pos)[b][k];
       if (j >= 0) {
-        const int qa = CM_jnt_qposadr[j];
+        const int qa = CMS(jnt_qposadr)[j];
         T qj[4], qn[4];
-        if (CM_jnt_type[j] == 1) {
+        if (CMS(jnt_type)[j] == 1) {
           T s, c;
-          cw_sincos<T>((T)0.5 * (qpos[qa] - (T)CMT(qpos0)[qa]), &s, &c);
-          qj[0] = c; qj[1] = (T)CMT(jnt_axis)[j][0] * s; qj[2] = (T)CMT(jnt_axis)[j][1] * s; qj[3] = (T)CMT(jnt_axis)[j][2] * s;
+          cw_sincos<T>((T)0.5 * (qpos[qa] - (T)CMTS(qpos0)[qa]), &s, &c);
+          qj[0] = c; qj[1] = (T)CMTS(jnt_axis)[j][0] * s; qj[2] = (T)CMTS(jnt_axis)[j][1] * s; qj[3] = (T)CMTS(jnt_axis)[j][2] * s;
         } else {
           qj[0] = qpos[qa]; qj[1] = qpos[qa + 1]; qj[2] = qpos[qa + 2]; qj[3] = qpos[qa + 3];
           cw_qnorm(qj);
@@ -389,7 +405,7 @@ template <typename T> CW_FN void cw_kinematics(CassieWs<T> &w, const T *qpos CW_
         for (int k = 0; k < 4; k++) q[k] = qn[k];
       }
     }
-    const unsigned jump = CM_body_jump[lane];
+    const unsigned jump = CMS(body_jump)[lane];
 #pragma unroll
     for (int r = 0; r < 4; r++) {
       const int a = (int)((jump >> (8 * r)) & 31u);
@@ -499,11 +515,11 @@ template <typename T> CW_FN void cw_kinematics(CassieWs<T> &w, const T *qpos CW_
             w.cdof[3 + a][k] = R[3 * k + a]; w.cdof[3 + a][3 + k] = 0;
           }
       } else {
-        const int j = CM_body_jnt[b];
+        const int j = CMS(body_jnt)[b];
         if (j >= 0) {
-          const int da = CM_jnt_dofadr[j];
-          if (CM_jnt_type[j] == 1) {
-            T al[3] = {(T)CMT(jnt_axis)[j][0], (T)CMT(jnt_axis)[j][1], (T)CMT(jnt_axis)[j][2]}, ax[3];
+          const int da = CMS(jnt_dofadr)[j];
+          if (CMS(jnt_type)[j] == 1) {
+            T al[3] = {(T)CMTS(jnt_axis)[j][0], (T)CMTS(jnt_axis)[j][1], (T)CMTS(jnt_axis)[j][2]}, ax[3];
             cw_mulv(ax, R, al);
             for (int k = 0; k < 3; k++) w.cdof[da][k] = ax[k];
             cw_cross(w.cdof[da] + 3, ax, off);
@@ -517,14 +533,14 @@ template <typename T> CW_FN void cw_kinematics(CassieWs<T> &w, const T *qpos CW_
         }
       }
       /* spatial inertia about org */
-      T in0 = (T)CMT(body_inertia)[b][0], in1 = (T)CMT(body_inertia)[b][1], in2 = (T)CMT(body_inertia)[b][2];
-      T in3 = (T)CMT(body_inertia)[b][3], in4 = (T)CMT(body_inertia)[b][4], in5 = (T)CMT(body_inertia)[b][5];
+      T in0 = (T)CMTS(body_inertia)[b][0], in1 = (T)CMTS(body_inertia)[b][1], in2 = (T)CMTS(body_inertia)[b][2];
+      T in3 = (T)CMTS(body_inertia)[b][3], in4 = (T)CMTS(body_inertia)[b][4], in5 = (T)CMTS(body_inertia)[b][5];
       T Ib[9] = {in0, in3, in4, in3, in1, in5, in4, in5, in2}, Tm[9], Iw[9];
       for (int r = 0; r < 3; r++)
         for (int c = 0; c < 3; c++) Tm[3 * r + c] = R[3 * r] * Ib[c] + R[3 * r + 1] * Ib[3 + c] + R[3 * r + 2] * Ib[6 + c];
       for (int r = 0; r < 3; r++)
         for (int c = 0; c < 3; c++) Iw[3 * r + c] = Tm[3 * r] * R[3 * c] + Tm[3 * r + 1] * R[3 * c + 1] + Tm[3 * r + 2] * R[3 * c + 2];
-      T ip[3] = {(T)CMT(body_ipos)[b][0], (T)CMT(body_ipos)[b][1], (T)CMT(body_ipos)[b][2]}, c[3];
+      T ip[3] = {(T)CMTS(body_ipos)[b][0], (T)CMTS(body_ipos)[b][1], (T)CMTS(body_ipos)[b][2]}, c[3];
       cw_mulv(c, R, ip);
       for (int k = 0; k < 3; k++) c[k] -= off[k]; /* xipos - org */
       const T mass = w.st[S_MASS + b], cc = cw_dot3(c, c);
@@ -574,7 +590,7 @@ template <typename T> CW_FN void cw_crb(CassieWs<T> &w CW_LANE_PARAM) {
     T v[10];
     const bool body = lane >= 1 && lane < CW_NB;
     for (int k = 0; k < 10; k++) v[k] = body ? w.crb[lane][k] : (T)0;
-    cw_subtree_sum<T, 10>(v, lane, body ? CM_body_subtree[lane] : 0);
+    cw_subtree_sum<T, 10>(v, lane, body ? CMS(body_subtree)[lane] : 0);
     CW_SYNC();
     if (body) for (int k = 0; k < 10; k++) w.crb[lane][k] = v[k];
     CW_SYNC();
@@ -602,10 +618,10 @@ template <typename T> CW_FN void cw_build_M(CassieWs<T> &w CW_LANE_PARAM) {
   CW_FOR_LANES {
     const int i = lane;
     T f[6];
-    cw_inert_mul(f, w.crb[CM_dof_body[i]], w.cdof[i]);
-    w.Mdiag[i] = cw_dot6(w.cdof[i], f) + (T)CMT(dof_armature)[i];
-    const int na = CM_dof_nanc[i], rp = CM_dof_rowptr[i];
-    for (int t = 0; t < na; t++) w.Ms[rp + t] = cw_dot6(w.cdof[CM_dof_anc[i][t]], f);
+    cw_inert_mul(f, w.crb[CMS(dof_body)[i]], w.cdof[i]);
+    w.Mdiag[i] = cw_dot6(w.cdof[i], f) + (T)CMTS(dof_armature)[i];
+    const int na = CMS(dof_nanc)[i], rp = CMS(dof_rowptr)[i];
+    for (int t = 0; t < na; t++) w.Ms[rp + t] = cw_dot6(w.cdof[CMS(dof_anc)[i][t]], f);
   }
   CW_SYNC();
 }
@@ -637,7 +653,7 @@ template <typename T, int NF> CW_FN void cw_factor_base(CassieWs<T> &w, T *M0, T
         acc[0] += Mp[0][ok + i] * Mp[0][ok + j] * w.Dinv[k];
         if (NF == 2) acc[NF - 1] += Mp[NF - 1][ok + i] * Mp[NF - 1][ok + j] * Dp[NF - 1][k];
       }
-      for (int f = 0; f < NF; f++) { if (i == j) Dp[f][i] -= acc[f]; else Mp[f][CM_dof_rowptr[i] + j] -= acc[f]; }
+      for (int f = 0; f < NF; f++) { if (i == j) Dp[f][i] -= acc[f]; else Mp[f][CMS(dof_rowptr)[i] + j] -= acc[f]; }
     }
   }
   CW_SYNC();
@@ -649,7 +665,7 @@ template <typename T, int NF> CW_FN void cw_factor_base(CassieWs<T> &w, T *M0, T
     CW_FOR_LANES {
       if (lane == 0) w.Dinv[k] = d[0];
       if (lane < k) {
-        const int ol = CM_dof_rowptr[lane];
+        const int ol = CMS(dof_rowptr)[lane];
         for (int f = 0; f < NF; f++) {
           const T a = Mp[f][ok + lane] * d[f];
           for (int j = 0; j < lane; j++) Mp[f][ol + j] -= a * Mp[f][ok + j];
@@ -690,7 +706,7 @@ template <typename T> __device__ __noinline__ void cw_factor2_dev(CassieWs<T> &w
   T *const D0 = w.vec[V_TMP], *const D1 = w.D;
   const bool leg = lane >= 6, rt = lane >= 19;
   const int ll = lane - (rt ? 13 : 0); /* the left leg's dof with the same role (CM_leg_ancmask is indexed by it) */
-  const int rank = CM_dof_nanc[lane], own = CM_dof_rowptr[lane];
+  const int rank = CMS(dof_nanc)[lane], own = CMS(dof_rowptr)[lane];
   T r0[16], r1[16]; /* own row of the first / second factor (at most 13 entries); entries >= rank are scratch (kept finite) */
   T d0 = w.Mdiag[lane], d1 = d0 + hdamp * w.st[S_DAMPING + lane];
 #pragma unroll
@@ -766,7 +782,7 @@ template <typename T> __device__ __noinline__ void cw_factor2_dev(CassieWs<T> &w
         a01 += M0[ok2 + bi] * M0[ok2 + bj] * w.Dinv[k + 1];
         a11 += M1[ok2 + bi] * M1[ok2 + bj] * D1[k + 1];
       }
-      const int at = CM_dof_rowptr[bi] + bj;
+      const int at = CMS(dof_rowptr)[bi] + bj;
       e0 = (bi == bj ? D0[bi] : M0[at]) - (a00 + a01);
       e1 = (bi == bj ? D1[bi] : M1[at]) - (a10 + a11);
     }
@@ -781,7 +797,7 @@ template <typename T> __device__ __noinline__ void cw_factor2_dev(CassieWs<T> &w
     __syncwarp();
     if (ent) {
       if (bi == bj) { w.Dinv[bi] = cw_rcp(e0); D1[bi] = cw_rcp(e1); }
-      else { const int at = CM_dof_rowptr[bi] + bj; M0[at] = e0; M1[at] = e1; }
+      else { const int at = CMS(dof_rowptr)[bi] + bj; M0[at] = e0; M1[at] = e1; }
     }
     __syncwarp();
   }
@@ -819,7 +835,7 @@ template <typename T, int NF> CW_NOINL void cw_factor(CassieWs<T> &w, T hdamp CW
         const bool rt = lane >= 19;
         const int ll = lane - (rt ? 13 : 0);
         if ((legmask >> ll) & 1u) {
-          const int ok = CM_dof_rowptr[rt ? kR : kL], ol = CM_dof_rowptr[lane];
+          const int ok = CMS(dof_rowptr)[rt ? kR : kL], ol = CMS(dof_rowptr)[lane];
           const unsigned below = legmask & ((1u << ll) - 1u);
           const int rank = 6 + __builtin_popcount(below); /* rank of `lane` in k's chain = its own chain length */
           T a[NF];
@@ -852,7 +868,7 @@ template <typename T> CW_NOINL void cw_solve_LT(const T *Ms, const T *Dinv, T *v
    * own matrix entry (row of the pivot, column = the lane's rank) from shared memory; 13 leg phases + 5 base phases. */
   {
     const bool rt = lane >= 19, base = lane < 6;
-    const int ll = lane - (rt ? 13 : 0), rank = CM_dof_nanc[lane];
+    const int ll = lane - (rt ? 13 : 0), rank = CMS(dof_nanc)[lane];
     const T dinv = Dinv[lane];
     T x = v[lane];
     const T *const colL = Ms + (base ? lane : rank + (rt ? CM_LEG_ROWSPAN : 0)); /* + row of the left pivot: the entry of this lane's leg */
@@ -893,13 +909,13 @@ template <typename T> CW_NOINL void cw_solve_LT(const T *Ms, const T *Dinv, T *v
 template <typename T> CW_NOINL void cw_solve_L(const T *Ms, const T *Dinv, T *v CW_LANE_PARAM) {
 #ifdef __CUDACC__
   { /* device: register-resident vector; the ancestor's value comes by shuffle (depth < 6: the base dof of that number) */
-    const int na = CM_dof_nanc[lane];
+    const int na = CMS(dof_nanc)[lane];
     const T dinv = Dinv[lane];
-    const T *const row = Ms + CM_dof_rowptr[lane];
+    const T *const row = Ms + CMS(dof_rowptr)[lane];
     T x = v[lane];
 #pragma unroll
     for (int lvl = 0; lvl < CM_MAXANC; lvl++) {
-      const int j = lvl < 6 ? lvl : CM_dof_anc[lane][lvl];
+      const int j = lvl < 6 ? lvl : CMS(dof_anc)[lane][lvl];
       const T xj = __shfl_sync(0xffffffffu, x, j & 31);
       const T c = row[lvl] * dinv; /* a valid word for every lane (the rows are at least 13 words from the end of the storage) */
       x -= (na > lvl ? c : (T)0) * xj;
@@ -920,7 +936,7 @@ template <typename T> CW_NOINL void cw_solve_L(const T *Ms, const T *Dinv, T *v 
 
 /* translational Jacobian column of a point (offset from org) on body b for dof = lane */
 template <typename T> CW_FN void cw_jac_col(const CassieWs<T> &w, int b, const T *off, int dof, T *col) {
-  if ((CM_body_dofmask[b] >> dof) & 1u) {
+  if ((CMS(body_dofmask)[b] >> dof) & 1u) {
     T t[3];
     cw_cross(t, w.cdof[dof], off);
     col[0] = t[0] + w.cdof[dof][3]; col[1] = t[1] + w.cdof[dof][4]; col[2] = t[2] + w.cdof[dof][5];
@@ -946,9 +962,9 @@ template <typename T> CW_FN void cw_make_frame(T *fr) { /* mju_makeFrame */
 }
 
 template <typename T> CW_FN void cw_geom_world(const CassieWs<T> &w, int g, T *c, T *ax) {
-  const int b = CM_geom_body[g];
-  T gp[3] = {(T)CMT(geom_pos)[g][0], (T)CMT(geom_pos)[g][1], (T)CMT(geom_pos)[g][2]};
-  T ga[3] = {(T)CMT(geom_axis)[g][0], (T)CMT(geom_axis)[g][1], (T)CMT(geom_axis)[g][2]}, t[3];
+  const int b = CMS(geom_body)[g];
+  T gp[3] = {(T)CMTS(geom_pos)[g][0], (T)CMTS(geom_pos)[g][1], (T)CMTS(geom_pos)[g][2]};
+  T ga[3] = {(T)CMTS(geom_axis)[g][0], (T)CMTS(geom_axis)[g][1], (T)CMTS(geom_axis)[g][2]}, t[3];
   cw_mulv(t, w.xmat[b], gp);
   for (int k = 0; k < 3; k++) c[k] = w.xpos[b][k] + t[k];
   cw_mulv(ax, w.xmat[b], ga);
@@ -964,12 +980,12 @@ template <typename T> CW_FN void cw_collision(CassieWs<T> &w CW_LANE_PARAM) {
   CW_FOR_LANES {
     w.u.p.cand_dist[lane] = 1;
     if (lane < 17) {
-      const int g = CW_CAND_GEOM[lane];
+      const int g = CMS(CW_CAND_GEOM)[lane];
       T fq[4] = {w.st[S_FLOORQ], w.st[S_FLOORQ + 1], w.st[S_FLOORQ + 2], w.st[S_FLOORQ + 3]}, Rf[9];
       cw_qmat(Rf, fq);
       T n[3] = {Rf[2], Rf[5], Rf[8]}, c[3], ax[3];
       cw_geom_world(w, g, c, ax);
-      const T r = (T)CMT(geom_radius)[g], hl = (T)CMT(geom_halflen)[g] * (T)CW_CAND_END[lane];
+      const T r = (T)CMTS(geom_radius)[g], hl = (T)CMTS(geom_halflen)[g] * (T)CMS(CW_CAND_END)[lane];
       T pc[3] = {c[0] + hl * ax[0], c[1] + hl * ax[1], c[2] + hl * ax[2]};
       T rel[3] = {pc[0], pc[1], pc[2] - (T)CM_FLOOR_Z};
       const T dist = cw_dot3(rel, n) - r;
@@ -980,11 +996,11 @@ template <typename T> CW_FN void cw_collision(CassieWs<T> &w CW_LANE_PARAM) {
         w.u.p.cand_hint[lane][k] = CW_CAND_END[lane] != 0 ? ax[k] : (T)0;
       }
     } else if (lane < 26) {
-      const int g1 = CW_PAIR_G1[lane - 17], g2 = CW_PAIR_G2[lane - 17];
+      const int g1 = CMS(CW_PAIR_G1)[lane - 17], g2 = CMS(CW_PAIR_G2)[lane - 17];
       T c1[3], a1[3], c2[3], a2[3];
       cw_geom_world(w, g1, c1, a1);
       cw_geom_world(w, g2, c2, a2);
-      const T h1 = (T)CMT(geom_halflen)[g1], h2 = (T)CMT(geom_halflen)[g2], r1 = (T)CMT(geom_radius)[g1], r2 = (T)CMT(geom_radius)[g2];
+      const T h1 = (T)CMTS(geom_halflen)[g1], h2 = (T)CMTS(geom_halflen)[g2], r1 = (T)CMTS(geom_radius)[g1], r2 = (T)CMTS(geom_radius)[g2];
       T r[3] = {c1[0] - c2[0], c1[1] - c2[1], c1[2] - c2[2]};
       const T b = cw_dot3(a1, a2), c = cw_dot3(a1, r), f = cw_dot3(a2, r), den = 1 - b * b;
       T ss = den > (T)1e-12 ? cw_div(b * f - c, den) : (T)0;
@@ -1023,8 +1039,8 @@ template <typename T> CW_FN void cw_collision(CassieWs<T> &w CW_LANE_PARAM) {
       cw_make_frame(fr);
       for (int k = 0; k < 9; k++) w.con_frame[lane][k] = fr[k];
       w.con_dist[lane] = w.u.p.cand_dist[s];
-      if (s < 17) { w.con_geom[lane] = CW_CAND_GEOM[s]; w.con_geom1[lane] = -1; w.con_dim[lane] = 3; w.con_mu[lane] = w.st[S_FRICTION]; }
-      else { w.con_geom[lane] = CW_PAIR_G2[s - 17]; w.con_geom1[lane] = CW_PAIR_G1[s - 17]; w.con_dim[lane] = 1; w.con_mu[lane] = 0; }
+      if (s < 17) { w.con_geom[lane] = CMS(CW_CAND_GEOM)[s]; w.con_geom1[lane] = -1; w.con_dim[lane] = 3; w.con_mu[lane] = w.st[S_FRICTION]; }
+      else { w.con_geom[lane] = CMS(CW_PAIR_G2)[s - 17]; w.con_geom1[lane] = CMS(CW_PAIR_G1)[s - 17]; w.con_dim[lane] = 1; w.con_mu[lane] = 0; }
       w.con_adr[lane] = -1;
     }
   }
@@ -1090,14 +1106,14 @@ template <typename T> CW_FN void cw_make_constraint(CassieWs<T> &w, const T *qpo
     /* joint limits */
 #ifdef __CUDA_ARCH__
     { /* device: lane = (limited joint, side) pair in the reference order; one ballot, then only the violated ones are visited */
-      const int jl = CW_LIM_JNT[lane >> 1], sidel = (lane & 1) ? 1 : -1;
-      const T distl = (T)sidel * ((T)CMT(jnt_range)[jl][lane & 1] - qpos[CM_jnt_qposadr[jl]]);
+      const int jl = CMS(CW_LIM_JNT)[lane >> 1], sidel = (lane & 1) ? 1 : -1;
+      const T distl = (T)sidel * ((T)CMTS(jnt_range)[jl][lane & 1] - qpos[CMS(jnt_qposadr)[jl]]);
       unsigned viol = __ballot_sync(0xffffffffu, distl < 0);
       while (viol) {
         const int l = cw_ctz(viol);
         viol &= viol - 1;
         if (r + crows < CW_NEFC) {
-          const int da = CM_jnt_dofadr[CW_LIM_JNT[l >> 1]];
+          const int da = CMS(jnt_dofadr)[CMS(CW_LIM_JNT)[l >> 1]];
           const T dist = __shfl_sync(0xffffffffu, distl, l);
           w.u.J[r][lane] = (lane == da) ? ((l & 1) ? (T)-1 : (T)1) : (T)0;
           if (lane == 0) { w.efc_aref[r] = dist; w.efc_R[r] = w.st[S_DOFINVW + da]; w.efc_type[r] = 1; }
@@ -1127,7 +1143,7 @@ template <typename T> CW_FN void cw_make_constraint(CassieWs<T> &w, const T *qpo
     const int nc = nckeep;
     for (int c = 0; c < nc; c++) {
       const int nrow = w.con_dim[c] == 3 ? 4 : 1;
-      const int b2 = CM_geom_body[w.con_geom[c]], g1 = w.con_geom1[c], b1 = g1 >= 0 ? CM_geom_body[g1] : 0;
+      const int b2 = CMS(geom_body)[w.con_geom[c]], g1 = w.con_geom1[c], b1 = g1 >= 0 ? CMS(geom_body)[g1] : 0;
       T off[3] = {w.con_pos[c][0] - org[0], w.con_pos[c][1] - org[1], w.con_pos[c][2] - org[2]};
       const T tran = w.st[S_BODYINVW + b1] + w.st[S_BODYINVW + b2], mu = w.con_mu[c], dist = w.con_dist[c];
       const T *fr = w.con_frame[c];
@@ -1245,7 +1261,7 @@ template <typename T> CW_FN void cw_rne(CassieWs<T> &w, const T *qvel CW_LANE_PA
 #ifdef __CUDACC__
     if (lane >= 1 && lane < CW_NB) {
       my_level = CM_body_level[lane]; my_parent = CM_body_parent[lane];
-      const int da = CM_body_dofadr[lane], nd = CM_body_dofnum[lane];
+      const int da = CMS(body_dofadr)[lane], nd = CMS(body_dofnum)[lane];
       for (int s = 0; s < nd; s++) {
         const T qd = qvel[da + s];
         for (int k = 0; k < 6; k++) jv[k] += w.cdof[da + s][k] * qd;
@@ -1257,7 +1273,7 @@ template <typename T> CW_FN void cw_rne(CassieWs<T> &w, const T *qvel CW_LANE_PA
 #ifdef __CUDACC__
   /* path sums down the tree by pointer jumping: 4 rounds of "add the partial sum of my 2^r-th ancestor" (CM_body_jump; a path
    * shorter than that points at lane 31, no body, which carries zeros) instead of 9 level sweeps through shared memory */
-  const unsigned jump = CM_body_jump[lane];
+  const unsigned jump = CMS(body_jump)[lane];
   {
 #pragma unroll
     for (int r = 0; r < 4; r++) {
@@ -1295,7 +1311,7 @@ template <typename T> CW_FN void cw_rne(CassieWs<T> &w, const T *qvel CW_LANE_PA
   CW_FOR_LANES {
     const int d = lane;
     T pre[6] = {0, 0, 0, 0, 0, 0};
-    if (d >= 6) { const int p = CM_body_parent[CM_dof_body[d]]; for (int k = 0; k < 6; k++) pre[k] = w.u.p.cvel[p][k]; }
+    if (d >= 6) { const int p = CMS(body_parent)[CMS(dof_body)[d]]; for (int k = 0; k < 6; k++) pre[k] = w.u.p.cvel[p][k]; }
     else if (d >= 3) { pre[3] = qvel[0]; pre[4] = qvel[1]; pre[5] = qvel[2]; }
     const T *cd = w.cdof[d];
     T *o = w.u.p.cdd[d];
@@ -1309,7 +1325,7 @@ template <typename T> CW_FN void cw_rne(CassieWs<T> &w, const T *qvel CW_LANE_PA
   {
     T ja[6] = {0, 0, 0, 0, 0, 0};
     if (lane >= 1 && lane < CW_NB) {
-      const int da = CM_body_dofadr[lane], nd = CM_body_dofnum[lane];
+      const int da = CMS(body_dofadr)[lane], nd = CMS(body_dofnum)[lane];
       for (int s = 0; s < nd; s++) {
         const T qd = qvel[da + s];
         for (int k = 0; k < 6; k++) ja[k] += w.u.p.cdd[da + s][k] * qd;
@@ -1365,7 +1381,7 @@ template <typename T> CW_FN void cw_rne(CassieWs<T> &w, const T *qvel CW_LANE_PA
     T v[6];
     const bool body = lane >= 1 && lane < CW_NB;
     for (int k = 0; k < 6; k++) v[k] = body ? w.u.p.cfrc[lane][k] : (T)0;
-    cw_subtree_sum<T, 6>(v, lane, body ? CM_body_subtree[lane] : 0);
+    cw_subtree_sum<T, 6>(v, lane, body ? CMS(body_subtree)[lane] : 0);
     CW_SYNC();
     if (body) for (int k = 0; k < 6; k++) w.u.p.cfrc[lane][k] = v[k];
     CW_SYNC();
@@ -1387,7 +1403,7 @@ template <typename T> CW_FN void cw_rne(CassieWs<T> &w, const T *qvel CW_LANE_PA
     CW_SYNC();
   }
 #endif
-  CW_FOR_LANES { w.vec[V_BIAS][lane] = cw_dot6(w.cdof[lane], w.u.p.cfrc[CM_dof_body[lane]]); }
+  CW_FOR_LANES { w.vec[V_BIAS][lane] = cw_dot6(w.cdof[lane], w.u.p.cfrc[CMS(dof_body)[lane]]); }
   CW_SYNC();
 }
 
@@ -1401,7 +1417,7 @@ template <typename T> CW_FN void cw_foot_forces(const CassieWs<T> &w, T *lz, T *
   for (int c = 0; c < w.ncon; c++) {
     const int adr = w.con_adr[c];
     if (adr < 0) continue;
-    const int b2 = CM_geom_body[w.con_geom[c]], g1 = w.con_geom1[c], b1 = g1 >= 0 ? CM_geom_body[g1] : 0;
+    const int b2 = CMS(geom_body)[w.con_geom[c]], g1 = w.con_geom1[c], b1 = g1 >= 0 ? CMS(geom_body)[g1] : 0;
     T fl[3] = {0, 0, 0};
     const T *f = w.efc_f + adr;
     if (w.con_dim[c] == 1) fl[0] = f[0];
@@ -1445,17 +1461,17 @@ template <typename T> CW_NOINL void cw_mj_step(CassieWs<T> &w, bool integrate, i
   /* sensors (positions / velocities) for the next wrapper call */
   CW_FOR_LANES {
     if (lane < CM_NU) {
-      const int qa = CM_act_qposadr[lane];
-      w.st[S_SENS_ACTPOS + lane] = (T)CMT(act_gear)[lane] * qpos[qa];
-      w.st[S_SENS_ACTVEL + lane] = (T)CMT(act_gear)[lane] * qvel[CM_act_dof[lane]];
+      const int qa = CMS(act_qposadr)[lane];
+      w.st[S_SENS_ACTPOS + lane] = (T)CMTS(act_gear)[lane] * qpos[qa];
+      w.st[S_SENS_ACTVEL + lane] = (T)CMTS(act_gear)[lane] * qvel[CMS(act_dof)[lane]];
       /* encoder count, truncation toward 0 (@0x7fe0-0x8137): same operations, in float64, on hi + lo */
       const double q = (double)qpos[qa] + (double)w.st[S_QLO + qa];
-      w.sti[I_SENSCNT + lane] = (int32_t)(CM_act_gear[lane] * q / CW_TWO_PI_D * (double)(1 << CM_drive_bits[lane]));
+      w.sti[I_SENSCNT + lane] = (int32_t)(CMS(d_act_gear)[lane] * q / CW_TWO_PI_D * (double)(1 << CMS(drive_bits)[lane]));
     } else if (lane < CM_NU + 6) {
-      const int qa = CM_jsens_qposadr[lane - CM_NU];
+      const int qa = CMS(jsens_qposadr)[lane - CM_NU];
       w.st[S_SENS_JPOS + lane - CM_NU] = qpos[qa];
       const double q = (double)qpos[qa] + (double)w.st[S_QLO + qa];
-      w.sti[I_SENSCNT + lane] = (int32_t)(q / CW_TWO_PI_D * (double)(1 << CM_jsens_bits[lane - CM_NU]));
+      w.sti[I_SENSCNT + lane] = (int32_t)(q / CW_TWO_PI_D * (double)(1 << CMS(jsens_bits)[lane - CM_NU]));
     } else if (lane < CM_NU + 10) {
       w.st[S_SENS_QUAT + lane - CM_NU - 6] = w.qkeep[0][lane - CM_NU - 6];
     } else if (lane < CM_NU + 13) {
@@ -1469,18 +1485,18 @@ template <typename T> CW_NOINL void cw_mj_step(CassieWs<T> &w, bool integrate, i
   CW_FOR_LANES {
     const int i = lane;
     T f = -w.st[S_DAMPING + i] * qvel[i] - w.vec[V_BIAS][i];
-    const int j = CM_dof_jnt[i];
-    const T k = (T)CMT(jnt_stiffness)[j];
-    if (k != 0) f -= k * qpos[CM_jnt_qposadr[j]];
+    const int j = CMS(dof_jnt)[i];
+    const T k = (T)CMTS(jnt_stiffness)[j];
+    if (k != 0) f -= k * qpos[CMS(jnt_qposadr)[j]];
     w.vec[V_SMOOTH][i] = f;
   }
   CW_SYNC();
   CW_FOR_LANES {
     if (lane < CM_NU) {
       T c = w.st[S_CTRL + lane];
-      const T cm = (T)CMT(act_ctrlmax)[lane];
+      const T cm = (T)CMTS(act_ctrlmax)[lane];
       c = cw_min(cw_max(c, -cm), cm);
-      w.vec[V_SMOOTH][CM_act_dof[lane]] += (T)CMT(act_gear)[lane] * c;
+      w.vec[V_SMOOTH][CMS(act_dof)[lane]] += (T)CMTS(act_gear)[lane] * c;
     } else if (lane >= 26) {
       /* mj_xfrcAccumulate for the pelvis (the body sim.apply_force pushes): wrench (f, tau) at xipos moved to org = pelvis
        * origin and projected on the pelvis' six dofs: slides take f, the ball takes R^T (tau + (xipos - org) x f) */
@@ -1517,13 +1533,13 @@ template <typename T> CW_NOINL void cw_mj_step(CassieWs<T> &w, bool integrate, i
     /* L qacc_warmstart (so that J a = B (L a)) */
 #ifdef __CUDACC__
     { /* one ancestor per depth: its value comes by shuffle (depth < 6: the base dof of that number) */
-      const int na = CM_dof_nanc[lane];
-      const T *const row = w.Ms + CM_dof_rowptr[lane];
+      const int na = CMS(dof_nanc)[lane];
+      const T *const row = w.Ms + CMS(dof_rowptr)[lane];
       const T aw = w.st[S_QACC_WS + lane];
       T acc = 0;
 #pragma unroll
       for (int lvl = 0; lvl < CM_MAXANC; lvl++) {
-        const int j = lvl < 6 ? lvl : CM_dof_anc[lane][lvl];
+        const int j = lvl < 6 ? lvl : CMS(dof_anc)[lane][lvl];
         const T xj = __shfl_sync(0xffffffffu, aw, j & 31);
         const T c = row[lvl];
         acc += (na > lvl ? c : (T)0) * xj;
@@ -1781,7 +1797,7 @@ template <typename T> CW_NOINL void cw_mj_step(CassieWs<T> &w, bool integrate, i
 #ifdef __CUDACC__
   { /* (L^T g)_j = g_j + sum over the descendants i of j of U_i[rank_j] g_i / D_i: same phase structure as cw_solve_LT, no chain */
     const bool rt = lane >= 19, base = lane < 6;
-    const int ll = lane - (rt ? 13 : 0), rank = CM_dof_nanc[lane];
+    const int ll = lane - (rt ? 13 : 0), rank = CMS(dof_nanc)[lane];
     const T g = w.vec[V_G][lane], gs = g * w.Dinv[lane];
     T sacc = g;
     const T *const colL = w.Ms + (base ? lane : rank + (rt ? CM_LEG_ROWSPAN : 0)), *const colR = w.Ms + CM_LEG_ROWSPAN + lane;
@@ -1828,13 +1844,13 @@ template <typename T> CW_NOINL void cw_mj_step(CassieWs<T> &w, bool integrate, i
   }
   CW_SYNC();
   CW_FOR_LANES {
-    const int i = lane, j = CM_dof_jnt[i];
-    if (CM_jnt_type[j] != 2) {
-      const int qa = CM_dof_qposadr[i];
+    const int i = lane, j = CMS(dof_jnt)[i];
+    if (CMS(jnt_type)[j] != 2) {
+      const int qa = CMS(dof_qposadr)[i];
       /* q += h (v_hi + v_lo): the low part of the velocity is far below the position's last bit, but it is free here */
       cw_acc_add(qpos[qa], w.st[S_QLO + qa], h, qvel[i]);
-    } else if (i == CM_jnt_dofadr[j]) {
-      const int qa = CM_jnt_qposadr[j];
+    } else if (i == CMS(jnt_dofadr)[j]) {
+      const int qa = CMS(jnt_qposadr)[j];
       T wv[3] = {qvel[i], qvel[i + 1], qvel[i + 2]};
       const T nrm = cw_sqrt<T>(cw_dot3(wv, wv)), ang = nrm * h;
       if (ang > (T)1e-15) {
