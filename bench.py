@@ -440,6 +440,37 @@ def main():
     env_steps = args.envs * args.horizon * world
 
     tc_mode = algo.tc_mode
+    # second roofline object: the learner's dominant GEMM (forward hidden layer of the update's actor minibatch, 65,536 x 256 x 256,
+    # csrc/tc_gemm3.cu) timed alone with CUDA events on the launching stream
+    learner_gemm = None
+    if rank == 0 and tc_mode:
+        try:
+            from apex_b200 import _capi
+            L_ = _capi.lib()
+            M_, K_, N_ = 2 * MINIBATCH, 256, 256
+            a_ = torch.randn(M_, K_, device=dev); w_ = torch.randn(N_, K_, device=dev) / 16; b_ = torch.zeros(N_, device=dev)
+            c_ = torch.empty(M_, N_, device=dev)
+            st_ = torch.cuda.current_stream(dev).cuda_stream
+            call = lambda: L_.apex_tc3_linear(a_.data_ptr(), K_, M_, K_, w_.data_ptr(), K_, 1, b_.data_ptr(), 1, None, 0, c_.data_ptr(), N_, tc_mode, st_)
+            for _ in range(3):
+                call()
+            torch.cuda.synchronize(dev)
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            for _ in range(20):
+                call()
+            g1.record()
+            torch.cuda.synchronize(dev)
+            us = g0.elapsed_time(g1) / 20 * 1e3
+            alg = 2.0 * M_ * K_ * N_
+            learner_gemm = {"kernel": f"k_tc3_nt<{tc_mode}> (+ weight-image kernel)", "shape": [M_, N_, K_], "us_per_launch": us,
+                            "algorithmic_tflops": alg / us / 1e6, "executed_tf32_tflops": tc_mode * alg / us / 1e6,
+                            "algorithmic_bytes": 2 * M_ * K_ * 4 + N_ * K_ * 4, "achieved_GBps": (2 * M_ * K_ * 4 + N_ * K_ * 4) / us / 1e3,
+                            "note": "split-tf32: 3 tcgen05 products per k step for float32 accuracy, so executed = 3 x algorithmic flops; "
+                                    "ncu of the same kernel: profiles/ncu_tc3_r02.json (tensor pipe 48 % of active cycles)"}
+            del a_, w_, b_, c_
+        except Exception as e:
+            learner_gemm = {"error": f"{type(e).__name__}: {e}"[:200]}
     extras = {}
     if not args.no_extras:
         del algo
@@ -508,6 +539,13 @@ def main():
                         "peak_source": peak_src, "kernel_share_of_step": sum(kms) / ms_instr, "compute": compute,
                         "note": "kernel_ms and the share come from a separate instrumented step (CUDA events around each launch); "
                                 "the dynamics kernel is FP32-issue/latency bound (SURVEY.md §8d): HBM fraction is expected << 1%"}}
+    if learner_gemm and "us_per_launch" in learner_gemm:
+        tf32_peak = peaks["bf16_tflops"] / 2 if "bf16_tflops" in peaks else 1125.0
+        learner_gemm.update({"bound": "tensor", "achieved": learner_gemm["executed_tf32_tflops"], "peak": tf32_peak, "unit": "TFLOP/s",
+                             "frac": learner_gemm["executed_tf32_tflops"] / tf32_peak,
+                             "peak_source": "MEASURED_PEAKS.json bf16_tflops / 2 (tf32 runs at half the bf16 rate)" if "bf16_tflops" in peaks
+                             else "nominal dense tf32", "hbm_frac": learner_gemm["achieved_GBps"] / peak})
+    out["roofline_learner_gemm"] = learner_gemm
     out.update(extras)
     if not args.no_cpu_baseline and world == 1:
         v, cores, sample, _ = cpu_arm(1, 1)
