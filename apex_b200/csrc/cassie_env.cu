@@ -74,16 +74,17 @@ __global__ void __launch_bounds__(sizeof(T) == 4 ? CW_STEP_THREADS_F32 : 224) k_
     if (threadIdx.x == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_addr), "r"(wpb) : "memory");
     __syncthreads();
   }
+  const int simrate_all = cw_simrate(sti[I_VARIANT]); /* one value for the batch (env 0's word): idle slots count the same barriers */
   if (e >= n || (active && !active[e])) { /* idle slot: keep the CTA barriers company, touch nothing */
     if (e < n && lane == 0) { reward[e] = 0; done[e] = 4; }
     if (bar_mask & CW_SPLIT) {
-      for (int s = 0; s < CW_SIMRATE; s++) {
+      for (int s = 0; s < simrate_all; s++) {
         if (s > 0) cw_mbar_wait(bar_addr, (unsigned)((s - 1) & 1));
         __syncwarp();
         cw_mbar_arrive(bar_addr, lane);
       }
     } else {
-      const int nbar = CW_SIMRATE * (1 + __popc(bar_mask & CW_BAR_ALL));
+      const int nbar = simrate_all * (1 + __popc(bar_mask & CW_BAR_ALL));
       for (int s = 0; s < nbar; s++) __syncthreads();
     }
     return;
@@ -282,7 +283,7 @@ int apex_cassie_env_step_masked(int dtype, void *st, int *sti, int n, const void
 
 /* CassieTraj-v0 (cassie/cassie_traj.py): same state record, variant flag 1, resets start from the reference trajectory */
 static int traj_ok(const void *traj, int traj_rows, int traj_len) {
-  return traj && traj_rows >= 1 && traj_len >= CW_SIMRATE && traj_rows >= traj_len / CW_SIMRATE + 1;
+  return traj && traj_rows >= 1 && traj_len >= 1; /* rows = len / simrate + 1 is the caller's contract (the simrate lives in the env state) */
 }
 int apex_cassietraj_env_init(int dtype, void *st, int *sti, int n, unsigned seed, int env_id0, int dyn_rand, void *stream) {
   return env_init_impl(dtype, st, sti, n, seed, env_id0, dyn_rand, 1, stream);

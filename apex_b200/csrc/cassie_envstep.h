@@ -96,8 +96,8 @@ template <typename T> CW_NOINL void cw_sim_step_pd(CassieWs<T> &w, int bar CW_LA
 }
 
 /* ---------- clock functions ---------- */
-template <typename T> CW_FN void cw_clock_knots(T swing, T stance, T *x, T *phaselen) {
-  const T F = 40, rel = (T)0.1;
+template <typename T> CW_FN void cw_clock_knots(T swing, T stance, T *x, T *phaselen, T F = (T)40) {
+  const T rel = (T)0.1;
   T seg[5] = {0, swing, swing + stance, 2 * swing + stance, 2 * swing + 2 * stance};
   for (int k = 0; k < 4; k++) {
     const T a = seg[k] * F, b = seg[k + 1] * F, off = (b - a) * rel;
@@ -114,6 +114,10 @@ CW_FN int cw_env_variant(int v) { return v & 0xFF; }
 CW_FN int cw_cmd_profile(int v) { return (v >> 8) & 0xFF; }
 CW_FN int cw_obs_dim(int v) { return cw_cmd_profile(v) ? CW_OBS_PHASE : CW_OBS; }
 CW_FN int cw_reward_kind(int v) { return (v >> 16) & 0xFF; } /* 0 clock_reward, 1 early_clock_reward, 2 no_speed_clock_reward */
+/* physics sub-steps per env step (CassieEnv(simrate=...), cassie.py:28,75): bits 24-31 of the variant word, 0 = the default 50;
+ * the clock frequency is FREQ = 2000 // simrate (cassie.py:545, 559) */
+CW_FN int cw_simrate(int v) { const int s = (v >> 24) & 0xFF; return s ? s : CW_SIMRATE; }
+CW_FN int cw_freq(int v) { return 2000 / cw_simrate(v); }
 template <typename T> CW_FN T cw_clock_eval(const T *x, T P, int which, T phase, int mode) {
   T xa, xb, ya, yb;
   if (phase < x[0]) { xa = x[7] - P; ya = cw_clock_y<T>(which, 7, mode); xb = x[0]; yb = cw_clock_y<T>(which, 0, mode); }
@@ -284,17 +288,17 @@ template <typename T> CW_FN T cw_uniform(uint32_t u, double lo, double hi) { ret
 /* swing / stance durations and the clock period from the commanded speed (cassie.py:556-559, phase_function.py:7-8), in float64
  * with the reference's operation order whatever T is: for CassieTraj-v0's discrete speeds the period lands on (or one ulp
  * below) an integer, and floor(phaselen) is used as an integer twice (phase draw :561, phase wrap :450) */
-CW_FN void cw_clock_from_speed(double speed, double *swing, double *stance, double *phaselen) {
+CW_FN void cw_clock_from_speed(double speed, double *swing, double *stance, double *phaselen, double freq = 40.0) {
   const double as = speed < 0 ? -speed : speed;
   const double total = cw_dadd(0.9, -cw_dmul(0.25 / 3.0, as)) / 2;
   const double k = (0.70 - 0.30) / 3;
   *swing = cw_dmul(cw_dadd(0.30, cw_dmul(k, as)), total);
   *stance = cw_dmul(cw_dadd(0.70, -cw_dmul(k, as)), total);
-  *phaselen = cw_dmul(cw_dadd(cw_dmul(2, *swing), cw_dmul(2, *stance)), 40.0); /* FREQ = 2000 // simrate */
+  *phaselen = cw_dmul(cw_dadd(cw_dmul(2, *swing), cw_dmul(2, *stance)), freq); /* FREQ = 2000 // simrate */
 }
 template <typename T> CW_FN void cw_set_clock(CassieWs<T> &w, T speed CW_LANE_PARAM) {
   double swing, stance, P;
-  cw_clock_from_speed((double)speed, &swing, &stance, &P);
+  cw_clock_from_speed((double)speed, &swing, &stance, &P, (double)cw_freq(w.sti[I_VARIANT]));
   CW_FOR_LANES {
     if (lane == 0) {
       w.st[S_SWING] = (T)swing; w.st[S_STANCE] = (T)stance; w.st[S_PHASELEN] = (T)P;
@@ -327,7 +331,7 @@ template <typename T> CW_NOINL void cw_env_reset(CassieWs<T> &w, T *obs_out, con
       stance = (double)(1u + (uint32_t)(((uint64_t)u1 * 30u) >> 32)) / 100;
     }
     const uint32_t c = (uint32_t)(((uint64_t)u2 * 3u) >> 32);
-    const double P = cw_dmul(cw_dadd(cw_dmul(2, swing), cw_dmul(2, stance)), 40.0); /* create_phase_reward: total_duration * FREQ */
+    const double P = cw_dmul(cw_dadd(cw_dmul(2, swing), cw_dmul(2, stance)), (double)cw_freq(w.sti[I_VARIANT])); /* create_phase_reward: total_duration * FREQ */
     CW_FOR_LANES {
       if (lane == 0) {
         w.st[S_SWING] = (T)swing; w.st[S_STANCE] = (T)stance; w.st[S_PHASELEN] = (T)P;
@@ -384,7 +388,8 @@ template <typename T> CW_NOINL void cw_env_reset(CassieWs<T> &w, T *obs_out, con
     /* set_qpos / set_qvel from get_ref_state(phase) (cassie_traj.py:681-689, 926-972): written straight into the state with
      * no mj_forward, so the sub-step below still reads the encoders of the fixed start pose */
     int ph = (int)phase;
-    if (ph > traj.len / CW_SIMRATE - 1) ph = (int)floor((double)((phase / plen) * (T)traj.len / (T)CW_SIMRATE));
+    const int sr = cw_simrate(w.sti[I_VARIANT]);
+    if (ph > traj.len / sr - 1) ph = (int)floor((double)((phase / plen) * (T)traj.len / (T)sr));
     if (ph > traj.rows - 1) ph = traj.rows - 1;
     const T *row = traj.table + (size_t)ph * CW_TRAJ_W;
     CW_FOR_LANES {
@@ -436,7 +441,9 @@ template <typename T> CW_NOINL void cw_env_reset_for_test(CassieWs<T> &w, T *obs
     }
     if (lane == 31) {
       w.st[S_PHASE] = 0; w.st[S_SPEED] = 0; w.st[S_ORIENT] = 0; w.st[S_PHASEADD] = 1;
-      w.st[S_SWING] = (T)0.15; w.st[S_STANCE] = (T)0.25; w.st[S_PHASELEN] = 32; w.sti[I_PHASEFLOOR] = 32; /* (0.3 + 0.5) * 40 */
+      /* create_phase_reward(0.15, 0.25, ...): phaselength = (2 * 0.15 + 2 * 0.25) * FREQ = 32 at simrate 50 */
+      const double plen0 = cw_dmul(cw_dadd(cw_dmul(2, 0.15), cw_dmul(2, 0.25)), (double)cw_freq(w.sti[I_VARIANT]));
+      w.st[S_SWING] = (T)0.15; w.st[S_STANCE] = (T)0.25; w.st[S_PHASELEN] = (T)plen0; w.sti[I_PHASEFLOOR] = (int)floor(plen0);
       w.sti[I_TIME] = 0; w.sti[I_COUNTER] = 0; w.sti[I_STANCEMODE] = 1;
       if (full) { w.sti[I_DRIVEINIT] = 0; w.sti[I_JOINTINIT] = 0; w.sti[I_SIMSTEPS] = 0; }
     }
@@ -493,7 +500,8 @@ template <typename T> CW_NOINL void cw_env_step(CassieWs<T> &w, T *obs_out, T *r
   int cost = 0;
   const int bar0 = w.bar_mask & CW_BAR_MASK;
   CW_MARK_START();
-  for (int s = 0; s < CW_SIMRATE; s++) {
+  const int simrate = cw_simrate(w.sti[I_VARIANT]);
+  for (int s = 0; s < simrate; s++) {
     /* sub-step s waits (somewhere, CW_SPLIT_POINT) for everybody's arrival of sub-step s - 1 = barrier phase s - 1 */
     const int flags = bar0 | (s > 0 ? CW_SPLIT_WAIT : 0) | (((s - 1) & 1) ? CW_SPLIT_PARITY : 0);
     const int bar = flags;
@@ -531,7 +539,7 @@ template <typename T> CW_NOINL void cw_env_step(CassieWs<T> &w, T *obs_out, T *r
     }
     CW_SYNC();
   }
-  lfrc /= (T)CW_SIMRATE; rfrc /= (T)CW_SIMRATE; lori /= (T)CW_SIMRATE; rori /= (T)CW_SIMRATE;
+  lfrc /= (T)simrate; rfrc /= (T)simrate; lori /= (T)simrate; rori /= (T)simrate;
   const T *qpos = w.st + S_QPOS, *qvel = w.st + S_QVEL;
   const T height = qpos[2];
   const int time = w.sti[I_TIME] + 1;
@@ -568,7 +576,7 @@ template <typename T> CW_NOINL void cw_env_step(CassieWs<T> &w, T *obs_out, T *r
     if (kind == 1) pelvis_acc = 0;
     const T pelvis_motion = straight_diff + height_diff + pelvis_acc;
     T x[8], P;
-    cw_clock_knots<T>(w.st[S_SWING], w.st[S_STANCE], x, &P);
+    cw_clock_knots<T>(w.st[S_SWING], w.st[S_STANCE], x, &P, (T)cw_freq(w.sti[I_VARIANT]));
     const int sm = w.sti[I_STANCEMODE];
     const T lfc = cw_clock_eval<T>(x, P, 0, phase, sm), lvc = cw_clock_eval<T>(x, P, 1, phase, sm);
     const T rfc = cw_clock_eval<T>(x, P, 2, phase, sm), rvc = cw_clock_eval<T>(x, P, 3, phase, sm);
@@ -621,7 +629,7 @@ template <typename T> CW_NOINL void cw_env_step(CassieWs<T> &w, T *obs_out, T *r
       w.sti[I_TIME] = time; w.sti[I_COUNTER] = counter; w.sti[I_HASPREV] = 1; w.sti[I_RNGCTR] = (int)(ctr + 2);
       w.st[S_PHASE] = phase; w.st[S_ORIENT] = orient; w.st[S_SPEED] = speed; w.st[S_SIDE] = side;
       w.sti[I_SOLVER_ITER] = w.solver_iter; w.sti[I_NCON] = w.ncon; w.sti[I_NEFC] = w.nefc; w.sti[I_COST] = cost;
-      w.sti[I_SIMSTEPS] += CW_SIMRATE;
+      w.sti[I_SIMSTEPS] += simrate;
     }
   }
   CW_SYNC();

@@ -156,7 +156,7 @@ enum {
 enum {
   I_DRIVEHIST = 0, I_TIME = 90, I_COUNTER = 91, I_HASPREV = 92, I_HASU = 93, I_DRIVEINIT = 94, I_JOINTINIT = 95,
   I_FLAGS = 96, I_STEPCOUNT = 97, I_RNGCTR = 98, I_ENVID = 99, I_SEED = 100, I_DYNRAND = 101, I_SOLVER_ITER = 102,
-  I_NCON = 103, I_NEFC = 104, I_VARIANT = 105 /* bits 0-7: 0 Cassie-v0, 1 CassieTraj-v0; bits 8-15: command profile 0 clock, 1 phase, 2 phase (library); bits 16-23: reward 0 clock, 1 early, 2 no_speed */, I_PHASEFLOOR = 106 /* floor(phaselen), from float64 */,
+  I_NCON = 103, I_NEFC = 104, I_VARIANT = 105 /* bits 0-7: 0 Cassie-v0, 1 CassieTraj-v0; bits 8-15: command profile 0 clock, 1 phase, 2 phase (library); bits 16-23: reward 0 clock, 1 early, 2 no_speed; bits 24-31: simrate (0 = 50) */, I_PHASEFLOOR = 106 /* floor(phaselen), from float64 */,
   I_COST = 107 /* sum over the last env step's sub-steps of solver_iter * nefc: load-balancing key */,
   I_STANCEMODE = 108 /* clock reward's stance_mode: 0 "zero", 1 "grounded" (also once reset_for_test has run, cassie.py:219,701), 2 "aerial" */,
   I_SIMSTEPS = 109 /* physics sub-steps since the simulator was last reset: sim.time() = that many additions of 0.0005 */,

@@ -35,8 +35,8 @@ class BatchedCassieEnv:
     def __init__(self, num_envs, device="cuda:0", dtype=torch.float32, seed=0, dynamics_randomization=True, simrate=50,
                  command_profile="clock", input_profile="full", reward="clock", max_traj_len=400, env_id0=0, history=0, balance=True,
                  **kwargs):
-        if simrate != 50 or command_profile not in ("clock", "phase") or input_profile != "full" or history != 0:
-            raise NotImplementedError("kernel is specialised for simrate=50, clock / phase command, full input, history=0")
+        if not 1 <= int(simrate) <= 127 or command_profile not in ("clock", "phase") or input_profile != "full" or history != 0:
+            raise NotImplementedError("kernel covers simrate 1..127, clock / phase command, full input, history=0")
         # The reward NAME configures the clock reward the way cassie.py:176-232 parses it:
         #   command_profile "phase": "library" in the name -> library phase inputs, "no_speed" -> no_speed_clock_reward, "early" ->
         #     early_clock_reward; the stance mode is drawn on every reset;
@@ -44,9 +44,8 @@ class BatchedCassieEnv:
         #     ("switch" names behave like "clock" in the reference: set_up_clock_reward renames them, so reset's `== "switch_clock"`
         #     branch, cassie.py:549-554, never runs).
         # "max_vel" (max_vel_clock_reward) and "load" (pickled clocks) are not on the kernel path.
+        # Any other name — e.g. "5k_speed_reward" in the experiment.info of the reference's shipped policies — is the plain clock reward.
         reward = reward or "clock"
-        if "clock" not in reward and reward not in ("library", "no_speed", "early"):
-            raise NotImplementedError("only the clock reward family (cassie/rewards/clock_rewards.py) is implemented")
         if "max_vel" in reward or "load" in reward or "no_incentive" in reward:
             raise NotImplementedError("max_vel_clock_reward / loaded clocks / no_incentive clocks are not on the kernel path")
         self._reward_kind = 1 if "early" in reward else 0
@@ -90,8 +89,8 @@ class BatchedCassieEnv:
         self.balance = bool(balance)
         self.order = torch.arange(n, dtype=torch.int32, device=self.device)
         self._init_state(int(seed) & 0xFFFFFFFF, int(env_id0))
-        # variant word: bits 8-15 command profile (observation width, reset draws), 16-23 reward kind
-        extra = (self._cmd_profile << 8) | (self._reward_kind << 16)
+        # variant word: bits 8-15 command profile (observation width, reset draws), 16-23 reward kind, 24-31 simrate (0 = 50)
+        extra = (self._cmd_profile << 8) | (self._reward_kind << 16) | ((int(self.simrate) if int(self.simrate) != 50 else 0) << 24)
         if extra:
             self.field("variant")[:, 0] |= extra
         if self._stance0:
@@ -143,7 +142,7 @@ class BatchedCassieEnv:
         old = self._plen64 if getattr(self, "_plen64", None) is not None else f("phaselen")[:, 0].double()
         clock = clock_from_speed(torch.as_tensor(new_speed, dtype=torch.float64, device=self.device).expand(self.num_envs),
                                  torch.as_tensor(new_side_speed, dtype=torch.float64, device=self.device).expand(self.num_envs),
-                                 f("phase")[:, 0].double(), old)
+                                 f("phase")[:, 0].double(), old, freq=2000 // int(self.simrate))
         on = torch.ones(self.num_envs, dtype=torch.bool, device=self.device) if active is None else active.bool()
         for name, v in zip(("speed", "side_speed", "swing", "stance", "phaselen", "phase"), clock[:6]):
             f(name)[:, 0] = torch.where(on, v.to(self.dtype), f(name)[:, 0])
@@ -210,7 +209,7 @@ class BatchedCassieEnv:
                 self.field(name)[:, 0] = torch.as_tensor(val, dtype=self.dtype, device=self.device)
 
 
-def clock_from_speed(new_speed, new_side_speed, phase, old_phaselen):
+def clock_from_speed(new_speed, new_side_speed, phase, old_phaselen, freq=40):
     """The arithmetic of CassieEnv.update_speed (cassie/cassie.py:751-768) on float64 tensors, one rounding per operation in the
     reference's order (separate torch ops, so nothing is contracted into an FMA): returns (speed, side_speed, swing, stance,
     phaselen, phase, floor(phaselen) as int32).  phase = int(phaselen * phase / old_phaselen) truncates like Python's int()."""
@@ -220,7 +219,7 @@ def clock_from_speed(new_speed, new_side_speed, phase, old_phaselen):
     k = (0.70 - 0.30) / 3
     swing = (0.30 + k * speed) * total
     stance = (0.70 - k * speed) * total
-    phaselen = (2 * swing + 2 * stance) * 40.0  # create_phase_reward: total_duration * FREQ, FREQ = 2000 // simrate
+    phaselen = (2 * swing + 2 * stance) * float(freq)  # create_phase_reward: total_duration * FREQ, FREQ = 2000 // simrate
     new_phase = torch.trunc(phaselen * phase / old_phaselen)
     return speed, side, swing, stance, phaselen, new_phase, torch.floor(phaselen).to(torch.int32)
 

@@ -159,10 +159,10 @@ def report_stats(data):
             "avg_pos_orient_failure": m(of[of > 0]), "avg_neg_orient_failure": m(of[of < 0])}
 
 
-def _steps_until(table, k0, duration):
+def _steps_until(table, k0, duration, simrate=SIMRATE):
     """How many policy steps `while curr_time < start_t + duration` runs when it starts after k0 sub-steps."""
     m, limit = 0, table[k0] + duration
-    while table[k0 + m * SIMRATE] < limit:
+    while table[k0 + m * simrate] < limit:
         m += 1
     return m
 
@@ -177,9 +177,10 @@ def perturb_trials(env, policy, angles, phases, sizes, num_phases=33, wait_time=
     angles, phases, sizes = (np.asarray(a) for a in (angles, phases, sizes))
     assert angles.shape == phases.shape == sizes.shape == (N,)
     pre = 2 * int(num_phases) + phases.astype(np.int64)
-    table = sim_time_table(int(pre.max() + 2) * SIMRATE + int((perturb_duration + wait_time) / 0.0005) + 4 * SIMRATE)
-    push = np.array([_steps_until(table, int(p) * SIMRATE, perturb_duration) for p in pre])
-    wait = np.array([_steps_until(table, int(p + q) * SIMRATE, wait_time) for p, q in zip(pre, push)])
+    sr = int(getattr(env, "simrate", SIMRATE))  # sub-steps per policy step of this env
+    table = sim_time_table(int(pre.max() + 2) * sr + int((perturb_duration + wait_time) / 0.0005) + 4 * sr)
+    push = np.array([_steps_until(table, int(p) * sr, perturb_duration, sr) for p in pre])
+    wait = np.array([_steps_until(table, int(p + q) * sr, wait_time, sr) for p, q in zip(pre, push)])
     t_pre, t_push, t_end = (torch.as_tensor(a, device=dev) for a in (pre, pre + push, pre + push + wait))
     force = torch.zeros((N, 6), dtype=torch.float64, device=dev)
     force[:, 0] = torch.as_tensor(sizes * np.cos(angles), device=dev)

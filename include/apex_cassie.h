@@ -42,6 +42,11 @@ extern "C" {
  * APEX_CASSIE_OBS_PHASE wide — [46 robot state | sin, cos clock | swing, stance duration | one-hot stance mode (grounded, aerial,
  * zero) | speed, side speed] — in every obs / term_obs argument below, and the clock reward uses the drawn durations and mode. */
 #define APEX_CASSIE_OBS_PHASE 55
+/* The other fields of the "variant" word, set the same way for every env of a batch after apex_cassie_env_init:
+ *   bits 16-23  reward: 0 clock_reward, 1 early_clock_reward, 2 no_speed_clock_reward (cassie/rewards/clock_rewards.py:6, 119, 225; the
+ *               stance mode of the clock profile's reward — "grounded" 1 / "aerial" 2 in its name — is the int field "stance_mode");
+ *   bits 24-31  simrate, physics sub-steps per env step (cassie.py:28, 75); 0 = the default 50, at most 127.  The clock runs at
+ *               2000 // simrate steps per second (cassie.py:545, 559). */
 
 /* size of the per-env persistent record: st is [n][state_words] reals, sti is [n][istate_words] int32 */
 int apex_cassie_state_words(void);

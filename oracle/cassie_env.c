@@ -121,8 +121,12 @@ void ce_sim_step_pd(ce_env_t *e, const ce_pd_in_t *u, ce_state_out_t *y) {
 /* NOFMA: the period must round exactly like the reference's Python floats (floor(phaselen) decides the phase draw and the
  * phase wrap, and CassieTraj-v0's discrete speeds put it on or one ulp below an integer), so gcc may not contract a*b+c here */
 #define NOFMA __attribute__((optimize("fp-contract=off")))
-NOFMA void ce_clock_knots(double swing, double stance, double x[8], double *phaselen) {
-  const double F = 40.0, rel = 0.1; /* FREQ = 2000 // simrate, strict_relaxer (cassie.py:90,559) */
+static double env_freq(const ce_env_t *e) { return (double)(2000 / (e->simrate ? e->simrate : 50)); } /* FREQ = 2000 // simrate (cassie.py:545, 559) */
+static int env_simrate(const ce_env_t *e) { return e->simrate ? e->simrate : 50; }
+NOFMA void ce_clock_knots_f(double swing, double stance, double F, double x[8], double *phaselen);
+NOFMA void ce_clock_knots(double swing, double stance, double x[8], double *phaselen) { ce_clock_knots_f(swing, stance, 40.0, x, phaselen); }
+NOFMA void ce_clock_knots_f(double swing, double stance, double F, double x[8], double *phaselen) {
+  const double rel = 0.1; /* strict_relaxer (cassie.py:90) */
   double seg[5] = {0, swing, swing + stance, 2 * swing + stance, 2 * swing + 2 * stance};
   for (int k = 0; k < 4; k++) {
     double a = seg[k] * F, b = seg[k + 1] * F, off = (b - a) * rel;
@@ -135,9 +139,13 @@ static const double CLOCK_Y[4][8] = { /* reward "clock": have_incentive, stance_
 double ce_clock_eval(double swing, double stance, int which, double phase) { return ce_clock_eval_mode(swing, stance, 0, which, phase); }
 /* stance_mode 0 "zero" (what reward "clock" trains with, cassie.py:219), 1 "grounded" (what reset_for_test installs, cassie.py:701):
  * the double-stance knots 2, 3, 6, 7 carry +1 on the force clocks and -1 on the velocity clocks (phase_function.py:53-56, 96-98) */
+double ce_clock_eval_mode_f(double swing, double stance, double F, int stance_mode, int which, double phase);
 double ce_clock_eval_mode(double swing, double stance, int stance_mode, int which, double phase) {
+  return ce_clock_eval_mode_f(swing, stance, 40.0, stance_mode, which, phase);
+}
+double ce_clock_eval_mode_f(double swing, double stance, double F, int stance_mode, int which, double phase) {
   double x[8], P;
-  ce_clock_knots(swing, stance, x, &P);
+  ce_clock_knots_f(swing, stance, F, x, &P);
   double yv[8];
   /* double-stance knots 2, 3, 6, 7 (phase_function.py:38-56, 85-103): "grounded" +1 on the force clocks, -1 on the velocity clocks;
    * "aerial" the opposite; "zero" 0 */
@@ -172,8 +180,11 @@ void ce_env_set_reward(ce_env_t *e, int reward_kind, int stance_mode) { e->rewar
 void ce_clock_from_speed(double speed, double *swing, double *stance, double *phaselen);
 void ce_clock_from_speed_signed(double speed, double *swing, double *stance, double *phaselen);
 static void set_clock(ce_env_t *e, double speed) { /* cassie.py:556-559 */
-  ce_clock_from_speed(speed, &e->swing_duration, &e->stance_duration, &e->phaselen);
+  double x[8], p40;
+  ce_clock_from_speed(speed, &e->swing_duration, &e->stance_duration, &p40);
+  ce_clock_knots_f(e->swing_duration, e->stance_duration, env_freq(e), x, &e->phaselen);
 }
+void ce_env_set_simrate(ce_env_t *e, int simrate) { e->simrate = simrate; }
 /* update_speed's variant (cassie.py:763-765): the same expressions on the signed speed — reset() takes abs(), update_speed does not */
 NOFMA void ce_clock_from_speed_signed(double speed, double *swing, double *stance, double *phaselen) {
   double total = (0.9 - 0.25 / 3.0 * speed) / 2;
@@ -281,10 +292,10 @@ double ce_env_reward(ce_env_t *e, const double *action) { /* clock_reward / earl
   if (kind == 1) pelvis_acc = 0; /* early_clock_reward drops the acceleration term (:162-163) */
   double pelvis_motion = straight_diff + height_diff + pelvis_acc;
   /* the env stores create_phase_reward's (right, left) pair as (left_clock, right_clock) — cassie.py:559 */
-  double left_frc_clock = ce_clock_eval_mode(e->swing_duration, e->stance_duration, e->stance_mode, 0, e->phase);
-  double left_vel_clock = ce_clock_eval_mode(e->swing_duration, e->stance_duration, e->stance_mode, 1, e->phase);
-  double right_frc_clock = ce_clock_eval_mode(e->swing_duration, e->stance_duration, e->stance_mode, 2, e->phase);
-  double right_vel_clock = ce_clock_eval_mode(e->swing_duration, e->stance_duration, e->stance_mode, 3, e->phase);
+  double left_frc_clock = ce_clock_eval_mode_f(e->swing_duration, e->stance_duration, env_freq(e), e->stance_mode, 0, e->phase);
+  double left_vel_clock = ce_clock_eval_mode_f(e->swing_duration, e->stance_duration, env_freq(e), e->stance_mode, 1, e->phase);
+  double right_frc_clock = ce_clock_eval_mode_f(e->swing_duration, e->stance_duration, env_freq(e), e->stance_mode, 2, e->phase);
+  double right_vel_clock = ce_clock_eval_mode_f(e->swing_duration, e->stance_duration, env_freq(e), e->stance_mode, 3, e->phase);
   double foot_frc_score = tan(PI / 4 * left_frc_clock * nlf) + tan(PI / 4 * right_frc_clock * nrf);
   double foot_vel_score = tan(PI / 4 * left_vel_clock * nlv) + tan(PI / 4 * right_vel_clock * nrv);
   if (kind == 1) { /* tanh scores (:175-178) */
@@ -311,7 +322,7 @@ double ce_env_reward(ce_env_t *e, const double *action) { /* clock_reward / earl
 }
 
 void ce_env_step_with(ce_env_t *e, const double *action, const ce_step_draws_t *dr, double *obs, double *reward, int *done) { /* cassie.py:389-496 */
-  const int simrate = 50;
+  const int simrate = env_simrate(e);
   e->l_foot_frc = e->r_foot_frc = 0;
   memset(e->l_foot_pos, 0, sizeof(e->l_foot_pos));
   memset(e->r_foot_pos, 0, sizeof(e->r_foot_pos));
@@ -441,7 +452,7 @@ void ce_env_reset_with(ce_env_t *e, const ce_reset_draws_t *dr, double *obs) { /
       e->stance_mode = c == 0 ? 1 : (c == 1 ? 2 : 0);
     }
     double x[8];
-    ce_clock_knots(e->swing_duration, e->stance_duration, x, &e->phaselen); /* create_phase_reward: phaselength = total * FREQ */
+    ce_clock_knots_f(e->swing_duration, e->stance_duration, env_freq(e), x, &e->phaselen); /* create_phase_reward: phaselength = total * FREQ */
   } else set_clock(e, e->speed);
   e->phase = dr->phase >= 0 ? (double)dr->phase /* random.randint(0, floor(phaselen)), cassie.py:561 */
                             : (double)(uint32_t)(((uint64_t)dr->phase_u32 * ((uint32_t)floor(e->phaselen) + 1)) >> 32);
@@ -464,7 +475,7 @@ void ce_env_reset_with(ce_env_t *e, const ce_reset_draws_t *dr, double *obs) { /
   if (e->variant == 1 && e->traj) {
     /* qpos, qvel = get_ref_state(phase); sim.set_qpos / set_qvel (cassie_traj.py:681-689, 926-972): plain stores into
      * mjData, no mj_forward — the sub-step below still reads the sensor values of the fixed start pose */
-    const int simrate = 50;
+    const int simrate = env_simrate(e);
     double phase = e->phase; /* self.speed is still the randint / 10 draw, self.counter is 0 */
     if (phase > e->traj_len / simrate - 1) phase = floor((phase / e->phaselen) * e->traj_len / simrate);
     int k = (int)phase;
@@ -501,7 +512,7 @@ void ce_env_reset_for_test_mode(ce_env_t *e, int full_reset, double *obs) {
   e->phase = 0; e->time = 0; e->counter = 0; e->orient_add = 0; e->phase_add = 1; e->speed = 0;
   e->swing_duration = 0.15; e->stance_duration = 0.25; e->stance_mode = 1; /* sticks: reset() never sets it back (cassie.py:548-559) */
   double x[8];
-  ce_clock_knots(e->swing_duration, e->stance_duration, x, &e->phaselen);
+  ce_clock_knots_f(e->swing_duration, e->stance_duration, env_freq(e), x, &e->phaselen);
   if (!full_reset) {
     memcpy(e->last_pelvis_pos, e->d.qpos, sizeof(e->last_pelvis_pos));
     e->l_foot_frc = e->r_foot_frc = 0;
@@ -540,7 +551,9 @@ void ce_env_update_speed(ce_env_t *e, double new_speed, double new_side_speed) {
   e->speed = fmin(fmax(new_speed, -0.3), 4.0);
   e->side_speed = fmin(fmax(new_side_speed, -0.3), 0.3);
   double old = e->phaselen;
-  ce_clock_from_speed_signed(e->speed, &e->swing_duration, &e->stance_duration, &e->phaselen);
+  double x[8], p40;
+  ce_clock_from_speed_signed(e->speed, &e->swing_duration, &e->stance_duration, &p40);
+  ce_clock_knots_f(e->swing_duration, e->stance_duration, env_freq(e), x, &e->phaselen);
   e->phase = (double)(long)(e->phaselen * e->phase / old);
 }
 /* CassieEnv.step_basic (cassie.py:499-521): the sub-steps of step() without the bookkeeping for the reward, no reward, no
@@ -552,7 +565,7 @@ void ce_env_step_basic(ce_env_t *e, const double *action, double *obs) {
     e->u.pgain[i] = PGAIN[k]; e->u.dgain[i] = DGAIN[k];
     e->u.ptarget[i] = action[i] + OFFSET[i] - e->menc_noise[i];
   }
-  for (int s = 0; s < 50; s++) ce_sim_step_pd(e, &e->u, &e->y);
+  for (int s = 0; s < env_simrate(e); s++) ce_sim_step_pd(e, &e->u, &e->y);
   e->time += 1;
   e->phase += e->phase_add;
   if (e->phase > e->phaselen) {

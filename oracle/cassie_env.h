@@ -60,6 +60,7 @@ typedef struct {
   int stance_mode; /* 0 "zero" (reward "clock", cassie.py:219), 1 "grounded" (also installed by reset_for_test, cassie.py:701), 2 "aerial" */
   int reward_kind; /* 0 clock_reward, 1 early_clock_reward ("early" in the reward name, cassie.py:176, 773-774), 2 no_speed_clock_reward
                     * (phase command profile with "no_speed" in the name, cassie.py:193-194); cassie/rewards/clock_rewards.py:6, 119, 225 */
+  int simrate;     /* physics sub-steps per env step (CassieEnv(simrate=...), cassie.py:28,75); 0 = the default 50.  FREQ = 2000 // simrate */
   int cmd_profile; /* 0 command_profile "clock"; 1 "phase" (reset draws swing / stance / stance mode, cassie.py:540-545); 2 "phase" with
                     * phase_input_mode "library" (reward name contains "library", cassie.py:529-539, 188-191) */
 } ce_env_t;
@@ -100,6 +101,7 @@ double ce_clock_eval_mode(double swing, double stance, int stance_mode, int whic
 void ce_env_init(ce_env_t *e, uint32_t seed, uint32_t env_id, int dyn_rand);
 void ce_env_set_command_profile(ce_env_t *e, int cmd_profile); /* 0 clock, 1 phase, 2 phase (library) */
 int ce_env_obs_dim(const ce_env_t *e);
+void ce_env_set_simrate(ce_env_t *e, int simrate); /* 0 or 50: the default; e.g. 60 for the reference's shipped policies */
 /* reward_kind 0 / 1 / 2 (see ce_env_t) and the stance mode of the clock profile's reward ("grounded" 1 / "aerial" 2 in its name, cassie.py:211-219) */
 void ce_env_set_reward(ce_env_t *e, int reward_kind, int stance_mode);
 void ce_env_reset(ce_env_t *e, double *obs);

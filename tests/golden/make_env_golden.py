@@ -121,7 +121,7 @@ def parse_step(calls, dyn):
     it = iter(calls)
     if dyn:
         k, a, b, v = next(it)
-        assert k == "u" and a == 60 and b == 30
+        assert k == "u" and a - b == 30  # the unused simrate draw: uniform(simrate + 10, simrate - 20)
     hit, val = [0, 0, 0], [0.0, 0.0, 0.0]
     for j, n in enumerate((300, 100, 300)):
         k, a, b, v = next(it)

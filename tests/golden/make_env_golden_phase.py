@@ -109,6 +109,19 @@ def main():
             for k, v in r.items():
                 res[f"{tag}.{k}"] = v
             print(tag, "episode lengths", r["ep_len"], "reward range", r["reward"].min(), r["reward"].max(), "stance mode", env.stance_mode)
+        # simrate 60 (what both shipped policies of the reference were trained with; FREQ = 2000 // 60 = 33) under the reward name of
+        # their experiment.info, "5k_speed_reward" — a name without special substrings, i.e. clock_reward with stance mode "zero"
+        G.parse_reset = ORIG_PARSE_RESET
+        for tag, dyn in (("simrate60_plain", False), ("simrate60_dynrand", True)):
+            np.random.seed(77 + dyn)
+            random.seed(5 + dyn)
+            rng = np.random.default_rng(61 + dyn)
+            env = CassieEnv(simrate=60, command_profile="clock", input_profile="full", dynamics_randomization=dyn, reward="5k_speed_reward")
+            assert env.reward_func == "clock" and env.stance_mode == "zero" and env.simrate == 60
+            r = G.record(env, dyn, n_episodes=4, steps_per_episode=8, rng=rng, hit_boost=True)
+            for k, v in r.items():
+                res[f"{tag}.{k}"] = v
+            print(tag, "episode lengths", r["ep_len"], "reward range", r["reward"].min(), r["reward"].max(), "phase_hi", r["reset_scalar"][:, 3])
         np.savez_compressed(os.path.join(HERE, "env_episodes_phase.npz"), **res)
     finally:
         os.chdir(cwd)

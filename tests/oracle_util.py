@@ -13,16 +13,17 @@ def dp(a):
 class OracleBatch:
     """N oracle environments (oracle/cassie_env.c) stepped on the host."""
 
-    def __init__(self, n, seed, dyn_rand, threads=8, trajectory=None, command_profile=0, reward_kind=0, stance_mode=0):
+    def __init__(self, n, seed, dyn_rand, threads=8, trajectory=None, command_profile=0, reward_kind=0, stance_mode=0, simrate=50):
         self.L = P.lib()
         self.n, self.threads = n, threads
         size = self.L.ce_sizeof_env()
         self.buf = (C.c_char * (size * n))()
         self.L.ce_batch_init(self.buf, n, C.c_uint(seed), int(dyn_rand), threads)
-        if command_profile or reward_kind or stance_mode:  # profile 1 phase, 2 phase (library); reward 1 early, 2 no_speed
+        if command_profile or reward_kind or stance_mode or simrate != 50:  # profile 1 phase, 2 phase (library); reward 1 early, 2 no_speed
             for i in range(n):
                 self.L.ce_env_set_command_profile(C.c_void_p(C.addressof(self.buf) + i * size), int(command_profile))
                 self.L.ce_env_set_reward(C.c_void_p(C.addressof(self.buf) + i * size), int(reward_kind), int(stance_mode))
+                self.L.ce_env_set_simrate(C.c_void_p(C.addressof(self.buf) + i * size), int(simrate))
         if trajectory is not None:  # CassieTraj-v0
             self.table, tlen = trajectory
             self.L.ce_batch_set_trajectory(self.buf, n, dp(self.table), self.table.shape[0], int(tlen))
@@ -58,12 +59,13 @@ class StepDraws(C.Structure):  # ce_step_draws_t
 class OracleEnv:
     """One oracle environment driven with injected draws (replay of episodes recorded from the reference's CassieEnv)."""
 
-    def __init__(self, dyn_rand, trajectory=None, command_profile=0, reward_kind=0, stance_mode=0):
+    def __init__(self, dyn_rand, trajectory=None, command_profile=0, reward_kind=0, stance_mode=0, simrate=50):
         self.L = P.lib()
         self.buf = (C.c_char * self.L.ce_sizeof_env())()
         self.L.ce_env_init(self.buf, C.c_uint(0), C.c_uint(0), int(dyn_rand))
         self.L.ce_env_set_command_profile(self.buf, int(command_profile))  # 0 clock, 1 phase, 2 phase (library)
         self.L.ce_env_set_reward(self.buf, int(reward_kind), int(stance_mode))  # 0 clock, 1 early, 2 no_speed; 0 zero, 1 grounded, 2 aerial
+        self.L.ce_env_set_simrate(self.buf, int(simrate))
         if trajectory is not None:  # CassieTraj-v0: (decimated table [rows, 67], rows of the full trajectory)
             self.table, tlen = trajectory
             self.L.ce_env_set_trajectory(self.buf, dp(self.table), self.table.shape[0], int(tlen))

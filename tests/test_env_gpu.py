@@ -8,11 +8,12 @@ from tests.oracle_util import OracleBatch
 pytestmark = pytest.mark.gpu
 
 
-def _run(dtype, dyn, n=16, steps=12, seed=11, command_profile="clock", reward="clock", max_traj_len=400):
+def _run(dtype, dyn, n=16, steps=12, seed=11, command_profile="clock", reward="clock", max_traj_len=400, simrate=50):
     from apex_b200.envs import BatchedCassieEnv
     env = BatchedCassieEnv(n, dtype=dtype, seed=seed, dynamics_randomization=dyn, command_profile=command_profile, reward=reward,
-                           max_traj_len=max_traj_len)
-    ora = OracleBatch(n, seed, dyn, command_profile=env._cmd_profile, reward_kind=env._reward_kind, stance_mode=env._stance0)
+                           max_traj_len=max_traj_len, simrate=simrate)
+    ora = OracleBatch(n, seed, dyn, command_profile=env._cmd_profile, reward_kind=env._reward_kind, stance_mode=env._stance0,
+                      simrate=simrate)
     o_g = env.reset().cpu().numpy().astype(np.float64)
     o_c = ora.reset().copy()
     rng = np.random.default_rng(3)
@@ -74,6 +75,17 @@ def test_reward_name_variants_f64_match_oracle(profile, reward):
     out, env = _run(torch.float64, dyn=True, n=32, steps=12, seed=29, command_profile=profile, reward=reward, max_traj_len=7)
     assert out["reset"] < 1e-10 and out["done_mismatch"] == 0
     assert np.max(out["obs"]) < 1e-8 and np.max(out["rew"]) < 1e-8, (np.max(out["obs"]), np.max(out["rew"]))
+
+
+@pytest.mark.parametrize("simrate", [60, 40])
+def test_simrate_f64_matches_oracle(simrate):
+    """CassieEnv(simrate=60) — the setting of both policies shipped with the reference — and 40: sub-steps per env step, clock
+    frequency 2000 // simrate, averages; float64 kernel vs the oracle (pinned to the reference's Python at simrate 60 by
+    tests/test_oracle_cpu.py::test_simrate_60_matches_the_reference_python), with in-kernel resets and partially idle CTAs."""
+    out, env = _run(torch.float64, dyn=True, n=40, steps=12, seed=31, reward="5k_speed_reward", max_traj_len=5, simrate=simrate)
+    assert out["reset"] < 1e-10 and out["done_mismatch"] == 0
+    assert np.max(out["obs"]) < 1e-8 and np.max(out["rew"]) < 1e-8, (np.max(out["obs"]), np.max(out["rew"]))
+    assert int(env.field("sim_steps")[:, 0].max()) <= 5 * simrate + 1
 
 
 def test_phase_command_profile_trains():

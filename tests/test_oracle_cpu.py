@@ -383,6 +383,30 @@ def test_env_layer_matches_the_reference_python(tag, dyn, traj):
     assert t == len(f("reward")) and f("done").sum() >= 1  # at least one episode ends by falling
 
 
+@pytest.mark.parametrize("tag,dyn", [("simrate60_plain", False), ("simrate60_dynrand", True)])
+def test_simrate_60_matches_the_reference_python(tag, dyn):
+    """CassieEnv(simrate=60) — what both policies shipped with the reference were trained at (trained_models/*/experiment.info) —
+    under their reward name "5k_speed_reward" (no special substring: clock_reward, stance mode "zero"): 60 sub-steps per env step,
+    FREQ = 2000 // 60 = 33 in the clock period and knots, averages over 60 sub-steps."""
+    from tests.oracle_util import OracleEnv
+    g = np.load(os.path.join(G, "env_episodes_phase.npz"))
+    f = lambda k: g[f"{tag}.{k}"]
+    env = OracleEnv(dyn, simrate=60)
+    t = 0
+    for ep, n in enumerate(f("ep_len")):
+        obs = env.reset_with(f("reset_scalar")[ep], f("reset_damping")[ep], f("reset_mass")[ep], f("reset_friction")[ep],
+                             f("reset_tilt")[ep], f("reset_menc")[ep], f("reset_jenc")[ep])
+        assert np.abs(obs - f("reset_obs")[ep]).max() < 1e-10
+        for k in range(n):
+            obs, rew, done = env.step_with(f("action")[t], f("step_hit")[t], f("step_val")[t])
+            qpos, qvel = env.qpos_qvel()
+            assert np.abs(qpos - f("qpos")[t]).max() < 1e-10 and np.abs(qvel - f("qvel")[t]).max() < 1e-8, (ep, k)
+            assert done == f("done")[t] and abs(rew - f("reward")[t]) < 1e-10, (ep, k, rew, f("reward")[t])
+            assert np.abs(obs - f("obs")[t]).max() < 1e-9
+            t += 1
+    assert t == len(f("reward"))
+
+
 @pytest.mark.parametrize("tag,profile,kind,stance", [("phase_nospeed", 1, 2, 0), ("phase_early", 1, 1, 0), ("clock_aerial_early", 0, 1, 2),
                                                       ("clock_grounded", 0, 0, 1)])
 def test_reward_name_variants_match_the_reference_python(tag, profile, kind, stance):
