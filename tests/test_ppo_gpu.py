@@ -318,3 +318,30 @@ def test_ppo_iteration_with_bf16_tensor_core_forward():
         res[prec] = (float(buf.rew.mean()), float(buf.val.abs().mean()), scal)
     assert abs(res["bf16"][0] - res["f32"][0]) < 0.05 * abs(res["f32"][0]) + 1e-3  # same rollout up to bf16 action noise
 
+
+
+def test_rollout_graph_replay_equals_eager_launches():
+    """PPO.sample_parallel captures the rollout as a CUDA graph on its second call and replays it afterwards (seed and anneal factor
+    come from device memory): with the policy held fixed, three consecutive rollouts must be bit-identical to the ones a second
+    instance produces by launching the same kernels one by one — observations, actions, log-probabilities, rewards, done flags,
+    values and returns, including the in-kernel episode resets and a changing anneal factor."""
+    from apex_b200.envs import BatchedCassieEnv
+    from apex_b200.policies import Gaussian_FF_Actor, FF_V
+    from apex_b200.ppo import PPO
+    out = {}
+    for graph in (False, True):
+        torch.manual_seed(0)
+        actor, critic = Gaussian_FF_Actor(50, 10, fixed_std=torch.ones(10) * float(np.exp(-1.5))), FF_V(50)
+        algo = PPO(dict(num_steps=256 * 24, minibatch_size=1024, epochs=1, seed=3, graph_rollout=graph, max_traj_len=10))
+        env_fn = lambda: BatchedCassieEnv(256, device="cuda:0", seed=5)
+        snaps = []
+        for it, anneal in enumerate((1.0, 1.0, 0.7)):
+            buf = algo.sample_parallel(env_fn, actor, critic, 256 * 24, 10, anneal=anneal)
+            torch.cuda.synchronize()
+            snaps.append([t.clone() for t in (buf.obs, buf.act, buf.logp, buf.rew, buf.done, buf.val, buf.ret, buf.term_val)])
+        out[graph] = snaps
+        assert (len(algo._roll_graphs) == 1) == graph
+    for a, b in zip(out[False], out[True]):
+        for x, y in zip(a, b):
+            assert torch.equal(x, y)
+    assert not torch.equal(out[True][0][1], out[True][1][1])  # a new seed every rollout
