@@ -37,26 +37,7 @@ class BatchedCassieEnv:
                  **kwargs):
         if not 1 <= int(simrate) <= 127 or command_profile not in ("clock", "phase") or input_profile != "full" or history != 0:
             raise NotImplementedError("kernel covers simrate 1..127, clock / phase command, full input, history=0")
-        # The reward NAME configures the clock reward the way cassie.py:176-232 parses it:
-        #   command_profile "phase": "library" in the name -> library phase inputs, "no_speed" -> no_speed_clock_reward, "early" ->
-        #     early_clock_reward; the stance mode is drawn on every reset;
-        #   command_profile "clock": "grounded" / "aerial" in the name -> that stance mode (else "zero"), "early" -> early_clock_reward
-        #     ("switch" names behave like "clock" in the reference: set_up_clock_reward renames them, so reset's `== "switch_clock"`
-        #     branch, cassie.py:549-554, never runs).
-        # "max_vel" (max_vel_clock_reward) and "load" (pickled clocks) are not on the kernel path.
-        # Any other name — e.g. "5k_speed_reward" in the experiment.info of the reference's shipped policies — is the plain clock reward.
-        reward = reward or "clock"
-        if "max_vel" in reward or "load" in reward or "no_incentive" in reward:
-            raise NotImplementedError("max_vel_clock_reward / loaded clocks / no_incentive clocks are not on the kernel path")
-        self._reward_kind = 1 if "early" in reward else 0
-        self._stance0 = 0
-        if command_profile == "phase":
-            self._cmd_profile = 2 if "library" in reward else 1
-            if "no_speed" in reward:  # reward_func "no_speed_clock" is dispatched before the early flag is looked at (cassie.py:771-780)
-                self._reward_kind = 2
-        else:
-            self._cmd_profile = 0
-            self._stance0 = 1 if "grounded" in reward else (2 if "aerial" in reward else 0)
+        self._cmd_profile, self._reward_kind, self._stance0 = parse_reward_name(command_profile, reward)
         reward = "clock"
         self.L = _lib.lib()
         self.device = torch.device(device)
@@ -207,6 +188,30 @@ class BatchedCassieEnv:
         for name, val in (("speed", speed), ("side_speed", side_speed), ("phase", phase)):
             if val is not None:
                 self.field(name)[:, 0] = torch.as_tensor(val, dtype=self.dtype, device=self.device)
+
+
+def parse_reward_name(command_profile, reward):
+    """(command profile code, reward kind, initial stance mode) from the reward NAME, the way cassie.py:176-232 parses it:
+      command_profile "phase": "library" in the name -> library phase inputs (code 2, else 1), "no_speed" -> no_speed_clock_reward
+        (kind 2; reward_func "no_speed_clock" is dispatched before the early flag is looked at, cassie.py:771-780), "early" ->
+        early_clock_reward (kind 1); the stance mode is drawn on every reset;
+      command_profile "clock" (code 0): "grounded" / "aerial" in the name -> stance mode 1 / 2 (else "zero", 0), "early" -> kind 1.
+        "switch" names behave like "clock" in the reference: set_up_clock_reward renames them, so reset's `== "switch_clock"`
+        branch (cassie.py:549-554) never runs.
+    Any other name — e.g. "5k_speed_reward" in the experiment.info of the reference's shipped policies — is the plain clock reward.
+    "max_vel" (max_vel_clock_reward), "load" (pickled clocks) and "no_incentive" clocks are not on the kernel path."""
+    reward = reward or "clock"
+    if "max_vel" in reward or "load" in reward or "no_incentive" in reward:
+        raise NotImplementedError("max_vel_clock_reward / loaded clocks / no_incentive clocks are not on the kernel path")
+    kind, stance0 = (1 if "early" in reward else 0), 0
+    if command_profile == "phase":
+        profile = 2 if "library" in reward else 1
+        if "no_speed" in reward:
+            kind = 2
+    else:
+        profile = 0
+        stance0 = 1 if "grounded" in reward else (2 if "aerial" in reward else 0)
+    return profile, kind, stance0
 
 
 def clock_from_speed(new_speed, new_side_speed, phase, old_phaselen, freq=40):

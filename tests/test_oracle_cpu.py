@@ -1096,3 +1096,21 @@ def test_recorded_trajectory_alignment_sweep(L):
         assert r["pelvis_lin"] > 3 * base["pelvis_lin"], (dz, r, base)
     shank_p, shank_r = pred[:, 12] + pred[:, 13], rec[:, 12] + rec[:, 13]
     assert np.corrcoef(shank_p, shank_r)[0, 1] > 0.9
+
+
+def test_reward_name_parsing_matches_the_reference_env():
+    """apex_b200.envs.parse_reward_name against what the reference's CassieEnv constructor derives from the same names (recorded by
+    tests/golden/make_env_golden_phase.py: reward_func, early flag, stance mode, phase input mode) and the remaining documented cases."""
+    from apex_b200.envs import parse_reward_name
+    g = np.load(os.path.join(G, "env_episodes_phase.npz"))
+    assert parse_reward_name("clock", "clock") == (0, 0, 0) and parse_reward_name("clock", None) == (0, 0, 0)
+    assert parse_reward_name("clock", "5k_speed_reward") == (0, 0, 0)          # the shipped policies' experiment.info
+    assert parse_reward_name("clock", "switch_clock") == (0, 0, 0)             # renamed to "clock" before reset could act on it
+    assert parse_reward_name("clock", "grounded_clock") == (0, 0, int(g["clock_grounded.stance_mode"]))
+    assert parse_reward_name("clock", "early_aerial_clock") == (0, 1, int(g["clock_aerial_early.stance_mode"]))
+    assert parse_reward_name("phase", "clock") == (1, 0, 0) and parse_reward_name("phase", "library_clock") == (2, 0, 0)
+    assert parse_reward_name("phase", "no_speed_clock") == (1, 2, 0) and parse_reward_name("phase", "early_clock") == (1, 1, 0)
+    assert parse_reward_name("phase", "early_no_speed_clock") == (1, 2, 0)     # reward_func "no_speed_clock" wins (cassie.py:771-780)
+    for bad in ("max_vel_clock", "load_clock_x", "no_incentive_clock"):
+        with pytest.raises(NotImplementedError):
+            parse_reward_name("clock", bad)
